@@ -1,0 +1,247 @@
+"""Generates tests/golden/*.npz|json from the REFERENCE ITSELF (authoring container only).
+
+Run:  python tests/golden/make_golden.py
+Needs /root/reference (read-only) + cv2; never runs on the GPU box.  Every fixture records the
+reference file:line whose output it holds.  Weights come from the reference module's own default
+init under a fixed torch seed; small models store their full state_dict, torchvision-backbone
+models store the trainable tail + a checksum of the (seed-reproducible) backbone tensors.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import refload  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+torch.set_num_threads(4)
+
+
+def npd(d):
+    return {k: v.detach().cpu().numpy() for k, v in d.items()}
+
+
+def save(name, **arrs):
+    np.savez_compressed(os.path.join(OUT, name), **arrs)
+    print("wrote", name, sum(a.nbytes for a in arrs.values() if hasattr(a, "nbytes")) // 1024, "KiB raw")
+
+
+def checksum(sd, prefix):
+    tot = 0.0
+    for k in sorted(sd):
+        if k.startswith(prefix) and sd[k].dtype.is_floating_point:
+            tot += float(sd[k].double().abs().sum())
+    return tot
+
+
+def run_step(model, x, y, loss_kind="ce"):
+    model.train()
+    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+    out = model(x)
+    if loss_kind == "ce":
+        loss = torch.nn.functional.cross_entropy(out, y)
+    else:
+        loss = torch.nn.functional.binary_cross_entropy_with_logits(out, y, reduction="mean")
+    loss.backward()
+    grads = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+    sd1 = {k: v.clone() for k, v in model.state_dict().items()}
+    return sd0, out.detach(), loss.detach(), grads, sd1
+
+
+def gold_sampling():
+    us, df = refload.sampling_functions()
+    table = {}
+    for n, T in [(100, 40), (80, 40), (79, 40), (45, 40), (399, 20), (21, 20), (20, 20), (30, 40),
+                 (7, 20), (1, 16), (125, 60), (300, 60), (61, 60), (59, 60), (1000, 30), (16, 16),
+                 (33, 16), (47, 16), (2, 3)]:
+        fr = list(range(n))
+        r = us(fr, T)
+        if len(r) < T:
+            r = df(r, T)
+        table[f"{n},{T}"] = r
+    # known-answer rows of SURVEY.md section 8(a.1) for variants that live inside loader functions
+    crime = {"30,40": list(range(30)) + [-1] * 10,          # lrcn/lrcn.py:151-155 zero-frame padding
+             "80,40": list(range(0, 80, 2)), "100,40": list(range(0, 100, 2))[:40]}
+    seek = {"125,60": [i * 2 for i in range(60)], "300,60": [i * 5 for i in range(60)],
+            "59,60": None}                                    # backup_ucf50.py:52-62
+    json.dump({"source": "medsos_lrcn/src/loader_data.py:35-51 run on list(range(n))",
+               "medsos": table, "crime": crime, "seek": seek},
+              open(os.path.join(OUT, "sampling.json"), "w"), indent=0)
+    print("wrote sampling.json")
+
+
+def gold_resize():
+    import cv2
+    rng = np.random.default_rng(7)
+    arrs = {}
+    cases = [(48, 64, 32, 32), (36, 64, 28, 28), (20, 30, 32, 48), (64, 64, 32, 32), (32, 32, 32, 32),
+             (45, 80, 16, 16), (9, 7, 24, 24)]
+    for i, (h, w, oh, ow) in enumerate(cases):
+        src = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        arrs[f"src{i}"] = src
+        arrs[f"dst{i}"] = cv2.resize(src, (ow, oh))      # loader_data.py:162 (default INTER_LINEAR)
+        arrs[f"rgb{i}"] = cv2.cvtColor(arrs[f"dst{i}"], cv2.COLOR_BGR2RGB)  # loader_data.py:163
+    arrs["cv2_version"] = np.array(cv2.__version__)
+    save("resize_cv2.npz", **arrs)
+
+
+def gold_smallcnn():
+    LRCN = refload.notebook_lrcn()
+    for tag, (C, T, H, S, B) in {"a": (5, 4, 8, 16, 3), "b": (50, 6, 32, 32, 4)}.items():
+        torch.manual_seed(100 + ord(tag))
+        m = LRCN(C, T, H, (3, S, S))
+        m.dropout.p = 0.0                                  # parity runs use p=0
+        with torch.no_grad():                               # non-trivial BN affine / running stats
+            for k in (1, 2, 3):
+                bn = getattr(m, f"bn{k}")
+                bn.weight.uniform_(0.5, 1.5)
+                bn.bias.uniform_(-0.3, 0.3)
+                bn.running_mean.uniform_(-1, 1)
+                bn.running_var.uniform_(0.5, 2.0)
+        g = torch.Generator().manual_seed(1234)
+        x = torch.randint(0, 256, (B, T, 3, S, S), generator=g).float()   # raw 0..255 (backup_ucf50.py:101)
+        if tag == "b":
+            x = x / 255.0
+        y = torch.randint(0, C, (B,), generator=g)
+        sd0, out, loss, grads, sd1 = run_step(m, x, y)
+        m.eval()
+        with torch.no_grad():
+            out_eval = m(x)
+        arrs = {"x": x.numpy(), "y": y.numpy(), "logits": out.numpy(), "loss": loss.numpy(),
+                "logits_eval_after": out_eval.numpy(),
+                "meta": np.array(json.dumps(dict(num_classes=C, T=T, hidden=H, size=S, B=B,
+                                                 source="nb:148-193 LRCN, dropout p=0")))}
+        for k, v in npd(sd0).items():
+            arrs["sd0/" + k] = v
+        for k, v in npd(grads).items():
+            arrs["grad/" + k] = v
+        for k, v in npd(sd1).items():
+            if "running" in k or "num_batches" in k:
+                arrs["sd1/" + k] = v
+        save(f"smallcnn_lrcn_{tag}.npz", **arrs)
+
+
+def gold_medsos():
+    for arch, S, B, T in [("resnet18", 32, 2, 3), ("resnet50", 64, 2, 2)]:
+        mm = refload.medsos_models(CONF_RNN_LAYER=3, CONF_RNN_OUT="all", CONF_CLASSIF_MODE="multiclass",
+                                   CONF_DROPOUT=0.0)
+        torch.manual_seed(7)
+        m = mm.LRCN(4, T, 32, 8, cnn_backbone=arch, rnn_type="lstm", rnn_out="all", bidirectional=False)
+        g = torch.Generator().manual_seed(1234)
+        x = torch.randint(0, 256, (B, T, 3, S, S), generator=g).float() / 255.0
+        y = torch.randint(0, 4, (B,), generator=g)
+        sd0, out, loss, grads, sd1 = run_step(m, x, y)
+        arrs = {"x": x.numpy(), "y": y.numpy(), "logits": out.numpy(), "loss": loss.numpy(),
+                "backbone_checksum": np.array(checksum(sd0, "cnn_backbone.")),
+                "meta": np.array(json.dumps(dict(arch=arch, size=S, B=B, T=T, hidden=32, rnn_input=8,
+                                                 rnn_layers=3, num_classes=4, seed=7,
+                                                 source="medsos_lrcn/src/models.py:121-234, dropout 0")))}
+        big = lambda k, v: arch == "resnet50" and v.size > 200000   # seed-reproducible; keep fixture small
+        arrs["tail_checksum"] = np.array(checksum({k: v for k, v in sd0.items() if not k.startswith("cnn_backbone.")}, ""))
+        for k, v in npd(sd0).items():
+            if not k.startswith("cnn_backbone.") and not big(k, v):
+                arrs["sd0/" + k] = v
+        for k, v in npd(grads).items():
+            if big(k, v):
+                arrs["gradsub16/" + k] = v[::16, ::16].copy()
+            else:
+                arrs["grad/" + k] = v
+        for k in ("cnn_backbone.bn1.running_mean", "cnn_backbone.bn1.running_var",
+                  "cnn_backbone.layer4.1.bn2.running_var", "cnn_backbone.layer2.0.downsample.1.running_mean"):
+            arrs["sd1/" + k] = sd1[k].numpy()
+        # pooled backbone features (pre-adapt) pin the CNN on its own
+        with torch.no_grad():
+            m2 = mm.LRCN(4, T, 32, 8, cnn_backbone=arch, rnn_type="lstm", rnn_out="all", bidirectional=False)
+            m2.load_state_dict(sd0)
+            m2.train()
+            feat = m2.cnn_backbone(x.view(B * T, 3, S, S))
+        arrs["features"] = feat.numpy()
+        save(f"medsos_lrcn_{arch}.npz", **arrs)
+
+
+def gold_simple():
+    # ucf50-lrcn.py topology: frozen backbone, 3 plain adapts, 2-layer biLSTM H=12, multiclass
+    C, g0 = refload.ucf50_lrcn(CONF_CNN_BACKBONE="resnet18", CONF_RNN_LAYER=2)
+    torch.manual_seed(11)
+    m = C(5, 3, 12, 16, cnn_backbone="resnet18")
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randint(0, 256, (2, 3, 3, 32, 32), generator=g).float() / 255.0
+    y = torch.randint(0, 5, (2,), generator=g)
+    sd0, out, loss, grads, sd1 = run_step(m, x, y)
+    arrs = {"x": x.numpy(), "y": y.numpy(), "logits": out.numpy(), "loss": loss.numpy(),
+            "backbone_checksum": np.array(checksum(sd0, "cnn_backbone.")),
+            "meta": np.array(json.dumps(dict(arch="resnet18", size=32, B=2, T=3, hidden=12, rnn_input=16,
+                                             rnn_layers=2, num_classes=5, seed=11,
+                                             source="lrcn/ucf50-lrcn.py:252-336")))}
+    for k, v in npd(sd0).items():
+        if not k.startswith("cnn_backbone."):
+            arrs["sd0/" + k] = v
+    for k, v in npd(grads).items():
+        arrs["grad/" + k] = v
+    save("ucf50_lrcn_resnet18.npz", **arrs)
+
+    # crime lrcn.py topology: frozen backbone (CONF_FINETUNE False), one adapt, per-class binary heads
+    C, g0 = refload.crime_lrcn(CONF_CNN_BACKBONE="resnet18", CONF_RNN_LAYER=2,
+                               CONF_CLASSIF_MODE="multiple_binary", CONF_FINETUNE=False)
+    torch.manual_seed(13)
+    m = C(3, 3, 12, 16, cnn_backbone="resnet18")
+    yb = torch.tensor([[1., 0., 0.], [0., 0., 1.]])
+    sd0, out, loss, grads, sd1 = run_step(m, x, yb, loss_kind="bce")
+    arrs = {"x": x.numpy(), "y": yb.numpy(), "logits": out.numpy(), "loss": loss.numpy(),
+            "backbone_checksum": np.array(checksum(sd0, "cnn_backbone.")),
+            "meta": np.array(json.dumps(dict(arch="resnet18", size=32, B=2, T=3, hidden=12, rnn_input=16,
+                                             rnn_layers=2, num_classes=3, seed=13,
+                                             source="lrcn/lrcn.py:181-305 multiple_binary; loss=mean BCEWithLogits")))}
+    for k, v in npd(sd0).items():
+        if not k.startswith("cnn_backbone."):
+            arrs["sd0/" + k] = v
+    for k, v in npd(grads).items():
+        arrs["grad/" + k] = v
+    save("crime_lrcn_resnet18.npz", **arrs)
+
+
+def gold_lstm():
+    # nn.LSTM exactly as the reference configures it (lrcn.py:236: 4-layer biLSTM H=56 -> here 2x2, H=7)
+    torch.manual_seed(5)
+    for tag, (inp, H, layers, bidir, B, T) in {"uni": (10, 6, 2, False, 3, 5), "bi": (9, 7, 2, True, 2, 4)}.items():
+        rnn = torch.nn.LSTM(inp, H, num_layers=layers, bidirectional=bidir, batch_first=True)
+        x = torch.randn(B, T, inp, requires_grad=True)
+        out, _ = rnn(x)
+        w = torch.randn_like(out)
+        (out * w).sum().backward()
+        arrs = {"x": x.detach().numpy(), "out": out.detach().numpy(), "w": w.numpy(), "dx": x.grad.numpy(),
+                "meta": np.array(json.dumps(dict(inp=inp, H=H, layers=layers, bidir=bidir)))}
+        for k, p in rnn.named_parameters():
+            arrs["p/" + k] = p.detach().numpy()
+            arrs["g/" + k] = p.grad.numpy()
+        save(f"lstm_{tag}.npz", **arrs)
+
+
+def gold_scan():
+    torch.manual_seed(3)
+    Bz, L, D, N = 2, 300, 12, 4
+    u = torch.randn(Bz, L, D)
+    delta = torch.nn.functional.softplus(torch.randn(Bz, L, D))
+    A = -torch.exp(torch.randn(D, N))
+    Bm = torch.randn(Bz, L, N)
+    Cm = torch.randn(Bz, L, N)
+    y_vm = refload.videomamba_scan()(u, delta, A, Bm, Cm)        # lrcn/videomamba.py:242-284 (reset @256)
+    y_f = refload.medsos_scan("forward")(u, delta, A, Bm, Cm)    # medsos models.py:47-71
+    y_b = refload.medsos_scan("backward")(u, delta, A, Bm, Cm)
+    save("scan.npz", u=u.numpy(), delta=delta.numpy(), A=A.numpy(), B=Bm.numpy(), C=Cm.numpy(),
+         y_videomamba=y_vm.numpy(), y_medsos_fwd=y_f.numpy(), y_medsos_bwd=y_b.numpy())
+
+
+if __name__ == "__main__":
+    assert refload.available(), "needs /root/reference"
+    gold_sampling()
+    gold_resize()
+    gold_smallcnn()
+    gold_lstm()
+    gold_medsos()
+    gold_simple()
+    gold_scan()
