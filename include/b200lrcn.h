@@ -1,0 +1,141 @@
+/* b200lrcn.h -- C ABI of libb200lrcn.so: hand-written sm_100a kernels for the LRCN hot path.
+ *
+ * The reference (AhmadRifqi86/video-classif) is pure Python/PyTorch and has no FFI of its own;
+ * its seam for this path is `nn.Module.forward(clips[B,T,C,H,W]) -> logits` plus autograd
+ * (medsos_lrcn/src/models.py:188-234, lrcn/ucf50-lrcn.py:304-336, lrcn/lrcn.py:285-305,
+ * lrcn/rgb_lrcn.py:247-263, notebook LRCN nb:174-193).  Every torch call site on that path
+ *  maps to one entry point below; the Python host side
+ * (video-classif_b200/*.py) binds them with ctypes and wraps them in torch.autograd.Functions.
+ *
+ * Conventions
+ *   - plain pointers are DEVICE pointers unless stated otherwise; no torch types, no ownership
+ *     transfer, no allocation inside the library; `stream` is a cudaStream_t passed as void*.
+ *   - return value: 0 ok, < 0 argument / environment error, > 0 a cudaError_t.  The message of
+ *     the last failure on the calling thread is b2_last_error().
+ *   - there is NO CPU or other-GPU fallback: b2_device_check() fails unless the device is sm_100.
+ *   - "ACCUMULATED" outputs are added into and must be zeroed by the caller.
+ *   - bf16 = 16-bit bfloat, "NHWC" tensors are [N][H][W][C] contiguous, "NCHW" [N][C][H][W].
+ */
+#ifndef B200LRCN_H_
+#define B200LRCN_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library status ------------------------------------------------------------------ */
+int b2_abi_version(void);
+const char* b2_last_error(void);
+long b2_launch_count(void);      /* kernels launched by this library since load (all streams) */
+int b2_device_check(void);
+
+/* ---- K1 frame ingest -------------------------------------------------------------------
+ * Replaces cv2.resize(INTER_LINEAR) + cv2.cvtColor(BGR2RGB) + `/255.0` + float32 + permute
+ * (medsos_lrcn/src/loader_data.py:162-163,182,201,112; crime path lrcn/lrcn.py:136-142) and the
+ * frame gather of uniform_sampling/duplicate_frames (loader_data.py:35-51).
+ * src: uint8 [n_src_frames][src_h][src_w][3] (frame stride in bytes); frame_index: n_out source
+ * frame numbers (device int32, NULL = identity, -1 = all-zero frame, lrcn/lrcn.py:155);
+ * dst: [n_out][3][dst_h][dst_w] fp32 or bf16.  The uint8 resize result is bit-identical to cv2. */
+int b2_ingest_u8(const void* src, int n_src_frames, int src_h, int src_w, long src_frame_stride,
+                 const int* frame_index, int n_out, void* dst, int dst_h, int dst_w, int out_bf16,
+                 int swap_rb, float divisor, void* stream);
+
+/* ---- K2 tensor-core GEMM / implicit-GEMM convolution (tcgen05 + TMEM + TMA) -------------
+ * b2_gemm_bf16_tn: D[M,N] = A[M,K] B[N,K]^T (+bias[N]) (ReLU); A,B bf16 row-major (lda/ldb in
+ * elements, multiples of 8), D bf16 or fp32 (ldd elements).  Replaces nn.Linear / the hoisted
+ * nn.LSTM input GEMM / 1x1 convolutions (models.py:200-202,213,221-226).
+ * col_sum/col_sumsq (fp32 [N], ACCUMULATED, may be NULL): per-column sum and sum of squares of
+ * the stored output -- the batch statistics of the BatchNorm that follows a convolution.
+ * b2_conv2d_nhwc_bf16: y[N,P,Q,Cout] = conv(x[N,H,W,C], w[Cout][R][S][C]); C % 64 == 0; zero
+ * padding `pad`, stride `stride`; replaces torchvision ResNet Conv2d layers (models.py:192). */
+int b2_gemm_bf16_tn(const void* A, long lda, const void* B, long ldb, void* D, long ldd, int M, int N,
+                    int K, const float* bias, const float* bias2, int out_bf16, int relu, float* col_sum,
+                    float* col_sumsq, void* stream);
+int b2_conv2d_nhwc_bf16(const void* x, int N, int H, int W, int C, const void* w, int Cout, int R, int S,
+                        int stride, int pad, void* y, const float* bias, int out_bf16, int relu,
+                        float* col_sum, float* col_sumsq, void* stream);
+
+/* ---- backbone glue (NHWC bf16) ----------------------------------------------------------
+ * b2_stem_im2col: NCHW fp32/bf16 frames -> [N*P*Q][Kp] bf16 patches of the 7x7/2 pad-3 stem conv,
+ * column k = (r*7+s)*3+c, zero padded to Kp.
+ * b2_bn_apply_nhwc: y = act( BN(x) [+ res | + BN2(res)] ), BatchNorm2d semantics of torch
+ * (train: batch statistics from sum/sumsq over `count` elements, running stats updated with
+ * momentum and unbiased variance; eval: running stats) -- models.py:192 under train_eval.py:12.
+ * res_mode 0 none, 1 identity shortcut (already activated), 2 down-sample branch (raw + own BN).
+ * b2_bn_relu_maxpool_nhwc: stem BN + ReLU + MaxPool2d(3,2,1).  b2_avgpool_nhwc: AdaptiveAvgPool2d(1). */
+int b2_stem_im2col(const void* x, int in_bf16, void* A, int N, int H, int W, int Kp, void* stream);
+int b2_bn_apply_nhwc(const void* x, void* y, long rows, int C, const float* sum, const float* sumsq,
+                     const float* gamma, const float* beta, float* running_mean, float* running_var,
+                     int res_mode, const void* res, const float* rsum, const float* rsumsq,
+                     const float* rgamma, const float* rbeta, float* rrunning_mean, float* rrunning_var,
+                     long count, float eps, float momentum, int train, int relu, void* stream);
+int b2_bn_relu_maxpool_nhwc(const void* x, void* y, int N, int H, int W, int C, const float* sum,
+                            const float* sumsq, const float* gamma, const float* beta, float* running_mean,
+                            float* running_var, float eps, float momentum, int train, void* stream);
+int b2_avgpool_nhwc(const void* x, float* out_f32, void* out_bf16, int N, int HW, int C, void* stream);
+
+/* ---- trainable tail ---------------------------------------------------------------------
+ * b2_act_ln_fwd/bwd: out = LayerNorm(act(pre)) with act = exact-erf GELU (apply_gelu=1) or
+ * identity -- `self.bnK(F.gelu(self.adaptK(x)))` models.py:200-202, `self.bn0(rnn_out)` :222.
+ * b2_sgemm: C = alpha op(A) op(B) + beta C, fp32 row-major (fp32 parity path, tiny-N layers,
+ * weight/input gradients).  b2_colsum_f32: bias gradients.  casts feed the bf16 GEMM. */
+int b2_act_ln_fwd(const float* pre, const float* gamma, const float* beta, float* out_f32, void* out_bf16,
+                  float* mean, float* rstd, long M, int N, float eps, int apply_gelu, void* stream);
+int b2_act_ln_bwd(const float* dout, const float* pre, const float* gamma, const float* mean,
+                  const float* rstd, float* dpre, float* dgamma /*ACCUMULATED*/, float* dbeta /*ACCUMULATED*/,
+                  long M, int N, int apply_gelu, void* stream);
+int b2_sgemm(int trans_a, int trans_b, int M, int N, int K, float alpha, const float* A, long lda,
+             const float* B, long ldb, float beta, float* C, long ldc, const float* bias, const float* bias2,
+             void* stream);
+int b2_colsum_f32(const float* X, long ld, long M, int N, float* out, int accumulate, void* stream);
+int b2_cast_f32_bf16(const float* src, void* dst, long n, void* stream);
+int b2_transpose_cast_f32_bf16(const float* src, long ld_src, void* dst, long ld_dst, long R, long C,
+                               void* stream);
+/* nn.Dropout(p) in train mode (nb:163, models.py:153,182): y = x*keep/(1-p) with a counter-hash
+ * mask; calling it again with the same seed on dy replays the mask for the backward pass. */
+int b2_dropout_f32(const float* x, float* y, long n, float p, unsigned long long seed, void* stream);
+
+/* ---- K3/K4 persistent LSTM --------------------------------------------------------------
+ * torch.nn.LSTM(batch_first=True) semantics (nb:169, models.py:156-158, lrcn.py:236): gate order
+ * i,f,g,o, zero initial state.  G[B][T][4H] = x W_ih^T + b_ih + b_hh is computed beforehand by the
+ * GEMM; out points at column dir*H of the [B][T][dirs*H] layer output (out_ld = dirs*H).
+ * gates/cstate ([B][T][4H] / [B][T][H], post-activation) are saved for BPTT (NULL at inference).
+ * b2_lstm_seq_bwd writes dG[B*T][4H] (row stride dG_ld) and ACCUMULATES dWhh[4H][H].
+ * bias/bias2 of b2_gemm_bf16_tn / b2_sgemm are added per output column (b_ih + b_hh). */
+int b2_lstm_seq_fwd(const float* G, const float* Whh, float* out, long out_ld, float* gates, float* cstate,
+                    int B, int T, int H, int reverse, void* stream);
+int b2_lstm_seq_bwd(const float* dout, long dout_ld, const float* out, long out_ld, const float* gates,
+                    const float* cstate, const float* Whh, float* dG, long dG_ld, float* dWhh, int B, int T,
+                    int H, int reverse, void* stream);
+
+/* ---- small TimeDistributed CNN, fp32 NCHW (nb:156-163,181-183; backup_ucf50.py:113-140) --
+ * b2_conv3x3_f32: Conv2d(k=3,padding=1) forward (transposed=0, w [Cout][Cin][3][3]) or data
+ * gradient (transposed=1: pass dy as x, Cin=Cout_fwd, Cout=Cin_fwd, same w).
+ * b2_conv3x3_wgrad_f32: ACCUMULATES dw.  b2_bn2d_*: train-mode BatchNorm2d statistics (double
+ * accumulators, ACCUMULATED), finalisation (scale/shift/mean/rstd + running-stat update), fused
+ * BN+ReLU(+MaxPool2d(2,2)) forward and its two-pass backward (s1 = dbeta, s2 = dgamma). */
+int b2_conv3x3_f32(const float* x, const float* w, const float* bias, float* y, int N, int Cin, int Cout,
+                   int H, int W, int transposed, void* stream);
+int b2_conv3x3_wgrad_f32(const float* x, const float* dy, float* dw, int N, int Cin, int Cout, int H, int W,
+                         void* stream);
+int b2_bn2d_stats_f32(const float* x, int N, int C, int HW, double* sum, double* sumsq, void* stream);
+int b2_bn2d_finalize(const double* sum, const double* sumsq, long count, const float* gamma,
+                     const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                     int train, float* scale, float* shift, float* mean, float* rstd, int C, void* stream);
+int b2_bn2d_act_pool_fwd_f32(const float* x, const float* scale, const float* shift, float* y, void* y_bf16,
+                             int N, int C, int H, int W, int pool, void* stream);
+int b2_bn2d_act_pool_bwd_reduce_f32(const float* x, const float* dy, const float* scale, const float* shift,
+                                    const float* mean, const float* rstd, int N, int C, int H, int W,
+                                    int pool, double* s1, double* s2, void* stream);
+int b2_bn2d_act_pool_bwd_apply_f32(const float* x, const float* dy, const float* scale, const float* shift,
+                                   const float* mean, const float* rstd, const float* gamma, const double* s1,
+                                   const double* s2, long count, int train, float* dx, int N, int C, int H,
+                                   int W, int pool, void* stream);
+int b2_f64_to_f32(const double* src, float* dst, int n, int accumulate, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200LRCN_H_ */

@@ -1,0 +1,221 @@
+"""GPU parity tests, kernel level: every b2_* kernel family through the C ABI vs the CPU oracle /
+the reference-generated golden vectors.  Bit-exact for byte/index work; stated tolerances for
+floating point (fp32 kernels 1e-4, bf16 tensor-core kernels 1e-2 of max|ref|)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import GOLDEN, err, golden_tensors, load_golden
+from oracle import lrcn_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import video_classif_b200 as vc
+    return vc.ops
+
+
+@pytest.mark.parametrize("M,N,K,bias,out_bf16,relu", [
+    (128, 32, 64, False, True, False), (300, 200, 136, True, True, True), (1000, 8, 512, True, False, False),
+    (160, 128, 16384, True, False, False), (1920, 224, 112, True, False, False), (4096, 50, 640, True, False, False),
+    (777, 1024, 2048, True, True, True), (5, 4, 8, True, False, False)])
+def test_gemm_tcgen05(ops, M, N, K, bias, out_bf16, relu):
+    torch.manual_seed(M + N + K)
+    A = torch.randn(M, K, device=DEV).bfloat16()
+    B = (torch.randn(N, K, device=DEV) / K ** 0.5).bfloat16()
+    b = torch.randn(N, device=DEV) if bias else None
+    s1, s2 = torch.zeros(N, device=DEV), torch.zeros(N, device=DEV)
+    D = ops.gemm_tn(A, B, bias=b, out_dtype=torch.bfloat16 if out_bf16 else torch.float32, relu=relu, stats=(s1, s2))
+    ref = A.float().cpu() @ B.float().cpu().t()          # bf16-rounded operands, fp32 CPU product
+    if bias:
+        ref = ref + b.cpu()
+    if relu:
+        ref = ref.relu()
+    assert err(D.float(), ref) < (6e-3 if out_bf16 else 2e-5)
+    r = ref.bfloat16().float() if out_bf16 else ref
+    assert err(s1, r.sum(0), floor=1e-3 * r.abs().sum(0).max().item()) < 2e-2
+    assert err(s2, (r * r).sum(0)) < 2e-2
+
+
+@pytest.mark.parametrize("N,H,W,C,Cout,R,stride,pad", [
+    (2, 8, 8, 64, 64, 1, 1, 0), (2, 8, 8, 64, 64, 3, 1, 1), (3, 14, 14, 128, 128, 3, 1, 1),
+    (3, 28, 28, 128, 128, 3, 2, 1), (3, 7, 7, 256, 512, 1, 2, 0), (5, 7, 7, 512, 512, 3, 2, 1),
+    (1, 5, 9, 64, 192, 3, 1, 1), (130, 4, 4, 64, 64, 3, 1, 1)])
+def test_conv_implicit_gemm_tma_im2col(ops, N, H, W, C, Cout, R, stride, pad):
+    torch.manual_seed(N * H + C)
+    x = torch.randn(N, C, H, W).bfloat16()
+    w = (torch.randn(Cout, C, R, R) / (C * R * R) ** 0.5).bfloat16()
+    s1, s2 = torch.zeros(Cout, device=DEV), torch.zeros(Cout, device=DEV)
+    y = ops.conv2d_nhwc(x.permute(0, 2, 3, 1).contiguous().to(DEV), w.permute(0, 2, 3, 1).contiguous().to(DEV), stride,
+                        pad, stats=(s1, s2))
+    ref = F.conv2d(x.float(), w.float(), stride=stride, padding=pad).permute(0, 2, 3, 1)
+    assert y.shape == ref.shape
+    assert err(y.float(), ref) < 6e-3
+    r = ref.bfloat16().float().reshape(-1, Cout)
+    assert err(s2, (r * r).sum(0)) < 2e-2
+
+
+def test_ingest_bit_exact_vs_cv2_golden(ops):
+    g = np.load(os.path.join(GOLDEN, "resize_cv2.npz"))
+    i = 0
+    while f"src{i}" in g.files:
+        src, rgb = g[f"src{i}"], g[f"rgb{i}"]
+        out = ops.ingest_u8(torch.from_numpy(src[None]).to(DEV), rgb.shape[0], rgb.shape[1], swap_rb=True, divisor=1.0)
+        got = out[0].permute(1, 2, 0).cpu().numpy()
+        assert np.array_equal(got, rgb.astype(np.float32)), f"case {i}"     # uint8 result identical to cv2
+        i += 1
+
+
+@pytest.mark.parametrize("h,w,oh,ow", [(360, 640, 112, 112), (37, 53, 112, 112), (128, 200, 64, 100), (224, 224, 112, 112),
+                                       (64, 64, 64, 64), (9, 7, 24, 24), (480, 854, 224, 224)])
+def test_ingest_vs_oracle(ops, h, w, oh, ow):
+    rng = np.random.default_rng(h * w)
+    clip = rng.integers(0, 256, (5, h, w, 3), dtype=np.uint8)
+    idx = [3, 0, -1, 4, 4, 1]
+    want = O.ingest_clip(clip[[max(i, 0) for i in idx]], oh, ow, swap_rb=True, divisor=255.0)
+    want[2] = 0.0
+    got = ops.ingest_u8(torch.from_numpy(clip).to(DEV), oh, ow, frame_index=torch.tensor(idx, dtype=torch.int32, device=DEV))
+    assert np.array_equal(got.cpu().numpy(), want)                              # fp32: bit-exact
+    got16 = ops.ingest_u8(torch.from_numpy(clip).to(DEV), oh, ow, out_dtype=torch.bfloat16, swap_rb=False, divisor=1.0)
+    want16 = torch.from_numpy(O.ingest_clip(clip, oh, ow, swap_rb=False, divisor=1.0)).bfloat16()
+    assert torch.equal(got16.cpu(), want16)
+
+
+@pytest.mark.parametrize("tag", ["uni", "bi"])
+@pytest.mark.parametrize("bf16", [False])
+def test_lstm_vs_reference_golden(ops, tag, bf16):
+    g, meta = load_golden(f"lstm_{tag}.npz")
+    rnn = torch.nn.LSTM(meta["inp"], meta["H"], num_layers=meta["layers"], bidirectional=meta["bidir"], batch_first=True)
+    rnn.load_state_dict(golden_tensors(g, "p/"))
+    rnn = rnn.to(DEV)
+    x = torch.from_numpy(g["x"]).to(DEV).requires_grad_(True)
+    out = ops.lstm_forward(x, rnn, bf16=bf16)
+    (out * torch.from_numpy(g["w"]).to(DEV)).sum().backward()
+    assert err(out, torch.from_numpy(g["out"])) < 1e-5
+    assert err(x.grad, torch.from_numpy(g["dx"])) < 1e-4
+    for k, v in golden_tensors(g, "g/").items():
+        assert err(getattr(rnn, k).grad, v) < 1e-4, k
+
+
+@pytest.mark.parametrize("B,T,In,H,layers,bidir", [(5, 7, 24, 32, 2, False), (3, 6, 40, 56, 2, True), (9, 30, 8, 32, 3, False)])
+def test_lstm_vs_oracle(ops, B, T, In, H, layers, bidir):
+    torch.manual_seed(B * T)
+    rnn = torch.nn.LSTM(In, H, num_layers=layers, bidirectional=bidir, batch_first=True)
+    x = torch.randn(B, T, In)
+    p = {"lstm." + k: v.detach().clone().requires_grad_(True) for k, v in rnn.named_parameters()}
+    xo = x.clone().requires_grad_(True)
+    ref = O.lstm_forward(xo, p, H, layers, bidir)
+    wgt = torch.randn_like(ref)
+    (ref * wgt).sum().backward()
+    rnn = rnn.to(DEV)
+    xg = x.to(DEV).requires_grad_(True)
+    out = ops.lstm_forward(xg, rnn)
+    (out * wgt.to(DEV)).sum().backward()
+    assert err(out, ref) < 1e-5
+    assert err(xg.grad, xo.grad) < 1e-4
+    for k, v in rnn.named_parameters():
+        assert err(v.grad, p["lstm." + k].grad) < 1e-4, k
+
+
+@pytest.mark.parametrize("M,N,gelu", [(37, 8, True), (64, 1024, True), (10, 960, False), (1920, 512, True)])
+def test_act_layernorm_fwd_bwd(ops, M, N, gelu):
+    torch.manual_seed(N)
+    pre = torch.randn(M, N) * 1.5
+    gam, bet = torch.rand(N) + 0.5, torch.randn(N) * 0.1
+    w = torch.randn(M, N)
+    po, go, bo = (t.clone().requires_grad_(True) for t in (pre, gam, bet))
+    ref = O.layernorm(O.gelu_exact(po) if gelu else po, go, bo)
+    (ref * w).sum().backward()
+    pg, gg, bg = (t.to(DEV).requires_grad_(True) for t in (pre, gam, bet))
+    out = ops.act_layernorm(pg, gg, bg, gelu, 1e-5)
+    (out * w.to(DEV)).sum().backward()
+    assert err(out, ref) < 1e-5
+    assert err(pg.grad, po.grad) < 1e-4
+    assert err(gg.grad, go.grad) < 1e-4 and err(bg.grad, bo.grad) < 1e-4
+
+
+@pytest.mark.parametrize("M,K,N,bf16", [(33, 70, 19, False), (160, 640, 50, False), (1920, 2048, 1024, True), (640, 512, 8, True)])
+def test_linear_fwd_bwd(ops, M, K, N, bf16):
+    torch.manual_seed(K)
+    x, w, b = torch.randn(M, K), torch.randn(N, K) / K ** 0.5, torch.randn(N)
+    g = torch.randn(M, N)
+    xo, wo, bo = (t.clone().requires_grad_(True) for t in (x, w, b))
+    ref = xo @ wo.t() + bo
+    (ref * g).sum().backward()
+    xg, wg, bg = (t.to(DEV).requires_grad_(True) for t in (x, w, b))
+    out = ops.linear(xg, wg, bg, bf16)
+    (out * g.to(DEV)).sum().backward()
+    tol = 1e-2 if bf16 else 1e-4            # bf16 operands / fp32 accumulate vs fp32
+    assert err(out, ref) < tol
+    assert err(xg.grad, xo.grad) < tol and err(wg.grad, wo.grad) < tol and err(bg.grad, bo.grad) < 1e-4
+
+
+@pytest.mark.parametrize("N,Cin,Cout,H,W,pool", [(3, 3, 16, 16, 16, False), (4, 16, 32, 32, 32, True), (2, 32, 64, 16, 16, True),
+                                                 (2, 5, 7, 10, 22, False)])
+def test_conv_bn_relu_pool_fwd_bwd(ops, N, Cin, Cout, H, W, pool):
+    torch.manual_seed(Cin * Cout)
+    conv = torch.nn.Conv2d(Cin, Cout, 3, padding=1)
+    bn = torch.nn.BatchNorm2d(Cout)
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.uniform_(-0.3, 0.3)
+        bn.running_mean.uniform_(-1, 1)
+        bn.running_var.uniform_(0.5, 2)
+    x = torch.randn(N, Cin, H, W) * 2
+    xo = x.clone().requires_grad_(True)
+    cw, cb, gam, bet = (t.detach().clone().requires_grad_(True) for t in (conv.weight, conv.bias, bn.weight, bn.bias))
+    z = F.conv2d(xo, cw, cb, padding=1)
+    yb, rm, rv = O.batchnorm2d_train(z, gam, bet, bn.running_mean.clone(), bn.running_var.clone())
+    ref = torch.relu(yb)
+    if pool:
+        ref = F.max_pool2d(ref, 2, 2)
+    wgt = torch.randn_like(ref)
+    (ref * wgt).sum().backward()
+    conv, bn = conv.to(DEV), bn.to(DEV)
+    xg = x.to(DEV).requires_grad_(True)
+    out = ops.conv_bn_relu_pool(xg, conv, bn, pool, True)
+    (out * wgt.to(DEV)).sum().backward()
+    assert err(out, ref) < 1e-5
+    assert err(bn.running_mean, rm) < 1e-5 and err(bn.running_var, rv) < 1e-5
+    assert int(bn.num_batches_tracked) == 1
+    gmax = max(v.grad.abs().max().item() for v in (cw, gam, bet))
+    assert err(xg.grad, xo.grad) < 1e-4
+    assert err(conv.weight.grad, cw.grad) < 1e-4
+    assert conv.bias.grad.abs().max().item() < 1e-4 * gmax                # analytically zero under train-mode BN
+    assert err(bn.weight.grad, gam.grad) < 1e-4 and err(bn.bias.grad, bet.grad) < 1e-4
+    # eval mode uses the running statistics
+    out_e = ops.conv_bn_relu_pool(x.to(DEV), conv, bn, pool, False)
+    ze = F.conv2d(x, conv.weight.cpu(), conv.bias.cpu(), padding=1)
+    ref_e = torch.relu(O.batchnorm2d_eval(ze, bn.weight.cpu(), bn.bias.cpu(), bn.running_mean.cpu(), bn.running_var.cpu()))
+    if pool:
+        ref_e = F.max_pool2d(ref_e, 2, 2)
+    assert err(out_e, ref_e.detach()) < 1e-5
+
+
+def test_dropout_rate_scale_and_backward_mask(ops):
+    x = torch.ones(1 << 20, device=DEV, requires_grad=True)
+    for p in (0.25, 0.5):
+        y = ops.dropout(x, p, True)
+        kept = (y != 0).float().mean().item()
+        assert abs(kept - (1 - p)) < 5e-3                                      # Bernoulli keep rate
+        assert torch.allclose(y[y != 0], torch.tensor(1 / (1 - p), device=DEV))
+        (gx,) = torch.autograd.grad(y.sum(), x)
+        assert torch.equal(gx != 0, y != 0)                                    # same mask replayed
+    assert ops.dropout(x, 0.5, False) is x and ops.dropout(x, 0.0, True) is x
+    y1, y2 = ops.dropout(x, 0.5, True), ops.dropout(x, 0.5, True)
+    assert not torch.equal(y1, y2)
+
+
+def test_errors_are_loud(ops):
+    import video_classif_b200 as vc
+    with pytest.raises(vc.B200LrcnError):
+        ops.sgemm(torch.randn(4, 4), torch.randn(4, 4))                        # CPU tensors: no fallback
+    with pytest.raises(vc.B200LrcnError):
+        ops.conv2d_nhwc(torch.zeros(1, 4, 4, 48, device=DEV, dtype=torch.bfloat16),
+                        torch.zeros(64, 3, 3, 48, device=DEV, dtype=torch.bfloat16), 1, 1)   # C % 64 != 0

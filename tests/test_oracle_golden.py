@@ -1,0 +1,143 @@
+"""CPU: pins oracle/lrcn_oracle.py against golden vectors produced by the reference itself
+(tests/golden/make_golden.py), and -- when /root/reference is present -- against the live reference."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, build_backbone_model, err, golden_tensors, load_golden
+from oracle import lrcn_oracle as O
+from oracle import refload
+
+
+def test_sampling_matches_reference_vectors():
+    t = json.load(open(os.path.join(GOLDEN, "sampling.json")))
+    for key, want in t["medsos"].items():
+        n, T = map(int, key.split(","))
+        assert O.medsos_indices(n, T) == want, key
+    for key, want in t["crime"].items():
+        n, T = map(int, key.split(","))
+        assert O.crime_indices(n, T) == want, key
+    for key, want in t["seek"].items():
+        n, T = map(int, key.split(","))
+        assert O.seek_indices(n, T) == want, key
+
+
+def test_resize_bit_exact_vs_cv2_golden():
+    g = np.load(os.path.join(GOLDEN, "resize_cv2.npz"))
+    i = 0
+    while f"src{i}" in g.files:
+        src, dst = g[f"src{i}"], g[f"dst{i}"]
+        got = O.resize_bilinear_u8(src, dst.shape[0], dst.shape[1])
+        assert np.array_equal(got, dst), f"case {i}"
+        clip = O.ingest_clip(src[None], dst.shape[0], dst.shape[1], swap_rb=True)
+        want = (g[f"rgb{i}"].astype(np.float64) / 255.0).astype(np.float32).transpose(2, 0, 1)
+        assert np.array_equal(clip[0], want)
+        i += 1
+    assert i >= 5
+
+
+def test_resize_bit_exact_vs_live_cv2():
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(3)
+    for _ in range(25):
+        h, w = rng.integers(2, 200, 2)
+        oh, ow = rng.integers(1, 130, 2)
+        src = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        assert np.array_equal(O.resize_bilinear_u8(src, int(oh), int(ow)), cv2.resize(src, (int(ow), int(oh))))
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_smallcnn_oracle_vs_golden(tag):
+    g, meta = load_golden(f"smallcnn_lrcn_{tag}.npz")
+    sd = golden_tensors(g, "sd0/")
+    p = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v)
+         for k, v in sd.items()}
+    x, y = torch.from_numpy(g["x"]), torch.from_numpy(g["y"])
+    logits, ns = O.small_cnn_lrcn_forward(p, x, meta["hidden"])
+    loss = O.cross_entropy_mean(logits, y)
+    loss.backward()
+    assert err(logits, torch.from_numpy(g["logits"])) < 2e-5
+    assert abs(loss.item() - float(g["loss"])) < 1e-5
+    gmax = max(float(np.abs(g[k]).max()) for k in g.files if k.startswith("grad/"))
+    for k, v in golden_tensors(g, "grad/").items():
+        if k.startswith("conv") and k.endswith(".bias"):
+            # analytically zero (train-mode BN removes the bias): both sides are rounding noise
+            assert p[k].grad.abs().max().item() < 1e-4 * gmax and v.abs().max().item() < 1e-4 * gmax, k
+        else:
+            assert err(p[k].grad, v) < 2e-4, k
+    for k, v in golden_tensors(g, "sd1/").items():
+        if "running" in k:
+            assert err(ns[k], v) < 1e-5, k
+    assert torch.equal(O.predict(logits), O.predict(torch.from_numpy(g["logits"])))
+
+
+@pytest.mark.parametrize("tag", ["uni", "bi"])
+def test_lstm_oracle_vs_golden(tag):
+    g, meta = load_golden(f"lstm_{tag}.npz")
+    p = {"lstm." + k: v.clone().requires_grad_(True) for k, v in golden_tensors(g, "p/").items()}
+    x = torch.from_numpy(g["x"]).requires_grad_(True)
+    out = O.lstm_forward(x, p, meta["H"], meta["layers"], meta["bidir"])
+    (out * torch.from_numpy(g["w"])).sum().backward()
+    assert err(out, torch.from_numpy(g["out"])) < 1e-5
+    assert err(x.grad, torch.from_numpy(g["dx"])) < 1e-5
+    for k, v in golden_tensors(g, "g/").items():
+        assert err(p["lstm." + k].grad, v) < 1e-5, k
+
+
+@pytest.mark.parametrize("arch", ["resnet18", "resnet50"])
+def test_medsos_oracle_vs_golden(arch):
+    m, g, meta = build_backbone_model(f"medsos_lrcn_{arch}.npz")
+    sd = {k: (v.detach().clone().requires_grad_(True) if v.dtype.is_floating_point and not k.startswith("cnn_backbone.")
+              else v.detach().clone()) for k, v in m.state_dict().items()}
+    x, y = torch.from_numpy(g["x"]), torch.from_numpy(g["y"])
+    B, T = x.shape[:2]
+    feat, ns = O.resnet_features(sd, x.reshape(B * T, *x.shape[2:]), arch, train=True)
+    assert err(feat, torch.from_numpy(g["features"])) < 1e-4
+    logits, ns = O.medsos_lrcn_forward(sd, x, arch, meta["hidden"], meta["rnn_layers"], False)
+    O.cross_entropy_mean(logits, y).backward()
+    assert err(logits, torch.from_numpy(g["logits"])) < 1e-4
+    for k, v in golden_tensors(g, "grad/").items():
+        assert err(sd[k].grad, v, floor=1e-7) < 2e-3, k
+    for k, v in golden_tensors(g, "gradsub16/").items():
+        assert err(sd[k].grad[::16, ::16], v, floor=1e-7) < 2e-3, k
+    for k, v in golden_tensors(g, "sd1/").items():
+        assert err(ns[k], v) < 1e-4, k
+
+
+def test_simple_and_crime_oracle_vs_golden():
+    m, g, meta = build_backbone_model("ucf50_lrcn_resnet18.npz")
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    x = torch.from_numpy(g["x"])
+    logits, _ = O.simple_lrcn_forward(sd, x, "resnet18", meta["hidden"], meta["rnn_layers"])
+    assert err(logits, torch.from_numpy(g["logits"])) < 1e-4
+    m, g, meta = build_backbone_model("crime_lrcn_resnet18.npz")
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    logits, _ = O.simple_lrcn_forward(sd, x, "resnet18", meta["hidden"], meta["rnn_layers"], adapt_names=("adapt",),
+                                      rnn_prefix="lstm.", num_heads=meta["num_classes"])
+    assert err(logits, torch.from_numpy(g["logits"])) < 1e-4
+
+
+def test_scan_oracle_vs_golden():
+    g = np.load(os.path.join(GOLDEN, "scan.npz"))
+    t = lambda k: torch.from_numpy(g[k])
+    args = (t("u"), t("delta"), t("A"), t("B"), t("C"))
+    assert err(O.selective_scan(*args, chunk_reset=256), t("y_videomamba")) < 1e-5
+    assert err(O.selective_scan(*args, chunk_reset=None), t("y_medsos_fwd")) < 1e-5
+    assert err(O.selective_scan(*args, chunk_reset=None, reverse=True), t("y_medsos_bwd")) < 1e-5
+
+
+@pytest.mark.skipif(not refload.available(), reason="/root/reference only exists in the authoring container")
+def test_oracle_vs_live_reference_smallcnn():
+    torch.manual_seed(3)
+    LRCN = refload.notebook_lrcn()
+    m = LRCN(7, 3, 6, (3, 8, 8))
+    m.dropout.p = 0.0
+    m.train()
+    x = torch.rand(2, 3, 3, 8, 8)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    ref = m(x)
+    got, _ = O.small_cnn_lrcn_forward(sd, x, 6)
+    assert err(got, ref) < 1e-5

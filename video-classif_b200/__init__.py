@@ -1,5 +1,15 @@
-"""b200-lrcn: B200-native LRCN clip-classification hot path."""
-from . import _lib  # noqa: F401
+"""b200-lrcn: B200-native LRCN clip-classification hot path.
+
+Importing the package never needs a GPU; running any operator does (sm_100a, no fallback)."""
+from . import _lib, sampling  # noqa: F401
 from ._lib import B200LrcnError  # noqa: F401
 
-__all__ = ["B200LrcnError"]
+
+def __getattr__(name):   # lazy: models/ops import torch + torchvision
+    if name in ("SmallCNNLRCN", "LRCN", "UCF50LRCN", "CrimeLRCN", "count_parameters"):
+        from . import models
+        return getattr(models, name)
+    if name in ("ops", "models", "ingest", "backbone", "dp", "scan"):
+        import importlib
+        return importlib.import_module("." + name, __name__)
+    raise AttributeError(name)

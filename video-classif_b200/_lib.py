@@ -1,47 +1,62 @@
 """ctypes binding of libb200lrcn.so -- the C-ABI boundary declared in include/b200lrcn.h.
 
-There is no CPU / other-GPU fallback: if the shared library is missing, or a call returns a
-non-zero status, a B200LrcnError is raised."""
+The header is the single source of truth: its prototypes are parsed here to build the ctypes
+signatures, so the Python side cannot drift from the ABI.  There is no CPU / other-GPU fallback:
+if the shared library is missing, or a call returns a non-zero status, B200LrcnError is raised."""
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_long, c_void_p
+import re
+from ctypes import c_char_p, c_float, c_int, c_long, c_ulonglong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200lrcn.so")
+HEADER_PATH = os.path.join(_HERE, "..", "include", "b200lrcn.h")
 
 
 class B200LrcnError(RuntimeError):
     pass
 
 
-_P, _I, _L, _F = c_void_p, c_int, c_long, c_float
+_SCALARS = {"int": c_int, "long": c_long, "float": c_float, "unsigned": c_ulonglong}
 
-# name -> argument ctypes (all functions return int status unless listed in _RET)
-SIGNATURES = {
-    "b2_abi_version": [],
-    "b2_last_error": [],
-    "b2_launch_count": [],
-    "b2_device_check": [],
-    "b2_gemm_bf16_tn": [_P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _I, _I, _P, _P, _P],
-    "b2_conv2d_nhwc_bf16": [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P, _P, _P],
-}
-_RET = {"b2_last_error": c_char_p, "b2_launch_count": c_long}
+
+def parse_header(path=HEADER_PATH):
+    """-> {name: (restype, [argtypes])} for every `b2_*` prototype in the header."""
+    src = open(path).read()
+    src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
+    out = {}
+    for ret, name, args in re.findall(r"\b(int|long|const char\*)\s+(b2_\w+)\s*\(([^)]*)\)\s*;", src):
+        argtypes = []
+        args = args.strip()
+        if args and args != "void":
+            for a in args.split(","):
+                a = a.strip()
+                if "*" in a:
+                    argtypes.append(c_void_p)
+                else:
+                    argtypes.append(_SCALARS[a.split()[0]])
+        restype = {"int": c_int, "long": c_long, "const char*": c_char_p}[ret]
+        out[name] = (restype, argtypes)
+    return out
+
 
 _lib = None
+_sigs = None
 
 
 def lib():
-    global _lib
+    global _lib, _sigs
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             raise B200LrcnError(
                 f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(there is no fallback path)")
         l = ctypes.CDLL(LIB_PATH)
-        for name, args in SIGNATURES.items():
-            fn = getattr(l, name)
-            fn.argtypes = args
-            fn.restype = _RET.get(name, c_int)
+        _sigs = parse_header()
+        for name, (restype, argtypes) in _sigs.items():
+            fn = getattr(l, name)      # AttributeError if the .so is stale w.r.t. the header
+            fn.argtypes = argtypes
+            fn.restype = restype
         _lib = l
     return _lib
 
@@ -60,8 +75,22 @@ def launch_count() -> int:
     return int(lib().b2_launch_count())
 
 
+_device_ok = False
+
+
+def require_device():
+    """Fail loudly unless the current CUDA device is a B200 (sm_100)."""
+    global _device_ok
+    if not _device_ok:
+        import torch
+        if not torch.cuda.is_available():
+            raise B200LrcnError("b200-lrcn needs a CUDA device (sm_100a); no CPU fallback exists")
+        call("b2_device_check")
+        _device_ok = True
+
+
 def ptr(t):
-    """data_ptr of a tensor or 0 for None."""
+    """data_ptr of a tensor or 0 (NULL) for None."""
     return 0 if t is None else t.data_ptr()
 
 

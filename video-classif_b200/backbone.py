@@ -1,0 +1,154 @@
+"""Frozen torchvision-ResNet frame encoder executed on the sm_100a kernels.
+
+The reference builds `getattr(torchvision.models, name)(pretrained=True)`, sets fc=Identity and
+freezes every parameter (medsos_lrcn/src/models.py:133-145, lrcn/ucf50-lrcn.py:263-272) but keeps
+the module in .train() mode (train_eval.py:12), so every BatchNorm uses BATCH statistics over all
+B*T frames and updates its running stats.  This runner reproduces exactly that, NHWC bf16:
+
+  stem   : 7x7/2 patches (b2_stem_im2col) -> tcgen05 GEMM (+column stats) -> BN+ReLU+maxpool
+  blocks : every conv is the tcgen05 implicit GEMM (1x1 = plain TMA GEMM, 3x3 / strided =
+           im2col-mode TMA) whose epilogue already emits the BN batch statistics; one
+           bn_apply pass normalises, adds the shortcut (identity or down-sample BN) and ReLUs
+  head   : global average pool -> [N, C] fp32
+
+The torchvision module is only a PARAMETER CONTAINER (state_dict keys / shapes / default init are
+the reference's); its forward is never called."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import call, ptr, stream_ptr
+from .ops import BF16, F32, conv2d_nhwc, gemm_tn
+
+SUPPORTED = ("resnet18", "resnet34", "resnet50", "resnet101", "resnet152")
+STEM_KP = 160   # 7*7*3 = 147 patch columns padded to a 16-byte multiple
+
+
+def make_backbone(name: str, pretrained: bool = False):
+    """torchvision constructor + the reference's head surgery (fc/classifier -> Identity).
+    Returns (module, feature_size)."""
+    import torchvision.models as tvm
+    if name not in SUPPORTED:
+        raise NotImplementedError(
+            f"cnn_backbone={name!r}: only ResNet-class backbones {SUPPORTED} run on the B200 kernels in this "
+            "round (DenseNet/MobileNet are listed under 'next' in DESIGN.md)")
+    net = getattr(tvm, name)(weights="DEFAULT" if pretrained else None)
+    feat = net.fc.in_features
+    net.fc = torch.nn.Identity()
+    return net, feat
+
+
+class ResNetRunner:
+    def __init__(self, net):
+        self.net = net
+        self._wcache = None
+        self._wkey = None
+
+    # ---- weights in kernel layout: [Cout, R, S, C] bf16 (K-major), stem [64, STEM_KP] ----
+    def _weights(self):
+        convs = [(n, m) for n, m in self.net.named_modules() if isinstance(m, torch.nn.Conv2d)]
+        key = tuple((m.weight.data_ptr(), m.weight._version) for _, m in convs)
+        if self._wkey != key:
+            cache = {}
+            for n, m in convs:
+                w = m.weight.detach()
+                if n == "conv1":
+                    wk = torch.zeros((w.shape[0], STEM_KP), device=w.device, dtype=BF16)
+                    wk[:, :147] = w.permute(0, 2, 3, 1).reshape(w.shape[0], 147).to(BF16)
+                else:
+                    wk = w.permute(0, 2, 3, 1).contiguous().to(BF16)
+                cache[n] = wk
+            self._wcache, self._wkey = cache, key
+        return self._wcache
+
+    def _bn(self, x, bn, stats, count, train, relu=True, res_mode=0, res=None, rbn=None, rstats=None):
+        rows = x.numel() // x.shape[-1]
+        C = x.shape[-1]
+        rs1 = rs2 = rg = rb = rrm = rrv = None
+        if res_mode == 2:
+            rs1, rs2 = (rstats if train else (None, None))
+            rg, rb, rrm, rrv = rbn.weight, rbn.bias, rbn.running_mean, rbn.running_var
+        s1, s2 = stats if train else (None, None)
+        mom = bn.momentum if bn.momentum is not None else 0.1
+        call("b2_bn_apply_nhwc", x.data_ptr(), x.data_ptr(), rows, C, ptr(s1), ptr(s2), bn.weight.data_ptr(),
+             bn.bias.data_ptr(), ptr(bn.running_mean), ptr(bn.running_var), res_mode, ptr(res), ptr(rs1), ptr(rs2),
+             ptr(rg), ptr(rb), ptr(rrm), ptr(rrv), count, float(bn.eps), float(mom), int(train), int(relu),
+             stream_ptr())
+        return x   # in place
+
+    def __call__(self, x, training: bool):
+        """x: [N,3,H,W] fp32 or bf16 (NCHW, the reference's frame tensor) -> [N, feat] fp32."""
+        _lib.require_device()
+        net = self.net
+        if torch.is_grad_enabled() and any(p.requires_grad for p in net.parameters()):
+            raise NotImplementedError(
+                "trainable CNN backbone (full fine-tune, rgb_lrcn.py:208-227) has no backward kernels yet; "
+                "freeze it (requires_grad=False) as medsos models.py:144-145 / ucf50-lrcn.py:271-272 do")
+        x = x.contiguous()
+        N, Cin, H, W = x.shape
+        assert Cin == 3, "frame encoder expects RGB frames"
+        dev = x.device
+        w = self._weights()
+        bns = [m for m in net.modules() if isinstance(m, torch.nn.BatchNorm2d)]
+        train = bool(training)
+        maxc = max(b.num_features for b in bns)
+        stat_buf = torch.zeros((len(bns), 2, maxc), device=dev, dtype=F32) if train else None
+        bn_index = {id(b): i for i, b in enumerate(bns)}
+
+        def stats_of(bn):
+            if not train:
+                return None
+            sb = stat_buf[bn_index[id(bn)]]
+            return (sb[0], sb[1])
+
+        st = stream_ptr()
+        # ---- stem ----
+        P, Q = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
+        A = torch.empty((N * P * Q, STEM_KP), device=dev, dtype=BF16)
+        call("b2_stem_im2col", x.data_ptr(), int(x.dtype == BF16), A.data_ptr(), N, H, W, STEM_KP, st)
+        raw = gemm_tn(A, w["conv1"], out_dtype=BF16, stats=stats_of(net.bn1))
+        del A
+        P2, Q2 = (P + 2 - 3) // 2 + 1, (Q + 2 - 3) // 2 + 1
+        y = torch.empty((N, P2, Q2, 64), device=dev, dtype=BF16)
+        s = stats_of(net.bn1)
+        mom = net.bn1.momentum if net.bn1.momentum is not None else 0.1
+        call("b2_bn_relu_maxpool_nhwc", raw.data_ptr(), y.data_ptr(), N, P, Q, 64, ptr(s[0] if s else None),
+             ptr(s[1] if s else None), net.bn1.weight.data_ptr(), net.bn1.bias.data_ptr(),
+             net.bn1.running_mean.data_ptr(), net.bn1.running_var.data_ptr(), float(net.bn1.eps), float(mom),
+             int(train), st)
+        del raw
+        # ---- residual stages ----
+        for li in range(1, 5):
+            layer = getattr(net, f"layer{li}")
+            for bi, blk in enumerate(layer):
+                pfx = f"layer{li}.{bi}"
+                stride = blk.stride if isinstance(blk.stride, int) else blk.stride[0]
+                bottleneck = hasattr(blk, "conv3")
+                if bottleneck:
+                    o = conv2d_nhwc(y, w[pfx + ".conv1"], 1, 0, stats_of(blk.bn1))
+                    o = self._bn(o, blk.bn1, stats_of(blk.bn1), o.numel() // o.shape[-1], train)
+                    o = conv2d_nhwc(o, w[pfx + ".conv2"], stride, 1, stats_of(blk.bn2))
+                    o = self._bn(o, blk.bn2, stats_of(blk.bn2), o.numel() // o.shape[-1], train)
+                    o = conv2d_nhwc(o, w[pfx + ".conv3"], 1, 0, stats_of(blk.bn3))
+                    last_bn = blk.bn3
+                else:
+                    o = conv2d_nhwc(y, w[pfx + ".conv1"], stride, 1, stats_of(blk.bn1))
+                    o = self._bn(o, blk.bn1, stats_of(blk.bn1), o.numel() // o.shape[-1], train)
+                    o = conv2d_nhwc(o, w[pfx + ".conv2"], 1, 1, stats_of(blk.bn2))
+                    last_bn = blk.bn2
+                cnt = o.numel() // o.shape[-1]
+                if blk.downsample is not None:
+                    dbn = blk.downsample[1]
+                    d = conv2d_nhwc(y, w[pfx + ".downsample.0"], stride, 0, stats_of(dbn))
+                    y = self._bn(o, last_bn, stats_of(last_bn), cnt, train, res_mode=2, res=d, rbn=dbn,
+                                 rstats=stats_of(dbn))
+                else:
+                    y = self._bn(o, last_bn, stats_of(last_bn), cnt, train, res_mode=1, res=y)
+        # ---- head ----
+        Nn, Hh, Ww, C = y.shape
+        feat = torch.empty((Nn, C), device=dev, dtype=F32)
+        call("b2_avgpool_nhwc", y.data_ptr(), feat.data_ptr(), 0, Nn, Hh * Ww, C, st)
+        if train:
+            torch._foreach_add_([b.num_batches_tracked for b in bns if b.num_batches_tracked is not None], 1)
+        return feat

@@ -1,0 +1,271 @@
+// NHWC bf16 glue kernels of the frame-CNN (ResNet-class backbone) path -- all HBM-bound,
+// 128-bit (8 x bf16) vector accesses, grids sized in multiples of the SM count.
+//
+//   stem_im2col     : fp32/bf16 NCHW frames -> [M, Kp] bf16 patch matrix for the 7x7/2 stem GEMM
+//   bn_apply        : train/eval BatchNorm (statistics come from the conv epilogue's column sums)
+//                     + optional residual (identity or a second raw tensor with its own BN) + ReLU
+//   bn_relu_maxpool : stem BN + ReLU + 3x3/2 max-pool in one pass
+//   avgpool         : global average pool -> [N, C] fp32 (+ bf16 copy for the adapt GEMM)
+//
+// BatchNorm semantics follow torch.nn.BatchNorm2d as the reference runs it (train mode even for
+// frozen backbones: medsos_lrcn/src/train_eval.py:12 + models.py:144-145): biased variance for
+// normalisation, running_var updated with the unbiased one, momentum 0.1.
+#include "common.cuh"
+
+namespace {
+
+struct BnSrc {
+  const float* sum;     // [C] column sums from the producing conv (train) or null (eval)
+  const float* sumsq;   // [C]
+  const float* gamma;   // [C]
+  const float* beta;    // [C]
+  float* running_mean;  // [C] updated in train mode, read in eval mode
+  float* running_var;   // [C]
+};
+
+// scale/shift for channel c ; block 0 also performs the running-stat update
+__device__ __forceinline__ float2 bn_scale_shift(const BnSrc& b, int c, float inv_count, float unbias, float eps,
+                                                 float momentum, bool train, bool update) {
+  float mean, var;
+  if (train) {
+    mean = b.sum[c] * inv_count;
+    var = fmaxf(b.sumsq[c] * inv_count - mean * mean, 0.f);
+    if (update && b.running_mean != nullptr) {
+      b.running_mean[c] = (1.f - momentum) * b.running_mean[c] + momentum * mean;
+      b.running_var[c] = (1.f - momentum) * b.running_var[c] + momentum * var * unbias;
+    }
+  } else {
+    mean = b.running_mean[c];
+    var = b.running_var[c];
+  }
+  const float rstd = rsqrtf(var + eps);
+  const float sc = b.gamma[c] * rstd;
+  return make_float2(sc, b.beta[c] - mean * sc);
+}
+
+__device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  unpack_bf16x2(u.x, v[0], v[1]);
+  unpack_bf16x2(u.y, v[2], v[3]);
+  unpack_bf16x2(u.z, v[4], v[5]);
+  unpack_bf16x2(u.w, v[6], v[7]);
+}
+__device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]);
+  u.y = pack_bf16x2(v[2], v[3]);
+  u.z = pack_bf16x2(v[4], v[5]);
+  u.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+// res_mode 0: none, 1: residual already normalised (identity shortcut), 2: residual raw + own BN
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const bf16* x, bf16* y, long rows, int C, BnSrc bn, int res_mode,
+                const bf16* __restrict__ res, BnSrc rbn, float inv_count, float unbias, float eps, float momentum,
+                int train, int relu) {
+  extern __shared__ float2 ss[];  // [C] (+ [C] for the residual BN)
+  float2* ss2 = ss + C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    ss[c] = bn_scale_shift(bn, c, inv_count, unbias, eps, momentum, train, blockIdx.x == 0);
+    if (res_mode == 2) ss2[c] = bn_scale_shift(rbn, c, inv_count, unbias, eps, momentum, train, blockIdx.x == 0);
+  }
+  __syncthreads();
+  const int vec_per_row = C >> 3;
+  const long total = rows * vec_per_row;
+  for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(v % vec_per_row) << 3;
+    float a[8];
+    load8(x + v * 8, a);
+    float r[8];
+    if (res_mode) load8(res + v * 8, r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float2 s = ss[c0 + j];
+      float o = fmaf(a[j], s.x, s.y);
+      if (res_mode == 1) o += r[j];
+      else if (res_mode == 2) {
+        const float2 s2 = ss2[c0 + j];
+        o += fmaf(r[j], s2.x, s2.y);
+      }
+      a[j] = relu ? fmaxf(o, 0.f) : o;
+    }
+    store8(y + v * 8, a);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bn_relu_maxpool_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N, int H, int W, int C, int P, int Q,
+                       BnSrc bn, float inv_count, float unbias, float eps, float momentum, int train) {
+  extern __shared__ float2 ss[];
+  for (int c = threadIdx.x; c < C; c += blockDim.x)
+    ss[c] = bn_scale_shift(bn, c, inv_count, unbias, eps, momentum, train, blockIdx.x == 0);
+  __syncthreads();
+  const int vec = C >> 3;
+  const long total = (long)N * P * Q * vec;
+  for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (long)gridDim.x * blockDim.x) {
+    const int cg = (int)(v % vec);
+    long t = v / vec;
+    const int q = (int)(t % Q);
+    t /= Q;
+    const int p = (int)(t % P);
+    const int n = (int)(t / P);
+    float m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = 0.f;  // post-ReLU values are >= 0 and the window is never empty
+    for (int dy = 0; dy < 3; ++dy) {
+      const int iy = 2 * p - 1 + dy;
+      if (iy < 0 || iy >= H) continue;
+      for (int dx = 0; dx < 3; ++dx) {
+        const int ix = 2 * q - 1 + dx;
+        if (ix < 0 || ix >= W) continue;
+        float a[8];
+        load8(x + (((long)n * H + iy) * W + ix) * C + cg * 8, a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float2 s = ss[cg * 8 + j];
+          m[j] = fmaxf(m[j], fmaf(a[j], s.x, s.y));
+        }
+      }
+    }
+    store8(y + v * 8, m);
+  }
+}
+
+// one thread per (n, 8-channel group); HW <= a few hundred
+__global__ void __launch_bounds__(256)
+avgpool_kernel(const bf16* __restrict__ x, float* __restrict__ out_f32, bf16* __restrict__ out_bf16, int N, int HW,
+               int C) {
+  const int vec = C >> 3;
+  const long total = (long)N * vec;
+  for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (long)gridDim.x * blockDim.x) {
+    const int cg = (int)(v % vec);
+    const long n = v / vec;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const bf16* p = x + n * HW * C + cg * 8;
+    for (int i = 0; i < HW; ++i) {
+      float a[8];
+      load8(p + (long)i * C, a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += a[j];
+    }
+    const float inv = 1.f / (float)HW;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] *= inv;
+    if (out_f32) {
+      float* o = out_f32 + n * C + cg * 8;
+      *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+    if (out_bf16) store8(out_bf16 + n * C + cg * 8, acc);
+  }
+}
+
+// Patch matrix for the 7x7 stride-2 pad-3 stem: row m = (n,p,q), column k = (r*7+s)*3 + c, padded
+// with zeros to Kp columns.  Each thread produces 8 consecutive k (one 16-byte store).
+template <typename InT>
+__global__ void __launch_bounds__(256)
+stem_im2col_kernel(const InT* __restrict__ x, bf16* __restrict__ A, int N, int H, int W, int P, int Q, int Kp) {
+  const int kvec = Kp >> 3;
+  const long total = (long)N * P * Q * kvec;
+  const long plane = (long)H * W;
+  for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (long)gridDim.x * blockDim.x) {
+    const int kv = (int)(v % kvec);
+    long m = v / kvec;
+    const int q = (int)(m % Q);
+    long t = m / Q;
+    const int p = (int)(t % P);
+    const int n = (int)(t / P);
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = kv * 8 + j;
+      float val = 0.f;
+      if (k < 147) {
+        const int c = k % 3;
+        const int tap = k / 3;
+        const int s = tap % 7, r = tap / 7;
+        const int iy = 2 * p - 3 + r, ix = 2 * q - 3 + s;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) val = (float)x[((long)n * 3 + c) * plane + (long)iy * W + ix];
+      }
+      o[j] = val;
+    }
+    store8(A + v * 8, o);
+  }
+}
+
+int grid_for(long work_items, int threads) {
+  long blocks = (work_items + threads - 1) / threads;
+  long cap = (long)b2_num_sms() * 8;
+  return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+}  // namespace
+
+B2_API int b2_bn_apply_nhwc(const void* x, void* y, long rows, int C, const float* sum, const float* sumsq,
+                            const float* gamma, const float* beta, float* running_mean, float* running_var,
+                            int res_mode, const void* res, const float* rsum, const float* rsumsq,
+                            const float* rgamma, const float* rbeta, float* rrunning_mean, float* rrunning_var,
+                            long count, float eps, float momentum, int train, int relu, void* stream) {
+  B2_ARG_CHECK(x && y && gamma && beta && rows > 0, "b2_bn_apply_nhwc: null pointer or empty");
+  B2_ARG_CHECK(C % 8 == 0 && C <= 4096, "b2_bn_apply_nhwc: C must be a multiple of 8 and <= 4096 (got %d)", C);
+  B2_ARG_CHECK(train ? (sum && sumsq) : (running_mean && running_var), "b2_bn_apply_nhwc: missing statistics");
+  B2_ARG_CHECK(res_mode == 0 || res, "b2_bn_apply_nhwc: residual pointer missing");
+  B2_ARG_CHECK(res_mode != 2 || (rgamma && rbeta && (train ? (rsum && rsumsq) : (rrunning_mean && rrunning_var))),
+               "b2_bn_apply_nhwc: residual BN parameters missing");
+  BnSrc bn = {sum, sumsq, gamma, beta, running_mean, running_var};
+  BnSrc rbn = {rsum, rsumsq, rgamma, rbeta, rrunning_mean, rrunning_var};
+  const size_t smem = (size_t)C * sizeof(float2) * (res_mode == 2 ? 2 : 1);
+  if (smem > 48 * 1024)
+    B2_CUDA_CHECK(cudaFuncSetAttribute(bn_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  const float inv = 1.f / (float)count;
+  const float unbias = count > 1 ? (float)((double)count / (double)(count - 1)) : 1.f;
+  bn_apply_kernel<<<grid_for(rows * (C / 8), 256), 256, smem, (cudaStream_t)stream>>>(
+      (const bf16*)x, (bf16*)y, rows, C, bn, res_mode, (const bf16*)res, rbn, inv, unbias, eps, momentum, train, relu);
+  B2_LAUNCH_CHECK("bn_apply_kernel");
+  return 0;
+}
+
+B2_API int b2_bn_relu_maxpool_nhwc(const void* x, void* y, int N, int H, int W, int C, const float* sum,
+                                   const float* sumsq, const float* gamma, const float* beta, float* running_mean,
+                                   float* running_var, float eps, float momentum, int train, void* stream) {
+  B2_ARG_CHECK(x && y && gamma && beta && N > 0 && H > 0 && W > 0, "b2_bn_relu_maxpool_nhwc: null pointer or empty");
+  B2_ARG_CHECK(C % 8 == 0 && C <= 4096, "b2_bn_relu_maxpool_nhwc: C must be a multiple of 8 and <= 4096");
+  B2_ARG_CHECK(train ? (sum && sumsq) : (running_mean && running_var), "b2_bn_relu_maxpool_nhwc: missing statistics");
+  const int P = (H + 2 - 3) / 2 + 1, Q = (W + 2 - 3) / 2 + 1;
+  BnSrc bn = {sum, sumsq, gamma, beta, running_mean, running_var};
+  const long count = (long)N * H * W;
+  const float inv = 1.f / (float)count;
+  const float unbias = count > 1 ? (float)((double)count / (double)(count - 1)) : 1.f;
+  bn_relu_maxpool_kernel<<<grid_for((long)N * P * Q * (C / 8), 256), 256, (size_t)C * sizeof(float2),
+                           (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, N, H, W, C, P, Q, bn, inv, unbias, eps,
+                                                   momentum, train);
+  B2_LAUNCH_CHECK("bn_relu_maxpool_kernel");
+  return 0;
+}
+
+B2_API int b2_avgpool_nhwc(const void* x, float* out_f32, void* out_bf16, int N, int HW, int C, void* stream) {
+  B2_ARG_CHECK(x && (out_f32 || out_bf16) && N > 0 && HW > 0, "b2_avgpool_nhwc: null pointer or empty");
+  B2_ARG_CHECK(C % 8 == 0, "b2_avgpool_nhwc: C must be a multiple of 8");
+  avgpool_kernel<<<grid_for((long)N * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, out_f32,
+                                                                                     (bf16*)out_bf16, N, HW, C);
+  B2_LAUNCH_CHECK("avgpool_kernel");
+  return 0;
+}
+
+B2_API int b2_stem_im2col(const void* x, int in_bf16, void* A, int N, int H, int W, int Kp, void* stream) {
+  B2_ARG_CHECK(x && A && N > 0 && H > 0 && W > 0, "b2_stem_im2col: null pointer or empty");
+  B2_ARG_CHECK(Kp >= 152 && Kp % 8 == 0, "b2_stem_im2col: Kp must be a multiple of 8 and >= 152");
+  const int P = (H + 6 - 7) / 2 + 1, Q = (W + 6 - 7) / 2 + 1;
+  const long total = (long)N * P * Q * (Kp / 8);
+  if (in_bf16)
+    stem_im2col_kernel<bf16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)A, N, H, W,
+                                                                                     P, Q, Kp);
+  else
+    stem_im2col_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const float*)x, (bf16*)A, N, H,
+                                                                                      W, P, Q, Kp);
+  B2_LAUNCH_CHECK("stem_im2col_kernel");
+  return 0;
+}

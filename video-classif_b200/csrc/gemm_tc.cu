@@ -153,6 +153,7 @@ struct EpiParams {
   void* D;
   long ldd;          // elements
   const float* bias; // [N] or null
+  const float* bias2; // [N] or null (second bias vector, e.g. LSTM b_hh)
   float* col_sum;    // [N] or null  (atomicAdd)
   float* col_sumsq;  // [N] or null
   int out_bf16;      // 1: bf16 out, 0: fp32 out
@@ -313,6 +314,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int j = 0; j < 32; ++j) {
           float x = __uint_as_float(raw[j]);
           if (ep.bias != nullptr && col0 + j < N) x += __ldg(ep.bias + col0 + j);
+          if (ep.bias2 != nullptr && col0 + j < N) x += __ldg(ep.bias2 + col0 + j);
           if (ep.relu) x = fmaxf(x, 0.0f);
           if (ep.out_bf16) x = bf16_round(x);
           v[j] = x;
@@ -475,8 +477,8 @@ int dispatch(int bn, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N,
 
 // D[M,N] = A[M,K] B[N,K]^T (+bias) ; see include/b200lrcn.h
 B2_API int b2_gemm_bf16_tn(const void* A, long lda, const void* B, long ldb, void* D, long ldd, int M, int N, int K,
-                           const float* bias, int out_bf16, int relu, float* col_sum, float* col_sumsq,
-                           void* stream) {
+                           const float* bias, const float* bias2, int out_bf16, int relu, float* col_sum,
+                           float* col_sumsq, void* stream) {
   B2_ARG_CHECK(A && B && D && M > 0 && N > 0 && K > 0, "b2_gemm_bf16_tn: null pointer or empty shape");
   B2_ARG_CHECK((lda % 8) == 0 && (ldb % 8) == 0, "b2_gemm_bf16_tn: lda/ldb must be multiples of 8 elements (16 B)");
   B2_ARG_CHECK(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "b2_gemm_bf16_tn: A/B must be 16 B aligned");
@@ -487,7 +489,7 @@ B2_API int b2_gemm_bf16_tn(const void* A, long lda, const void* B, long ldb, voi
   if (int r = make_tmap_2d(&ta, A, M, K, lda, BM)) return r;
   if (int r = make_tmap_2d(&tb, B, N, K, ldb, bn)) return r;
   ConvGeom g = {};
-  EpiParams ep = {D, ldd, bias, col_sum, col_sumsq, out_bf16, relu};
+  EpiParams ep = {D, ldd, bias, bias2, col_sum, col_sumsq, out_bf16, relu};
   return dispatch(bn, ta, tb, M, N, K, g, ep, (cudaStream_t)stream);
 }
 
@@ -509,7 +511,7 @@ B2_API int b2_conv2d_nhwc_bf16(const void* x, int Nimg, int H, int W, int C, con
   const int M = (int)Ml;
   const int K = R * S * C;
   const int bn = pick_bn(Cout);
-  EpiParams ep = {y, (long)Cout, bias, col_sum, col_sumsq, out_bf16, relu};
+  EpiParams ep = {y, (long)Cout, bias, nullptr, col_sum, col_sumsq, out_bf16, relu};
   CUtensorMap ta, tb;
   if (int r = make_tmap_2d(&tb, w, Cout, K, K, bn)) return r;
   if (R == 1 && S == 1 && stride == 1 && pad == 0) {

@@ -1,0 +1,317 @@
+// Trainable-tail kernels (adapt / head layers): exact-erf GELU + LayerNorm forward/backward,
+// fp32 SIMT GEMM (all transpose combinations; the fp32 parity path and the tiny-N layers),
+// column sums (bias gradients), casts and cast-transposes that feed the tcgen05 GEMM.
+//
+// Reference semantics: medsos_lrcn/src/models.py:200-202,221-226 -- `LN(gelu(Linear(x)))` where the
+// attributes named bn* are nn.LayerNorm (biased variance, eps 1e-5) and F.gelu is the erf form.
+#include "common.cuh"
+
+namespace {
+
+constexpr float kInvSqrt2 = 0.70710678118654752440f;
+constexpr float kInvSqrt2Pi = 0.39894228040143267794f;
+
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * kInvSqrt2)); }
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  return 0.5f * (1.f + erff(x * kInvSqrt2)) + x * kInvSqrt2Pi * expf(-0.5f * x * x);
+}
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+  if (w == 0) {
+    t = warp_sum(t);
+    if (l == 0) red[0] = t;
+  }
+  __syncthreads();
+  return red[0];
+}
+
+// one block per row: out = LN(act(pre)) * gamma + beta ; act = GELU or identity
+__global__ void __launch_bounds__(256)
+act_ln_fwd_kernel(const float* __restrict__ pre, const float* __restrict__ gamma, const float* __restrict__ beta,
+                  float* __restrict__ out_f32, bf16* __restrict__ out_bf16, float* __restrict__ mean_out,
+                  float* __restrict__ rstd_out, int N, float eps, int apply_gelu) {
+  __shared__ float red[32];
+  const long row = blockIdx.x;
+  const float* p = pre + row * N;
+  float s = 0.f;
+  for (int c = threadIdx.x; c < N; c += blockDim.x) {
+    const float g = apply_gelu ? gelu_f(p[c]) : p[c];
+    s += g;
+  }
+  const float mean = block_sum(s, red) / (float)N;
+  float q = 0.f;
+  for (int c = threadIdx.x; c < N; c += blockDim.x) {
+    const float g = (apply_gelu ? gelu_f(p[c]) : p[c]) - mean;
+    q += g * g;
+  }
+  const float var = block_sum(q, red) / (float)N;
+  const float rstd = rsqrtf(var + eps);
+  if (threadIdx.x == 0) {
+    mean_out[row] = mean;
+    rstd_out[row] = rstd;
+  }
+  for (int c = threadIdx.x; c < N; c += blockDim.x) {
+    const float g = apply_gelu ? gelu_f(p[c]) : p[c];
+    const float o = (g - mean) * rstd * gamma[c] + beta[c];
+    if (out_f32) out_f32[row * N + c] = o;
+    if (out_bf16) out_bf16[row * N + c] = __float2bfloat16_rn(o);
+  }
+}
+
+// grid-stride over rows; per-thread dgamma/dbeta partials for columns tid + k*256 (N <= 256*kMaxCols)
+constexpr int kMaxCols = 16;
+__global__ void __launch_bounds__(256)
+act_ln_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ pre, const float* __restrict__ gamma,
+                  const float* __restrict__ mean_in, const float* __restrict__ rstd_in, float* __restrict__ dpre,
+                  float* __restrict__ dgamma, float* __restrict__ dbeta, long M, int N, int apply_gelu) {
+  __shared__ float red[32];
+  float dg_acc[kMaxCols], db_acc[kMaxCols];
+#pragma unroll
+  for (int k = 0; k < kMaxCols; ++k) dg_acc[k] = db_acc[k] = 0.f;
+  for (long row = blockIdx.x; row < M; row += gridDim.x) {
+    const float* p = pre + row * N;
+    const float* d = dout + row * N;
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxCols; ++k) {
+      const int c = threadIdx.x + k * 256;
+      if (c < N) {
+        const float g = apply_gelu ? gelu_f(p[c]) : p[c];
+        const float xh = (g - mean) * rstd;
+        const float dxh = d[c] * gamma[c];
+        s1 += dxh;
+        s2 += dxh * xh;
+        dg_acc[k] += d[c] * xh;
+        db_acc[k] += d[c];
+      }
+    }
+    const float m1 = block_sum(s1, red) / (float)N;
+    const float m2 = block_sum(s2, red) / (float)N;
+#pragma unroll
+    for (int k = 0; k < kMaxCols; ++k) {
+      const int c = threadIdx.x + k * 256;
+      if (c < N) {
+        const float x = p[c];
+        const float g = apply_gelu ? gelu_f(x) : x;
+        const float xh = (g - mean) * rstd;
+        const float dxh = d[c] * gamma[c];
+        float dgv = rstd * (dxh - m1 - xh * m2);
+        if (apply_gelu) dgv *= gelu_grad_f(x);
+        dpre[row * N + c] = dgv;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kMaxCols; ++k) {
+    const int c = threadIdx.x + k * 256;
+    if (c < N) {
+      atomicAdd(dgamma + c, dg_acc[k]);
+      atomicAdd(dbeta + c, db_acc[k]);
+    }
+  }
+}
+
+// ---- fp32 SIMT GEMM: C[M,N] = alpha * op(A)[M,K] op(B)[K,N] + beta * C, row-major ----
+constexpr int TS = 64, TK = 16;
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256)
+sgemm_kernel(int M, int N, int K, float alpha, const float* __restrict__ A, long lda, const float* __restrict__ B,
+             long ldb, float beta, float* __restrict__ C, long ldc, const float* __restrict__ bias,
+             const float* __restrict__ bias2) {
+  __shared__ float As[TK][TS + 4];
+  __shared__ float Bs[TK][TS + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * TS, n0 = blockIdx.x * TS;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += TK) {
+    for (int i = threadIdx.x; i < TS * TK; i += 256) {
+      int m, k;
+      if (TA) { m = i % TS; k = i / TS; } else { k = i % TK; m = i / TK; }
+      const int gm = m0 + m, gk = k0 + k;
+      float v = 0.f;
+      if (gm < M && gk < K) v = TA ? A[(long)gk * lda + gm] : A[(long)gm * lda + gk];
+      As[k][m] = v;
+    }
+    for (int i = threadIdx.x; i < TS * TK; i += 256) {
+      int n, k;
+      if (TB) { k = i % TK; n = i / TK; } else { n = i % TS; k = i / TS; }
+      const int gn = n0 + n, gk = k0 + k;
+      float v = 0.f;
+      if (gn < N && gk < K) v = TB ? B[(long)gn * ldb + gk] : B[(long)gk * ldb + gn];
+      Bs[k][n] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < TK; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + ty * 4 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + tx * 4 + j;
+      if (gn >= N) continue;
+      float* c = C + (long)gm * ldc + gn;
+      float v = alpha * acc[i][j];
+      if (bias) v += bias[gn];
+      if (bias2) v += bias2[gn];
+      *c = (beta == 0.f) ? v : v + beta * (*c);
+    }
+  }
+}
+
+// out[c] (+)= sum_r X[r, c]
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ X, long ld, long M, int N, float* __restrict__ out, int accumulate) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ry = threadIdx.x >> 5;
+  float s = 0.f;
+  if (c < N)
+    for (long r = ry; r < M; r += 8) s += X[r * ld + c];
+  red[ry][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (ry == 0 && c < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+    out[c] = accumulate ? out[c] + t : t;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long n) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+// dst[c, r] (bf16, ld_dst) = src[r, c] (fp32, ld_src) ; 32x32 smem tile transpose
+__global__ void __launch_bounds__(256)
+transpose_cast_kernel(const float* __restrict__ src, long ld_src, bf16* __restrict__ dst, long ld_dst, long R,
+                      long Ccols) {
+  __shared__ float tile[32][33];
+  const long r0 = (long)blockIdx.y * 32, c0 = (long)blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const long r = r0 + i, c = c0 + tx;
+    tile[i][tx] = (r < R && c < Ccols) ? src[r * ld_src + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const long c = c0 + i, r = r0 + tx;
+    if (c < Ccols && r < R) dst[c * ld_dst + r] = __float2bfloat16_rn(tile[tx][i]);
+  }
+}
+
+// y = x * keep(i) / (1-p), keep(i) = [hash(seed, i) >= p] -- the same call with the same seed
+// replays the mask for the backward pass (dx = dy * keep / (1-p)).
+__device__ __forceinline__ uint32_t mix32(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return (uint32_t)((z ^ (z >> 31)) >> 32);
+}
+__global__ void __launch_bounds__(256)
+dropout_kernel(const float* __restrict__ x, float* __restrict__ y, long n, float p, unsigned long long seed) {
+  const float inv_keep = 1.f / (1.f - p);
+  const uint32_t thresh = (uint32_t)((double)p * 4294967296.0);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const uint32_t r = mix32(seed * 0xD1342543DE82EF95ull + (uint64_t)i);
+    y[i] = (r >= thresh) ? x[i] * inv_keep : 0.f;
+  }
+}
+
+}  // namespace
+
+B2_API int b2_dropout_f32(const float* x, float* y, long n, float p, unsigned long long seed, void* stream) {
+  B2_ARG_CHECK(x && y && n > 0, "b2_dropout_f32: null pointer or empty");
+  B2_ARG_CHECK(p >= 0.f && p < 1.f, "b2_dropout_f32: p must be in [0,1)");
+  long blocks = (n + 255) / 256;
+  const long cap = (long)b2_num_sms() * 8;
+  dropout_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(x, y, n, p, seed);
+  B2_LAUNCH_CHECK("dropout_kernel");
+  return 0;
+}
+
+B2_API int b2_act_ln_fwd(const float* pre, const float* gamma, const float* beta, float* out_f32, void* out_bf16,
+                         float* mean, float* rstd, long M, int N, float eps, int apply_gelu, void* stream) {
+  B2_ARG_CHECK(pre && gamma && beta && mean && rstd && (out_f32 || out_bf16) && M > 0 && N > 0,
+               "b2_act_ln_fwd: null pointer or empty");
+  act_ln_fwd_kernel<<<(unsigned)M, 256, 0, (cudaStream_t)stream>>>(pre, gamma, beta, out_f32, (bf16*)out_bf16, mean,
+                                                                   rstd, N, eps, apply_gelu);
+  B2_LAUNCH_CHECK("act_ln_fwd_kernel");
+  return 0;
+}
+
+// dgamma / dbeta are ACCUMULATED into (caller zeroes them)
+B2_API int b2_act_ln_bwd(const float* dout, const float* pre, const float* gamma, const float* mean,
+                         const float* rstd, float* dpre, float* dgamma, float* dbeta, long M, int N, int apply_gelu,
+                         void* stream) {
+  B2_ARG_CHECK(dout && pre && gamma && mean && rstd && dpre && dgamma && dbeta && M > 0 && N > 0,
+               "b2_act_ln_bwd: null pointer or empty");
+  B2_ARG_CHECK(N <= 256 * kMaxCols, "b2_act_ln_bwd: N=%d exceeds %d", N, 256 * kMaxCols);
+  const long cap = (long)b2_num_sms() * 2;
+  act_ln_bwd_kernel<<<(unsigned)(M < cap ? M : cap), 256, 0, (cudaStream_t)stream>>>(dout, pre, gamma, mean, rstd,
+                                                                                    dpre, dgamma, dbeta, M, N,
+                                                                                    apply_gelu);
+  B2_LAUNCH_CHECK("act_ln_bwd_kernel");
+  return 0;
+}
+
+B2_API int b2_sgemm(int trans_a, int trans_b, int M, int N, int K, float alpha, const float* A, long lda,
+                    const float* B, long ldb, float beta, float* C, long ldc, const float* bias, const float* bias2,
+                    void* stream) {
+  B2_ARG_CHECK(A && B && C && M > 0 && N > 0 && K > 0, "b2_sgemm: null pointer or empty shape");
+  dim3 grid(b2_ceil_div(N, TS), b2_ceil_div(M, TS));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!trans_a && !trans_b) sgemm_kernel<false, false><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, bias2);
+  else if (!trans_a && trans_b) sgemm_kernel<false, true><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, bias2);
+  else if (trans_a && !trans_b) sgemm_kernel<true, false><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, bias2);
+  else sgemm_kernel<true, true><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, bias2);
+  B2_LAUNCH_CHECK("sgemm_kernel");
+  return 0;
+}
+
+B2_API int b2_colsum_f32(const float* X, long ld, long M, int N, float* out, int accumulate, void* stream) {
+  B2_ARG_CHECK(X && out && M > 0 && N > 0, "b2_colsum_f32: null pointer or empty");
+  colsum_kernel<<<b2_ceil_div(N, 32), 256, 0, (cudaStream_t)stream>>>(X, ld, M, N, out, accumulate);
+  B2_LAUNCH_CHECK("colsum_kernel");
+  return 0;
+}
+
+B2_API int b2_cast_f32_bf16(const float* src, void* dst, long n, void* stream) {
+  B2_ARG_CHECK(src && dst && n > 0, "b2_cast_f32_bf16: null pointer or empty");
+  long blocks = (n + 255) / 256;
+  const long cap = (long)b2_num_sms() * 8;
+  cast_f32_bf16_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, n);
+  B2_LAUNCH_CHECK("cast_f32_bf16_kernel");
+  return 0;
+}
+
+B2_API int b2_transpose_cast_f32_bf16(const float* src, long ld_src, void* dst, long ld_dst, long R, long Ccols,
+                                      void* stream) {
+  B2_ARG_CHECK(src && dst && R > 0 && Ccols > 0, "b2_transpose_cast_f32_bf16: null pointer or empty");
+  dim3 grid(b2_ceil_div(Ccols, 32), b2_ceil_div(R, 32));
+  transpose_cast_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, ld_src, (bf16*)dst, ld_dst, R, Ccols);
+  B2_LAUNCH_CHECK("transpose_cast_kernel");
+  return 0;
+}

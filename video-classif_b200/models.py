@@ -1,0 +1,267 @@
+"""Drop-in LRCN modules: same constructor arguments, forward contract and state_dict layout as the
+reference classes, executed on the sm_100a kernels.
+
+    SmallCNNLRCN  <- notebook `LRCN` (lrcn/.ipynb_checkpoints/LRCN-ucf50-checkpoint.ipynb nb:148-193)
+    LRCN          <- medsos_lrcn/src/models.py:121-234  (frozen backbone, GELU/LN adapts, LN head)
+    UCF50LRCN     <- lrcn/ucf50-lrcn.py:252-336         (frozen backbone, 3 plain adapts, biLSTM)
+    CrimeLRCN     <- lrcn/lrcn.py:181-305 / lrcn/rgb_lrcn.py:168-263 (one adapt, attribute `lstm`)
+
+`forward(x: float32[B,T,C,H,W]) -> logits[B,num_classes]`.  The torch.nn sub-modules (Conv2d,
+BatchNorm2d, Linear, LayerNorm, LSTM, torchvision ResNet) are PARAMETER CONTAINERS only: they give
+the reference's state_dict keys, shapes and default initialisation; their forward is never
+called -- every layer runs through video_classif_b200.ops.  The reference reads several
+hyper-parameters from module globals (CONF_RNN_LAYER, CONF_RNN_OUT, CONF_CLASSIF_MODE,
+CONF_DROPOUT); here they are explicit keyword arguments with the reference's defaults."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .backbone import ResNetRunner, make_backbone
+
+
+def _check_input(x, seq_len=None):
+    if x.dim() != 5:
+        raise ValueError(f"expected clips [B,T,C,H,W], got shape {tuple(x.shape)}")
+    if not x.is_cuda:
+        raise ops._lib.B200LrcnError("b200-lrcn modules run on an sm_100a CUDA device only (no CPU fallback)")
+
+
+class SmallCNNLRCN(nn.Module):
+    """Notebook `LRCN(num_classes, sequence_length, hidden_size, input_shape=(3,64,64))`.
+
+    precision="fp32": every layer in fp32 (parity 1e-4).  precision="bf16": the layer-0 gate GEMM
+    [B*T,16384]x[16384,4H] and the classifier run on the tcgen05 GEMM (bf16 operands, fp32 accumulate)."""
+
+    def __init__(self, num_classes, sequence_length, hidden_size, input_shape=(3, 64, 64), dropout=0.5,
+                 lstm_layers=2, precision="fp32"):
+        super().__init__()
+        self.sequence_length = sequence_length
+        self.num_classes = num_classes
+        self.hidden_size = hidden_size
+        self.precision = precision
+        self.conv1 = nn.Conv2d(3, 16, kernel_size=3, padding=1)
+        self.conv2 = nn.Conv2d(16, 32, kernel_size=3, padding=1)
+        self.conv3 = nn.Conv2d(32, 64, kernel_size=3, padding=1)
+        self.bn1 = nn.BatchNorm2d(16)
+        self.bn2 = nn.BatchNorm2d(32)
+        self.bn3 = nn.BatchNorm2d(64)
+        self.pool = nn.MaxPool2d(2, 2)
+        self.dropout = nn.Dropout(dropout)
+        cnn_out_size = (input_shape[1] // 4) * (input_shape[2] // 4) * 64
+        self.lstm = nn.LSTM(input_size=cnn_out_size, hidden_size=hidden_size, num_layers=lstm_layers, batch_first=True)
+        self.fc = nn.Linear(hidden_size * sequence_length, num_classes)
+
+    def forward(self, x):
+        _check_input(x)
+        B, T, C, H, W = x.shape
+        bf16 = self.precision == "bf16"
+        y = x.reshape(B * T, C, H, W)
+        if y.dtype != torch.float32:
+            y = y.float()
+        y = ops.conv_bn_relu_pool(y, self.conv1, self.bn1, False, self.training)
+        y = ops.conv_bn_relu_pool(y, self.conv2, self.bn2, True, self.training)
+        y = ops.conv_bn_relu_pool(y, self.conv3, self.bn3, True, self.training)
+        y = ops.dropout(y, self.dropout.p, self.training)
+        feat = y.reshape(B, T, -1)                       # channel-major (c*h*w) flatten, as nb:186
+        out = ops.lstm_forward(feat, self.lstm, bf16=bf16)
+        return ops.linear(out.reshape(B, -1), self.fc.weight, self.fc.bias, bf16=bf16)
+
+
+class _BackboneLRCN(nn.Module):
+    """Shared machinery of the torchvision-backbone variants."""
+
+    def _make_backbone(self, name, pretrained):
+        self.cnn_backbone, feat = make_backbone(name, pretrained)
+        object.__setattr__(self, "_runner", ResNetRunner(self.cnn_backbone))
+        return feat
+
+    def _features(self, x):
+        _check_input(x)
+        B, T, C, H, W = x.shape
+        return self._runner(x.reshape(B * T, C, H, W), self.training).reshape(B, T, -1)
+
+    def __getstate__(self):                 # torch.save(model) (train_eval.py:53) must keep working
+        d = self.__dict__.copy()
+        d.pop("_runner", None)              # kernel-layout weight cache is rebuilt on load
+        return d
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        object.__setattr__(self, "_runner", ResNetRunner(self.cnn_backbone))
+
+
+class LRCN(_BackboneLRCN):
+    """medsos_lrcn/src/models.py:121-234.  Keyword defaults are all_config.py's values
+    (CONF_RNN_LAYER=3, CONF_DROPOUT=0.25, CONF_CLASSIF_MODE='multiclass'); rnn_type must be 'lstm'."""
+
+    def __init__(self, num_classes, sequence_length, hidden_size, rnn_input_size, cnn_backbone="resnet50",
+                 rnn_type="lstm", rnn_out="all", bidirectional=False, rnn_layers=3, dropout=0.25,
+                 classif_mode="multiclass", pretrained=False, precision="bf16"):
+        super().__init__()
+        if rnn_type != "lstm":
+            raise NotImplementedError(f"rnn_type={rnn_type!r}: only the LSTM temporal layer is built (GRU/Mamba are 'next')")
+        self.sequence_length = sequence_length
+        self.hidden_size = hidden_size
+        self.backbone = cnn_backbone
+        self.rnn_type = rnn_type
+        self.rnn_out = rnn_out
+        self.bidirectional = bidirectional
+        self.classif_mode = classif_mode
+        self.precision = precision
+        f = self._make_backbone(cnn_backbone, pretrained)
+        for p in self.cnn_backbone.parameters():
+            p.requires_grad = False
+        self.adapt1 = nn.Linear(f, f // 2)
+        self.bn1 = nn.LayerNorm(f // 2)
+        self.adapt2 = nn.Linear(f // 2, f // 4)
+        self.bn2 = nn.LayerNorm(f // 4)
+        self.adapt3 = nn.Linear(f // 4, rnn_input_size)
+        self.bn3 = nn.LayerNorm(rnn_input_size)
+        self.drop1 = nn.Dropout(p=dropout)
+        self.rnn = nn.LSTM(input_size=rnn_input_size, hidden_size=hidden_size, num_layers=rnn_layers,
+                           bidirectional=bidirectional, batch_first=True)
+        self.rnn_output_size = hidden_size * (2 if bidirectional else 1)
+        fc_in = self.rnn_output_size * (sequence_length if rnn_out == "all" else 1)
+        if classif_mode == "multiclass":
+            self.fc = nn.Linear(fc_in, fc_in // 2)
+            self.fca = nn.Linear(fc_in // 2, fc_in // 4)
+            self.fcb = nn.Linear(fc_in // 4, num_classes)
+            self.bn0 = nn.LayerNorm(fc_in)
+            self.bna = nn.LayerNorm(fc_in // 2)
+            self.bnb = nn.LayerNorm(fc_in // 4)
+            self.drop2 = nn.Dropout(dropout)
+        else:
+            self.fc = nn.ModuleList([nn.Linear(fc_in, 1) for _ in range(num_classes)])
+
+    def forward(self, x):
+        bf16 = self.precision == "bf16"
+        B = x.shape[0]
+        y = self._features(x)
+        tr = self.training
+        lin, aln = ops.linear, ops.act_layernorm
+        y = ops.dropout(aln(lin(y, self.adapt1.weight, self.adapt1.bias, bf16), self.bn1.weight, self.bn1.bias, True, self.bn1.eps), self.drop1.p, tr)
+        y = ops.dropout(aln(lin(y, self.adapt2.weight, self.adapt2.bias, bf16), self.bn2.weight, self.bn2.bias, True, self.bn2.eps), self.drop1.p, tr)
+        y = aln(lin(y, self.adapt3.weight, self.adapt3.bias, bf16), self.bn3.weight, self.bn3.bias, True, self.bn3.eps)
+        r = ops.lstm_forward(y, self.rnn, bf16=bf16)
+        r = r.reshape(B, -1) if self.rnn_out == "all" else r[:, -1, :]
+        if self.classif_mode == "multiclass":
+            o = aln(r, self.bn0.weight, self.bn0.bias, False, self.bn0.eps)
+            o = aln(lin(o, self.fc.weight, self.fc.bias, bf16), self.bna.weight, self.bna.bias, True, self.bna.eps)
+            o = aln(lin(o, self.fca.weight, self.fca.bias, bf16), self.bnb.weight, self.bnb.bias, True, self.bnb.eps)
+            o = ops.dropout(o, self.drop2.p, tr)
+            return lin(o, self.fcb.weight, self.fcb.bias, bf16)
+        return _binary_heads(r, self.fc, bf16)
+
+
+def _binary_heads(r, heads, bf16):
+    """torch.cat([fc_i(x) for fc_i in self.fc], dim=1) (lrcn.py:303) == one GEMM with stacked rows;
+    the stacked weight is a differentiable view of the per-head parameters so fc.{i}.* get their grads."""
+    w = torch.cat([h.weight for h in heads], dim=0)
+    b = torch.cat([h.bias for h in heads], dim=0)
+    return ops.linear(r, w, b, bf16)
+
+
+class UCF50LRCN(_BackboneLRCN):
+    """lrcn/ucf50-lrcn.py:252-336: frozen backbone, adapt1..3 plain Linear, N-layer biLSTM (attribute
+    `rnn`), `fc` Linear or per-class binary heads."""
+
+    def __init__(self, num_classes, sequence_length, hidden_size, rnn_input_size, cnn_backbone="resnet50",
+                 rnn_type="lstm", rnn_out="all", rnn_layers=4, classif_mode="multiclass", pretrained=False,
+                 precision="bf16"):
+        super().__init__()
+        if rnn_type != "lstm":
+            raise NotImplementedError(f"rnn_type={rnn_type!r}: only the LSTM temporal layer is built")
+        self.sequence_length = sequence_length
+        self.hidden_size = hidden_size
+        self.backbone = cnn_backbone
+        self.rnn_type = rnn_type
+        self.rnn_out = rnn_out
+        self.classif_mode = classif_mode
+        self.precision = precision
+        f = self._make_backbone(cnn_backbone, pretrained)
+        for p in self.cnn_backbone.parameters():
+            p.requires_grad = False
+        self.adapt1 = nn.Linear(f, f // 2)
+        self.adapt2 = nn.Linear(f // 2, f // 4)
+        self.adapt3 = nn.Linear(f // 4, rnn_input_size)
+        self.rnn = nn.LSTM(input_size=rnn_input_size, hidden_size=hidden_size, num_layers=rnn_layers,
+                           bidirectional=True, batch_first=True)
+        fc_in = hidden_size * 2 * (sequence_length if rnn_out == "all" else 1)
+        if classif_mode == "multiclass":
+            self.fc = nn.Linear(fc_in, num_classes)
+        else:
+            self.fc = nn.ModuleList([nn.Linear(fc_in, 1) for _ in range(num_classes)])
+
+    def forward(self, x):
+        bf16 = self.precision == "bf16"
+        B = x.shape[0]
+        y = self._features(x)
+        for a in (self.adapt1, self.adapt2, self.adapt3):
+            y = ops.linear(y, a.weight, a.bias, bf16)
+        r = ops.lstm_forward(y, self.rnn, bf16=bf16)
+        r = r.reshape(B, -1) if self.rnn_out == "all" else r[:, -1, :]
+        if self.classif_mode == "multiclass":
+            return ops.linear(r, self.fc.weight, self.fc.bias, bf16)
+        return _binary_heads(r, self.fc, bf16)
+
+
+class CrimeLRCN(_BackboneLRCN):
+    """lrcn/lrcn.py:181-305 (and rgb_lrcn.py:168-263 with classif_mode='multiclass'): backbone,
+    one `adapt` Linear, N-layer biLSTM stored as `lstm`, `fc` or per-class heads.
+    freeze_until_layer / finetune follow freeze_cnn_layers (lrcn.py:246-283); a backbone left
+    trainable is rejected at forward time (no backbone backward kernels yet)."""
+
+    def __init__(self, num_classes, sequence_length, hidden_size, rnn_input_size, cnn_backbone="resnet50",
+                 rnn_out="all", freeze_until_layer=None, rnn_layers=4, classif_mode="multiple_binary",
+                 finetune=False, pretrained=False, precision="bf16"):
+        super().__init__()
+        self.sequence_length = sequence_length
+        self.num_classes = num_classes
+        self.hidden_size = hidden_size
+        self.backbone = cnn_backbone
+        self.rnn_out = rnn_out
+        self.classif_mode = classif_mode
+        self.precision = precision
+        f = self._make_backbone(cnn_backbone, pretrained)
+        self.freeze_cnn_layers(freeze_until_layer, unfreeze_dense_layer=finetune)
+        self.adapt = nn.Linear(f, rnn_input_size)
+        self.lstm = nn.LSTM(input_size=rnn_input_size, hidden_size=hidden_size, num_layers=rnn_layers,
+                            bidirectional=True, batch_first=True)
+        fc_in = hidden_size * 2 * (sequence_length if rnn_out == "all" else 1)
+        if classif_mode == "multiclass":
+            self.fc = nn.Linear(fc_in, num_classes)
+        elif classif_mode == "multiple_binary":
+            self.fc = nn.ModuleList([nn.Linear(fc_in, 1) for _ in range(num_classes)])
+        else:
+            raise ValueError(f"Unsupported CLASSIF_MODE: {classif_mode}")
+
+    def freeze_cnn_layers(self, freeze_until_layer=None, unfreeze_dense_layer=False):
+        if unfreeze_dense_layer:
+            for p in self.cnn_backbone.fc.parameters():     # Identity: nothing to unfreeze (lrcn.py:250-253)
+                p.requires_grad = True
+        elif freeze_until_layer is None:
+            for p in self.cnn_backbone.parameters():
+                p.requires_grad = False
+        else:
+            for i, (_, p) in enumerate(self.cnn_backbone.named_parameters()):
+                p.requires_grad = i > freeze_until_layer
+
+    def forward(self, x):
+        bf16 = self.precision == "bf16"
+        B = x.shape[0]
+        y = self._features(x)
+        y = ops.linear(y, self.adapt.weight, self.adapt.bias, bf16)
+        r = ops.lstm_forward(y, self.lstm, bf16=bf16)
+        r = r.reshape(B, -1) if self.rnn_out == "all" else r[:, -1, :]
+        if self.classif_mode == "multiclass":
+            return ops.linear(r, self.fc.weight, self.fc.bias, bf16)
+        return _binary_heads(r, self.fc, bf16)
+
+
+def count_parameters(model):
+    """train_eval.py:121-130: (trainable, frozen) parameter counts."""
+    tr = sum(p.numel() for p in model.parameters() if p.requires_grad)
+    fr = sum(p.numel() for p in model.parameters() if not p.requires_grad)
+    return tr, fr

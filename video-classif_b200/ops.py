@@ -1,0 +1,435 @@
+"""Host-side operator layer: thin wrappers over the C ABI (include/b200lrcn.h) and the
+torch.autograd.Functions that give the hand-written kernels a backward.
+
+torch is used here for device memory (torch.empty / zeros), streams and autograd bookkeeping only;
+every arithmetic step of the forward and backward pass is a b2_* kernel.  No CPU fallback: all
+entry points raise B200LrcnError when the tensors are not on an sm_100 device."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import call, ptr, stream_ptr
+
+F32, BF16 = torch.float32, torch.bfloat16
+# GEMMs smaller than this many MACs stay on the fp32 SIMT kernel even in bf16 mode
+TC_MIN_MACS = 1 << 22
+
+
+def _chk(*ts):
+    _lib.require_device()
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.B200LrcnError("b200-lrcn operators need CUDA tensors (no CPU fallback)")
+
+
+def _pad8(n):
+    return (n + 7) // 8 * 8
+
+
+# ----------------------------------------------------------------------------------------
+# raw kernel wrappers
+# ----------------------------------------------------------------------------------------
+
+def gemm_tn(A, B, bias=None, out_dtype=F32, relu=False, stats=None, M=None, N=None, K=None, bias2=None):
+    """D[M,N] = A[M,K] @ B[N,K]^T (+bias).  A, B bf16 2-D (row stride multiple of 8)."""
+    _chk(A, B)
+    assert A.dtype == BF16 and B.dtype == BF16
+    M = A.shape[0] if M is None else M
+    K = A.shape[1] if K is None else K
+    N = B.shape[0] if N is None else N
+    D = torch.empty((M, N), device=A.device, dtype=out_dtype)
+    s1, s2 = stats if stats is not None else (None, None)
+    call("b2_gemm_bf16_tn", A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), D.data_ptr(), N, M, N, K,
+         ptr(bias), ptr(bias2), int(out_dtype == BF16), int(relu), ptr(s1), ptr(s2), stream_ptr())
+    return D
+
+
+def conv2d_nhwc(x, w, stride, pad, stats=None):
+    """x [N,H,W,C] bf16, w [Cout,R,S,C] bf16 -> raw conv output [N,P,Q,Cout] bf16 (+ column stats)."""
+    _chk(x, w)
+    N, H, W, C = x.shape
+    Cout, R, S, _ = w.shape
+    P = (H + 2 * pad - R) // stride + 1
+    Q = (W + 2 * pad - S) // stride + 1
+    y = torch.empty((N, P, Q, Cout), device=x.device, dtype=BF16)
+    s1, s2 = stats if stats is not None else (None, None)
+    call("b2_conv2d_nhwc_bf16", x.data_ptr(), N, H, W, C, w.data_ptr(), Cout, R, S, stride, pad, y.data_ptr(), 0, 1,
+         0, ptr(s1), ptr(s2), stream_ptr())
+    return y
+
+
+def sgemm(A, B, trans_a=False, trans_b=False, out=None, alpha=1.0, beta=0.0, M=None, N=None, K=None, bias=None,
+          bias2=None):
+    """fp32 row-major C = alpha op(A) op(B) + beta C on the SIMT kernel."""
+    _chk(A, B)
+    assert A.dtype == F32 and B.dtype == F32 and A.stride(-1) == 1 and B.stride(-1) == 1
+    if M is None:
+        M = A.shape[1] if trans_a else A.shape[0]
+    if K is None:
+        K = A.shape[0] if trans_a else A.shape[1]
+    if N is None:
+        N = B.shape[0] if trans_b else B.shape[1]
+    if out is None:
+        out = torch.empty((M, N), device=A.device, dtype=F32)
+        beta = 0.0
+    call("b2_sgemm", int(trans_a), int(trans_b), M, N, K, float(alpha), A.data_ptr(), A.stride(0), B.data_ptr(),
+         B.stride(0), float(beta), out.data_ptr(), out.stride(0), ptr(bias), ptr(bias2), stream_ptr())
+    return out
+
+
+def colsum(X, out=None, accumulate=False):
+    _chk(X)
+    M, N = X.shape
+    if out is None:
+        out = torch.empty(N, device=X.device, dtype=F32)
+        accumulate = False
+    call("b2_colsum_f32", X.data_ptr(), X.stride(0), M, N, out.data_ptr(), int(accumulate), stream_ptr())
+    return out
+
+
+def cast_bf16(x):
+    _chk(x)
+    x = x.contiguous()
+    y = torch.empty(x.shape, device=x.device, dtype=BF16)
+    call("b2_cast_f32_bf16", x.data_ptr(), y.data_ptr(), x.numel(), stream_ptr())
+    return y
+
+
+def transpose_cast_bf16(x):
+    """fp32 [R,C] (any row stride) -> bf16 [C, pad8(R)] view [:, :R] (row stride padded for TMA)."""
+    _chk(x)
+    assert x.stride(1) == 1
+    R, C = x.shape
+    buf = torch.empty((C, _pad8(R)), device=x.device, dtype=BF16)
+    call("b2_transpose_cast_f32_bf16", x.data_ptr(), x.stride(0), buf.data_ptr(), buf.stride(0), R, C, stream_ptr())
+    return buf[:, :R]
+
+
+def ingest_u8(frames_u8, out_h, out_w, frame_index=None, out_dtype=F32, swap_rb=True, divisor=255.0):
+    """uint8 [F,H0,W0,3] device frames -> [n_out,3,out_h,out_w]; see b2_ingest_u8."""
+    _chk(frames_u8)
+    assert frames_u8.dtype == torch.uint8 and frames_u8.dim() == 4 and frames_u8.shape[-1] == 3
+    frames_u8 = frames_u8.contiguous()
+    Fr, H0, W0, _ = frames_u8.shape
+    n_out = Fr if frame_index is None else frame_index.numel()
+    if frame_index is not None:
+        assert frame_index.dtype == torch.int32 and frame_index.is_cuda
+    out = torch.empty((n_out, 3, out_h, out_w), device=frames_u8.device, dtype=out_dtype)
+    call("b2_ingest_u8", frames_u8.data_ptr(), Fr, H0, W0, H0 * W0 * 3, ptr(frame_index), n_out, out.data_ptr(), out_h,
+         out_w, int(out_dtype == BF16), int(swap_rb), float(divisor), stream_ptr())
+    return out
+
+
+# ----------------------------------------------------------------------------------------
+# autograd: Linear
+# ----------------------------------------------------------------------------------------
+
+def _linear_fwd(x2, weight, bias, bf16, bias2=None):
+    M, K = x2.shape
+    N = weight.shape[0]
+    if bf16 and M * N * K >= TC_MIN_MACS and K % 8 == 0:
+        xa = x2 if x2.dtype == BF16 else cast_bf16(x2)
+        return gemm_tn(xa, cast_bf16(weight), bias=bias, bias2=bias2, out_dtype=F32)
+    xf = x2 if x2.dtype == F32 else x2.float()
+    return sgemm(xf, weight, trans_b=True, bias=bias, bias2=bias2)
+
+
+class LinearFn(torch.autograd.Function):
+    """y = x W^T + b  (nn.Linear).  bf16=True routes large products to the tcgen05 GEMM."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, bf16):
+        _chk(x, weight)
+        x2 = x.reshape(-1, x.shape[-1])
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        y = _linear_fwd(x2, weight, bias, bf16)
+        ctx.save_for_backward(x2, weight)
+        ctx.has_bias = bias is not None
+        ctx.bf16 = bf16
+        ctx.x_shape = x.shape
+        return y.reshape(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, weight = ctx.saved_tensors
+        N, K = weight.shape
+        dy2 = dy.reshape(-1, N)
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        M = dy2.shape[0]
+        dx = dw = db = None
+        big = ctx.bf16 and M * N * K >= TC_MIN_MACS
+        if ctx.needs_input_grad[0]:
+            if big and N % 8 == 0:
+                dx = gemm_tn(cast_bf16(dy2), transpose_cast_bf16(weight), out_dtype=F32)   # [M,N]x[K,N]^T
+            else:
+                dx = sgemm(dy2, weight)
+            dx = dx.reshape(ctx.x_shape)
+        if ctx.needs_input_grad[1]:
+            xf = x2 if x2.dtype == F32 else x2.float()
+            if big:
+                dw = gemm_tn(transpose_cast_bf16(dy2), transpose_cast_bf16(xf), out_dtype=F32)  # [N,M]x[K,M]^T
+            else:
+                dw = sgemm(dy2, xf, trans_a=True)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = colsum(dy2)
+        return dx, dw, db, None
+
+
+def linear(x, weight, bias=None, bf16=False):
+    return LinearFn.apply(x, weight, bias, bf16)
+
+
+# ----------------------------------------------------------------------------------------
+# autograd: (GELU +) LayerNorm
+# ----------------------------------------------------------------------------------------
+
+class ActLayerNormFn(torch.autograd.Function):
+    """LayerNorm(gelu(pre)) (apply_gelu) or LayerNorm(pre): models.py:200-202,222-224."""
+
+    @staticmethod
+    def forward(ctx, pre, gamma, beta, apply_gelu, eps):
+        _chk(pre, gamma, beta)
+        N = pre.shape[-1]
+        p2 = pre.reshape(-1, N).contiguous()
+        M = p2.shape[0]
+        out = torch.empty_like(p2)
+        mean = torch.empty(M, device=pre.device, dtype=F32)
+        rstd = torch.empty(M, device=pre.device, dtype=F32)
+        call("b2_act_ln_fwd", p2.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), 0, mean.data_ptr(),
+             rstd.data_ptr(), M, N, float(eps), int(apply_gelu), stream_ptr())
+        ctx.save_for_backward(p2, gamma, mean, rstd)
+        ctx.apply_gelu = apply_gelu
+        return out.reshape(pre.shape)
+
+    @staticmethod
+    def backward(ctx, dout):
+        p2, gamma, mean, rstd = ctx.saved_tensors
+        M, N = p2.shape
+        d2 = dout.reshape(M, N).contiguous()
+        dpre = torch.empty_like(p2)
+        dgamma = torch.zeros(N, device=p2.device, dtype=F32)
+        dbeta = torch.zeros(N, device=p2.device, dtype=F32)
+        call("b2_act_ln_bwd", d2.data_ptr(), p2.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+             dpre.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), M, N, int(ctx.apply_gelu), stream_ptr())
+        return dpre.reshape(dout.shape), dgamma, dbeta, None, None
+
+
+def act_layernorm(pre, gamma, beta, apply_gelu=True, eps=1e-5):
+    return ActLayerNormFn.apply(pre, gamma, beta, apply_gelu, eps)
+
+
+# ----------------------------------------------------------------------------------------
+# autograd: dropout
+# ----------------------------------------------------------------------------------------
+
+class DropoutFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, p, seed):
+        _chk(x)
+        xc = x.contiguous()
+        y = torch.empty_like(xc)
+        call("b2_dropout_f32", xc.data_ptr(), y.data_ptr(), xc.numel(), float(p), int(seed), stream_ptr())
+        ctx.p, ctx.seed = p, seed
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dc = dy.contiguous()
+        dx = torch.empty_like(dc)
+        call("b2_dropout_f32", dc.data_ptr(), dx.data_ptr(), dc.numel(), float(ctx.p), int(ctx.seed), stream_ptr())
+        return dx, None, None
+
+
+_dropout_counter = [0]
+
+
+def dropout(x, p, training):
+    """nn.Dropout(p): identity in eval mode or when p == 0."""
+    if not training or p <= 0.0:
+        return x
+    _dropout_counter[0] += 1
+    seed = (torch.initial_seed() * 1000003 + _dropout_counter[0]) & 0x7FFFFFFFFFFFFFFF
+    return DropoutFn.apply(x, float(p), seed)
+
+
+# ----------------------------------------------------------------------------------------
+# autograd: one LSTM layer (all directions)
+# ----------------------------------------------------------------------------------------
+
+class LSTMLayerFn(torch.autograd.Function):
+    """One nn.LSTM layer, batch_first, zero initial state; params = (w_ih, w_hh, b_ih, b_hh) per
+    direction (forward first, then `_reverse`).  Output [B,T,dirs*H] = cat(fwd, bwd)."""
+
+    @staticmethod
+    def forward(ctx, x, hidden, bf16, need_grad, *params):
+        _chk(x, *params)
+        B, T, In = x.shape
+        dirs = len(params) // 4
+        H = hidden
+        xc = x.contiguous()
+        x2 = xc.reshape(B * T, In)
+        out = torch.empty((B, T, dirs * H), device=x.device, dtype=F32)
+        saved = []
+        for d in range(dirs):
+            w_ih, w_hh, b_ih, b_hh = params[4 * d:4 * d + 4]
+            G = _linear_fwd(x2, w_ih, b_ih, bf16, bias2=b_hh)   # hoisted gate GEMM for all T steps
+            if need_grad:
+                gates = torch.empty((B, T, 4 * H), device=x.device, dtype=F32)
+                cst = torch.empty((B, T, H), device=x.device, dtype=F32)
+            else:
+                gates = cst = None
+            o = out[:, :, d * H:]
+            call("b2_lstm_seq_fwd", G.data_ptr(), w_hh.data_ptr(), o.data_ptr(), dirs * H, ptr(gates), ptr(cst), B, T,
+                 H, int(d == 1), stream_ptr())
+            saved += [gates, cst]
+        if need_grad:
+            ctx.save_for_backward(x2, out, *saved, *params)
+        ctx.dims = (B, T, In, H, dirs)
+        ctx.bf16 = bf16
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, T, In, H, dirs = ctx.dims
+        x2, out = ctx.saved_tensors[:2]
+        saved = ctx.saved_tensors[2:2 + 2 * dirs]
+        params = ctx.saved_tensors[2 + 2 * dirs:]
+        dout = dout.contiguous()
+        grads = []
+        big = ctx.bf16 and B * T * 4 * H * In >= TC_MIN_MACS and H % 2 == 0
+        H4 = 4 * H
+        dG_all = torch.empty((B * T, dirs * H4), device=dout.device, dtype=F32)   # [dG_fwd | dG_bwd]
+        xf = x2 if x2.dtype == F32 else x2.float()
+        for d in range(dirs):
+            w_ih, w_hh, b_ih, b_hh = params[4 * d:4 * d + 4]
+            gates, cst = saved[2 * d:2 * d + 2]
+            dG = dG_all[:, d * H4:(d + 1) * H4]
+            dWhh = torch.zeros_like(w_hh)
+            do = dout[:, :, d * H:]
+            oo = out[:, :, d * H:]
+            call("b2_lstm_seq_bwd", do.data_ptr(), dirs * H, oo.data_ptr(), dirs * H, gates.data_ptr(), cst.data_ptr(),
+                 w_hh.data_ptr(), dG.data_ptr(), dirs * H4, dWhh.data_ptr(), B, T, H, int(d == 1), stream_ptr())
+            if big:
+                dWih = gemm_tn(transpose_cast_bf16(dG), transpose_cast_bf16(xf), out_dtype=F32)
+            else:
+                dWih = sgemm(dG, xf, trans_a=True)
+            db = colsum(dG)
+            grads += [dWih, dWhh, db, db]
+        dx = None
+        if ctx.needs_input_grad[0]:
+            # dx = [dG_fwd | dG_bwd] @ [W_ih ; W_ih_reverse]  -- one GEMM over K = dirs*4H
+            w_cat = params[0] if dirs == 1 else torch.cat([params[0], params[4]], dim=0)
+            if big:
+                dx = gemm_tn(cast_bf16(dG_all), transpose_cast_bf16(w_cat), out_dtype=F32)
+            else:
+                dx = sgemm(dG_all, w_cat)
+            dx = dx.reshape(B, T, In)
+        return (dx, None, None, None, *grads)
+
+
+def lstm_forward(x, lstm_module, bf16=False):
+    """Runs a torch.nn.LSTM *parameter container* (batch_first, no proj, dropout 0) on the
+    persistent kernels.  Returns the [B,T,dirs*H] output of the last layer."""
+    assert lstm_module.batch_first and lstm_module.proj_size == 0
+    dirs = 2 if lstm_module.bidirectional else 1
+    H = lstm_module.hidden_size
+    need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in lstm_module.parameters()))
+    y = x
+    for layer in range(lstm_module.num_layers):
+        params = []
+        for d in range(dirs):
+            sfx = f"_l{layer}" + ("_reverse" if d == 1 else "")
+            params += [getattr(lstm_module, "weight_ih" + sfx), getattr(lstm_module, "weight_hh" + sfx),
+                       getattr(lstm_module, "bias_ih" + sfx), getattr(lstm_module, "bias_hh" + sfx)]
+        y = LSTMLayerFn.apply(y, H, bf16, need_grad, *params)
+    return y
+
+
+# ----------------------------------------------------------------------------------------
+# autograd: small-CNN block  conv3x3 -> BatchNorm2d -> ReLU [-> MaxPool2d(2,2)]   (fp32 NCHW)
+# ----------------------------------------------------------------------------------------
+
+class ConvBnReluPoolFn(torch.autograd.Function):
+    """`pool(F.relu(bn(conv(x))))` of the notebook LRCN (nb:181-183) as conv + statistics +
+    fused BN/ReLU/pool kernels, with the matching backward (pool/ReLU mask recomputed, two-pass BN
+    backward, conv data- and weight-gradient kernels)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, gamma, beta, running_mean, running_var, train, pool, momentum, eps):
+        _chk(x, w, gamma, beta)
+        x = x.contiguous()
+        N, Cin, H, W = x.shape
+        Cout = w.shape[0]
+        dev = x.device
+        st = stream_ptr()
+        z = torch.empty((N, Cout, H, W), device=dev, dtype=F32)
+        call("b2_conv3x3_f32", x.data_ptr(), w.data_ptr(), ptr(b), z.data_ptr(), N, Cin, Cout, H, W, 0, st)
+        scale = torch.empty(Cout, device=dev, dtype=F32)
+        shift = torch.empty_like(scale)
+        mean = torch.empty_like(scale)
+        rstd = torch.empty_like(scale)
+        count = N * H * W
+        if train:
+            sums = torch.zeros((2, Cout), device=dev, dtype=torch.float64)
+            call("b2_bn2d_stats_f32", z.data_ptr(), N, Cout, H * W, sums[0].data_ptr(), sums[1].data_ptr(), st)
+            call("b2_bn2d_finalize", sums[0].data_ptr(), sums[1].data_ptr(), count, gamma.data_ptr(), beta.data_ptr(),
+                 ptr(running_mean), ptr(running_var), float(momentum), float(eps), 1, scale.data_ptr(),
+                 shift.data_ptr(), mean.data_ptr(), rstd.data_ptr(), Cout, st)
+        else:
+            call("b2_bn2d_finalize", 0, 0, count, gamma.data_ptr(), beta.data_ptr(), running_mean.data_ptr(),
+                 running_var.data_ptr(), float(momentum), float(eps), 0, scale.data_ptr(), shift.data_ptr(),
+                 mean.data_ptr(), rstd.data_ptr(), Cout, st)
+        Ho, Wo = (H // 2, W // 2) if pool else (H, W)
+        y = torch.empty((N, Cout, Ho, Wo), device=dev, dtype=F32)
+        call("b2_bn2d_act_pool_fwd_f32", z.data_ptr(), scale.data_ptr(), shift.data_ptr(), y.data_ptr(), 0, N, Cout, H,
+             W, int(pool), st)
+        ctx.save_for_backward(x, w, z, scale, shift, mean, rstd, gamma)
+        ctx.cfg = (train, pool, b is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, z, scale, shift, mean, rstd, gamma = ctx.saved_tensors
+        train, pool, has_bias = ctx.cfg
+        N, Cin, H, W = x.shape
+        Cout = w.shape[0]
+        dev = x.device
+        st = stream_ptr()
+        dy = dy.contiguous()
+        s = torch.zeros((2, Cout), device=dev, dtype=torch.float64)
+        call("b2_bn2d_act_pool_bwd_reduce_f32", z.data_ptr(), dy.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+             mean.data_ptr(), rstd.data_ptr(), N, Cout, H, W, int(pool), s[0].data_ptr(), s[1].data_ptr(), st)
+        dz = torch.empty_like(z)
+        call("b2_bn2d_act_pool_bwd_apply_f32", z.data_ptr(), dy.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+             mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), s[0].data_ptr(), s[1].data_ptr(), N * H * W,
+             int(train), dz.data_ptr(), N, Cout, H, W, int(pool), st)
+        dbeta = torch.empty(Cout, device=dev, dtype=F32)
+        dgamma = torch.empty(Cout, device=dev, dtype=F32)
+        call("b2_f64_to_f32", s[0].data_ptr(), dbeta.data_ptr(), Cout, 0, st)
+        call("b2_f64_to_f32", s[1].data_ptr(), dgamma.data_ptr(), Cout, 0, st)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            call("b2_conv3x3_f32", dz.data_ptr(), w.data_ptr(), 0, dx.data_ptr(), N, Cout, Cin, H, W, 1, st)
+        if ctx.needs_input_grad[1]:
+            dw = torch.zeros_like(w)
+            call("b2_conv3x3_wgrad_f32", x.data_ptr(), dz.data_ptr(), dw.data_ptr(), N, Cin, Cout, H, W, st)
+        if has_bias and ctx.needs_input_grad[2]:
+            sb = torch.zeros(Cout, device=dev, dtype=torch.float64)
+            call("b2_bn2d_stats_f32", dz.data_ptr(), N, Cout, H * W, sb.data_ptr(), 0, st)
+            db = torch.empty(Cout, device=dev, dtype=F32)
+            call("b2_f64_to_f32", sb.data_ptr(), db.data_ptr(), Cout, 0, st)
+        return dx, dw, db, dgamma, dbeta, None, None, None, None, None, None
+
+
+def conv_bn_relu_pool(x, conv, bn, pool, training):
+    """conv: nn.Conv2d(k=3,pad=1) container, bn: nn.BatchNorm2d container."""
+    train = training or not bn.track_running_stats
+    y = ConvBnReluPoolFn.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, train,
+                               pool, bn.momentum if bn.momentum is not None else 0.1, bn.eps)
+    if training and bn.track_running_stats:
+        bn.num_batches_tracked += 1
+    return y
