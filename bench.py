@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""LRCN train clips/s on B200 (BASELINE.json metric) -- see DESIGN.md section "Measurement".
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (hand-written sm_100a kernels)
+  python bench.py --impl reference ...                           the reference path on the host CPU cores
+
+Workload (BASELINE.json configs[1]): medsos LRCN classifier -- frozen ResNet-50 frame encoder in
+train-mode BN, 3x(Linear+GELU+LayerNorm) adapts, 3-layer LSTM H=32 over T frames, LN/GELU head,
+4 classes -- 16 frames x 112x112 RGB, 64 clips per GPU, full train step
+(zero_grad, forward, CrossEntropy, backward, Adam).  Synthetic clips, random-init weights.
+
+One JSON line on stdout (rank 0).  `value` = clips/s with the float32 clips resident in HBM;
+`e2e` = the same step through the public host API: pinned uint8 host clips -> H2D -> ingest kernel ->
+train step -> loss read back, every step.  N > 1: one process per GPU (torchrun), clips sharded by
+rank, gradient buckets all-reduced over NCCL, time = max over ranks."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(name="medsos-lrcn-resnet50", frames=16, size=112, clips_per_gpu=64, num_classes=4, hidden=32,
+                rnn_input=8, rnn_layers=3)
+METRIC = "lrcn_train_clips_per_sec"
+RESNET50_GFLOP_PER_FRAME_112 = 2.152     # SURVEY.md section 8(d), torch.utils.flop_counter, fwd
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-clips", type=int, default=8, help="clips per step of the CPU arms (bounded sample)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs only)")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["bf16_tflops_sustained"], d["hbm_gbs"], "measured (MEASURED_PEAKS.json, sustained)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        self.stop_flag = True
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 6:
+                continue
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arms: the oracle port of the reference train step on the host cores
+# ------------------------------------------------------------------------------------------------
+
+def cpu_reference_step_rate(clips, steps, warmup):
+    """zero_grad -> forward -> CE -> backward -> Adam of the reference topology, fp32, torch CPU
+    kernels with every host thread (the reference's own execution engine), on `clips` clips/step."""
+    import torch
+    import video_classif_b200 as vc
+    from oracle import lrcn_oracle as O
+    W = WORKLOAD
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    shell = vc.LRCN(W["num_classes"], W["frames"], W["hidden"], W["rnn_input"], cnn_backbone="resnet50",
+                    rnn_layers=W["rnn_layers"], dropout=0.0)        # parameter container only (CPU)
+    sd = {k: v.detach().clone() for k, v in shell.state_dict().items()}
+    train_keys = [k for k, p in shell.named_parameters() if p.requires_grad]
+    for k in train_keys:
+        sd[k].requires_grad_(True)
+    opt = torch.optim.Adam([sd[k] for k in train_keys], lr=1e-4)
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randint(0, 256, (clips, W["frames"], 3, W["size"], W["size"]), generator=g).float() / 255.0
+    y = torch.randint(0, W["num_classes"], (clips,), generator=g)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        logits, ns = O.medsos_lrcn_forward(sd, x, "resnet50", W["hidden"], W["rnn_layers"], False)
+        loss = O.cross_entropy_mean(logits, y)
+        loss.backward()
+        opt.step()
+        for k, v in ns.items():
+            sd[k] = v
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    times.sort()
+    med = times[len(times) // 2]
+    return clips / med, med, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 5))
+    warm = max(1, min(args.warmup, 2))
+    rate, sec, cores = cpu_reference_step_rate(args.cpu_clips, steps, warm)
+    W = WORKLOAD
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "clips/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{W['name']}: {W['frames']} frames x {W['size']}x{W['size']}, train step, "
+                               f"{args.cpu_clips} clips/step (bounded CPU sample of the 64-clip batch)"},
+        "cpu_baseline": {"value": rate, "unit": "clips/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.cpu_clips} clips/step x {steps} steps, oracle port (torch CPU fp32 kernels)"},
+        "e2e": {"value": rate, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import video_classif_b200 as vc
+    from video_classif_b200 import _lib, ops
+    from video_classif_b200.ingest import ingest_batch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W = WORKLOAD
+    B, T, S = W["clips_per_gpu"], W["frames"], W["size"]
+    torch.manual_seed(0)
+    model = vc.LRCN(W["num_classes"], T, W["hidden"], W["rnn_input"], cnn_backbone="resnet50",
+                    rnn_layers=W["rnn_layers"], dropout=0.25, precision="bf16").to(dev).train()
+    dp = None
+    if world > 1:
+        from video_classif_b200.dp import GradBucketAllReduce, broadcast_parameters
+        broadcast_parameters(model)
+        dp = GradBucketAllReduce(model)
+    opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-4, fused=True)
+    g = torch.Generator().manual_seed(1234 + rank)
+    NBUF = 4                                                   # distinct synthetic batches, cycled
+    host_u8 = [torch.randint(0, 256, (B, T, S, S, 3), generator=g, dtype=torch.uint8).pin_memory() for _ in range(NBUF)]
+    host_y = [torch.randint(0, W["num_classes"], (B,), generator=g).pin_memory() for _ in range(NBUF)]
+    dev_x = [ingest_batch(h.to(dev), S, S) for h in host_u8]   # float32 [B,T,3,S,S] resident in HBM
+    dev_y = [h.to(dev) for h in host_y]
+    l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def step(x, y):
+        opt.zero_grad(set_to_none=True)
+        loss = torch.nn.functional.cross_entropy(model(x), y)
+        loss.backward()
+        if dp is not None:
+            dp.finish()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- resident-input throughput (`value`) ----------------
+    for i in range(args.warmup):
+        step(dev_x[i % NBUF], dev_y[i % NBUF])
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(dev_x[i % NBUF], dev_y[i % NBUF])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - n0
+    clocks = sampler.summary() if sampler else None
+    t = torch.tensor([ms, float(launches)], device=dev, dtype=torch.float64)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, launches = tmax[0].item(), tsum[1].item()
+    ms_per_step = ms / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+
+    # ---------------- end to end from pinned host uint8 clips (`e2e`) ----------------
+    copy_stream = torch.cuda.Stream(device=dev)
+    stage_u8 = [torch.empty((B, T, S, S, 3), dtype=torch.uint8, device=dev) for _ in range(2)]
+    stage_y = [torch.empty((B,), dtype=torch.int64, device=dev) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def prefetch(i):
+        s = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[s])
+            stage_u8[s].copy_(host_u8[i % NBUF], non_blocking=True)
+            stage_y[s].copy_(host_y[i % NBUF], non_blocking=True)
+            ready[s].record(copy_stream)
+
+    def e2e_loop(n):
+        for s in range(2):
+            freed[s].record(torch.cuda.current_stream())
+        prefetch(0)
+        for i in range(n):
+            s = i % 2
+            if i + 1 < n:
+                prefetch(i + 1)                                  # overlaps this step's compute
+            torch.cuda.current_stream().wait_event(ready[s])
+            x = ingest_batch(stage_u8[s], S, S)                  # K1: uint8 -> float32 CHW /255 on the GPU
+            loss = step(x, stage_y[s])
+            freed[s].record(torch.cuda.current_stream())
+            loss_host.copy_(loss.detach(), non_blocking=True)    # D2H read of the step's loss
+        torch.cuda.synchronize()
+
+    if args.no_e2e:
+        ms_e2e = float("nan")
+    else:
+        e2e_loop(2)
+        barrier()
+        e0.record()
+        e2e_loop(args.steps)
+        e1.record()
+        barrier()
+        ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = t[0].item()
+    e2e_value = world * B / (ms_e2e / args.steps * 1e-3)
+    h2d = host_u8[0].numel() + host_y[0].numel() * 8
+    d2h = 4
+
+    # ---------------- roofline of the dominant kernel (tcgen05 GEMM / implicit-GEMM conv) -----------
+    roof = None
+    tflops_peak, hbm_peak, peak_src = peaks()
+    if not args.no_roofline and rank == 0:
+        events = []
+        orig_gemm, orig_conv = ops.gemm_tn, ops.conv2d_nhwc
+        import video_classif_b200.backbone as bb
+
+        def timed(fn, flops_of):
+            def wrap(*a, **k):
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                out = fn(*a, **k)
+                e.record()
+                events.append((s, e, flops_of(a, k, out)))
+                return out
+            return wrap
+
+        def gemm_flops(a, k, out):
+            return 2.0 * out.shape[0] * out.shape[1] * a[0].shape[1]
+
+        def conv_flops(a, k, out):
+            w = a[1]
+            return 2.0 * out.numel() * w.shape[1] * w.shape[2] * w.shape[3]
+
+        ops.gemm_tn = timed(orig_gemm, gemm_flops)
+        ops.conv2d_nhwc = timed(orig_conv, conv_flops)
+        bb.gemm_tn, bb.conv2d_nhwc = ops.gemm_tn, ops.conv2d_nhwc
+        try:
+            for i in range(2):
+                events.clear()
+                l2_flush.zero_()
+                step(dev_x[i % NBUF], dev_y[i % NBUF])
+                torch.cuda.synchronize()
+        finally:
+            ops.gemm_tn, ops.conv2d_nhwc = orig_gemm, orig_conv
+            bb.gemm_tn, bb.conv2d_nhwc = orig_gemm, orig_conv
+        tot_ms = sum(s.elapsed_time(e) for s, e, _ in events)
+        tot_fl = sum(f for _, _, f in events)
+        achieved = tot_fl / (tot_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "achieved": achieved, "peak": tflops_peak, "unit": "TFLOP/s",
+                "frac": achieved / tflops_peak, "traffic": None, "kernel": "gemm_tc_kernel (tcgen05 GEMM + implicit-GEMM conv)",
+                "launches_per_step": len(events), "kernel_ms_per_step": tot_ms, "algorithmic_gflop_per_step": tot_fl / 1e9,
+                "share_of_step": tot_ms / ms_per_step, "peak_source": peak_src}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, sec, cores = cpu_reference_step_rate(args.cpu_clips, 3, 1)
+        cpu = {"value": rate, "unit": "clips/s", "cores": cores, "kind": "port",
+               "sample": f"{args.cpu_clips} clips/step x 3 steps of the same train step, oracle port (torch CPU fp32 kernels)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{W['name']}: {T} frames x {S}x{S}, {B} clips/GPU, frozen ResNet-50 (train-mode BN) + "
+                                   f"GELU/LN adapts + {W['rnn_layers']}-layer LSTM H={W['hidden']} + head, full train step "
+                                   "(fwd, CE, bwd, Adam); BASELINE.json configs[1]",
+                       "global_batch": world * B, "parallelism": f"dp{world}",
+                       "timing": f"{NBUF} distinct input batches cycled; per-step working set (~6 GB activations) exceeds L2"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps,
+                    "path": "pinned uint8 host clips -> H2D (copy stream, double buffered) -> b2_ingest_u8 -> train step -> loss D2H"},
+            "gpu_launches": int(launches),
+            "gflop_per_clip_fwd_backbone": RESNET50_GFLOP_PER_FRAME_112 * T,
+        }
+        if roof:
+            line["roofline"] = roof
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

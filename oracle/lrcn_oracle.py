@@ -278,48 +278,69 @@ def _bn(x, sd, name, train, new_stats):
                             sd[name + ".running_mean"], sd[name + ".running_var"])
 
 
+def _bf16(t):
+    return t.bfloat16().float()
+
+
 def resnet_features(sd: Dict[str, torch.Tensor], x: torch.Tensor, arch: str, train: bool = True,
-                    prefix: str = "cnn_backbone."):
+                    prefix: str = "cnn_backbone.", emulate_bf16: bool = False, return_stages: bool = False):
     """torchvision.models.resnet{18,34,50,101} with fc=Identity (models.py:133-137): conv7x7/2,
     BN, ReLU, maxpool3x3/2, 4 stages of basic / bottleneck (v1.5: stride on the 3x3) blocks,
-    global average pool.  Train-mode BN even when frozen (train_eval.py:12)."""
+    global average pool.  Train-mode BN even when frozen (train_eval.py:12).
+
+    emulate_bf16=True restates the SAME graph with bf16 storage at the points the B200 path rounds
+    (conv operands, raw conv outputs, activation outputs; fp32 accumulation, fp32 BN statistics)
+    -- the yardstick for how far any bf16 execution of this (chaotic, randomly initialised,
+    batch-statistics) network may drift from the fp32 reference.
+    return_stages=True additionally returns the spatial mean of the stem and of each stage."""
     kind, depths = _RESNET_CFG[arch]
     g = lambda k: sd[prefix + k]
     sdp = {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
     ns: Dict[str, torch.Tensor] = {}
-    y = F.conv2d(x, g("conv1.weight"), None, stride=2, padding=3)
+    rnd = _bf16 if emulate_bf16 else (lambda t: t)
+
+    def conv(inp, w, **kw):
+        return rnd(F.conv2d(rnd(inp), rnd(w), None, **kw))
+
+    stages = []
+    y = conv(x, g("conv1.weight"), stride=2, padding=3)
     y = torch.relu(_bn(y, sdp, "bn1", train, ns))
-    y = F.max_pool2d(y, 3, 2, 1)
+    y = rnd(F.max_pool2d(y, 3, 2, 1))
+    stages.append(y.mean(dim=(2, 3)))
     for si, depth in enumerate(depths):
         for bi in range(depth):
             p = f"layer{si + 1}.{bi}"
             stride = 2 if (si > 0 and bi == 0) else 1
             idt = y
             if kind == "basic":
-                o = F.conv2d(y, sdp[p + ".conv1.weight"], None, stride=stride, padding=1)
-                o = torch.relu(_bn(o, sdp, p + ".bn1", train, ns))
-                o = F.conv2d(o, sdp[p + ".conv2.weight"], None, padding=1)
+                o = conv(y, sdp[p + ".conv1.weight"], stride=stride, padding=1)
+                o = rnd(torch.relu(_bn(o, sdp, p + ".bn1", train, ns)))
+                o = conv(o, sdp[p + ".conv2.weight"], padding=1)
                 o = _bn(o, sdp, p + ".bn2", train, ns)
             else:
-                o = F.conv2d(y, sdp[p + ".conv1.weight"], None)
-                o = torch.relu(_bn(o, sdp, p + ".bn1", train, ns))
-                o = F.conv2d(o, sdp[p + ".conv2.weight"], None, stride=stride, padding=1)
-                o = torch.relu(_bn(o, sdp, p + ".bn2", train, ns))
-                o = F.conv2d(o, sdp[p + ".conv3.weight"], None)
+                o = conv(y, sdp[p + ".conv1.weight"])
+                o = rnd(torch.relu(_bn(o, sdp, p + ".bn1", train, ns)))
+                o = conv(o, sdp[p + ".conv2.weight"], stride=stride, padding=1)
+                o = rnd(torch.relu(_bn(o, sdp, p + ".bn2", train, ns)))
+                o = conv(o, sdp[p + ".conv3.weight"])
                 o = _bn(o, sdp, p + ".bn3", train, ns)
             if (p + ".downsample.0.weight") in sdp:
-                idt = F.conv2d(y, sdp[p + ".downsample.0.weight"], None, stride=stride)
+                idt = conv(y, sdp[p + ".downsample.0.weight"], stride=stride)
                 idt = _bn(idt, sdp, p + ".downsample.1", train, ns)
-            y = torch.relu(o + idt)
+            y = rnd(torch.relu(o + idt))
+        stages.append(y.mean(dim=(2, 3)))
     feat = y.mean(dim=(2, 3))
-    return feat, {prefix + k: v for k, v in ns.items()}
+    ns = {prefix + k: v for k, v in ns.items()}
+    if return_stages:
+        return feat, ns, stages
+    return feat, ns
 
 
 def medsos_lrcn_forward(sd, x, arch, hidden, rnn_layers, bidirectional, rnn_out="all",
-                        train=True):
+                        train=True, emulate_bf16_backbone=False):
     """medsos_lrcn/src/models.py:188-234 with rnn_type='lstm', multiclass head, dropout p=0."""
     B, T, C, H, W = x.shape
-    feat, ns = resnet_features(sd, x.reshape(B * T, C, H, W), arch, train)
+    feat, ns = resnet_features(sd, x.reshape(B * T, C, H, W), arch, train, emulate_bf16=emulate_bf16_backbone)
     y = feat.reshape(B, T, -1)
     for k in (1, 2, 3):
         y = y @ sd[f"adapt{k}.weight"].t() + sd[f"adapt{k}.bias"]
@@ -334,12 +355,12 @@ def medsos_lrcn_forward(sd, x, arch, hidden, rnn_layers, bidirectional, rnn_out=
 
 def simple_lrcn_forward(sd, x, arch, hidden, rnn_layers, adapt_names=("adapt1", "adapt2", "adapt3"),
                         rnn_prefix="rnn.", rnn_out="all", num_heads: Optional[int] = None,
-                        train=True):
+                        train=True, emulate_bf16_backbone=False):
     """lrcn/ucf50-lrcn.py:304-336 (three plain Linear adapts, attribute `rnn`) and
     lrcn/lrcn.py:285-305 / rgb_lrcn.py:247-263 (one `adapt`, attribute `lstm`); always
     bidirectional.  num_heads!=None -> per-class binary heads fc.{i} concatenated (lrcn.py:303)."""
     B, T, C, H, W = x.shape
-    feat, ns = resnet_features(sd, x.reshape(B * T, C, H, W), arch, train)
+    feat, ns = resnet_features(sd, x.reshape(B * T, C, H, W), arch, train, emulate_bf16=emulate_bf16_backbone)
     y = feat.reshape(B, T, -1)
     for a in adapt_names:
         y = y @ sd[a + ".weight"].t() + sd[a + ".bias"]

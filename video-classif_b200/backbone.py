@@ -77,8 +77,15 @@ class ResNetRunner:
              stream_ptr())
         return x   # in place
 
-    def __call__(self, x, training: bool):
-        """x: [N,3,H,W] fp32 or bf16 (NCHW, the reference's frame tensor) -> [N, feat] fp32."""
+    def _pool(self, y):
+        Nn, Hh, Ww, C = y.shape
+        feat = torch.empty((Nn, C), device=y.device, dtype=F32)
+        call("b2_avgpool_nhwc", y.data_ptr(), feat.data_ptr(), 0, Nn, Hh * Ww, C, stream_ptr())
+        return feat
+
+    def __call__(self, x, training: bool, return_stages: bool = False):
+        """x: [N,3,H,W] fp32 or bf16 (NCHW, the reference's frame tensor) -> [N, feat] fp32.
+        return_stages=True also returns the spatial means after the stem and each stage (tests)."""
         _lib.require_device()
         net = self.net
         if torch.is_grad_enabled() and any(p.requires_grad for p in net.parameters()):
@@ -118,6 +125,7 @@ class ResNetRunner:
              net.bn1.running_mean.data_ptr(), net.bn1.running_var.data_ptr(), float(net.bn1.eps), float(mom),
              int(train), st)
         del raw
+        stages = [self._pool(y)] if return_stages else None
         # ---- residual stages ----
         for li in range(1, 5):
             layer = getattr(net, f"layer{li}")
@@ -145,10 +153,12 @@ class ResNetRunner:
                                  rstats=stats_of(dbn))
                 else:
                     y = self._bn(o, last_bn, stats_of(last_bn), cnt, train, res_mode=1, res=y)
+            if return_stages:
+                stages.append(self._pool(y))
         # ---- head ----
-        Nn, Hh, Ww, C = y.shape
-        feat = torch.empty((Nn, C), device=dev, dtype=F32)
-        call("b2_avgpool_nhwc", y.data_ptr(), feat.data_ptr(), 0, Nn, Hh * Ww, C, st)
+        feat = self._pool(y)
         if train:
             torch._foreach_add_([b.num_batches_tracked for b in bns if b.num_batches_tracked is not None], 1)
+        if return_stages:
+            return feat, stages
         return feat
