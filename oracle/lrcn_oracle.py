@@ -264,6 +264,9 @@ _RESNET_CFG = {
     "resnet34": ("basic", [3, 4, 6, 3]),
     "resnet50": ("bottleneck", [3, 4, 6, 3]),
     "resnet101": ("bottleneck", [3, 4, 23, 3]),
+    # test-only shallow variants (one block per stage: every block geometry, little chaos)
+    "resnet10": ("basic", [1, 1, 1, 1]),
+    "resnet14": ("bottleneck", [1, 1, 1, 1]),
 }
 
 

@@ -24,7 +24,7 @@ def gemm_case(M, N, K, bias=True, out_bf16=True, relu=False, stats=False, reps=0
     D = torch.full((M, N), float("nan"), device=dev, dtype=torch.bfloat16 if out_bf16 else torch.float32)
     s1 = torch.zeros(N, device=dev) if stats else None
     s2 = torch.zeros(N, device=dev) if stats else None
-    args = (A.data_ptr(), K, B.data_ptr(), K, D.data_ptr(), N, M, N, K, _lib.ptr(b), int(out_bf16), int(relu),
+    args = (A.data_ptr(), K, B.data_ptr(), K, D.data_ptr(), N, M, N, K, _lib.ptr(b), 0, int(out_bf16), int(relu),
             _lib.ptr(s1), _lib.ptr(s2), st())
     _lib.call("b2_gemm_bf16_tn", *args)
     torch.cuda.synchronize()
@@ -43,7 +43,7 @@ def gemm_case(M, N, K, bias=True, out_bf16=True, relu=False, stats=False, reps=0
         for _ in range(reps): _lib.call("b2_gemm_bf16_tn", *args)
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
-        msg += f"  {ms*1e3:.1f} us  {2.0*M*N*K/ms/1e9:.1f} TFLOP/s"
+        msg += f"  {ms*1e3:.1f} us  {2.0*M*N*K/ms/1e9:.1f} TFLOP/s  {(M*K+M*N)*2/ms/1e6:.0f} GB/s"
     print(msg, flush=True)
     return e
 
@@ -95,6 +95,15 @@ if which in ("all", "gemm"):
     gemm_case(1505280, 256, 64, bias=False, stats=True, reps=5)
     gemm_case(1505280, 64, 256, bias=False, stats=True, reps=5)
     gemm_case(94080, 2048, 512, bias=False, stats=True, reps=5)
+if which in ("all", "layers"):
+    for st_ in (False, True):
+        gemm_case(802816, 256, 64, bias=False, stats=st_, reps=5)
+        gemm_case(802816, 64, 256, bias=False, stats=st_, reps=5)
+        gemm_case(200704, 512, 128, bias=False, stats=st_, reps=5)
+        gemm_case(200704, 128, 512, bias=False, stats=st_, reps=5)
+        gemm_case(50176, 1024, 256, bias=False, stats=st_, reps=5)
+        gemm_case(16384, 2048, 512, bias=False, stats=st_, reps=5)
+        gemm_case(3211264, 64, 160, bias=False, stats=st_, reps=5)
 if which in ("all", "conv"):
     conv_case(2, 8, 8, 64, 64, 1, 1, 0)
     conv_case(2, 8, 8, 64, 64, 3, 1, 1)

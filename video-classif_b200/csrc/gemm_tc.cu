@@ -160,13 +160,16 @@ struct EpiParams {
   int relu;
 };
 
+constexpr int kMaxStatN = 2048;  // widest layer whose BN statistics are reduced in shared memory
+
 template <int BN>
 struct SmemLayout {
   static constexpr int kStageBytes = (BM * BK + BN * BK) * 2;
   static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
   static constexpr int kTileBytes = kStageBytes * kStages;
   static constexpr int kBarOffset = kTileBytes;
-  static constexpr int kTotal = kTileBytes + (2 * kStages + 4) * 8 + 16 + 1024;  // +1024 alignment slack
+  static constexpr int kStatOffset = kBarOffset + (2 * kStages + 4) * 8 + 16;     // per-CTA column statistics
+  static constexpr int kTotal = kStatOffset + 2 * kMaxStatN * 4 + 1024;           // +1024 alignment slack
 };
 
 template <int BN>
@@ -183,6 +186,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint64_t* tfull_bar = empty_bar + kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  // Column statistics are accumulated per CTA in shared memory over ALL its tiles and flushed to
+  // global memory once: N global atomics per CTA instead of per tile (the per-tile version was
+  // bound by L2 atomic throughput on a few hundred hot addresses).
+  float* stat_s = reinterpret_cast<float*>(smem + L::kStatOffset);   // [2][kMaxStatN]
+  const bool smem_stats = ep.col_sum != nullptr && N <= kMaxStatN;
+  if (smem_stats)
+    for (int i = threadIdx.x; i < 2 * kMaxStatN; i += kThreads) stat_s[i] = 0.f;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -373,8 +383,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
           }
           if (col0 + lane < N) {
-            atomicAdd(ep.col_sum + col0 + lane, s1[0]);
-            atomicAdd(ep.col_sumsq + col0 + lane, s2[0]);
+            if (smem_stats) {
+              atomicAdd(stat_s + col0 + lane, s1[0]);
+              atomicAdd(stat_s + kMaxStatN + col0 + lane, s2[0]);
+            } else {
+              atomicAdd(ep.col_sum + col0 + lane, s1[0]);
+              atomicAdd(ep.col_sumsq + col0 + lane, s2[0]);
+            }
           }
         }
       }
@@ -386,6 +401,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
+  if (smem_stats) {
+    for (int c = threadIdx.x; c < N; c += kThreads) {
+      atomicAdd(ep.col_sum + c, stat_s[c]);
+      atomicAdd(ep.col_sumsq + c, stat_s[kMaxStatN + c]);
+    }
+  }
   if (warp == 1) {
     tc_fence_after();
     tc_dealloc(tmem_base, kTmemCols);
