@@ -104,6 +104,10 @@ if which in ("all", "layers"):
         gemm_case(50176, 1024, 256, bias=False, stats=st_, reps=5)
         gemm_case(16384, 2048, 512, bias=False, stats=st_, reps=5)
         gemm_case(3211264, 64, 160, bias=False, stats=st_, reps=5)
+if which == "one":
+    gemm_case(802816, 256, 64, bias=False, stats=False, reps=0)
+    gemm_case(802816, 256, 64, bias=False, stats=True, reps=0)
+    gemm_case(802816, 64, 256, bias=False, stats=True, reps=0)
 if which in ("all", "conv"):
     conv_case(2, 8, 8, 64, 64, 1, 1, 0)
     conv_case(2, 8, 8, 64, 64, 3, 1, 1)

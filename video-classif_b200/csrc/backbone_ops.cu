@@ -73,24 +73,47 @@ bn_apply_kernel(const bf16* x, bf16* y, long rows, int C, BnSrc bn, int res_mode
   __syncthreads();
   const int vec_per_row = C >> 3;
   const long total = rows * vec_per_row;
-  for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (long)gridDim.x * blockDim.x) {
-    const int c0 = (int)(v % vec_per_row) << 3;
-    float a[8];
-    load8(x + v * 8, a);
-    float r[8];
-    if (res_mode) load8(res + v * 8, r);
+  const long stride = (long)gridDim.x * blockDim.x;
+  constexpr int U = 4;   // independent 16-byte loads in flight per thread and stream
+  for (long v0 = (long)blockIdx.x * blockDim.x + threadIdx.x; v0 < total; v0 += stride * U) {
+    uint4 xa[U], ra[U];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float2 s = ss[c0 + j];
-      float o = fmaf(a[j], s.x, s.y);
-      if (res_mode == 1) o += r[j];
-      else if (res_mode == 2) {
-        const float2 s2 = ss2[c0 + j];
-        o += fmaf(r[j], s2.x, s2.y);
+    for (int u = 0; u < U; ++u) {
+      const long v = v0 + u * stride;
+      if (v < total) {
+        xa[u] = *reinterpret_cast<const uint4*>(x + v * 8);
+        if (res_mode) ra[u] = __ldg(reinterpret_cast<const uint4*>(res + v * 8));
       }
-      a[j] = relu ? fmaxf(o, 0.f) : o;
     }
-    store8(y + v * 8, a);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long v = v0 + u * stride;
+      if (v >= total) break;
+      const int c0 = (int)(v % vec_per_row) << 3;
+      float a[8], r[8];
+      unpack_bf16x2(xa[u].x, a[0], a[1]);
+      unpack_bf16x2(xa[u].y, a[2], a[3]);
+      unpack_bf16x2(xa[u].z, a[4], a[5]);
+      unpack_bf16x2(xa[u].w, a[6], a[7]);
+      if (res_mode) {
+        unpack_bf16x2(ra[u].x, r[0], r[1]);
+        unpack_bf16x2(ra[u].y, r[2], r[3]);
+        unpack_bf16x2(ra[u].z, r[4], r[5]);
+        unpack_bf16x2(ra[u].w, r[6], r[7]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float2 s = ss[c0 + j];
+        float o = fmaf(a[j], s.x, s.y);
+        if (res_mode == 1) o += r[j];
+        else if (res_mode == 2) {
+          const float2 s2 = ss2[c0 + j];
+          o += fmaf(r[j], s2.x, s2.y);
+        }
+        a[j] = relu ? fmaxf(o, 0.f) : o;
+      }
+      store8(y + v * 8, a);
+    }
   }
 }
 

@@ -25,7 +25,8 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;                      // two warps per TMEM lane quarter
+constexpr int kThreads = 64 + 32 * kEpiWarps;    // TMA warp + MMA warp + epilogue warps
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -160,7 +161,7 @@ struct EpiParams {
   int relu;
 };
 
-constexpr int kMaxStatN = 2048;  // widest layer whose BN statistics are reduced in shared memory
+constexpr int kScratchWords = 32 * 17;  // per-epilogue-warp transpose scratch: 32 rows x 16 bf16x2 words (+1 pad)
 
 template <int BN>
 struct SmemLayout {
@@ -168,8 +169,9 @@ struct SmemLayout {
   static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
   static constexpr int kTileBytes = kStageBytes * kStages;
   static constexpr int kBarOffset = kTileBytes;
-  static constexpr int kStatOffset = kBarOffset + (2 * kStages + 4) * 8 + 16;     // per-CTA column statistics
-  static constexpr int kTotal = kStatOffset + 2 * kMaxStatN * 4 + 1024;           // +1024 alignment slack
+  static constexpr int kStatOffset = kBarOffset + (2 * kStages + 4) * 8 + 16;     // per-CTA column statistics [2][BN]
+  static constexpr int kScratchOffset = kStatOffset + 2 * BN * 4;
+  static constexpr int kTotal = kScratchOffset + kEpiWarps * kScratchWords * 4 + 1024;   // +1024 alignment slack
 };
 
 template <int BN>
@@ -186,13 +188,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint64_t* tfull_bar = empty_bar + kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  // Column statistics are accumulated per CTA in shared memory over ALL its tiles and flushed to
-  // global memory once: N global atomics per CTA instead of per tile (the per-tile version was
-  // bound by L2 atomic throughput on a few hundred hot addresses).
-  float* stat_s = reinterpret_cast<float*>(smem + L::kStatOffset);   // [2][kMaxStatN]
-  const bool smem_stats = ep.col_sum != nullptr && N <= kMaxStatN;
-  if (smem_stats)
-    for (int i = threadIdx.x; i < 2 * kMaxStatN; i += kThreads) stat_s[i] = 0.f;
+  // Column statistics (sum, sum of squares of the stored values) are accumulated per CTA in shared
+  // memory over all consecutive tiles of one n-block and flushed to global memory only when the
+  // n-block changes (tiles are ordered m-fastest, so that is at most n_blocks times per CTA).
+  float* stat_s = reinterpret_cast<float*>(smem + L::kStatOffset);   // [2][BN]
+  uint32_t* scratch_s = reinterpret_cast<uint32_t*>(smem + L::kScratchOffset);
+  const bool want_stats = ep.col_sum != nullptr;
+  for (int i = threadIdx.x; i < 2 * BN; i += kThreads) stat_s[i] = 0.f;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -210,7 +212,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -229,8 +231,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / n_blocks;
-        const int n_blk = tile % n_blocks;
+        const int n_blk = tile / m_blocks;           // m-fastest: concurrent CTAs share one weight tile
+        const int m_blk = tile - n_blk * m_blocks;
         int cn = 0, cw = 0, ch = 0;
         if (g.is_conv) {
           const int m0 = m_blk * BM;
@@ -300,12 +302,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
   } else {
-    // =========================== epilogue (warps 2..5) ===========================
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+    // =========================== epilogue (warps 2..9) ===========================
+    const int quarter = warp & 3;          // TMEM lane quarter this warp may read (hardware rule: warp % 4)
+    const int half = (warp - 2) >> 2;      // the two warps of a quarter take alternate 32-column chunks
+    const int epi_tid = threadIdx.x - 64;
+    uint32_t* scr = scratch_s + (warp - 2) * kScratchWords;
     int it = 0;
+    int stat_nblk = -1;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int m_blk = tile / n_blocks;
-      const int n_blk = tile % n_blocks;
+      const int n_blk = tile / m_blocks;
+      const int m_blk = tile - n_blk * m_blocks;
+      if (want_stats && n_blk != stat_nblk) {
+        if (stat_nblk >= 0) {                       // flush the finished n-block (rare)
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          for (int c = epi_tid; c < BN; c += 32 * kEpiWarps) {
+            const int col = stat_nblk * BN + c;
+            if (col < N) {
+              atomicAdd(ep.col_sum + col, stat_s[c]);
+              atomicAdd(ep.col_sumsq + col, stat_s[BN + c]);
+            }
+            stat_s[c] = 0.f;
+            stat_s[BN + c] = 0.f;
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+        stat_nblk = n_blk;
+      }
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -313,7 +335,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int row = m_blk * BM + quarter * 32 + lane;
       const bool row_ok = row < M;
 #pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
+      for (int ch = half; ch < BN / 32; ch += 2) {
         const int col0 = n_blk * BN + ch * 32;
         if (col0 >= N) break;  // warp-uniform
         uint32_t raw[32];
@@ -321,75 +343,116 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         tc_wait_ld();
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(raw[j]);
-          if (ep.bias != nullptr && col0 + j < N) x += __ldg(ep.bias + col0 + j);
-          if (ep.bias2 != nullptr && col0 + j < N) x += __ldg(ep.bias2 + col0 + j);
-          if (ep.relu) x = fmaxf(x, 0.0f);
-          if (ep.out_bf16) x = bf16_round(x);
-          v[j] = x;
-        }
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
         const bool full_chunk = (col0 + 32 <= N);
-        if (row_ok) {
-          if (ep.out_bf16) {
+        // every option below is a WARP-UNIFORM branch around its own loop: predicating 64 bias loads
+        // and adds per chunk (the first version) cost more issue slots than the whole rest of the epilogue
+        if (ep.bias != nullptr) {
+          if (full_chunk) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + j));
+              v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
+            }
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < N) v[j] += __ldg(ep.bias + col0 + j);
+          }
+        }
+        if (ep.bias2 != nullptr) {
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < N) v[j] += __ldg(ep.bias2 + col0 + j);
+        }
+        if (ep.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+        }
+        if (ep.out_bf16) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+          if (row_ok) {
             bf16* dp = reinterpret_cast<bf16*>(ep.D) + (long)row * ep.ldd + col0;
-            if (full_chunk && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0)) {
+            if (full_chunk && ((reinterpret_cast<uintptr_t>(dp) & 31) == 0)) {
+              // two 256-bit stores: full 32-byte sectors, no partial-sector writes at L2
+              asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dp), "r"(pk[0]), "r"(pk[1]),
+                           "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
+                           : "memory");
+              asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dp + 16), "r"(pk[8]), "r"(pk[9]),
+                           "r"(pk[10]), "r"(pk[11]), "r"(pk[12]), "r"(pk[13]), "r"(pk[14]), "r"(pk[15])
+                           : "memory");
+            } else if (full_chunk && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0)) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 o;
-                o.x = pack_bf16x2(v[j], v[j + 1]);
-                o.y = pack_bf16x2(v[j + 2], v[j + 3]);
-                o.z = pack_bf16x2(v[j + 4], v[j + 5]);
-                o.w = pack_bf16x2(v[j + 6], v[j + 7]);
-                *reinterpret_cast<uint4*>(dp + j) = o;
-              }
+              for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<uint4*>(dp + 2 * j) = make_uint4(pk[j], pk[j + 1], pk[j + 2], pk[j + 3]);
             } else {
-#pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (col0 + j < N) dp[j] = __float2bfloat16_rn(v[j]);
             }
-          } else {
-            float* dp = reinterpret_cast<float*>(ep.D) + (long)row * ep.ldd + col0;
-            if (full_chunk && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0)) {
+          }
+          if (want_stats) {
+            // statistics of the values as stored (bf16): transpose the 32x32 chunk through the
+            // warp's scratch so that lane c sums column c -- 16 STS + 32 LDS instead of a 62-shuffle
+            // butterfly.  Row stride 17 words: conflict-free writes; reads are pair-broadcasts.
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
+            for (int j = 0; j < 16; ++j) scr[lane * 17 + j] = row_ok ? pk[j] : 0u;
+            __syncwarp();
+            float s1 = 0.f, s2 = 0.f;
+            const int w = lane >> 1;
+            const bool hi = (lane & 1) != 0;
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < N) dp[j] = v[j];
+            for (int r = 0; r < 32; ++r) {
+              const uint32_t u = scr[r * 17 + w];
+              const float x = __uint_as_float(hi ? (u & 0xffff0000u) : (u << 16));
+              s1 += x;
+              s2 = fmaf(x, x, s2);
+            }
+            __syncwarp();
+            if (col0 + lane < N) {
+              atomicAdd(stat_s + ch * 32 + lane, s1);
+              atomicAdd(stat_s + BN + ch * 32 + lane, s2);
             }
           }
+        } else if (row_ok) {
+          float* dp = reinterpret_cast<float*>(ep.D) + (long)row * ep.ldd + col0;
+          if (full_chunk && ((reinterpret_cast<uintptr_t>(dp) & 31) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8)
+              asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dp + j), "f"(v[j]), "f"(v[j + 1]),
+                           "f"(v[j + 2]), "f"(v[j + 3]), "f"(v[j + 4]), "f"(v[j + 5]), "f"(v[j + 6]), "f"(v[j + 7])
+                           : "memory");
+          } else if (full_chunk && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < N) dp[j] = v[j];
+          }
         }
-        if (ep.col_sum != nullptr) {
-          // column sums over this warp's 32 rows: butterfly reduce-scatter, lane l ends with column l
-          float s1[32], s2[32];
+        if (want_stats && !ep.out_bf16) {
+          // fp32 output: column sums over this warp's 32 rows by butterfly reduce-scatter (lane l ends with column l)
+          float s2[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float x = row_ok ? v[j] : 0.0f;
-            s1[j] = x;
-            s2[j] = x * x;
+            v[j] = row_ok ? v[j] : 0.0f;
+            s2[j] = v[j] * v[j];
           }
 #pragma unroll
           for (int off = 16; off >= 1; off >>= 1) {
             const bool up = (lane & off) != 0;
 #pragma unroll
             for (int i = 0; i < off; ++i) {
-              const float send1 = up ? s1[i] : s1[i + off];
-              const float keep1 = up ? s1[i + off] : s1[i];
-              s1[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, off);
+              const float send1 = up ? v[i] : v[i + off];
+              const float keep1 = up ? v[i + off] : v[i];
+              v[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, off);
               const float send2 = up ? s2[i] : s2[i + off];
               const float keep2 = up ? s2[i + off] : s2[i];
               s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
             }
           }
           if (col0 + lane < N) {
-            if (smem_stats) {
-              atomicAdd(stat_s + col0 + lane, s1[0]);
-              atomicAdd(stat_s + kMaxStatN + col0 + lane, s2[0]);
-            } else {
-              atomicAdd(ep.col_sum + col0 + lane, s1[0]);
-              atomicAdd(ep.col_sumsq + col0 + lane, s2[0]);
-            }
+            atomicAdd(stat_s + ch * 32 + lane, v[0]);
+            atomicAdd(stat_s + BN + ch * 32 + lane, s2[0]);
           }
         }
       }
@@ -401,10 +464,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
-  if (smem_stats) {
-    for (int c = threadIdx.x; c < N; c += kThreads) {
-      atomicAdd(ep.col_sum + c, stat_s[c]);
-      atomicAdd(ep.col_sumsq + c, stat_s[kMaxStatN + c]);
+  if (want_stats) {   // flush the last n-block this CTA worked on
+    int last_tile = -1;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) last_tile = tile;
+    if (last_tile >= 0) {
+      const int nb = last_tile / m_blocks;
+      for (int c = threadIdx.x; c < BN; c += kThreads) {
+        const int col = nb * BN + c;
+        if (col < N) {
+          atomicAdd(ep.col_sum + col, stat_s[c]);
+          atomicAdd(ep.col_sumsq + col, stat_s[BN + c]);
+        }
+      }
     }
   }
   if (warp == 1) {
