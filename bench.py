@@ -33,8 +33,8 @@ RESNET50_GFLOP_PER_FRAME_112 = 2.152     # SURVEY.md section 8(d), torch.utils.f
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-clips", type=int, default=8, help="clips per step of the CPU arms (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -52,26 +52,35 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (one streaming
+    `nvidia-smi -lms 50` process; only samples taken between start() and summary() count)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.rows, self.recording = [], False
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
 
     def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([c.strip() for c in out.strip().split(",")])
-            except Exception:
-                pass
-            time.sleep(0.1)
+        if self.proc is None:
+            return
+        for line in self.proc.stdout:
+            if self.recording:
+                self.rows.append([c.strip() for c in line.strip().split(",")])
+
+    def begin(self):
+        self.recording = True
 
     def summary(self):
-        self.stop_flag = True
+        self.recording = False
+        if self.proc is not None:
+            self.proc.terminate()
         sm, mx, reasons = [], 0, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
@@ -210,9 +219,12 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
+        time.sleep(0.3)                      # let the nvidia-smi stream start before the timed region
     n0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if sampler:
+        sampler.begin()
     e0.record()
     for i in range(args.steps):
         step(dev_x[i % NBUF], dev_y[i % NBUF])

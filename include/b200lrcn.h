@@ -59,7 +59,7 @@ int b2_conv2d_nhwc_bf16(const void* x, int N, int H, int W, int C, const void* w
 
 /* ---- backbone glue (NHWC bf16) ----------------------------------------------------------
  * b2_stem_im2col: NCHW fp32/bf16 frames -> [N*P*Q][Kp] bf16 patches of the 7x7/2 pad-3 stem conv,
- * column k = (r*7+s)*3+c, zero padded to Kp.
+ * column k = (c*7+r)*8+s (filter rows padded to 8 taps), Kp = 168.
  * b2_bn_apply_nhwc: y = act( BN(x) [+ res | + BN2(res)] ), BatchNorm2d semantics of torch
  * (train: batch statistics from sum/sumsq over `count` elements, running stats updated with
  * momentum and unbiased variance; eval: running stats) -- models.py:192 under train_eval.py:12.

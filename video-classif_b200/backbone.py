@@ -22,7 +22,7 @@ from ._lib import call, ptr, stream_ptr
 from .ops import BF16, F32, conv2d_nhwc, gemm_tn
 
 SUPPORTED = ("resnet18", "resnet34", "resnet50", "resnet101", "resnet152")
-STEM_KP = 160   # 7*7*3 = 147 patch columns padded to a 16-byte multiple
+STEM_KP = 168   # stem patch columns: (c*7 + r)*8 + s, filter rows padded from 7 to 8 taps
 
 
 def make_backbone(name: str, pretrained: bool = False):
@@ -54,8 +54,9 @@ class ResNetRunner:
             for n, m in convs:
                 w = m.weight.detach()
                 if n == "conv1":
-                    wk = torch.zeros((w.shape[0], STEM_KP), device=w.device, dtype=BF16)
-                    wk[:, :147] = w.permute(0, 2, 3, 1).reshape(w.shape[0], 147).to(BF16)
+                    wk = torch.zeros((w.shape[0], 3, 7, 8), device=w.device, dtype=BF16)
+                    wk[:, :, :, :7] = w.to(BF16)                  # [Cout, c, r, s] with a zero 8th tap
+                    wk = wk.reshape(w.shape[0], STEM_KP)
                 else:
                     wk = w.permute(0, 2, 3, 1).contiguous().to(BF16)
                 cache[n] = wk

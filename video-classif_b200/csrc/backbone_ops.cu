@@ -60,6 +60,69 @@ __device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
 }
 
 // res_mode 0: none, 1: residual already normalised (identity shortcut), 2: residual raw + own BN
+// Fast path (C/8 divides the block size, true for every ResNet width): a thread's 8 channels never
+// change while it grid-strides, so their scale/shift live in registers -- the loop is pure
+// load / fma / store with U independent 16-byte loads in flight per stream.
+template <int RES_MODE>
+__global__ void __launch_bounds__(256)
+bn_apply_reg_kernel(const bf16* x, bf16* y, long rows, int C, BnSrc bn, const bf16* __restrict__ res, BnSrc rbn,
+                    float inv_count, float unbias, float eps, float momentum, int train, int relu) {
+  const int vec_per_row = C >> 3;
+  const int c0 = (threadIdx.x % vec_per_row) << 3;
+  const bool updater = blockIdx.x == 0 && threadIdx.x < vec_per_row;
+  float sc[8], sh[8], sc2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float2 s = bn_scale_shift(bn, c0 + j, inv_count, unbias, eps, momentum, train, updater);
+    sc[j] = s.x;
+    sh[j] = s.y;
+    if (RES_MODE == 2) {
+      const float2 s2 = bn_scale_shift(rbn, c0 + j, inv_count, unbias, eps, momentum, train, updater);
+      sc2[j] = s2.x;
+      sh[j] += s2.y;
+    }
+  }
+  const long total = rows * vec_per_row;
+  const long stride = (long)gridDim.x * blockDim.x;     // multiple of vec_per_row
+  constexpr int U = 4;
+  for (long v0 = (long)blockIdx.x * blockDim.x + threadIdx.x; v0 < total; v0 += stride * U) {
+    uint4 xa[U], ra[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long v = v0 + u * stride;
+      if (v < total) {
+        xa[u] = *reinterpret_cast<const uint4*>(x + v * 8);
+        if (RES_MODE) ra[u] = __ldg(reinterpret_cast<const uint4*>(res + v * 8));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long v = v0 + u * stride;
+      if (v >= total) break;
+      float a[8], r[8];
+      unpack_bf16x2(xa[u].x, a[0], a[1]);
+      unpack_bf16x2(xa[u].y, a[2], a[3]);
+      unpack_bf16x2(xa[u].z, a[4], a[5]);
+      unpack_bf16x2(xa[u].w, a[6], a[7]);
+      if (RES_MODE) {
+        unpack_bf16x2(ra[u].x, r[0], r[1]);
+        unpack_bf16x2(ra[u].y, r[2], r[3]);
+        unpack_bf16x2(ra[u].z, r[4], r[5]);
+        unpack_bf16x2(ra[u].w, r[6], r[7]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float o = fmaf(a[j], sc[j], sh[j]);
+        if (RES_MODE == 1) o += r[j];
+        if (RES_MODE == 2) o = fmaf(r[j], sc2[j], o);
+        a[j] = relu ? fmaxf(o, 0.f) : o;
+      }
+      store8(y + v * 8, a);
+    }
+  }
+}
+
+// generic fallback (any C multiple of 8): scale/shift staged in shared memory
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const bf16* x, bf16* y, long rows, int C, BnSrc bn, int res_mode,
                 const bf16* __restrict__ res, BnSrc rbn, float inv_count, float unbias, float eps, float momentum,
@@ -73,47 +136,23 @@ bn_apply_kernel(const bf16* x, bf16* y, long rows, int C, BnSrc bn, int res_mode
   __syncthreads();
   const int vec_per_row = C >> 3;
   const long total = rows * vec_per_row;
-  const long stride = (long)gridDim.x * blockDim.x;
-  constexpr int U = 4;   // independent 16-byte loads in flight per thread and stream
-  for (long v0 = (long)blockIdx.x * blockDim.x + threadIdx.x; v0 < total; v0 += stride * U) {
-    uint4 xa[U], ra[U];
+  for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(v % vec_per_row) << 3;
+    float a[8], r[8];
+    load8(x + v * 8, a);
+    if (res_mode) load8(res + v * 8, r);
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long v = v0 + u * stride;
-      if (v < total) {
-        xa[u] = *reinterpret_cast<const uint4*>(x + v * 8);
-        if (res_mode) ra[u] = __ldg(reinterpret_cast<const uint4*>(res + v * 8));
+    for (int j = 0; j < 8; ++j) {
+      const float2 s = ss[c0 + j];
+      float o = fmaf(a[j], s.x, s.y);
+      if (res_mode == 1) o += r[j];
+      else if (res_mode == 2) {
+        const float2 s2 = ss2[c0 + j];
+        o += fmaf(r[j], s2.x, s2.y);
       }
+      a[j] = relu ? fmaxf(o, 0.f) : o;
     }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long v = v0 + u * stride;
-      if (v >= total) break;
-      const int c0 = (int)(v % vec_per_row) << 3;
-      float a[8], r[8];
-      unpack_bf16x2(xa[u].x, a[0], a[1]);
-      unpack_bf16x2(xa[u].y, a[2], a[3]);
-      unpack_bf16x2(xa[u].z, a[4], a[5]);
-      unpack_bf16x2(xa[u].w, a[6], a[7]);
-      if (res_mode) {
-        unpack_bf16x2(ra[u].x, r[0], r[1]);
-        unpack_bf16x2(ra[u].y, r[2], r[3]);
-        unpack_bf16x2(ra[u].z, r[4], r[5]);
-        unpack_bf16x2(ra[u].w, r[6], r[7]);
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float2 s = ss[c0 + j];
-        float o = fmaf(a[j], s.x, s.y);
-        if (res_mode == 1) o += r[j];
-        else if (res_mode == 2) {
-          const float2 s2 = ss2[c0 + j];
-          o += fmaf(r[j], s2.x, s2.y);
-        }
-        a[j] = relu ? fmaxf(o, 0.f) : o;
-      }
-      store8(y + v * 8, a);
-    }
+    store8(y + v * 8, a);
   }
 }
 
@@ -136,19 +175,26 @@ bn_relu_maxpool_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N, 
     float m[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) m[j] = 0.f;  // post-ReLU values are >= 0 and the window is never empty
-    for (int dy = 0; dy < 3; ++dy) {
-      const int iy = 2 * p - 1 + dy;
-      if (iy < 0 || iy >= H) continue;
-      for (int dx = 0; dx < 3; ++dx) {
-        const int ix = 2 * q - 1 + dx;
-        if (ix < 0 || ix >= W) continue;
-        float a[8];
-        load8(x + (((long)n * H + iy) * W + ix) * C + cg * 8, a);
+    uint4 win[9];
+    bool ok[9];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float2 s = ss[cg * 8 + j];
-          m[j] = fmaxf(m[j], fmaf(a[j], s.x, s.y));
-        }
+    for (int t9 = 0; t9 < 9; ++t9) {        // issue all 9 window loads before using any
+      const int iy = 2 * p - 1 + t9 / 3, ix = 2 * q - 1 + t9 % 3;
+      ok[t9] = iy >= 0 && iy < H && ix >= 0 && ix < W;
+      if (ok[t9]) win[t9] = __ldg(reinterpret_cast<const uint4*>(x + (((long)n * H + iy) * W + ix) * C + cg * 8));
+    }
+#pragma unroll
+    for (int t9 = 0; t9 < 9; ++t9) {
+      if (!ok[t9]) continue;
+      float a[8];
+      unpack_bf16x2(win[t9].x, a[0], a[1]);
+      unpack_bf16x2(win[t9].y, a[2], a[3]);
+      unpack_bf16x2(win[t9].z, a[4], a[5]);
+      unpack_bf16x2(win[t9].w, a[6], a[7]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float2 sc = ss[cg * 8 + j];
+        m[j] = fmaxf(m[j], fmaf(a[j], sc.x, sc.y));
       }
     }
     store8(y + v * 8, m);
@@ -186,12 +232,14 @@ avgpool_kernel(const bf16* __restrict__ x, float* __restrict__ out_f32, bf16* __
   }
 }
 
-// Patch matrix for the 7x7 stride-2 pad-3 stem: row m = (n,p,q), column k = (r*7+s)*3 + c, padded
-// with zeros to Kp columns.  Each thread produces 8 consecutive k (one 16-byte store).
+// Patch matrix for the 7x7 stride-2 pad-3 stem: row m = (n,p,q), column k = (c*7 + r)*8 + s with the
+// filter row padded from 7 to 8 taps (the weight matrix carries a zero in the s = 7 slot), so each
+// 16-byte output vector is 8 CONSECUTIVE input pixels of one input row: contiguous reads, no
+// per-element div/mod.  Kp = 3*7*8 = 168.
 template <typename InT>
 __global__ void __launch_bounds__(256)
 stem_im2col_kernel(const InT* __restrict__ x, bf16* __restrict__ A, int N, int H, int W, int P, int Q, int Kp) {
-  const int kvec = Kp >> 3;
+  const int kvec = Kp >> 3;   // 21
   const long total = (long)N * P * Q * kvec;
   const long plane = (long)H * W;
   for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (long)gridDim.x * blockDim.x) {
@@ -201,19 +249,19 @@ stem_im2col_kernel(const InT* __restrict__ x, bf16* __restrict__ A, int N, int H
     long t = m / Q;
     const int p = (int)(t % P);
     const int n = (int)(t / P);
+    const int c = kv / 7, r = kv - c * 7;
+    const int iy = 2 * p - 3 + r;
+    const int ix0 = 2 * q - 3;
     float o[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = kv * 8 + j;
-      float val = 0.f;
-      if (k < 147) {
-        const int c = k % 3;
-        const int tap = k / 3;
-        const int s = tap % 7, r = tap / 7;
-        const int iy = 2 * p - 3 + r, ix = 2 * q - 3 + s;
-        if (iy >= 0 && iy < H && ix >= 0 && ix < W) val = (float)x[((long)n * 3 + c) * plane + (long)iy * W + ix];
+    for (int j = 0; j < 8; ++j) o[j] = 0.f;
+    if (c < 3 && iy >= 0 && iy < H) {
+      const InT* row = x + ((long)n * 3 + c) * plane + (long)iy * W;
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        const int ix = ix0 + j;
+        if (ix >= 0 && ix < W) o[j] = (float)row[ix];
       }
-      o[j] = val;
     }
     store8(A + v * 8, o);
   }
@@ -221,7 +269,7 @@ stem_im2col_kernel(const InT* __restrict__ x, bf16* __restrict__ A, int N, int H
 
 int grid_for(long work_items, int threads) {
   long blocks = (work_items + threads - 1) / threads;
-  long cap = (long)b2_num_sms() * 8;
+  long cap = (long)b2_num_sms() * 16;
   return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
 }
 
@@ -245,8 +293,23 @@ B2_API int b2_bn_apply_nhwc(const void* x, void* y, long rows, int C, const floa
     B2_CUDA_CHECK(cudaFuncSetAttribute(bn_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   const float inv = 1.f / (float)count;
   const float unbias = count > 1 ? (float)((double)count / (double)(count - 1)) : 1.f;
-  bn_apply_kernel<<<grid_for(rows * (C / 8), 256), 256, smem, (cudaStream_t)stream>>>(
-      (const bf16*)x, (bf16*)y, rows, C, bn, res_mode, (const bf16*)res, rbn, inv, unbias, eps, momentum, train, relu);
+  const int vec_per_row = C / 8;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (vec_per_row <= 256 && 256 % vec_per_row == 0) {
+    const int grid = grid_for((rows * vec_per_row + 3) / 4, 256);
+    if (res_mode == 0)
+      bn_apply_reg_kernel<0><<<grid, 256, 0, st>>>((const bf16*)x, (bf16*)y, rows, C, bn, (const bf16*)res, rbn, inv,
+                                                   unbias, eps, momentum, train, relu);
+    else if (res_mode == 1)
+      bn_apply_reg_kernel<1><<<grid, 256, 0, st>>>((const bf16*)x, (bf16*)y, rows, C, bn, (const bf16*)res, rbn, inv,
+                                                   unbias, eps, momentum, train, relu);
+    else
+      bn_apply_reg_kernel<2><<<grid, 256, 0, st>>>((const bf16*)x, (bf16*)y, rows, C, bn, (const bf16*)res, rbn, inv,
+                                                   unbias, eps, momentum, train, relu);
+  } else {
+    bn_apply_kernel<<<grid_for(rows * vec_per_row, 256), 256, smem, st>>>(
+        (const bf16*)x, (bf16*)y, rows, C, bn, res_mode, (const bf16*)res, rbn, inv, unbias, eps, momentum, train, relu);
+  }
   B2_LAUNCH_CHECK("bn_apply_kernel");
   return 0;
 }
@@ -280,7 +343,7 @@ B2_API int b2_avgpool_nhwc(const void* x, float* out_f32, void* out_bf16, int N,
 
 B2_API int b2_stem_im2col(const void* x, int in_bf16, void* A, int N, int H, int W, int Kp, void* stream) {
   B2_ARG_CHECK(x && A && N > 0 && H > 0 && W > 0, "b2_stem_im2col: null pointer or empty");
-  B2_ARG_CHECK(Kp >= 152 && Kp % 8 == 0, "b2_stem_im2col: Kp must be a multiple of 8 and >= 152");
+  B2_ARG_CHECK(Kp == 168, "b2_stem_im2col: Kp must be 168 (3 channels x 7 rows x 8 padded taps)");
   const int P = (H + 6 - 7) / 2 + 1, Q = (W + 6 - 7) / 2 + 1;
   const long total = (long)N * P * Q * (Kp / 8);
   if (in_bf16)

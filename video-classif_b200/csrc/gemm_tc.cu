@@ -86,6 +86,18 @@ __device__ __forceinline__ void tma_load_im2col_4d(void* dst, const void* tmap, 
       "h"(off_h)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const void* tmap, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_alloc(uint32_t* dst_smem, uint32_t ncols) {
@@ -159,30 +171,35 @@ struct EpiParams {
   float* col_sumsq;  // [N] or null
   int out_bf16;      // 1: bf16 out, 0: fp32 out
   int relu;
+  int tma_store;     // bf16 output leaves through smem staging + TMA bulk stores (tmap_d valid)
 };
 
-constexpr int kScratchWords = 32 * 17;  // per-epilogue-warp transpose scratch: 32 rows x 16 bf16x2 words (+1 pad)
+constexpr int kStgBytes = 32 * 64;  // epilogue staging tile: 32 rows x 32 bf16 (64-byte rows, SWIZZLE_64B)
 
 template <int BN>
 struct SmemLayout {
   static constexpr int kStageBytes = (BM * BK + BN * BK) * 2;
-  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 5 : (BN >= 64 ? 7 : 8));
+  static constexpr int kStgBufs = (BN >= 256) ? 1 : 2;   // staging tiles per epilogue warp
   static constexpr int kTileBytes = kStageBytes * kStages;
   static constexpr int kBarOffset = kTileBytes;
-  static constexpr int kStatOffset = kBarOffset + (2 * kStages + 4) * 8 + 16;     // per-CTA column statistics [2][BN]
-  static constexpr int kScratchOffset = kStatOffset + 2 * BN * 4;
-  static constexpr int kTotal = kScratchOffset + kEpiWarps * kScratchWords * 4 + 1024;   // +1024 alignment slack
+  static constexpr int kStatOffset = kBarOffset + (2 * kStages + 4) * 8 + 16;     // per-CTA column statistics [4 quarters][2][BN]
+  static constexpr int kScratchOffset = kStatOffset + 4 * 2 * BN * 4;
+  static constexpr int kScratchOffset1k = (kScratchOffset + 1023) / 1024 * 1024;        // staging tiles 1024-aligned
+  static constexpr int kTotal = kScratchOffset1k + kEpiWarps * kStgBufs * kStgBytes + 1024;   // +1024 alignment slack
 };
 
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M, int N,
-               int K, ConvGeom g, EpiParams ep) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const __grid_constant__ CUtensorMap tmap_d, int M, int N, int K, ConvGeom g, EpiParams ep) {
   using L = SmemLayout<BN>;
   constexpr int kStages = L::kStages;
   constexpr uint32_t kTmemCols = 2 * BN;  // two accumulators (32 <= cols <= 512, power of two)
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment (SWIZZLE_128B) computed as an OFFSET so that every derived pointer keeps its
+  // shared-memory provenance (integer round-tripping made the compiler emit generic LD/ST/atomics).
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;
@@ -191,10 +208,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   // Column statistics (sum, sum of squares of the stored values) are accumulated per CTA in shared
   // memory over all consecutive tiles of one n-block and flushed to global memory only when the
   // n-block changes (tiles are ordered m-fastest, so that is at most n_blocks times per CTA).
-  float* stat_s = reinterpret_cast<float*>(smem + L::kStatOffset);   // [2][BN]
-  uint32_t* scratch_s = reinterpret_cast<uint32_t*>(smem + L::kScratchOffset);
+  // One private copy per TMEM lane quarter: the two warps of a quarter own disjoint chunks, so a slot
+  // has exactly one writer and plain read-modify-write replaces shared-memory CAS atomics.
+  float* stat_s = reinterpret_cast<float*>(smem + L::kStatOffset);   // [4][2][BN]
+  uint8_t* staging_s = smem + L::kScratchOffset1k;
   const bool want_stats = ep.col_sum != nullptr;
-  for (int i = threadIdx.x; i < 2 * BN; i += kThreads) stat_s[i] = 0.f;
+  for (int i = threadIdx.x; i < 8 * BN; i += kThreads) stat_s[i] = 0.f;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -306,7 +325,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int quarter = warp & 3;          // TMEM lane quarter this warp may read (hardware rule: warp % 4)
     const int half = (warp - 2) >> 2;      // the two warps of a quarter take alternate 32-column chunks
     const int epi_tid = threadIdx.x - 64;
-    uint32_t* scr = scratch_s + (warp - 2) * kScratchWords;
+    uint8_t* stg_base = staging_s + (warp - 2) * L::kStgBufs * kStgBytes;
+    int stg_buf = 0;
     int it = 0;
     int stat_nblk = -1;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -318,11 +338,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           for (int c = epi_tid; c < BN; c += 32 * kEpiWarps) {
             const int col = stat_nblk * BN + c;
             if (col < N) {
-              atomicAdd(ep.col_sum + col, stat_s[c]);
-              atomicAdd(ep.col_sumsq + col, stat_s[BN + c]);
+              atomicAdd(ep.col_sum + col, stat_s[c] + stat_s[2 * BN + c] + stat_s[4 * BN + c] + stat_s[6 * BN + c]);
+              atomicAdd(ep.col_sumsq + col,
+                        stat_s[BN + c] + stat_s[3 * BN + c] + stat_s[5 * BN + c] + stat_s[7 * BN + c]);
             }
-            stat_s[c] = 0.f;
-            stat_s[BN + c] = 0.f;
+#pragma unroll
+            for (int qq = 0; qq < 8; ++qq) stat_s[qq * BN + c] = 0.f;
           }
           asm volatile("bar.sync 1, 256;" ::: "memory");
         }
@@ -371,10 +392,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           uint32_t pk[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-          if (row_ok) {
+          uint8_t* stg = stg_base + stg_buf * kStgBytes;
+          const bool staged = ep.tma_store || want_stats;
+          if (staged) {
+            // The 32x32 bf16 chunk goes to a 64-byte-swizzled staging tile (lane = row, 4 x STS.128,
+            // conflict-free).  From there (a) one TMA bulk store writes it to global memory in full
+            // 64-byte row segments without occupying the LSU or any registers, and (b) the BN
+            // statistics are column sums read straight back from the tile (lane pairs share a word).
+            if (ep.tma_store && lane == 0) bulk_wait_read<L::kStgBufs - 1>();   // tile free again?
+            __syncwarp();
+            if (want_stats && !row_ok) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) pk[j] = 0u;       // rows past M: no statistics (TMA clips the store)
+            }
+            const int sw = (lane >> 1) & 3;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              *reinterpret_cast<uint4*>(stg + lane * 64 + ((c ^ sw) << 4)) =
+                  make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+          }
+          if (ep.tma_store) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmap_d, stg, col0, m_blk * BM + quarter * 32);
+              bulk_commit();
+            }
+          } else if (row_ok) {
+            if (staged) __syncwarp();
             bf16* dp = reinterpret_cast<bf16*>(ep.D) + (long)row * ep.ldd + col0;
             if (full_chunk && ((reinterpret_cast<uintptr_t>(dp) & 31) == 0)) {
-              // two 256-bit stores: full 32-byte sectors, no partial-sector writes at L2
               asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dp), "r"(pk[0]), "r"(pk[1]),
                            "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
                            : "memory");
@@ -389,30 +436,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               for (int j = 0; j < 32; ++j)
                 if (col0 + j < N) dp[j] = __float2bfloat16_rn(v[j]);
             }
+          } else if (staged) {
+            __syncwarp();
           }
           if (want_stats) {
-            // statistics of the values as stored (bf16): transpose the 32x32 chunk through the
-            // warp's scratch so that lane c sums column c -- 16 STS + 32 LDS instead of a 62-shuffle
-            // butterfly.  Row stride 17 words: conflict-free writes; reads are pair-broadcasts.
+            float s1a = 0.f, s1b = 0.f, s1c = 0.f, s1d = 0.f, s2a = 0.f, s2b = 0.f, s2c = 0.f, s2d = 0.f;
+            const int w = lane >> 1;                       // bf16x2 word of the row this lane pair reads
+            const int sh = (lane & 1) ? 0 : 16;            // even lanes take the low bf16 of the word
+            const uint8_t* colp = stg + ((w & 3) << 2);
+            const int wc = w >> 2;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) scr[lane * 17 + j] = row_ok ? pk[j] : 0u;
-            __syncwarp();
-            float s1 = 0.f, s2 = 0.f;
-            const int w = lane >> 1;
-            const bool hi = (lane & 1) != 0;
+            for (int r = 0; r < 32; r += 4) {              // four independent accumulation chains
+              uint32_t u[4];
 #pragma unroll
-            for (int r = 0; r < 32; ++r) {
-              const uint32_t u = scr[r * 17 + w];
-              const float x = __uint_as_float(hi ? (u & 0xffff0000u) : (u << 16));
-              s1 += x;
-              s2 = fmaf(x, x, s2);
+              for (int q4 = 0; q4 < 4; ++q4)
+                u[q4] = *reinterpret_cast<const uint32_t*>(colp + (r + q4) * 64 + ((wc ^ (((r + q4) >> 1) & 3)) << 4));
+              const float x0 = __uint_as_float((u[0] << sh) & 0xffff0000u);
+              const float x1 = __uint_as_float((u[1] << sh) & 0xffff0000u);
+              const float x2 = __uint_as_float((u[2] << sh) & 0xffff0000u);
+              const float x3 = __uint_as_float((u[3] << sh) & 0xffff0000u);
+              s1a += x0; s1b += x1; s1c += x2; s1d += x3;
+              s2a = fmaf(x0, x0, s2a); s2b = fmaf(x1, x1, s2b); s2c = fmaf(x2, x2, s2c); s2d = fmaf(x3, x3, s2d);
             }
-            __syncwarp();
-            if (col0 + lane < N) {
-              atomicAdd(stat_s + ch * 32 + lane, s1);
-              atomicAdd(stat_s + BN + ch * 32 + lane, s2);
-            }
+            float* st = stat_s + quarter * 2 * BN + ch * 32 + lane;
+            st[0] += (s1a + s1b) + (s1c + s1d);
+            st[BN] += (s2a + s2b) + (s2c + s2d);
           }
+          if (staged) stg_buf = (stg_buf + 1) % L::kStgBufs;
         } else if (row_ok) {
           float* dp = reinterpret_cast<float*>(ep.D) + (long)row * ep.ldd + col0;
           if (full_chunk && ((reinterpret_cast<uintptr_t>(dp) & 31) == 0)) {
@@ -450,16 +500,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
             }
           }
-          if (col0 + lane < N) {
-            atomicAdd(stat_s + ch * 32 + lane, v[0]);
-            atomicAdd(stat_s + BN + ch * 32 + lane, s2[0]);
-          }
+          float* st = stat_s + quarter * 2 * BN + ch * 32 + lane;
+          st[0] += v[0];
+          st[BN] += s2[0];
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
+    if (ep.tma_store && lane == 0) bulk_wait_all();   // all bulk stores of this warp have landed
   }
 
   tc_fence_before();
@@ -472,8 +522,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int c = threadIdx.x; c < BN; c += kThreads) {
         const int col = nb * BN + c;
         if (col < N) {
-          atomicAdd(ep.col_sum + col, stat_s[c]);
-          atomicAdd(ep.col_sumsq + col, stat_s[BN + c]);
+          atomicAdd(ep.col_sum + col, stat_s[c] + stat_s[2 * BN + c] + stat_s[4 * BN + c] + stat_s[6 * BN + c]);
+          atomicAdd(ep.col_sumsq + col, stat_s[BN + c] + stat_s[3 * BN + c] + stat_s[5 * BN + c] + stat_s[7 * BN + c]);
         }
       }
     }
@@ -516,14 +566,15 @@ int load_driver_entry_points() {
   return 0;
 }
 
-int make_tmap_2d(CUtensorMap* map, const void* base, long rows, long cols, long ld_elems, int box_rows) {
+int make_tmap_2d(CUtensorMap* map, const void* base, long rows, long cols, long ld_elems, int box_rows,
+                 int box_cols = BK, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld_elems * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
-                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     b2_set_error("cuTensorMapEncodeTiled failed (%d): rows=%ld cols=%ld ld=%ld box_rows=%d base=%p", (int)r, rows,
                  cols, ld_elems, box_rows, base);
@@ -533,8 +584,8 @@ int make_tmap_2d(CUtensorMap* map, const void* base, long rows, long cols, long 
 }
 
 template <int BN>
-int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const ConvGeom& g,
-                const EpiParams& ep, cudaStream_t stream) {
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, int M, int N, int K,
+                const ConvGeom& g, const EpiParams& ep, cudaStream_t stream) {
   using L = SmemLayout<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -543,7 +594,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int 
   }
   const int tiles = b2_ceil_div(M, BM) * b2_ceil_div(N, BN);
   const int grid = tiles < b2_num_sms() ? tiles : b2_num_sms();
-  gemm_tc_kernel<BN><<<grid, kThreads, L::kTotal, stream>>>(ta, tb, M, N, K, g, ep);
+  gemm_tc_kernel<BN><<<grid, kThreads, L::kTotal, stream>>>(ta, tb, td, M, N, K, g, ep);
   B2_LAUNCH_CHECK("gemm_tc_kernel");
   return 0;
 }
@@ -556,12 +607,19 @@ int pick_bn(int N) {
 }
 
 int dispatch(int bn, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const ConvGeom& g,
-             const EpiParams& ep, cudaStream_t stream) {
+             EpiParams ep, cudaStream_t stream) {
+  // bf16 outputs whose rows are 16-byte multiples leave through TMA bulk stores
+  CUtensorMap td = ta;
+  ep.tma_store = 0;
+  if (ep.out_bf16 && (ep.ldd % 8) == 0 && ((uintptr_t)ep.D & 15) == 0) {
+    if (int r = make_tmap_2d(&td, ep.D, M, N, ep.ldd, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return r;
+    ep.tma_store = 1;
+  }
   switch (bn) {
-    case 256: return launch_gemm<256>(ta, tb, M, N, K, g, ep, stream);
-    case 128: return launch_gemm<128>(ta, tb, M, N, K, g, ep, stream);
-    case 64: return launch_gemm<64>(ta, tb, M, N, K, g, ep, stream);
-    default: return launch_gemm<32>(ta, tb, M, N, K, g, ep, stream);
+    case 256: return launch_gemm<256>(ta, tb, td, M, N, K, g, ep, stream);
+    case 128: return launch_gemm<128>(ta, tb, td, M, N, K, g, ep, stream);
+    case 64: return launch_gemm<64>(ta, tb, td, M, N, K, g, ep, stream);
+    default: return launch_gemm<32>(ta, tb, td, M, N, K, g, ep, stream);
   }
 }
 
@@ -581,7 +639,7 @@ B2_API int b2_gemm_bf16_tn(const void* A, long lda, const void* B, long ldb, voi
   if (int r = make_tmap_2d(&ta, A, M, K, lda, BM)) return r;
   if (int r = make_tmap_2d(&tb, B, N, K, ldb, bn)) return r;
   ConvGeom g = {};
-  EpiParams ep = {D, ldd, bias, bias2, col_sum, col_sumsq, out_bf16, relu};
+  EpiParams ep = {D, ldd, bias, bias2, col_sum, col_sumsq, out_bf16, relu, 0};
   return dispatch(bn, ta, tb, M, N, K, g, ep, (cudaStream_t)stream);
 }
 
@@ -603,7 +661,7 @@ B2_API int b2_conv2d_nhwc_bf16(const void* x, int Nimg, int H, int W, int C, con
   const int M = (int)Ml;
   const int K = R * S * C;
   const int bn = pick_bn(Cout);
-  EpiParams ep = {y, (long)Cout, bias, nullptr, col_sum, col_sumsq, out_bf16, relu};
+  EpiParams ep = {y, (long)Cout, bias, nullptr, col_sum, col_sumsq, out_bf16, relu, 0};
   CUtensorMap ta, tb;
   if (int r = make_tmap_2d(&tb, w, Cout, K, K, bn)) return r;
   if (R == 1 && S == 1 && stride == 1 && pad == 0) {
