@@ -66,6 +66,16 @@ int b2_conv2d_nhwc_bf16(const void* x, int N, int H, int W, int C, const void* w
  * res_mode 0 none, 1 identity shortcut (already activated), 2 down-sample branch (raw + own BN).
  * b2_bn_relu_maxpool_nhwc: stem BN + ReLU + MaxPool2d(3,2,1).  b2_avgpool_nhwc: AdaptiveAvgPool2d(1). */
 int b2_stem_im2col(const void* x, int in_bf16, void* A, int N, int H, int W, int Kp, void* stream);
+/* Direct stem convolution (Conv2d 3->64, 7x7, stride 2, pad 3; torchvision ResNet.conv1 under
+ * models.py:192) without a patch matrix: b2_stem_pack repacks NCHW fp32/bf16 frames into zero-padded
+ * bf16 units of 2 pixels x 4 channels, even/odd rows in separate planes (b2_stem_packed_bytes bytes);
+ * b2_stem_conv_bf16 runs the convolution as a Toeplitz-descriptor tcgen05 GEMM over that stream and
+ * writes raw NHWC bf16 [N][P][Q][64] + the per-channel sum / sum of squares (ACCUMULATED, may be NULL).
+ * wk: weights as bf16 [28][64][8] with k = r*32 + s*4 + c (s = 7 and c = 3 slots zero). */
+long b2_stem_packed_bytes(int N, int H, int W);
+int b2_stem_pack(const void* x, int in_bf16, void* xp, int N, int H, int W, void* stream);
+int b2_stem_conv_bf16(const void* xp, const void* wk, void* y, int N, int H, int W, float* col_sum,
+                      float* col_sumsq, void* stream);
 int b2_bn_apply_nhwc(const void* x, void* y, long rows, int C, const float* sum, const float* sumsq,
                      const float* gamma, const float* beta, float* running_mean, float* running_var,
                      int res_mode, const void* res, const float* rsum, const float* rsumsq,

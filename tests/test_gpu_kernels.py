@@ -61,6 +61,25 @@ def test_conv_implicit_gemm_tma_im2col(ops, N, H, W, C, Cout, R, stride, pad):
     assert err(s2, (r * r).sum(0)) < 2e-2
 
 
+@pytest.mark.parametrize("N,H,W", [(2, 32, 32), (3, 112, 112), (2, 64, 96), (1, 224, 224), (5, 17, 23), (300, 16, 16)])
+def test_stem_conv_direct_toeplitz(ops, N, H, W):
+    """ResNet conv1 (7x7/2 pad 3) as the Toeplitz-descriptor tcgen05 kernel vs torch fp32 conv on the
+    bf16-rounded operands; also the fused per-channel statistics."""
+    torch.manual_seed(N + H + W)
+    x = torch.rand(N, 3, H, W)
+    w = (torch.randn(64, 3, 7, 7) / 147 ** 0.5)
+    s1, s2 = torch.zeros(64, device=DEV), torch.zeros(64, device=DEV)
+    y = ops.stem_conv(x.to(DEV), ops.pack_stem_weight(w.to(DEV)), stats=(s1, s2))
+    ref = F.conv2d(x.bfloat16().float(), w.bfloat16().float(), stride=2, padding=3).permute(0, 2, 3, 1)
+    assert y.shape == ref.shape
+    assert err(y.float(), ref) < 6e-3
+    r = ref.bfloat16().float().reshape(-1, 64)
+    assert err(s1, r.sum(0), floor=1e-3 * r.abs().sum(0).max().item()) < 2e-2
+    assert err(s2, (r * r).sum(0)) < 2e-2
+    yb = ops.stem_conv(x.to(DEV).bfloat16(), ops.pack_stem_weight(w.to(DEV)))      # bf16 input frames
+    assert torch.equal(yb, y)
+
+
 def test_ingest_bit_exact_vs_cv2_golden(ops):
     g = np.load(os.path.join(GOLDEN, "resize_cv2.npz"))
     i = 0

@@ -19,7 +19,7 @@ import torch
 
 from . import _lib
 from ._lib import call, ptr, stream_ptr
-from .ops import BF16, F32, conv2d_nhwc, gemm_tn
+from .ops import BF16, F32, conv2d_nhwc, gemm_tn, pack_stem_weight, stem_conv
 
 SUPPORTED = ("resnet18", "resnet34", "resnet50", "resnet101", "resnet152")
 STEM_KP = 168   # stem patch columns: (c*7 + r)*8 + s, filter rows padded from 7 to 8 taps
@@ -44,6 +44,7 @@ class ResNetRunner:
         self.net = net
         self._wcache = None
         self._wkey = None
+        self.stem_impl = "direct"     # "im2col": patch matrix + plain GEMM (A/B parity tests)
 
     # ---- weights in kernel layout: [Cout, R, S, C] bf16 (K-major), stem [64, STEM_KP] ----
     def _weights(self):
@@ -56,7 +57,9 @@ class ResNetRunner:
                 if n == "conv1":
                     wk = torch.zeros((w.shape[0], 3, 7, 8), device=w.device, dtype=BF16)
                     wk[:, :, :, :7] = w.to(BF16)                  # [Cout, c, r, s] with a zero 8th tap
-                    wk = wk.reshape(w.shape[0], STEM_KP)
+                    cache["conv1.im2col"] = wk.reshape(w.shape[0], STEM_KP)
+                    # direct stem kernel: k = r*32 + s*4 + c (s = 7, c = 3 zero), stored [k/8][Cout][8]
+                    wk = pack_stem_weight(w)
                 else:
                     wk = w.permute(0, 2, 3, 1).contiguous().to(BF16)
                 cache[n] = wk
@@ -113,10 +116,14 @@ class ResNetRunner:
         st = stream_ptr()
         # ---- stem ----
         P, Q = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
-        A = torch.empty((N * P * Q, STEM_KP), device=dev, dtype=BF16)
-        call("b2_stem_im2col", x.data_ptr(), int(x.dtype == BF16), A.data_ptr(), N, H, W, STEM_KP, st)
-        raw = gemm_tn(A, w["conv1"], out_dtype=BF16, stats=stats_of(net.bn1))
-        del A
+        s_stem = stats_of(net.bn1)
+        if self.stem_impl == "direct":
+            raw = stem_conv(x, w["conv1"], stats=s_stem)
+        else:                                   # patch-matrix path (kept for A/B parity tests)
+            A = torch.empty((N * P * Q, STEM_KP), device=dev, dtype=BF16)
+            call("b2_stem_im2col", x.data_ptr(), int(x.dtype == BF16), A.data_ptr(), N, H, W, STEM_KP, st)
+            raw = gemm_tn(A, w["conv1.im2col"], out_dtype=BF16, stats=s_stem)
+            del A
         P2, Q2 = (P + 2 - 3) // 2 + 1, (Q + 2 - 3) // 2 + 1
         y = torch.empty((N, P2, Q2, 64), device=dev, dtype=BF16)
         s = stats_of(net.bn1)

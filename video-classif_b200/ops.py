@@ -59,6 +59,31 @@ def conv2d_nhwc(x, w, stride, pad, stats=None):
     return y
 
 
+def pack_stem_weight(w):
+    """torch conv1 weight [64,3,7,7] -> bf16 [28][64][8] for b2_stem_conv_bf16 (k = r*32 + s*4 + c)."""
+    assert tuple(w.shape[1:]) == (3, 7, 7) and w.shape[0] == 64
+    w4 = torch.zeros((64, 7, 8, 4), device=w.device, dtype=BF16)
+    w4[:, :, :7, :3] = w.detach().permute(0, 2, 3, 1).to(BF16)
+    return w4.reshape(64, 28, 8).permute(1, 0, 2).contiguous()
+
+
+def stem_conv(x, wk, stats=None):
+    """x [N,3,H,W] fp32/bf16 NCHW, wk = pack_stem_weight(conv1.weight) -> raw conv output [N,P,Q,64] bf16
+    (Conv2d 7x7 stride 2 pad 3) + optional per-channel sum / sum-of-squares."""
+    _chk(x, wk)
+    x = x.contiguous()
+    N, C, H, W = x.shape
+    assert C == 3 and x.dtype in (F32, BF16)
+    P, Q = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    xp = torch.empty(_lib.lib().b2_stem_packed_bytes(N, H, W), device=x.device, dtype=torch.uint8)
+    st = stream_ptr()
+    call("b2_stem_pack", x.data_ptr(), int(x.dtype == BF16), xp.data_ptr(), N, H, W, st)
+    y = torch.empty((N, P, Q, 64), device=x.device, dtype=BF16)
+    s1, s2 = stats if stats is not None else (None, None)
+    call("b2_stem_conv_bf16", xp.data_ptr(), wk.data_ptr(), y.data_ptr(), N, H, W, ptr(s1), ptr(s2), st)
+    return y
+
+
 def sgemm(A, B, trans_a=False, trans_b=False, out=None, alpha=1.0, beta=0.0, M=None, N=None, K=None, bias=None,
           bias2=None):
     """fp32 row-major C = alpha op(A) op(B) + beta C on the SIMT kernel."""
