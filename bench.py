@@ -297,7 +297,7 @@ def run_ours(args):
     tflops_peak, hbm_peak, peak_src = peaks()
     if not args.no_roofline and rank == 0:
         events = []
-        orig_gemm, orig_conv = ops.gemm_tn, ops.conv2d_nhwc
+        orig_gemm, orig_conv, orig_convbn = ops.gemm_tn, ops.conv2d_nhwc, ops.conv2d_bn_nhwc
         import video_classif_b200.backbone as bb
 
         def timed(fn, flops_of):
@@ -314,12 +314,16 @@ def run_ours(args):
             return 2.0 * out.shape[0] * out.shape[1] * a[0].shape[1]
 
         def conv_flops(a, k, out):
-            w = a[1]
-            return 2.0 * out.numel() * w.shape[1] * w.shape[2] * w.shape[3]
+            x, w = a[0], a[1]
+            stride, pad = a[2], a[3]
+            P = (x.shape[1] + 2 * pad - w.shape[1]) // stride + 1
+            Q = (x.shape[2] + 2 * pad - w.shape[2]) // stride + 1
+            return 2.0 * x.shape[0] * P * Q * w.shape[0] * w.shape[1] * w.shape[2] * w.shape[3]
 
         ops.gemm_tn = timed(orig_gemm, gemm_flops)
         ops.conv2d_nhwc = timed(orig_conv, conv_flops)
-        bb.gemm_tn, bb.conv2d_nhwc = ops.gemm_tn, ops.conv2d_nhwc
+        ops.conv2d_bn_nhwc = timed(orig_convbn, conv_flops)      # a statistics-only pass counts its flops too
+        bb.gemm_tn, bb.conv2d_nhwc, bb.conv2d_bn_nhwc = ops.gemm_tn, ops.conv2d_nhwc, ops.conv2d_bn_nhwc
         try:
             for i in range(2):
                 events.clear()
@@ -327,8 +331,8 @@ def run_ours(args):
                 step(dev_x[i % NBUF], dev_y[i % NBUF])
                 torch.cuda.synchronize()
         finally:
-            ops.gemm_tn, ops.conv2d_nhwc = orig_gemm, orig_conv
-            bb.gemm_tn, bb.conv2d_nhwc = orig_gemm, orig_conv
+            ops.gemm_tn, ops.conv2d_nhwc, ops.conv2d_bn_nhwc = orig_gemm, orig_conv, orig_convbn
+            bb.gemm_tn, bb.conv2d_nhwc, bb.conv2d_bn_nhwc = orig_gemm, orig_conv, orig_convbn
         tot_ms = sum(s.elapsed_time(e) for s, e, _ in events)
         tot_fl = sum(f for _, _, f in events)
         achieved = tot_fl / (tot_ms * 1e-3) / 1e12

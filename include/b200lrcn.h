@@ -57,6 +57,36 @@ int b2_conv2d_nhwc_bf16(const void* x, int N, int H, int W, int C, const void* w
                         int stride, int pad, void* y, const float* bias, int out_bf16, int relu,
                         float* col_sum, float* col_sumsq, void* stream);
 
+/* Convolution with the train-mode BatchNorms of a ResNet block folded in (torchvision Bottleneck /
+ * BasicBlock under models.py:192, train_eval.py:12), all optional (NULL = off):
+ *   a_scale/a_shift [C]   : the INPUT is a raw conv output; relu?(x*scale+shift) is applied to the A
+ *                           operand tile in shared memory (zero padding stays zero) -- the normalised
+ *                           tensor is never materialised
+ *   col_sum/col_sumsq [Cout] (ACCUMULATED): statistics of the raw output; y = NULL makes this a
+ *                           statistics-only pass (nothing is written)
+ *   fin_*                 : the last CTA converts (col_sum, col_sumsq) into fin_scale/fin_shift [Cout]
+ *                           (biased variance, eps) and updates the running stats (momentum, unbiased
+ *                           variance); *fin_counter must be 0 at launch
+ *   o_scale/o_shift [Cout]: BatchNorm of the OUTPUT applied in the epilogue on the fp32 accumulators
+ *   res [N,P,Q,Cout] bf16 : shortcut added before the final ReLU; r_scale/r_shift = its own BatchNorm
+ *                           (down-sample branch stored raw) or NULL (identity shortcut)
+ * Bottleneck: conv1 (stats+fin) -> conv2 (a=bn1, stats+fin) -> conv3 statistics pass (a=bn2, y=NULL,
+ * stats+fin) -> conv3 output pass (a=bn2, o=bn3, res, relu). */
+int b2_conv2d_bn_nhwc_bf16(const void* x, int N, int H, int W, int C, const void* w, int Cout, int R, int S,
+                           int stride, int pad, void* y, const float* a_scale, const float* a_shift, int a_relu,
+                           const float* o_scale, const float* o_shift, const void* res, const float* r_scale,
+                           const float* r_shift, int relu, float* col_sum, float* col_sumsq,
+                           const float* fin_gamma, const float* fin_beta, float* fin_running_mean,
+                           float* fin_running_var, float* fin_scale, float* fin_shift, unsigned int* fin_counter,
+                           float eps, float momentum, void* stream);
+/* scale/shift of one BatchNorm2d from batch statistics (train: also the running-stat update) or from the
+ * running statistics (train = 0); b2_scale_shift_apply_nhwc: y = act(x*scale+shift [+ res | + res*rscale+rshift]). */
+int b2_bn_finalize_nhwc(const float* sum, const float* sumsq, const float* gamma, const float* beta,
+                        float* running_mean, float* running_var, long count, float eps, float momentum, int train,
+                        float* scale, float* shift, int C, void* stream);
+int b2_scale_shift_apply_nhwc(const void* x, void* y, long rows, int C, const float* scale, const float* shift,
+                              const void* res, const float* rscale, const float* rshift, int relu, void* stream);
+
 /* ---- backbone glue (NHWC bf16) ----------------------------------------------------------
  * b2_stem_im2col: NCHW fp32/bf16 frames -> [N*P*Q][Kp] bf16 patches of the 7x7/2 pad-3 stem conv,
  * column k = (c*7+r)*8+s (filter rows padded to 8 taps), Kp = 168.

@@ -80,6 +80,62 @@ def test_stem_conv_direct_toeplitz(ops, N, H, W):
     assert torch.equal(yb, y)
 
 
+@pytest.mark.parametrize("N,H,W,C,Cout,R,stride,pad", [
+    (3, 9, 9, 64, 64, 3, 1, 1), (2, 14, 14, 128, 256, 1, 1, 0), (5, 12, 10, 64, 128, 3, 2, 1), (70, 4, 4, 256, 64, 3, 1, 1),
+    (4, 7, 7, 128, 512, 1, 2, 0)])
+def test_conv_bn_folded(ops, N, H, W, C, Cout, R, stride, pad):
+    """b2_conv2d_bn_nhwc_bf16: input BatchNorm+ReLU applied to the A tile in shared memory (padding stays 0),
+    statistics + finalisation tail, statistics-only pass, and the BN3 + shortcut(+BN) + ReLU epilogue."""
+    torch.manual_seed(N * H + C + Cout)
+    xr = torch.randn(N, C, H, W).bfloat16()                         # raw output of the previous conv
+    a_sc, a_sh = torch.rand(C) + 0.5, torch.randn(C) * 0.3
+    w = (torch.randn(Cout, C, R, R) / (C * R * R) ** 0.5).bfloat16()
+    xin = torch.relu(xr.float() * a_sc.view(1, -1, 1, 1) + a_sh.view(1, -1, 1, 1)).bfloat16().float()
+    raw_ref = F.conv2d(xin, w.float(), stride=stride, padding=pad).permute(0, 2, 3, 1)        # [N,P,Q,Cout] fp32
+    xg = xr.permute(0, 2, 3, 1).contiguous().to(DEV)
+    wg = w.permute(0, 2, 3, 1).contiguous().to(DEV)
+    a = (a_sc.to(DEV), a_sh.to(DEV))
+    # (1) raw output + statistics + finalisation
+    gamma, beta = (torch.rand(Cout) + 0.5).to(DEV), torch.randn(Cout).to(DEV)
+    rm, rv = torch.zeros(Cout, device=DEV), torch.ones(Cout, device=DEV)
+    buf = torch.zeros(4 * Cout + 4, device=DEV)
+    s1, s2, fs, fh, cnt = buf[:Cout], buf[Cout:2 * Cout], buf[2 * Cout:3 * Cout], buf[3 * Cout:4 * Cout], buf[4 * Cout:]
+    y = ops.conv2d_bn_nhwc(xg, wg, stride, pad, a=a, stats=(s1, s2), fin=(gamma, beta, rm, rv, fs, fh, cnt, 1e-5, 0.1))
+    assert err(y.float(), raw_ref) < 6e-3
+    r = raw_ref.bfloat16().float().reshape(-1, Cout)
+    cntf = r.shape[0]
+    mean, var = r.mean(0), r.var(0, unbiased=False)
+    assert err(s1, r.sum(0), floor=1e-3 * r.abs().sum(0).max().item()) < 2e-2
+    assert err(s2, (r * r).sum(0)) < 2e-2
+    sc_ref = gamma.cpu() / torch.sqrt(var + 1e-5)
+    assert err(fs, sc_ref) < 2e-2 and err(fh, beta.cpu() - mean * sc_ref, floor=1.0) < 2e-2
+    assert err(rm, 0.1 * mean, floor=1e-2) < 2e-2 and err(rv, 0.9 + 0.1 * var * cntf / (cntf - 1)) < 2e-2
+    # (2) statistics-only pass gives the same sums and writes nothing
+    buf2 = torch.zeros(4 * Cout + 4, device=DEV)
+    none = ops.conv2d_bn_nhwc(xg, wg, stride, pad, a=a, stats=(buf2[:Cout], buf2[Cout:2 * Cout]),
+                              fin=(gamma, beta, None, None, buf2[2 * Cout:3 * Cout], buf2[3 * Cout:4 * Cout],
+                                   buf2[4 * Cout:], 1e-5, 0.1), store=False)
+    assert none is None
+    assert torch.allclose(buf2[:2 * Cout], buf[:2 * Cout], rtol=1e-5, atol=1e-3)
+    assert torch.allclose(buf2[2 * Cout:4 * Cout], buf[2 * Cout:4 * Cout], rtol=1e-4, atol=1e-4)
+    # (3) output pass: BN(out) + shortcut (identity / raw + own BN) + ReLU on the fp32 accumulators
+    res = torch.randn(raw_ref.shape).bfloat16()
+    r_sc, r_sh = torch.rand(Cout) + 0.5, torch.randn(Cout) * 0.3
+    o = (fs, fh)
+    out1 = ops.conv2d_bn_nhwc(xg, wg, stride, pad, a=a, o=o, res=res.to(DEV), relu=True)
+    ref1 = torch.relu(raw_ref * fs.cpu() + fh.cpu() + res.float())
+    assert err(out1.float(), ref1) < 8e-3
+    out2 = ops.conv2d_bn_nhwc(xg, wg, stride, pad, a=a, o=o, res=res.to(DEV), r=(r_sc.to(DEV), r_sh.to(DEV)), relu=True)
+    ref2 = torch.relu(raw_ref * fs.cpu() + fh.cpu() + res.float() * r_sc + r_sh)
+    assert err(out2.float(), ref2) < 8e-3
+    out3 = ops.conv2d_bn_nhwc(xg, wg, stride, pad, a=a, o=o, relu=False)
+    assert err(out3.float(), raw_ref * fs.cpu() + fh.cpu()) < 8e-3
+    # (4) stand-alone scale/shift apply (BasicBlock output)
+    out4 = ops.scale_shift_apply(y.clone(), fs, fh, res=res.to(DEV), r=(r_sc.to(DEV), r_sh.to(DEV)), relu=True)
+    ref4 = torch.relu(y.float().cpu() * fs.cpu() + fh.cpu() + res.float() * r_sc + r_sh)
+    assert err(out4.float(), ref4) < 8e-3
+
+
 def test_ingest_bit_exact_vs_cv2_golden(ops):
     g = np.load(os.path.join(GOLDEN, "resize_cv2.npz"))
     i = 0

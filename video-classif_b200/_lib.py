@@ -9,7 +9,7 @@ import re
 from ctypes import c_char_p, c_float, c_int, c_long, c_ulonglong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200lrcn.so")
+LIB_PATH = os.environ.get("B2_LIB_OVERRIDE") or os.path.join(_HERE, "libb200lrcn.so")   # override: A/B kernel experiments
 HEADER_PATH = os.path.join(_HERE, "..", "include", "b200lrcn.h")
 
 

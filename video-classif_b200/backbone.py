@@ -15,11 +15,14 @@ The torchvision module is only a PARAMETER CONTAINER (state_dict keys / shapes /
 the reference's); its forward is never called."""
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
 from ._lib import call, ptr, stream_ptr
-from .ops import BF16, F32, conv2d_nhwc, gemm_tn, pack_stem_weight, stem_conv
+from .ops import (BF16, F32, conv2d_bn_nhwc, conv2d_nhwc, gemm_tn, pack_stem_weight, scale_shift_apply,
+                  stem_conv)
 
 SUPPORTED = ("resnet18", "resnet34", "resnet50", "resnet101", "resnet152")
 STEM_KP = 168   # stem patch columns: (c*7 + r)*8 + s, filter rows padded from 7 to 8 taps
@@ -40,11 +43,13 @@ def make_backbone(name: str, pretrained: bool = False):
 
 
 class ResNetRunner:
+    FUSE_BN = os.environ.get("B2_FUSE_BN", "0") == "1"   # class default; tests run both settings
     def __init__(self, net):
         self.net = net
         self._wcache = None
         self._wkey = None
         self.stem_impl = "direct"     # "im2col": patch matrix + plain GEMM (A/B parity tests)
+        self.fuse_bn = ResNetRunner.FUSE_BN   # BatchNorms folded into the conv kernels vs stand-alone bn_apply passes
 
     # ---- weights in kernel layout: [Cout, R, S, C] bf16 (K-major), stem [64, STEM_KP] ----
     def _weights(self):
@@ -104,14 +109,34 @@ class ResNetRunner:
         bns = [m for m in net.modules() if isinstance(m, torch.nn.BatchNorm2d)]
         train = bool(training)
         maxc = max(b.num_features for b in bns)
-        stat_buf = torch.zeros((len(bns), 2, maxc), device=dev, dtype=F32) if train else None
+        # per BatchNorm: [sum | sumsq | scale | shift] (maxc floats each) + a finalisation counter word
+        stat_buf = torch.zeros((len(bns), 4 * maxc + 4), device=dev, dtype=F32)
         bn_index = {id(b): i for i, b in enumerate(bns)}
 
         def stats_of(bn):
             if not train:
                 return None
             sb = stat_buf[bn_index[id(bn)]]
-            return (sb[0], sb[1])
+            return (sb[0:maxc], sb[maxc:2 * maxc])
+
+        def ss_of(bn):                         # (scale, shift) written by the producer's finalisation tail
+            sb = stat_buf[bn_index[id(bn)]]
+            return (sb[2 * maxc:3 * maxc], sb[3 * maxc:4 * maxc])
+
+        def fin_of(bn):
+            if not train:
+                return None
+            sb = stat_buf[bn_index[id(bn)]]
+            return (bn.weight, bn.bias, bn.running_mean, bn.running_var, sb[2 * maxc:3 * maxc], sb[3 * maxc:4 * maxc],
+                    sb[4 * maxc:], bn.eps, bn.momentum if bn.momentum is not None else 0.1)
+
+        fuse = self.fuse_bn
+        if fuse and not train:                 # eval: scale/shift straight from the running statistics
+            for b in bns:
+                sc, sh = ss_of(b)
+                call("b2_bn_finalize_nhwc", 0, 0, b.weight.data_ptr(), b.bias.data_ptr(), b.running_mean.data_ptr(),
+                     b.running_var.data_ptr(), 1, float(b.eps), 0.1, 0, sc.data_ptr(), sh.data_ptr(), b.num_features,
+                     stream_ptr())
 
         st = stream_ptr()
         # ---- stem ----
@@ -141,6 +166,44 @@ class ResNetRunner:
                 pfx = f"layer{li}.{bi}"
                 stride = blk.stride if isinstance(blk.stride, int) else blk.stride[0]
                 bottleneck = hasattr(blk, "conv3")
+                if fuse:
+                    # BatchNorms folded into the conv kernels: statistics + finalisation in the producer,
+                    # normalise+ReLU in the consumer's A-tile transform, BN3 + shortcut + ReLU in the epilogue
+                    # of a second conv3 pass (gemm_tc.cu); no stand-alone BN pass over the activations
+                    ds = blk.downsample is not None
+                    if bottleneck:
+                        r1 = conv2d_bn_nhwc(y, w[pfx + ".conv1"], 1, 0, stats=stats_of(blk.bn1), fin=fin_of(blk.bn1))
+                        # a 3x3 consumer would re-normalise every input pixel 9 times (once per tap) and
+                        # doubles the shared-memory traffic per k-block: one in-place pass over this small
+                        # tensor is cheaper; the 1x1 consumer (conv3) takes the A transform
+                        sc1, sh1 = ss_of(blk.bn1)
+                        scale_shift_apply(r1, sc1, sh1, relu=True)
+                        r2 = conv2d_bn_nhwc(r1, w[pfx + ".conv2"], stride, 1, stats=stats_of(blk.bn2),
+                                            fin=fin_of(blk.bn2))
+                        del r1
+                        if ds:
+                            dbn = blk.downsample[1]
+                            rd = conv2d_bn_nhwc(y, w[pfx + ".downsample.0"], stride, 0, stats=stats_of(dbn),
+                                                fin=fin_of(dbn))
+                        if train:              # statistics-only pass of conv3
+                            conv2d_bn_nhwc(r2, w[pfx + ".conv3"], 1, 0, a=ss_of(blk.bn2), stats=stats_of(blk.bn3),
+                                           fin=fin_of(blk.bn3), store=False)
+                        y = conv2d_bn_nhwc(r2, w[pfx + ".conv3"], 1, 0, a=ss_of(blk.bn2), o=ss_of(blk.bn3),
+                                           res=rd if ds else y, r=ss_of(dbn) if ds else None, relu=True)
+                        del r2
+                    else:
+                        r1 = conv2d_bn_nhwc(y, w[pfx + ".conv1"], stride, 1, stats=stats_of(blk.bn1), fin=fin_of(blk.bn1))
+                        sc1, sh1 = ss_of(blk.bn1)
+                        scale_shift_apply(r1, sc1, sh1, relu=True)
+                        r2 = conv2d_bn_nhwc(r1, w[pfx + ".conv2"], 1, 1, stats=stats_of(blk.bn2), fin=fin_of(blk.bn2))
+                        del r1
+                        if ds:
+                            dbn = blk.downsample[1]
+                            rd = conv2d_bn_nhwc(y, w[pfx + ".downsample.0"], stride, 0, stats=stats_of(dbn),
+                                                fin=fin_of(dbn))
+                        sc, sh = ss_of(blk.bn2)
+                        y = scale_shift_apply(r2, sc, sh, res=rd if ds else y, r=ss_of(dbn) if ds else None, relu=True)
+                    continue
                 if bottleneck:
                     o = conv2d_nhwc(y, w[pfx + ".conv1"], 1, 0, stats_of(blk.bn1))
                     o = self._bn(o, blk.bn1, stats_of(blk.bn1), o.numel() // o.shape[-1], train)

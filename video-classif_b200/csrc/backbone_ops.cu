@@ -122,6 +122,43 @@ bn_apply_reg_kernel(const bf16* x, bf16* y, long rows, int C, BnSrc bn, const bf
   }
 }
 
+// y = act( x * scale[c] + shift[c] [+ res | + res * rscale[c] + rshift[c]] ) with PRECOMPUTED per-channel
+// scale/shift (written by the BatchNorm finalisation tail of the producing conv kernel, gemm_tc.cu).
+// Any C multiple of 8: the channel group of a vector is recomputed per element (one integer modulo).
+template <int RES_MODE>
+__global__ void __launch_bounds__(256)
+scale_shift_apply_kernel(const bf16* x, bf16* y, long rows, int C, const float* __restrict__ scale,
+                         const float* __restrict__ shift, const bf16* __restrict__ res,
+                         const float* __restrict__ rscale, const float* __restrict__ rshift, int relu) {
+  const int vec_per_row = C >> 3;
+  const long total = rows * vec_per_row;
+  for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(v % vec_per_row) << 3;
+    float a[8], r[8];
+    load8(x + v * 8, a);
+    if (RES_MODE) load8(res + v * 8, r);
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + c0)), s1 = __ldg(reinterpret_cast<const float4*>(scale + c0 + 4));
+    const float4 h0 = __ldg(reinterpret_cast<const float4*>(shift + c0)), h1 = __ldg(reinterpret_cast<const float4*>(shift + c0 + 4));
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+    float rs[8], rh[8];
+    if (RES_MODE == 2) {
+      const float4 t0 = __ldg(reinterpret_cast<const float4*>(rscale + c0)), t1 = __ldg(reinterpret_cast<const float4*>(rscale + c0 + 4));
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(rshift + c0)), g1 = __ldg(reinterpret_cast<const float4*>(rshift + c0 + 4));
+      rs[0] = t0.x; rs[1] = t0.y; rs[2] = t0.z; rs[3] = t0.w; rs[4] = t1.x; rs[5] = t1.y; rs[6] = t1.z; rs[7] = t1.w;
+      rh[0] = g0.x; rh[1] = g0.y; rh[2] = g0.z; rh[3] = g0.w; rh[4] = g1.x; rh[5] = g1.y; rh[6] = g1.z; rh[7] = g1.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float o = fmaf(a[j], sc[j], sh[j]);
+      if (RES_MODE == 1) o += r[j];
+      if (RES_MODE == 2) o += fmaf(r[j], rs[j], rh[j]);
+      a[j] = relu ? fmaxf(o, 0.f) : o;
+    }
+    store8(y + v * 8, a);
+  }
+}
+
 // generic fallback (any C multiple of 8): scale/shift staged in shared memory
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const bf16* x, bf16* y, long rows, int C, BnSrc bn, int res_mode,
@@ -311,6 +348,28 @@ B2_API int b2_bn_apply_nhwc(const void* x, void* y, long rows, int C, const floa
         (const bf16*)x, (bf16*)y, rows, C, bn, res_mode, (const bf16*)res, rbn, inv, unbias, eps, momentum, train, relu);
   }
   B2_LAUNCH_CHECK("bn_apply_kernel");
+  return 0;
+}
+
+B2_API int b2_scale_shift_apply_nhwc(const void* x, void* y, long rows, int C, const float* scale, const float* shift,
+                                     const void* res, const float* rscale, const float* rshift, int relu,
+                                     void* stream) {
+  B2_ARG_CHECK(x && y && scale && shift && rows > 0, "b2_scale_shift_apply_nhwc: null pointer or empty");
+  B2_ARG_CHECK(C % 8 == 0, "b2_scale_shift_apply_nhwc: C must be a multiple of 8 (got %d)", C);
+  B2_ARG_CHECK((rscale == nullptr) == (rshift == nullptr) && (rscale == nullptr || res != nullptr),
+               "b2_scale_shift_apply_nhwc: shortcut BatchNorm needs rscale, rshift and res");
+  const int grid = grid_for(rows * (C / 8), 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (res == nullptr)
+    scale_shift_apply_kernel<0><<<grid, 256, 0, st>>>((const bf16*)x, (bf16*)y, rows, C, scale, shift, nullptr, nullptr,
+                                                      nullptr, relu);
+  else if (rscale == nullptr)
+    scale_shift_apply_kernel<1><<<grid, 256, 0, st>>>((const bf16*)x, (bf16*)y, rows, C, scale, shift, (const bf16*)res,
+                                                      nullptr, nullptr, relu);
+  else
+    scale_shift_apply_kernel<2><<<grid, 256, 0, st>>>((const bf16*)x, (bf16*)y, rows, C, scale, shift, (const bf16*)res,
+                                                      rscale, rshift, relu);
+  B2_LAUNCH_CHECK("scale_shift_apply_kernel");
   return 0;
 }
 

@@ -1,6 +1,7 @@
-// tcgen05 / TMEM / TMA GEMM and implicit-GEMM convolution for sm_100a.
+// tcgen05 / TMEM / TMA GEMM and implicit-GEMM convolution for sm_100a, with the train-mode
+// BatchNorm of a ResNet block folded into its producer and consumer.
 //
-//   D[M,N] = A[M,K] * B[N,K]^T (+ bias[N]) (ReLU) ; fp32 accumulate in TMEM, bf16 operands.
+//   D[M,N] = epi( tf(A)[M,K] * B[N,K]^T )          fp32 accumulate in TMEM, bf16 operands.
 //
 // A is fed by TMA either from a plain row-major matrix (2-D tiled tensor map: Linear layers,
 // 1x1 stride-1 convolutions over NHWC activations, hoisted LSTM gate GEMMs) or straight from an
@@ -8,12 +9,23 @@
 // per filter tap and 64-channel slab, zero padding and stride handled by the copy engine), so no
 // im2col matrix ever exists in HBM.  B (the weights, [N,K] K-major) always comes from a 2-D map.
 //
-// Kernel anatomy: persistent CTAs (one per SM), 6 warps:
-//   warp 0      TMA producer           (smem ring of kStages {A 128x64, B BNx64} bf16 tiles, SW128)
-//   warp 1      MMA issuer + TMEM owner (tcgen05.mma cta_group::1, M=128, N=BN, K=16 per instr)
-//   warps 2..5  epilogue               (tcgen05.ld 32x32b -> bias/ReLU/bf16 -> global, plus the
-//                                       per-column sum / sum-of-squares the train-mode BatchNorm
-//                                       that follows needs, so BN statistics cost no extra pass)
+// BatchNorm fusion (train mode needs the statistics of the WHOLE conv output before anything can be
+// normalised, so it is split across kernels instead of costing extra passes over the activations):
+//   * producer epilogue: per-column sum / sum-of-squares of the raw conv output (col_sum/col_sumsq);
+//     the last CTA to finish turns them into per-channel scale/shift (+ running-stat update): BnFinal
+//   * consumer prologue ("A transform"): 4 extra warps rewrite each A tile in shared memory as
+//     relu(a * scale[c] + shift[c]) between the TMA arrival and the MMA, so the normalised tensor is
+//     never materialised (zero-padding taps stay zero)
+//   * block output: the conv3 GEMM runs twice -- a statistics-only pass (store = 0), then a pass whose
+//     epilogue applies BN3, adds the shortcut (identity, or the raw down-sample conv with its own
+//     BN) and ReLUs -- instead of writing the raw tensor and re-reading it.
+//
+// Kernel anatomy: persistent CTAs (one per SM), 14 warps:
+//   warp 0        TMA producer           (smem ring of kStages {A 128x64, B BNx64} bf16 tiles, SW128)
+//   warp 1        MMA issuer + TMEM owner (tcgen05.mma cta_group::1, M=128, N=BN, K=16 per instr)
+//   warps 2..9    epilogue               (tcgen05.ld 32x32b -> bias / BN / residual / ReLU -> bf16 ->
+//                                         swizzled staging tile -> TMA bulk store; column statistics)
+//   warps 10..13  A transform            (idle unless at.scale is set)
 // TMEM holds two BN-column accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "tc_ptx.cuh"
 
@@ -26,7 +38,10 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
 constexpr int kEpiWarps = 8;                      // two warps per TMEM lane quarter
-constexpr int kThreads = 64 + 32 * kEpiWarps;    // TMA warp + MMA warp + epilogue warps
+constexpr int kTfWarps = 4;                       // A-transform warps
+constexpr int kEpiThread0 = 64;
+constexpr int kTfThread0 = 64 + 32 * kEpiWarps;
+constexpr int kThreads = kTfThread0 + 32 * kTfWarps;
 
 using namespace tc;
 
@@ -37,6 +52,24 @@ struct ConvGeom {   // im2col producer geometry (all zero for plain GEMM)
   int c_slabs;      // C / 64
   int stride;
   int lower_w, lower_h;   // = -pad
+  int H, W;         // input height / width (padding mask of the A transform)
+};
+
+struct ATransform {      // a' = relu?(a * scale[c] + shift[c]) applied to the A operand in shared memory
+  const float* scale;    // [K channels] or null (no transform)
+  const float* shift;
+  int relu;
+};
+
+struct BnFinal {         // BatchNorm finalisation by the last CTA: (col_sum, col_sumsq) -> scale/shift
+  float* scale;          // [N] or null (no finalisation)
+  float* shift;
+  const float* gamma;
+  const float* beta;
+  float* running_mean;   // may be null
+  float* running_var;
+  unsigned int* counter; // zeroed by the caller before the launch
+  float inv_count, unbias, eps, momentum;
 };
 
 struct EpiParams {
@@ -44,11 +77,19 @@ struct EpiParams {
   long ldd;          // elements
   const float* bias; // [N] or null
   const float* bias2; // [N] or null (second bias vector, e.g. LSTM b_hh)
-  float* col_sum;    // [N] or null  (atomicAdd)
+  float* col_sum;    // [N] or null  (atomicAdd) -- statistics of the raw (pre-BN) output
   float* col_sumsq;  // [N] or null
   int out_bf16;      // 1: bf16 out, 0: fp32 out
   int relu;
   int tma_store;     // bf16 output leaves through smem staging + TMA bulk stores (tmap_d valid)
+  int store;         // 0: statistics-only pass, D is never written
+  const float* o_scale;   // [N] or null: BatchNorm of the output applied in the epilogue
+  const float* o_shift;
+  const bf16* res;        // [M][ldres] or null: shortcut added before the ReLU
+  long ldres;
+  const float* r_scale;   // [N] or null: BatchNorm of the shortcut (down-sample branch)
+  const float* r_shift;
+  BnFinal fin;
 };
 
 constexpr int kStgBytes = 32 * 64;  // epilogue staging tile: 32 rows x 32 bf16 (64-byte rows, SWIZZLE_64B)
@@ -56,20 +97,34 @@ constexpr int kStgBytes = 32 * 64;  // epilogue staging tile: 32 rows x 32 bf16 
 template <int BN>
 struct SmemLayout {
   static constexpr int kStageBytes = (BM * BK + BN * BK) * 2;
-  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 5 : (BN >= 64 ? 7 : 8));
-  static constexpr int kStgBufs = (BN >= 256) ? 1 : 2;   // staging tiles per epilogue warp
+  #ifndef B2_STAGES256
+#define B2_STAGES256 3
+#endif
+  static constexpr int kStages = (BN >= 256) ? B2_STAGES256 : (BN >= 128 ? 5 : (BN >= 64 ? 7 : 8));
+  static constexpr int kStgBufs = 2;                     // output staging tiles per epilogue warp
   static constexpr int kTileBytes = kStageBytes * kStages;
   static constexpr int kBarOffset = kTileBytes;
-  static constexpr int kStatOffset = kBarOffset + (2 * kStages + 4) * 8 + 16;     // per-CTA column statistics [4 quarters][2][BN]
+  static constexpr int kNumBars = 3 * kStages + 4 + kEpiWarps;
+  // [4 quarters][2][BN] column statistics at flush time; the SAME bytes hold the per-column
+  // {o_scale, o_shift, r_scale, r_shift}[BN] of an output pass (statistics and output BN never mix)
+  static constexpr int kStatOffset = (kBarOffset + kNumBars * 8 + 16 + 15) / 16 * 16;
   static constexpr int kScratchOffset = kStatOffset + 4 * 2 * BN * 4;
   static constexpr int kScratchOffset1k = (kScratchOffset + 1023) / 1024 * 1024;        // staging tiles 1024-aligned
-  static constexpr int kTotal = kScratchOffset1k + kEpiWarps * kStgBufs * kStgBytes + 1024;   // +1024 alignment slack
+  static constexpr int kResOffset = kScratchOffset1k + kEpiWarps * kStgBufs * kStgBytes;   // shortcut tiles (TMA loads)
+  static constexpr int kTotal = kResOffset + kEpiWarps * kStgBytes + 1024;   // +1024 alignment slack
 };
+
+__device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
 
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-               const __grid_constant__ CUtensorMap tmap_d, int M, int N, int K, ConvGeom g, EpiParams ep) {
+               const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_r, int M, int N,
+               int K, ConvGeom g, ATransform at, EpiParams ep) {
   using L = SmemLayout<BN>;
   constexpr int kStages = L::kStages;
   constexpr uint32_t kTmemCols = 2 * BN;  // two accumulators (32 <= cols <= 512, power of two)
@@ -79,17 +134,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
   uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tfull_bar = empty_bar + kStages;
+  uint64_t* tf_bar = empty_bar + kStages;
+  uint64_t* tfull_bar = tf_bar + kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  // Column statistics (sum, sum of squares of the stored values) are accumulated per CTA in shared
-  // memory over all consecutive tiles of one n-block and flushed to global memory only when the
-  // n-block changes (tiles are ordered m-fastest, so that is at most n_blocks times per CTA).
-  // One private copy per TMEM lane quarter: the two warps of a quarter own disjoint chunks, so a slot
-  // has exactly one writer and plain read-modify-write replaces shared-memory CAS atomics.
-  float* stat_s = reinterpret_cast<float*>(smem + L::kStatOffset);   // [4][2][BN]
+  uint64_t* res_bar = tempty_bar + 2;            // one per epilogue warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + kEpiWarps);
+  // Column statistics (sum, sum of squares of the stored values) live in REGISTERS of the epilogue
+  // warps (each warp owns fixed 32-column chunks of the n-block) over all consecutive tiles of one
+  // n-block; they are combined through this buffer ([4 quarters][2][BN], one writer per slot) and
+  // flushed to global memory only when the n-block changes (tiles are ordered m-fastest).
+  float* stat_s = reinterpret_cast<float*>(smem + L::kStatOffset);
   uint8_t* staging_s = smem + L::kScratchOffset1k;
+  uint8_t* res_s = smem + L::kResOffset;
   const bool want_stats = ep.col_sum != nullptr;
+  const bool use_tf = at.scale != nullptr;
   for (int i = threadIdx.x; i < 8 * BN; i += kThreads) stat_s[i] = 0.f;
 
   const int warp = threadIdx.x >> 5;
@@ -105,11 +163,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
+      mbar_init(&tf_bar[i], 32 * kTfWarps);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], kEpiWarps);
     }
+    for (int i = 0; i < kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -140,17 +200,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           cw = g.lower_w + q * g.stride;
           ch = g.lower_h + p * g.stride;
         }
+        int tap = 0, slab = 0;                       // k-block -> (filter tap, 64-channel slab) without divisions
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::kStageBytes;
           uint8_t* sb = sa + BM * BK * 2;
           mbar_expect_tx(&full_bar[stage], L::kStageBytes);
           if (g.is_conv) {
-            const int tap = kb / g.c_slabs;
-            const int c0 = (kb - tap * g.c_slabs) * BK;
             const int r = tap / g.S;
             const int s = tap - r * g.S;
-            tma_load_im2col_4d(sa, &tmap_a, &full_bar[stage], c0, cw, ch, cn, (uint16_t)s, (uint16_t)r);
+            tma_load_im2col_4d(sa, &tmap_a, &full_bar[stage], slab * BK, cw, ch, cn, (uint16_t)s, (uint16_t)r);
+            if (++slab == g.c_slabs) {
+              slab = 0;
+              ++tap;
+            }
           } else {
             tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
           }
@@ -165,6 +228,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     constexpr uint32_t idesc = make_idesc(BM, BN);
+    uint64_t* ready_bar = use_tf ? tf_bar : full_bar;   // with a transform the MMA waits for the rewritten tile
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -175,7 +239,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
       for (int kb = 0; kb < k_blocks; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+        mbar_wait(&ready_bar[stage], phase);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
@@ -197,189 +261,308 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
       }
     }
-  } else {
+  } else if (warp < 2 + kEpiWarps) {
     // =========================== epilogue (warps 2..9) ===========================
+    constexpr int kChunks = BN / 32;
+    constexpr int kMyChunks = (kChunks + 1) / 2;   // chunks per warp: ch = half + 2 j
     const int quarter = warp & 3;          // TMEM lane quarter this warp may read (hardware rule: warp % 4)
     const int half = (warp - 2) >> 2;      // the two warps of a quarter take alternate 32-column chunks
-    const int epi_tid = threadIdx.x - 64;
+    const int epi_tid = threadIdx.x - kEpiThread0;
     uint8_t* stg_base = staging_s + (warp - 2) * L::kStgBufs * kStgBytes;
+    uint8_t* res_stg = res_s + (warp - 2) * kStgBytes;
+    uint64_t* my_res_bar = &res_bar[warp - 2];
+    uint32_t res_phase = 0;
+    const bool has_res = ep.res != nullptr;
+    const bool has_obn = ep.o_scale != nullptr;
+    const bool has_rbn = ep.r_scale != nullptr;
+    const bool post = has_obn || has_res;
+    const bool stats_bf16 = want_stats && ep.out_bf16;
+    float* ss_s = stat_s;                  // [4][BN]: o_scale, o_shift, r_scale, r_shift of the current n-block
     int stg_buf = 0;
     int it = 0;
-    int stat_nblk = -1;
+    int cur_nblk = -1;
+    // statistics: lane (w = lane & 15, hf = lane >> 4) sums columns 2w, 2w+1 over rows 16 hf .. 16 hf + 15;
+    // the per-warp partial sums accumulate in stat_s (one writer per slot) until the n-block changes
+    const int sw_w = lane & 15, sw_hf = lane >> 4;
+    const int sw = (lane >> 1) & 3;        // SWIZZLE_64B phase of this lane's staging row
+    // staging reads: row r = i (hf = 0) or 16 + (i ^ 1) (hf = 1) so the two half-warps never share a
+    // bank; word address = r*64 + (((w >> 2) ^ ((r >> 1) & 3)) << 4) + (w & 3) * 4
+    uint32_t rd_off[2][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t col = (uint32_t)((((sw_w >> 2) ^ k) << 4) + (sw_w & 3) * 4) + (uint32_t)(sw_hf * 1024);
+      rd_off[0][k] = col + (uint32_t)(sw_hf * 64);    // even i: row i + hf
+      rd_off[1][k] = col - (uint32_t)(sw_hf * 64);    // odd i:  row i - hf
+    }
+    const bool my_chunk0_valid = half < kChunks;
+    // shortcut tiles arrive by TMA one chunk ahead: (tile, j) -> 32x32 bf16 box at (row0, col0)
+    auto issue_res = [&](int tile, int j) {
+      const int n_blk = tile / m_blocks;
+      const int m_blk = tile - n_blk * m_blocks;
+      mbar_expect_tx(my_res_bar, kStgBytes);
+      tma_load_2d(res_stg, &tmap_r, my_res_bar, n_blk * BN + (half + 2 * j) * 32, m_blk * BM + quarter * 32);
+    };
+    if (has_res && my_chunk0_valid && lane == 0 && (int)blockIdx.x < num_tiles) issue_res(blockIdx.x, 0);
+
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int n_blk = tile / m_blocks;
       const int m_blk = tile - n_blk * m_blocks;
-      if (want_stats && n_blk != stat_nblk) {
-        if (stat_nblk >= 0) {                       // flush the finished n-block (rare)
+      if (n_blk != cur_nblk) {
+        if (want_stats && cur_nblk >= 0) {
+          // ---- flush the finished n-block: stat_s (4 quarter copies) -> global atomics, then clear
           asm volatile("bar.sync 1, 256;" ::: "memory");
           for (int c = epi_tid; c < BN; c += 32 * kEpiWarps) {
-            const int col = stat_nblk * BN + c;
+            const int col = cur_nblk * BN + c;
             if (col < N) {
               atomicAdd(ep.col_sum + col, stat_s[c] + stat_s[2 * BN + c] + stat_s[4 * BN + c] + stat_s[6 * BN + c]);
-              atomicAdd(ep.col_sumsq + col,
-                        stat_s[BN + c] + stat_s[3 * BN + c] + stat_s[5 * BN + c] + stat_s[7 * BN + c]);
+              atomicAdd(ep.col_sumsq + col, stat_s[BN + c] + stat_s[3 * BN + c] + stat_s[5 * BN + c] + stat_s[7 * BN + c]);
             }
 #pragma unroll
             for (int qq = 0; qq < 8; ++qq) stat_s[qq * BN + c] = 0.f;
           }
           asm volatile("bar.sync 1, 256;" ::: "memory");
         }
-        stat_nblk = n_blk;
+        if (post) {
+          // ---- per-column BatchNorm coefficients of the new n-block -> shared memory
+          asm volatile("bar.sync 1, 256;" ::: "memory");       // everyone is done with the previous block's values
+          for (int c = epi_tid; c < BN; c += 32 * kEpiWarps) {
+            const int col = n_blk * BN + c;
+            const bool ok = col < N;
+            ss_s[c] = (has_obn && ok) ? __ldg(ep.o_scale + col) : 1.f;
+            ss_s[BN + c] = (has_obn && ok) ? __ldg(ep.o_shift + col) : 0.f;
+            ss_s[2 * BN + c] = (has_rbn && ok) ? __ldg(ep.r_scale + col) : 1.f;
+            ss_s[3 * BN + c] = (has_rbn && ok) ? __ldg(ep.r_shift + col) : 0.f;
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+        cur_nblk = n_blk;
       }
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
       const int row = m_blk * BM + quarter * 32 + lane;
       const bool row_ok = row < M;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
 #pragma unroll 1
-      for (int ch = half; ch < BN / 32; ch += 2) {
+      for (int j = 0; j < kMyChunks; ++j) {
+        const int ch = half + 2 * j;
         const int col0 = n_blk * BN + ch * 32;
-        if (col0 >= N) break;  // warp-uniform
-        uint32_t raw[32];
-        tc_ld32(tmem_base + (uint32_t)(acc * BN + ch * 32) + ((uint32_t)(quarter * 32) << 16), raw);
-        tc_wait_ld();
-        float v[32];
+        if (ch < kChunks && col0 < N) {   // warp-uniform
+          const bool full_chunk = (col0 + 32 <= N);
+          uint32_t raw[32];
+          tc_ld32(tmem_base + (uint32_t)(acc * BN + ch * 32) + ((uint32_t)(quarter * 32) << 16), raw);
+          uint4 rres[4];
+          if (has_res) {   // this chunk's shortcut tile: own row (64 B) out of the swizzled TMA tile
+            mbar_wait(my_res_bar, res_phase);
+            res_phase ^= 1;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-        const bool full_chunk = (col0 + 32 <= N);
-        // every option below is a WARP-UNIFORM branch around its own loop: predicating 64 bias loads
-        // and adds per chunk (the first version) cost more issue slots than the whole rest of the epilogue
-        if (ep.bias != nullptr) {
-          if (full_chunk) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 bv = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + j));
-              v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
+            for (int c = 0; c < 4; ++c) rres[c] = *reinterpret_cast<const uint4*>(res_stg + lane * 64 + ((c ^ sw) << 4));
+            __syncwarp();
+            if (lane == 0) {                                   // prefetch the next chunk this warp will handle
+              if (j + 1 < kMyChunks && half + 2 * (j + 1) < kChunks) issue_res(tile, j + 1);
+              else if (tile + (int)gridDim.x < num_tiles) issue_res(tile + gridDim.x, 0);
             }
-          } else {
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < N) v[j] += __ldg(ep.bias + col0 + j);
           }
-        }
-        if (ep.bias2 != nullptr) {
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < N) v[j] += __ldg(ep.bias2 + col0 + j);
-        }
-        if (ep.relu) {
+          tc_wait_ld();
+          float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-        }
-        if (ep.out_bf16) {
+          for (int jj = 0; jj < 32; ++jj) v[jj] = __uint_as_float(raw[jj]);
+          // every option below is a WARP-UNIFORM branch around its own loop
+          if (ep.bias != nullptr) {
+            if (full_chunk) {
+#pragma unroll
+              for (int jj = 0; jj < 32; jj += 4) {
+                const float4 bv = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + jj));
+                v[jj] += bv.x; v[jj + 1] += bv.y; v[jj + 2] += bv.z; v[jj + 3] += bv.w;
+              }
+            } else {
+              for (int jj = 0; jj < 32; ++jj)
+                if (col0 + jj < N) v[jj] += __ldg(ep.bias + col0 + jj);
+            }
+          }
+          if (ep.bias2 != nullptr) {
+            for (int jj = 0; jj < 32; ++jj)
+              if (col0 + jj < N) v[jj] += __ldg(ep.bias2 + col0 + jj);
+          }
+          // raw-output statistics are taken on the bf16-rounded conv result BEFORE any output BN
           uint32_t pk[16];
+          if (ep.out_bf16 && (stats_bf16 || !post)) {
+            if (ep.relu && !post) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+              for (int jj = 0; jj < 16; ++jj) pk[jj] = pack_bf16x2_relu(v[2 * jj], v[2 * jj + 1]);
+            } else {
+#pragma unroll
+              for (int jj = 0; jj < 16; ++jj) pk[jj] = pack_bf16x2(v[2 * jj], v[2 * jj + 1]);
+            }
+          }
           uint8_t* stg = stg_base + stg_buf * kStgBytes;
-          const bool staged = ep.tma_store || want_stats;
-          if (staged) {
-            // The 32x32 bf16 chunk goes to a 64-byte-swizzled staging tile (lane = row, 4 x STS.128,
-            // conflict-free).  From there (a) one TMA bulk store writes it to global memory in full
-            // 64-byte row segments without occupying the LSU or any registers, and (b) the BN
-            // statistics are column sums read straight back from the tile (lane pairs share a word).
+          if (stats_bf16) {
+            // 32x32 bf16 chunk -> 64-byte-swizzled staging tile (lane = row, 4 x STS.128, conflict-free);
+            // column sums are read straight back from the tile.
             if (ep.tma_store && lane == 0) bulk_wait_read<L::kStgBufs - 1>();   // tile free again?
             __syncwarp();
-            if (want_stats && !row_ok) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) pk[j] = 0u;       // rows past M: no statistics (TMA clips the store)
-            }
-            const int sw = (lane >> 1) & 3;
 #pragma unroll
             for (int c = 0; c < 4; ++c)
               *reinterpret_cast<uint4*>(stg + lane * 64 + ((c ^ sw) << 4)) =
-                  make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-          }
-          if (ep.tma_store) {
-            fence_proxy_async_smem();
+                  row_ok ? make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]) : make_uint4(0u, 0u, 0u, 0u);
             __syncwarp();
-            if (lane == 0) {
-              tma_store_2d(&tmap_d, stg, col0, m_blk * BM + quarter * 32);
-              bulk_commit();
+            float2 s1a = make_float2(0.f, 0.f), s1b = s1a, s2a = s1a, s2b = s1a;
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+              const uint32_t u0 = *reinterpret_cast<const uint32_t*>(stg + rd_off[0][(i >> 1) & 3] + i * 64);
+              const uint32_t u1 = *reinterpret_cast<const uint32_t*>(stg + rd_off[1][(i >> 1) & 3] + (i + 1) * 64);
+              const float2 x0 = make_float2(__uint_as_float(u0 << 16), __uint_as_float(u0 & 0xffff0000u));
+              const float2 x1 = make_float2(__uint_as_float(u1 << 16), __uint_as_float(u1 & 0xffff0000u));
+              s1a = __fadd2_rn(s1a, x0);
+              s1b = __fadd2_rn(s1b, x1);
+              s2a = __ffma2_rn(x0, x0, s2a);
+              s2b = __ffma2_rn(x1, x1, s2b);
             }
-          } else if (row_ok) {
-            if (staged) __syncwarp();
-            bf16* dp = reinterpret_cast<bf16*>(ep.D) + (long)row * ep.ldd + col0;
-            if (full_chunk && ((reinterpret_cast<uintptr_t>(dp) & 31) == 0)) {
-              asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dp), "r"(pk[0]), "r"(pk[1]),
-                           "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
-                           : "memory");
-              asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dp + 16), "r"(pk[8]), "r"(pk[9]),
-                           "r"(pk[10]), "r"(pk[11]), "r"(pk[12]), "r"(pk[13]), "r"(pk[14]), "r"(pk[15])
-                           : "memory");
-            } else if (full_chunk && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0)) {
-#pragma unroll
-              for (int j = 0; j < 16; j += 4)
-                *reinterpret_cast<uint4*>(dp + 2 * j) = make_uint4(pk[j], pk[j + 1], pk[j + 2], pk[j + 3]);
-            } else {
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < N) dp[j] = __float2bfloat16_rn(v[j]);
-            }
-          } else if (staged) {
-            __syncwarp();
-          }
-          if (want_stats) {
-            float s1a = 0.f, s1b = 0.f, s1c = 0.f, s1d = 0.f, s2a = 0.f, s2b = 0.f, s2c = 0.f, s2d = 0.f;
-            const int w = lane >> 1;                       // bf16x2 word of the row this lane pair reads
-            const int sh = (lane & 1) ? 0 : 16;            // even lanes take the low bf16 of the word
-            const uint8_t* colp = stg + ((w & 3) << 2);
-            const int wc = w >> 2;
-#pragma unroll
-            for (int r = 0; r < 32; r += 4) {              // four independent accumulation chains
-              uint32_t u[4];
-#pragma unroll
-              for (int q4 = 0; q4 < 4; ++q4)
-                u[q4] = *reinterpret_cast<const uint32_t*>(colp + (r + q4) * 64 + ((wc ^ (((r + q4) >> 1) & 3)) << 4));
-              const float x0 = __uint_as_float((u[0] << sh) & 0xffff0000u);
-              const float x1 = __uint_as_float((u[1] << sh) & 0xffff0000u);
-              const float x2 = __uint_as_float((u[2] << sh) & 0xffff0000u);
-              const float x3 = __uint_as_float((u[3] << sh) & 0xffff0000u);
-              s1a += x0; s1b += x1; s1c += x2; s1d += x3;
-              s2a = fmaf(x0, x0, s2a); s2b = fmaf(x1, x1, s2b); s2c = fmaf(x2, x2, s2c); s2d = fmaf(x3, x3, s2d);
-            }
-            float* st = stat_s + quarter * 2 * BN + ch * 32 + lane;
-            st[0] += (s1a + s1b) + (s1c + s1d);
-            st[BN] += (s2a + s2b) + (s2c + s2d);
-          }
-          if (staged) stg_buf = (stg_buf + 1) % L::kStgBufs;
-        } else if (row_ok) {
-          float* dp = reinterpret_cast<float*>(ep.D) + (long)row * ep.ldd + col0;
-          if (full_chunk && ((reinterpret_cast<uintptr_t>(dp) & 31) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8)
-              asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dp + j), "f"(v[j]), "f"(v[j + 1]),
-                           "f"(v[j + 2]), "f"(v[j + 3]), "f"(v[j + 4]), "f"(v[j + 5]), "f"(v[j + 6]), "f"(v[j + 7])
-                           : "memory");
-          } else if (full_chunk && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < N) dp[j] = v[j];
-          }
-        }
-        if (want_stats && !ep.out_bf16) {
-          // fp32 output: column sums over this warp's 32 rows by butterfly reduce-scatter (lane l ends with column l)
-          float s2[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            v[j] = row_ok ? v[j] : 0.0f;
-            s2[j] = v[j] * v[j];
-          }
-#pragma unroll
-          for (int off = 16; off >= 1; off >>= 1) {
-            const bool up = (lane & off) != 0;
-#pragma unroll
-            for (int i = 0; i < off; ++i) {
-              const float send1 = up ? v[i] : v[i + off];
-              const float keep1 = up ? v[i + off] : v[i];
-              v[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, off);
-              const float send2 = up ? s2[i] : s2[i + off];
-              const float keep2 = up ? s2[i + off] : s2[i];
-              s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
+            float2 t1 = __fadd2_rn(s1a, s1b), t2 = __fadd2_rn(s2a, s2b);
+            t1.x += __shfl_xor_sync(0xffffffffu, t1.x, 16);
+            t1.y += __shfl_xor_sync(0xffffffffu, t1.y, 16);
+            t2.x += __shfl_xor_sync(0xffffffffu, t2.x, 16);
+            t2.y += __shfl_xor_sync(0xffffffffu, t2.y, 16);
+            if (sw_hf == 0) {
+              float2* st = reinterpret_cast<float2*>(stat_s + quarter * 2 * BN + ch * 32 + 2 * sw_w);
+              float2* st2 = reinterpret_cast<float2*>(stat_s + quarter * 2 * BN + BN + ch * 32 + 2 * sw_w);
+              *st = __fadd2_rn(*st, t1);
+              *st2 = __fadd2_rn(*st2, t2);
             }
           }
-          float* st = stat_s + quarter * 2 * BN + ch * 32 + lane;
-          st[0] += v[0];
-          st[BN] += s2[0];
+          if (ep.store) {
+            if (post) {
+              // BatchNorm of this conv's output + shortcut (+ its BatchNorm) + ReLU on the fp32 accumulators;
+              // the coefficients are broadcast reads of the n-block table in shared memory
+              const float* sc_p = ss_s + ch * 32;
+              if (has_obn) {
+#pragma unroll
+                for (int jj = 0; jj < 32; jj += 4) {
+                  const float4 sc = *reinterpret_cast<const float4*>(sc_p + jj);
+                  const float4 sh = *reinterpret_cast<const float4*>(sc_p + BN + jj);
+                  v[jj] = fmaf(v[jj], sc.x, sh.x);
+                  v[jj + 1] = fmaf(v[jj + 1], sc.y, sh.y);
+                  v[jj + 2] = fmaf(v[jj + 2], sc.z, sh.z);
+                  v[jj + 3] = fmaf(v[jj + 3], sc.w, sh.w);
+                }
+              }
+              if (has_res) {
+                const uint32_t* rw = reinterpret_cast<const uint32_t*>(rres);
+                if (has_rbn) {
+#pragma unroll
+                  for (int jj = 0; jj < 32; jj += 4) {
+                    const float4 sc = *reinterpret_cast<const float4*>(sc_p + 2 * BN + jj);
+                    const float4 sh = *reinterpret_cast<const float4*>(sc_p + 3 * BN + jj);
+                    const uint32_t w0 = rw[jj >> 1], w1 = rw[(jj >> 1) + 1];
+                    v[jj] += fmaf(__uint_as_float(w0 << 16), sc.x, sh.x);
+                    v[jj + 1] += fmaf(__uint_as_float(w0 & 0xffff0000u), sc.y, sh.y);
+                    v[jj + 2] += fmaf(__uint_as_float(w1 << 16), sc.z, sh.z);
+                    v[jj + 3] += fmaf(__uint_as_float(w1 & 0xffff0000u), sc.w, sh.w);
+                  }
+                } else {
+#pragma unroll
+                  for (int jj = 0; jj < 16; ++jj) {
+                    v[2 * jj] += __uint_as_float(rw[jj] << 16);
+                    v[2 * jj + 1] += __uint_as_float(rw[jj] & 0xffff0000u);
+                  }
+                }
+              }
+              if (ep.out_bf16) {
+                if (ep.relu) {
+#pragma unroll
+                  for (int jj = 0; jj < 16; ++jj) pk[jj] = pack_bf16x2_relu(v[2 * jj], v[2 * jj + 1]);
+                } else {
+#pragma unroll
+                  for (int jj = 0; jj < 16; ++jj) pk[jj] = pack_bf16x2(v[2 * jj], v[2 * jj + 1]);
+                }
+              }
+            }
+            if (ep.out_bf16) {
+              if (ep.tma_store) {
+                // staging tile -> one TMA bulk store in full 64-byte row segments (no LSU, no registers)
+                if (!stats_bf16) {
+                  if (lane == 0) bulk_wait_read<L::kStgBufs - 1>();
+                  __syncwarp();
+                }
+                if (!stats_bf16 || post) {
+#pragma unroll
+                  for (int c = 0; c < 4; ++c)
+                    *reinterpret_cast<uint4*>(stg + lane * 64 + ((c ^ sw) << 4)) =
+                        make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                  tma_store_2d(&tmap_d, stg, col0, m_blk * BM + quarter * 32);
+                  bulk_commit();
+                }
+                stg_buf = (stg_buf + 1) % L::kStgBufs;
+              } else if (row_ok) {
+                bf16* dp = reinterpret_cast<bf16*>(ep.D) + (long)row * ep.ldd + col0;
+                if (full_chunk && ((reinterpret_cast<uintptr_t>(dp) & 31) == 0)) {
+                  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dp), "r"(pk[0]), "r"(pk[1]),
+                               "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
+                               : "memory");
+                  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dp + 16), "r"(pk[8]), "r"(pk[9]),
+                               "r"(pk[10]), "r"(pk[11]), "r"(pk[12]), "r"(pk[13]), "r"(pk[14]), "r"(pk[15])
+                               : "memory");
+                } else if (full_chunk && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0)) {
+#pragma unroll
+                  for (int jj = 0; jj < 16; jj += 4)
+                    *reinterpret_cast<uint4*>(dp + 2 * jj) = make_uint4(pk[jj], pk[jj + 1], pk[jj + 2], pk[jj + 3]);
+                } else {
+                  for (int jj = 0; jj < 32; ++jj)
+                    if (col0 + jj < N) dp[jj] = __ushort_as_bfloat16((unsigned short)(pk[jj >> 1] >> ((jj & 1) * 16)));
+                }
+              }
+            } else if (row_ok) {
+              if (ep.relu) {
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj) v[jj] = fmaxf(v[jj], 0.0f);
+              }
+              float* dp = reinterpret_cast<float*>(ep.D) + (long)row * ep.ldd + col0;
+              if (full_chunk && ((reinterpret_cast<uintptr_t>(dp) & 31) == 0)) {
+#pragma unroll
+                for (int jj = 0; jj < 32; jj += 8)
+                  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dp + jj), "f"(v[jj]), "f"(v[jj + 1]),
+                               "f"(v[jj + 2]), "f"(v[jj + 3]), "f"(v[jj + 4]), "f"(v[jj + 5]), "f"(v[jj + 6]), "f"(v[jj + 7])
+                               : "memory");
+              } else if (full_chunk && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0)) {
+#pragma unroll
+                for (int jj = 0; jj < 32; jj += 4)
+                  *reinterpret_cast<float4*>(dp + jj) = make_float4(v[jj], v[jj + 1], v[jj + 2], v[jj + 3]);
+              } else {
+                for (int jj = 0; jj < 32; ++jj)
+                  if (col0 + jj < N) dp[jj] = v[jj];
+              }
+            }
+          }
+          if (want_stats && !ep.out_bf16) {
+            // fp32 output (statistics of the value as stored, ReLU included): column sums over this warp's
+            // 32 rows by butterfly reduce-scatter (lane l ends with column l)
+            float s2[32];
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) {
+              v[jj] = row_ok ? v[jj] : 0.0f;
+              s2[jj] = v[jj] * v[jj];
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+              const bool up = (lane & off) != 0;
+#pragma unroll
+              for (int i = 0; i < off; ++i) {
+                const float send1 = up ? v[i] : v[i + off];
+                const float keep1 = up ? v[i + off] : v[i];
+                v[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, off);
+                const float send2 = up ? s2[i] : s2[i + off];
+                const float keep2 = up ? s2[i + off] : s2[i];
+                s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
+              }
+            }
+            float* st = stat_s + quarter * 2 * BN + ch * 32 + lane;      // lane l holds column l
+            st[0] += v[0];
+            st[BN] += s2[0];
+          }
         }
       }
       tc_fence_before();
@@ -387,21 +570,135 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
     if (ep.tma_store && lane == 0) bulk_wait_all();   // all bulk stores of this warp have landed
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (want_stats) {   // flush the last n-block this CTA worked on
-    int last_tile = -1;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) last_tile = tile;
-    if (last_tile >= 0) {
-      const int nb = last_tile / m_blocks;
-      for (int c = threadIdx.x; c < BN; c += kThreads) {
-        const int col = nb * BN + c;
+    if (want_stats && cur_nblk >= 0) {
+      // ---- final flush (same as above)
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int c = epi_tid; c < BN; c += 32 * kEpiWarps) {
+        const int col = cur_nblk * BN + c;
         if (col < N) {
           atomicAdd(ep.col_sum + col, stat_s[c] + stat_s[2 * BN + c] + stat_s[4 * BN + c] + stat_s[6 * BN + c]);
           atomicAdd(ep.col_sumsq + col, stat_s[BN + c] + stat_s[3 * BN + c] + stat_s[5 * BN + c] + stat_s[7 * BN + c]);
         }
+      }
+    }
+  } else if (use_tf) {
+    // =========================== A transform (warps 10..13) ===========================
+    // thread = (16-byte chunk c of the 128-byte row, rows rb + 16 i): 8 channels whose scale/shift are
+    // loaded once per k-block.  Branch-free and batched (8 LDS.128 in flight, then math, then 8 STS.128);
+    // zero-padding taps of an im2col tile keep the 0 the TMA wrote (select, not branch).
+    const int tt = threadIdx.x - kTfThread0;
+    const int c = tt & 7;
+    const int rb = tt >> 3;
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t row_off[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = rb + 16 * i;
+      row_off[i] = (uint32_t)(row * 128 + ((c ^ (row & 7)) << 4));
+    }
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n_blk = tile / m_blocks;
+      const int m_blk = tile - n_blk * m_blocks;
+      int iy0[8], ix0[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        iy0[i] = 0;
+        ix0[i] = 0;
+      }
+      if (g.is_conv) {
+        const int pq = g.P * g.Q;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int m = m_blk * BM + rb + 16 * i;
+          const int n = m / pq;
+          const int rem = m - n * pq;
+          const int p = rem / g.Q;
+          iy0[i] = (m < M) ? p * g.stride + g.lower_h : -(1 << 20);
+          ix0[i] = (rem - p * g.Q) * g.stride + g.lower_w;
+        }
+      }
+      int r = 0, s = 0, slab = 0;
+      const unsigned uH = g.is_conv ? (unsigned)g.H : 0x7fffffffu, uW = g.is_conv ? (unsigned)g.W : 0x7fffffffu;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        const int c0 = (g.is_conv ? slab : kb) * BK + c * 8;
+        const float4 sc0 = __ldg(reinterpret_cast<const float4*>(at.scale + c0));
+        const float4 sc1 = __ldg(reinterpret_cast<const float4*>(at.scale + c0 + 4));
+        const float4 sh0 = __ldg(reinterpret_cast<const float4*>(at.shift + c0));
+        const float4 sh1 = __ldg(reinterpret_cast<const float4*>(at.shift + c0 + 4));
+        mbar_wait(&full_bar[stage], phase);
+        uint8_t* sa = smem + stage * L::kStageBytes;
+        uint4 u[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) u[i] = *reinterpret_cast<const uint4*>(sa + row_off[i]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const bool ok = (unsigned)(iy0[i] + r) < uH && (unsigned)(ix0[i] + s) < uW;
+          float2 a0 = make_float2(__uint_as_float(u[i].x << 16), __uint_as_float(u[i].x & 0xffff0000u));
+          float2 a1 = make_float2(__uint_as_float(u[i].y << 16), __uint_as_float(u[i].y & 0xffff0000u));
+          float2 a2 = make_float2(__uint_as_float(u[i].z << 16), __uint_as_float(u[i].z & 0xffff0000u));
+          float2 a3 = make_float2(__uint_as_float(u[i].w << 16), __uint_as_float(u[i].w & 0xffff0000u));
+          a0 = __ffma2_rn(a0, make_float2(sc0.x, sc0.y), make_float2(sh0.x, sh0.y));
+          a1 = __ffma2_rn(a1, make_float2(sc0.z, sc0.w), make_float2(sh0.z, sh0.w));
+          a2 = __ffma2_rn(a2, make_float2(sc1.x, sc1.y), make_float2(sh1.x, sh1.y));
+          a3 = __ffma2_rn(a3, make_float2(sc1.z, sc1.w), make_float2(sh1.z, sh1.w));
+          uint4 t;
+          if (at.relu) {
+            t.x = pack_bf16x2_relu(a0.x, a0.y);
+            t.y = pack_bf16x2_relu(a1.x, a1.y);
+            t.z = pack_bf16x2_relu(a2.x, a2.y);
+            t.w = pack_bf16x2_relu(a3.x, a3.y);
+          } else {
+            t.x = pack_bf16x2(a0.x, a0.y);
+            t.y = pack_bf16x2(a1.x, a1.y);
+            t.z = pack_bf16x2(a2.x, a2.y);
+            t.w = pack_bf16x2(a3.x, a3.y);
+          }
+          u[i].x = ok ? t.x : 0u;
+          u[i].y = ok ? t.y : 0u;
+          u[i].z = ok ? t.z : 0u;
+          u[i].w = ok ? t.w : 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(sa + row_off[i]) = u[i];
+        fence_proxy_async_smem();        // generic-proxy writes -> visible to the tensor core (async proxy)
+        mbar_arrive(&tf_bar[stage]);
+        if (g.is_conv && ++slab == g.c_slabs) {
+          slab = 0;
+          if (++s == g.S) {
+            s = 0;
+            ++r;
+          }
+        }
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (ep.fin.scale != nullptr) {
+    // BatchNorm finalisation by the last CTA to get here: every CTA's statistics are in global memory
+    __shared__ int is_last;
+    __threadfence();
+    if (threadIdx.x == 0) is_last = (atomicAdd(ep.fin.counter, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (is_last) {
+      __threadfence();
+      const BnFinal& f = ep.fin;
+      for (int c = threadIdx.x; c < N; c += kThreads) {
+        const float mean = __ldcg(ep.col_sum + c) * f.inv_count;
+        const float var = fmaxf(__ldcg(ep.col_sumsq + c) * f.inv_count - mean * mean, 0.f);
+        if (f.running_mean != nullptr) {
+          f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * mean;
+          f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * var * f.unbias;
+        }
+        const float sc = f.gamma[c] * rsqrtf(var + f.eps);
+        f.scale[c] = sc;
+        f.shift[c] = f.beta[c] - mean * sc;
       }
     }
   }
@@ -461,8 +758,8 @@ int make_tmap_2d(CUtensorMap* map, const void* base, long rows, long cols, long 
 }
 
 template <int BN>
-int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, int M, int N, int K,
-                const ConvGeom& g, const EpiParams& ep, cudaStream_t stream) {
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tr, int M, int N,
+                int K, const ConvGeom& g, const ATransform& at, const EpiParams& ep, cudaStream_t stream) {
   using L = SmemLayout<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -471,7 +768,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
   }
   const int tiles = b2_ceil_div(M, BM) * b2_ceil_div(N, BN);
   const int grid = tiles < b2_num_sms() ? tiles : b2_num_sms();
-  gemm_tc_kernel<BN><<<grid, kThreads, L::kTotal, stream>>>(ta, tb, td, M, N, K, g, ep);
+  gemm_tc_kernel<BN><<<grid, kThreads, L::kTotal, stream>>>(ta, tb, td, tr, M, N, K, g, at, ep);
   B2_LAUNCH_CHECK("gemm_tc_kernel");
   return 0;
 }
@@ -484,67 +781,64 @@ int pick_bn(int N) {
 }
 
 int dispatch(int bn, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const ConvGeom& g,
-             EpiParams ep, cudaStream_t stream) {
+             const ATransform& at, EpiParams ep, cudaStream_t stream) {
   // bf16 outputs whose rows are 16-byte multiples leave through TMA bulk stores
-  CUtensorMap td = ta;
+  CUtensorMap td = ta, tr = ta;
   ep.tma_store = 0;
-  if (ep.out_bf16 && (ep.ldd % 8) == 0 && ((uintptr_t)ep.D & 15) == 0) {
+  if (ep.store && ep.out_bf16 && (ep.ldd % 8) == 0 && ((uintptr_t)ep.D & 15) == 0) {
     if (int r = make_tmap_2d(&td, ep.D, M, N, ep.ldd, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return r;
     ep.tma_store = 1;
   }
+  if (ep.res != nullptr) {   // shortcut tiles are fetched by TMA (same 32x32 SWIZZLE_64B boxes as the store)
+    if (int r = make_tmap_2d(&tr, ep.res, M, N, ep.ldres, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return r;
+  }
   switch (bn) {
-    case 256: return launch_gemm<256>(ta, tb, td, M, N, K, g, ep, stream);
-    case 128: return launch_gemm<128>(ta, tb, td, M, N, K, g, ep, stream);
-    case 64: return launch_gemm<64>(ta, tb, td, M, N, K, g, ep, stream);
-    default: return launch_gemm<32>(ta, tb, td, M, N, K, g, ep, stream);
+    case 256: return launch_gemm<256>(ta, tb, td, tr, M, N, K, g, at, ep, stream);
+    case 128: return launch_gemm<128>(ta, tb, td, tr, M, N, K, g, at, ep, stream);
+    case 64: return launch_gemm<64>(ta, tb, td, tr, M, N, K, g, at, ep, stream);
+    default: return launch_gemm<32>(ta, tb, td, tr, M, N, K, g, at, ep, stream);
   }
 }
 
-}  // namespace
-
-// D[M,N] = A[M,K] B[N,K]^T (+bias) ; see include/b200lrcn.h
-B2_API int b2_gemm_bf16_tn(const void* A, long lda, const void* B, long ldb, void* D, long ldd, int M, int N, int K,
-                           const float* bias, const float* bias2, int out_bf16, int relu, float* col_sum,
-                           float* col_sumsq, void* stream) {
-  B2_ARG_CHECK(A && B && D && M > 0 && N > 0 && K > 0, "b2_gemm_bf16_tn: null pointer or empty shape");
-  B2_ARG_CHECK((lda % 8) == 0 && (ldb % 8) == 0, "b2_gemm_bf16_tn: lda/ldb must be multiples of 8 elements (16 B)");
-  B2_ARG_CHECK(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "b2_gemm_bf16_tn: A/B must be 16 B aligned");
-  B2_ARG_CHECK((col_sum == nullptr) == (col_sumsq == nullptr), "b2_gemm_bf16_tn: col_sum and col_sumsq go together");
-  if (int r = load_driver_entry_points()) return r;
-  const int bn = pick_bn(N);
-  CUtensorMap ta, tb;
-  if (int r = make_tmap_2d(&ta, A, M, K, lda, BM)) return r;
-  if (int r = make_tmap_2d(&tb, B, N, K, ldb, bn)) return r;
-  ConvGeom g = {};
-  EpiParams ep = {D, ldd, bias, bias2, col_sum, col_sumsq, out_bf16, relu, 0};
-  return dispatch(bn, ta, tb, M, N, K, g, ep, (cudaStream_t)stream);
+EpiParams plain_epi(void* D, long ldd, const float* bias, const float* bias2, int out_bf16, int relu, float* col_sum,
+                    float* col_sumsq) {
+  EpiParams ep = {};
+  ep.D = D;
+  ep.ldd = ldd;
+  ep.bias = bias;
+  ep.bias2 = bias2;
+  ep.col_sum = col_sum;
+  ep.col_sumsq = col_sumsq;
+  ep.out_bf16 = out_bf16;
+  ep.relu = relu;
+  ep.store = 1;
+  return ep;
 }
 
-// y[N,P,Q,Cout] = conv(x[N,H,W,C], w[Cout,R,S,C]) ; NHWC bf16, C % 64 == 0 ; see include/b200lrcn.h
-B2_API int b2_conv2d_nhwc_bf16(const void* x, int Nimg, int H, int W, int C, const void* w, int Cout, int R, int S,
-                               int stride, int pad, void* y, const float* bias, int out_bf16, int relu,
-                               float* col_sum, float* col_sumsq, void* stream) {
-  B2_ARG_CHECK(x && w && y && Nimg > 0 && H > 0 && W > 0 && Cout > 0, "b2_conv2d_nhwc_bf16: null pointer or empty shape");
-  B2_ARG_CHECK(C % 64 == 0, "b2_conv2d_nhwc_bf16: C must be a multiple of 64 (got %d)", C);
+int conv_common(const void* x, int Nimg, int H, int W, int C, const void* w, int Cout, int R, int S, int stride,
+                int pad, const ATransform& at, EpiParams ep, cudaStream_t stream, const char* who) {
+  B2_ARG_CHECK(x && w && Nimg > 0 && H > 0 && W > 0 && Cout > 0, "%s: null pointer or empty shape", who);
+  B2_ARG_CHECK(C % 64 == 0, "%s: C must be a multiple of 64 (got %d)", who, C);
   B2_ARG_CHECK(R >= 1 && S >= 1 && R <= 7 && S <= 7 && stride >= 1 && stride <= 8 && pad >= 0 && pad <= 3,
-               "b2_conv2d_nhwc_bf16: unsupported filter geometry R=%d S=%d stride=%d pad=%d", R, S, stride, pad);
-  B2_ARG_CHECK((col_sum == nullptr) == (col_sumsq == nullptr), "b2_conv2d_nhwc_bf16: col_sum and col_sumsq go together");
+               "%s: unsupported filter geometry R=%d S=%d stride=%d pad=%d", who, R, S, stride, pad);
+  B2_ARG_CHECK((ep.col_sum == nullptr) == (ep.col_sumsq == nullptr), "%s: col_sum and col_sumsq go together", who);
   const int P = (H + 2 * pad - R) / stride + 1;
   const int Q = (W + 2 * pad - S) / stride + 1;
-  B2_ARG_CHECK(P > 0 && Q > 0, "b2_conv2d_nhwc_bf16: empty output");
+  B2_ARG_CHECK(P > 0 && Q > 0, "%s: empty output", who);
   if (int r = load_driver_entry_points()) return r;
   const long Ml = (long)Nimg * P * Q;
-  B2_ARG_CHECK(Ml < (1L << 31), "b2_conv2d_nhwc_bf16: too many output pixels");
+  B2_ARG_CHECK(Ml < (1L << 31), "%s: too many output pixels", who);
   const int M = (int)Ml;
   const int K = R * S * C;
   const int bn = pick_bn(Cout);
-  EpiParams ep = {y, (long)Cout, bias, nullptr, col_sum, col_sumsq, out_bf16, relu, 0};
+  ep.ldd = Cout;
+  if (ep.res != nullptr) ep.ldres = Cout;
   CUtensorMap ta, tb;
   if (int r = make_tmap_2d(&tb, w, Cout, K, K, bn)) return r;
   if (R == 1 && S == 1 && stride == 1 && pad == 0) {
     if (int r = make_tmap_2d(&ta, x, M, C, C, BM)) return r;
     ConvGeom g = {};
-    return dispatch(bn, ta, tb, M, Cout, K, g, ep, (cudaStream_t)stream);
+    return dispatch(bn, ta, tb, M, Cout, K, g, at, ep, stream);
   }
   // IM2COL-mode map over the NHWC activation: dims {C, W, H, N}; the bounding box of filter-window
   // base positions is [-pad, dim-1 + (pad - (R-1))] and is walked with the convolution stride.
@@ -569,6 +863,124 @@ B2_API int b2_conv2d_nhwc_bf16(const void* x, int Nimg, int H, int W, int C, con
     cudaDriverGetVersion(&drv);
     if (drv <= 13010 && (long)Nimg * H * W * C * 2 < 131072) reinterpret_cast<uint64_t*>(&ta)[1] &= ~(1ull << 21);
   }
-  ConvGeom g = {1, P, Q, S, C / 64, stride, -pad, -pad};
-  return dispatch(bn, ta, tb, M, Cout, K, g, ep, (cudaStream_t)stream);
+  ConvGeom g = {1, P, Q, S, C / 64, stride, -pad, -pad, H, W};
+  return dispatch(bn, ta, tb, M, Cout, K, g, at, ep, stream);
+}
+
+__global__ void bn_finalize_kernel(const float* sum, const float* sumsq, const float* gamma, const float* beta,
+                                   float* running_mean, float* running_var, float inv_count, float unbias, float eps,
+                                   float momentum, int train, float* scale, float* shift, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float mean, var;
+  if (train) {
+    mean = sum[c] * inv_count;
+    var = fmaxf(sumsq[c] * inv_count - mean * mean, 0.f);
+    if (running_mean != nullptr) {
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * var * unbias;
+    }
+  } else {
+    mean = running_mean[c];
+    var = running_var[c];
+  }
+  const float sc = gamma[c] * rsqrtf(var + eps);
+  scale[c] = sc;
+  shift[c] = beta[c] - mean * sc;
+}
+
+}  // namespace
+
+// D[M,N] = A[M,K] B[N,K]^T (+bias) ; see include/b200lrcn.h
+B2_API int b2_gemm_bf16_tn(const void* A, long lda, const void* B, long ldb, void* D, long ldd, int M, int N, int K,
+                           const float* bias, const float* bias2, int out_bf16, int relu, float* col_sum,
+                           float* col_sumsq, void* stream) {
+  B2_ARG_CHECK(A && B && D && M > 0 && N > 0 && K > 0, "b2_gemm_bf16_tn: null pointer or empty shape");
+  B2_ARG_CHECK((lda % 8) == 0 && (ldb % 8) == 0, "b2_gemm_bf16_tn: lda/ldb must be multiples of 8 elements (16 B)");
+  B2_ARG_CHECK(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "b2_gemm_bf16_tn: A/B must be 16 B aligned");
+  B2_ARG_CHECK((col_sum == nullptr) == (col_sumsq == nullptr), "b2_gemm_bf16_tn: col_sum and col_sumsq go together");
+  if (int r = load_driver_entry_points()) return r;
+  const int bn = pick_bn(N);
+  CUtensorMap ta, tb;
+  if (int r = make_tmap_2d(&ta, A, M, K, lda, BM)) return r;
+  if (int r = make_tmap_2d(&tb, B, N, K, ldb, bn)) return r;
+  ConvGeom g = {};
+  ATransform at = {};
+  return dispatch(bn, ta, tb, M, N, K, g, at, plain_epi(D, ldd, bias, bias2, out_bf16, relu, col_sum, col_sumsq),
+                  (cudaStream_t)stream);
+}
+
+// y[N,P,Q,Cout] = conv(x[N,H,W,C], w[Cout,R,S,C]) ; NHWC bf16, C % 64 == 0 ; see include/b200lrcn.h
+B2_API int b2_conv2d_nhwc_bf16(const void* x, int Nimg, int H, int W, int C, const void* w, int Cout, int R, int S,
+                               int stride, int pad, void* y, const float* bias, int out_bf16, int relu,
+                               float* col_sum, float* col_sumsq, void* stream) {
+  B2_ARG_CHECK(y != nullptr, "b2_conv2d_nhwc_bf16: null output");
+  ATransform at = {};
+  return conv_common(x, Nimg, H, W, C, w, Cout, R, S, stride, pad, at,
+                     plain_epi(y, Cout, bias, nullptr, out_bf16, relu, col_sum, col_sumsq), (cudaStream_t)stream,
+                     "b2_conv2d_nhwc_bf16");
+}
+
+// Convolution with the BatchNorms of a ResNet block folded in ; see include/b200lrcn.h
+B2_API int b2_conv2d_bn_nhwc_bf16(const void* x, int Nimg, int H, int W, int C, const void* w, int Cout, int R,
+                                  int S, int stride, int pad, void* y, const float* a_scale, const float* a_shift,
+                                  int a_relu, const float* o_scale, const float* o_shift, const void* res,
+                                  const float* r_scale, const float* r_shift, int relu, float* col_sum,
+                                  float* col_sumsq, const float* fin_gamma, const float* fin_beta,
+                                  float* fin_running_mean, float* fin_running_var, float* fin_scale,
+                                  float* fin_shift, unsigned int* fin_counter, float eps, float momentum,
+                                  void* stream) {
+  const char* who = "b2_conv2d_bn_nhwc_bf16";
+  B2_ARG_CHECK((a_scale == nullptr) == (a_shift == nullptr), "%s: a_scale and a_shift go together", who);
+  B2_ARG_CHECK((o_scale == nullptr) == (o_shift == nullptr), "%s: o_scale and o_shift go together", who);
+  B2_ARG_CHECK((r_scale == nullptr) == (r_shift == nullptr), "%s: r_scale and r_shift go together", who);
+  B2_ARG_CHECK(r_scale == nullptr || res != nullptr, "%s: shortcut BatchNorm without a shortcut tensor", who);
+  B2_ARG_CHECK(y != nullptr || (o_scale == nullptr && res == nullptr && col_sum != nullptr),
+               "%s: a statistics-only pass (y = NULL) takes col_sum/col_sumsq and no output BatchNorm / shortcut", who);
+  B2_ARG_CHECK((res == nullptr && o_scale == nullptr) || Cout % 32 == 0,
+               "%s: output BatchNorm / shortcut need Cout %% 32 == 0", who);
+  B2_ARG_CHECK(res == nullptr || ((uintptr_t)res & 15) == 0, "%s: shortcut must be 16 B aligned", who);
+  B2_ARG_CHECK(res == nullptr || Cout % pick_bn(Cout) == 0, "%s: a shortcut needs Cout to fill whole column blocks", who);
+  B2_ARG_CHECK(col_sum == nullptr || (o_scale == nullptr && res == nullptr),
+               "%s: statistics are taken on the raw output; they do not combine with an output BatchNorm / shortcut", who);
+  B2_ARG_CHECK(fin_scale == nullptr || (fin_shift && fin_gamma && fin_beta && fin_counter && col_sum),
+               "%s: BatchNorm finalisation needs gamma/beta/shift/counter and the statistics buffers", who);
+  ATransform at = {a_scale, a_shift, a_relu};
+  EpiParams ep = plain_epi(y, Cout, nullptr, nullptr, 1, relu, col_sum, col_sumsq);
+  ep.store = y != nullptr;
+  ep.o_scale = o_scale;
+  ep.o_shift = o_shift;
+  ep.res = (const bf16*)res;
+  ep.r_scale = r_scale;
+  ep.r_shift = r_shift;
+  if (fin_scale != nullptr) {
+    const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
+    const double count = (double)Nimg * P * Q;
+    ep.fin.scale = fin_scale;
+    ep.fin.shift = fin_shift;
+    ep.fin.gamma = fin_gamma;
+    ep.fin.beta = fin_beta;
+    ep.fin.running_mean = fin_running_mean;
+    ep.fin.running_var = fin_running_var;
+    ep.fin.counter = fin_counter;
+    ep.fin.inv_count = (float)(1.0 / count);
+    ep.fin.unbias = count > 1 ? (float)(count / (count - 1.0)) : 1.f;
+    ep.fin.eps = eps;
+    ep.fin.momentum = momentum;
+  }
+  return conv_common(x, Nimg, H, W, C, w, Cout, R, S, stride, pad, at, ep, (cudaStream_t)stream, who);
+}
+
+B2_API int b2_bn_finalize_nhwc(const float* sum, const float* sumsq, const float* gamma, const float* beta,
+                               float* running_mean, float* running_var, long count, float eps, float momentum,
+                               int train, float* scale, float* shift, int C, void* stream) {
+  B2_ARG_CHECK(gamma && beta && scale && shift && C > 0 && count > 0, "b2_bn_finalize_nhwc: null pointer or empty");
+  B2_ARG_CHECK(train ? (sum && sumsq) : (running_mean && running_var), "b2_bn_finalize_nhwc: missing statistics");
+  const float inv = (float)(1.0 / (double)count);
+  const float unbias = count > 1 ? (float)((double)count / (double)(count - 1)) : 1.f;
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sum, sumsq, gamma, beta, running_mean,
+                                                                         running_var, inv, unbias, eps, momentum,
+                                                                         train, scale, shift, C);
+  B2_LAUNCH_CHECK("bn_finalize_kernel");
+  return 0;
 }

@@ -19,18 +19,25 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  // try_wait suspends the thread in hardware for up to the hinted time, so a waiting warp costs (almost)
+  // no issue slots; the retry counter is a watchdog: a protocol bug must fault, never hang the GPU.
   uint32_t done;
   const uint32_t addr = smem_u32(bar);
+  uint32_t tries = 0;
   long long t0 = 0;
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
+#ifndef B2_NO_TRYWAIT_HINT
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+#else
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+#endif
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(addr), "r"(parity)
+        : "r"(addr), "r"(parity), "r"(1000000u)
         : "memory");
-    if (!done) {  // watchdog: a protocol bug must fault, never hang the GPU
+    if (!done && (++tries & 1023u) == 0) {
       const long long now = clock64();
       if (t0 == 0) t0 = now;
       else if (now - t0 > 8000000000LL) {

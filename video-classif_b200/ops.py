@@ -59,6 +59,44 @@ def conv2d_nhwc(x, w, stride, pad, stats=None):
     return y
 
 
+def conv2d_bn_nhwc(x, w, stride, pad, a=None, a_relu=True, o=None, res=None, r=None, relu=False, stats=None,
+                   fin=None, store=True):
+    """b2_conv2d_bn_nhwc_bf16: convolution with the BatchNorms around it folded in (see include/b200lrcn.h).
+    a / o / r = (scale, shift) fp32 vectors for the input / output / shortcut BatchNorm; stats = (sum, sumsq);
+    fin = (gamma, beta, running_mean, running_var, scale_out, shift_out, counter_u32, eps, momentum);
+    store=False: statistics-only pass (returns None)."""
+    _chk(x, w)
+    N, H, W, C = x.shape
+    Cout, R, S, _ = w.shape
+    P = (H + 2 * pad - R) // stride + 1
+    Q = (W + 2 * pad - S) // stride + 1
+    y = torch.empty((N, P, Q, Cout), device=x.device, dtype=BF16) if store else None
+    a0, a1 = a if a is not None else (None, None)
+    o0, o1 = o if o is not None else (None, None)
+    r0, r1 = r if r is not None else (None, None)
+    s1, s2 = stats if stats is not None else (None, None)
+    if fin is not None:
+        g, b, rm, rv, fs, fh, cnt, eps, mom = fin
+    else:
+        g = b = rm = rv = fs = fh = cnt = None
+        eps, mom = 1e-5, 0.1
+    call("b2_conv2d_bn_nhwc_bf16", x.data_ptr(), N, H, W, C, w.data_ptr(), Cout, R, S, stride, pad, ptr(y), ptr(a0),
+         ptr(a1), int(a_relu), ptr(o0), ptr(o1), ptr(res), ptr(r0), ptr(r1), int(relu), ptr(s1), ptr(s2), ptr(g), ptr(b),
+         ptr(rm), ptr(rv), ptr(fs), ptr(fh), ptr(cnt), float(eps), float(mom), stream_ptr())
+    return y
+
+
+def scale_shift_apply(x, scale, shift, res=None, r=None, relu=True, out=None):
+    """y = act(x*scale[c] + shift[c] [+ res | + res*rscale[c] + rshift[c]]) over NHWC bf16 (in place by default)."""
+    _chk(x)
+    C = x.shape[-1]
+    out = x if out is None else out
+    r0, r1 = r if r is not None else (None, None)
+    call("b2_scale_shift_apply_nhwc", x.data_ptr(), out.data_ptr(), x.numel() // C, C, scale.data_ptr(), shift.data_ptr(),
+         ptr(res), ptr(r0), ptr(r1), int(relu), stream_ptr())
+    return out
+
+
 def pack_stem_weight(w):
     """torch conv1 weight [64,3,7,7] -> bf16 [28][64][8] for b2_stem_conv_bf16 (k = r*32 + s*4 + c)."""
     assert tuple(w.shape[1:]) == (3, 7, 7) and w.shape[0] == 64
