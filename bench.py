@@ -314,6 +314,8 @@ def run_ours(args):
             return 2.0 * out.shape[0] * out.shape[1] * a[0].shape[1]
 
         def conv_flops(a, k, out):
+            if k.get("store", True) is False:      # statistics-only pass: its time counts, its flops are recompute
+                return 0.0
             x, w = a[0], a[1]
             stride, pad = a[2], a[3]
             P = (x.shape[1] + 2 * pad - w.shape[1]) // stride + 1

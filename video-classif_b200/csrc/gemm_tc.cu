@@ -20,7 +20,16 @@
 //     epilogue applies BN3, adds the shortcut (identity, or the raw down-sample conv with its own
 //     BN) and ReLUs -- instead of writing the raw tensor and re-reading it.
 //
-// Kernel anatomy: persistent CTAs (one per SM), 14 warps:
+// The kernel is specialised at compile time by epilogue MODE and by the presence of the A transform, so
+// that every instantiation is a few hundred straight-line SASS instructions per role: the first
+// monolithic version (8.6k instructions, every option a run-time branch) was instruction-fetch bound in
+// the epilogue warps (ncu: stall_no_inst on most epilogue instructions).
+//   EPI_GENERIC  bias / bias2 / ReLU, fp32 or bf16 output, optional statistics (Linear layers, tests)
+//   EPI_BF16     raw bf16 conv output through TMA bulk stores (+ optional statistics, finalisation)
+//   EPI_STATS    statistics-only pass (nothing stored)
+//   EPI_POST     BatchNorm of the output + shortcut (+ its BatchNorm) + ReLU, bf16 through TMA stores
+//
+// Kernel anatomy: persistent CTAs (one per SM), 10 warps (+4 with the A transform):
 //   warp 0        TMA producer           (smem ring of kStages {A 128x64, B BNx64} bf16 tiles, SW128)
 //   warp 1        MMA issuer + TMEM owner (tcgen05.mma cta_group::1, M=128, N=BN, K=16 per instr)
 //   warps 2..9    epilogue               (tcgen05.ld 32x32b -> bias / BN / residual / ReLU -> bf16 ->
@@ -41,7 +50,10 @@ constexpr int kEpiWarps = 8;                      // two warps per TMEM lane qua
 constexpr int kTfWarps = 4;                       // A-transform warps
 constexpr int kEpiThread0 = 64;
 constexpr int kTfThread0 = 64 + 32 * kEpiWarps;
-constexpr int kThreads = kTfThread0 + 32 * kTfWarps;
+constexpr int kThreadsTf = kTfThread0 + 32 * kTfWarps;   // with the A transform
+constexpr int kThreadsNoTf = kTfThread0;                 // without: the 4 transform warps do not exist
+
+enum EpiMode { EPI_GENERIC = 0, EPI_BF16 = 1, EPI_STATS = 2, EPI_POST = 3 };
 
 using namespace tc;
 
@@ -120,8 +132,8 @@ __device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
   return d;
 }
 
-template <int BN>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int BN, int MODE, bool TF>
+__global__ void __launch_bounds__(TF ? kThreadsTf : kThreadsNoTf, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_r, int M, int N,
                int K, ConvGeom g, ATransform at, EpiParams ep) {
@@ -146,8 +158,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   float* stat_s = reinterpret_cast<float*>(smem + L::kStatOffset);
   uint8_t* staging_s = smem + L::kScratchOffset1k;
   uint8_t* res_s = smem + L::kResOffset;
-  const bool want_stats = ep.col_sum != nullptr;
-  const bool use_tf = at.scale != nullptr;
+  constexpr int kThreads = TF ? kThreadsTf : kThreadsNoTf;
+  constexpr bool kGeneric = MODE == EPI_GENERIC;
+  constexpr bool kPost = MODE == EPI_POST;
+  constexpr bool kStore = MODE != EPI_STATS;
+  const bool want_stats = MODE == EPI_STATS || (MODE != EPI_POST && ep.col_sum != nullptr);
   for (int i = threadIdx.x; i < 8 * BN; i += kThreads) stat_s[i] = 0.f;
 
   const int warp = threadIdx.x >> 5;
@@ -228,7 +243,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     constexpr uint32_t idesc = make_idesc(BM, BN);
-    uint64_t* ready_bar = use_tf ? tf_bar : full_bar;   // with a transform the MMA waits for the rewritten tile
+    uint64_t* ready_bar = TF ? tf_bar : full_bar;   // with a transform the MMA waits for the rewritten tile
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -272,11 +287,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint8_t* res_stg = res_s + (warp - 2) * kStgBytes;
     uint64_t* my_res_bar = &res_bar[warp - 2];
     uint32_t res_phase = 0;
-    const bool has_res = ep.res != nullptr;
-    const bool has_obn = ep.o_scale != nullptr;
-    const bool has_rbn = ep.r_scale != nullptr;
-    const bool post = has_obn || has_res;
-    const bool stats_bf16 = want_stats && ep.out_bf16;
+    // options an instantiation does not have fold to constants (the code behind them disappears)
+    const bool has_res = kPost && ep.res != nullptr;
+    const bool has_obn = kPost && ep.o_scale != nullptr;
+    const bool has_rbn = kPost && ep.r_scale != nullptr;
+    constexpr bool post = kPost;
+    const bool out_bf16 = kGeneric ? ep.out_bf16 != 0 : true;
+    const bool relu = (kGeneric || kPost) ? ep.relu != 0 : false;
+    const bool tma_store = kGeneric ? ep.tma_store != 0 : kStore;
+    const bool stats_bf16 = want_stats && out_bf16;
     float* ss_s = stat_s;                  // [4][BN]: o_scale, o_shift, r_scale, r_shift of the current n-block
     int stg_buf = 0;
     int it = 0;
@@ -322,7 +341,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
           asm volatile("bar.sync 1, 256;" ::: "memory");
         }
-        if (post) {
+        if (kPost) {
           // ---- per-column BatchNorm coefficients of the new n-block -> shared memory
           asm volatile("bar.sync 1, 256;" ::: "memory");       // everyone is done with the previous block's values
           for (int c = epi_tid; c < BN; c += 32 * kEpiWarps) {
@@ -368,7 +387,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
           for (int jj = 0; jj < 32; ++jj) v[jj] = __uint_as_float(raw[jj]);
           // every option below is a WARP-UNIFORM branch around its own loop
-          if (ep.bias != nullptr) {
+          if (kGeneric && ep.bias != nullptr) {
             if (full_chunk) {
 #pragma unroll
               for (int jj = 0; jj < 32; jj += 4) {
@@ -380,14 +399,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 if (col0 + jj < N) v[jj] += __ldg(ep.bias + col0 + jj);
             }
           }
-          if (ep.bias2 != nullptr) {
+          if (kGeneric && ep.bias2 != nullptr) {
             for (int jj = 0; jj < 32; ++jj)
               if (col0 + jj < N) v[jj] += __ldg(ep.bias2 + col0 + jj);
           }
           // raw-output statistics are taken on the bf16-rounded conv result BEFORE any output BN
           uint32_t pk[16];
-          if (ep.out_bf16 && (stats_bf16 || !post)) {
-            if (ep.relu && !post) {
+          if (out_bf16 && (stats_bf16 || !post)) {
+            if (relu && !post) {
 #pragma unroll
               for (int jj = 0; jj < 16; ++jj) pk[jj] = pack_bf16x2_relu(v[2 * jj], v[2 * jj + 1]);
             } else {
@@ -399,7 +418,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           if (stats_bf16) {
             // 32x32 bf16 chunk -> 64-byte-swizzled staging tile (lane = row, 4 x STS.128, conflict-free);
             // column sums are read straight back from the tile.
-            if (ep.tma_store && lane == 0) bulk_wait_read<L::kStgBufs - 1>();   // tile free again?
+            if (tma_store && lane == 0) bulk_wait_read<L::kStgBufs - 1>();   // tile free again?
             __syncwarp();
 #pragma unroll
             for (int c = 0; c < 4; ++c)
@@ -430,7 +449,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               *st2 = __fadd2_rn(*st2, t2);
             }
           }
-          if (ep.store) {
+          if (kStore) {
             if (post) {
               // BatchNorm of this conv's output + shortcut (+ its BatchNorm) + ReLU on the fp32 accumulators;
               // the coefficients are broadcast reads of the n-block table in shared memory
@@ -467,8 +486,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                   }
                 }
               }
-              if (ep.out_bf16) {
-                if (ep.relu) {
+              if (out_bf16) {
+                if (relu) {
 #pragma unroll
                   for (int jj = 0; jj < 16; ++jj) pk[jj] = pack_bf16x2_relu(v[2 * jj], v[2 * jj + 1]);
                 } else {
@@ -477,8 +496,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 }
               }
             }
-            if (ep.out_bf16) {
-              if (ep.tma_store) {
+            if (out_bf16) {
+              if (tma_store) {
                 // staging tile -> one TMA bulk store in full 64-byte row segments (no LSU, no registers)
                 if (!stats_bf16) {
                   if (lane == 0) bulk_wait_read<L::kStgBufs - 1>();
@@ -497,7 +516,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                   bulk_commit();
                 }
                 stg_buf = (stg_buf + 1) % L::kStgBufs;
-              } else if (row_ok) {
+              } else if (kGeneric && row_ok) {
                 bf16* dp = reinterpret_cast<bf16*>(ep.D) + (long)row * ep.ldd + col0;
                 if (full_chunk && ((reinterpret_cast<uintptr_t>(dp) & 31) == 0)) {
                   asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dp), "r"(pk[0]), "r"(pk[1]),
@@ -515,8 +534,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     if (col0 + jj < N) dp[jj] = __ushort_as_bfloat16((unsigned short)(pk[jj >> 1] >> ((jj & 1) * 16)));
                 }
               }
-            } else if (row_ok) {
-              if (ep.relu) {
+            } else if (kGeneric && row_ok) {
+              if (relu) {
 #pragma unroll
                 for (int jj = 0; jj < 32; ++jj) v[jj] = fmaxf(v[jj], 0.0f);
               }
@@ -537,7 +556,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               }
             }
           }
-          if (want_stats && !ep.out_bf16) {
+          if (kGeneric && want_stats && !out_bf16) {
             // fp32 output (statistics of the value as stored, ReLU included): column sums over this warp's
             // 32 rows by butterfly reduce-scatter (lane l ends with column l)
             float s2[32];
@@ -569,7 +588,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
-    if (ep.tma_store && lane == 0) bulk_wait_all();   // all bulk stores of this warp have landed
+    if (tma_store && lane == 0) bulk_wait_all();   // all bulk stores of this warp have landed
     if (want_stats && cur_nblk >= 0) {
       // ---- final flush (same as above)
       asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -581,7 +600,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
       }
     }
-  } else if (use_tf) {
+  } else if (TF) {
     // =========================== A transform (warps 10..13) ===========================
     // thread = (16-byte chunk c of the 128-byte row, rows rb + 16 i): 8 channels whose scale/shift are
     // loaded once per k-block.  Branch-free and batched (8 LDS.128 in flight, then math, then 8 STS.128);
@@ -757,18 +776,20 @@ int make_tmap_2d(CUtensorMap* map, const void* base, long rows, long cols, long 
   return 0;
 }
 
-template <int BN>
+template <int BN, int MODE, bool TF>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tr, int M, int N,
                 int K, const ConvGeom& g, const ATransform& at, const EpiParams& ep, cudaStream_t stream) {
   using L = SmemLayout<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    B2_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    B2_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, MODE, TF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       L::kTotal));
     attr_set = true;
   }
   const int tiles = b2_ceil_div(M, BM) * b2_ceil_div(N, BN);
   const int grid = tiles < b2_num_sms() ? tiles : b2_num_sms();
-  gemm_tc_kernel<BN><<<grid, kThreads, L::kTotal, stream>>>(ta, tb, td, tr, M, N, K, g, at, ep);
+  gemm_tc_kernel<BN, MODE, TF><<<grid, TF ? kThreadsTf : kThreadsNoTf, L::kTotal, stream>>>(ta, tb, td, tr, M, N, K, g,
+                                                                                           at, ep);
   B2_LAUNCH_CHECK("gemm_tc_kernel");
   return 0;
 }
@@ -778,6 +799,21 @@ int pick_bn(int N) {
   if (N > 64) return 128;
   if (N > 32) return 64;
   return 32;
+}
+
+template <int MODE, bool TF>
+int dispatch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tr,
+                int M, int N, int K, const ConvGeom& g, const ATransform& at, const EpiParams& ep, cudaStream_t stream) {
+  switch (bn) {
+    case 256: return launch_gemm<256, MODE, TF>(ta, tb, td, tr, M, N, K, g, at, ep, stream);
+    case 128: return launch_gemm<128, MODE, TF>(ta, tb, td, tr, M, N, K, g, at, ep, stream);
+    case 64: return launch_gemm<64, MODE, TF>(ta, tb, td, tr, M, N, K, g, at, ep, stream);
+    default:
+      if constexpr (MODE == EPI_GENERIC && !TF)
+        return launch_gemm<32, MODE, TF>(ta, tb, td, tr, M, N, K, g, at, ep, stream);
+      b2_set_error("gemm_tc: this epilogue needs at least 64 output columns (got %d)", N);
+      return -1;
+  }
 }
 
 int dispatch(int bn, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const ConvGeom& g,
@@ -792,11 +828,31 @@ int dispatch(int bn, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N,
   if (ep.res != nullptr) {   // shortcut tiles are fetched by TMA (same 32x32 SWIZZLE_64B boxes as the store)
     if (int r = make_tmap_2d(&tr, ep.res, M, N, ep.ldres, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return r;
   }
-  switch (bn) {
-    case 256: return launch_gemm<256>(ta, tb, td, tr, M, N, K, g, at, ep, stream);
-    case 128: return launch_gemm<128>(ta, tb, td, tr, M, N, K, g, at, ep, stream);
-    case 64: return launch_gemm<64>(ta, tb, td, tr, M, N, K, g, at, ep, stream);
-    default: return launch_gemm<32>(ta, tb, td, tr, M, N, K, g, at, ep, stream);
+  // pick the compile-time specialisation: the lean conv epilogues need whole 32-column chunks, a bf16 output
+  // that can leave by TMA, and no bias / ReLU on the raw output; everything else takes the generic one
+  const bool tf = at.scale != nullptr;
+  const bool lean = bn >= 64 && (N % 32) == 0 && ep.bias == nullptr && ep.bias2 == nullptr && ep.out_bf16;
+  const bool post = ep.o_scale != nullptr || ep.res != nullptr;
+  int mode = EPI_GENERIC;
+  if (lean && !ep.store && !post) mode = EPI_STATS;
+  else if (lean && ep.store && ep.tma_store && post) mode = EPI_POST;
+  else if (lean && ep.store && ep.tma_store && !ep.relu) mode = EPI_BF16;
+  if (mode == EPI_GENERIC && (tf || post || !ep.store)) {
+    b2_set_error("gemm_tc: BatchNorm folding needs a 16 B aligned bf16 output with N %% 32 == 0 and N >= 64 (N=%d)", N);
+    return -1;
+  }
+  switch (mode) {
+    case EPI_STATS:
+      return tf ? dispatch_bn<EPI_STATS, true>(bn, ta, tb, td, tr, M, N, K, g, at, ep, stream)
+                : dispatch_bn<EPI_STATS, false>(bn, ta, tb, td, tr, M, N, K, g, at, ep, stream);
+    case EPI_POST:
+      return tf ? dispatch_bn<EPI_POST, true>(bn, ta, tb, td, tr, M, N, K, g, at, ep, stream)
+                : dispatch_bn<EPI_POST, false>(bn, ta, tb, td, tr, M, N, K, g, at, ep, stream);
+    case EPI_BF16:
+      return tf ? dispatch_bn<EPI_BF16, true>(bn, ta, tb, td, tr, M, N, K, g, at, ep, stream)
+                : dispatch_bn<EPI_BF16, false>(bn, ta, tb, td, tr, M, N, K, g, at, ep, stream);
+    default:
+      return dispatch_bn<EPI_GENERIC, false>(bn, ta, tb, td, tr, M, N, K, g, at, ep, stream);
   }
 }
 

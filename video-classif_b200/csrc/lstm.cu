@@ -39,13 +39,28 @@ lstm_fwd_kernel(const float* __restrict__ G, const float* __restrict__ Whh, floa
   float c = 0.f;
   for (int i = j; i < NB * H; i += blockDim.x) h_s[i] = 0.f;
   __syncthreads();
+  // the hoisted gate pre-activations of step s+1 are fetched while step s computes: the only global-memory
+  // latency left on the recurrence's critical path is the first step's
+  float g_next[NB];
+#pragma unroll
+  for (int b = 0; b < NB; ++b)
+    g_next[b] = (active && b0 + b < B) ? G[((long)(b0 + b) * T + (reverse ? T - 1 : 0)) * H4 + j] : 0.f;
   for (int step = 0; step < T; ++step) {
     const int t = reverse ? T - 1 - step : step;
+    float g_cur[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) g_cur[b] = g_next[b];
+    if (step + 1 < T) {
+      const int tn = reverse ? t - 1 : t + 1;
+#pragma unroll
+      for (int b = 0; b < NB; ++b)
+        if (active && b0 + b < B) g_next[b] = G[((long)(b0 + b) * T + tn) * H4 + j];
+    }
     if (active) {
 #pragma unroll
       for (int b = 0; b < NB; ++b) {
         if (b0 + b < B) {
-          float acc = G[((long)(b0 + b) * T + t) * H4 + j];
+          float acc = g_cur[b];
           const float* hb = h_s + b * H;
 #pragma unroll
           for (int k = 0; k < HP; ++k)
@@ -100,17 +115,39 @@ lstm_bwd_kernel(const float* __restrict__ dout, long dout_ld, const float* __res
 #pragma unroll
   for (int k = 0; k < HP; ++k) dw[k] = 0.f;
   __syncthreads();
-  for (int step = T - 1; step >= 0; --step) {
-    const int t = reverse ? T - 1 - step : step;
-    const int tp = reverse ? t + 1 : t - 1;   // time index of the previous state in recurrence order
-    const bool has_prev = step > 0;
+  // saved activations and the incoming gradient of step s-1 are fetched while step s computes
+  struct Saved { float ig, fg, gg, og, cc, cprev, dout, hprev; };
+  auto fetch = [&](int step) {
+    Saved v = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (upd) {
+      const int t = reverse ? T - 1 - step : step;
+      const int tp = reverse ? t + 1 : t - 1;
       const long bt = (long)(b0 + ub) * T + t;
       const float* gp = gates + bt * H4;
-      const float ig = gp[uk], fg = gp[H + uk], gg = gp[2 * H + uk], og = gp[3 * H + uk];
-      const float cc = cst[bt * H + uk];
-      const float cprev = has_prev ? cst[((long)(b0 + ub) * T + tp) * H + uk] : 0.f;
-      const float dh = dout[bt * dout_ld + uk] + dh_rec;
+      v.ig = gp[uk];
+      v.fg = gp[H + uk];
+      v.gg = gp[2 * H + uk];
+      v.og = gp[3 * H + uk];
+      v.cc = cst[bt * H + uk];
+      v.dout = dout[bt * dout_ld + uk];
+      if (step > 0) {
+        v.cprev = cst[((long)(b0 + ub) * T + tp) * H + uk];
+        v.hprev = out[((long)(b0 + ub) * T + tp) * out_ld + uk];
+      }
+    }
+    return v;
+  };
+  Saved nxt = fetch(T - 1);
+  for (int step = T - 1; step >= 0; --step) {
+    const int t = reverse ? T - 1 - step : step;
+    const Saved cur = nxt;
+    if (step > 0) nxt = fetch(step - 1);
+    if (upd) {
+      const long bt = (long)(b0 + ub) * T + t;
+      const float ig = cur.ig, fg = cur.fg, gg = cur.gg, og = cur.og;
+      const float cc = cur.cc;
+      const float cprev = cur.cprev;
+      const float dh = cur.dout + dh_rec;
       const float tc = tanhf(cc);
       const float dct = dc + dh * og * (1.f - tc * tc);
       float* d = dg_s + ub * H4;
@@ -128,7 +165,7 @@ lstm_bwd_kernel(const float* __restrict__ dout, long dout_ld, const float* __res
       go[2 * H + uk] = dgg;
       go[3 * H + uk] = dgo;
       dc = dct * fg;
-      hp_s[ub * H + uk] = has_prev ? out[((long)(b0 + ub) * T + tp) * out_ld + uk] : 0.f;
+      hp_s[ub * H + uk] = cur.hprev;
     } else if (active && ub < NB) {
       float* d = dg_s + ub * H4;   // rows beyond the batch contribute nothing
       d[uk] = d[H + uk] = d[2 * H + uk] = d[3 * H + uk] = 0.f;

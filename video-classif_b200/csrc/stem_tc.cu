@@ -244,27 +244,34 @@ stem_conv_kernel(const uint4* __restrict__ xp, const uint4* __restrict__ wk, bf1
           *reinterpret_cast<uint4*>(stg + lane * 64 + ((c ^ sw) << 4)) =
               make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
         __syncwarp();
-        float s1a = 0.f, s1b = 0.f, s1c = 0.f, s1d = 0.f, s2a = 0.f, s2b = 0.f, s2c = 0.f, s2d = 0.f;
-        const int w = lane >> 1;
-        const int sh = (lane & 1) ? 0 : 16;
-        const uint8_t* colp = stg + ((w & 3) << 2);
-        const int wc = w >> 2;
+        // lane (w = lane & 15, hf = lane >> 4) sums columns 2w, 2w+1 over rows 16 hf .. 16 hf + 15 straight from
+        // the swizzled tile (same scheme as gemm_tc.cu: packed fp32 adds, the two half-warps never share a bank)
+        const int sw_w = lane & 15, sw_hf = lane >> 4;
+        float2 s1a = make_float2(0.f, 0.f), s1b = s1a, s2a = s1a, s2b = s1a;
 #pragma unroll
-        for (int r = 0; r < 32; r += 4) {
-          uint32_t uu[4];
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4)
-            uu[q4] = *reinterpret_cast<const uint32_t*>(colp + (r + q4) * 64 + ((wc ^ (((r + q4) >> 1) & 3)) << 4));
-          const float x0 = __uint_as_float((uu[0] << sh) & 0xffff0000u);
-          const float x1 = __uint_as_float((uu[1] << sh) & 0xffff0000u);
-          const float x2 = __uint_as_float((uu[2] << sh) & 0xffff0000u);
-          const float x3 = __uint_as_float((uu[3] << sh) & 0xffff0000u);
-          s1a += x0; s1b += x1; s1c += x2; s1d += x3;
-          s2a = fmaf(x0, x0, s2a); s2b = fmaf(x1, x1, s2b); s2c = fmaf(x2, x2, s2c); s2d = fmaf(x3, x3, s2d);
+        for (int i = 0; i < 16; i += 2) {
+          const int k = (i >> 1) & 3;
+          const uint32_t col = (uint32_t)((((sw_w >> 2) ^ k) << 4) + (sw_w & 3) * 4) + (uint32_t)(sw_hf * 1024);
+          const uint32_t u0 = *reinterpret_cast<const uint32_t*>(stg + col + (uint32_t)(sw_hf * 64) + i * 64);
+          const uint32_t u1 = *reinterpret_cast<const uint32_t*>(stg + col - (uint32_t)(sw_hf * 64) + (i + 1) * 64);
+          const float2 x0 = make_float2(__uint_as_float(u0 << 16), __uint_as_float(u0 & 0xffff0000u));
+          const float2 x1 = make_float2(__uint_as_float(u1 << 16), __uint_as_float(u1 & 0xffff0000u));
+          s1a = __fadd2_rn(s1a, x0);
+          s1b = __fadd2_rn(s1b, x1);
+          s2a = __ffma2_rn(x0, x0, s2a);
+          s2b = __ffma2_rn(x1, x1, s2b);
         }
-        float* st = stat_s + quarter * 2 * kCout + ch * 32 + lane;
-        st[0] += (s1a + s1b) + (s1c + s1d);
-        st[kCout] += (s2a + s2b) + (s2c + s2d);
+        float2 t1 = __fadd2_rn(s1a, s1b), t2 = __fadd2_rn(s2a, s2b);
+        t1.x += __shfl_xor_sync(0xffffffffu, t1.x, 16);
+        t1.y += __shfl_xor_sync(0xffffffffu, t1.y, 16);
+        t2.x += __shfl_xor_sync(0xffffffffu, t2.x, 16);
+        t2.y += __shfl_xor_sync(0xffffffffu, t2.y, 16);
+        if (sw_hf == 0) {
+          float2* st = reinterpret_cast<float2*>(stat_s + quarter * 2 * kCout + ch * 32 + 2 * sw_w);
+          float2* st2 = reinterpret_cast<float2*>(stat_s + quarter * 2 * kCout + kCout + ch * 32 + 2 * sw_w);
+          *st = __fadd2_rn(*st, t1);
+          *st2 = __fadd2_rn(*st2, t2);
+        }
         __syncwarp();
       }
     }

@@ -124,19 +124,24 @@ template <bool TA, bool TB>
 __global__ void __launch_bounds__(256)
 sgemm_kernel(int M, int N, int K, float alpha, const float* __restrict__ A, long lda, const float* __restrict__ B,
              long ldb, float beta, float* __restrict__ C, long ldc, const float* __restrict__ bias,
-             const float* __restrict__ bias2) {
+             const float* __restrict__ bias2, int k_per_split) {
+  // split-K (gridDim.z > 1): each z-slice reduces its own K range and adds into a pre-zeroed C with atomics --
+  // skinny products (LSTM weight gradients: 4H x In outputs over K = B*T rows) otherwise run on 1-2 CTAs
   __shared__ float As[TK][TS + 4];
   __shared__ float Bs[TK][TS + 4];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int m0 = blockIdx.y * TS, n0 = blockIdx.x * TS;
+  const int k_begin = blockIdx.z * k_per_split;
+  const int k_end = min(K, k_begin + k_per_split);
+  const bool split = gridDim.z > 1;
   float acc[4][4] = {};
-  for (int k0 = 0; k0 < K; k0 += TK) {
+  for (int k0 = k_begin; k0 < k_end; k0 += TK) {
     for (int i = threadIdx.x; i < TS * TK; i += 256) {
       int m, k;
       if (TA) { m = i % TS; k = i / TS; } else { k = i % TK; m = i / TK; }
       const int gm = m0 + m, gk = k0 + k;
       float v = 0.f;
-      if (gm < M && gk < K) v = TA ? A[(long)gk * lda + gm] : A[(long)gm * lda + gk];
+      if (gm < M && gk < k_end) v = TA ? A[(long)gk * lda + gm] : A[(long)gm * lda + gk];
       As[k][m] = v;
     }
     for (int i = threadIdx.x; i < TS * TK; i += 256) {
@@ -144,7 +149,7 @@ sgemm_kernel(int M, int N, int K, float alpha, const float* __restrict__ A, long
       if (TB) { k = i % TK; n = i / TK; } else { n = i % TS; k = i / TS; }
       const int gn = n0 + n, gk = k0 + k;
       float v = 0.f;
-      if (gn < N && gk < K) v = TB ? B[(long)gn * ldb + gk] : B[(long)gk * ldb + gn];
+      if (gn < N && gk < k_end) v = TB ? B[(long)gn * ldb + gk] : B[(long)gk * ldb + gn];
       Bs[k][n] = v;
     }
     __syncthreads();
@@ -172,14 +177,17 @@ sgemm_kernel(int M, int N, int K, float alpha, const float* __restrict__ A, long
       if (gn >= N) continue;
       float* c = C + (long)gm * ldc + gn;
       float v = alpha * acc[i][j];
-      if (bias) v += bias[gn];
-      if (bias2) v += bias2[gn];
-      *c = (beta == 0.f) ? v : v + beta * (*c);
+      if (blockIdx.z == 0) {
+        if (bias) v += bias[gn];
+        if (bias2) v += bias2[gn];
+      }
+      if (split) atomicAdd(c, v);
+      else *c = (beta == 0.f) ? v : v + beta * (*c);
     }
   }
 }
 
-// out[c] (+)= sum_r X[r, c]
+// out[c] (+)= sum_r X[r, c] ; gridDim.y row slices (> 1: atomics into a pre-zeroed / accumulated out)
 __global__ void __launch_bounds__(256)
 colsum_kernel(const float* __restrict__ X, long ld, long M, int N, float* __restrict__ out, int accumulate) {
   __shared__ float red[8][33];
@@ -187,14 +195,15 @@ colsum_kernel(const float* __restrict__ X, long ld, long M, int N, float* __rest
   const int ry = threadIdx.x >> 5;
   float s = 0.f;
   if (c < N)
-    for (long r = ry; r < M; r += 8) s += X[r * ld + c];
+    for (long r = (long)blockIdx.y * 8 + ry; r < M; r += 8L * gridDim.y) s += X[r * ld + c];
   red[ry][threadIdx.x & 31] = s;
   __syncthreads();
   if (ry == 0 && c < N) {
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
-    out[c] = accumulate ? out[c] + t : t;
+    if (gridDim.y > 1) atomicAdd(out + c, t);
+    else out[c] = accumulate ? out[c] + t : t;
   }
 }
 
@@ -281,19 +290,39 @@ B2_API int b2_sgemm(int trans_a, int trans_b, int M, int N, int K, float alpha, 
                     const float* B, long ldb, float beta, float* C, long ldc, const float* bias, const float* bias2,
                     void* stream) {
   B2_ARG_CHECK(A && B && C && M > 0 && N > 0 && K > 0, "b2_sgemm: null pointer or empty shape");
-  dim3 grid(b2_ceil_div(N, TS), b2_ceil_div(M, TS));
   cudaStream_t st = (cudaStream_t)stream;
-  if (!trans_a && !trans_b) sgemm_kernel<false, false><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, bias2);
-  else if (!trans_a && trans_b) sgemm_kernel<false, true><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, bias2);
-  else if (trans_a && !trans_b) sgemm_kernel<true, false><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, bias2);
-  else sgemm_kernel<true, true><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, bias2);
+  const int tiles = b2_ceil_div(N, TS) * b2_ceil_div(M, TS);
+  int splits = 1;
+  if (beta == 0.f && tiles * 2 <= b2_num_sms() && K >= 8 * TK) {   // skinny output, long reduction: split K
+    splits = b2_num_sms() / tiles;
+    const int max_splits = K / (4 * TK);
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+  }
+  int k_per_split = (b2_ceil_div(K, splits) + TK - 1) / TK * TK;
+  splits = b2_ceil_div(K, k_per_split);
+  if (splits > 1) B2_CUDA_CHECK(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, st));
+  dim3 grid(b2_ceil_div(N, TS), b2_ceil_div(M, TS), splits);
+  if (!trans_a && !trans_b) sgemm_kernel<false, false><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, bias2, k_per_split);
+  else if (!trans_a && trans_b) sgemm_kernel<false, true><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, bias2, k_per_split);
+  else if (trans_a && !trans_b) sgemm_kernel<true, false><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, bias2, k_per_split);
+  else sgemm_kernel<true, true><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, bias2, k_per_split);
   B2_LAUNCH_CHECK("sgemm_kernel");
   return 0;
 }
 
 B2_API int b2_colsum_f32(const float* X, long ld, long M, int N, float* out, int accumulate, void* stream) {
   B2_ARG_CHECK(X && out && M > 0 && N > 0, "b2_colsum_f32: null pointer or empty");
-  colsum_kernel<<<b2_ceil_div(N, 32), 256, 0, (cudaStream_t)stream>>>(X, ld, M, N, out, accumulate);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int col_blocks = b2_ceil_div(N, 32);
+  int slices = 1;
+  if (M >= 256 && col_blocks * 2 <= b2_num_sms()) {
+    slices = b2_num_sms() / col_blocks;
+    if (slices > M / 64) slices = (int)(M / 64);
+    if (slices < 1) slices = 1;
+  }
+  if (slices > 1 && !accumulate) B2_CUDA_CHECK(cudaMemsetAsync(out, 0, (size_t)N * 4, st));
+  colsum_kernel<<<dim3(col_blocks, slices), 256, 0, st>>>(X, ld, M, N, out, accumulate);
   B2_LAUNCH_CHECK("colsum_kernel");
   return 0;
 }
