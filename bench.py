@@ -295,9 +295,9 @@ def run_ours(args):
     # ---------------- roofline of the dominant kernel (tcgen05 GEMM / implicit-GEMM conv) -----------
     roof = None
     tflops_peak, hbm_peak, peak_src = peaks()
-    if not args.no_roofline and rank == 0:
+    if not args.no_roofline:       # every rank runs these steps (they contain the gradient all-reduce); rank 0 reports
         events = []
-        orig_gemm, orig_conv, orig_convbn = ops.gemm_tn, ops.conv2d_nhwc, ops.conv2d_bn_nhwc
+        orig_gemm, orig_conv, orig_convbn, orig_gram = ops.gemm_tn, ops.conv2d_nhwc, ops.conv2d_bn_nhwc, ops.conv1x1_gram_bnstats
         import video_classif_b200.backbone as bb
 
         def timed(fn, flops_of):
@@ -325,7 +325,9 @@ def run_ours(args):
         ops.gemm_tn = timed(orig_gemm, gemm_flops)
         ops.conv2d_nhwc = timed(orig_conv, conv_flops)
         ops.conv2d_bn_nhwc = timed(orig_convbn, conv_flops)      # a statistics-only pass counts its flops too
-        bb.gemm_tn, bb.conv2d_nhwc, bb.conv2d_bn_nhwc = ops.gemm_tn, ops.conv2d_nhwc, ops.conv2d_bn_nhwc
+        ops.conv1x1_gram_bnstats = timed(orig_gram, lambda a, k, out: 0.0)   # tensor-core statistics: time, no algorithmic flops
+        bb.gemm_tn, bb.conv2d_nhwc, bb.conv2d_bn_nhwc, bb.conv1x1_gram_bnstats = (ops.gemm_tn, ops.conv2d_nhwc, ops.conv2d_bn_nhwc,
+                                                                                 ops.conv1x1_gram_bnstats)
         try:
             for i in range(2):
                 events.clear()
@@ -333,15 +335,15 @@ def run_ours(args):
                 step(dev_x[i % NBUF], dev_y[i % NBUF])
                 torch.cuda.synchronize()
         finally:
-            ops.gemm_tn, ops.conv2d_nhwc, ops.conv2d_bn_nhwc = orig_gemm, orig_conv, orig_convbn
-            bb.gemm_tn, bb.conv2d_nhwc, bb.conv2d_bn_nhwc = orig_gemm, orig_conv, orig_convbn
+            ops.gemm_tn, ops.conv2d_nhwc, ops.conv2d_bn_nhwc, ops.conv1x1_gram_bnstats = orig_gemm, orig_conv, orig_convbn, orig_gram
+            bb.gemm_tn, bb.conv2d_nhwc, bb.conv2d_bn_nhwc, bb.conv1x1_gram_bnstats = orig_gemm, orig_conv, orig_convbn, orig_gram
         tot_ms = sum(s.elapsed_time(e) for s, e, _ in events)
         tot_fl = sum(f for _, _, f in events)
         achieved = tot_fl / (tot_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": achieved, "peak": tflops_peak, "unit": "TFLOP/s",
                 "frac": achieved / tflops_peak, "traffic": None, "kernel": "gemm_tc_kernel (tcgen05 GEMM + implicit-GEMM conv)",
                 "launches_per_step": len(events), "kernel_ms_per_step": tot_ms, "algorithmic_gflop_per_step": tot_fl / 1e9,
-                "share_of_step": tot_ms / ms_per_step, "peak_source": peak_src}
+                "share_of_step": tot_ms / ms_per_step, "peak_source": peak_src} if rank == 0 else None
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -87,6 +87,19 @@ int b2_bn_finalize_nhwc(const float* sum, const float* sumsq, const float* gamma
 int b2_scale_shift_apply_nhwc(const void* x, void* y, long rows, int C, const float* scale, const float* shift,
                               const void* res, const float* rscale, const float* rshift, int relu, void* stream);
 
+/* BatchNorm statistics + finalisation of a 1x1 convolution y = relu?(x*a_scale+a_shift) W^T WITHOUT computing y
+ * (torchvision Bottleneck.bn3 in train mode, models.py:192): per-channel sum_m y and sum_m y^2 follow from the
+ * K-vector s = sum_m t[m,:] and the K x K Gram matrix G = sum_m t^T t of the transformed input (tensor-core
+ * MN-major MMA over one streaming pass of x), evaluated per output channel in fp64.  x [M, C] bf16 (C = 64 or 128),
+ * w [Cout, C] bf16; workspace: b2_gram_workspace_floats(C) floats (scratch, zeroed inside); col_sum/col_sumsq [Cout] optional outputs
+ * (OVERWRITTEN); fin_scale/fin_shift [Cout] = gamma*rstd, beta - mean*gamma*rstd; running stats updated when given. */
+long b2_gram_workspace_floats(int C);
+int b2_conv1x1_gram_bnstats_bf16(const void* x, long M, int C, const void* w, int Cout, const float* a_scale,
+                                 const float* a_shift, int a_relu, float* workspace, float* col_sum, float* col_sumsq,
+                                 const float* fin_gamma, const float* fin_beta, float* fin_running_mean,
+                                 float* fin_running_var, float* fin_scale, float* fin_shift, float eps, float momentum,
+                                 void* stream);
+
 /* ---- backbone glue (NHWC bf16) ----------------------------------------------------------
  * b2_stem_im2col: NCHW fp32/bf16 frames -> [N*P*Q][Kp] bf16 patches of the 7x7/2 pad-3 stem conv,
  * column k = (c*7+r)*8+s (filter rows padded to 8 taps), Kp = 168.

@@ -136,6 +136,32 @@ def test_conv_bn_folded(ops, N, H, W, C, Cout, R, stride, pad):
     assert err(out4.float(), ref4) < 8e-3
 
 
+@pytest.mark.parametrize("M,C,Cout", [(128, 64, 256), (256, 128, 512), (1000, 64, 64), (5000, 128, 256), (70000, 64, 256),
+                                      (33333, 128, 512)])
+def test_gram_bn_statistics(ops, M, C, Cout):
+    """b2_conv1x1_gram_bnstats_bf16: sum / sum-of-squares / BN scale+shift of relu(x*a+b) @ W^T from the Gram
+    matrix (MN-major tcgen05 MMA) vs the directly computed fp64 statistics of the same product."""
+    torch.manual_seed(M + C)
+    xr = (torch.randn(M, C) * 1.5).bfloat16()
+    a_sc, a_sh = torch.rand(C) + 0.5, torch.randn(C) * 0.3 + 0.5
+    w = (torch.randn(Cout, C) / C ** 0.5).bfloat16()
+    t = torch.relu(xr.float() * a_sc + a_sh).bfloat16().double()
+    y = t @ w.double().t()
+    gamma, beta = (torch.rand(Cout) + 0.5).to(DEV), torch.randn(Cout).to(DEV)
+    rm, rv = torch.zeros(Cout, device=DEV), torch.ones(Cout, device=DEV)
+    s1, s2 = torch.full((Cout,), 7.0, device=DEV), torch.full((Cout,), 7.0, device=DEV)
+    fs, fh = torch.empty(Cout, device=DEV), torch.empty(Cout, device=DEV)
+    ops.conv1x1_gram_bnstats(xr.to(DEV), w.to(DEV), (a_sc.to(DEV), a_sh.to(DEV)),
+                             (gamma, beta, rm, rv, fs, fh, None, 1e-5, 0.1), stats=(s1, s2))
+    mean, var = y.mean(0), y.var(0, unbiased=False)
+    assert err(s1, y.sum(0), floor=1e-3 * y.abs().sum(0).max().item()) < 1e-3
+    assert err(s2, (y * y).sum(0)) < 1e-3
+    sc_ref = gamma.cpu().double() / torch.sqrt(var + 1e-5)
+    assert err(fs, sc_ref) < 2e-3
+    assert err(fh, beta.cpu().double() - mean * sc_ref, floor=1.0) < 2e-3
+    assert err(rm, 0.1 * mean, floor=1e-2) < 2e-3 and err(rv, 0.9 + 0.1 * var * M / max(M - 1, 1)) < 2e-3
+
+
 def test_ingest_bit_exact_vs_cv2_golden(ops):
     g = np.load(os.path.join(GOLDEN, "resize_cv2.npz"))
     i = 0

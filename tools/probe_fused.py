@@ -16,7 +16,7 @@ print(torch.cuda.get_device_name(0), "frames", NF, flush=True)
 
 
 def timeit(fn, reps=5):
-    if mode == "ncu":
+    if mode in ("ncu", "gram"):
         fn()
         torch.cuda.synchronize()
         return float("nan")
@@ -62,6 +62,8 @@ def case(name, H, C, Cout, R, stride, pad, variants):
             return ops.conv2d_bn_nhwc(x, w, stride, pad, a=a, stats=st, fin=fin, store=False)
         if v == "statsonly":
             return ops.conv2d_bn_nhwc(x, w, stride, pad, stats=st, fin=fin, store=False)
+        if v == "gram":
+            return ops.conv1x1_gram_bnstats(x, w, a, fin)
         if v == "a+o":
             return ops.conv2d_bn_nhwc(x, w, stride, pad, a=a, o=o, relu=True)
         if v == "a+o+res":
@@ -87,6 +89,9 @@ if mode == "quick":
     case("l1.conv3", 28, 64, 256, 1, 1, 0, ["plain", "stats", "a+statsonly", "a+o+res"])
     case("l3.conv2", 7, 256, 256, 3, 1, 1, ["plain", "stats"])
     case("l4.conv2", 4, 512, 512, 3, 1, 1, ["plain", "stats"])
+elif mode == "gram":
+    case("l1.conv3", 28, 64, 256, 1, 1, 0, ["gram", "a+o+res"])
+    case("l2.conv3", 14, 128, 512, 1, 1, 0, ["gram", "a+o+res"])
 elif mode == "ncu":
     case("l1.conv2", 28, 64, 64, 3, 1, 1, ["a+stats"])
     case("l1.conv3", 28, 64, 256, 1, 1, 0, ["a+statsonly", "a+o+res"])
@@ -98,10 +103,10 @@ else:
     print(f"stem       plain        {timeit(lambda: ops.stem_conv(xs, wk)):8.1f} us (pack + conv)")
     case("l1.conv1", 28, 256, 64, 1, 1, 0, ["plain", "stats"])
     case("l1.conv2", 28, 64, 64, 3, 1, 1, ["apply", "plain", "stats", "a", "a+stats"])
-    case("l1.conv3", 28, 64, 256, 1, 1, 0, ["plain", "stats", "statsonly", "a", "a+statsonly", "a+o", "o+res", "a+o+res", "a+o+res+r"])
+    case("l1.conv3", 28, 64, 256, 1, 1, 0, ["plain", "stats", "statsonly", "a", "a+statsonly", "gram", "a+o", "o+res", "a+o+res", "a+o+res+r"])
     case("l2.conv2", 28, 128, 128, 3, 2, 1, ["apply", "plain", "stats"])
     case("l2.conv2", 14, 128, 128, 3, 1, 1, ["apply", "plain", "stats", "a", "a+stats"])
-    case("l2.conv3", 14, 128, 512, 1, 1, 0, ["plain", "stats", "a+statsonly", "a+o+res"])
+    case("l2.conv3", 14, 128, 512, 1, 1, 0, ["plain", "stats", "a+statsonly", "gram", "a+o+res"])
     case("l3.conv2", 7, 256, 256, 3, 1, 1, ["plain", "a+stats"])
     case("l3.conv3", 7, 256, 1024, 1, 1, 0, ["plain", "stats", "a+statsonly", "a+o+res"])
 print("PROBE DONE")

@@ -21,8 +21,8 @@ import torch
 
 from . import _lib
 from ._lib import call, ptr, stream_ptr
-from .ops import (BF16, F32, conv2d_bn_nhwc, conv2d_nhwc, gemm_tn, pack_stem_weight, scale_shift_apply,
-                  stem_conv)
+from .ops import (BF16, F32, GRAM_CHANNELS, conv1x1_gram_bnstats, conv2d_bn_nhwc, conv2d_nhwc, gemm_tn, pack_stem_weight,
+                  scale_shift_apply, stem_conv)
 
 SUPPORTED = ("resnet18", "resnet34", "resnet50", "resnet101", "resnet152")
 STEM_KP = 168   # stem patch columns: (c*7 + r)*8 + s, filter rows padded from 7 to 8 taps
@@ -43,7 +43,7 @@ def make_backbone(name: str, pretrained: bool = False):
 
 
 class ResNetRunner:
-    FUSE_BN = os.environ.get("B2_FUSE_BN", "0") == "1"   # class default; tests run both settings
+    FUSE_BN = os.environ.get("B2_FUSE_BN", "1") == "1"   # class default; tests run both settings
     def __init__(self, net):
         self.net = net
         self._wcache = None
@@ -185,7 +185,11 @@ class ResNetRunner:
                             dbn = blk.downsample[1]
                             rd = conv2d_bn_nhwc(y, w[pfx + ".downsample.0"], stride, 0, stats=stats_of(dbn),
                                                 fin=fin_of(dbn))
-                        if train:              # statistics-only pass of conv3
+                        if train and r2.shape[-1] in GRAM_CHANNELS:
+                            # BN3 statistics from the Gram matrix of conv3's (transformed) input: one HBM-bound
+                            # pass over the small tensor instead of a full conv3 whose output is thrown away
+                            conv1x1_gram_bnstats(r2, w[pfx + ".conv3"], ss_of(blk.bn2), fin_of(blk.bn3))
+                        elif train:            # statistics-only pass of conv3
                             conv2d_bn_nhwc(r2, w[pfx + ".conv3"], 1, 0, a=ss_of(blk.bn2), stats=stats_of(blk.bn3),
                                            fin=fin_of(blk.bn3), store=False)
                         y = conv2d_bn_nhwc(r2, w[pfx + ".conv3"], 1, 0, a=ss_of(blk.bn2), o=ss_of(blk.bn3),

@@ -106,24 +106,28 @@ struct EpiParams {
 
 constexpr int kStgBytes = 32 * 64;  // epilogue staging tile: 32 rows x 32 bf16 (64-byte rows, SWIZZLE_64B)
 
-template <int BN>
+constexpr int kResSlots = 4;         // EPI_POST: per-warp ring of shortcut / output tiles (power of two)
+
+template <int BN, int MODE>
 struct SmemLayout {
+  static constexpr bool kPost = MODE == EPI_POST;
   static constexpr int kStageBytes = (BM * BK + BN * BK) * 2;
-  #ifndef B2_STAGES256
-#define B2_STAGES256 3
-#endif
-  static constexpr int kStages = (BN >= 256) ? B2_STAGES256 : (BN >= 128 ? 5 : (BN >= 64 ? 7 : 8));
-  static constexpr int kStgBufs = 2;                     // output staging tiles per epilogue warp
+  // EPI_POST trades operand stages for the 64 KB shortcut ring (its GEMMs are short-K and memory bound)
+  static constexpr int kStages = kPost ? (BN >= 256 ? 3 : (BN >= 128 ? 4 : 5))
+                                       : (BN >= 256 ? 3 : (BN >= 128 ? 5 : (BN >= 64 ? 7 : 8)));
+  static constexpr int kStgBufs = 2;                     // output staging tiles per epilogue warp (not EPI_POST)
   static constexpr int kTileBytes = kStageBytes * kStages;
   static constexpr int kBarOffset = kTileBytes;
-  static constexpr int kNumBars = 3 * kStages + 4 + kEpiWarps;
+  static constexpr int kNumBars = 3 * kStages + 4 + kEpiWarps * kResSlots;
   // [4 quarters][2][BN] column statistics at flush time; the SAME bytes hold the per-column
   // {o_scale, o_shift, r_scale, r_shift}[BN] of an output pass (statistics and output BN never mix)
   static constexpr int kStatOffset = (kBarOffset + kNumBars * 8 + 16 + 15) / 16 * 16;
   static constexpr int kScratchOffset = kStatOffset + 4 * 2 * BN * 4;
-  static constexpr int kScratchOffset1k = (kScratchOffset + 1023) / 1024 * 1024;        // staging tiles 1024-aligned
-  static constexpr int kResOffset = kScratchOffset1k + kEpiWarps * kStgBufs * kStgBytes;   // shortcut tiles (TMA loads)
-  static constexpr int kTotal = kResOffset + kEpiWarps * kStgBytes + 1024;   // +1024 alignment slack
+  static constexpr int kScratchOffset1k = (kScratchOffset + 1023) / 1024 * 1024;        // tiles 1024-aligned
+  // non-POST: kEpiWarps x kStgBufs staging tiles; POST: kEpiWarps x kResSlots shortcut-in / output-out tiles
+  static constexpr int kScratchBytes = kEpiWarps * (kPost ? kResSlots : kStgBufs) * kStgBytes;
+  static constexpr int kTotal = kScratchOffset1k + kScratchBytes + 1024;   // +1024 alignment slack
+  static_assert(kTotal <= 227 * 1024, "shared memory budget");
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
@@ -137,7 +141,7 @@ __global__ void __launch_bounds__(TF ? kThreadsTf : kThreadsNoTf, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_r, int M, int N,
                int K, ConvGeom g, ATransform at, EpiParams ep) {
-  using L = SmemLayout<BN>;
+  using L = SmemLayout<BN, MODE>;
   constexpr int kStages = L::kStages;
   constexpr uint32_t kTmemCols = 2 * BN;  // two accumulators (32 <= cols <= 512, power of two)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -149,15 +153,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint64_t* tf_bar = empty_bar + kStages;
   uint64_t* tfull_bar = tf_bar + kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* res_bar = tempty_bar + 2;            // one per epilogue warp
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + kEpiWarps);
+  uint64_t* res_bar = tempty_bar + 2;            // kResSlots per epilogue warp (EPI_POST)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + kEpiWarps * kResSlots);
   // Column statistics (sum, sum of squares of the stored values) live in REGISTERS of the epilogue
   // warps (each warp owns fixed 32-column chunks of the n-block) over all consecutive tiles of one
   // n-block; they are combined through this buffer ([4 quarters][2][BN], one writer per slot) and
   // flushed to global memory only when the n-block changes (tiles are ordered m-fastest).
   float* stat_s = reinterpret_cast<float*>(smem + L::kStatOffset);
-  uint8_t* staging_s = smem + L::kScratchOffset1k;
-  uint8_t* res_s = smem + L::kResOffset;
+  uint8_t* staging_s = smem + L::kScratchOffset1k;      // EPI_POST: the shortcut / output ring lives here
   constexpr int kThreads = TF ? kThreadsTf : kThreadsNoTf;
   constexpr bool kGeneric = MODE == EPI_GENERIC;
   constexpr bool kPost = MODE == EPI_POST;
@@ -184,7 +187,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], kEpiWarps);
     }
-    for (int i = 0; i < kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
+    for (int i = 0; i < kEpiWarps * kResSlots; ++i) mbar_init(&res_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -283,27 +286,153 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int quarter = warp & 3;          // TMEM lane quarter this warp may read (hardware rule: warp % 4)
     const int half = (warp - 2) >> 2;      // the two warps of a quarter take alternate 32-column chunks
     const int epi_tid = threadIdx.x - kEpiThread0;
-    uint8_t* stg_base = staging_s + (warp - 2) * L::kStgBufs * kStgBytes;
-    uint8_t* res_stg = res_s + (warp - 2) * kStgBytes;
-    uint64_t* my_res_bar = &res_bar[warp - 2];
-    uint32_t res_phase = 0;
-    // options an instantiation does not have fold to constants (the code behind them disappears)
-    const bool has_res = kPost && ep.res != nullptr;
-    const bool has_obn = kPost && ep.o_scale != nullptr;
-    const bool has_rbn = kPost && ep.r_scale != nullptr;
-    constexpr bool post = kPost;
-    const bool out_bf16 = kGeneric ? ep.out_bf16 != 0 : true;
-    const bool relu = (kGeneric || kPost) ? ep.relu != 0 : false;
-    const bool tma_store = kGeneric ? ep.tma_store != 0 : kStore;
-    const bool stats_bf16 = want_stats && out_bf16;
-    float* ss_s = stat_s;                  // [4][BN]: o_scale, o_shift, r_scale, r_shift of the current n-block
-    int stg_buf = 0;
+    const int sw = (lane >> 1) & 3;        // SWIZZLE_64B phase of this lane's row in a 32x32 bf16 tile
     int it = 0;
     int cur_nblk = -1;
+    if constexpr (kPost) {
+      // ---- BatchNorm of the output + shortcut (+ its BatchNorm) + ReLU on the fp32 accumulators.
+      // Each warp owns a ring of kResSlots 32x32 bf16 tiles: the shortcut tile of chunk-iteration i arrives
+      // by TMA kResSlots-1 iterations ahead (48 KB of shortcut loads in flight per SM: with one tile of
+      // look-ahead the kernel was latency-bound at ~1.2 TB/s), is combined IN PLACE with the accumulators
+      // and leaves by a TMA bulk store from the same tile.
+      constexpr int R = kResSlots;
+      uint8_t* ring = staging_s + (warp - 2) * R * kStgBytes;
+      uint64_t* rbar = res_bar + (warp - 2) * R;
+      const bool has_res = ep.res != nullptr;
+      const bool has_obn = ep.o_scale != nullptr;
+      const bool has_rbn = ep.r_scale != nullptr;
+      const bool relu = ep.relu != 0;
+      float* ss_s = stat_s;                // [4][BN]: o_scale, o_shift, r_scale, r_shift of the current n-block
+      const int my_tiles = ((int)blockIdx.x < num_tiles) ? (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+      const int total_iters = my_tiles * kMyChunks;
+      auto issue_res = [&](int i) {        // chunk-iteration i -> (tile, chunk) -> slot i % R
+        const int tile = blockIdx.x + (i / kMyChunks) * gridDim.x;
+        const int j = i - (i / kMyChunks) * kMyChunks;
+        const int n_blk = tile / m_blocks;
+        const int m_blk = tile - n_blk * m_blocks;
+        uint64_t* bar = &rbar[i & (R - 1)];
+        mbar_expect_tx(bar, kStgBytes);
+        tma_load_2d(ring + (i & (R - 1)) * kStgBytes, &tmap_r, bar, n_blk * BN + (half + 2 * j) * 32,
+                    m_blk * BM + quarter * 32);
+      };
+      if (has_res && lane == 0)
+        for (int i = 0; i < R - 1 && i < total_iters; ++i) issue_res(i);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int n_blk = tile / m_blocks;
+        const int m_blk = tile - n_blk * m_blocks;
+        if (n_blk != cur_nblk) {
+          // ---- per-column BatchNorm coefficients of the new n-block -> shared memory
+          asm volatile("bar.sync 1, 256;" ::: "memory");       // everyone is done with the previous block's values
+          for (int c = epi_tid; c < BN; c += 32 * kEpiWarps) {
+            const int col = n_blk * BN + c;
+            const bool ok = col < N;
+            ss_s[c] = (has_obn && ok) ? __ldg(ep.o_scale + col) : 1.f;
+            ss_s[BN + c] = (has_obn && ok) ? __ldg(ep.o_shift + col) : 0.f;
+            ss_s[2 * BN + c] = (has_rbn && ok) ? __ldg(ep.r_scale + col) : 1.f;
+            ss_s[3 * BN + c] = (has_rbn && ok) ? __ldg(ep.r_shift + col) : 0.f;
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          cur_nblk = n_blk;
+        }
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int j = 0; j < kMyChunks; ++j) {
+          const int ch = half + 2 * j;
+          const int col0 = n_blk * BN + ch * 32;
+          const int i = it * kMyChunks + j;
+          uint8_t* slot = ring + (i & (R - 1)) * kStgBytes;
+          if (col0 < N) {   // warp-uniform (always true with a shortcut: the host requires N % BN == 0)
+            uint32_t raw[32];
+            tc_ld32(tmem_base + (uint32_t)(acc * BN + ch * 32) + ((uint32_t)(quarter * 32) << 16), raw);
+            uint4 rres[4];
+            if (has_res) {   // own row (64 B) of the swizzled shortcut tile
+              mbar_wait(&rbar[i & (R - 1)], (uint32_t)(i / R) & 1u);
+#pragma unroll
+              for (int c = 0; c < 4; ++c) rres[c] = *reinterpret_cast<const uint4*>(slot + lane * 64 + ((c ^ sw) << 4));
+            } else {         // the slot's previous bulk store (R iterations ago) must have been read out
+              if (lane == 0) bulk_wait_read<R - 1>();
+              __syncwarp();
+            }
+            tc_wait_ld();
+            float v[32];
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) v[jj] = __uint_as_float(raw[jj]);
+            const float* sc_p = ss_s + ch * 32;
+            if (has_obn) {
+#pragma unroll
+              for (int jj = 0; jj < 32; jj += 4) {
+                const float4 sc = *reinterpret_cast<const float4*>(sc_p + jj);
+                const float4 sh = *reinterpret_cast<const float4*>(sc_p + BN + jj);
+                v[jj] = fmaf(v[jj], sc.x, sh.x);
+                v[jj + 1] = fmaf(v[jj + 1], sc.y, sh.y);
+                v[jj + 2] = fmaf(v[jj + 2], sc.z, sh.z);
+                v[jj + 3] = fmaf(v[jj + 3], sc.w, sh.w);
+              }
+            }
+            if (has_res) {
+              const uint32_t* rw = reinterpret_cast<const uint32_t*>(rres);
+              if (has_rbn) {
+#pragma unroll
+                for (int jj = 0; jj < 32; jj += 4) {
+                  const float4 sc = *reinterpret_cast<const float4*>(sc_p + 2 * BN + jj);
+                  const float4 sh = *reinterpret_cast<const float4*>(sc_p + 3 * BN + jj);
+                  const uint32_t w0 = rw[jj >> 1], w1 = rw[(jj >> 1) + 1];
+                  v[jj] += fmaf(__uint_as_float(w0 << 16), sc.x, sh.x);
+                  v[jj + 1] += fmaf(__uint_as_float(w0 & 0xffff0000u), sc.y, sh.y);
+                  v[jj + 2] += fmaf(__uint_as_float(w1 << 16), sc.z, sh.z);
+                  v[jj + 3] += fmaf(__uint_as_float(w1 & 0xffff0000u), sc.w, sh.w);
+                }
+              } else {
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj) {
+                  v[2 * jj] += __uint_as_float(rw[jj] << 16);
+                  v[2 * jj + 1] += __uint_as_float(rw[jj] & 0xffff0000u);
+                }
+              }
+            }
+            uint32_t pk[16];
+            if (relu) {
+#pragma unroll
+              for (int jj = 0; jj < 16; ++jj) pk[jj] = pack_bf16x2_relu(v[2 * jj], v[2 * jj + 1]);
+            } else {
+#pragma unroll
+              for (int jj = 0; jj < 16; ++jj) pk[jj] = pack_bf16x2(v[2 * jj], v[2 * jj + 1]);
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              *reinterpret_cast<uint4*>(slot + lane * 64 + ((c ^ sw) << 4)) =
+                  make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmap_d, slot, col0, m_blk * BM + quarter * 32);
+              bulk_commit();
+              if (has_res && i + R - 1 < total_iters) {
+                bulk_wait_read<1>();       // the store of iteration i-1 has left its slot: refill it
+                issue_res(i + R - 1);
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      }
+      if (lane == 0) bulk_wait_all();
+    } else {
+    uint8_t* stg_base = staging_s + (warp - 2) * L::kStgBufs * kStgBytes;
+    // options an instantiation does not have fold to constants (the code behind them disappears)
+    const bool out_bf16 = kGeneric ? ep.out_bf16 != 0 : true;
+    const bool relu = kGeneric ? ep.relu != 0 : false;
+    const bool tma_store = kGeneric ? ep.tma_store != 0 : kStore;
+    const bool stats_bf16 = want_stats && out_bf16;
+    int stg_buf = 0;
     // statistics: lane (w = lane & 15, hf = lane >> 4) sums columns 2w, 2w+1 over rows 16 hf .. 16 hf + 15;
     // the per-warp partial sums accumulate in stat_s (one writer per slot) until the n-block changes
     const int sw_w = lane & 15, sw_hf = lane >> 4;
-    const int sw = (lane >> 1) & 3;        // SWIZZLE_64B phase of this lane's staging row
     // staging reads: row r = i (hf = 0) or 16 + (i ^ 1) (hf = 1) so the two half-warps never share a
     // bank; word address = r*64 + (((w >> 2) ^ ((r >> 1) & 3)) << 4) + (w & 3) * 4
     uint32_t rd_off[2][4];
@@ -313,15 +442,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       rd_off[0][k] = col + (uint32_t)(sw_hf * 64);    // even i: row i + hf
       rd_off[1][k] = col - (uint32_t)(sw_hf * 64);    // odd i:  row i - hf
     }
-    const bool my_chunk0_valid = half < kChunks;
-    // shortcut tiles arrive by TMA one chunk ahead: (tile, j) -> 32x32 bf16 box at (row0, col0)
-    auto issue_res = [&](int tile, int j) {
-      const int n_blk = tile / m_blocks;
-      const int m_blk = tile - n_blk * m_blocks;
-      mbar_expect_tx(my_res_bar, kStgBytes);
-      tma_load_2d(res_stg, &tmap_r, my_res_bar, n_blk * BN + (half + 2 * j) * 32, m_blk * BM + quarter * 32);
-    };
-    if (has_res && my_chunk0_valid && lane == 0 && (int)blockIdx.x < num_tiles) issue_res(blockIdx.x, 0);
 
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int n_blk = tile / m_blocks;
@@ -341,19 +461,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
           asm volatile("bar.sync 1, 256;" ::: "memory");
         }
-        if (kPost) {
-          // ---- per-column BatchNorm coefficients of the new n-block -> shared memory
-          asm volatile("bar.sync 1, 256;" ::: "memory");       // everyone is done with the previous block's values
-          for (int c = epi_tid; c < BN; c += 32 * kEpiWarps) {
-            const int col = n_blk * BN + c;
-            const bool ok = col < N;
-            ss_s[c] = (has_obn && ok) ? __ldg(ep.o_scale + col) : 1.f;
-            ss_s[BN + c] = (has_obn && ok) ? __ldg(ep.o_shift + col) : 0.f;
-            ss_s[2 * BN + c] = (has_rbn && ok) ? __ldg(ep.r_scale + col) : 1.f;
-            ss_s[3 * BN + c] = (has_rbn && ok) ? __ldg(ep.r_shift + col) : 0.f;
-          }
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-        }
         cur_nblk = n_blk;
       }
       const int acc = it & 1;
@@ -370,18 +477,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const bool full_chunk = (col0 + 32 <= N);
           uint32_t raw[32];
           tc_ld32(tmem_base + (uint32_t)(acc * BN + ch * 32) + ((uint32_t)(quarter * 32) << 16), raw);
-          uint4 rres[4];
-          if (has_res) {   // this chunk's shortcut tile: own row (64 B) out of the swizzled TMA tile
-            mbar_wait(my_res_bar, res_phase);
-            res_phase ^= 1;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) rres[c] = *reinterpret_cast<const uint4*>(res_stg + lane * 64 + ((c ^ sw) << 4));
-            __syncwarp();
-            if (lane == 0) {                                   // prefetch the next chunk this warp will handle
-              if (j + 1 < kMyChunks && half + 2 * (j + 1) < kChunks) issue_res(tile, j + 1);
-              else if (tile + (int)gridDim.x < num_tiles) issue_res(tile + gridDim.x, 0);
-            }
-          }
           tc_wait_ld();
           float v[32];
 #pragma unroll
@@ -403,10 +498,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (int jj = 0; jj < 32; ++jj)
               if (col0 + jj < N) v[jj] += __ldg(ep.bias2 + col0 + jj);
           }
-          // raw-output statistics are taken on the bf16-rounded conv result BEFORE any output BN
+          // statistics are taken on the bf16-rounded value as stored
           uint32_t pk[16];
-          if (out_bf16 && (stats_bf16 || !post)) {
-            if (relu && !post) {
+          if (out_bf16) {
+            if (relu) {
 #pragma unroll
               for (int jj = 0; jj < 16; ++jj) pk[jj] = pack_bf16x2_relu(v[2 * jj], v[2 * jj + 1]);
             } else {
@@ -450,60 +545,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
           }
           if (kStore) {
-            if (post) {
-              // BatchNorm of this conv's output + shortcut (+ its BatchNorm) + ReLU on the fp32 accumulators;
-              // the coefficients are broadcast reads of the n-block table in shared memory
-              const float* sc_p = ss_s + ch * 32;
-              if (has_obn) {
-#pragma unroll
-                for (int jj = 0; jj < 32; jj += 4) {
-                  const float4 sc = *reinterpret_cast<const float4*>(sc_p + jj);
-                  const float4 sh = *reinterpret_cast<const float4*>(sc_p + BN + jj);
-                  v[jj] = fmaf(v[jj], sc.x, sh.x);
-                  v[jj + 1] = fmaf(v[jj + 1], sc.y, sh.y);
-                  v[jj + 2] = fmaf(v[jj + 2], sc.z, sh.z);
-                  v[jj + 3] = fmaf(v[jj + 3], sc.w, sh.w);
-                }
-              }
-              if (has_res) {
-                const uint32_t* rw = reinterpret_cast<const uint32_t*>(rres);
-                if (has_rbn) {
-#pragma unroll
-                  for (int jj = 0; jj < 32; jj += 4) {
-                    const float4 sc = *reinterpret_cast<const float4*>(sc_p + 2 * BN + jj);
-                    const float4 sh = *reinterpret_cast<const float4*>(sc_p + 3 * BN + jj);
-                    const uint32_t w0 = rw[jj >> 1], w1 = rw[(jj >> 1) + 1];
-                    v[jj] += fmaf(__uint_as_float(w0 << 16), sc.x, sh.x);
-                    v[jj + 1] += fmaf(__uint_as_float(w0 & 0xffff0000u), sc.y, sh.y);
-                    v[jj + 2] += fmaf(__uint_as_float(w1 << 16), sc.z, sh.z);
-                    v[jj + 3] += fmaf(__uint_as_float(w1 & 0xffff0000u), sc.w, sh.w);
-                  }
-                } else {
-#pragma unroll
-                  for (int jj = 0; jj < 16; ++jj) {
-                    v[2 * jj] += __uint_as_float(rw[jj] << 16);
-                    v[2 * jj + 1] += __uint_as_float(rw[jj] & 0xffff0000u);
-                  }
-                }
-              }
-              if (out_bf16) {
-                if (relu) {
-#pragma unroll
-                  for (int jj = 0; jj < 16; ++jj) pk[jj] = pack_bf16x2_relu(v[2 * jj], v[2 * jj + 1]);
-                } else {
-#pragma unroll
-                  for (int jj = 0; jj < 16; ++jj) pk[jj] = pack_bf16x2(v[2 * jj], v[2 * jj + 1]);
-                }
-              }
-            }
             if (out_bf16) {
               if (tma_store) {
                 // staging tile -> one TMA bulk store in full 64-byte row segments (no LSU, no registers)
                 if (!stats_bf16) {
                   if (lane == 0) bulk_wait_read<L::kStgBufs - 1>();
                   __syncwarp();
-                }
-                if (!stats_bf16 || post) {
 #pragma unroll
                   for (int c = 0; c < 4; ++c)
                     *reinterpret_cast<uint4*>(stg + lane * 64 + ((c ^ sw) << 4)) =
@@ -599,6 +646,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           atomicAdd(ep.col_sumsq + col, stat_s[BN + c] + stat_s[3 * BN + c] + stat_s[5 * BN + c] + stat_s[7 * BN + c]);
         }
       }
+    }
     }
   } else if (TF) {
     // =========================== A transform (warps 10..13) ===========================
@@ -779,7 +827,7 @@ int make_tmap_2d(CUtensorMap* map, const void* base, long rows, long cols, long 
 template <int BN, int MODE, bool TF>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tr, int M, int N,
                 int K, const ConvGeom& g, const ATransform& at, const EpiParams& ep, cudaStream_t stream) {
-  using L = SmemLayout<BN>;
+  using L = SmemLayout<BN, MODE>;
   static bool attr_set = false;
   if (!attr_set) {
     B2_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, MODE, TF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -923,6 +971,335 @@ int conv_common(const void* x, int Nimg, int H, int W, int C, const void* w, int
   return dispatch(bn, ta, tb, M, Cout, K, g, at, ep, stream);
 }
 
+// ------------------------------------------------------------------ Gram-matrix BatchNorm statistics
+// Train-mode BN3 of a bottleneck needs the statistics of the conv3 output y = t W^T (t = relu(bn2(conv2 raw)),
+// [M, K]; W [N, K], N = 4K) before anything can be normalised.  A statistics-only GEMM pass drains M x N
+// accumulators from TMEM (64 B/clk/SM) and is epilogue bound.  Both moments follow from K-sized reductions:
+//     sum_m y[m,n]   = < w_n , s >          s = sum_m t[m,:]
+//     sum_m y[m,n]^2 = w_n^T G w_n          G = sum_m t[m,:]^T t[m,:]   (K x K Gram matrix)
+// so this kernel streams the activation ONCE (HBM bound), rewrites each tile in shared memory exactly as the
+// conv3 A transform does, and feeds the SAME tile to the tensor core as both operands in MN-major form
+// (reduction over the 128 rows of the tile): G accumulates in TMEM over all of a CTA's tiles and is drained
+// once at the end (vector reductions into a global fp32 workspace); s comes from one extra N = 16 MMA against
+// a ones matrix.  gram_finalize_kernel evaluates the two forms per output channel in fp64 and finalises the
+// BatchNorm.  Exact for the unrounded fp32 conv output (more accurate than summing bf16-rounded outputs).
+//
+// A "super tile" is two 16 KB SWIZZLE_128B panels of 128 rows x 64 channels, M/N = 128 for the MMA:
+//   K = 128: the two 64-channel halves of one 128-row tile;  K = 64: two consecutive 128-row tiles side by
+//   side (the Gram of [t1 | t2] holds t1^T t1 and t2^T t2 on its diagonal blocks, summed at drain time).
+constexpr int kGramStages = 5;
+constexpr int kGramCopies = 8;           // partial global accumulators: shortens the same-address atomic chains 8x
+constexpr int kGramThreads = 64 + 256;   // TMA warp, MMA warp, 8 transform warps (4 per panel; the first 4 also drain)
+constexpr int kGramStageBytes = 2 * BM * BK * 2;                    // 32 KB
+constexpr int kGramOnesOffset = kGramStages * kGramStageBytes;      // 1 KB of bf16 ones
+constexpr int kGramBarOffset = kGramOnesOffset + 1024;
+constexpr int kGramSmem = kGramBarOffset + (3 * kGramStages + 1) * 8 + 16 + 1024;
+
+// MN-major SWIZZLE_128B descriptor: 64 contiguous MN elements per 128 B row (one row per K index), 8-row
+// groups SBO = 1024 B apart, 64-element MN blocks LBO bytes apart (the panel stride).
+__device__ __forceinline__ uint64_t make_sw128_mn_desc(uint32_t smem_addr, uint32_t lbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <int KC>
+__global__ void __launch_bounds__(kGramThreads, 1)
+gram_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, int M, ATransform at, float* __restrict__ gram,
+                  float* __restrict__ sum_a) {
+  static_assert(KC == 64 || KC == 128, "gram_stats_kernel: 64 or 128 input channels");
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kGramBarOffset);
+  uint64_t* tf_bar = full_bar + kGramStages;
+  uint64_t* empty_bar = tf_bar + kGramStages;
+  uint64_t* done_bar = empty_bar + kGramStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+  constexpr uint32_t kTmemCols = 256;        // G: columns 0..127, s: columns 128..143
+  constexpr int kRowsPerSuper = KC == 64 ? 2 * BM : BM;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_super = (M + kRowsPerSuper - 1) / kRowsPerSuper;
+
+  for (int i = threadIdx.x; i < 256; i += kGramThreads)
+    reinterpret_cast<uint32_t*>(smem + kGramOnesOffset)[i] = 0x3F803F80u;   // bf16 1.0 pairs
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    for (int i = 0; i < kGramStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&tf_bar[i], 256);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tc_alloc(tmem_slot, kTmemCols);
+    tc_relinquish();
+  }
+  fence_proxy_async_smem();        // the ones matrix is read by the tensor core (async proxy)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int st = blockIdx.x; st < num_super; st += gridDim.x) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * kGramStageBytes;
+        mbar_expect_tx(&full_bar[stage], kGramStageBytes);
+        if (KC == 128) {
+          tma_load_2d(sa, &tmap_a, &full_bar[stage], 0, st * BM);
+          tma_load_2d(sa + BM * BK * 2, &tmap_a, &full_bar[stage], BK, st * BM);
+        } else {
+          tma_load_2d(sa, &tmap_a, &full_bar[stage], 0, st * 2 * BM);
+          tma_load_2d(sa + BM * BK * 2, &tmap_a, &full_bar[stage], 0, st * 2 * BM + BM);   // fully OOB rows -> zeros
+        }
+        if (++stage == kGramStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // both operands MN-major (bits 15, 16): D[128 x 128] += P^T P ; s: D[128 x 16] += P^T ones (B K-major)
+    constexpr uint32_t idesc_g = make_idesc(128, 128) | (1u << 15) | (1u << 16);
+    constexpr uint32_t idesc_s = make_idesc(128, 16) | (1u << 15);
+    const uint64_t ones_desc = make_nosw_desc(smem_u32(smem + kGramOnesOffset), 128, 256);
+    int stage = 0;
+    uint32_t phase = 0;
+    bool first = true;
+    for (int st = blockIdx.x; st < num_super; st += gridDim.x) {
+      mbar_wait(&tf_bar[stage], phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sa = smem_u32(smem + stage * kGramStageBytes);
+#pragma unroll
+        for (int ks = 0; ks < BM / UMMA_K; ++ks) {          // 16 tile rows (two 8-row groups) per MMA
+          const uint64_t d = make_sw128_mn_desc(sa + ks * 2048, BM * BK * 2);
+          tc_mma_bf16(tmem_base, d, d, idesc_g, !(first && ks == 0));
+          tc_mma_bf16(tmem_base + 128, d, ones_desc, idesc_s, !(first && ks == 0));
+        }
+        tc_commit(&empty_bar[stage]);
+      }
+      first = false;
+      __syncwarp();
+      if (++stage == kGramStages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    if (lane == 0) tc_commit(done_bar);
+    __syncwarp();
+  } else {
+    // =========================== A transform (warps 2..5), then the drain ===========================
+    const int tt = (threadIdx.x - 64) & 127;
+    const int p = (threadIdx.x - 64) >> 7;          // the panel this group of 4 warps rewrites
+    const int c = tt & 7;
+    const int rb = tt >> 3;
+    uint32_t row_off[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = rb + 16 * i;
+      row_off[i] = (uint32_t)(row * 128 + ((c ^ (row & 7)) << 4));
+    }
+    float4 sc0[1], sc1[1], sh0[1], sh1[1];          // this thread's 8 channels never change
+    {
+      const int c0 = (KC == 128 ? p * BK : 0) + c * 8;
+      sc0[0] = __ldg(reinterpret_cast<const float4*>(at.scale + c0));
+      sc1[0] = __ldg(reinterpret_cast<const float4*>(at.scale + c0 + 4));
+      sh0[0] = __ldg(reinterpret_cast<const float4*>(at.shift + c0));
+      sh1[0] = __ldg(reinterpret_cast<const float4*>(at.shift + c0 + 4));
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int st = blockIdx.x; st < num_super; st += gridDim.x) {
+      mbar_wait(&full_bar[stage], phase);
+      {
+        uint8_t* sa = smem + stage * kGramStageBytes + p * (BM * BK * 2);
+        const int row0 = (KC == 128 ? st * BM : st * 2 * BM + p * BM) + rb;
+        constexpr int cs = 0;
+        uint4 u[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) u[i] = *reinterpret_cast<const uint4*>(sa + row_off[i]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const bool ok = row0 + 16 * i < M;           // rows past the end stay zero
+          float2 a0 = make_float2(__uint_as_float(u[i].x << 16), __uint_as_float(u[i].x & 0xffff0000u));
+          float2 a1 = make_float2(__uint_as_float(u[i].y << 16), __uint_as_float(u[i].y & 0xffff0000u));
+          float2 a2 = make_float2(__uint_as_float(u[i].z << 16), __uint_as_float(u[i].z & 0xffff0000u));
+          float2 a3 = make_float2(__uint_as_float(u[i].w << 16), __uint_as_float(u[i].w & 0xffff0000u));
+          a0 = __ffma2_rn(a0, make_float2(sc0[cs].x, sc0[cs].y), make_float2(sh0[cs].x, sh0[cs].y));
+          a1 = __ffma2_rn(a1, make_float2(sc0[cs].z, sc0[cs].w), make_float2(sh0[cs].z, sh0[cs].w));
+          a2 = __ffma2_rn(a2, make_float2(sc1[cs].x, sc1[cs].y), make_float2(sh1[cs].x, sh1[cs].y));
+          a3 = __ffma2_rn(a3, make_float2(sc1[cs].z, sc1[cs].w), make_float2(sh1[cs].z, sh1[cs].w));
+          uint4 t;
+          if (at.relu) {
+            t.x = pack_bf16x2_relu(a0.x, a0.y);
+            t.y = pack_bf16x2_relu(a1.x, a1.y);
+            t.z = pack_bf16x2_relu(a2.x, a2.y);
+            t.w = pack_bf16x2_relu(a3.x, a3.y);
+          } else {
+            t.x = pack_bf16x2(a0.x, a0.y);
+            t.y = pack_bf16x2(a1.x, a1.y);
+            t.z = pack_bf16x2(a2.x, a2.y);
+            t.w = pack_bf16x2(a3.x, a3.y);
+          }
+          u[i].x = ok ? t.x : 0u;
+          u[i].y = ok ? t.y : 0u;
+          u[i].z = ok ? t.z : 0u;
+          u[i].w = ok ? t.w : 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(sa + row_off[i]) = u[i];
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&tf_bar[stage]);
+      if (++stage == kGramStages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    // ---- drain (warps 2..5): lane = feature row f of the accumulator; vector reductions into the workspace
+    if (warp < 6) {
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    const int quarter = warp & 3;
+    const int f = quarter * 32 + lane;
+    gram += (long)(blockIdx.x % kGramCopies) * (KC * KC + KC);        // this CTA's partial workspace
+    sum_a = gram + KC * KC;
+#pragma unroll 1
+    for (int ch = 0; ch < 4; ++ch) {
+      if (KC == 64 && (ch >> 1) != (quarter >> 1)) continue;      // only the two diagonal 64 x 64 blocks
+      uint32_t raw[32];
+      tc_ld32(tmem_base + (uint32_t)(ch * 32) + ((uint32_t)(quarter * 32) << 16), raw);
+      tc_wait_ld();
+      float* dst = KC == 128 ? gram + (long)f * 128 + ch * 32 : gram + (long)(f & 63) * 64 + (ch & 1) * 32;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(raw[j])),
+                     "f"(__uint_as_float(raw[j + 1])), "f"(__uint_as_float(raw[j + 2])), "f"(__uint_as_float(raw[j + 3]))
+                     : "memory");
+    }
+    {
+      uint32_t raw[32];
+      tc_ld32(tmem_base + 128u + ((uint32_t)(quarter * 32) << 16), raw);     // every column of the N = 16 block = s
+      tc_wait_ld();
+      atomicAdd(sum_a + (KC == 128 ? f : (f & 63)), __uint_as_float(raw[0]));
+    }
+    tc_fence_before();
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tc_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// Finalisation, two small kernels:
+//   gram_reduce_kernel   sums the kGramCopies partial workspaces and centres: Cov = G/M - m m^T, m = s/M
+//   gram_finalize_kernel one warp per pair of output channels: mean_n = <w_n, m>, var_n = w_n^T Cov w_n in fp32
+//                        (the centred form keeps the cancellation out of the long sums: 1e-5 relative on var
+//                        against an fp64 evaluation at the layer shapes), then the BatchNorm finalisation.
+__global__ void __launch_bounds__(256)
+gram_reduce_kernel(const float* __restrict__ ws, float* __restrict__ cov, int KC, float inv) {
+  const int copy_stride = KC * KC + KC;
+  const int i4 = blockIdx.x * blockDim.x + threadIdx.x;          // one float4 of the K x K matrix per thread
+  if (i4 >= KC * KC / 4) return;
+  const int k = (i4 * 4) / KC, l = (i4 * 4) - k * KC;
+  float4 t = make_float4(0.f, 0.f, 0.f, 0.f), ml = t;
+  float mk = 0.f;
+#pragma unroll
+  for (int c = 0; c < kGramCopies; ++c) {
+    const float* base = ws + c * copy_stride;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(base) + i4);
+    const float4 sl = __ldg(reinterpret_cast<const float4*>(base + KC * KC + l));
+    mk += __ldg(base + KC * KC + k);
+    t.x += g.x; t.y += g.y; t.z += g.z; t.w += g.w;
+    ml.x += sl.x; ml.y += sl.y; ml.z += sl.z; ml.w += sl.w;
+  }
+  mk *= inv;
+  t.x = fmaf(t.x, inv, -mk * (ml.x * inv));
+  t.y = fmaf(t.y, inv, -mk * (ml.y * inv));
+  t.z = fmaf(t.z, inv, -mk * (ml.z * inv));
+  t.w = fmaf(t.w, inv, -mk * (ml.w * inv));
+  reinterpret_cast<float4*>(cov)[i4] = t;
+  if (l == 0) cov[KC * KC + k] = mk;                              // the mean vector follows the matrix
+}
+
+constexpr int kGramFinWarps = 8;
+constexpr int kGramFinPerWarp = 2;       // output channels per warp
+__global__ void __launch_bounds__(32 * kGramFinWarps)
+gram_finalize_kernel(const float* __restrict__ cov, const bf16* __restrict__ W, int N, int KC, float* __restrict__ col_sum,
+                     float* __restrict__ col_sumsq, BnFinal f, float count) {
+  extern __shared__ float gsm[];             // Cov [KC*KC] + mean [KC], weight rows [warps][2][KC]
+  float* cov_s = gsm;
+  float* m_s = gsm + KC * KC;
+  float* w_s = m_s + KC;
+  for (int i4 = threadIdx.x; i4 < (KC * KC + KC) / 4; i4 += blockDim.x)
+    reinterpret_cast<float4*>(cov_s)[i4] = __ldg(reinterpret_cast<const float4*>(cov) + i4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = (blockIdx.x * kGramFinWarps + warp) * kGramFinPerWarp;
+  float* w0 = w_s + (warp * kGramFinPerWarp) * KC;
+  float* w1 = w0 + KC;
+  for (int l = lane; l < KC; l += 32) {
+    w0[l] = (n0 < N) ? __bfloat162float(W[(long)n0 * KC + l]) : 0.f;
+    w1[l] = (n0 + 1 < N) ? __bfloat162float(W[(long)(n0 + 1) * KC + l]) : 0.f;
+  }
+  __syncthreads();
+  if (n0 >= N) return;
+  const int per = KC / 32;                   // 2 or 4 columns of Cov per lane
+  float u0[4] = {0.f, 0.f, 0.f, 0.f}, u1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+  for (int k = 0; k < KC; ++k) {
+    const float a0 = w0[k], a1 = w1[k];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (j < per) {
+        const float cv = cov_s[k * KC + lane + 32 * j];
+        u0[j] = fmaf(a0, cv, u0[j]);
+        u1[j] = fmaf(a1, cv, u1[j]);
+      }
+    }
+  }
+  float q0 = 0.f, q1 = 0.f, m0 = 0.f, m1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (j < per) {
+      const int l = lane + 32 * j;
+      q0 = fmaf(w0[l], u0[j], q0);
+      q1 = fmaf(w1[l], u1[j], q1);
+      m0 = fmaf(w0[l], m_s[l], m0);
+      m1 = fmaf(w1[l], m_s[l], m1);
+    }
+  }
+  q0 = warp_sum(q0); q1 = warp_sum(q1); m0 = warp_sum(m0); m1 = warp_sum(m1);
+  if (lane < kGramFinPerWarp && n0 + lane < N) {
+    const int n = n0 + lane;
+    const float mean = lane == 0 ? m0 : m1;
+    const float var = fmaxf(lane == 0 ? q0 : q1, 0.f);
+    if (col_sum != nullptr) {
+      col_sum[n] = mean * count;
+      col_sumsq[n] = (var + mean * mean) * count;
+    }
+    if (f.running_mean != nullptr) {
+      f.running_mean[n] = (1.f - f.momentum) * f.running_mean[n] + f.momentum * mean;
+      f.running_var[n] = (1.f - f.momentum) * f.running_var[n] + f.momentum * var * f.unbias;
+    }
+    const float sc = f.gamma[n] * rsqrtf(var + f.eps);
+    f.scale[n] = sc;
+    f.shift[n] = f.beta[n] - mean * sc;
+  }
+}
+
 __global__ void bn_finalize_kernel(const float* sum, const float* sumsq, const float* gamma, const float* beta,
                                    float* running_mean, float* running_var, float inv_count, float unbias, float eps,
                                    float momentum, int train, float* scale, float* shift, int C) {
@@ -1038,5 +1415,66 @@ B2_API int b2_bn_finalize_nhwc(const float* sum, const float* sumsq, const float
                                                                          running_var, inv, unbias, eps, momentum,
                                                                          train, scale, shift, C);
   B2_LAUNCH_CHECK("bn_finalize_kernel");
+  return 0;
+}
+
+// BatchNorm statistics + finalisation of a 1x1 convolution's output WITHOUT computing the output (Gram-matrix
+// form, see gram_stats_kernel) ; include/b200lrcn.h
+B2_API long b2_gram_workspace_floats(int C) { return (long)(kGramCopies + 1) * ((long)C * C + C); }
+
+B2_API int b2_conv1x1_gram_bnstats_bf16(const void* x, long M, int C, const void* w, int Cout, const float* a_scale,
+                                        const float* a_shift, int a_relu, float* workspace, float* col_sum,
+                                        float* col_sumsq, const float* fin_gamma, const float* fin_beta,
+                                        float* fin_running_mean, float* fin_running_var, float* fin_scale,
+                                        float* fin_shift, float eps, float momentum, void* stream) {
+  const char* who = "b2_conv1x1_gram_bnstats_bf16";
+  B2_ARG_CHECK(x && w && a_scale && a_shift && workspace && fin_gamma && fin_beta && fin_scale && fin_shift,
+               "%s: null pointer", who);
+  B2_ARG_CHECK(M > 0 && M < (1L << 31) && Cout > 0, "%s: empty or oversized shape", who);
+  B2_ARG_CHECK(C == 64 || C == 128, "%s: 64 or 128 input channels (got %d)", who, C);
+  B2_ARG_CHECK((col_sum == nullptr) == (col_sumsq == nullptr), "%s: col_sum and col_sumsq go together", who);
+  B2_ARG_CHECK(((uintptr_t)x & 15) == 0 && ((uintptr_t)workspace & 15) == 0, "%s: x / workspace must be 16 B aligned", who);
+  if (int r = load_driver_entry_points()) return r;
+  cudaStream_t st = (cudaStream_t)stream;
+  CUtensorMap ta;
+  if (int r = make_tmap_2d(&ta, x, M, C, C, BM)) return r;
+  float* gram = workspace;
+  float* sum_a = workspace + (long)C * C;
+  B2_CUDA_CHECK(cudaMemsetAsync(workspace, 0, (size_t)kGramCopies * ((size_t)C * C + C) * sizeof(float), st));
+  ATransform at = {a_scale, a_shift, a_relu};
+  const int rows_per_super = C == 64 ? 2 * BM : BM;
+  const int num_super = b2_ceil_div(M, rows_per_super);
+  const int grid = num_super < b2_num_sms() ? num_super : b2_num_sms();
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2_CUDA_CHECK(cudaFuncSetAttribute(gram_stats_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGramSmem));
+    B2_CUDA_CHECK(cudaFuncSetAttribute(gram_stats_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGramSmem));
+    B2_CUDA_CHECK(cudaFuncSetAttribute(gram_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (128 * 128 + 128 + kGramFinWarps * kGramFinPerWarp * 128) * 4));
+    attr_set = true;
+  }
+  if (C == 64)
+    gram_stats_kernel<64><<<grid, kGramThreads, kGramSmem, st>>>(ta, (int)M, at, gram, sum_a);
+  else
+    gram_stats_kernel<128><<<grid, kGramThreads, kGramSmem, st>>>(ta, (int)M, at, gram, sum_a);
+  B2_LAUNCH_CHECK("gram_stats_kernel");
+  BnFinal f = {};
+  f.scale = fin_scale;
+  f.shift = fin_shift;
+  f.gamma = fin_gamma;
+  f.beta = fin_beta;
+  f.running_mean = fin_running_mean;
+  f.running_var = fin_running_var;
+  f.inv_count = (float)(1.0 / (double)M);
+  f.unbias = M > 1 ? (float)((double)M / ((double)M - 1.0)) : 1.f;
+  f.eps = eps;
+  f.momentum = momentum;
+  float* cov = workspace + (long)kGramCopies * ((long)C * C + C);      // centred covariance + mean vector
+  gram_reduce_kernel<<<b2_ceil_div(C * C / 4, 256), 256, 0, st>>>(workspace, cov, C, f.inv_count);
+  B2_LAUNCH_CHECK("gram_reduce_kernel");
+  gram_finalize_kernel<<<b2_ceil_div(Cout, kGramFinWarps * kGramFinPerWarp), 32 * kGramFinWarps,
+                         (size_t)(C * C + C + kGramFinWarps * kGramFinPerWarp * C) * sizeof(float), st>>>(
+      cov, (const bf16*)w, Cout, C, col_sum, col_sumsq, f, (float)M);
+  B2_LAUNCH_CHECK("gram_finalize_kernel");
   return 0;
 }

@@ -86,6 +86,26 @@ def conv2d_bn_nhwc(x, w, stride, pad, a=None, a_relu=True, o=None, res=None, r=N
     return y
 
 
+def conv1x1_gram_bnstats(x, w, a, fin, stats=None, a_relu=True):
+    """b2_conv1x1_gram_bnstats_bf16: train-mode BatchNorm statistics + finalisation of the 1x1 convolution
+    relu?(x*a_scale+a_shift) @ w^T without computing its output (Gram-matrix form, one pass over x).
+    x [..., C] bf16 (C = 64 or 128), w [Cout, (1, 1,) C] bf16; a = (scale, shift); fin as in conv2d_bn_nhwc;
+    stats = optional (sum, sumsq) outputs (overwritten)."""
+    _chk(x, w)
+    C = x.shape[-1]
+    Cout = w.shape[0]
+    M = x.numel() // C
+    ws = torch.empty(_lib.lib().b2_gram_workspace_floats(C), device=x.device, dtype=F32)
+    s1, s2 = stats if stats is not None else (None, None)
+    g, b, rm, rv, fs, fh, _cnt, eps, mom = fin
+    call("b2_conv1x1_gram_bnstats_bf16", x.data_ptr(), M, C, w.data_ptr(), Cout, a[0].data_ptr(), a[1].data_ptr(),
+         int(a_relu), ws.data_ptr(), ptr(s1), ptr(s2), g.data_ptr(), b.data_ptr(), ptr(rm), ptr(rv), fs.data_ptr(),
+         fh.data_ptr(), float(eps), float(mom), stream_ptr())
+
+
+GRAM_CHANNELS = (64, 128)
+
+
 def scale_shift_apply(x, scale, shift, res=None, r=None, relu=True, out=None):
     """y = act(x*scale[c] + shift[c] [+ res | + res*rscale[c] + rshift[c]]) over NHWC bf16 (in place by default)."""
     _chk(x)
