@@ -188,6 +188,16 @@ int b2_bn2d_act_pool_bwd_apply_f32(const float* x, const float* dy, const float*
                                    int W, int pool, void* stream);
 int b2_f64_to_f32(const double* src, float* dst, int n, int accumulate, void* stream);
 
+/* ---- selective scan forward (VideoMamba temporal mixer; lrcn/videomamba.py:242-284 parallel_scan,
+ * medsos_lrcn/src/models.py:47-71) -------------------------------------------------------------------
+ * x_t = exp(delta_t A) x_{t-1} + delta_t B_t u_t ; y_t = <x_t, C_t>.  u, delta, y [batch, L, D] fp32;
+ * A [D, N]; B, C [batch, L, N]; N in {4, 8, 16, 32}.
+ * chunk_reset > 0: the state restarts from zero every chunk_reset steps (videomamba.py resets per 256-step
+ * chunk); <= 0: one scan over L.  reverse = 1: u and delta are read time-reversed, B and C are not, y is written
+ * time-reversed (the medsos "backward" direction). */
+int b2_selective_scan_fwd(const float* u, const float* delta, const float* A, const float* B, const float* C, float* y,
+                          int batch, int L, int D, int N, int chunk_reset, int reverse, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

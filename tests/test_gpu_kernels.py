@@ -313,6 +313,32 @@ def test_dropout_rate_scale_and_backward_mask(ops):
     assert not torch.equal(y1, y2)
 
 
+def test_selective_scan_vs_reference_golden(ops):
+    """Fused scan vs the outputs of the reference's own parallel_scan implementations (tests/golden/scan.npz):
+    videomamba.py (state reset every 256 steps), medsos forward and 'backward' (u/delta flipped, B/C not)."""
+    g = np.load(os.path.join(GOLDEN, "scan.npz"))
+    args = [torch.from_numpy(g[k]).to(DEV) for k in ("u", "delta", "A", "B", "C")]
+    assert err(ops.selective_scan(*args, chunk_reset=256), torch.from_numpy(g["y_videomamba"])) < 1e-4
+    assert err(ops.selective_scan(*args, chunk_reset=None), torch.from_numpy(g["y_medsos_fwd"])) < 1e-4
+    assert err(ops.selective_scan(*args, chunk_reset=None, reverse=True), torch.from_numpy(g["y_medsos_bwd"])) < 1e-4
+
+
+@pytest.mark.parametrize("B,L,D,N,chunk,reverse", [(2, 700, 256, 16, 256, False), (3, 37, 100, 8, None, True),
+                                                   (1, 1, 130, 16, 256, False), (2, 513, 2048, 16, 256, False),
+                                                   (2, 16, 2048, 16, None, True), (1, 300, 64, 32, 100, False)])
+def test_selective_scan_vs_oracle(ops, B, L, D, N, chunk, reverse):
+    """Ragged channel counts, single-step sequences, several chunks, the BASELINE config-5 widths (D=2048, N=16)."""
+    gen = torch.Generator().manual_seed(B * L + D)
+    u = torch.randn(B, L, D, generator=gen)
+    delta = F.softplus(torch.randn(B, L, D, generator=gen))
+    A = -torch.exp(torch.randn(D, N, generator=gen))
+    Bm, Cm = torch.randn(B, L, N, generator=gen), torch.randn(B, L, N, generator=gen)
+    ref = O.selective_scan(u, delta, A, Bm, Cm, chunk_reset=chunk, reverse=reverse)
+    got = ops.selective_scan(u.to(DEV), delta.to(DEV), A.to(DEV), Bm.to(DEV), Cm.to(DEV), chunk_reset=chunk, reverse=reverse)
+    assert got.shape == ref.shape
+    assert err(got, ref) < 1e-4
+
+
 def test_errors_are_loud(ops):
     import video_classif_b200 as vc
     with pytest.raises(vc.B200LrcnError):

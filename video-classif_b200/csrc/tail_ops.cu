@@ -293,7 +293,9 @@ B2_API int b2_sgemm(int trans_a, int trans_b, int M, int N, int K, float alpha, 
   cudaStream_t st = (cudaStream_t)stream;
   const int tiles = b2_ceil_div(N, TS) * b2_ceil_div(M, TS);
   int splits = 1;
-  if (beta == 0.f && tiles * 2 <= b2_num_sms() && K >= 8 * TK) {   // skinny output, long reduction: split K
+  // skinny output, long reduction: split K.  Only the A^T B form (weight gradients) -- atomics make the sum order
+  // vary from run to run, and forward passes must stay bit-reproducible (torch.save / torch.load round trips)
+  if (trans_a && beta == 0.f && tiles * 2 <= b2_num_sms() && K >= 8 * TK) {
     splits = b2_num_sms() / tiles;
     const int max_splits = K / (4 * TK);
     if (splits > max_splits) splits = max_splits;

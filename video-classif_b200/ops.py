@@ -204,6 +204,20 @@ def ingest_u8(frames_u8, out_h, out_w, frame_index=None, out_dtype=F32, swap_rb=
     return out
 
 
+def selective_scan(u, delta, A, Bm, Cm, chunk_reset=256, reverse=False):
+    """b2_selective_scan_fwd: y[B,L,D] of the VideoMamba scan (videomamba.py:242-284; chunk_reset=None +
+    reverse for medsos models.py:47-71).  Forward only (BASELINE config 5)."""
+    _chk(u, delta, A, Bm, Cm)
+    u, delta, A, Bm, Cm = (t.contiguous().float() for t in (u, delta, A, Bm, Cm))
+    Bsz, L, D = u.shape
+    N = A.shape[1]
+    assert delta.shape == u.shape and A.shape[0] == D and Bm.shape == (Bsz, L, N) and Cm.shape == (Bsz, L, N)
+    y = torch.empty_like(u)
+    call("b2_selective_scan_fwd", u.data_ptr(), delta.data_ptr(), A.data_ptr(), Bm.data_ptr(), Cm.data_ptr(), y.data_ptr(),
+         Bsz, L, D, N, int(chunk_reset or 0), int(reverse), stream_ptr())
+    return y
+
+
 # ----------------------------------------------------------------------------------------
 # autograd: Linear
 # ----------------------------------------------------------------------------------------
