@@ -188,6 +188,21 @@ int b2_bn2d_act_pool_bwd_apply_f32(const float* x, const float* dy, const float*
                                    int W, int pool, void* stream);
 int b2_f64_to_f32(const double* src, float* dst, int n, int accumulate, void* stream);
 
+/* ---- whole-stack persistent LSTM (unidirectional nn.LSTM, H <= 64, input width <= 64, T <= 64, <= 8 layers):
+ * every layer and timestep in one launch; medsos_lrcn/src/models.py:156-158,205 as tuned by all_config.py:14-17.
+ * w_ih / w_hh / b_ih / b_hh (and dw_ih / dw_hh / db) are HOST arrays of `layers` device pointers in nn.LSTM layout
+ * (weight_ih_l{k} [4H, in_k], weight_hh_l{k} [4H, H], gate order i,f,g,o).  out [layers, B, T, H] holds every
+ * layer's output sequence (the module output is out[layers-1]); gates [layers, B, T, 4H] / cstate [layers, B, T, H]
+ * are saved for BPTT (NULL for inference).  Backward: dout [B, T, H] = gradient of the top layer's output sequence;
+ * dw_ih / dw_hh / db are ACCUMULATED into (caller zeroes); db[k] is the gradient of b_ih_l{k} and of b_hh_l{k};
+ * dx [B, T, In0] may be NULL. */
+int b2_lstm_stack_fwd(const float* x, int In0, const void* const* w_ih, const void* const* w_hh, const void* const* b_ih,
+                      const void* const* b_hh, int layers, float* out, float* gates, float* cstate, int B, int T, int H,
+                      void* stream);
+int b2_lstm_stack_bwd(const float* dout, const float* x, int In0, const void* const* w_ih, const void* const* w_hh,
+                      int layers, const float* out, const float* gates, const float* cstate, float* dx,
+                      void* const* dw_ih, void* const* dw_hh, void* const* db, int B, int T, int H, void* stream);
+
 /* ---- selective scan forward (VideoMamba temporal mixer; lrcn/videomamba.py:242-284 parallel_scan,
  * medsos_lrcn/src/models.py:47-71) -------------------------------------------------------------------
  * x_t = exp(delta_t A) x_{t-1} + delta_t B_t u_t ; y_t = <x_t, C_t>.  u, delta, y [batch, L, D] fp32;

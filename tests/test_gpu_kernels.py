@@ -204,8 +204,14 @@ def test_lstm_vs_reference_golden(ops, tag, bf16):
         assert err(getattr(rnn, k).grad, v) < 1e-4, k
 
 
-@pytest.mark.parametrize("B,T,In,H,layers,bidir", [(5, 7, 24, 32, 2, False), (3, 6, 40, 56, 2, True), (9, 30, 8, 32, 3, False)])
-def test_lstm_vs_oracle(ops, B, T, In, H, layers, bidir):
+@pytest.mark.parametrize("B,T,In,H,layers,bidir,stack", [
+    (5, 7, 24, 32, 2, False, True), (5, 7, 24, 32, 2, False, False), (3, 6, 40, 56, 2, True, True),
+    (9, 30, 8, 32, 3, False, True), (9, 30, 8, 32, 3, False, False), (4, 40, 64, 56, 4, False, True),
+    (70, 16, 8, 32, 3, False, True), (2, 1, 3, 5, 1, False, True), (3, 64, 33, 64, 2, False, True)])
+def test_lstm_vs_oracle(ops, B, T, In, H, layers, bidir, stack, monkeypatch):
+    """stack=True: narrow unidirectional stacks run as ONE persistent launch per pass (lstm_stack.cu);
+    stack=False forces the per-layer kernels + hoisted gate GEMM on the same shapes."""
+    monkeypatch.setattr(ops, "LSTM_STACK", stack)
     torch.manual_seed(B * T)
     rnn = torch.nn.LSTM(In, H, num_layers=layers, bidirectional=bidir, batch_first=True)
     x = torch.randn(B, T, In)
@@ -222,6 +228,8 @@ def test_lstm_vs_oracle(ops, B, T, In, H, layers, bidir):
     assert err(xg.grad, xo.grad) < 1e-4
     for k, v in rnn.named_parameters():
         assert err(v.grad, p["lstm." + k].grad) < 1e-4, k
+    with torch.no_grad():                                     # inference: nothing saved for BPTT
+        assert err(ops.lstm_forward(x.to(DEV), rnn), ref) < 1e-5
 
 
 @pytest.mark.parametrize("M,N,gelu", [(37, 8, True), (64, 1024, True), (10, 960, False), (1920, 512, True)])

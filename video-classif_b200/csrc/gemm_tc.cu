@@ -849,6 +849,15 @@ int pick_bn(int N) {
   return 32;
 }
 
+// Plain GEMMs (Linear layers, their gradients): a small problem in 256-wide tiles leaves most SMs idle -- narrow
+// the tile until the grid covers the machine (M = 1024, N = 1024: 32 tiles of 256 -> 128 tiles of 64).
+int pick_bn_gemm(int M, int N) {
+  int bn = pick_bn(N);
+  const int m_blocks = b2_ceil_div(M, BM);
+  while (bn > 64 && m_blocks * b2_ceil_div(N, bn) < b2_num_sms()) bn >>= 1;
+  return bn;
+}
+
 template <int MODE, bool TF>
 int dispatch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tr,
                 int M, int N, int K, const ConvGeom& g, const ATransform& at, const EpiParams& ep, cudaStream_t stream) {
@@ -1333,7 +1342,7 @@ B2_API int b2_gemm_bf16_tn(const void* A, long lda, const void* B, long ldb, voi
   B2_ARG_CHECK(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "b2_gemm_bf16_tn: A/B must be 16 B aligned");
   B2_ARG_CHECK((col_sum == nullptr) == (col_sumsq == nullptr), "b2_gemm_bf16_tn: col_sum and col_sumsq go together");
   if (int r = load_driver_entry_points()) return r;
-  const int bn = pick_bn(N);
+  const int bn = pick_bn_gemm(M, N);
   CUtensorMap ta, tb;
   if (int r = make_tmap_2d(&ta, A, M, K, lda, BM)) return r;
   if (int r = make_tmap_2d(&tb, B, N, K, ldb, bn)) return r;

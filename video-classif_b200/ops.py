@@ -427,6 +427,70 @@ class LSTMLayerFn(torch.autograd.Function):
         return (dx, None, None, None, *grads)
 
 
+def _ptr_array(tensors):
+    import ctypes
+    arr = (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+    return arr, ctypes.cast(arr, ctypes.c_void_p)
+
+
+class LSTMStackFn(torch.autograd.Function):
+    """A whole unidirectional nn.LSTM stack in one launch per direction of time (b2_lstm_stack_fwd / _bwd):
+    params = (w_ih, w_hh, b_ih, b_hh) per layer.  Output = the top layer's [B,T,H] sequence."""
+
+    @staticmethod
+    def forward(ctx, x, hidden, need_grad, *params):
+        _chk(x, *params)
+        B, T, In = x.shape
+        L = len(params) // 4
+        H = hidden
+        xc = x.contiguous()
+        dev = x.device
+        out = torch.empty((L, B, T, H), device=dev, dtype=F32)
+        gates = torch.empty((L, B, T, 4 * H), device=dev, dtype=F32) if need_grad else None
+        cst = torch.empty((L, B, T, H), device=dev, dtype=F32) if need_grad else None
+        keep = [_ptr_array([params[4 * l + i] for l in range(L)]) for i in range(4)]
+        call("b2_lstm_stack_fwd", xc.data_ptr(), In, keep[0][1], keep[1][1], keep[2][1], keep[3][1], L, out.data_ptr(),
+             ptr(gates), ptr(cst), B, T, H, stream_ptr())
+        if need_grad:
+            ctx.save_for_backward(xc, out, gates, cst, *params)
+        ctx.dims = (B, T, In, H, L)
+        return out[L - 1]
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, T, In, H, L = ctx.dims
+        xc, out, gates, cst = ctx.saved_tensors[:4]
+        params = ctx.saved_tensors[4:]
+        dev = dout.device
+        dout = dout.contiguous()
+        # one zeroed slab for every parameter gradient of the stack (accumulated with atomics in the kernel)
+        sizes = []
+        for l in range(L):
+            sizes += [params[4 * l].numel(), params[4 * l + 1].numel(), 4 * H]
+        slab = torch.zeros(sum(sizes), device=dev, dtype=F32)
+        views, off = [], 0
+        for n in sizes:
+            views.append(slab[off:off + n])
+            off += n
+        dwih = [views[3 * l].view_as(params[4 * l]) for l in range(L)]
+        dwhh = [views[3 * l + 1].view_as(params[4 * l + 1]) for l in range(L)]
+        db = [views[3 * l + 2] for l in range(L)]
+        dx = torch.empty((B, T, In), device=dev, dtype=F32) if ctx.needs_input_grad[0] else None
+        k_wih = _ptr_array([params[4 * l] for l in range(L)])
+        k_whh = _ptr_array([params[4 * l + 1] for l in range(L)])
+        k_dwih, k_dwhh, k_db = _ptr_array(dwih), _ptr_array(dwhh), _ptr_array(db)
+        call("b2_lstm_stack_bwd", dout.data_ptr(), xc.data_ptr(), In, k_wih[1], k_whh[1], L, out.data_ptr(),
+             gates.data_ptr(), cst.data_ptr(), ptr(dx), k_dwih[1], k_dwhh[1], k_db[1], B, T, H, stream_ptr())
+        grads = []
+        for l in range(L):
+            grads += [dwih[l], dwhh[l], db[l], db[l]]
+        return (dx, None, None, *grads)
+
+
+STACK_MAX_H, STACK_MAX_IN, STACK_MAX_T, STACK_MAX_LAYERS = 64, 64, 64, 8
+LSTM_STACK = True      # False: always the per-layer kernels + hoisted gate GEMM (A/B parity tests)
+
+
 def lstm_forward(x, lstm_module, bf16=False):
     """Runs a torch.nn.LSTM *parameter container* (batch_first, no proj, dropout 0) on the
     persistent kernels.  Returns the [B,T,dirs*H] output of the last layer."""
@@ -434,6 +498,16 @@ def lstm_forward(x, lstm_module, bf16=False):
     dirs = 2 if lstm_module.bidirectional else 1
     H = lstm_module.hidden_size
     need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in lstm_module.parameters()))
+    B, T, In = x.shape
+    if (LSTM_STACK and dirs == 1 and H <= STACK_MAX_H and In <= STACK_MAX_IN and T <= STACK_MAX_T
+            and lstm_module.num_layers <= STACK_MAX_LAYERS and x.dtype == F32):
+        # narrow unidirectional stack: all layers and timesteps in one persistent launch
+        params = []
+        for layer in range(lstm_module.num_layers):
+            sfx = f"_l{layer}"
+            params += [getattr(lstm_module, "weight_ih" + sfx), getattr(lstm_module, "weight_hh" + sfx),
+                       getattr(lstm_module, "bias_ih" + sfx), getattr(lstm_module, "bias_hh" + sfx)]
+        return LSTMStackFn.apply(x, H, need_grad, *params)
     y = x
     for layer in range(lstm_module.num_layers):
         params = []
