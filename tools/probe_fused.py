@@ -92,9 +92,11 @@ if mode == "quick":
 elif mode == "gram":
     case("l1.conv3", 28, 64, 256, 1, 1, 0, ["gram", "a+o+res"])
     case("l2.conv3", 14, 128, 512, 1, 1, 0, ["gram", "a+o+res"])
-elif mode == "ncu":
-    case("l1.conv2", 28, 64, 64, 3, 1, 1, ["a+stats"])
-    case("l1.conv3", 28, 64, 256, 1, 1, 0, ["a+statsonly", "a+o+res"])
+elif mode == "ncu":      # one launch each of the representative kernels, for `ncu --set full`
+    case("l1.conv3", 28, 64, 256, 1, 1, 0, ["a+o+res", "gram"])      # EPI_POST (HBM bound) + Gram statistics
+    case("l3.conv2", 7, 256, 256, 3, 1, 1, ["stats"])                 # EPI_BF16 3x3 implicit GEMM (tensor bound)
+    case("l1.conv2", 28, 64, 64, 3, 1, 1, ["stats"])                  # BN = 64 3x3 (L2 -> SM bound)
+    case("l3.conv1", 7, 1024, 256, 1, 1, 0, ["stats"])                # 1x1 reduce, K = 1024
 else:
     xs = torch.rand(NF, 3, 112, 112, device=dev)
     wk = ops.pack_stem_weight(torch.randn(64, 3, 7, 7, device=dev) / 12)
