@@ -90,7 +90,7 @@ int b2_scale_shift_apply_nhwc(const void* x, void* y, long rows, int C, const fl
 /* BatchNorm statistics + finalisation of a 1x1 convolution y = relu?(x*a_scale+a_shift) W^T WITHOUT computing y
  * (torchvision Bottleneck.bn3 in train mode, models.py:192): per-channel sum_m y and sum_m y^2 follow from the
  * K-vector s = sum_m t[m,:] and the K x K Gram matrix G = sum_m t^T t of the transformed input (tensor-core
- * MN-major MMA over one streaming pass of x), evaluated per output channel in fp64.  x [M, C] bf16 (C = 64 or 128),
+ * MN-major MMA over one streaming pass of x), evaluated per output channel in fp64.  x [M, C] bf16 (C = 64, 128 or 256),
  * w [Cout, C] bf16; workspace: b2_gram_workspace_floats(C) floats (scratch, zeroed inside); col_sum/col_sumsq [Cout] optional outputs
  * (OVERWRITTEN); fin_scale/fin_shift [Cout] = gamma*rstd, beta - mean*gamma*rstd; running stats updated when given. */
 long b2_gram_workspace_floats(int C);

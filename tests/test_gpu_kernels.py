@@ -137,7 +137,7 @@ def test_conv_bn_folded(ops, N, H, W, C, Cout, R, stride, pad):
 
 
 @pytest.mark.parametrize("M,C,Cout", [(128, 64, 256), (256, 128, 512), (1000, 64, 64), (5000, 128, 256), (70000, 64, 256),
-                                      (33333, 128, 512)])
+                                      (33333, 128, 512), (128, 256, 1024), (50176, 256, 1024), (777, 256, 64)])
 def test_gram_bn_statistics(ops, M, C, Cout):
     """b2_conv1x1_gram_bnstats_bf16: sum / sum-of-squares / BN scale+shift of relu(x*a+b) @ W^T from the Gram
     matrix (MN-major tcgen05 MMA) vs the directly computed fp64 statistics of the same product."""

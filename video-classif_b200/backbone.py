@@ -48,12 +48,17 @@ class ResNetRunner:
         self.net = net
         self._wcache = None
         self._wkey = None
+        self._convs = None
+        self._bns = None
+        self._frozen = None
         self.stem_impl = "direct"     # "im2col": patch matrix + plain GEMM (A/B parity tests)
         self.fuse_bn = ResNetRunner.FUSE_BN   # BatchNorms folded into the conv kernels vs stand-alone bn_apply passes
 
     # ---- weights in kernel layout: [Cout, R, S, C] bf16 (K-major), stem [64, STEM_KP] ----
     def _weights(self):
-        convs = [(n, m) for n, m in self.net.named_modules() if isinstance(m, torch.nn.Conv2d)]
+        convs = self._convs          # module list is fixed after construction: walk the tree once, not per call
+        if convs is None:
+            convs = self._convs = [(n, m) for n, m in self.net.named_modules() if isinstance(m, torch.nn.Conv2d)]
         key = tuple((m.weight.data_ptr(), m.weight._version) for _, m in convs)
         if self._wkey != key:
             cache = {}
@@ -97,7 +102,9 @@ class ResNetRunner:
         return_stages=True also returns the spatial means after the stem and each stage (tests)."""
         _lib.require_device()
         net = self.net
-        if torch.is_grad_enabled() and any(p.requires_grad for p in net.parameters()):
+        if self._frozen is None:
+            self._frozen = list(net.parameters())
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self._frozen):
             raise NotImplementedError(
                 "trainable CNN backbone (full fine-tune, rgb_lrcn.py:208-227) has no backward kernels yet; "
                 "freeze it (requires_grad=False) as medsos models.py:144-145 / ucf50-lrcn.py:271-272 do")
@@ -106,36 +113,40 @@ class ResNetRunner:
         assert Cin == 3, "frame encoder expects RGB frames"
         dev = x.device
         w = self._weights()
-        bns = [m for m in net.modules() if isinstance(m, torch.nn.BatchNorm2d)]
+        if self._bns is None:
+            bl = [m for m in net.modules() if isinstance(m, torch.nn.BatchNorm2d)]
+            self._bns = (bl, max(b.num_features for b in bl), {id(b): i for i, b in enumerate(bl)})
+        bns, maxc, bn_index = self._bns
         train = bool(training)
-        maxc = max(b.num_features for b in bns)
-        # per BatchNorm: [sum | sumsq | scale | shift] (maxc floats each) + a finalisation counter word
+        # per BatchNorm: [sum | sumsq | scale | shift] (maxc floats each) + a finalisation counter word.  The slots are
+        # handed to the kernels as raw device addresses (no per-launch tensor views on the host)
         stat_buf = torch.zeros((len(bns), 4 * maxc + 4), device=dev, dtype=F32)
-        bn_index = {id(b): i for i, b in enumerate(bns)}
+        row_bytes = (4 * maxc + 4) * 4
+        sb_base = stat_buf.data_ptr()
+
+        def slot(bn, k):
+            return sb_base + bn_index[id(bn)] * row_bytes + k * maxc * 4
 
         def stats_of(bn):
             if not train:
                 return None
-            sb = stat_buf[bn_index[id(bn)]]
-            return (sb[0:maxc], sb[maxc:2 * maxc])
+            return (slot(bn, 0), slot(bn, 1))
 
         def ss_of(bn):                         # (scale, shift) written by the producer's finalisation tail
-            sb = stat_buf[bn_index[id(bn)]]
-            return (sb[2 * maxc:3 * maxc], sb[3 * maxc:4 * maxc])
+            return (slot(bn, 2), slot(bn, 3))
 
         def fin_of(bn):
             if not train:
                 return None
-            sb = stat_buf[bn_index[id(bn)]]
-            return (bn.weight, bn.bias, bn.running_mean, bn.running_var, sb[2 * maxc:3 * maxc], sb[3 * maxc:4 * maxc],
-                    sb[4 * maxc:], bn.eps, bn.momentum if bn.momentum is not None else 0.1)
+            return (bn.weight, bn.bias, bn.running_mean, bn.running_var, slot(bn, 2), slot(bn, 3),
+                    slot(bn, 4), bn.eps, bn.momentum if bn.momentum is not None else 0.1)
 
         fuse = self.fuse_bn
         if fuse and not train:                 # eval: scale/shift straight from the running statistics
             for b in bns:
                 sc, sh = ss_of(b)
                 call("b2_bn_finalize_nhwc", 0, 0, b.weight.data_ptr(), b.bias.data_ptr(), b.running_mean.data_ptr(),
-                     b.running_var.data_ptr(), 1, float(b.eps), 0.1, 0, sc.data_ptr(), sh.data_ptr(), b.num_features,
+                     b.running_var.data_ptr(), 1, float(b.eps), 0.1, 0, sc, sh, b.num_features,
                      stream_ptr())
 
         st = stream_ptr()

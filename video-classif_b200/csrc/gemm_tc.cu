@@ -119,10 +119,10 @@ struct SmemLayout {
   static constexpr int kTileBytes = kStageBytes * kStages;
   static constexpr int kBarOffset = kTileBytes;
   static constexpr int kNumBars = 3 * kStages + 4 + kEpiWarps * kResSlots;
-  // [4 quarters][2][BN] column statistics at flush time; the SAME bytes hold the per-column
+  // [4 quarters x 2 half-warps][2][BN] column statistics at flush time; the SAME bytes hold the per-column
   // {o_scale, o_shift, r_scale, r_shift}[BN] of an output pass (statistics and output BN never mix)
   static constexpr int kStatOffset = (kBarOffset + kNumBars * 8 + 16 + 15) / 16 * 16;
-  static constexpr int kScratchOffset = kStatOffset + 4 * 2 * BN * 4;
+  static constexpr int kScratchOffset = kStatOffset + 8 * 2 * BN * 4;
   static constexpr int kScratchOffset1k = (kScratchOffset + 1023) / 1024 * 1024;        // tiles 1024-aligned
   // non-POST: kEpiWarps x kStgBufs staging tiles; POST: kEpiWarps x kResSlots shortcut-in / output-out tiles
   static constexpr int kScratchBytes = kEpiWarps * (kPost ? kResSlots : kStgBufs) * kStgBytes;
@@ -166,7 +166,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   constexpr bool kPost = MODE == EPI_POST;
   constexpr bool kStore = MODE != EPI_STATS;
   const bool want_stats = MODE == EPI_STATS || (MODE != EPI_POST && ep.col_sum != nullptr);
-  for (int i = threadIdx.x; i < 8 * BN; i += kThreads) stat_s[i] = 0.f;
+  for (int i = threadIdx.x; i < 16 * BN; i += kThreads) stat_s[i] = 0.f;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -453,11 +453,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           for (int c = epi_tid; c < BN; c += 32 * kEpiWarps) {
             const int col = cur_nblk * BN + c;
             if (col < N) {
-              atomicAdd(ep.col_sum + col, stat_s[c] + stat_s[2 * BN + c] + stat_s[4 * BN + c] + stat_s[6 * BN + c]);
-              atomicAdd(ep.col_sumsq + col, stat_s[BN + c] + stat_s[3 * BN + c] + stat_s[5 * BN + c] + stat_s[7 * BN + c]);
+              float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+              for (int qq = 0; qq < 8; ++qq) {
+                a1 += stat_s[qq * 2 * BN + c];
+                a2 += stat_s[qq * 2 * BN + BN + c];
+              }
+              atomicAdd(ep.col_sum + col, a1);
+              atomicAdd(ep.col_sumsq + col, a2);
             }
 #pragma unroll
-            for (int qq = 0; qq < 8; ++qq) stat_s[qq * BN + c] = 0.f;
+            for (int qq = 0; qq < 16; ++qq) stat_s[qq * BN + c] = 0.f;
           }
           asm volatile("bar.sync 1, 256;" ::: "memory");
         }
@@ -532,17 +538,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               s2a = __ffma2_rn(x0, x0, s2a);
               s2b = __ffma2_rn(x1, x1, s2b);
             }
-            float2 t1 = __fadd2_rn(s1a, s1b), t2 = __fadd2_rn(s2a, s2b);
-            t1.x += __shfl_xor_sync(0xffffffffu, t1.x, 16);
-            t1.y += __shfl_xor_sync(0xffffffffu, t1.y, 16);
-            t2.x += __shfl_xor_sync(0xffffffffu, t2.x, 16);
-            t2.y += __shfl_xor_sync(0xffffffffu, t2.y, 16);
-            if (sw_hf == 0) {
-              float2* st = reinterpret_cast<float2*>(stat_s + quarter * 2 * BN + ch * 32 + 2 * sw_w);
-              float2* st2 = reinterpret_cast<float2*>(stat_s + quarter * 2 * BN + BN + ch * 32 + 2 * sw_w);
-              *st = __fadd2_rn(*st, t1);
-              *st2 = __fadd2_rn(*st2, t2);
-            }
+            // each half-warp owns its own copy of the statistics (no shuffle, no atomics: one writer per slot)
+            float2* st = reinterpret_cast<float2*>(stat_s + (quarter * 2 + sw_hf) * 2 * BN + ch * 32 + 2 * sw_w);
+            float2* st2 = reinterpret_cast<float2*>(stat_s + (quarter * 2 + sw_hf) * 2 * BN + BN + ch * 32 + 2 * sw_w);
+            *st = __fadd2_rn(*st, __fadd2_rn(s1a, s1b));
+            *st2 = __fadd2_rn(*st2, __fadd2_rn(s2a, s2b));
           }
           if (kStore) {
             if (out_bf16) {
@@ -625,7 +625,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
               }
             }
-            float* st = stat_s + quarter * 2 * BN + ch * 32 + lane;      // lane l holds column l
+            float* st = stat_s + quarter * 4 * BN + ch * 32 + lane;      // lane l holds column l (half-warp-0 copy)
             st[0] += v[0];
             st[BN] += s2[0];
           }
@@ -642,8 +642,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int c = epi_tid; c < BN; c += 32 * kEpiWarps) {
         const int col = cur_nblk * BN + c;
         if (col < N) {
-          atomicAdd(ep.col_sum + col, stat_s[c] + stat_s[2 * BN + c] + stat_s[4 * BN + c] + stat_s[6 * BN + c]);
-          atomicAdd(ep.col_sumsq + col, stat_s[BN + c] + stat_s[3 * BN + c] + stat_s[5 * BN + c] + stat_s[7 * BN + c]);
+          float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+          for (int qq = 0; qq < 8; ++qq) {
+            a1 += stat_s[qq * 2 * BN + c];
+            a2 += stat_s[qq * 2 * BN + BN + c];
+          }
+          atomicAdd(ep.col_sum + col, a1);
+          atomicAdd(ep.col_sumsq + col, a2);
         }
       }
     }
@@ -996,13 +1002,24 @@ int conv_common(const void* x, int Nimg, int H, int W, int C, const void* w, int
 // A "super tile" is two 16 KB SWIZZLE_128B panels of 128 rows x 64 channels, M/N = 128 for the MMA:
 //   K = 128: the two 64-channel halves of one 128-row tile;  K = 64: two consecutive 128-row tiles side by
 //   side (the Gram of [t1 | t2] holds t1^T t1 and t2^T t2 on its diagonal blocks, summed at drain time).
-constexpr int kGramStages = 5;
 constexpr int kGramCopies = 8;           // partial global accumulators: shortens the same-address atomic chains 8x
-constexpr int kGramThreads = 64 + 256;   // TMA warp, MMA warp, 8 transform warps (4 per panel; the first 4 also drain)
-constexpr int kGramStageBytes = 2 * BM * BK * 2;                    // 32 KB
-constexpr int kGramOnesOffset = kGramStages * kGramStageBytes;      // 1 KB of bf16 ones
-constexpr int kGramBarOffset = kGramOnesOffset + 1024;
-constexpr int kGramSmem = kGramBarOffset + (3 * kGramStages + 1) * 8 + 16 + 1024;
+constexpr int kGramThreads = 64 + 256;   // TMA warp, MMA warp, 8 transform warps (the first 4 also drain)
+constexpr int kPanelBytes = BM * BK * 2; // 16 KB: 128 rows x 64 channels, SWIZZLE_128B
+
+template <int KC>
+struct GramLayout {
+  static constexpr int kPanels = KC == 256 ? 4 : 2;              // panels per super tile
+  static constexpr int kStages = KC == 256 ? 3 : 5;
+  static constexpr int kStageBytes = kPanels * kPanelBytes;      // 32 / 64 KB
+  static constexpr int kOnesOffset = kStages * kStageBytes;      // 1 KB of bf16 ones
+  static constexpr int kBarOffset = kOnesOffset + 1024;
+  static constexpr int kSmem = kBarOffset + (3 * kStages + 1) * 8 + 16 + 1024;
+  // TMEM columns: K <= 128: G [0,128), s [128,144).  K = 256: G rows 0..127 x all 256 columns [0,256),
+  // G rows 128..255 x columns 128..255 [256,384) (the lower-left block is the transpose of the upper-right one),
+  // s rows 0..127 [384,400), s rows 128..255 [400,416)
+  static constexpr uint32_t kTmemCols = KC == 256 ? 512 : 256;
+  static constexpr uint32_t kSumCol0 = KC == 256 ? 384 : 128;
+};
 
 // MN-major SWIZZLE_128B descriptor: 64 contiguous MN elements per 128 B row (one row per K index), 8-row
 // groups SBO = 1024 B apart, 64-element MN blocks LBO bytes apart (the panel stride).
@@ -1018,27 +1035,27 @@ __device__ __forceinline__ uint64_t make_sw128_mn_desc(uint32_t smem_addr, uint3
 
 template <int KC>
 __global__ void __launch_bounds__(kGramThreads, 1)
-gram_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, int M, ATransform at, float* __restrict__ gram,
-                  float* __restrict__ sum_a) {
-  static_assert(KC == 64 || KC == 128, "gram_stats_kernel: 64 or 128 input channels");
+gram_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, int M, ATransform at, float* __restrict__ ws) {
+  static_assert(KC == 64 || KC == 128 || KC == 256, "gram_stats_kernel: 64, 128 or 256 input channels");
+  using G = GramLayout<KC>;
+  constexpr int kStages = G::kStages;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kGramBarOffset);
-  uint64_t* tf_bar = full_bar + kGramStages;
-  uint64_t* empty_bar = tf_bar + kGramStages;
-  uint64_t* done_bar = empty_bar + kGramStages;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + G::kBarOffset);
+  uint64_t* tf_bar = full_bar + kStages;
+  uint64_t* empty_bar = tf_bar + kStages;
+  uint64_t* done_bar = empty_bar + kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
-  constexpr uint32_t kTmemCols = 256;        // G: columns 0..127, s: columns 128..143
   constexpr int kRowsPerSuper = KC == 64 ? 2 * BM : BM;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_super = (M + kRowsPerSuper - 1) / kRowsPerSuper;
 
   for (int i = threadIdx.x; i < 256; i += kGramThreads)
-    reinterpret_cast<uint32_t*>(smem + kGramOnesOffset)[i] = 0x3F803F80u;   // bf16 1.0 pairs
+    reinterpret_cast<uint32_t*>(smem + G::kOnesOffset)[i] = 0x3F803F80u;   // bf16 1.0 pairs
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
-    for (int i = 0; i < kGramStages; ++i) {
+    for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&tf_bar[i], 256);
       mbar_init(&empty_bar[i], 1);
@@ -1047,7 +1064,7 @@ gram_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, int M, ATransform 
     fence_barrier_init();
   }
   if (warp == 1) {
-    tc_alloc(tmem_slot, kTmemCols);
+    tc_alloc(tmem_slot, G::kTmemCols);
     tc_relinquish();
   }
   fence_proxy_async_smem();        // the ones matrix is read by the tensor core (async proxy)
@@ -1062,26 +1079,28 @@ gram_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, int M, ATransform 
       uint32_t phase = 0;
       for (int st = blockIdx.x; st < num_super; st += gridDim.x) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * kGramStageBytes;
-        mbar_expect_tx(&full_bar[stage], kGramStageBytes);
-        if (KC == 128) {
-          tma_load_2d(sa, &tmap_a, &full_bar[stage], 0, st * BM);
-          tma_load_2d(sa + BM * BK * 2, &tmap_a, &full_bar[stage], BK, st * BM);
-        } else {
+        uint8_t* sa = smem + stage * G::kStageBytes;
+        mbar_expect_tx(&full_bar[stage], G::kStageBytes);
+        if (KC == 64) {
           tma_load_2d(sa, &tmap_a, &full_bar[stage], 0, st * 2 * BM);
-          tma_load_2d(sa + BM * BK * 2, &tmap_a, &full_bar[stage], 0, st * 2 * BM + BM);   // fully OOB rows -> zeros
+          tma_load_2d(sa + kPanelBytes, &tmap_a, &full_bar[stage], 0, st * 2 * BM + BM);   // fully OOB rows -> zeros
+        } else {
+#pragma unroll
+          for (int pp = 0; pp < G::kPanels; ++pp)
+            tma_load_2d(sa + pp * kPanelBytes, &tmap_a, &full_bar[stage], pp * BK, st * BM);
         }
-        if (++stage == kGramStages) {
+        if (++stage == kStages) {
           stage = 0;
           phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
-    // both operands MN-major (bits 15, 16): D[128 x 128] += P^T P ; s: D[128 x 16] += P^T ones (B K-major)
-    constexpr uint32_t idesc_g = make_idesc(128, 128) | (1u << 15) | (1u << 16);
+    // operands MN-major (bits 15, 16): D += P^T P ; column sums: D[128 x 16] += P^T ones (B K-major)
+    constexpr uint32_t idesc_g = make_idesc(128, KC == 256 ? 256 : 128) | (1u << 15) | (1u << 16);
+    constexpr uint32_t idesc_g2 = make_idesc(128, 128) | (1u << 15) | (1u << 16);
     constexpr uint32_t idesc_s = make_idesc(128, 16) | (1u << 15);
-    const uint64_t ones_desc = make_nosw_desc(smem_u32(smem + kGramOnesOffset), 128, 256);
+    const uint64_t ones_desc = make_nosw_desc(smem_u32(smem + G::kOnesOffset), 128, 256);
     int stage = 0;
     uint32_t phase = 0;
     bool first = true;
@@ -1089,18 +1108,24 @@ gram_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, int M, ATransform 
       mbar_wait(&tf_bar[stage], phase);
       tc_fence_after();
       if (lane == 0) {
-        const uint32_t sa = smem_u32(smem + stage * kGramStageBytes);
+        const uint32_t sa = smem_u32(smem + stage * G::kStageBytes);
 #pragma unroll
         for (int ks = 0; ks < BM / UMMA_K; ++ks) {          // 16 tile rows (two 8-row groups) per MMA
-          const uint64_t d = make_sw128_mn_desc(sa + ks * 2048, BM * BK * 2);
-          tc_mma_bf16(tmem_base, d, d, idesc_g, !(first && ks == 0));
-          tc_mma_bf16(tmem_base + 128, d, ones_desc, idesc_s, !(first && ks == 0));
+          const uint32_t acc = !(first && ks == 0);
+          const uint64_t d0 = make_sw128_mn_desc(sa + ks * 2048, kPanelBytes);
+          tc_mma_bf16(tmem_base, d0, d0, idesc_g, acc);                       // features 0..127 x all
+          tc_mma_bf16(tmem_base + G::kSumCol0, d0, ones_desc, idesc_s, acc);
+          if (KC == 256) {
+            const uint64_t d2 = make_sw128_mn_desc(sa + 2 * kPanelBytes + ks * 2048, kPanelBytes);
+            tc_mma_bf16(tmem_base + 256, d2, d2, idesc_g2, acc);              // features 128..255 x 128..255
+            tc_mma_bf16(tmem_base + G::kSumCol0 + 16, d2, ones_desc, idesc_s, acc);
+          }
         }
         tc_commit(&empty_bar[stage]);
       }
       first = false;
       __syncwarp();
-      if (++stage == kGramStages) {
+      if (++stage == kStages) {
         stage = 0;
         phase ^= 1;
       }
@@ -1108,9 +1133,9 @@ gram_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, int M, ATransform 
     if (lane == 0) tc_commit(done_bar);
     __syncwarp();
   } else {
-    // =========================== A transform (warps 2..5), then the drain ===========================
+    // =========================== A transform (warps 2..9), then the drain (warps 2..5) ===========================
     const int tt = (threadIdx.x - 64) & 127;
-    const int p = (threadIdx.x - 64) >> 7;          // the panel this group of 4 warps rewrites
+    const int grp = (threadIdx.x - 64) >> 7;        // group of 4 warps: panels grp, grp + 2 (K = 256) or panel grp
     const int c = tt & 7;
     const int rb = tt >> 3;
     uint32_t row_off[8];
@@ -1119,22 +1144,25 @@ gram_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, int M, ATransform 
       const int row = rb + 16 * i;
       row_off[i] = (uint32_t)(row * 128 + ((c ^ (row & 7)) << 4));
     }
-    float4 sc0[1], sc1[1], sh0[1], sh1[1];          // this thread's 8 channels never change
-    {
-      const int c0 = (KC == 128 ? p * BK : 0) + c * 8;
-      sc0[0] = __ldg(reinterpret_cast<const float4*>(at.scale + c0));
-      sc1[0] = __ldg(reinterpret_cast<const float4*>(at.scale + c0 + 4));
-      sh0[0] = __ldg(reinterpret_cast<const float4*>(at.shift + c0));
-      sh1[0] = __ldg(reinterpret_cast<const float4*>(at.shift + c0 + 4));
+    constexpr int kMine = KC == 256 ? 2 : 1;        // panels per thread group; a thread's channels are fixed per panel
+    float4 sc0[kMine], sc1[kMine], sh0[kMine], sh1[kMine];
+#pragma unroll
+    for (int q = 0; q < kMine; ++q) {
+      const int c0 = (KC == 64 ? 0 : (grp + 2 * q) * BK) + c * 8;
+      sc0[q] = __ldg(reinterpret_cast<const float4*>(at.scale + c0));
+      sc1[q] = __ldg(reinterpret_cast<const float4*>(at.scale + c0 + 4));
+      sh0[q] = __ldg(reinterpret_cast<const float4*>(at.shift + c0));
+      sh1[q] = __ldg(reinterpret_cast<const float4*>(at.shift + c0 + 4));
     }
     int stage = 0;
     uint32_t phase = 0;
     for (int st = blockIdx.x; st < num_super; st += gridDim.x) {
       mbar_wait(&full_bar[stage], phase);
-      {
-        uint8_t* sa = smem + stage * kGramStageBytes + p * (BM * BK * 2);
-        const int row0 = (KC == 128 ? st * BM : st * 2 * BM + p * BM) + rb;
-        constexpr int cs = 0;
+#pragma unroll
+      for (int q = 0; q < kMine; ++q) {
+        const int p = grp + 2 * q;
+        uint8_t* sa = smem + stage * G::kStageBytes + p * kPanelBytes;
+        const int row0 = (KC == 64 ? st * 2 * BM + p * BM : st * BM) + rb;
         uint4 u[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) u[i] = *reinterpret_cast<const uint4*>(sa + row_off[i]);
@@ -1145,10 +1173,10 @@ gram_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, int M, ATransform 
           float2 a1 = make_float2(__uint_as_float(u[i].y << 16), __uint_as_float(u[i].y & 0xffff0000u));
           float2 a2 = make_float2(__uint_as_float(u[i].z << 16), __uint_as_float(u[i].z & 0xffff0000u));
           float2 a3 = make_float2(__uint_as_float(u[i].w << 16), __uint_as_float(u[i].w & 0xffff0000u));
-          a0 = __ffma2_rn(a0, make_float2(sc0[cs].x, sc0[cs].y), make_float2(sh0[cs].x, sh0[cs].y));
-          a1 = __ffma2_rn(a1, make_float2(sc0[cs].z, sc0[cs].w), make_float2(sh0[cs].z, sh0[cs].w));
-          a2 = __ffma2_rn(a2, make_float2(sc1[cs].x, sc1[cs].y), make_float2(sh1[cs].x, sh1[cs].y));
-          a3 = __ffma2_rn(a3, make_float2(sc1[cs].z, sc1[cs].w), make_float2(sh1[cs].z, sh1[cs].w));
+          a0 = __ffma2_rn(a0, make_float2(sc0[q].x, sc0[q].y), make_float2(sh0[q].x, sh0[q].y));
+          a1 = __ffma2_rn(a1, make_float2(sc0[q].z, sc0[q].w), make_float2(sh0[q].z, sh0[q].w));
+          a2 = __ffma2_rn(a2, make_float2(sc1[q].x, sc1[q].y), make_float2(sh1[q].x, sh1[q].y));
+          a3 = __ffma2_rn(a3, make_float2(sc1[q].z, sc1[q].w), make_float2(sh1[q].z, sh1[q].w));
           uint4 t;
           if (at.relu) {
             t.x = pack_bf16x2_relu(a0.x, a0.y);
@@ -1171,50 +1199,57 @@ gram_stats_kernel(const __grid_constant__ CUtensorMap tmap_a, int M, ATransform 
       }
       fence_proxy_async_smem();
       mbar_arrive(&tf_bar[stage]);
-      if (++stage == kGramStages) {
+      if (++stage == kStages) {
         stage = 0;
         phase ^= 1;
       }
     }
-    // ---- drain (warps 2..5): lane = feature row f of the accumulator; vector reductions into the workspace
+    // ---- drain (warps 2..5): lane = feature row f of the accumulator; vector reductions into this CTA's
+    // partial workspace [KC*KC Gram | KC sums]
     if (warp < 6) {
-    mbar_wait(done_bar, 0);
-    tc_fence_after();
-    const int quarter = warp & 3;
-    const int f = quarter * 32 + lane;
-    gram += (long)(blockIdx.x % kGramCopies) * (KC * KC + KC);        // this CTA's partial workspace
-    sum_a = gram + KC * KC;
+      mbar_wait(done_bar, 0);
+      tc_fence_after();
+      const int quarter = warp & 3;
+      const int f = quarter * 32 + lane;
+      float* gram = ws + (long)(blockIdx.x % kGramCopies) * (KC * KC + KC);
+      float* sum_a = gram + KC * KC;
+      constexpr int kChunks = KC == 256 ? 12 : 4;
 #pragma unroll 1
-    for (int ch = 0; ch < 4; ++ch) {
-      if (KC == 64 && (ch >> 1) != (quarter >> 1)) continue;      // only the two diagonal 64 x 64 blocks
-      uint32_t raw[32];
-      tc_ld32(tmem_base + (uint32_t)(ch * 32) + ((uint32_t)(quarter * 32) << 16), raw);
-      tc_wait_ld();
-      float* dst = KC == 128 ? gram + (long)f * 128 + ch * 32 : gram + (long)(f & 63) * 64 + (ch & 1) * 32;
+      for (int ch = 0; ch < kChunks; ++ch) {
+        if (KC == 64 && (ch >> 1) != (quarter >> 1)) continue;      // only the two diagonal 64 x 64 blocks
+        uint32_t raw[32];
+        tc_ld32(tmem_base + (uint32_t)(ch * 32) + ((uint32_t)(quarter * 32) << 16), raw);
+        tc_wait_ld();
+        float* dst;
+        if (KC == 64) dst = gram + (long)(f & 63) * 64 + (ch & 1) * 32;
+        else if (KC == 128) dst = gram + (long)f * 128 + ch * 32;
+        else dst = ch < 8 ? gram + (long)f * 256 + ch * 32 : gram + (long)(128 + f) * 256 + 128 + (ch - 8) * 32;
 #pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(raw[j])),
-                     "f"(__uint_as_float(raw[j + 1])), "f"(__uint_as_float(raw[j + 2])), "f"(__uint_as_float(raw[j + 3]))
-                     : "memory");
-    }
-    {
-      uint32_t raw[32];
-      tc_ld32(tmem_base + 128u + ((uint32_t)(quarter * 32) << 16), raw);     // every column of the N = 16 block = s
-      tc_wait_ld();
-      atomicAdd(sum_a + (KC == 128 ? f : (f & 63)), __uint_as_float(raw[0]));
-    }
-    tc_fence_before();
+        for (int j = 0; j < 32; j += 4)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(raw[j])),
+                       "f"(__uint_as_float(raw[j + 1])), "f"(__uint_as_float(raw[j + 2])), "f"(__uint_as_float(raw[j + 3]))
+                       : "memory");
+      }
+      {
+        uint32_t raw[32];     // every column of an N = 16 block holds s; K = 256: columns 0 and 16 of this load
+        tc_ld32(tmem_base + G::kSumCol0 + ((uint32_t)(quarter * 32) << 16), raw);
+        tc_wait_ld();
+        atomicAdd(sum_a + (KC == 64 ? (f & 63) : f), __uint_as_float(raw[0]));
+        if (KC == 256) atomicAdd(sum_a + 128 + f, __uint_as_float(raw[16]));
+      }
+      tc_fence_before();
     }
   }
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tc_dealloc(tmem_base, kTmemCols);
+    tc_dealloc(tmem_base, G::kTmemCols);
   }
 }
 
 // Finalisation, two small kernels:
-//   gram_reduce_kernel   sums the kGramCopies partial workspaces and centres: Cov = G/M - m m^T, m = s/M
+//   gram_reduce_kernel   sums the kGramCopies partial workspaces, mirrors the block the K = 256 kernel leaves out
+//                        and centres: Cov = G/M - m m^T, m = s/M
 //   gram_finalize_kernel one warp per pair of output channels: mean_n = <w_n, m>, var_n = w_n^T Cov w_n in fp32
 //                        (the centred form keeps the cancellation out of the long sums: 1e-5 relative on var
 //                        against an fp64 evaluation at the layer shapes), then the BatchNorm finalisation.
@@ -1224,12 +1259,21 @@ gram_reduce_kernel(const float* __restrict__ ws, float* __restrict__ cov, int KC
   const int i4 = blockIdx.x * blockDim.x + threadIdx.x;          // one float4 of the K x K matrix per thread
   if (i4 >= KC * KC / 4) return;
   const int k = (i4 * 4) / KC, l = (i4 * 4) - k * KC;
+  const bool mirror = KC == 256 && k >= 128 && l < 128;           // G[k][l] = G[l][k]
   float4 t = make_float4(0.f, 0.f, 0.f, 0.f), ml = t;
   float mk = 0.f;
 #pragma unroll
   for (int c = 0; c < kGramCopies; ++c) {
     const float* base = ws + c * copy_stride;
-    const float4 g = __ldg(reinterpret_cast<const float4*>(base) + i4);
+    float4 g;
+    if (mirror) {
+      g.x = __ldg(base + (l + 0) * KC + k);
+      g.y = __ldg(base + (l + 1) * KC + k);
+      g.z = __ldg(base + (l + 2) * KC + k);
+      g.w = __ldg(base + (l + 3) * KC + k);
+    } else {
+      g = __ldg(reinterpret_cast<const float4*>(base) + i4);
+    }
     const float4 sl = __ldg(reinterpret_cast<const float4*>(base + KC * KC + l));
     mk += __ldg(base + KC * KC + k);
     t.x += g.x; t.y += g.y; t.z += g.z; t.w += g.w;
@@ -1246,15 +1290,14 @@ gram_reduce_kernel(const float* __restrict__ ws, float* __restrict__ cov, int KC
 
 constexpr int kGramFinWarps = 8;
 constexpr int kGramFinPerWarp = 2;       // output channels per warp
+constexpr int kGramFinChunk = 16384;     // floats of Cov staged in shared memory at a time (64 KB)
 __global__ void __launch_bounds__(32 * kGramFinWarps)
 gram_finalize_kernel(const float* __restrict__ cov, const bf16* __restrict__ W, int N, int KC, float* __restrict__ col_sum,
                      float* __restrict__ col_sumsq, BnFinal f, float count) {
-  extern __shared__ float gsm[];             // Cov [KC*KC] + mean [KC], weight rows [warps][2][KC]
+  extern __shared__ float gsm[];             // Cov rows [chunk], mean [KC], weight rows [warps][2][KC]
   float* cov_s = gsm;
-  float* m_s = gsm + KC * KC;
+  float* m_s = gsm + kGramFinChunk;
   float* w_s = m_s + KC;
-  for (int i4 = threadIdx.x; i4 < (KC * KC + KC) / 4; i4 += blockDim.x)
-    reinterpret_cast<float4*>(cov_s)[i4] = __ldg(reinterpret_cast<const float4*>(cov) + i4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = (blockIdx.x * kGramFinWarps + warp) * kGramFinPerWarp;
   float* w0 = w_s + (warp * kGramFinPerWarp) * KC;
@@ -1263,25 +1306,33 @@ gram_finalize_kernel(const float* __restrict__ cov, const bf16* __restrict__ W, 
     w0[l] = (n0 < N) ? __bfloat162float(W[(long)n0 * KC + l]) : 0.f;
     w1[l] = (n0 + 1 < N) ? __bfloat162float(W[(long)(n0 + 1) * KC + l]) : 0.f;
   }
-  __syncthreads();
-  if (n0 >= N) return;
-  const int per = KC / 32;                   // 2 or 4 columns of Cov per lane
-  float u0[4] = {0.f, 0.f, 0.f, 0.f}, u1[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-  for (int k = 0; k < KC; ++k) {
-    const float a0 = w0[k], a1 = w1[k];
+  for (int i = threadIdx.x; i < KC; i += blockDim.x) m_s[i] = cov[KC * KC + i];
+  const int per = KC / 32;                   // 2, 4 or 8 columns of Cov per lane
+  const int rows = kGramFinChunk / KC < KC ? kGramFinChunk / KC : KC;     // Cov rows per staged chunk
+  float u0[8], u1[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (j < per) {
-        const float cv = cov_s[k * KC + lane + 32 * j];
-        u0[j] = fmaf(a0, cv, u0[j]);
-        u1[j] = fmaf(a1, cv, u1[j]);
+  for (int j = 0; j < 8; ++j) u0[j] = u1[j] = 0.f;
+  for (int k0 = 0; k0 < KC; k0 += rows) {
+    __syncthreads();
+    for (int i4 = threadIdx.x; i4 < rows * KC / 4; i4 += blockDim.x)
+      reinterpret_cast<float4*>(cov_s)[i4] = __ldg(reinterpret_cast<const float4*>(cov + (long)k0 * KC) + i4);
+    __syncthreads();
+#pragma unroll 4
+    for (int k = 0; k < rows; ++k) {
+      const float a0 = w0[k0 + k], a1 = w1[k0 + k];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (j < per) {
+          const float cv = cov_s[k * KC + lane + 32 * j];
+          u0[j] = fmaf(a0, cv, u0[j]);
+          u1[j] = fmaf(a1, cv, u1[j]);
+        }
       }
     }
   }
   float q0 = 0.f, q1 = 0.f, m0 = 0.f, m1 = 0.f;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < 8; ++j) {
     if (j < per) {
       const int l = lane + 32 * j;
       q0 = fmaf(w0[l], u0[j], q0);
@@ -1431,6 +1482,22 @@ B2_API int b2_bn_finalize_nhwc(const float* sum, const float* sumsq, const float
 // form, see gram_stats_kernel) ; include/b200lrcn.h
 B2_API long b2_gram_workspace_floats(int C) { return (long)(kGramCopies + 1) * ((long)C * C + C); }
 
+template <int KC>
+int launch_gram(const CUtensorMap& ta, long M, const ATransform& at, float* workspace, cudaStream_t st) {
+  using G = GramLayout<KC>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2_CUDA_CHECK(cudaFuncSetAttribute(gram_stats_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::kSmem));
+    attr_set = true;
+  }
+  const int rows_per_super = KC == 64 ? 2 * BM : BM;
+  const int num_super = b2_ceil_div(M, rows_per_super);
+  const int grid = num_super < b2_num_sms() ? num_super : b2_num_sms();
+  gram_stats_kernel<KC><<<grid, kGramThreads, G::kSmem, st>>>(ta, (int)M, at, workspace);
+  B2_LAUNCH_CHECK("gram_stats_kernel");
+  return 0;
+}
+
 B2_API int b2_conv1x1_gram_bnstats_bf16(const void* x, long M, int C, const void* w, int Cout, const float* a_scale,
                                         const float* a_shift, int a_relu, float* workspace, float* col_sum,
                                         float* col_sumsq, const float* fin_gamma, const float* fin_beta,
@@ -1440,33 +1507,18 @@ B2_API int b2_conv1x1_gram_bnstats_bf16(const void* x, long M, int C, const void
   B2_ARG_CHECK(x && w && a_scale && a_shift && workspace && fin_gamma && fin_beta && fin_scale && fin_shift,
                "%s: null pointer", who);
   B2_ARG_CHECK(M > 0 && M < (1L << 31) && Cout > 0, "%s: empty or oversized shape", who);
-  B2_ARG_CHECK(C == 64 || C == 128, "%s: 64 or 128 input channels (got %d)", who, C);
+  B2_ARG_CHECK(C == 64 || C == 128 || C == 256, "%s: 64, 128 or 256 input channels (got %d)", who, C);
   B2_ARG_CHECK((col_sum == nullptr) == (col_sumsq == nullptr), "%s: col_sum and col_sumsq go together", who);
   B2_ARG_CHECK(((uintptr_t)x & 15) == 0 && ((uintptr_t)workspace & 15) == 0, "%s: x / workspace must be 16 B aligned", who);
   if (int r = load_driver_entry_points()) return r;
   cudaStream_t st = (cudaStream_t)stream;
   CUtensorMap ta;
   if (int r = make_tmap_2d(&ta, x, M, C, C, BM)) return r;
-  float* gram = workspace;
-  float* sum_a = workspace + (long)C * C;
   B2_CUDA_CHECK(cudaMemsetAsync(workspace, 0, (size_t)kGramCopies * ((size_t)C * C + C) * sizeof(float), st));
   ATransform at = {a_scale, a_shift, a_relu};
-  const int rows_per_super = C == 64 ? 2 * BM : BM;
-  const int num_super = b2_ceil_div(M, rows_per_super);
-  const int grid = num_super < b2_num_sms() ? num_super : b2_num_sms();
-  static bool attr_set = false;
-  if (!attr_set) {
-    B2_CUDA_CHECK(cudaFuncSetAttribute(gram_stats_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGramSmem));
-    B2_CUDA_CHECK(cudaFuncSetAttribute(gram_stats_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGramSmem));
-    B2_CUDA_CHECK(cudaFuncSetAttribute(gram_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (128 * 128 + 128 + kGramFinWarps * kGramFinPerWarp * 128) * 4));
-    attr_set = true;
-  }
-  if (C == 64)
-    gram_stats_kernel<64><<<grid, kGramThreads, kGramSmem, st>>>(ta, (int)M, at, gram, sum_a);
-  else
-    gram_stats_kernel<128><<<grid, kGramThreads, kGramSmem, st>>>(ta, (int)M, at, gram, sum_a);
-  B2_LAUNCH_CHECK("gram_stats_kernel");
+  int r = C == 64 ? launch_gram<64>(ta, M, at, workspace, st)
+                  : (C == 128 ? launch_gram<128>(ta, M, at, workspace, st) : launch_gram<256>(ta, M, at, workspace, st));
+  if (r) return r;
   BnFinal f = {};
   f.scale = fin_scale;
   f.shift = fin_shift;
@@ -1481,8 +1533,13 @@ B2_API int b2_conv1x1_gram_bnstats_bf16(const void* x, long M, int C, const void
   float* cov = workspace + (long)kGramCopies * ((long)C * C + C);      // centred covariance + mean vector
   gram_reduce_kernel<<<b2_ceil_div(C * C / 4, 256), 256, 0, st>>>(workspace, cov, C, f.inv_count);
   B2_LAUNCH_CHECK("gram_reduce_kernel");
-  gram_finalize_kernel<<<b2_ceil_div(Cout, kGramFinWarps * kGramFinPerWarp), 32 * kGramFinWarps,
-                         (size_t)(C * C + C + kGramFinWarps * kGramFinPerWarp * C) * sizeof(float), st>>>(
+  static bool fin_attr = false;
+  const size_t fin_smem = (size_t)(kGramFinChunk + 256 + kGramFinWarps * kGramFinPerWarp * 256) * sizeof(float);
+  if (!fin_attr) {
+    B2_CUDA_CHECK(cudaFuncSetAttribute(gram_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
+    fin_attr = true;
+  }
+  gram_finalize_kernel<<<b2_ceil_div(Cout, kGramFinWarps * kGramFinPerWarp), 32 * kGramFinWarps, fin_smem, st>>>(
       cov, (const bf16*)w, Cout, C, col_sum, col_sumsq, f, (float)M);
   B2_LAUNCH_CHECK("gram_finalize_kernel");
   return 0;

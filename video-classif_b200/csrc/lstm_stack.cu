@@ -40,6 +40,28 @@ struct StackGradParams {
   float* db[kMaxLayers];          // [4H]: gradient of b_ih (== gradient of b_hh)
 };
 
+// dst[r * dst_stride + k] = src[r * cols + k] for a dense [rows, cols] global matrix, by the whole block
+__device__ __forceinline__ void stage_rows(float* dst, const float* __restrict__ src, int rows, int cols, int dst_stride) {
+  const int total = rows * cols;
+  const int nt = blockDim.x;
+  for (int i0 = 0; i0 < total; i0 += 8 * nt) {
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int i = i0 + q * nt + threadIdx.x;
+      v[q] = i < total ? src[i] : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int i = i0 + q * nt + threadIdx.x;
+      if (i < total) {
+        const int r = i / cols;
+        dst[r * dst_stride + (i - r * cols)] = v[q];
+      }
+    }
+  }
+}
+
 template <int HP>   // HP >= H: register array size of a W_hh row
 __global__ void __launch_bounds__(4 * HP)
 lstm_stack_fwd_kernel(StackParams p) {
@@ -115,6 +137,7 @@ __global__ void __launch_bounds__(4 * HP)
 lstm_stack_bwd_kernel(StackParams p, StackGradParams g) {
   extern __shared__ float sm[];
   const int T = p.T, H = p.H, H4 = 4 * H;
+  constexpr int kWarps = 4 * HP / 32;
   float* xin_s = sm;                          // [T][kMaxIn]  input sequence of the current layer
   float* hout_s = xin_s + T * kMaxIn;         // [T][kMaxIn]  output sequence of the current layer (h_{t-1} lookups)
   float* dh_s = hout_s + T * kMaxIn;          // [T][kMaxIn]  incoming gradient of the output sequence
@@ -122,10 +145,16 @@ lstm_stack_bwd_kernel(StackParams p, StackGradParams g) {
   float* wih_s = dxs_s + T * kMaxIn;          // [4H][kMaxIn]
   float* whh_s = wih_s + 4 * HP * kMaxIn;     // [4H][HP]
   float* dg_s = whh_s + 4 * HP * HP;          // [4H]
+  float* part_s = dg_s + 4 * HP;              // [kWarps][2 * kMaxIn]: per-warp partial dh_{t-1} | dx_t
   const int j = threadIdx.x;
+  const int warp = j >> 5, lane = j & 31;
   const int b = blockIdx.x;
   const bool active = j < H4;
   const bool upd = j < H;
+  // rows of the gate-gradient vector this warp reduces over in the transposed products
+  const int rows_per_warp = (H4 + kWarps - 1) / kWarps;
+  const int r_begin = warp * rows_per_warp;
+  const int r_end = min(H4, r_begin + rows_per_warp);
   for (int i = j; i < T * H; i += blockDim.x) {
     const int t = i / H, k = i - t * H;
     dh_s[t * kMaxIn + k] = g.dout[((long)b * T + t) * H + k];
@@ -134,36 +163,31 @@ lstm_stack_bwd_kernel(StackParams p, StackGradParams g) {
     const int In = l == 0 ? p.In0 : H;
     const long lb = ((long)l * p.B + b) * T;
     __syncthreads();     // previous layer's use of the staging buffers is over
-    for (int i = j; i < T * In; i += blockDim.x) {
-      const int t = i / In, k = i - t * In;
-      xin_s[t * kMaxIn + k] = l == 0 ? p.x[((long)b * T + t) * In + k]
-                                     : p.out[((((long)(l - 1)) * p.B + b) * T + t) * H + k];
-    }
-    for (int i = j; i < T * H; i += blockDim.x) {
-      const int t = i / H, k = i - t * H;
-      hout_s[t * kMaxIn + k] = p.out[(lb + t) * H + k];
-    }
-    for (int i = j; i < H4 * In; i += blockDim.x) {
-      const int r = i / In, k = i - r * In;
-      wih_s[r * kMaxIn + k] = p.w_ih[l][i];
-    }
-    for (int i = j; i < H4 * H; i += blockDim.x) {
-      const int r = i / H, k = i - r * H;
-      whh_s[r * HP + k] = p.w_hh[l][i];
-    }
+    // staging: batches of 8 independent coalesced loads per thread (latency paid once per batch, not per element)
+    stage_rows(xin_s, l == 0 ? p.x + (long)b * T * In : p.out + (((long)(l - 1)) * p.B + b) * T * H, T, In, kMaxIn);
+    stage_rows(hout_s, p.out + lb * H, T, H, kMaxIn);
+    stage_rows(wih_s, p.w_ih[l], H4, In, kMaxIn);
+    stage_rows(whh_s, p.w_hh[l], H4, H, HP);
     float dwih[kMaxIn], dwhh[HP];
 #pragma unroll
     for (int k = 0; k < kMaxIn; ++k) dwih[k] = 0.f;
 #pragma unroll
     for (int k = 0; k < HP; ++k) dwhh[k] = 0.f;
     float dbias = 0.f, dc = 0.f, dh_rec = 0.f;
+    // saved gates / cell states of step t-1 are fetched while step t computes
+    float nig = 0.f, nfg = 0.f, ngg = 0.f, nog = 0.f, ncc = 0.f, ncp = 0.f;
+    auto fetch = [&](int t) {
+      const float* gp = p.gates + (lb + t) * H4;
+      nig = gp[j]; nfg = gp[H + j]; ngg = gp[2 * H + j]; nog = gp[3 * H + j];
+      ncc = p.cst[(lb + t) * H + j];
+      ncp = t > 0 ? p.cst[(lb + t - 1) * H + j] : 0.f;
+    };
+    if (upd) fetch(T - 1);
     __syncthreads();
     for (int t = T - 1; t >= 0; --t) {
       if (upd) {
-        const float* gp = p.gates + (lb + t) * H4;
-        const float ig = gp[j], fg = gp[H + j], gg = gp[2 * H + j], og = gp[3 * H + j];
-        const float cc = p.cst[(lb + t) * H + j];
-        const float cprev = t > 0 ? p.cst[(lb + t - 1) * H + j] : 0.f;
+        const float ig = nig, fg = nfg, gg = ngg, og = nog, cc = ncc, cprev = ncp;
+        if (t > 0) fetch(t - 1);
         const float dh = dh_s[t * kMaxIn + j] + dh_rec;
         const float tc = tanhf(cc);
         const float dct = dc + dh * og * (1.f - tc * tc);
@@ -188,17 +212,36 @@ lstm_stack_bwd_kernel(StackParams p, StackGradParams g) {
         }
         dbias += dgj;
       }
-      if (upd) {            // dh_{t-1}[k] = sum_j dG[j] W_hh[j][k]
-        float acc = 0.f;
-        for (int r = 0; r < H4; ++r) acc = fmaf(dg_s[r], whh_s[r * HP + j], acc);
-        dh_rec = acc;
-      }
-      if (j < In) {         // dx_t[k] = sum_j dG[j] W_ih[j][k]
-        float acc = 0.f;
-        for (int r = 0; r < H4; ++r) acc = fmaf(dg_s[r], wih_s[r * kMaxIn + j], acc);
-        dxs_s[t * kMaxIn + j] = acc;
+      {
+        // transposed products, split over the warps by gate row: dh_{t-1}[k] = sum_r dG[r] W_hh[r][k],
+        // dx_t[k] = sum_r dG[r] W_ih[r][k]; lane handles columns lane and lane + 32
+        float a0 = 0.f, a1 = 0.f, x0 = 0.f, x1 = 0.f;
+        for (int r = r_begin; r < r_end; ++r) {
+          const float d = dg_s[r];
+          a0 = fmaf(d, whh_s[r * HP + lane], a0);
+          if (HP > 32) a1 = fmaf(d, whh_s[r * HP + 32 + lane], a1);
+          x0 = fmaf(d, wih_s[r * kMaxIn + lane], x0);
+          x1 = fmaf(d, wih_s[r * kMaxIn + 32 + lane], x1);
+        }
+        float* ps = part_s + warp * 2 * kMaxIn;
+        ps[lane] = a0;
+        ps[32 + lane] = a1;
+        ps[kMaxIn + lane] = x0;
+        ps[kMaxIn + 32 + lane] = x1;
       }
       __syncthreads();
+      if (upd) {
+        float acc = 0.f;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) acc += part_s[w * 2 * kMaxIn + j];
+        dh_rec = acc;
+      }
+      if (j < In) {
+        float acc = 0.f;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) acc += part_s[w * 2 * kMaxIn + kMaxIn + j];
+        dxs_s[t * kMaxIn + j] = acc;
+      }
     }
     if (active) {
 #pragma unroll
@@ -209,6 +252,7 @@ lstm_stack_bwd_kernel(StackParams p, StackGradParams g) {
         if (k < H) atomicAdd(g.dw_hh[l] + (long)j * H + k, dwhh[k]);
       atomicAdd(g.db[l] + j, dbias);
     }
+    __syncthreads();      // dxs_s complete
     if (l == 0) {
       if (g.dx != nullptr)
         for (int i = j; i < T * In; i += blockDim.x) {
@@ -297,10 +341,10 @@ B2_API int b2_lstm_stack_bwd(const float* dout, const float* x, int In0, const v
     attr = true;
   }
   if (H <= 32) {
-    const size_t smem = (size_t)(4 * T * kMaxIn + 4 * 32 * kMaxIn + 4 * 32 * 32 + 4 * 32) * sizeof(float);
+    const size_t smem = (size_t)(4 * T * kMaxIn + 4 * 32 * kMaxIn + 4 * 32 * 32 + 4 * 32 + 4 * 2 * kMaxIn) * sizeof(float);
     lstm_stack_bwd_kernel<32><<<B, 128, smem, st>>>(p, g);
   } else {
-    const size_t smem = (size_t)(4 * T * kMaxIn + 4 * 64 * kMaxIn + 4 * 64 * 64 + 4 * 64) * sizeof(float);
+    const size_t smem = (size_t)(4 * T * kMaxIn + 4 * 64 * kMaxIn + 4 * 64 * 64 + 4 * 64 + 8 * 2 * kMaxIn) * sizeof(float);
     B2_ARG_CHECK(smem <= 220 * 1024, "%s: T=%d too long for the shared-memory staging at H=%d", who, T, H);
     lstm_stack_bwd_kernel<64><<<B, 256, smem, st>>>(p, g);
   }

@@ -39,6 +39,7 @@ struct StemGeom {
   int tiles_per_img;
   int even_bytes, odd_bytes, stage_bytes;
   long img_units;        // 2 * Hq * Wq
+  uint32_t magic_wq, magic_tpi;   // ceil(2^32 / d): u / d == __umulhi(u, magic) for u < 2^32 / d (checked on the host)
 };
 
 __host__ __device__ inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
@@ -55,6 +56,8 @@ StemGeom make_geom(int N, int H, int W) {
   g.odd_bytes = (2 * g.Wq + 131) * 16;
   g.stage_bytes = align_up(g.even_bytes, 128) + align_up(g.odd_bytes, 128);
   g.img_units = 2L * g.Hq * g.Wq;
+  g.magic_wq = (uint32_t)(((1ull << 32) + g.Wq - 1) / g.Wq);
+  g.magic_tpi = (uint32_t)(((1ull << 32) + g.tiles_per_img - 1) / g.tiles_per_img);
   return g;
 }
 
@@ -109,10 +112,10 @@ stem_conv_kernel(const uint4* __restrict__ xp, const uint4* __restrict__ wk, bf1
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* w_bar = tempty_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
-  float* stat_s = reinterpret_cast<float*>(after + 128);            // [4 quarters][2][64]
-  uint8_t* staging_s = after + 128 + 4 * 2 * kCout * 4;            // kEpiWarps x kStgBytes
+  float* stat_s = reinterpret_cast<float*>(after + 128);            // [4 quarters x 2 half-warps][2][64]
+  uint8_t* staging_s = after + 128 + 8 * 2 * kCout * 4;            // kEpiWarps x kStgBytes
   const bool want_stats = col_sum != nullptr;
-  for (int i = threadIdx.x; i < 8 * kCout; i += kThreads) stat_s[i] = 0.f;
+  for (int i = threadIdx.x; i < 16 * kCout; i += kThreads) stat_s[i] = 0.f;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -148,7 +151,7 @@ stem_conv_kernel(const uint4* __restrict__ xp, const uint4* __restrict__ wk, bf1
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int img = tile / g.tiles_per_img;
+        const int img = g.tiles_per_img == 1 ? tile : (int)__umulhi((uint32_t)tile, g.magic_tpi);
         const int u0 = (tile - img * g.tiles_per_img) * 128;
         const uint4* src_even = xp + (long)img * g.img_units + u0;
         const uint4* src_odd = src_even + (long)g.Hq * g.Wq;
@@ -206,9 +209,9 @@ stem_conv_kernel(const uint4* __restrict__ xp, const uint4* __restrict__ wk, bf1
     uint8_t* stg = staging_s + (warp - 2) * kStgBytes;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int img = tile / g.tiles_per_img;
+      const int img = g.tiles_per_img == 1 ? tile : (int)__umulhi((uint32_t)tile, g.magic_tpi);
       const int u = (tile - img * g.tiles_per_img) * 128 + quarter * 32 + lane;
-      const int p = u / g.Wq;
+      const int p = (int)__umulhi((uint32_t)u, g.magic_wq);
       const int q = u - p * g.Wq;
       const bool row_ok = p < g.P && q < g.Q;
       const int acc = it & 1;
@@ -261,17 +264,11 @@ stem_conv_kernel(const uint4* __restrict__ xp, const uint4* __restrict__ wk, bf1
           s2a = __ffma2_rn(x0, x0, s2a);
           s2b = __ffma2_rn(x1, x1, s2b);
         }
-        float2 t1 = __fadd2_rn(s1a, s1b), t2 = __fadd2_rn(s2a, s2b);
-        t1.x += __shfl_xor_sync(0xffffffffu, t1.x, 16);
-        t1.y += __shfl_xor_sync(0xffffffffu, t1.y, 16);
-        t2.x += __shfl_xor_sync(0xffffffffu, t2.x, 16);
-        t2.y += __shfl_xor_sync(0xffffffffu, t2.y, 16);
-        if (sw_hf == 0) {
-          float2* st = reinterpret_cast<float2*>(stat_s + quarter * 2 * kCout + ch * 32 + 2 * sw_w);
-          float2* st2 = reinterpret_cast<float2*>(stat_s + quarter * 2 * kCout + kCout + ch * 32 + 2 * sw_w);
-          *st = __fadd2_rn(*st, t1);
-          *st2 = __fadd2_rn(*st2, t2);
-        }
+        // each half-warp owns its own copy of the statistics (no shuffle, no atomics: one writer per slot)
+        float2* st = reinterpret_cast<float2*>(stat_s + (quarter * 2 + sw_hf) * 2 * kCout + ch * 32 + 2 * sw_w);
+        float2* st2 = reinterpret_cast<float2*>(stat_s + (quarter * 2 + sw_hf) * 2 * kCout + kCout + ch * 32 + 2 * sw_w);
+        *st = __fadd2_rn(*st, __fadd2_rn(s1a, s1b));
+        *st2 = __fadd2_rn(*st2, __fadd2_rn(s2a, s2b));
         __syncwarp();
       }
     }
@@ -281,9 +278,14 @@ stem_conv_kernel(const uint4* __restrict__ xp, const uint4* __restrict__ wk, bf1
   __syncthreads();
   if (want_stats) {
     for (int c = threadIdx.x; c < kCout; c += kThreads) {
-      atomicAdd(col_sum + c, stat_s[c] + stat_s[2 * kCout + c] + stat_s[4 * kCout + c] + stat_s[6 * kCout + c]);
-      atomicAdd(col_sumsq + c,
-                stat_s[kCout + c] + stat_s[3 * kCout + c] + stat_s[5 * kCout + c] + stat_s[7 * kCout + c]);
+      float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+      for (int qq = 0; qq < 8; ++qq) {
+        a1 += stat_s[qq * 2 * kCout + c];
+        a2 += stat_s[qq * 2 * kCout + kCout + c];
+      }
+      atomicAdd(col_sum + c, a1);
+      atomicAdd(col_sumsq + c, a2);
     }
   }
   if (warp == 1) {
@@ -293,7 +295,7 @@ stem_conv_kernel(const uint4* __restrict__ xp, const uint4* __restrict__ wk, bf1
 }
 
 int stem_smem_bytes(const StemGeom& g) {
-  return kWBytes + kStages * g.stage_bytes + 128 + 4 * 2 * kCout * 4 + kEpiWarps * kStgBytes + 256;
+  return kWBytes + kStages * g.stage_bytes + 128 + 8 * 2 * kCout * 4 + kEpiWarps * kStgBytes + 256;
 }
 
 }  // namespace
@@ -329,6 +331,9 @@ B2_API int b2_stem_conv_bf16(const void* xp, const void* wk, void* y, int N, int
   const int smem = stem_smem_bytes(g);
   B2_ARG_CHECK(smem <= 227 * 1024, "b2_stem_conv_bf16: frame width %d too large for the shared-memory stage", W);
   B2_ARG_CHECK((long)g.N * g.tiles_per_img < (1L << 31), "b2_stem_conv_bf16: too many tiles");
+  B2_ARG_CHECK((unsigned long)g.N * g.tiles_per_img * g.tiles_per_img < (1ul << 32) &&
+                   (unsigned long)(g.tiles_per_img * 128 + 128) * g.Wq < (1ul << 32),
+               "b2_stem_conv_bf16: shape outside the multiply-high division range");
   static int attr_smem = 0;
   if (smem > attr_smem) {
     B2_CUDA_CHECK(cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

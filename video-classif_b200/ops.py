@@ -89,7 +89,7 @@ def conv2d_bn_nhwc(x, w, stride, pad, a=None, a_relu=True, o=None, res=None, r=N
 def conv1x1_gram_bnstats(x, w, a, fin, stats=None, a_relu=True):
     """b2_conv1x1_gram_bnstats_bf16: train-mode BatchNorm statistics + finalisation of the 1x1 convolution
     relu?(x*a_scale+a_shift) @ w^T without computing its output (Gram-matrix form, one pass over x).
-    x [..., C] bf16 (C = 64 or 128), w [Cout, (1, 1,) C] bf16; a = (scale, shift); fin as in conv2d_bn_nhwc;
+    x [..., C] bf16 (C in GRAM_CHANNELS), w [Cout, (1, 1,) C] bf16; a = (scale, shift); fin as in conv2d_bn_nhwc;
     stats = optional (sum, sumsq) outputs (overwritten)."""
     _chk(x, w)
     C = x.shape[-1]
@@ -98,12 +98,12 @@ def conv1x1_gram_bnstats(x, w, a, fin, stats=None, a_relu=True):
     ws = torch.empty(_lib.lib().b2_gram_workspace_floats(C), device=x.device, dtype=F32)
     s1, s2 = stats if stats is not None else (None, None)
     g, b, rm, rv, fs, fh, _cnt, eps, mom = fin
-    call("b2_conv1x1_gram_bnstats_bf16", x.data_ptr(), M, C, w.data_ptr(), Cout, a[0].data_ptr(), a[1].data_ptr(),
-         int(a_relu), ws.data_ptr(), ptr(s1), ptr(s2), g.data_ptr(), b.data_ptr(), ptr(rm), ptr(rv), fs.data_ptr(),
-         fh.data_ptr(), float(eps), float(mom), stream_ptr())
+    call("b2_conv1x1_gram_bnstats_bf16", x.data_ptr(), M, C, w.data_ptr(), Cout, ptr(a[0]), ptr(a[1]),
+         int(a_relu), ws.data_ptr(), ptr(s1), ptr(s2), g.data_ptr(), b.data_ptr(), ptr(rm), ptr(rv), ptr(fs),
+         ptr(fh), float(eps), float(mom), stream_ptr())
 
 
-GRAM_CHANNELS = (64, 128)
+GRAM_CHANNELS = (64, 128, 256)
 
 
 def scale_shift_apply(x, scale, shift, res=None, r=None, relu=True, out=None):
@@ -112,7 +112,7 @@ def scale_shift_apply(x, scale, shift, res=None, r=None, relu=True, out=None):
     C = x.shape[-1]
     out = x if out is None else out
     r0, r1 = r if r is not None else (None, None)
-    call("b2_scale_shift_apply_nhwc", x.data_ptr(), out.data_ptr(), x.numel() // C, C, scale.data_ptr(), shift.data_ptr(),
+    call("b2_scale_shift_apply_nhwc", x.data_ptr(), out.data_ptr(), x.numel() // C, C, ptr(scale), ptr(shift),
          ptr(res), ptr(r0), ptr(r1), int(relu), stream_ptr())
     return out
 
