@@ -1290,16 +1290,40 @@ gram_reduce_kernel(const float* __restrict__ ws, float* __restrict__ cov, int KC
 
 constexpr int kGramFinWarps = 8;
 constexpr int kGramFinPerWarp = 2;       // output channels per warp
-constexpr int kGramFinChunk = 16384;     // floats of Cov staged in shared memory at a time (64 KB)
+constexpr int kGramFinRows = 64;         // Cov rows per CTA (grid.y = K / 64 row chunks: partial quadratic forms)
+// grid = (ceil(N / 16), K / 64).  CTA (nb, kc) stages Cov rows [64 kc, 64 kc + 64) and adds
+//   q_n += sum_{k in chunk} sum_l w_k Cov[k][l] w_l      (the quadratic form is linear in the row chunk)
+// into acc[n]; the last chunk-CTA of a channel block (counter) turns (mean, var) into the BatchNorm coefficients.
+// acc [N] and counters [gridDim.x] are zeroed by the caller.
 __global__ void __launch_bounds__(32 * kGramFinWarps)
-gram_finalize_kernel(const float* __restrict__ cov, const bf16* __restrict__ W, int N, int KC, float* __restrict__ col_sum,
-                     float* __restrict__ col_sumsq, BnFinal f, float count) {
-  extern __shared__ float gsm[];             // Cov rows [chunk], mean [KC], weight rows [warps][2][KC]
+gram_finalize_kernel(const float* __restrict__ cov, const bf16* __restrict__ W, int N, int KC, float* __restrict__ acc,
+                     unsigned int* __restrict__ counters, float* __restrict__ col_sum, float* __restrict__ col_sumsq,
+                     BnFinal f, float count) {
+  extern __shared__ float gsm[];             // Cov rows [64][KC], mean [KC], weight rows [warps][2][KC]
   float* cov_s = gsm;
-  float* m_s = gsm + kGramFinChunk;
+  float* m_s = gsm + kGramFinRows * KC;
   float* w_s = m_s + KC;
+  __shared__ int is_last;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = (blockIdx.x * kGramFinWarps + warp) * kGramFinPerWarp;
+  const int k0 = blockIdx.y * kGramFinRows;
+  const int rows = min(kGramFinRows, KC - k0);
+  // staging: batches of 8 independent float4 loads per thread
+  const float4* src = reinterpret_cast<const float4*>(cov + (long)k0 * KC);
+  const int n4 = rows * KC / 4;
+  for (int i0 = 0; i0 < n4; i0 += 8 * 32 * kGramFinWarps) {
+    float4 v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int i = i0 + q * 32 * kGramFinWarps + threadIdx.x;
+      v[q] = i < n4 ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int i = i0 + q * 32 * kGramFinWarps + threadIdx.x;
+      if (i < n4) reinterpret_cast<float4*>(cov_s)[i] = v[q];
+    }
+  }
   float* w0 = w_s + (warp * kGramFinPerWarp) * KC;
   float* w1 = w0 + KC;
   for (int l = lane; l < KC; l += 32) {
@@ -1307,45 +1331,53 @@ gram_finalize_kernel(const float* __restrict__ cov, const bf16* __restrict__ W, 
     w1[l] = (n0 + 1 < N) ? __bfloat162float(W[(long)(n0 + 1) * KC + l]) : 0.f;
   }
   for (int i = threadIdx.x; i < KC; i += blockDim.x) m_s[i] = cov[KC * KC + i];
+  __syncthreads();
   const int per = KC / 32;                   // 2, 4 or 8 columns of Cov per lane
-  const int rows = kGramFinChunk / KC < KC ? kGramFinChunk / KC : KC;     // Cov rows per staged chunk
   float u0[8], u1[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) u0[j] = u1[j] = 0.f;
-  for (int k0 = 0; k0 < KC; k0 += rows) {
-    __syncthreads();
-    for (int i4 = threadIdx.x; i4 < rows * KC / 4; i4 += blockDim.x)
-      reinterpret_cast<float4*>(cov_s)[i4] = __ldg(reinterpret_cast<const float4*>(cov + (long)k0 * KC) + i4);
-    __syncthreads();
 #pragma unroll 4
-    for (int k = 0; k < rows; ++k) {
-      const float a0 = w0[k0 + k], a1 = w1[k0 + k];
+  for (int k = 0; k < rows; ++k) {
+    const float a0 = w0[k0 + k], a1 = w1[k0 + k];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (j < per) {
-          const float cv = cov_s[k * KC + lane + 32 * j];
-          u0[j] = fmaf(a0, cv, u0[j]);
-          u1[j] = fmaf(a1, cv, u1[j]);
-        }
+    for (int j = 0; j < 8; ++j) {
+      if (j < per) {
+        const float cv = cov_s[k * KC + lane + 32 * j];
+        u0[j] = fmaf(a0, cv, u0[j]);
+        u1[j] = fmaf(a1, cv, u1[j]);
       }
     }
   }
-  float q0 = 0.f, q1 = 0.f, m0 = 0.f, m1 = 0.f;
+  float q0 = 0.f, q1 = 0.f;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     if (j < per) {
       const int l = lane + 32 * j;
       q0 = fmaf(w0[l], u0[j], q0);
       q1 = fmaf(w1[l], u1[j], q1);
-      m0 = fmaf(w0[l], m_s[l], m0);
-      m1 = fmaf(w1[l], m_s[l], m1);
     }
   }
-  q0 = warp_sum(q0); q1 = warp_sum(q1); m0 = warp_sum(m0); m1 = warp_sum(m1);
+  q0 = warp_sum(q0);
+  q1 = warp_sum(q1);
+  if (lane < kGramFinPerWarp && n0 + lane < N) atomicAdd(acc + n0 + lane, lane == 0 ? q0 : q1);
+  // ---- the last row-chunk CTA of this channel block finalises its channels
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(counters + blockIdx.x, 1u) == gridDim.y - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  float m0 = 0.f, m1 = 0.f;
+  for (int l = lane; l < KC; l += 32) {
+    m0 = fmaf(w0[l], m_s[l], m0);
+    m1 = fmaf(w1[l], m_s[l], m1);
+  }
+  m0 = warp_sum(m0);
+  m1 = warp_sum(m1);
   if (lane < kGramFinPerWarp && n0 + lane < N) {
     const int n = n0 + lane;
     const float mean = lane == 0 ? m0 : m1;
-    const float var = fmaxf(lane == 0 ? q0 : q1, 0.f);
+    const float var = fmaxf(__ldcg(acc + n), 0.f);
     if (col_sum != nullptr) {
       col_sum[n] = mean * count;
       col_sumsq[n] = (var + mean * mean) * count;
@@ -1480,7 +1512,10 @@ B2_API int b2_bn_finalize_nhwc(const float* sum, const float* sumsq, const float
 
 // BatchNorm statistics + finalisation of a 1x1 convolution's output WITHOUT computing the output (Gram-matrix
 // form, see gram_stats_kernel) ; include/b200lrcn.h
-B2_API long b2_gram_workspace_floats(int C) { return (long)(kGramCopies + 1) * ((long)C * C + C); }
+// [kGramCopies x (K*K + K)] partial Gram / sums | [4096] per-channel accumulators | [256] channel-block counters |
+// [K*K + K] centred covariance + mean
+constexpr int kGramMaxCout = 4096;
+B2_API long b2_gram_workspace_floats(int C) { return (long)(kGramCopies + 1) * ((long)C * C + C) + kGramMaxCout + 256; }
 
 template <int KC>
 int launch_gram(const CUtensorMap& ta, long M, const ATransform& at, float* workspace, cudaStream_t st) {
@@ -1506,7 +1541,7 @@ B2_API int b2_conv1x1_gram_bnstats_bf16(const void* x, long M, int C, const void
   const char* who = "b2_conv1x1_gram_bnstats_bf16";
   B2_ARG_CHECK(x && w && a_scale && a_shift && workspace && fin_gamma && fin_beta && fin_scale && fin_shift,
                "%s: null pointer", who);
-  B2_ARG_CHECK(M > 0 && M < (1L << 31) && Cout > 0, "%s: empty or oversized shape", who);
+  B2_ARG_CHECK(M > 0 && M < (1L << 31) && Cout > 0 && Cout <= kGramMaxCout, "%s: empty or oversized shape", who);
   B2_ARG_CHECK(C == 64 || C == 128 || C == 256, "%s: 64, 128 or 256 input channels (got %d)", who, C);
   B2_ARG_CHECK((col_sum == nullptr) == (col_sumsq == nullptr), "%s: col_sum and col_sumsq go together", who);
   B2_ARG_CHECK(((uintptr_t)x & 15) == 0 && ((uintptr_t)workspace & 15) == 0, "%s: x / workspace must be 16 B aligned", who);
@@ -1514,7 +1549,9 @@ B2_API int b2_conv1x1_gram_bnstats_bf16(const void* x, long M, int C, const void
   cudaStream_t st = (cudaStream_t)stream;
   CUtensorMap ta;
   if (int r = make_tmap_2d(&ta, x, M, C, C, BM)) return r;
-  B2_CUDA_CHECK(cudaMemsetAsync(workspace, 0, (size_t)kGramCopies * ((size_t)C * C + C) * sizeof(float), st));
+  // one memset: the partial accumulators and the finalisation accumulators / counters are adjacent
+  float* fin_acc = workspace + (long)kGramCopies * ((long)C * C + C);
+  B2_CUDA_CHECK(cudaMemsetAsync(workspace, 0, ((size_t)kGramCopies * ((size_t)C * C + C) + kGramMaxCout + 256) * sizeof(float), st));
   ATransform at = {a_scale, a_shift, a_relu};
   int r = C == 64 ? launch_gram<64>(ta, M, at, workspace, st)
                   : (C == 128 ? launch_gram<128>(ta, M, at, workspace, st) : launch_gram<256>(ta, M, at, workspace, st));
@@ -1530,17 +1567,19 @@ B2_API int b2_conv1x1_gram_bnstats_bf16(const void* x, long M, int C, const void
   f.unbias = M > 1 ? (float)((double)M / ((double)M - 1.0)) : 1.f;
   f.eps = eps;
   f.momentum = momentum;
-  float* cov = workspace + (long)kGramCopies * ((long)C * C + C);      // centred covariance + mean vector
+  float* cov = fin_acc + kGramMaxCout + 256;                           // centred covariance + mean vector
   gram_reduce_kernel<<<b2_ceil_div(C * C / 4, 256), 256, 0, st>>>(workspace, cov, C, f.inv_count);
   B2_LAUNCH_CHECK("gram_reduce_kernel");
   static bool fin_attr = false;
-  const size_t fin_smem = (size_t)(kGramFinChunk + 256 + kGramFinWarps * kGramFinPerWarp * 256) * sizeof(float);
+  const size_t fin_smem = (size_t)(kGramFinRows * 256 + 256 + kGramFinWarps * kGramFinPerWarp * 256) * sizeof(float);
   if (!fin_attr) {
     B2_CUDA_CHECK(cudaFuncSetAttribute(gram_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
     fin_attr = true;
   }
-  gram_finalize_kernel<<<b2_ceil_div(Cout, kGramFinWarps * kGramFinPerWarp), 32 * kGramFinWarps, fin_smem, st>>>(
-      cov, (const bf16*)w, Cout, C, col_sum, col_sumsq, f, (float)M);
+  dim3 fgrid(b2_ceil_div(Cout, kGramFinWarps * kGramFinPerWarp), b2_ceil_div(C, kGramFinRows));
+  gram_finalize_kernel<<<fgrid, 32 * kGramFinWarps, (size_t)(kGramFinRows * C + C + kGramFinWarps * kGramFinPerWarp * C) * sizeof(float), st>>>(
+      cov, (const bf16*)w, Cout, C, fin_acc, reinterpret_cast<unsigned int*>(fin_acc + kGramMaxCout), col_sum, col_sumsq, f,
+      (float)M);
   B2_LAUNCH_CHECK("gram_finalize_kernel");
   return 0;
 }

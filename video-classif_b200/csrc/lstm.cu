@@ -74,10 +74,10 @@ lstm_fwd_kernel(const float* __restrict__ G, const float* __restrict__ Whh, floa
       const float* p = pre_s + ub * H4;
       const float ig = sigmoidf_(p[uk]);
       const float fg = sigmoidf_(p[H + uk]);
-      const float gg = tanhf(p[2 * H + uk]);
+      const float gg = tanhf_(p[2 * H + uk]);
       const float og = sigmoidf_(p[3 * H + uk]);
       c = fg * c + ig * gg;
-      const float h = og * tanhf(c);
+      const float h = og * tanhf_(c);
       h_s[ub * H + uk] = h;
       const long bt = (long)(b0 + ub) * T + t;
       out[bt * out_ld + uk] = h;
@@ -148,7 +148,7 @@ lstm_bwd_kernel(const float* __restrict__ dout, long dout_ld, const float* __res
       const float cc = cur.cc;
       const float cprev = cur.cprev;
       const float dh = cur.dout + dh_rec;
-      const float tc = tanhf(cc);
+      const float tc = tanhf_(cc);
       const float dct = dc + dh * og * (1.f - tc * tc);
       float* d = dg_s + ub * H4;
       const float di = dct * gg * ig * (1.f - ig);

@@ -75,10 +75,11 @@ lstm_stack_fwd_kernel(StackParams p) {
   const int b = blockIdx.x;
   const bool active = j < H4;
   const bool upd = j < H;
-  for (int i = j; i < T * p.In0; i += blockDim.x) {
-    const int t = i / p.In0, k = i - t * p.In0;
-    seq_a[t * kMaxIn + k] = p.x[((long)b * T + t) * p.In0 + k];
-  }
+  // padding columns must read as zero: the dot products below run over whole float4 groups
+  for (int i = j; i < 2 * T * kMaxIn; i += blockDim.x) seq_a[i] = 0.f;
+  for (int i = j; i < HP; i += blockDim.x) h_s[i] = 0.f;
+  __syncthreads();
+  stage_rows(seq_a, p.x + (long)b * T * p.In0, T, p.In0, kMaxIn);
   int In = p.In0;
   for (int l = 0; l < p.layers; ++l) {
     float wih[kMaxIn], whh[HP];
@@ -93,24 +94,51 @@ lstm_stack_fwd_kernel(StackParams p) {
     const long lb = ((long)l * p.B + b) * T;
     for (int t = 0; t < T; ++t) {
       if (active) {
-        float acc = bias;
-        const float* xt = seq_a + t * kMaxIn;
+        // 128-bit broadcast loads, four in flight, four independent partial sums (with scalar loads the
+        // compiler recycled one destination register and every element paid a full LDS latency: 2.2 us / step)
+        float acc[4] = {bias, 0.f, 0.f, 0.f};
+        const float4* xt4 = reinterpret_cast<const float4*>(seq_a + t * kMaxIn);
 #pragma unroll
-        for (int k = 0; k < kMaxIn; ++k)
-          if (k < In) acc = fmaf(wih[k], xt[k], acc);
+        for (int k0 = 0; k0 < kMaxIn; k0 += 16) {
+          if (k0 < In) {
+            float4 v[4];
 #pragma unroll
-        for (int k = 0; k < HP; ++k)
-          if (k < H) acc = fmaf(whh[k], h_s[k], acc);
-        pre_s[j] = acc;
+            for (int q = 0; q < 4; ++q) v[q] = xt4[k0 / 4 + q];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              acc[0] = fmaf(wih[k0 + 4 * q], v[q].x, acc[0]);
+              acc[1] = fmaf(wih[k0 + 4 * q + 1], v[q].y, acc[1]);
+              acc[2] = fmaf(wih[k0 + 4 * q + 2], v[q].z, acc[2]);
+              acc[3] = fmaf(wih[k0 + 4 * q + 3], v[q].w, acc[3]);
+            }
+          }
+        }
+        const float4* h4 = reinterpret_cast<const float4*>(h_s);
+#pragma unroll
+        for (int k0 = 0; k0 < HP; k0 += 16) {
+          if (k0 < H) {
+            float4 v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[q] = h4[k0 / 4 + q];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              acc[0] = fmaf(whh[k0 + 4 * q], v[q].x, acc[0]);
+              acc[1] = fmaf(whh[k0 + 4 * q + 1], v[q].y, acc[1]);
+              acc[2] = fmaf(whh[k0 + 4 * q + 2], v[q].z, acc[2]);
+              acc[3] = fmaf(whh[k0 + 4 * q + 3], v[q].w, acc[3]);
+            }
+          }
+        }
+        pre_s[j] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
       }
       __syncthreads();
       if (upd) {
         const float ig = sigmoidf_(pre_s[j]);
         const float fg = sigmoidf_(pre_s[H + j]);
-        const float gg = tanhf(pre_s[2 * H + j]);
+        const float gg = tanhf_(pre_s[2 * H + j]);
         const float og = sigmoidf_(pre_s[3 * H + j]);
         c = fg * c + ig * gg;
-        const float h = og * tanhf(c);
+        const float h = og * tanhf_(c);
         h_s[j] = h;
         seq_b[t * kMaxIn + j] = h;
         p.out[(lb + t) * H + j] = h;
@@ -155,6 +183,7 @@ lstm_stack_bwd_kernel(StackParams p, StackGradParams g) {
   const int rows_per_warp = (H4 + kWarps - 1) / kWarps;
   const int r_begin = warp * rows_per_warp;
   const int r_end = min(H4, r_begin + rows_per_warp);
+  for (int i = j; i < 2 * T * kMaxIn; i += blockDim.x) xin_s[i] = 0.f;     // xin_s | hout_s: zero padding columns
   for (int i = j; i < T * H; i += blockDim.x) {
     const int t = i / H, k = i - t * H;
     dh_s[t * kMaxIn + k] = g.dout[((long)b * T + t) * H + k];
@@ -189,7 +218,7 @@ lstm_stack_bwd_kernel(StackParams p, StackGradParams g) {
         const float ig = nig, fg = nfg, gg = ngg, og = nog, cc = ncc, cprev = ncp;
         if (t > 0) fetch(t - 1);
         const float dh = dh_s[t * kMaxIn + j] + dh_rec;
-        const float tc = tanhf(cc);
+        const float tc = tanhf_(cc);
         const float dct = dc + dh * og * (1.f - tc * tc);
         dg_s[j] = dct * gg * ig * (1.f - ig);
         dg_s[H + j] = dct * cprev * fg * (1.f - fg);
@@ -200,15 +229,39 @@ lstm_stack_bwd_kernel(StackParams p, StackGradParams g) {
       __syncthreads();
       if (active) {
         const float dgj = dg_s[j];
-        const float* xt = xin_s + t * kMaxIn;
+        const float4* xt4 = reinterpret_cast<const float4*>(xin_s + t * kMaxIn);
 #pragma unroll
-        for (int k = 0; k < kMaxIn; ++k)
-          if (k < In) dwih[k] = fmaf(dgj, xt[k], dwih[k]);
+        for (int k0 = 0; k0 < kMaxIn; k0 += 16) {
+          if (k0 < In) {
+            float4 v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[q] = xt4[k0 / 4 + q];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              dwih[k0 + 4 * q] = fmaf(dgj, v[q].x, dwih[k0 + 4 * q]);
+              dwih[k0 + 4 * q + 1] = fmaf(dgj, v[q].y, dwih[k0 + 4 * q + 1]);
+              dwih[k0 + 4 * q + 2] = fmaf(dgj, v[q].z, dwih[k0 + 4 * q + 2]);
+              dwih[k0 + 4 * q + 3] = fmaf(dgj, v[q].w, dwih[k0 + 4 * q + 3]);
+            }
+          }
+        }
         if (t > 0) {
-          const float* hp = hout_s + (t - 1) * kMaxIn;
+          const float4* hp4 = reinterpret_cast<const float4*>(hout_s + (t - 1) * kMaxIn);
 #pragma unroll
-          for (int k = 0; k < HP; ++k)
-            if (k < H) dwhh[k] = fmaf(dgj, hp[k], dwhh[k]);
+          for (int k0 = 0; k0 < HP; k0 += 16) {
+            if (k0 < H) {
+              float4 v[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) v[q] = hp4[k0 / 4 + q];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                dwhh[k0 + 4 * q] = fmaf(dgj, v[q].x, dwhh[k0 + 4 * q]);
+                dwhh[k0 + 4 * q + 1] = fmaf(dgj, v[q].y, dwhh[k0 + 4 * q + 1]);
+                dwhh[k0 + 4 * q + 2] = fmaf(dgj, v[q].z, dwhh[k0 + 4 * q + 2]);
+                dwhh[k0 + 4 * q + 3] = fmaf(dgj, v[q].w, dwhh[k0 + 4 * q + 3]);
+              }
+            }
+          }
         }
         dbias += dgj;
       }
@@ -216,6 +269,7 @@ lstm_stack_bwd_kernel(StackParams p, StackGradParams g) {
         // transposed products, split over the warps by gate row: dh_{t-1}[k] = sum_r dG[r] W_hh[r][k],
         // dx_t[k] = sum_r dG[r] W_ih[r][k]; lane handles columns lane and lane + 32
         float a0 = 0.f, a1 = 0.f, x0 = 0.f, x1 = 0.f;
+#pragma unroll 8
         for (int r = r_begin; r < r_end; ++r) {
           const float d = dg_s[r];
           a0 = fmaf(d, whh_s[r * HP + lane], a0);

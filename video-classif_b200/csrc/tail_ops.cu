@@ -119,7 +119,7 @@ act_ln_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ pre,
 }
 
 // ---- fp32 SIMT GEMM: C[M,N] = alpha * op(A)[M,K] op(B)[K,N] + beta * C, row-major ----
-constexpr int TS = 64, TK = 16;
+constexpr int TS = 64, TK = 32;
 template <bool TA, bool TB>
 __global__ void __launch_bounds__(256)
 sgemm_kernel(int M, int N, int K, float alpha, const float* __restrict__ A, long lda, const float* __restrict__ B,
@@ -135,24 +135,34 @@ sgemm_kernel(int M, int N, int K, float alpha, const float* __restrict__ A, long
   const int k_end = min(K, k_begin + k_per_split);
   const bool split = gridDim.z > 1;
   float acc[4][4] = {};
-  for (int k0 = k_begin; k0 < k_end; k0 += TK) {
-    for (int i = threadIdx.x; i < TS * TK; i += 256) {
+  // software pipeline: the global loads of k-tile i+1 are in flight (registers) while tile i is multiplied --
+  // the skinny LRCN products (64 x 128 outputs, K = 256..1024) run on 1-4 CTAs and were pure load latency
+  constexpr int kPer = TS * TK / 256;       // elements of each operand tile per thread
+  float ra[kPer], rb[kPer];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+      const int i = threadIdx.x + q * 256;
       int m, k;
       if (TA) { m = i % TS; k = i / TS; } else { k = i % TK; m = i / TK; }
       const int gm = m0 + m, gk = k0 + k;
-      float v = 0.f;
-      if (gm < M && gk < k_end) v = TA ? A[(long)gk * lda + gm] : A[(long)gm * lda + gk];
-      As[k][m] = v;
+      ra[q] = (gm < M && gk < k_end) ? (TA ? A[(long)gk * lda + gm] : A[(long)gm * lda + gk]) : 0.f;
+      int n, kk;
+      if (TB) { kk = i % TK; n = i / TK; } else { n = i % TS; kk = i / TS; }
+      const int gn = n0 + n, gk2 = k0 + kk;
+      rb[q] = (gn < N && gk2 < k_end) ? (TB ? B[(long)gn * ldb + gk2] : B[(long)gk2 * ldb + gn]) : 0.f;
     }
-    for (int i = threadIdx.x; i < TS * TK; i += 256) {
-      int n, k;
-      if (TB) { k = i % TK; n = i / TK; } else { n = i % TS; k = i / TS; }
-      const int gn = n0 + n, gk = k0 + k;
-      float v = 0.f;
-      if (gn < N && gk < k_end) v = TB ? B[(long)gn * ldb + gk] : B[(long)gk * ldb + gn];
-      Bs[k][n] = v;
+  };
+  fetch(k_begin);
+  for (int k0 = k_begin; k0 < k_end; k0 += TK) {
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+      const int i = threadIdx.x + q * 256;
+      if (TA) As[i / TS][i % TS] = ra[q]; else As[i % TK][i / TK] = ra[q];
+      if (TB) Bs[i % TK][i / TK] = rb[q]; else Bs[i / TS][i % TS] = rb[q];
     }
     __syncthreads();
+    if (k0 + TK < k_end) fetch(k0 + TK);
 #pragma unroll
     for (int k = 0; k < TK; ++k) {
       float a[4], b[4];
