@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs only)")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="run the frozen encoder pass and the trainable tail of each step back to back on one stream")
     return ap.parse_args()
 
 
@@ -198,14 +200,30 @@ def run_ours(args):
     dev_y = [h.to(dev) for h in host_y]
     l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
-    def step(x, y):
+    def step(x, y, h=None):
+        """One train step; h = handle of model.encode_async(x) when the frozen encoder pass was prefetched."""
         opt.zero_grad(set_to_none=True)
-        loss = torch.nn.functional.cross_entropy(model(x), y)
+        loss = torch.nn.functional.cross_entropy(model(x, features=h), y)
         loss.backward()
         if dp is not None:
             dp.finish()
         opt.step()
         return loss
+
+    pipelined = not args.no_pipeline
+
+    def run_steps(n):
+        """n steps over the resident batches.  Pipelined: the frozen encoder pass of batch i+1 is launched on the
+        model's side stream before the trainable tail of batch i (same results, same work per step)."""
+        if not pipelined:
+            for i in range(n):
+                step(dev_x[i % NBUF], dev_y[i % NBUF])
+            return
+        h = model.encode_async(dev_x[0])
+        for i in range(n):
+            h_next = model.encode_async(dev_x[(i + 1) % NBUF]) if i + 1 < n else None
+            step(dev_x[i % NBUF], dev_y[i % NBUF], h)
+            h = h_next
 
     def barrier():
         if world > 1:
@@ -213,8 +231,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---------------- resident-input throughput (`value`) ----------------
-    for i in range(args.warmup):
-        step(dev_x[i % NBUF], dev_y[i % NBUF])
+    run_steps(args.warmup)
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -226,8 +243,7 @@ def run_ours(args):
     if sampler:
         sampler.begin()
     e0.record()
-    for i in range(args.steps):
-        step(dev_x[i % NBUF], dev_y[i % NBUF])
+    run_steps(args.steps)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -245,33 +261,57 @@ def run_ours(args):
 
     # ---------------- end to end from pinned host uint8 clips (`e2e`) ----------------
     copy_stream = torch.cuda.Stream(device=dev)
-    stage_u8 = [torch.empty((B, T, S, S, 3), dtype=torch.uint8, device=dev) for _ in range(2)]
-    stage_y = [torch.empty((B,), dtype=torch.int64, device=dev) for _ in range(2)]
-    ready = [torch.cuda.Event() for _ in range(2)]
-    freed = [torch.cuda.Event() for _ in range(2)]
+    NSTG = 3
+    stage_u8 = [torch.empty((B, T, S, S, 3), dtype=torch.uint8, device=dev) for _ in range(NSTG)]
+    stage_y = [torch.empty((B,), dtype=torch.int64, device=dev) for _ in range(NSTG)]
+    ready = [torch.cuda.Event() for _ in range(NSTG)]
+    freed_u8 = [torch.cuda.Event() for _ in range(NSTG)]     # the ingest kernel has read the staged clips
+    freed_y = [torch.cuda.Event() for _ in range(NSTG)]      # the step has read the staged labels
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
 
     def prefetch(i):
-        s = i % 2
+        s = i % NSTG
         with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(freed[s])
+            copy_stream.wait_event(freed_u8[s])
+            copy_stream.wait_event(freed_y[s])
             stage_u8[s].copy_(host_u8[i % NBUF], non_blocking=True)
             stage_y[s].copy_(host_y[i % NBUF], non_blocking=True)
             ready[s].record(copy_stream)
 
+    def ingest_slot(i):
+        """K1 (uint8 -> float32 CHW /255) on the encoder's stream when pipelined, so the float clips never change pools."""
+        s = i % NSTG
+        st = model.side_stream(dev) if pipelined else torch.cuda.current_stream()
+        with torch.cuda.stream(st):
+            st.wait_event(ready[s])
+            x = ingest_batch(stage_u8[s], S, S)
+            freed_u8[s].record(st)
+        return x
+
     def e2e_loop(n):
-        for s in range(2):
-            freed[s].record(torch.cuda.current_stream())
+        """Every step: H2D of its uint8 clips (copy stream, two batches ahead), ingest kernel, encoder pass (one batch
+        ahead on the side stream when pipelined), trainable tail, loss read back."""
+        cur = torch.cuda.current_stream()
+        for s in range(NSTG):
+            freed_u8[s].record(cur)
+            freed_y[s].record(cur)
         prefetch(0)
+        if n > 1:
+            prefetch(1)
+        x = ingest_slot(0)
+        h = model.encode_async(x) if pipelined else None
         for i in range(n):
-            s = i % 2
+            if i + 2 < n:
+                prefetch(i + 2)
+            x_next = h_next = None
             if i + 1 < n:
-                prefetch(i + 1)                                  # overlaps this step's compute
-            torch.cuda.current_stream().wait_event(ready[s])
-            x = ingest_batch(stage_u8[s], S, S)                  # K1: uint8 -> float32 CHW /255 on the GPU
-            loss = step(x, stage_y[s])
-            freed[s].record(torch.cuda.current_stream())
+                x_next = ingest_slot(i + 1)
+                h_next = model.encode_async(x_next) if pipelined else None
+            cur.wait_event(ready[i % NSTG])                      # labels of this step
+            loss = step(x, stage_y[i % NSTG], h)
+            freed_y[i % NSTG].record(cur)
             loss_host.copy_(loss.detach(), non_blocking=True)    # D2H read of the step's loss
+            x, h = x_next, h_next
         torch.cuda.synchronize()
 
     if args.no_e2e:
@@ -376,11 +416,13 @@ def run_ours(args):
                                    f"GELU/LN adapts + {W['rnn_layers']}-layer LSTM H={W['hidden']} + head, full train step "
                                    "(fwd, CE, bwd, Adam); BASELINE.json configs[1]",
                        "global_batch": world * B, "parallelism": f"dp{world}",
-                       "timing": f"{NBUF} distinct input batches cycled; per-step working set (~6 GB activations) exceeds L2"},
+                       "timing": f"{NBUF} distinct input batches cycled; per-step working set (~6 GB activations) exceeds L2",
+                       "pipeline": ("frozen encoder pass of batch i+1 on a side stream under the trainable tail of batch i "
+                                    "(model.encode_async); same work per step" if pipelined else "none")},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps,
-                    "path": "pinned uint8 host clips -> H2D (copy stream, double buffered) -> b2_ingest_u8 -> train step -> loss D2H"},
+                    "path": "pinned uint8 host clips -> H2D (copy stream, two batches ahead) -> b2_ingest_u8 -> encoder pass -> trainable tail -> loss D2H"},
             "gpu_launches": int(launches),
             "gflop_per_clip_fwd_backbone": RESNET50_GFLOP_PER_FRAME_112 * T,
         }

@@ -752,11 +752,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
 
   tc_fence_before();
+  // every thread makes ITS statistics reductions device-visible BEFORE the block barrier: a fence by thread 0
+  // alone (after the barrier) does not wait for the other warps' in-flight reductions, and the last CTA then
+  // finalised from incomplete sums whenever the CTAs' finish times spread (seen with a second stream running)
+  if (ep.fin.scale != nullptr) __threadfence();
   __syncthreads();
   if (ep.fin.scale != nullptr) {
     // BatchNorm finalisation by the last CTA to get here: every CTA's statistics are in global memory
     __shared__ int is_last;
-    __threadfence();
     if (threadIdx.x == 0) is_last = (atomicAdd(ep.fin.counter, 1u) == gridDim.x - 1);
     __syncthreads();
     if (is_last) {

@@ -69,6 +69,14 @@ class SmallCNNLRCN(nn.Module):
         return ops.linear(out.reshape(B, -1), self.fc.weight, self.fc.bias, bf16=bf16)
 
 
+class _FeatureHandle:
+    """Result of encode_async(): the feature tensor (valid once `event` has fired) for clips of `shape`."""
+    __slots__ = ("tensor", "event", "shape")
+
+    def __init__(self, tensor, event, shape):
+        self.tensor, self.event, self.shape = tensor, event, shape
+
+
 class _BackboneLRCN(nn.Module):
     """Shared machinery of the torchvision-backbone variants."""
 
@@ -82,9 +90,51 @@ class _BackboneLRCN(nn.Module):
         B, T, C, H, W = x.shape
         return self._runner(x.reshape(B * T, C, H, W), self.training).reshape(B, T, -1)
 
+    # ---- optional encoder prefetch (frozen backbone only) ------------------------------------------------
+    # The frozen frame encoder does not depend on the optimizer update, so the encoder pass of batch i+1 can run
+    # on a second stream while the (latency-bound, low-occupancy) trainable tail of batch i runs its forward,
+    # backward and optimizer step.  Results are identical to calling forward(x) batch by batch: the encoder sees
+    # the batches in the same order (BatchNorm running statistics included).
+    #     h = model.encode_async(x_next) ... logits = model(x, features=h)
+    def side_stream(self, device):
+        """The stream encode_async() runs on.  Producing the clips on it (`with torch.cuda.stream(...)`: H2D wait,
+        ingest kernel) keeps their storage in that stream's allocator pool: no cross-stream hand-over per batch."""
+        side = self.__dict__.get("_side_stream")
+        if side is None or side.device != torch.device(device):
+            side = torch.cuda.Stream(device=device)
+            object.__setattr__(self, "_side_stream", side)
+        return side
+
+    def encode_async(self, x):
+        """Launch the frame encoder for clips `x` on the model's side stream; returns a handle for forward()."""
+        _check_input(x)
+        if any(p.requires_grad for p in self.cnn_backbone.parameters()):
+            raise NotImplementedError("encode_async() is for a frozen frame encoder (its pass must not depend on the optimizer step)")
+        self._runner._weights()                    # kernel-layout weights are (re)built on the caller's stream
+        cur = torch.cuda.current_stream(x.device)
+        side = self.side_stream(x.device)
+        side.wait_stream(cur)                      # x may have been produced on the caller's stream
+        with torch.cuda.stream(side), torch.no_grad():
+            feat = self._features(x)
+            done = torch.cuda.Event()
+            done.record(side)
+        x.record_stream(side)
+        return _FeatureHandle(feat, done, tuple(x.shape))
+
+    def _features_or_handle(self, x, features):
+        if features is None:
+            return self._features(x)
+        if not isinstance(features, _FeatureHandle) or features.shape != tuple(x.shape):
+            raise ValueError("features= expects the handle encode_async() returned for these clips")
+        cur = torch.cuda.current_stream(x.device)
+        cur.wait_event(features.event)
+        features.tensor.record_stream(cur)
+        return features.tensor
+
     def __getstate__(self):                 # torch.save(model) (train_eval.py:53) must keep working
         d = self.__dict__.copy()
         d.pop("_runner", None)              # kernel-layout weight cache is rebuilt on load
+        d.pop("_side_stream", None)
         return d
 
     def __setstate__(self, state):
@@ -135,10 +185,10 @@ class LRCN(_BackboneLRCN):
         else:
             self.fc = nn.ModuleList([nn.Linear(fc_in, 1) for _ in range(num_classes)])
 
-    def forward(self, x):
+    def forward(self, x, features=None):
         bf16 = self.precision == "bf16"
         B = x.shape[0]
-        y = self._features(x)
+        y = self._features_or_handle(x, features)
         tr = self.training
         lin, aln = ops.linear, ops.act_layernorm
         y = ops.dropout(aln(lin(y, self.adapt1.weight, self.adapt1.bias, bf16), self.bn1.weight, self.bn1.bias, True, self.bn1.eps), self.drop1.p, tr)
@@ -194,10 +244,10 @@ class UCF50LRCN(_BackboneLRCN):
         else:
             self.fc = nn.ModuleList([nn.Linear(fc_in, 1) for _ in range(num_classes)])
 
-    def forward(self, x):
+    def forward(self, x, features=None):
         bf16 = self.precision == "bf16"
         B = x.shape[0]
-        y = self._features(x)
+        y = self._features_or_handle(x, features)
         for a in (self.adapt1, self.adapt2, self.adapt3):
             y = ops.linear(y, a.weight, a.bias, bf16)
         r = ops.lstm_forward(y, self.rnn, bf16=bf16)
@@ -248,10 +298,10 @@ class CrimeLRCN(_BackboneLRCN):
             for i, (_, p) in enumerate(self.cnn_backbone.named_parameters()):
                 p.requires_grad = i > freeze_until_layer
 
-    def forward(self, x):
+    def forward(self, x, features=None):
         bf16 = self.precision == "bf16"
         B = x.shape[0]
-        y = self._features(x)
+        y = self._features_or_handle(x, features)
         y = ops.linear(y, self.adapt.weight, self.adapt.bias, bf16)
         r = ops.lstm_forward(y, self.lstm, bf16=bf16)
         r = r.reshape(B, -1) if self.rnn_out == "all" else r[:, -1, :]
