@@ -28,7 +28,8 @@ extern "C" {
 /* ---- library status ------------------------------------------------------------------ */
 int b2_abi_version(void);
 const char* b2_last_error(void);
-long b2_launch_count(void);      /* kernels launched by this library since load (all streams) */
+long b2_launch_count(void);
+int b2_add_launch_count(long n);   /* kernels replayed from a captured CUDA graph (host layer bookkeeping) */      /* kernels launched by this library since load (all streams) */
 int b2_device_check(void);
 
 /* ---- K1 frame ingest -------------------------------------------------------------------
@@ -86,6 +87,19 @@ int b2_bn_finalize_nhwc(const float* sum, const float* sumsq, const float* gamma
                         float* scale, float* shift, int C, void* stream);
 int b2_scale_shift_apply_nhwc(const void* x, void* y, long rows, int C, const float* scale, const float* shift,
                               const void* res, const float* rscale, const float* rshift, int relu, void* stream);
+
+/* 3x3 / stride 1 / pad 1 convolution of a narrow stage (C = Cout = 64: Bottleneck.conv2 of layer1, BasicBlock convs
+ * of layer1) as a halo-tile kernel: one TMA brings the (TH+2) x (W+2) input halo of TH output rows into shared
+ * memory and the nine filter taps are nine shifted descriptors over that tile (no 9x re-fetch through L2), the 72 KB
+ * of weights stay resident; a_scale/a_shift (optional) = BatchNorm(+ReLU) of the INPUT applied to the halo once per
+ * tile; col_sum/col_sumsq, fin_* as b2_conv2d_bn_nhwc_bf16.  b2_conv3x3_halo_supported() tells whether a shape is
+ * covered (otherwise use b2_conv2d_bn_nhwc_bf16). */
+int b2_conv3x3_halo_supported(int N, int H, int W, int C, int Cout);
+int b2_conv3x3_halo_bn_nhwc_bf16(const void* x, int N, int H, int W, int C, const void* w, int Cout, void* y,
+                                 const float* a_scale, const float* a_shift, int a_relu, float* col_sum, float* col_sumsq,
+                                 const float* fin_gamma, const float* fin_beta, float* fin_running_mean,
+                                 float* fin_running_var, float* fin_scale, float* fin_shift, unsigned int* fin_counter,
+                                 float eps, float momentum, void* stream);
 
 /* BatchNorm statistics + finalisation of a 1x1 convolution y = relu?(x*a_scale+a_shift) W^T WITHOUT computing y
  * (torchvision Bottleneck.bn3 in train mode, models.py:192): per-channel sum_m y and sum_m y^2 follow from the

@@ -136,6 +136,41 @@ def test_conv_bn_folded(ops, N, H, W, C, Cout, R, stride, pad):
     assert err(out4.float(), ref4) < 8e-3
 
 
+@pytest.mark.parametrize("N,H,W", [(2, 28, 28), (3, 14, 14), (5, 7, 7), (2, 9, 13), (1, 4, 4), (40, 28, 28), (3, 56, 56),
+                                   (2, 5, 60)])
+@pytest.mark.parametrize("with_a", [False, True])
+def test_conv3x3_halo(ops, N, H, W, with_a):
+    """Halo-tile 3x3 conv (nine shifted SWIZZLE_128B descriptors over one shared-memory tile) vs torch conv2d on the
+    bf16-rounded operands: output, statistics, in-kernel BatchNorm finalisation; optional input BatchNorm+ReLU with
+    zero padding preserved."""
+    C = Cout = 64
+    torch.manual_seed(N * H + W)
+    xr = torch.randn(N, C, H, W).bfloat16()
+    w = (torch.randn(Cout, C, 3, 3) / (C * 9) ** 0.5).bfloat16()
+    a_sc, a_sh = torch.rand(C) + 0.5, torch.randn(C) * 0.3
+    xin = torch.relu(xr.float() * a_sc.view(1, -1, 1, 1) + a_sh.view(1, -1, 1, 1)).bfloat16().float() if with_a else xr.float()
+    ref = F.conv2d(xin, w.float(), stride=1, padding=1).permute(0, 2, 3, 1)
+    xg = xr.permute(0, 2, 3, 1).contiguous().to(DEV)
+    wg = w.permute(0, 2, 3, 1).contiguous().to(DEV)
+    assert ops.conv3x3_halo_supported(xg, wg, 1, 1)
+    gamma, beta = (torch.rand(Cout) + 0.5).to(DEV), torch.randn(Cout).to(DEV)
+    rm, rv = torch.zeros(Cout, device=DEV), torch.ones(Cout, device=DEV)
+    buf = torch.zeros(4 * Cout + 4, device=DEV)
+    s1, s2, fs, fh, cnt = buf[:Cout], buf[Cout:2 * Cout], buf[2 * Cout:3 * Cout], buf[3 * Cout:4 * Cout], buf[4 * Cout:]
+    y = ops.conv3x3_halo_bn(xg, wg, a=(a_sc.to(DEV), a_sh.to(DEV)) if with_a else None, stats=(s1, s2),
+                            fin=(gamma, beta, rm, rv, fs, fh, cnt, 1e-5, 0.1))
+    assert y.shape == ref.shape
+    assert err(y.float(), ref) < 6e-3
+    r = ref.bfloat16().float().reshape(-1, Cout)
+    assert err(s1, r.sum(0), floor=1e-3 * r.abs().sum(0).max().item()) < 2e-2
+    assert err(s2, (r * r).sum(0)) < 2e-2
+    mean, var = r.mean(0), r.var(0, unbiased=False)
+    sc_ref = gamma.cpu() / torch.sqrt(var + 1e-5)
+    assert err(fs, sc_ref) < 2e-2 and err(fh, beta.cpu() - mean * sc_ref, floor=1.0) < 2e-2
+    y2 = ops.conv2d_bn_nhwc(xg, wg, 1, 1, a=(a_sc.to(DEV), a_sh.to(DEV)) if with_a else None)     # im2col-TMA kernel
+    assert err(y.float(), y2.float()) < 6e-3
+
+
 @pytest.mark.parametrize("M,C,Cout", [(128, 64, 256), (256, 128, 512), (1000, 64, 64), (5000, 128, 256), (70000, 64, 256),
                                       (33333, 128, 512), (128, 256, 1024), (50176, 256, 1024), (777, 256, 64)])
 def test_gram_bn_statistics(ops, M, C, Cout):

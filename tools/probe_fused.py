@@ -62,6 +62,10 @@ def case(name, H, C, Cout, R, stride, pad, variants):
             return ops.conv2d_bn_nhwc(x, w, stride, pad, a=a, stats=st, fin=fin, store=False)
         if v == "statsonly":
             return ops.conv2d_bn_nhwc(x, w, stride, pad, stats=st, fin=fin, store=False)
+        if v == "halo":
+            return ops.conv3x3_halo_bn(x, w, stats=st, fin=fin)
+        if v == "halo+a":
+            return ops.conv3x3_halo_bn(x, w, a=a, stats=st, fin=fin)
         if v == "gram":
             return ops.conv1x1_gram_bnstats(x, w, a, fin)
         if v == "a+o":
@@ -104,7 +108,7 @@ else:
     print(f"stem       stats        {timeit(lambda: ops.stem_conv(xs, wk, stats=st)):8.1f} us (pack + conv)")
     print(f"stem       plain        {timeit(lambda: ops.stem_conv(xs, wk)):8.1f} us (pack + conv)")
     case("l1.conv1", 28, 256, 64, 1, 1, 0, ["plain", "stats"])
-    case("l1.conv2", 28, 64, 64, 3, 1, 1, ["apply", "plain", "stats", "a", "a+stats"])
+    case("l1.conv2", 28, 64, 64, 3, 1, 1, ["apply", "plain", "stats", "a", "a+stats", "halo", "halo+a"])
     case("l1.conv3", 28, 64, 256, 1, 1, 0, ["plain", "stats", "statsonly", "a", "a+statsonly", "gram", "a+o", "o+res", "a+o+res", "a+o+res+r"])
     case("l2.conv2", 28, 128, 128, 3, 2, 1, ["apply", "plain", "stats"])
     case("l2.conv2", 14, 128, 128, 3, 1, 1, ["apply", "plain", "stats", "a", "a+stats"])

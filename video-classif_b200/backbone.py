@@ -21,7 +21,7 @@ import torch
 
 from . import _lib
 from ._lib import call, ptr, stream_ptr
-from .ops import (BF16, F32, GRAM_CHANNELS, conv1x1_gram_bnstats, conv2d_bn_nhwc, conv2d_nhwc, gemm_tn, pack_stem_weight,
+from .ops import (BF16, F32, GRAM_CHANNELS, conv1x1_gram_bnstats, conv2d_bn_nhwc, conv3x3_halo_bn, conv3x3_halo_supported, conv2d_nhwc, gemm_tn, pack_stem_weight,
                   scale_shift_apply, stem_conv)
 
 SUPPORTED = ("resnet18", "resnet34", "resnet50", "resnet101", "resnet152")
@@ -51,6 +51,8 @@ class ResNetRunner:
         self._convs = None
         self._bns = None
         self._frozen = None
+        self._graphs = {}
+        self.use_graph = False        # models route through graphed() when set (enable_encoder_graph())
         self.stem_impl = "direct"     # "im2col": patch matrix + plain GEMM (A/B parity tests)
         self.fuse_bn = ResNetRunner.FUSE_BN   # BatchNorms folded into the conv kernels vs stand-alone bn_apply passes
 
@@ -75,6 +77,43 @@ class ResNetRunner:
                 cache[n] = wk
             self._wcache, self._wkey = cache, key
         return self._wcache
+
+    # ---- CUDA-graph replay of the whole encoder pass (static shapes, frozen weights) ---------------------------
+    def graphed(self, x, training: bool):
+        """Same result as self(x, training), replayed from a CUDA graph captured on first use for this input shape /
+        mode / weight version: one graph launch instead of ~110 kernel launches from Python per pass.  The captured
+        pass reads a static copy of x and writes static activations; the returned features live in one of 4 rotating
+        buffers (valid until the 4th following call)."""
+        _lib.require_device()
+        self._weights()
+        key = (tuple(x.shape), x.dtype, x.device.index, bool(training), self._wkey, self.fuse_bn, self.stem_impl)
+        entry = self._graphs.get(key)
+        if entry is None:
+            bufs = [b for b in self.net.buffers()]
+            saved = [b.detach().clone() for b in bufs]          # the warm-up pass must not advance the running stats
+            static_x = x.detach().clone()
+            self(static_x, training)                             # warm-up: function attributes, allocator pools
+            for b, sv in zip(bufs, saved):
+                b.copy_(sv)
+            torch.cuda.synchronize(x.device)
+            graph = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count()
+            with torch.cuda.graph(graph):
+                static_feat = self(static_x, training)
+            # results rotate through a small ring of persistent buffers: no per-call allocation (a tensor handed from
+            # the encoder's stream to the consumer's stream every step made the caching allocator hold blocks back)
+            ring = [torch.empty_like(static_feat) for _ in range(4)]
+            entry = [graph, static_x, static_feat, _lib.launch_count() - n0, ring, 0]
+            self._graphs[key] = entry
+        graph, static_x, static_feat, n_launch, ring, idx = entry
+        if x.data_ptr() != static_x.data_ptr():
+            static_x.copy_(x)
+        graph.replay()
+        call("b2_add_launch_count", n_launch)
+        out = ring[idx]
+        entry[5] = (idx + 1) % len(ring)
+        out.copy_(static_feat)
+        return out
 
     def _bn(self, x, bn, stats, count, train, relu=True, res_mode=0, res=None, rbn=None, rstats=None):
         rows = x.numel() // x.shape[-1]
@@ -187,10 +226,15 @@ class ResNetRunner:
                         # a 3x3 consumer would re-normalise every input pixel 9 times (once per tap) and
                         # doubles the shared-memory traffic per k-block: one in-place pass over this small
                         # tensor is cheaper; the 1x1 consumer (conv3) takes the A transform
-                        sc1, sh1 = ss_of(blk.bn1)
-                        scale_shift_apply(r1, sc1, sh1, relu=True)
-                        r2 = conv2d_bn_nhwc(r1, w[pfx + ".conv2"], stride, 1, stats=stats_of(blk.bn2),
-                                            fin=fin_of(blk.bn2))
+                        if conv3x3_halo_supported(r1, w[pfx + ".conv2"], stride, 1):
+                            # 64-channel stage: halo-tile conv, BN1+ReLU applied to the halo once per tile
+                            r2 = conv3x3_halo_bn(r1, w[pfx + ".conv2"], a=ss_of(blk.bn1), stats=stats_of(blk.bn2),
+                                                 fin=fin_of(blk.bn2))
+                        else:
+                            sc1, sh1 = ss_of(blk.bn1)
+                            scale_shift_apply(r1, sc1, sh1, relu=True)
+                            r2 = conv2d_bn_nhwc(r1, w[pfx + ".conv2"], stride, 1, stats=stats_of(blk.bn2),
+                                                fin=fin_of(blk.bn2))
                         del r1
                         if ds:
                             dbn = blk.downsample[1]
@@ -207,10 +251,18 @@ class ResNetRunner:
                                            res=rd if ds else y, r=ss_of(dbn) if ds else None, relu=True)
                         del r2
                     else:
-                        r1 = conv2d_bn_nhwc(y, w[pfx + ".conv1"], stride, 1, stats=stats_of(blk.bn1), fin=fin_of(blk.bn1))
-                        sc1, sh1 = ss_of(blk.bn1)
-                        scale_shift_apply(r1, sc1, sh1, relu=True)
-                        r2 = conv2d_bn_nhwc(r1, w[pfx + ".conv2"], 1, 1, stats=stats_of(blk.bn2), fin=fin_of(blk.bn2))
+                        if conv3x3_halo_supported(y, w[pfx + ".conv1"], stride, 1):
+                            r1 = conv3x3_halo_bn(y, w[pfx + ".conv1"], stats=stats_of(blk.bn1), fin=fin_of(blk.bn1))
+                        else:
+                            r1 = conv2d_bn_nhwc(y, w[pfx + ".conv1"], stride, 1, stats=stats_of(blk.bn1),
+                                                fin=fin_of(blk.bn1))
+                        if conv3x3_halo_supported(r1, w[pfx + ".conv2"], 1, 1):
+                            r2 = conv3x3_halo_bn(r1, w[pfx + ".conv2"], a=ss_of(blk.bn1), stats=stats_of(blk.bn2),
+                                                 fin=fin_of(blk.bn2))
+                        else:
+                            sc1, sh1 = ss_of(blk.bn1)
+                            scale_shift_apply(r1, sc1, sh1, relu=True)
+                            r2 = conv2d_bn_nhwc(r1, w[pfx + ".conv2"], 1, 1, stats=stats_of(blk.bn2), fin=fin_of(blk.bn2))
                         del r1
                         if ds:
                             dbn = blk.downsample[1]

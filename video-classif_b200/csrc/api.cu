@@ -34,6 +34,12 @@ int b2_num_sms() {
 B2_API int b2_abi_version(void) { return 1; }
 B2_API const char* b2_last_error(void) { return g_err; }
 B2_API long b2_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+// replaying a captured CUDA graph launches its kernels without passing through the entry points: the host layer
+// credits them here so that b2_launch_count() stays the number of kernels executed
+B2_API int b2_add_launch_count(long n) {
+  g_launches.fetch_add(n, std::memory_order_relaxed);
+  return 0;
+}
 
 // 0 when the current device is a compute-capability 10.x part (B200); otherwise an error.
 // There is no CPU or other-architecture fallback anywhere in this library.

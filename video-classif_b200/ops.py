@@ -86,6 +86,33 @@ def conv2d_bn_nhwc(x, w, stride, pad, a=None, a_relu=True, o=None, res=None, r=N
     return y
 
 
+def conv3x3_halo_supported(x, w, stride, pad):
+    N, H, W, C = x.shape
+    return (stride == 1 and pad == 1 and tuple(w.shape[1:3]) == (3, 3)
+            and bool(_lib.lib().b2_conv3x3_halo_supported(N, H, W, C, w.shape[0])))
+
+
+def conv3x3_halo_bn(x, w, a=None, a_relu=True, stats=None, fin=None):
+    """b2_conv3x3_halo_bn_nhwc_bf16: 3x3/1/1 conv of a 64-channel stage from one halo tile per TH output rows
+    (nine shifted descriptors, resident weights); a = (scale, shift) of the input BatchNorm(+ReLU), applied to the
+    halo once per tile; stats / fin as conv2d_bn_nhwc.  Returns the raw bf16 output [N,H,W,64]."""
+    _chk(x, w)
+    N, H, W, C = x.shape
+    Cout = w.shape[0]
+    y = torch.empty((N, H, W, Cout), device=x.device, dtype=BF16)
+    a0, a1 = a if a is not None else (None, None)
+    s1, s2 = stats if stats is not None else (None, None)
+    if fin is not None:
+        g, b, rm, rv, fs, fh, cnt, eps, mom = fin
+    else:
+        g = b = rm = rv = fs = fh = cnt = None
+        eps, mom = 1e-5, 0.1
+    call("b2_conv3x3_halo_bn_nhwc_bf16", x.data_ptr(), N, H, W, C, w.data_ptr(), Cout, y.data_ptr(), ptr(a0), ptr(a1),
+         int(a_relu), ptr(s1), ptr(s2), ptr(g), ptr(b), ptr(rm), ptr(rv), ptr(fs), ptr(fh), ptr(cnt), float(eps),
+         float(mom), stream_ptr())
+    return y
+
+
 def conv1x1_gram_bnstats(x, w, a, fin, stats=None, a_relu=True):
     """b2_conv1x1_gram_bnstats_bf16: train-mode BatchNorm statistics + finalisation of the 1x1 convolution
     relu?(x*a_scale+a_shift) @ w^T without computing its output (Gram-matrix form, one pass over x).
