@@ -46,7 +46,9 @@ def test_gemm_tcgen05(ops, M, N, K, bias, out_bf16, relu):
 @pytest.mark.parametrize("N,H,W,C,Cout,R,stride,pad", [
     (2, 8, 8, 64, 64, 1, 1, 0), (2, 8, 8, 64, 64, 3, 1, 1), (3, 14, 14, 128, 128, 3, 1, 1),
     (3, 28, 28, 128, 128, 3, 2, 1), (3, 7, 7, 256, 512, 1, 2, 0), (5, 7, 7, 512, 512, 3, 2, 1),
-    (1, 5, 9, 64, 192, 3, 1, 1), (130, 4, 4, 64, 64, 3, 1, 1)])
+    (1, 5, 9, 64, 192, 3, 1, 1), (130, 4, 4, 64, 64, 3, 1, 1),
+    # large enough for the two-CTA cluster path (weight tile multicast): odd and even row-block counts
+    (40, 28, 28, 256, 256, 1, 1, 0), (64, 14, 14, 128, 512, 3, 1, 1), (97, 7, 7, 512, 512, 3, 1, 1)])
 def test_conv_implicit_gemm_tma_im2col(ops, N, H, W, C, Cout, R, stride, pad):
     torch.manual_seed(N * H + C)
     x = torch.randn(N, C, H, W).bfloat16()
@@ -82,7 +84,8 @@ def test_stem_conv_direct_toeplitz(ops, N, H, W):
 
 @pytest.mark.parametrize("N,H,W,C,Cout,R,stride,pad", [
     (3, 9, 9, 64, 64, 3, 1, 1), (2, 14, 14, 128, 256, 1, 1, 0), (5, 12, 10, 64, 128, 3, 2, 1), (70, 4, 4, 256, 64, 3, 1, 1),
-    (4, 7, 7, 128, 512, 1, 2, 0)])
+    (4, 7, 7, 128, 512, 1, 2, 0), (40, 28, 28, 256, 256, 1, 1, 0), (150, 7, 7, 256, 1024, 1, 1, 0),
+    (66, 14, 14, 128, 256, 3, 1, 1)])
 def test_conv_bn_folded(ops, N, H, W, C, Cout, R, stride, pad):
     """b2_conv2d_bn_nhwc_bf16: input BatchNorm+ReLU applied to the A tile in shared memory (padding stays 0),
     statistics + finalisation tail, statistics-only pass, and the BN3 + shortcut(+BN) + ReLU epilogue."""

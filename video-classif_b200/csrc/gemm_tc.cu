@@ -40,6 +40,7 @@
 
 #include <cudaTypedefs.h>
 #include <mutex>
+#include <stdlib.h>
 
 namespace {
 
@@ -136,7 +137,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
   return d;
 }
 
-template <int BN, int MODE, bool TF>
+template <int BN, int MODE, bool TF, bool CL = false>
 __global__ void __launch_bounds__(TF ? kThreadsTf : kThreadsNoTf, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_r, int M, int N,
@@ -170,7 +171,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m_blocks = (M + BM - 1) / BM;
+  // CL: clusters of two CTAs work on the tile pair (2p, 2p+1) -- same weight columns, adjacent rows (tiles are
+  // ordered m-fastest and the grid is even, so blockIdx.x parity = tile parity = cluster rank).  Each CTA fetches HALF
+  // of the weight tile and TMA-multicasts it into both CTAs' stages: the L2 -> SM traffic of the B operand, the
+  // larger one at BN = 256, halves.  A slot is refilled only after BOTH CTAs' MMAs released it (empty count 2).
+  // The row-block count is padded to even; an all-out-of-range tile loads zeros and stores nothing.
+  const int m_blocks = CL ? (((M + BM - 1) / BM + 1) & ~1) : (M + BM - 1) / BM;
   const int n_blocks = (N + BN - 1) / BN;
   const int num_tiles = m_blocks * n_blocks;
   const int k_blocks = (K + BK - 1) / BK;
@@ -180,7 +186,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     prefetch_tmap(&tmap_b);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], CL ? 2 : 1);
       mbar_init(&tf_bar[i], 32 * kTfWarps);
     }
     for (int i = 0; i < 2; ++i) {
@@ -196,6 +202,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if (CL) cluster_sync();          // the peer's barriers exist before any multicast can reach them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -235,7 +242,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           } else {
             tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
           }
-          tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
+          if (CL) {
+            const int rank = (int)cluster_ctarank();
+            tma_load_2d_multicast(sb + rank * (BN / 2) * BK * 2, &tmap_b, &full_bar[stage], kb * BK,
+                                  n_blk * BN + rank * (BN / 2), (uint16_t)3);
+          } else {
+            tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
+          }
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -269,7 +282,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             // +32 B per K=16 step inside the 128 B swizzle row (encoded >>4 -> +2)
             tc_mma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
           }
-          tc_commit(&empty_bar[stage]);                       // frees the smem slot when the MMAs retire
+          if (CL) tc_commit_multicast(&empty_bar[stage], (uint16_t)3);   // frees the slot in BOTH CTAs
+          else tc_commit(&empty_bar[stage]);                  // frees the smem slot when the MMAs retire
           if (kb == k_blocks - 1) tc_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
         }
         __syncwarp();
@@ -475,15 +489,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const bool row_ok = row < M;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-#pragma unroll 1
-      for (int j = 0; j < kMyChunks; ++j) {
+      // TMEM reads are software-pipelined: the tcgen05.ld of chunk j+1 is in flight while chunk j is converted,
+      // reduced and staged, and the accumulator is handed back to the MMA warp as soon as the last read has landed
+      auto chunk_ok = [&](int j) { return j < kMyChunks && half + 2 * j < kChunks && n_blk * BN + (half + 2 * j) * 32 < N; };
+      auto issue = [&](int j, uint32_t (&raw)[32]) {
+        tc_ld32(tmem_base + (uint32_t)(acc * BN + (half + 2 * j) * 32) + ((uint32_t)(quarter * 32) << 16), raw);
+      };
+      auto release_acc = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      };
+      auto process = [&](int j, const uint32_t (&raw)[32]) {
         const int ch = half + 2 * j;
         const int col0 = n_blk * BN + ch * 32;
-        if (ch < kChunks && col0 < N) {   // warp-uniform
+        {
           const bool full_chunk = (col0 + 32 <= N);
-          uint32_t raw[32];
-          tc_ld32(tmem_base + (uint32_t)(acc * BN + ch * 32) + ((uint32_t)(quarter * 32) << 16), raw);
-          tc_wait_ld();
           float v[32];
 #pragma unroll
           for (int jj = 0; jj < 32; ++jj) v[jj] = __uint_as_float(raw[jj]);
@@ -630,10 +651,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             st[BN] += s2[0];
           }
         }
+      };
+      uint32_t raw_a[32], raw_b[32];
+      if (!chunk_ok(0)) {
+        release_acc();
+      } else {
+        issue(0, raw_a);
+#pragma unroll 1
+        for (int j = 0; j < kMyChunks; j += 2) {
+          if (!chunk_ok(j)) break;
+          tc_wait_ld();
+          const bool more_b = chunk_ok(j + 1);
+          if (more_b) issue(j + 1, raw_b);
+          else release_acc();
+          process(j, raw_a);
+          if (more_b) {
+            tc_wait_ld();
+            const bool more_a = chunk_ok(j + 2);
+            if (more_a) issue(j + 2, raw_a);
+            else release_acc();
+            process(j + 1, raw_b);
+          }
+        }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
     if (tma_store && lane == 0) bulk_wait_all();   // all bulk stores of this warp have landed
     if (want_stats && cur_nblk >= 0) {
@@ -782,6 +822,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     tc_fence_after();
     tc_dealloc(tmem_base, kTmemCols);
   }
+  if (CL) cluster_sync();          // no CTA leaves while its peer can still multicast into it / arrive on its barriers
 }
 
 // ------------------------------------------------------------------ host side
@@ -833,20 +874,38 @@ int make_tmap_2d(CUtensorMap* map, const void* base, long rows, long cols, long 
   return 0;
 }
 
-template <int BN, int MODE, bool TF>
+template <int BN, int MODE, bool TF, bool CL = false>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tr, int M, int N,
                 int K, const ConvGeom& g, const ATransform& at, const EpiParams& ep, cudaStream_t stream) {
   using L = SmemLayout<BN, MODE>;
   static bool attr_set = false;
   if (!attr_set) {
-    B2_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, MODE, TF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B2_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, MODE, TF, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        L::kTotal));
     attr_set = true;
   }
-  const int tiles = b2_ceil_div(M, BM) * b2_ceil_div(N, BN);
-  const int grid = tiles < b2_num_sms() ? tiles : b2_num_sms();
-  gemm_tc_kernel<BN, MODE, TF><<<grid, TF ? kThreadsTf : kThreadsNoTf, L::kTotal, stream>>>(ta, tb, td, tr, M, N, K, g,
-                                                                                           at, ep);
+  const int m_blocks = CL ? ((b2_ceil_div(M, BM) + 1) & ~1) : b2_ceil_div(M, BM);
+  const int tiles = m_blocks * b2_ceil_div(N, BN);
+  int grid = tiles < b2_num_sms() ? tiles : b2_num_sms();
+  if (CL) {
+    grid &= ~1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(TF ? kThreadsTf : kThreadsNoTf);
+    cfg.dynamicSmemBytes = L::kTotal;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    B2_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, MODE, TF, CL>, ta, tb, td, tr, M, N, K, g, at, ep));
+  } else {
+    gemm_tc_kernel<BN, MODE, TF, CL><<<grid, TF ? kThreadsTf : kThreadsNoTf, L::kTotal, stream>>>(ta, tb, td, tr, M, N, K,
+                                                                                                g, at, ep);
+  }
   B2_LAUNCH_CHECK("gemm_tc_kernel");
   return 0;
 }
@@ -869,7 +928,12 @@ int pick_bn_gemm(int M, int N) {
 
 template <int MODE, bool TF>
 int dispatch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tr,
-                int M, int N, int K, const ConvGeom& g, const ATransform& at, const EpiParams& ep, cudaStream_t stream) {
+                int M, int N, int K, const ConvGeom& g, const ATransform& at, const EpiParams& ep, cudaStream_t stream,
+                const CUtensorMap* tb_half = nullptr) {
+  if constexpr (MODE != EPI_GENERIC) {
+    if (bn == 256 && tb_half != nullptr)      // two-CTA clusters with the weight tile multicast (see the kernel)
+      return launch_gemm<256, MODE, TF, true>(ta, *tb_half, td, tr, M, N, K, g, at, ep, stream);
+  }
   switch (bn) {
     case 256: return launch_gemm<256, MODE, TF>(ta, tb, td, tr, M, N, K, g, at, ep, stream);
     case 128: return launch_gemm<128, MODE, TF>(ta, tb, td, tr, M, N, K, g, at, ep, stream);
@@ -883,7 +947,7 @@ int dispatch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const CUte
 }
 
 int dispatch(int bn, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const ConvGeom& g,
-             const ATransform& at, EpiParams ep, cudaStream_t stream) {
+             const ATransform& at, EpiParams ep, cudaStream_t stream, const CUtensorMap* tb_half = nullptr) {
   // bf16 outputs whose rows are 16-byte multiples leave through TMA bulk stores
   CUtensorMap td = ta, tr = ta;
   ep.tma_store = 0;
@@ -909,14 +973,14 @@ int dispatch(int bn, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N,
   }
   switch (mode) {
     case EPI_STATS:
-      return tf ? dispatch_bn<EPI_STATS, true>(bn, ta, tb, td, tr, M, N, K, g, at, ep, stream)
-                : dispatch_bn<EPI_STATS, false>(bn, ta, tb, td, tr, M, N, K, g, at, ep, stream);
+      return tf ? dispatch_bn<EPI_STATS, true>(bn, ta, tb, td, tr, M, N, K, g, at, ep, stream, tb_half)
+                : dispatch_bn<EPI_STATS, false>(bn, ta, tb, td, tr, M, N, K, g, at, ep, stream, tb_half);
     case EPI_POST:
-      return tf ? dispatch_bn<EPI_POST, true>(bn, ta, tb, td, tr, M, N, K, g, at, ep, stream)
-                : dispatch_bn<EPI_POST, false>(bn, ta, tb, td, tr, M, N, K, g, at, ep, stream);
+      return tf ? dispatch_bn<EPI_POST, true>(bn, ta, tb, td, tr, M, N, K, g, at, ep, stream, tb_half)
+                : dispatch_bn<EPI_POST, false>(bn, ta, tb, td, tr, M, N, K, g, at, ep, stream, tb_half);
     case EPI_BF16:
-      return tf ? dispatch_bn<EPI_BF16, true>(bn, ta, tb, td, tr, M, N, K, g, at, ep, stream)
-                : dispatch_bn<EPI_BF16, false>(bn, ta, tb, td, tr, M, N, K, g, at, ep, stream);
+      return tf ? dispatch_bn<EPI_BF16, true>(bn, ta, tb, td, tr, M, N, K, g, at, ep, stream, tb_half)
+                : dispatch_bn<EPI_BF16, false>(bn, ta, tb, td, tr, M, N, K, g, at, ep, stream, tb_half);
     default:
       return dispatch_bn<EPI_GENERIC, false>(bn, ta, tb, td, tr, M, N, K, g, at, ep, stream);
   }
@@ -955,12 +1019,19 @@ int conv_common(const void* x, int Nimg, int H, int W, int C, const void* w, int
   const int bn = pick_bn(Cout);
   ep.ldd = Cout;
   if (ep.res != nullptr) ep.ldres = Cout;
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tbh;
   if (int r = make_tmap_2d(&tb, w, Cout, K, K, bn)) return r;
+  // weight-multicast clusters pay off where the B tile dominates the operand traffic and the grid fills the machine
+  const CUtensorMap* tb_half = nullptr;
+  if (bn == 256 && K >= 256 && Cout % 256 == 0 && (long)b2_ceil_div(M, BM) * (Cout / 256) >= b2_num_sms() &&
+      getenv("B2_CLUSTER") != nullptr) {   // opt-in: measured no gain on B200 (unicast TMA from neighbouring SMs is already de-duplicated in L2)
+    if (int r = make_tmap_2d(&tbh, w, Cout, K, K, bn / 2)) return r;
+    tb_half = &tbh;
+  }
   if (R == 1 && S == 1 && stride == 1 && pad == 0) {
     if (int r = make_tmap_2d(&ta, x, M, C, C, BM)) return r;
     ConvGeom g = {};
-    return dispatch(bn, ta, tb, M, Cout, K, g, at, ep, stream);
+    return dispatch(bn, ta, tb, M, Cout, K, g, at, ep, stream, tb_half);
   }
   // IM2COL-mode map over the NHWC activation: dims {C, W, H, N}; the bounding box of filter-window
   // base positions is [-pad, dim-1 + (pad - (R-1))] and is walked with the convolution stride.
@@ -986,7 +1057,7 @@ int conv_common(const void* x, int Nimg, int H, int W, int C, const void* w, int
     if (drv <= 13010 && (long)Nimg * H * W * C * 2 < 131072) reinterpret_cast<uint64_t*>(&ta)[1] &= ~(1ull << 21);
   }
   ConvGeom g = {1, P, Q, S, C / 64, stride, -pad, -pad, H, W};
-  return dispatch(bn, ta, tb, M, Cout, K, g, at, ep, stream);
+  return dispatch(bn, ta, tb, M, Cout, K, g, at, ep, stream, tb_half);
 }
 
 // ------------------------------------------------------------------ Gram-matrix BatchNorm statistics
