@@ -322,6 +322,43 @@ class CrimeLRCN(_BackboneLRCN):
         return _binary_heads(r, self.fc, bf16)
 
 
+class GraphedInference:
+    """Whole eval-mode forward of an LRCN module captured in one CUDA graph for a fixed clip shape -- the single-clip
+    serving path of the reference (medsos_lrcn/src/deployment.py:61-101, worker.py:104-129: `model.eval()`,
+    `torch.no_grad()`, `model(clip[None])`, argmax).  BatchNorm uses the running statistics, dropout is the identity,
+    so the forward is a fixed kernel sequence: replaying the graph removes every per-kernel launch from the host
+    (B = 1 latency is launch bound).  Re-capture (a new GraphedInference) after the weights change.
+
+        infer = GraphedInference(model, clips_like)     # clips_like: a [B,T,3,H,W] CUDA tensor of the serving shape
+        logits = infer(clips)                            # same values as model.eval()(clips)"""
+
+    def __init__(self, model, example):
+        _check_input(example)
+        self.model = model
+        model.eval()
+        self.static_x = example.detach().clone()
+        with torch.no_grad():
+            model(self.static_x)                         # warm-up: weight caches, function attributes, allocator
+            torch.cuda.synchronize(example.device)
+            self.graph = torch.cuda.CUDAGraph()
+            n0 = ops._lib.launch_count()
+            with torch.cuda.graph(self.graph):
+                self.static_out = model(self.static_x)
+            self.n_launch = ops._lib.launch_count() - n0
+
+    def __call__(self, x):
+        if tuple(x.shape) != tuple(self.static_x.shape):
+            raise ValueError(f"captured for clips of shape {tuple(self.static_x.shape)}, got {tuple(x.shape)}")
+        self.static_x.copy_(x)
+        self.graph.replay()
+        ops._lib.call("b2_add_launch_count", self.n_launch)
+        return self.static_out.clone()
+
+    def predict(self, x):
+        """argmax class per clip (train_eval.py:27 / deployment.py: first maximal index)."""
+        return self(x).argmax(dim=1)
+
+
 def count_parameters(model):
     """train_eval.py:121-130: (trainable, frozen) parameter counts."""
     tr = sum(p.numel() for p in model.parameters() if p.requires_grad)
