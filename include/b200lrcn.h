@@ -202,6 +202,16 @@ int b2_bn2d_act_pool_bwd_apply_f32(const float* x, const float* dy, const float*
                                    int W, int pool, void* stream);
 int b2_f64_to_f32(const double* src, float* dst, int n, int accumulate, void* stream);
 
+/* ---- persistent GRU layer (torch.nn.GRU semantics, gate order r,z,n; lrcn/backup_ucf50.py:126, medsos models.py:160-170)
+ * G [B,T,3H] = x W_ih^T + b_ih (hoisted gate GEMM); Whh [3H,H]; bhh [3H] (b_hn stays inside the r product);
+ * out [B,T,*] with row stride out_ld (a direction's slice of the [B,T,dirs*H] output); saved [B,T,4H] = r,z,n,hh_n for
+ * BPTT (NULL for inference); reverse = 1 runs t = T-1..0 (the `_reverse` parameters).
+ * Backward: dG [B,T,3H] (row stride dG_ld) = gradient of G; dWhh / dbhh ACCUMULATED into (caller zeroes). */
+int b2_gru_seq_fwd(const float* G, const float* Whh, const float* bhh, float* out, long out_ld, float* saved, int B, int T,
+                   int H, int reverse, void* stream);
+int b2_gru_seq_bwd(const float* dout, long dout_ld, const float* out, long out_ld, const float* saved, const float* Whh,
+                   float* dG, long dG_ld, float* dWhh, float* dbhh, int B, int T, int H, int reverse, void* stream);
+
 /* ---- whole-stack persistent LSTM (unidirectional nn.LSTM, H <= 64, input width <= 64, T <= 64, <= 8 layers):
  * every layer and timestep in one launch; medsos_lrcn/src/models.py:156-158,205 as tuned by all_config.py:14-17.
  * w_ih / w_hh / b_ih / b_hh (and dw_ih / dw_hh / db) are HOST arrays of `layers` device pointers in nn.LSTM layout

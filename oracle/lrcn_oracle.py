@@ -230,8 +230,38 @@ def lstm_forward(x, params: Dict[str, torch.Tensor], hidden: int, num_layers: in
     return inp
 
 
+def gru_forward(x, params: Dict[str, torch.Tensor], hidden: int, num_layers: int, bidirectional: bool,
+                prefix: str = "lstm."):
+    """nn.GRU(batch_first=True, zero initial state) -- lrcn/backup_ucf50.py:126 (attribute `lstm`), medsos
+    models.py:160-170.  Gate order r,z,n; r = sig(W_ir x + b_ir + W_hr h + b_hr), z likewise,
+    n = tanh(W_in x + b_in + r * (W_hn h + b_hn)), h' = (1 - z) n + z h; `_reverse` runs t = T-1..0."""
+    B, T, _ = x.shape
+    inp = x
+    for layer in range(num_layers):
+        outs = []
+        for d in range(2 if bidirectional else 1):
+            sfx = f"l{layer}" + ("_reverse" if d == 1 else "")
+            w_ih, w_hh = params[f"{prefix}weight_ih_{sfx}"], params[f"{prefix}weight_hh_{sfx}"]
+            b_ih, b_hh = params[f"{prefix}bias_ih_{sfx}"], params[f"{prefix}bias_hh_{sfx}"]
+            h = x.new_zeros(B, hidden)
+            hs = [None] * T
+            for t in (range(T - 1, -1, -1) if d == 1 else range(T)):
+                gi = inp[:, t] @ w_ih.t() + b_ih
+                gh = h @ w_hh.t() + b_hh
+                ir, iz, i_n = gi.split(hidden, dim=1)
+                hr, hz, hn = gh.split(hidden, dim=1)
+                r = torch.sigmoid(ir + hr)
+                z = torch.sigmoid(iz + hz)
+                n = torch.tanh(i_n + r * hn)
+                h = (1.0 - z) * n + z * h
+                hs[t] = h
+            outs.append(torch.stack(hs, dim=1))
+        inp = torch.cat(outs, dim=-1) if bidirectional else outs[0]
+    return inp
+
+
 def small_cnn_lrcn_forward(params: Dict[str, torch.Tensor], x: torch.Tensor, hidden: int,
-                           train: bool = True, lstm_layers: int = 2):
+                           train: bool = True, lstm_layers: int = 2, gru: bool = False):
     """Notebook `LRCN.forward` (nb:174-193): conv1-bn1-relu, conv2-bn2-relu-pool,
     conv3-bn3-relu-pool, (dropout p=0 for parity), reshape(B,T,C*H*W) [channel-major],
     2-layer LSTM, flatten all T, fc.  Returns (logits, dict of new running stats)."""
@@ -252,7 +282,10 @@ def small_cnn_lrcn_forward(params: Dict[str, torch.Tensor], x: torch.Tensor, hid
         if k >= 2:
             y = F.max_pool2d(y, 2, 2)
     feat = y.reshape(B, T, -1)
-    out = lstm_forward(feat, params, hidden, lstm_layers, False, prefix="lstm.")
+    if gru:        # LRCN2 (lrcn/backup_ucf50.py:126,146): one bidirectional GRU layer stored as `lstm`
+        out = gru_forward(feat, params, hidden, 1, True, prefix="lstm.")
+    else:
+        out = lstm_forward(feat, params, hidden, lstm_layers, False, prefix="lstm.")
     logits = out.reshape(B, -1) @ params["fc.weight"].t() + params["fc.bias"]
     return logits, new_stats
 

@@ -221,6 +221,41 @@ def gold_lstm():
         save(f"lstm_{tag}.npz", **arrs)
 
 
+def gold_gru():
+    # nn.GRU as the reference configures it (backup_ucf50.py:126 1-layer bidirectional; models.py:167-169 N layers)
+    torch.manual_seed(6)
+    for tag, (inp, H, layers, bidir, B, T) in {"uni": (10, 6, 2, False, 3, 5), "bi": (9, 7, 2, True, 2, 4)}.items():
+        rnn = torch.nn.GRU(inp, H, num_layers=layers, bidirectional=bidir, batch_first=True)
+        x = torch.randn(B, T, inp, requires_grad=True)
+        out, _ = rnn(x)
+        w = torch.randn_like(out)
+        (out * w).sum().backward()
+        arrs = {"x": x.detach().numpy(), "out": out.detach().numpy(), "w": w.numpy(), "dx": x.grad.numpy(),
+                "meta": np.array(json.dumps(dict(inp=inp, H=H, layers=layers, bidir=bidir)))}
+        for k, p in rnn.named_parameters():
+            arrs["p/" + k] = p.detach().numpy()
+            arrs["g/" + k] = p.grad.numpy()
+        save(f"gru_{tag}.npz", **arrs)
+    # the reference's own LRCN2 class (small CNN + biGRU), one train step
+    LRCN2 = refload.backup_lrcn2()
+    C, T, H, S, B = 5, 4, 8, 16, 3
+    torch.manual_seed(77)
+    m = LRCN2(C, T, H, (3, S, S))
+    m.dropout.p = 0.0
+    gen = torch.Generator().manual_seed(4321)
+    x = torch.randint(0, 256, (B, T, 3, S, S), generator=gen).float() / 255.0
+    y = torch.randint(0, C, (B,), generator=gen)
+    sd0, out, loss, grads, sd1 = run_step(m, x, y)
+    arrs = {"x": x.numpy(), "y": y.numpy(), "logits": out.numpy(), "loss": loss.numpy(),
+            "meta": np.array(json.dumps(dict(num_classes=C, T=T, hidden=H, size=S, B=B,
+                                             source="lrcn/backup_ucf50.py:105-151 LRCN2, dropout p=0")))}
+    for k, v in npd(sd0).items():
+        arrs["sd0/" + k] = v
+    for k, v in npd(grads).items():
+        arrs["grad/" + k] = v
+    save("smallcnn_gru.npz", **arrs)
+
+
 def gold_scan():
     torch.manual_seed(3)
     Bz, L, D, N = 2, 300, 12, 4
@@ -245,3 +280,4 @@ if __name__ == "__main__":
     gold_medsos()
     gold_simple()
     gold_scan()
+    gold_gru()

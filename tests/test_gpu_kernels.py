@@ -270,6 +270,44 @@ def test_lstm_vs_oracle(ops, B, T, In, H, layers, bidir, stack, monkeypatch):
         assert err(ops.lstm_forward(x.to(DEV), rnn), ref) < 1e-5
 
 
+@pytest.mark.parametrize("tag", ["uni", "bi"])
+def test_gru_vs_reference_golden(ops, tag):
+    g, meta = load_golden(f"gru_{tag}.npz")
+    rnn = torch.nn.GRU(meta["inp"], meta["H"], num_layers=meta["layers"], bidirectional=meta["bidir"], batch_first=True)
+    rnn.load_state_dict(golden_tensors(g, "p/"))
+    rnn = rnn.to(DEV)
+    x = torch.from_numpy(g["x"]).to(DEV).requires_grad_(True)
+    out = ops.gru_forward(x, rnn)
+    (out * torch.from_numpy(g["w"]).to(DEV)).sum().backward()
+    assert err(out, torch.from_numpy(g["out"])) < 1e-5
+    assert err(x.grad, torch.from_numpy(g["dx"])) < 1e-4
+    for k, v in golden_tensors(g, "g/").items():
+        assert err(getattr(rnn, k).grad, v) < 1e-4, k
+
+
+@pytest.mark.parametrize("B,T,In,H,layers,bidir", [(5, 7, 24, 32, 2, False), (3, 6, 40, 56, 2, True), (9, 30, 8, 32, 3, False),
+                                                  (2, 1, 3, 5, 1, True), (70, 16, 1024, 32, 1, True), (6, 20, 64, 64, 1, False)])
+def test_gru_vs_oracle(ops, B, T, In, H, layers, bidir):
+    torch.manual_seed(B * T + 1)
+    rnn = torch.nn.GRU(In, H, num_layers=layers, bidirectional=bidir, batch_first=True)
+    x = torch.randn(B, T, In) * (0.3 if In > 256 else 1.0)
+    p = {"lstm." + k: v.detach().clone().requires_grad_(True) for k, v in rnn.named_parameters()}
+    xo = x.clone().requires_grad_(True)
+    ref = O.gru_forward(xo, p, H, layers, bidir)
+    wgt = torch.randn_like(ref)
+    (ref * wgt).sum().backward()
+    rnn = rnn.to(DEV)
+    xg = x.to(DEV).requires_grad_(True)
+    out = ops.gru_forward(xg, rnn)
+    (out * wgt.to(DEV)).sum().backward()
+    assert err(out, ref) < 1e-5
+    assert err(xg.grad, xo.grad) < 1e-4
+    for k, v in rnn.named_parameters():
+        assert err(v.grad, p["lstm." + k].grad) < 1e-4, k
+    with torch.no_grad():
+        assert err(ops.gru_forward(x.to(DEV), rnn), ref) < 1e-5
+
+
 @pytest.mark.parametrize("M,N,gelu", [(37, 8, True), (64, 1024, True), (10, 960, False), (1920, 512, True)])
 def test_act_layernorm_fwd_bwd(ops, M, N, gelu):
     torch.manual_seed(N)

@@ -120,6 +120,36 @@ def test_simple_and_crime_oracle_vs_golden():
     assert err(logits, torch.from_numpy(g["logits"])) < 1e-4
 
 
+@pytest.mark.parametrize("tag", ["uni", "bi"])
+def test_gru_oracle_vs_golden(tag):
+    """Manual GRU cell of the oracle vs torch.nn.GRU outputs and gradients recorded from the reference's engine."""
+    g, meta = load_golden(f"gru_{tag}.npz")
+    p = {"lstm." + k: v.clone().requires_grad_(True) for k, v in golden_tensors(g, "p/").items()}
+    x = torch.from_numpy(g["x"]).requires_grad_(True)
+    out = O.gru_forward(x, p, meta["H"], meta["layers"], meta["bidir"])
+    (out * torch.from_numpy(g["w"])).sum().backward()
+    assert err(out, torch.from_numpy(g["out"])) < 1e-5
+    assert err(x.grad, torch.from_numpy(g["dx"])) < 1e-4
+    for k, v in golden_tensors(g, "g/").items():
+        assert err(p["lstm." + k].grad, v) < 1e-4, k
+
+
+def test_smallcnn_gru_oracle_vs_golden():
+    """LRCN2 (lrcn/backup_ucf50.py:105-151) restated by the oracle vs the reference class's own train step."""
+    g, meta = load_golden("smallcnn_gru.npz")
+    sd = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point else v) for k, v in golden_tensors(g, "sd0/").items()}
+    x, y = torch.from_numpy(g["x"]), torch.from_numpy(g["y"])
+    logits, _ = O.small_cnn_lrcn_forward(sd, x, meta["hidden"], gru=True)
+    O.cross_entropy_mean(logits, y).backward()
+    assert err(logits, torch.from_numpy(g["logits"])) < 1e-4
+    gmax = max(float(np.abs(g[k]).max()) for k in g.files if k.startswith("grad/"))
+    for k, v in golden_tensors(g, "grad/").items():
+        if k.startswith("conv") and k.endswith(".bias"):       # cancelled by the BatchNorm that follows: pure rounding noise
+            assert sd[k].grad.abs().max().item() < 1e-4 * gmax, k
+        else:
+            assert err(sd[k].grad, v, floor=1e-7) < 2e-3, k
+
+
 def test_scan_oracle_vs_golden():
     g = np.load(os.path.join(GOLDEN, "scan.npz"))
     t = lambda k: torch.from_numpy(g[k])

@@ -6,7 +6,7 @@ from ._lib import B200LrcnError  # noqa: F401
 
 
 def __getattr__(name):   # lazy: models/ops import torch + torchvision
-    if name in ("SmallCNNLRCN", "LRCN", "UCF50LRCN", "CrimeLRCN", "GraphedInference", "count_parameters"):
+    if name in ("SmallCNNLRCN", "SmallCNNGRU", "LRCN", "UCF50LRCN", "CrimeLRCN", "GraphedInference", "count_parameters"):
         from . import models
         return getattr(models, name)
     if name in ("ops", "models", "ingest", "backbone", "dp", "scan"):

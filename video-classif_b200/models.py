@@ -65,8 +65,22 @@ class SmallCNNLRCN(nn.Module):
         y = ops.conv_bn_relu_pool(y, self.conv3, self.bn3, True, self.training)
         y = ops.dropout(y, self.dropout.p, self.training)
         feat = y.reshape(B, T, -1)                       # channel-major (c*h*w) flatten, as nb:186
-        out = ops.lstm_forward(feat, self.lstm, bf16=bf16)
+        out = ops.rnn_forward(feat, self.lstm, bf16=bf16)      # nn.LSTM (notebook LRCN) or nn.GRU (LRCN2)
         return ops.linear(out.reshape(B, -1), self.fc.weight, self.fc.bias, bf16=bf16)
+
+
+class SmallCNNGRU(SmallCNNLRCN):
+    """`LRCN2(num_classes, sequence_length, hidden_size, input_shape)` of lrcn/backup_ucf50.py:105-151: the same
+    small frame CNN, Dropout(0.3), ONE bidirectional nn.GRU layer stored under the attribute name `lstm`
+    (checkpoint keys lstm.weight_ih_l0[_reverse] [3H, .]), fc over all T steps of both directions."""
+
+    def __init__(self, num_classes, sequence_length, hidden_size, input_shape=(3, 64, 64), dropout=0.3, precision="fp32"):
+        super().__init__(num_classes, sequence_length, hidden_size, input_shape, dropout=dropout, lstm_layers=1,
+                         precision=precision)
+        cnn_out_size = (input_shape[1] // 4) * (input_shape[2] // 4) * 64
+        self.lstm = nn.GRU(input_size=cnn_out_size, hidden_size=hidden_size, num_layers=1, bidirectional=True,
+                           batch_first=True)
+        self.fc = nn.Linear(hidden_size * sequence_length * 2, num_classes)
 
 
 class _FeatureHandle:
@@ -162,8 +176,8 @@ class LRCN(_BackboneLRCN):
                  rnn_type="lstm", rnn_out="all", bidirectional=False, rnn_layers=3, dropout=0.25,
                  classif_mode="multiclass", pretrained=False, precision="bf16"):
         super().__init__()
-        if rnn_type != "lstm":
-            raise NotImplementedError(f"rnn_type={rnn_type!r}: only the LSTM temporal layer is built (GRU/Mamba are 'next')")
+        if rnn_type not in ("lstm", "gru"):
+            raise NotImplementedError(f"rnn_type={rnn_type!r}: the LSTM and GRU temporal layers are built (the Mamba block is 'next')")
         self.sequence_length = sequence_length
         self.hidden_size = hidden_size
         self.backbone = cnn_backbone
@@ -182,7 +196,8 @@ class LRCN(_BackboneLRCN):
         self.adapt3 = nn.Linear(f // 4, rnn_input_size)
         self.bn3 = nn.LayerNorm(rnn_input_size)
         self.drop1 = nn.Dropout(p=dropout)
-        self.rnn = nn.LSTM(input_size=rnn_input_size, hidden_size=hidden_size, num_layers=rnn_layers,
+        rnn_cls = nn.LSTM if rnn_type == "lstm" else nn.GRU          # models.py:154-170
+        self.rnn = rnn_cls(input_size=rnn_input_size, hidden_size=hidden_size, num_layers=rnn_layers,
                            bidirectional=bidirectional, batch_first=True)
         self.rnn_output_size = hidden_size * (2 if bidirectional else 1)
         fc_in = self.rnn_output_size * (sequence_length if rnn_out == "all" else 1)
@@ -206,7 +221,7 @@ class LRCN(_BackboneLRCN):
         y = ops.dropout(aln(lin(y, self.adapt1.weight, self.adapt1.bias, bf16), self.bn1.weight, self.bn1.bias, True, self.bn1.eps), self.drop1.p, tr)
         y = ops.dropout(aln(lin(y, self.adapt2.weight, self.adapt2.bias, bf16), self.bn2.weight, self.bn2.bias, True, self.bn2.eps), self.drop1.p, tr)
         y = aln(lin(y, self.adapt3.weight, self.adapt3.bias, bf16), self.bn3.weight, self.bn3.bias, True, self.bn3.eps)
-        r = ops.lstm_forward(y, self.rnn, bf16=bf16)
+        r = ops.rnn_forward(y, self.rnn, bf16=bf16)
         r = r.reshape(B, -1) if self.rnn_out == "all" else r[:, -1, :]
         if self.classif_mode == "multiclass":
             o = aln(r, self.bn0.weight, self.bn0.bias, False, self.bn0.eps)

@@ -454,6 +454,93 @@ class LSTMLayerFn(torch.autograd.Function):
         return (dx, None, None, None, *grads)
 
 
+class GRULayerFn(torch.autograd.Function):
+    """One nn.GRU layer, batch_first, zero initial state; params = (w_ih, w_hh, b_ih, b_hh) per direction (forward
+    first, then `_reverse`).  Output [B,T,dirs*H] = cat(fwd, bwd).  The input-to-gate product for all T steps is one
+    hoisted GEMM (tcgen05 when bf16 and large enough), the recurrence one persistent kernel per direction."""
+
+    @staticmethod
+    def forward(ctx, x, hidden, bf16, need_grad, *params):
+        _chk(x, *params)
+        B, T, In = x.shape
+        dirs = len(params) // 4
+        H = hidden
+        xc = x.contiguous()
+        x2 = xc.reshape(B * T, In)
+        out = torch.empty((B, T, dirs * H), device=x.device, dtype=F32)
+        saved = []
+        for d in range(dirs):
+            w_ih, w_hh, b_ih, b_hh = params[4 * d:4 * d + 4]
+            G = _linear_fwd(x2, w_ih, b_ih, bf16)
+            sv = torch.empty((B, T, 4 * H), device=x.device, dtype=F32) if need_grad else None
+            o = out[:, :, d * H:]
+            call("b2_gru_seq_fwd", G.data_ptr(), w_hh.data_ptr(), b_hh.data_ptr(), o.data_ptr(), dirs * H, ptr(sv), B, T, H,
+                 int(d == 1), stream_ptr())
+            saved.append(sv)
+        if need_grad:
+            ctx.save_for_backward(x2, out, *saved, *params)
+        ctx.dims = (B, T, In, H, dirs)
+        ctx.bf16 = bf16
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, T, In, H, dirs = ctx.dims
+        x2, out = ctx.saved_tensors[:2]
+        saved = ctx.saved_tensors[2:2 + dirs]
+        params = ctx.saved_tensors[2 + dirs:]
+        dout = dout.contiguous()
+        H3 = 3 * H
+        big = ctx.bf16 and B * T * H3 * In >= TC_MIN_MACS and H % 8 == 0
+        dG_all = torch.empty((B * T, dirs * H3), device=dout.device, dtype=F32)
+        xf = x2 if x2.dtype == F32 else x2.float()
+        grads = []
+        for d in range(dirs):
+            w_ih, w_hh, b_ih, b_hh = params[4 * d:4 * d + 4]
+            dG = dG_all[:, d * H3:(d + 1) * H3]
+            dWhh = torch.zeros_like(w_hh)
+            dbhh = torch.zeros_like(b_hh)
+            call("b2_gru_seq_bwd", dout[:, :, d * H:].data_ptr(), dirs * H, out[:, :, d * H:].data_ptr(), dirs * H,
+                 saved[d].data_ptr(), w_hh.data_ptr(), dG.data_ptr(), dirs * H3, dWhh.data_ptr(), dbhh.data_ptr(), B, T, H,
+                 int(d == 1), stream_ptr())
+            if big:
+                dWih = gemm_tn(transpose_cast_bf16(dG), transpose_cast_bf16(xf), out_dtype=F32)
+            else:
+                dWih = sgemm(dG, xf, trans_a=True)
+            grads += [dWih, dWhh, colsum(dG), dbhh]
+        dx = None
+        if ctx.needs_input_grad[0]:
+            w_cat = params[0] if dirs == 1 else torch.cat([params[0], params[4]], dim=0)
+            if big:
+                dx = gemm_tn(cast_bf16(dG_all), transpose_cast_bf16(w_cat), out_dtype=F32)
+            else:
+                dx = sgemm(dG_all, w_cat)
+            dx = dx.reshape(B, T, In)
+        return (dx, None, None, None, *grads)
+
+
+def gru_forward(x, gru_module, bf16=False):
+    """Runs a torch.nn.GRU *parameter container* (batch_first, dropout 0) on the persistent kernels."""
+    assert gru_module.batch_first
+    dirs = 2 if gru_module.bidirectional else 1
+    H = gru_module.hidden_size
+    need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in gru_module.parameters()))
+    y = x
+    for layer in range(gru_module.num_layers):
+        params = []
+        for d in range(dirs):
+            sfx = f"_l{layer}" + ("_reverse" if d == 1 else "")
+            params += [getattr(gru_module, "weight_ih" + sfx), getattr(gru_module, "weight_hh" + sfx),
+                       getattr(gru_module, "bias_ih" + sfx), getattr(gru_module, "bias_hh" + sfx)]
+        y = GRULayerFn.apply(y, H, bf16, need_grad, *params)
+    return y
+
+
+def rnn_forward(x, module, bf16=False):
+    """nn.LSTM or nn.GRU parameter container -> [B,T,dirs*H]."""
+    return gru_forward(x, module, bf16) if isinstance(module, torch.nn.GRU) else lstm_forward(x, module, bf16)
+
+
 def _ptr_array(tensors):
     import ctypes
     arr = (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
