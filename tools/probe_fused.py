@@ -16,7 +16,7 @@ print(torch.cuda.get_device_name(0), "frames", NF, flush=True)
 
 
 def timeit(fn, reps=5):
-    if mode in ("ncu", "gram"):
+    if mode in ("ncu", "ncu2", "gram"):
         fn()
         torch.cuda.synchronize()
         return float("nan")
@@ -96,6 +96,14 @@ if mode == "quick":
 elif mode == "gram":
     case("l1.conv3", 28, 64, 256, 1, 1, 0, ["gram", "a+o+res"])
     case("l2.conv3", 14, 128, 512, 1, 1, 0, ["gram", "a+o+res"])
+elif mode == "tf":       # is the A transform worth it at the 7x7 / 4x4 stages?
+    case("l3.conv3", 7, 256, 1024, 1, 1, 0, ["apply", "a+o+res", "o+res", "a+statsonly", "statsonly", "gram"])
+    case("l4.conv3", 4, 512, 2048, 1, 1, 0, ["apply", "a+o+res", "o+res", "a+statsonly", "statsonly"])
+    case("l2.conv3", 14, 128, 512, 1, 1, 0, ["apply", "a+o+res", "o+res"])
+elif mode == "ncu2":     # the 7x7 / 4x4 stages: conv3 + BN3 + shortcut, statistics-only pass, 1x1 reduce
+    case("l3.conv3", 7, 256, 1024, 1, 1, 0, ["a+o+res", "plain"])
+    case("l4.conv3", 4, 512, 2048, 1, 1, 0, ["a+o+res", "a+statsonly"])
+    case("l4.conv2", 4, 512, 512, 3, 1, 1, ["stats"])
 elif mode == "ncu":      # one launch each of the representative kernels, for `ncu --set full`
     case("l1.conv3", 28, 64, 256, 1, 1, 0, ["a+o+res", "gram"])      # EPI_POST (HBM bound) + Gram statistics
     case("l3.conv2", 7, 256, 256, 3, 1, 1, ["stats"])                 # EPI_BF16 3x3 implicit GEMM (tensor bound)

@@ -240,14 +240,22 @@ class ResNetRunner:
                             dbn = blk.downsample[1]
                             rd = conv2d_bn_nhwc(y, w[pfx + ".downsample.0"], stride, 0, stats=stats_of(dbn),
                                                 fin=fin_of(dbn))
-                        if train and r2.shape[-1] in GRAM_CHANNELS:
+                        # BN2 + ReLU on conv3's input: folded into conv3's A-tile transform for the narrow stages; at
+                        # 256+ channels the transform warps are the serial stage of a short-K pipeline (measured:
+                        # 62 -> 39 us statistics pass, 67 -> 46 us output pass at layer4), so the small tensor is
+                        # normalised in place once instead
+                        a2 = ss_of(blk.bn2)
+                        if r2.shape[-1] >= 256:
+                            scale_shift_apply(r2, a2[0], a2[1], relu=True)
+                            a2 = None
+                        if train and a2 is not None and r2.shape[-1] in GRAM_CHANNELS:
                             # BN3 statistics from the Gram matrix of conv3's (transformed) input: one HBM-bound
                             # pass over the small tensor instead of a full conv3 whose output is thrown away
-                            conv1x1_gram_bnstats(r2, w[pfx + ".conv3"], ss_of(blk.bn2), fin_of(blk.bn3))
+                            conv1x1_gram_bnstats(r2, w[pfx + ".conv3"], a2, fin_of(blk.bn3))
                         elif train:            # statistics-only pass of conv3
-                            conv2d_bn_nhwc(r2, w[pfx + ".conv3"], 1, 0, a=ss_of(blk.bn2), stats=stats_of(blk.bn3),
+                            conv2d_bn_nhwc(r2, w[pfx + ".conv3"], 1, 0, a=a2, stats=stats_of(blk.bn3),
                                            fin=fin_of(blk.bn3), store=False)
-                        y = conv2d_bn_nhwc(r2, w[pfx + ".conv3"], 1, 0, a=ss_of(blk.bn2), o=ss_of(blk.bn3),
+                        y = conv2d_bn_nhwc(r2, w[pfx + ".conv3"], 1, 0, a=a2, o=ss_of(blk.bn3),
                                            res=rd if ds else y, r=ss_of(dbn) if ds else None, relu=True)
                         del r2
                     else:
