@@ -96,6 +96,12 @@ if mode == "quick":
 elif mode == "gram":
     case("l1.conv3", 28, 64, 256, 1, 1, 0, ["gram", "a+o+res"])
     case("l2.conv3", 14, 128, 512, 1, 1, 0, ["gram", "a+o+res"])
+elif mode == "deep":     # long-K tensor-bound layers: 3 vs 4 operand stages (B2_NO_DEEP=1)
+    case("l3.conv1", 7, 1024, 256, 1, 1, 0, ["stats"])
+    case("l3.conv2", 7, 256, 256, 3, 1, 1, ["stats"])
+    case("l4.conv1", 4, 2048, 512, 1, 1, 0, ["stats"])
+    case("l4.conv2", 4, 512, 512, 3, 1, 1, ["stats"])
+    case("l4.conv3", 4, 512, 2048, 1, 1, 0, ["statsonly"])
 elif mode == "tf":       # is the A transform worth it at the 7x7 / 4x4 stages?
     case("l3.conv3", 7, 256, 1024, 1, 1, 0, ["apply", "a+o+res", "o+res", "a+statsonly", "statsonly", "gram"])
     case("l4.conv3", 4, 512, 2048, 1, 1, 0, ["apply", "a+o+res", "o+res", "a+statsonly", "statsonly"])

@@ -109,14 +109,16 @@ constexpr int kStgBytes = 32 * 64;  // epilogue staging tile: 32 rows x 32 bf16 
 
 constexpr int kResSlots = 4;         // EPI_POST: per-warp ring of shortcut / output tiles (power of two)
 
-template <int BN, int MODE>
+template <int BN, int MODE, bool DEEP = false>
 struct SmemLayout {
   static constexpr bool kPost = MODE == EPI_POST;
   static constexpr int kStageBytes = (BM * BK + BN * BK) * 2;
-  // EPI_POST trades operand stages for the 64 KB shortcut ring (its GEMMs are short-K and memory bound)
+  // EPI_POST trades operand stages for the 64 KB shortcut ring (its GEMMs are short-K and memory bound).
+  // DEEP (BN = 256, long K, tensor bound): a 4th operand stage paid for with the second staging tile -- three
+  // 48 KB stages cover ~0.8 us of TMA latency, less than the latency of an L2 hit under load
   static constexpr int kStages = kPost ? (BN >= 256 ? 3 : (BN >= 128 ? 4 : 5))
-                                       : (BN >= 256 ? 3 : (BN >= 128 ? 5 : (BN >= 64 ? 7 : 8)));
-  static constexpr int kStgBufs = 2;                     // output staging tiles per epilogue warp (not EPI_POST)
+                                       : (BN >= 256 ? (DEEP ? 4 : 3) : (BN >= 128 ? 5 : (BN >= 64 ? 7 : 8)));
+  static constexpr int kStgBufs = DEEP ? 1 : 2;          // output staging tiles per epilogue warp (not EPI_POST)
   static constexpr int kTileBytes = kStageBytes * kStages;
   static constexpr int kBarOffset = kTileBytes;
   static constexpr int kNumBars = 3 * kStages + 4 + kEpiWarps * kResSlots;
@@ -137,12 +139,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
   return d;
 }
 
-template <int BN, int MODE, bool TF, bool CL = false>
+template <int BN, int MODE, bool TF, bool CL = false, bool DEEP = false>
 __global__ void __launch_bounds__(TF ? kThreadsTf : kThreadsNoTf, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_r, int M, int N,
                int K, ConvGeom g, ATransform at, EpiParams ep) {
-  using L = SmemLayout<BN, MODE>;
+  using L = SmemLayout<BN, MODE, DEEP>;
   constexpr int kStages = L::kStages;
   constexpr uint32_t kTmemCols = 2 * BN;  // two accumulators (32 <= cols <= 512, power of two)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -874,13 +876,13 @@ int make_tmap_2d(CUtensorMap* map, const void* base, long rows, long cols, long 
   return 0;
 }
 
-template <int BN, int MODE, bool TF, bool CL = false>
+template <int BN, int MODE, bool TF, bool CL = false, bool DEEP = false>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tr, int M, int N,
                 int K, const ConvGeom& g, const ATransform& at, const EpiParams& ep, cudaStream_t stream) {
-  using L = SmemLayout<BN, MODE>;
+  using L = SmemLayout<BN, MODE, DEEP>;
   static bool attr_set = false;
   if (!attr_set) {
-    B2_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, MODE, TF, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B2_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, MODE, TF, CL, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        L::kTotal));
     attr_set = true;
   }
@@ -901,10 +903,10 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    B2_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, MODE, TF, CL>, ta, tb, td, tr, M, N, K, g, at, ep));
+    B2_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, MODE, TF, CL, DEEP>, ta, tb, td, tr, M, N, K, g, at, ep));
   } else {
-    gemm_tc_kernel<BN, MODE, TF, CL><<<grid, TF ? kThreadsTf : kThreadsNoTf, L::kTotal, stream>>>(ta, tb, td, tr, M, N, K,
-                                                                                                g, at, ep);
+    gemm_tc_kernel<BN, MODE, TF, CL, DEEP><<<grid, TF ? kThreadsTf : kThreadsNoTf, L::kTotal, stream>>>(ta, tb, td, tr, M,
+                                                                                                      N, K, g, at, ep);
   }
   B2_LAUNCH_CHECK("gemm_tc_kernel");
   return 0;
@@ -933,6 +935,10 @@ int dispatch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const CUte
   if constexpr (MODE != EPI_GENERIC) {
     if (bn == 256 && tb_half != nullptr)      // two-CTA clusters with the weight tile multicast (see the kernel)
       return launch_gemm<256, MODE, TF, true>(ta, *tb_half, td, tr, M, N, K, g, at, ep, stream);
+  }
+  if constexpr ((MODE == EPI_BF16 || MODE == EPI_STATS) && !TF) {
+    if (bn == 256 && K >= 512 && getenv("B2_NO_DEEP") == nullptr)   // long K: four operand stages
+      return launch_gemm<256, MODE, TF, false, true>(ta, tb, td, tr, M, N, K, g, at, ep, stream);
   }
   switch (bn) {
     case 256: return launch_gemm<256, MODE, TF>(ta, tb, td, tr, M, N, K, g, at, ep, stream);
