@@ -16,7 +16,7 @@ print(torch.cuda.get_device_name(0), "frames", NF, flush=True)
 
 
 def timeit(fn, reps=5):
-    if mode in ("ncu", "ncu2", "gram"):
+    if mode in ("ncu", "ncu2", "ncu3", "gram"):
         fn()
         torch.cuda.synchronize()
         return float("nan")
@@ -96,6 +96,9 @@ if mode == "quick":
 elif mode == "gram":
     case("l1.conv3", 28, 64, 256, 1, 1, 0, ["gram", "a+o+res"])
     case("l2.conv3", 14, 128, 512, 1, 1, 0, ["gram", "a+o+res"])
+elif mode == "ncu3":
+    case("l3.conv1", 7, 1024, 256, 1, 1, 0, ["stats"])
+    case("l2.conv1", 14, 512, 128, 1, 1, 0, ["stats"])
 elif mode == "deep":     # long-K tensor-bound layers: 3 vs 4 operand stages (B2_NO_DEEP=1)
     case("l3.conv1", 7, 1024, 256, 1, 1, 0, ["stats"])
     case("l3.conv2", 7, 256, 256, 3, 1, 1, ["stats"])
