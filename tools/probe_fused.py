@@ -16,7 +16,7 @@ print(torch.cuda.get_device_name(0), "frames", NF, flush=True)
 
 
 def timeit(fn, reps=5):
-    if mode in ("ncu", "ncu2", "ncu3", "gram"):
+    if mode in ("ncu", "ncu2", "ncu3", "ncu4", "gram"):
         fn()
         torch.cuda.synchronize()
         return float("nan")
@@ -96,6 +96,8 @@ if mode == "quick":
 elif mode == "gram":
     case("l1.conv3", 28, 64, 256, 1, 1, 0, ["gram", "a+o+res"])
     case("l2.conv3", 14, 128, 512, 1, 1, 0, ["gram", "a+o+res"])
+elif mode == "ncu4":
+    case("l1.conv2", 28, 64, 64, 3, 1, 1, ["halo+a"])
 elif mode == "ncu3":
     case("l3.conv1", 7, 1024, 256, 1, 1, 0, ["stats"])
     case("l2.conv1", 14, 512, 128, 1, 1, 0, ["stats"])

@@ -158,7 +158,12 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     constexpr uint32_t idesc = make_idesc(128, kN);
     uint64_t* ready_bar = TF ? tf_bar : full_bar;
     mbar_wait(w_bar, 0);
-    const uint32_t w_addr = smem_u32(w_s);
+    // descriptors are built once: the address field (bits 0..13, 16-byte units) of a tap / k-step is the base
+    // plus a constant, so the single issuing thread spends two 64-bit adds per MMA instead of two rebuilds
+    const uint64_t db0 = make_sw128_desc(smem_u32(w_s));
+    uint32_t a_off[kTaps];
+#pragma unroll
+    for (int t = 0; t < kTaps; ++t) a_off[t] = (uint32_t)(((t / 3) * g.Wp + (t % 3)) * 8);   // halo rows * 128 B / 16
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -169,15 +174,13 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       tc_fence_after();
       if (lane == 0) {
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kN);
-        const uint32_t st = smem_u32(stage_s + stage * g.stage_bytes);
+        const uint64_t da0 = make_sw128_desc_rows(smem_u32(stage_s + stage * g.stage_bytes), 0, 0);
 #pragma unroll
         for (int t = 0; t < kTaps; ++t) {
-          const int shift = (t / 3) * g.Wp + (t % 3);            // halo rows between output row u and its tap pixel
 #pragma unroll
           for (int k = 0; k < kC / 16; ++k) {
-            const uint64_t da = make_sw128_desc_rows(st, shift, k * 32);
-            const uint64_t db = make_sw128_desc(w_addr + (uint32_t)(t * kWTileBytes + k * 32));
-            tc_mma_bf16(d_tmem, da, db, idesc, (t | k) != 0);
+            tc_mma_bf16(d_tmem, da0 + (uint64_t)(a_off[t] + k * 2), db0 + (uint64_t)(t * (kWTileBytes / 16) + k * 2), idesc,
+                        (t | k) != 0);
           }
         }
         tc_commit(&empty_bar[stage]);

@@ -207,6 +207,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (CL) cluster_sync();          // the peer's barriers exist before any multicast can reach them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  grid_dependency_wait();          // PDL: the set-up above overlapped the previous kernel's tail; its results are visible now
+  grid_launch_dependents();
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
@@ -889,25 +891,30 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
   const int m_blocks = CL ? ((b2_ceil_div(M, BM) + 1) & ~1) : b2_ceil_div(M, BM);
   const int tiles = m_blocks * b2_ceil_div(N, BN);
   int grid = tiles < b2_num_sms() ? tiles : b2_num_sms();
-  if (CL) {
-    grid &= ~1;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(TF ? kThreadsTf : kThreadsNoTf);
-    cfg.dynamicSmemBytes = L::kTotal;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    B2_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, MODE, TF, CL, DEEP>, ta, tb, td, tr, M, N, K, g, at, ep));
-  } else {
-    gemm_tc_kernel<BN, MODE, TF, CL, DEEP><<<grid, TF ? kThreadsTf : kThreadsNoTf, L::kTotal, stream>>>(ta, tb, td, tr, M,
-                                                                                                      N, K, g, at, ep);
+  if (CL) grid &= ~1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(TF ? kThreadsTf : kThreadsNoTf);
+  cfg.dynamicSmemBytes = L::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  static const bool pdl = getenv("B2_PDL") != nullptr;   // opt-in: measured no gain (encoder pass 5.02 vs 5.01 ms)
+  if (pdl) {        // programmatic dependent launch: start the set-up while the previous kernel drains
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
   }
+  if (CL) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  B2_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, MODE, TF, CL, DEEP>, ta, tb, td, tr, M, N, K, g, at, ep));
   B2_LAUNCH_CHECK("gemm_tc_kernel");
   return 0;
 }

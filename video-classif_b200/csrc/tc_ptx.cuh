@@ -121,6 +121,13 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// (barrier init, TMEM allocation, descriptor prefetch) while the previous kernel in the stream is still draining;
+// everything that READS memory the previous kernel wrote must come after this wait (a no-op without the attribute).
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// ... and lets the NEXT kernel's CTAs be scheduled as soon as this kernel's CTAs leave their SMs
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- thread-block clusters: rank, cluster barrier, multicast TMA load, multicast tcgen05 commit ----
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
