@@ -237,6 +237,16 @@ int b2_lstm_stack_bwd(const float* dout, const float* x, int In0, const void* co
 int b2_selective_scan_fwd(const float* u, const float* delta, const float* A, const float* B, const float* C, float* y,
                           int batch, int L, int D, int N, int chunk_reset, int reverse, void* stream);
 
+/* Elementwise pieces of the Mamba ResidualBlock around the scan (medsos_lrcn/src/models.py:9-117), forward only, fp32:
+ * RMSNorm over the last dim; causal depthwise Conv1d over time (k taps, padding k-1, output trimmed to L) + SiLU on
+ * [B, L, D] tensors (x row stride x_ld >= D: a column slice of in_proj's output); softplus (threshold 20);
+ * y = a * silu(res[:, c % res_cols]) (res row stride res_ld). */
+int b2_rmsnorm_f32(const float* x, const float* w, float* y, long rows, int D, float eps, void* stream);
+int b2_dwconv1d_silu_f32(const float* x, long x_ld, const float* w, const float* b, float* y, int B, int L, int D, int K,
+                         void* stream);
+int b2_softplus_f32(const float* x, float* y, long n, void* stream);
+int b2_mul_silu_f32(const float* a, const float* res, long res_ld, int res_cols, float* y, long rows, int cols, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -438,6 +438,35 @@ def selective_scan(u, delta, A, Bm, Cm, chunk_reset: Optional[int] = 256, revers
     return y
 
 
+def mamba_block_forward(sd, x, prefix, bidirectional=False, eps=1e-5):
+    """medsos_lrcn/src/models.py:19-117 `ResidualBlock.forward`: mixer(norm(x)) + x, restated functionally.
+    norm: x * rsqrt(mean(x^2) + eps) * w; mixer: in_proj -> split (x, res) -> causal depthwise conv1d (padding k-1,
+    trimmed to L) -> SiLU -> x_proj -> split (delta_raw, B, C) -> softplus(dt_proj) -> A = -exp(A_log) -> scan forward
+    [and reversed: u / delta flipped, B / C not] -> y * silu(res [repeated when bidirectional]) -> out_proj."""
+    g = lambda k: sd[prefix + k]
+    Bsz, L, dm = x.shape
+    xn = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps) * g("norm.weight")
+    xr = xn @ g("mixer.in_proj.weight").t() + g("mixer.in_proj.bias")
+    di = g("mixer.A_log").shape[0]
+    n = g("mixer.A_log").shape[1]
+    xi, res = xr[..., :di], xr[..., di:]
+    w = g("mixer.conv1d.weight")
+    K = w.shape[-1]
+    xc = F.conv1d(xi.transpose(1, 2), w, g("mixer.conv1d.bias"), padding=K - 1, groups=di)[:, :, :L].transpose(1, 2)
+    xc = xc * torch.sigmoid(xc)
+    xp = xc @ g("mixer.x_proj.weight").t()
+    dt_rank = g("mixer.dt_proj.weight").shape[1]
+    delta = F.softplus(xp[..., :dt_rank] @ g("mixer.dt_proj.weight").t() + g("mixer.dt_proj.bias"))
+    Bm, Cm = xp[..., dt_rank:dt_rank + n], xp[..., dt_rank + n:]
+    A = -torch.exp(g("mixer.A_log"))
+    y = selective_scan(xc, delta, A, Bm, Cm, chunk_reset=None)
+    if bidirectional:
+        y = torch.cat([y, selective_scan(xc, delta, A, Bm, Cm, chunk_reset=None, reverse=True)], dim=-1)
+        res = torch.cat([res, res], dim=-1)
+    y = y * (res * torch.sigmoid(res))
+    return y @ g("mixer.out_proj.weight").t() + g("mixer.out_proj.bias") + x
+
+
 # --------------------------------------------------------------------------------------
 # 5. Train step + prediction (train_eval.py:20-43)
 # --------------------------------------------------------------------------------------

@@ -256,6 +256,21 @@ def gold_gru():
     save("smallcnn_gru.npz", **arrs)
 
 
+def gold_mamba():
+    # the reference's own ResidualBlock (medsos models.py:107-117) as LRCN builds it: d_inner = 2 d_model, n_state = dt_rank = H
+    mod = refload.medsos_models()
+    for tag, bidir in (("uni", False), ("bi", True)):
+        torch.manual_seed(31 + bidir)
+        blk = mod.ResidualBlock(8, 16, 32, 32, bidirectional=bidir).eval()
+        x = torch.randn(3, 16, 8)
+        with torch.no_grad():
+            out = blk(x)
+        arrs = {"x": x.numpy(), "out": out.numpy(), "meta": np.array(json.dumps(dict(bidir=bidir, d_model=8, n_state=32)))}
+        for k, v in blk.state_dict().items():
+            arrs["p/" + k] = v.numpy()
+        save(f"mamba_block_{tag}.npz", **arrs)
+
+
 def gold_scan():
     torch.manual_seed(3)
     Bz, L, D, N = 2, 300, 12, 4
@@ -281,3 +296,4 @@ if __name__ == "__main__":
     gold_simple()
     gold_scan()
     gold_gru()
+    gold_mamba()

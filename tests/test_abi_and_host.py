@@ -98,8 +98,14 @@ def test_state_dict_layout_matches_reference_checkpoints():
     assert ck["fc.2.weight"].shape == (1, 2 * 56 * 4) and "adapt.weight" in ck
     with pytest.raises(NotImplementedError):
         vc.LRCN(4, 3, 32, 8, cnn_backbone="densenet121")
-    with pytest.raises(NotImplementedError):
-        vc.LRCN(4, 3, 32, 8, cnn_backbone="resnet18", rnn_type="mamba")
+    mam = vc.LRCN(4, 3, 32, 8, cnn_backbone="resnet18", rnn_type="mamba", rnn_layers=2).state_dict()   # models.py:159-164
+    assert mam["rnn.1.mixer.A_log"].shape == (16, 32) and mam["rnn.0.mixer.in_proj.weight"].shape == (32, 8)
+    assert mam["rnn.0.mixer.conv1d.weight"].shape == (16, 1, 3) and mam["rnn.0.mixer.x_proj.weight"].shape == (96, 16)
+    assert mam["rnn.0.norm.weight"].shape == (8,) and mam["fc.weight"].shape == (12, 24)
+    gru = vc.LRCN(4, 3, 32, 8, cnn_backbone="resnet18", rnn_type="gru", rnn_layers=2, bidirectional=True).state_dict()
+    assert gru["rnn.weight_ih_l1_reverse"].shape == (96, 64)
+    with pytest.raises(ValueError):
+        vc.LRCN(4, 3, 32, 8, cnn_backbone="resnet18", rnn_type="transformer")
 
 
 def test_ingest_divisor_rounding_is_exact_in_fp32():

@@ -150,6 +150,15 @@ def test_smallcnn_gru_oracle_vs_golden():
             assert err(sd[k].grad, v, floor=1e-7) < 2e-3, k
 
 
+@pytest.mark.parametrize("tag", ["uni", "bi"])
+def test_mamba_block_oracle_vs_golden(tag):
+    """Mamba ResidualBlock restated by the oracle vs the output of the reference's own class (medsos models.py:107-117)."""
+    g, meta = load_golden(f"mamba_block_{tag}.npz")
+    sd = golden_tensors(g, "p/")
+    out = O.mamba_block_forward(sd, torch.from_numpy(g["x"]), "", bidirectional=meta["bidir"])
+    assert err(out, torch.from_numpy(g["out"])) < 1e-5
+
+
 def test_scan_oracle_vs_golden():
     g = np.load(os.path.join(GOLDEN, "scan.npz"))
     t = lambda k: torch.from_numpy(g[k])

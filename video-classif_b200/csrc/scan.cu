@@ -110,3 +110,106 @@ B2_API int b2_selective_scan_fwd(const float* u, const float* delta, const float
   B2_LAUNCH_CHECK("selective_scan_fwd_kernel");
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// The elementwise pieces of the reference's Mamba ResidualBlock around the scan (medsos_lrcn/src/models.py:9-117,
+// lrcn/videomamba.py:203-330), forward only:
+//   rmsnorm        x * rsqrt(mean(x^2, -1) + eps) * w                                   (models.py:9-17)
+//   dwconv1d_silu  Conv1d(d, d, k, groups=d, padding=k-1)(x)[:, :, :L] then SiLU: causal depthwise conv over time,
+//                  y[l] = b + sum_j w[j] x[l - (k-1) + j]                               (models.py:83-88)
+//   softplus       log(1 + exp(x)) with torch's threshold 20                            (models.py:92)
+//   mul_silu       y * silu(res)                                                        (models.py:103)
+namespace {
+
+__device__ __forceinline__ float siluf_(float x) { return x / (1.f + __expf(-x)); }
+
+__global__ void __launch_bounds__(256)
+rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y, long rows, int D,
+               float eps) {
+  const int lane = threadIdx.x & 31;
+  const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);      // one warp per row
+  if (row >= rows) return;
+  const float* p = x + row * D;
+  float s = 0.f;
+  for (int c = lane; c < D; c += 32) s = fmaf(p[c], p[c], s);
+  s = warp_sum(s);
+  const float r = rsqrtf(s / (float)D + eps);
+  for (int c = lane; c < D; c += 32) y[row * D + c] = p[c] * r * w[c];
+}
+
+// x, y [B, L, ld] (channels innermost, the reference rearranges to [B, D, L] only for nn.Conv1d); w [D, K]; b [D]
+__global__ void __launch_bounds__(256)
+dwconv1d_silu_kernel(const float* __restrict__ x, long x_ld, const float* __restrict__ w, const float* __restrict__ b,
+                     float* __restrict__ y, int B, int L, int D, int K) {
+  const long total = (long)B * L * D;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int d = (int)(i % D);
+    const long bl = i / D;
+    const int l = (int)(bl % L);
+    const long bb = bl / L;
+    float acc = b != nullptr ? b[d] : 0.f;
+    for (int j = 0; j < K; ++j) {
+      const int ls = l - (K - 1) + j;
+      if (ls >= 0) acc = fmaf(w[d * K + j], x[(bb * L + ls) * x_ld + d], acc);
+    }
+    y[i] = siluf_(acc);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+softplus_kernel(const float* __restrict__ x, float* __restrict__ y, long n) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    y[i] = v > 20.f ? v : log1pf(expf(v));
+  }
+}
+
+// y[r, c] = a[r, c] * silu(res[r, c % res_cols])  (res_cols < cols: the bidirectional block repeats res)
+__global__ void __launch_bounds__(256)
+mul_silu_kernel(const float* __restrict__ a, const float* __restrict__ res, long res_ld, int res_cols, float* __restrict__ y,
+                long rows, int cols) {
+  const long total = rows * cols;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / cols;
+    const int c = (int)(i - r * cols);
+    y[i] = a[i] * siluf_(res[r * res_ld + (c % res_cols)]);
+  }
+}
+
+int ew_grid(long n) {
+  long blocks = (n + 255) / 256;
+  const long cap = (long)b2_num_sms() * 8;
+  return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+}  // namespace
+
+B2_API int b2_rmsnorm_f32(const float* x, const float* w, float* y, long rows, int D, float eps, void* stream) {
+  B2_ARG_CHECK(x && w && y && rows > 0 && D > 0, "b2_rmsnorm_f32: null pointer or empty");
+  rmsnorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, w, y, rows, D, eps);
+  B2_LAUNCH_CHECK("rmsnorm_kernel");
+  return 0;
+}
+
+B2_API int b2_dwconv1d_silu_f32(const float* x, long x_ld, const float* w, const float* b, float* y, int B, int L, int D,
+                                int K, void* stream) {
+  B2_ARG_CHECK(x && w && y && B > 0 && L > 0 && D > 0 && K > 0 && x_ld >= D, "b2_dwconv1d_silu_f32: bad arguments");
+  dwconv1d_silu_kernel<<<ew_grid((long)B * L * D), 256, 0, (cudaStream_t)stream>>>(x, x_ld, w, b, y, B, L, D, K);
+  B2_LAUNCH_CHECK("dwconv1d_silu_kernel");
+  return 0;
+}
+
+B2_API int b2_softplus_f32(const float* x, float* y, long n, void* stream) {
+  B2_ARG_CHECK(x && y && n > 0, "b2_softplus_f32: null pointer or empty");
+  softplus_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(x, y, n);
+  B2_LAUNCH_CHECK("softplus_kernel");
+  return 0;
+}
+
+B2_API int b2_mul_silu_f32(const float* a, const float* res, long res_ld, int res_cols, float* y, long rows, int cols,
+                           void* stream) {
+  B2_ARG_CHECK(a && res && y && rows > 0 && cols > 0 && res_cols > 0 && res_ld >= res_cols, "b2_mul_silu_f32: bad arguments");
+  mul_silu_kernel<<<ew_grid(rows * cols), 256, 0, (cudaStream_t)stream>>>(a, res, res_ld, res_cols, y, rows, cols);
+  B2_LAUNCH_CHECK("mul_silu_kernel");
+  return 0;
+}

@@ -83,6 +83,44 @@ class SmallCNNGRU(SmallCNNLRCN):
         self.fc = nn.Linear(hidden_size * sequence_length * 2, num_classes)
 
 
+class RMSNorm(nn.Module):
+    """Parameter container of medsos_lrcn/src/models.py:9-17."""
+
+    def __init__(self, d_model, eps=1e-5):
+        super().__init__()
+        self.eps = eps
+        self.weight = nn.Parameter(torch.ones(d_model))
+
+
+class ParallelMamba(nn.Module):
+    """Parameter container of medsos_lrcn/src/models.py:19-45 (same attribute names, shapes and default init)."""
+
+    def __init__(self, d_model, d_inner, n_state, dt_rank, bias=True, conv_bias=True, kernel_size=3, bidirectional=False):
+        super().__init__()
+        self.d_model, self.d_inner, self.n_state, self.dt_rank = d_model, d_inner, n_state, dt_rank
+        self.bidirectional = bidirectional
+        self.A_log = nn.Parameter(torch.randn(d_inner, n_state))
+        self.D = nn.Parameter(torch.randn(d_inner))
+        self.in_proj = nn.Linear(d_model, d_inner * 2, bias=bias)
+        self.conv1d = nn.Conv1d(d_inner, d_inner, bias=conv_bias, kernel_size=kernel_size, groups=d_inner,
+                                padding=kernel_size - 1)
+        self.x_proj = nn.Linear(d_inner, dt_rank + n_state * 2, bias=False)
+        self.dt_proj = nn.Linear(dt_rank, d_inner, bias=True)
+        self.out_proj = nn.Linear(d_inner * (2 if bidirectional else 1), d_model, bias=bias)
+
+
+class ResidualBlock(nn.Module):
+    """medsos_lrcn/src/models.py:107-117: `mixer(norm(x)) + x`, executed by ops.mamba_block_forward (forward only)."""
+
+    def __init__(self, d_model, d_inner, n_state, dt_rank, bias=True, conv_bias=True, kernel_size=3, bidirectional=False):
+        super().__init__()
+        self.mixer = ParallelMamba(d_model, d_inner, n_state, dt_rank, bias, conv_bias, kernel_size, bidirectional)
+        self.norm = RMSNorm(d_model)
+
+    def forward(self, x):
+        return ops.mamba_block_forward(x, self, self.mixer.bidirectional)
+
+
 class _FeatureHandle:
     """Result of encode_async(): the feature tensor (valid once `event` has fired) for clips of `shape`."""
     __slots__ = ("tensor", "event", "shape")
@@ -176,8 +214,8 @@ class LRCN(_BackboneLRCN):
                  rnn_type="lstm", rnn_out="all", bidirectional=False, rnn_layers=3, dropout=0.25,
                  classif_mode="multiclass", pretrained=False, precision="bf16"):
         super().__init__()
-        if rnn_type not in ("lstm", "gru"):
-            raise NotImplementedError(f"rnn_type={rnn_type!r}: the LSTM and GRU temporal layers are built (the Mamba block is 'next')")
+        if rnn_type not in ("lstm", "gru", "mamba"):
+            raise ValueError(f"rnn_type={rnn_type!r}: expected 'lstm', 'gru' or 'mamba' (models.py:154-170)")
         self.sequence_length = sequence_length
         self.hidden_size = hidden_size
         self.backbone = cnn_backbone
@@ -196,10 +234,15 @@ class LRCN(_BackboneLRCN):
         self.adapt3 = nn.Linear(f // 4, rnn_input_size)
         self.bn3 = nn.LayerNorm(rnn_input_size)
         self.drop1 = nn.Dropout(p=dropout)
-        rnn_cls = nn.LSTM if rnn_type == "lstm" else nn.GRU          # models.py:154-170
-        self.rnn = rnn_cls(input_size=rnn_input_size, hidden_size=hidden_size, num_layers=rnn_layers,
-                           bidirectional=bidirectional, batch_first=True)
-        self.rnn_output_size = hidden_size * (2 if bidirectional else 1)
+        if rnn_type == "mamba":                                       # models.py:159-164 (inference only here)
+            self.rnn = nn.ModuleList([ResidualBlock(rnn_input_size, rnn_input_size * 2, hidden_size, hidden_size,
+                                                    bidirectional=bidirectional) for _ in range(rnn_layers)])
+            self.rnn_output_size = rnn_input_size
+        else:
+            rnn_cls = nn.LSTM if rnn_type == "lstm" else nn.GRU      # models.py:154-170
+            self.rnn = rnn_cls(input_size=rnn_input_size, hidden_size=hidden_size, num_layers=rnn_layers,
+                               bidirectional=bidirectional, batch_first=True)
+            self.rnn_output_size = hidden_size * (2 if bidirectional else 1)
         fc_in = self.rnn_output_size * (sequence_length if rnn_out == "all" else 1)
         if classif_mode == "multiclass":
             self.fc = nn.Linear(fc_in, fc_in // 2)
@@ -221,7 +264,12 @@ class LRCN(_BackboneLRCN):
         y = ops.dropout(aln(lin(y, self.adapt1.weight, self.adapt1.bias, bf16), self.bn1.weight, self.bn1.bias, True, self.bn1.eps), self.drop1.p, tr)
         y = ops.dropout(aln(lin(y, self.adapt2.weight, self.adapt2.bias, bf16), self.bn2.weight, self.bn2.bias, True, self.bn2.eps), self.drop1.p, tr)
         y = aln(lin(y, self.adapt3.weight, self.adapt3.bias, bf16), self.bn3.weight, self.bn3.bias, True, self.bn3.eps)
-        r = ops.rnn_forward(y, self.rnn, bf16=bf16)
+        if self.rnn_type == "mamba":
+            r = y
+            for blk in self.rnn:
+                r = blk(r)
+        else:
+            r = ops.rnn_forward(y, self.rnn, bf16=bf16)
         r = r.reshape(B, -1) if self.rnn_out == "all" else r[:, -1, :]
         if self.classif_mode == "multiclass":
             o = aln(r, self.bn0.weight, self.bn0.bias, False, self.bn0.eps)

@@ -245,6 +245,55 @@ def selective_scan(u, delta, A, Bm, Cm, chunk_reset=256, reverse=False):
     return y
 
 
+def rmsnorm(x, weight, eps=1e-5):
+    _chk(x, weight)
+    xc = x.contiguous()
+    y = torch.empty_like(xc)
+    D = xc.shape[-1]
+    call("b2_rmsnorm_f32", xc.data_ptr(), weight.data_ptr(), y.data_ptr(), xc.numel() // D, D, float(eps), stream_ptr())
+    return y
+
+
+def mamba_block_forward(x, blk, bidirectional=False):
+    """Forward of the reference's Mamba `ResidualBlock` (medsos_lrcn/src/models.py:19-117: RMSNorm -> in_proj -> causal
+    depthwise conv + SiLU -> x_proj / dt_proj + softplus -> selective scan (forward [+ reversed]) -> * silu(res) ->
+    out_proj, + x) on the b2_* kernels.  `blk` is a parameter container with the reference's attribute names
+    (norm.weight, mixer.{A_log, in_proj, conv1d, x_proj, dt_proj, out_proj}).  Inference only: the block has no
+    backward kernels yet."""
+    if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in blk.parameters())):
+        raise NotImplementedError("the Mamba temporal block runs forward only (wrap the call in torch.no_grad(); "
+                                  "its backward kernels are listed under 'next' in DESIGN.md)")
+    _chk(x)
+    mx = blk.mixer
+    B, L, dm = x.shape
+    di, n = mx.A_log.shape
+    dt_rank = mx.dt_proj.weight.shape[1]
+    K = mx.conv1d.weight.shape[-1]
+    xc_in = x.contiguous()
+    xn = rmsnorm(xc_in, blk.norm.weight, blk.norm.eps)
+    xr = sgemm(xn.reshape(B * L, dm), mx.in_proj.weight, trans_b=True, bias=mx.in_proj.bias)          # [B*L, 2*di]
+    xc = torch.empty((B, L, di), device=x.device, dtype=F32)
+    call("b2_dwconv1d_silu_f32", xr.data_ptr(), 2 * di, mx.conv1d.weight.data_ptr(), ptr(mx.conv1d.bias), xc.data_ptr(), B, L,
+         di, K, stream_ptr())
+    xp = sgemm(xc.reshape(B * L, di), mx.x_proj.weight, trans_b=True)                                  # [B*L, dt_rank + 2n]
+    dpre = sgemm(xp[:, :dt_rank], mx.dt_proj.weight, trans_b=True, bias=mx.dt_proj.bias)               # [B*L, di]
+    delta = torch.empty_like(dpre)
+    call("b2_softplus_f32", dpre.data_ptr(), delta.data_ptr(), dpre.numel(), stream_ptr())
+    Bm = xp[:, dt_rank:dt_rank + n].contiguous().reshape(B, L, n)
+    Cm = xp[:, dt_rank + n:].contiguous().reshape(B, L, n)
+    A = -torch.exp(mx.A_log.detach())                     # parameter transform (models.py:94), like the weight re-layouts
+    delta3 = delta.reshape(B, L, di)
+    y = selective_scan(xc, delta3, A, Bm, Cm, chunk_reset=None)
+    if bidirectional:
+        y = torch.cat([y, selective_scan(xc, delta3, A, Bm, Cm, chunk_reset=None, reverse=True)], dim=-1)
+    cols = y.shape[-1]
+    g = torch.empty_like(y)
+    call("b2_mul_silu_f32", y.data_ptr(), xr.data_ptr() + di * 4, 2 * di, di, g.data_ptr(), B * L, cols, stream_ptr())
+    out = xc_in.reshape(B * L, dm).clone()                # residual: out = y W^T + b + 1 * x
+    sgemm(g.reshape(B * L, cols), mx.out_proj.weight, trans_b=True, out=out, beta=1.0, bias=mx.out_proj.bias)
+    return out.reshape(B, L, dm)
+
+
 # ----------------------------------------------------------------------------------------
 # autograd: Linear
 # ----------------------------------------------------------------------------------------
