@@ -247,6 +247,20 @@ int b2_dwconv1d_silu_f32(const float* x, long x_ld, const float* w, const float*
 int b2_softplus_f32(const float* x, float* y, long n, void* stream);
 int b2_mul_silu_f32(const float* a, const float* res, long res_ld, int res_cols, float* y, long rows, int cols, void* stream);
 
+/* Backward of the same pieces (training rnn_type="mamba": small L / D / N).  Buffers marked ACCUMULATED are added into
+ * with atomics and must be zeroed by the caller.  b2_selective_scan_bwd: no chunk reset; workspace = batch*D*L*N floats
+ * (recomputed forward states); dA_log is the gradient of A_log where A = -exp(A_log). */
+int b2_rmsnorm_bwd_f32(const float* dy, const float* x, const float* w, float* dx, float* dw, long rows, int D, float eps,
+                       void* stream);
+int b2_dwconv1d_silu_bwd_f32(const float* dy, const float* x, long x_ld, const float* w, const float* b, float* dx, long dx_ld,
+                             float* dw, float* db, int B, int L, int D, int K, void* stream);
+int b2_softplus_bwd_f32(const float* dy, const float* x, float* dx, long n, void* stream);
+int b2_mul_silu_bwd_f32(const float* dy, const float* a, const float* res, long res_ld, int res_cols, float* da, float* dres,
+                        long dres_ld, long rows, int cols, void* stream);
+int b2_selective_scan_bwd(const float* u, const float* delta, const float* A, const float* B, const float* C, const float* dy,
+                          float* workspace, float* du, float* ddelta, float* dA_log, float* dB, float* dC, int batch, int L,
+                          int D, int N, int reverse, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

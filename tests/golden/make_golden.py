@@ -263,11 +263,17 @@ def gold_mamba():
         torch.manual_seed(31 + bidir)
         blk = mod.ResidualBlock(8, 16, 32, 32, bidirectional=bidir).eval()
         x = torch.randn(3, 16, 8)
-        with torch.no_grad():
-            out = blk(x)
-        arrs = {"x": x.numpy(), "out": out.numpy(), "meta": np.array(json.dumps(dict(bidir=bidir, d_model=8, n_state=32)))}
+        x.requires_grad_(True)
+        r = torch.randn(3, 16, 8)                                    # loss = <out, r>: the reference's own autograd gradients
+        out = blk(x)
+        (out * r).sum().backward()
+        arrs = {"x": x.detach().numpy(), "out": out.detach().numpy(), "r": r.numpy(), "dx": x.grad.numpy(),
+                "meta": np.array(json.dumps(dict(bidir=bidir, d_model=8, n_state=32)))}
         for k, v in blk.state_dict().items():
             arrs["p/" + k] = v.numpy()
+        for k, v in blk.named_parameters():
+            if v.grad is not None:                                   # parameters the forward never touches have none
+                arrs["g/" + k] = v.grad.numpy()
         save(f"mamba_block_{tag}.npz", **arrs)
 
 

@@ -155,8 +155,15 @@ def test_mamba_block_oracle_vs_golden(tag):
     """Mamba ResidualBlock restated by the oracle vs the output of the reference's own class (medsos models.py:107-117)."""
     g, meta = load_golden(f"mamba_block_{tag}.npz")
     sd = golden_tensors(g, "p/")
-    out = O.mamba_block_forward(sd, torch.from_numpy(g["x"]), "", bidirectional=meta["bidir"])
+    for v in sd.values():
+        v.requires_grad_(True)
+    x = torch.from_numpy(g["x"]).requires_grad_(True)
+    out = O.mamba_block_forward(sd, x, "", bidirectional=meta["bidir"])
     assert err(out, torch.from_numpy(g["out"])) < 1e-5
+    (out * torch.from_numpy(g["r"])).sum().backward()            # the reference's autograd gradients of <out, r>
+    assert err(x.grad, torch.from_numpy(g["dx"])) < 1e-4
+    for k, v in golden_tensors(g, "g/").items():
+        assert err(sd[k].grad, v, floor=1e-7) < 1e-4, k
 
 
 def test_scan_oracle_vs_golden():

@@ -213,3 +213,215 @@ B2_API int b2_mul_silu_f32(const float* a, const float* res, long res_ld, int re
   B2_LAUNCH_CHECK("mul_silu_kernel");
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Backward of the Mamba block's pieces (training the medsos rnn_type="mamba" variant: L = T <= 64 frames, D = 16,
+// N = 32 -- tiny tensors, so these kernels favour simplicity: one thread per output element / per (batch, channel)
+// scan, atomics for the cross-thread parameter sums).
+namespace {
+
+// dx = w r (dy - xhat * mean(dy * w * xhat)),  xhat = x r,  r = rsqrt(mean(x^2) + eps);  dw[c] += sum_rows dy * xhat
+__global__ void __launch_bounds__(256)
+rmsnorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ w,
+                   float* __restrict__ dx, float* __restrict__ dw, long rows, int D, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* p = x + row * D;
+  const float* g = dy + row * D;
+  float s = 0.f;
+  for (int c = lane; c < D; c += 32) s = fmaf(p[c], p[c], s);
+  s = warp_sum(s);
+  const float r = rsqrtf(s / (float)D + eps);
+  float m = 0.f;
+  for (int c = lane; c < D; c += 32) m = fmaf(g[c] * w[c], p[c] * r, m);
+  m = warp_sum(m) / (float)D;
+  for (int c = lane; c < D; c += 32) {
+    const float xh = p[c] * r;
+    dx[row * D + c] = r * (g[c] * w[c] - xh * m);
+    atomicAdd(dw + c, g[c] * xh);
+  }
+}
+
+// thread per (b, l, d): recomputes the pre-activation p = b + sum_j w[j] x[l-(K-1)+j], dp = dy * silu'(p); scatters
+// dx (atomics into a zeroed buffer with row stride dx_ld), dw[d][j], db[d]
+__global__ void __launch_bounds__(256)
+dwconv1d_silu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, long x_ld, const float* __restrict__ w,
+                         const float* __restrict__ b, float* __restrict__ dx, long dx_ld, float* __restrict__ dw,
+                         float* __restrict__ db, int B, int L, int D, int K) {
+  const long total = (long)B * L * D;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int d = (int)(i % D);
+    const long bl = i / D;
+    const int l = (int)(bl % L);
+    const long bb = bl / L;
+    float p = b != nullptr ? b[d] : 0.f;
+    for (int j = 0; j < K; ++j) {
+      const int ls = l - (K - 1) + j;
+      if (ls >= 0) p = fmaf(w[d * K + j], x[(bb * L + ls) * x_ld + d], p);
+    }
+    const float sg = 1.f / (1.f + __expf(-p));
+    const float dp = dy[i] * sg * (1.f + p * (1.f - sg));
+    for (int j = 0; j < K; ++j) {
+      const int ls = l - (K - 1) + j;
+      if (ls >= 0) {
+        atomicAdd(dx + (bb * L + ls) * dx_ld + d, dp * w[d * K + j]);
+        atomicAdd(dw + d * K + j, dp * x[(bb * L + ls) * x_ld + d]);
+      }
+    }
+    if (db != nullptr) atomicAdd(db + d, dp);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+softplus_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dx, long n) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    dx[i] = v > 20.f ? dy[i] : dy[i] / (1.f + __expf(-v));
+  }
+}
+
+// y = a * silu(res[:, c % res_cols]): da = dy * silu(res); dres[:, c % res_cols] += dy * a * silu'(res) (atomics, zeroed)
+__global__ void __launch_bounds__(256)
+mul_silu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ a, const float* __restrict__ res, long res_ld,
+                    int res_cols, float* __restrict__ da, float* __restrict__ dres, long dres_ld, long rows, int cols) {
+  const long total = rows * cols;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / cols;
+    const int c = (int)(i - r * cols);
+    const float v = res[r * res_ld + (c % res_cols)];
+    const float sg = 1.f / (1.f + __expf(-v));
+    da[i] = dy[i] * v * sg;
+    atomicAdd(dres + r * dres_ld + (c % res_cols), dy[i] * a[i] * sg * (1.f + v * (1.f - sg)));
+  }
+}
+
+// BPTT of the scan, one thread per (batch, channel), no chunk reset: the forward states x_t [N] of the whole
+// sequence are recomputed into a global workspace states[b, d, t, n] (L * N floats per thread), then the steps are
+// walked backwards.  du / ddelta [B, L, D] are written; dA_log [D, N] (through A = -exp(A_log): dA_log = dA * A),
+// dB / dC [B, L, N] are accumulated with atomics (caller zeroes them).
+template <int N>
+__global__ void __launch_bounds__(128)
+selective_scan_bwd_kernel(const float* __restrict__ u, const float* __restrict__ delta, const float* __restrict__ A,
+                          const float* __restrict__ Bm, const float* __restrict__ Cm, const float* __restrict__ dy,
+                          float* __restrict__ states, float* __restrict__ du, float* __restrict__ ddelta,
+                          float* __restrict__ dA_log, float* __restrict__ dB, float* __restrict__ dC, int batch, int L, int D,
+                          int reverse) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)batch * D) return;
+  const int d = (int)(idx % D);
+  const long b = idx / D;
+  const long row0 = b * L;
+  float a[N], x[N];
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+    a[n] = A[(long)d * N + n];
+    x[n] = 0.f;
+  }
+  float* st = states + idx * (long)L * N;
+  for (int t = 0; t < L; ++t) {                      // forward recompute (same arithmetic as the forward kernel)
+    const int ts = reverse ? L - 1 - t : t;
+    const float dl = delta[(row0 + ts) * D + d];
+    const float duv = dl * u[(row0 + ts) * D + d];
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      x[n] = fmaf(ex2_approx(dl * a[n] * kLog2e), x[n], duv * Bm[(row0 + t) * N + n]);
+      st[(long)t * N + n] = x[n];
+    }
+  }
+  float g[N], dAacc[N];                               // g: gradient flowing into x_t from step t+1
+#pragma unroll
+  for (int n = 0; n < N; ++n) g[n] = dAacc[n] = 0.f;
+  for (int t = L - 1; t >= 0; --t) {
+    const int ts = reverse ? L - 1 - t : t;
+    const float dl = delta[(row0 + ts) * D + d];
+    const float uv = u[(row0 + ts) * D + d];
+    const float dyv = dy[(row0 + ts) * D + d];
+    float ddl = 0.f, duv = 0.f;
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      const float xt = st[(long)t * N + n];
+      const float xp = t > 0 ? st[(long)(t - 1) * N + n] : 0.f;
+      const float bt = Bm[(row0 + t) * N + n];
+      const float ct = Cm[(row0 + t) * N + n];
+      const float at = ex2_approx(dl * a[n] * kLog2e);
+      atomicAdd(dC + (row0 + t) * N + n, dyv * xt);
+      const float dx = fmaf(dyv, ct, g[n]);
+      const float da = dx * xp;                       // gradient of a_t = exp(delta_t A)
+      ddl = fmaf(da * at, a[n], ddl);
+      ddl = fmaf(dx * bt, uv, ddl);
+      dAacc[n] = fmaf(da * at, dl, dAacc[n]);
+      atomicAdd(dB + (row0 + t) * N + n, dx * dl * uv);
+      duv = fmaf(dx * dl, bt, duv);
+      g[n] = at * dx;
+    }
+    du[(row0 + ts) * D + d] = duv;
+    ddelta[(row0 + ts) * D + d] = ddl;
+  }
+#pragma unroll
+  for (int n = 0; n < N; ++n) atomicAdd(dA_log + (long)d * N + n, dAacc[n] * a[n]);
+}
+
+}  // namespace
+
+// dw is ACCUMULATED into (caller zeroes)
+B2_API int b2_rmsnorm_bwd_f32(const float* dy, const float* x, const float* w, float* dx, float* dw, long rows, int D,
+                              float eps, void* stream) {
+  B2_ARG_CHECK(dy && x && w && dx && dw && rows > 0 && D > 0, "b2_rmsnorm_bwd_f32: null pointer or empty");
+  rmsnorm_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(dy, x, w, dx, dw, rows, D, eps);
+  B2_LAUNCH_CHECK("rmsnorm_bwd_kernel");
+  return 0;
+}
+
+// dx (row stride dx_ld), dw [D,K], db [D] are ACCUMULATED into (caller zeroes)
+B2_API int b2_dwconv1d_silu_bwd_f32(const float* dy, const float* x, long x_ld, const float* w, const float* b, float* dx,
+                                    long dx_ld, float* dw, float* db, int B, int L, int D, int K, void* stream) {
+  B2_ARG_CHECK(dy && x && w && dx && dw && B > 0 && L > 0 && D > 0 && K > 0 && x_ld >= D && dx_ld >= D,
+               "b2_dwconv1d_silu_bwd_f32: bad arguments");
+  dwconv1d_silu_bwd_kernel<<<ew_grid((long)B * L * D), 256, 0, (cudaStream_t)stream>>>(dy, x, x_ld, w, b, dx, dx_ld, dw, db,
+                                                                                     B, L, D, K);
+  B2_LAUNCH_CHECK("dwconv1d_silu_bwd_kernel");
+  return 0;
+}
+
+B2_API int b2_softplus_bwd_f32(const float* dy, const float* x, float* dx, long n, void* stream) {
+  B2_ARG_CHECK(dy && x && dx && n > 0, "b2_softplus_bwd_f32: null pointer or empty");
+  softplus_bwd_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(dy, x, dx, n);
+  B2_LAUNCH_CHECK("softplus_bwd_kernel");
+  return 0;
+}
+
+// dres (row stride dres_ld) is ACCUMULATED into (caller zeroes); da is overwritten
+B2_API int b2_mul_silu_bwd_f32(const float* dy, const float* a, const float* res, long res_ld, int res_cols, float* da,
+                               float* dres, long dres_ld, long rows, int cols, void* stream) {
+  B2_ARG_CHECK(dy && a && res && da && dres && rows > 0 && cols > 0 && res_cols > 0, "b2_mul_silu_bwd_f32: bad arguments");
+  mul_silu_bwd_kernel<<<ew_grid(rows * cols), 256, 0, (cudaStream_t)stream>>>(dy, a, res, res_ld, res_cols, da, dres, dres_ld,
+                                                                            rows, cols);
+  B2_LAUNCH_CHECK("mul_silu_bwd_kernel");
+  return 0;
+}
+
+// workspace: batch * D * L * N floats; du / ddelta overwritten; dA_log [D,N], dB / dC [batch,L,N] ACCUMULATED (caller zeroes)
+B2_API int b2_selective_scan_bwd(const float* u, const float* delta, const float* A, const float* Bm, const float* Cm,
+                                 const float* dy, float* workspace, float* du, float* ddelta, float* dA_log, float* dB,
+                                 float* dC, int batch, int L, int D, int N, int reverse, void* stream) {
+  B2_ARG_CHECK(u && delta && A && Bm && Cm && dy && workspace && du && ddelta && dA_log && dB && dC,
+               "b2_selective_scan_bwd: null pointer");
+  B2_ARG_CHECK(batch > 0 && L > 0 && D > 0, "b2_selective_scan_bwd: empty shape");
+  B2_ARG_CHECK(N == 4 || N == 8 || N == 16 || N == 32, "b2_selective_scan_bwd: n_state must be 4, 8, 16 or 32 (got %d)", N);
+  const long threads = (long)batch * D;
+  const unsigned grid = (unsigned)((threads + 127) / 128);
+  cudaStream_t st = (cudaStream_t)stream;
+#define B2_SCAN_BWD(NN)                                                                                              \
+  selective_scan_bwd_kernel<NN><<<grid, 128, 0, st>>>(u, delta, A, Bm, Cm, dy, workspace, du, ddelta, dA_log, dB, dC, \
+                                                      batch, L, D, reverse)
+  switch (N) {
+    case 4: B2_SCAN_BWD(4); break;
+    case 8: B2_SCAN_BWD(8); break;
+    case 16: B2_SCAN_BWD(16); break;
+    default: B2_SCAN_BWD(32); break;
+  }
+#undef B2_SCAN_BWD
+  B2_LAUNCH_CHECK("selective_scan_bwd_kernel");
+  return 0;
+}

@@ -110,7 +110,7 @@ class ParallelMamba(nn.Module):
 
 
 class ResidualBlock(nn.Module):
-    """medsos_lrcn/src/models.py:107-117: `mixer(norm(x)) + x`, executed by ops.mamba_block_forward (forward only)."""
+    """medsos_lrcn/src/models.py:107-117: `mixer(norm(x)) + x`, executed by ops.mamba_block_forward (autograd: ops.MambaBlockFn)."""
 
     def __init__(self, d_model, d_inner, n_state, dt_rank, bias=True, conv_bias=True, kernel_size=3, bidirectional=False):
         super().__init__()
@@ -234,7 +234,7 @@ class LRCN(_BackboneLRCN):
         self.adapt3 = nn.Linear(f // 4, rnn_input_size)
         self.bn3 = nn.LayerNorm(rnn_input_size)
         self.drop1 = nn.Dropout(p=dropout)
-        if rnn_type == "mamba":                                       # models.py:159-164 (inference only here)
+        if rnn_type == "mamba":                                       # models.py:159-164
             self.rnn = nn.ModuleList([ResidualBlock(rnn_input_size, rnn_input_size * 2, hidden_size, hidden_size,
                                                     bidirectional=bidirectional) for _ in range(rnn_layers)])
             self.rnn_output_size = rnn_input_size

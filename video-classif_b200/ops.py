@@ -254,34 +254,25 @@ def rmsnorm(x, weight, eps=1e-5):
     return y
 
 
-def mamba_block_forward(x, blk, bidirectional=False):
-    """Forward of the reference's Mamba `ResidualBlock` (medsos_lrcn/src/models.py:19-117: RMSNorm -> in_proj -> causal
-    depthwise conv + SiLU -> x_proj / dt_proj + softplus -> selective scan (forward [+ reversed]) -> * silu(res) ->
-    out_proj, + x) on the b2_* kernels.  `blk` is a parameter container with the reference's attribute names
-    (norm.weight, mixer.{A_log, in_proj, conv1d, x_proj, dt_proj, out_proj}).  Inference only: the block has no
-    backward kernels yet."""
-    if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in blk.parameters())):
-        raise NotImplementedError("the Mamba temporal block runs forward only (wrap the call in torch.no_grad(); "
-                                  "its backward kernels are listed under 'next' in DESIGN.md)")
-    _chk(x)
-    mx = blk.mixer
+def _mamba_fwd(x, norm_w, eps, A_log, in_w, in_b, conv_w, conv_b, xproj_w, dt_w, dt_b, out_w, out_b, bidirectional):
+    """Forward chain of the Mamba block; returns (out, saved intermediates)."""
     B, L, dm = x.shape
-    di, n = mx.A_log.shape
-    dt_rank = mx.dt_proj.weight.shape[1]
-    K = mx.conv1d.weight.shape[-1]
+    di, n = A_log.shape
+    dt_rank = dt_w.shape[1]
+    K = conv_w.shape[-1]
     xc_in = x.contiguous()
-    xn = rmsnorm(xc_in, blk.norm.weight, blk.norm.eps)
-    xr = sgemm(xn.reshape(B * L, dm), mx.in_proj.weight, trans_b=True, bias=mx.in_proj.bias)          # [B*L, 2*di]
+    xn = rmsnorm(xc_in, norm_w, eps)
+    xr = sgemm(xn.reshape(B * L, dm), in_w, trans_b=True, bias=in_b)                                   # [B*L, 2*di]
     xc = torch.empty((B, L, di), device=x.device, dtype=F32)
-    call("b2_dwconv1d_silu_f32", xr.data_ptr(), 2 * di, mx.conv1d.weight.data_ptr(), ptr(mx.conv1d.bias), xc.data_ptr(), B, L,
-         di, K, stream_ptr())
-    xp = sgemm(xc.reshape(B * L, di), mx.x_proj.weight, trans_b=True)                                  # [B*L, dt_rank + 2n]
-    dpre = sgemm(xp[:, :dt_rank], mx.dt_proj.weight, trans_b=True, bias=mx.dt_proj.bias)               # [B*L, di]
+    call("b2_dwconv1d_silu_f32", xr.data_ptr(), 2 * di, conv_w.data_ptr(), ptr(conv_b), xc.data_ptr(), B, L, di, K,
+         stream_ptr())
+    xp = sgemm(xc.reshape(B * L, di), xproj_w, trans_b=True)                                           # [B*L, dt_rank + 2n]
+    dpre = sgemm(xp[:, :dt_rank], dt_w, trans_b=True, bias=dt_b)                                       # [B*L, di]
     delta = torch.empty_like(dpre)
     call("b2_softplus_f32", dpre.data_ptr(), delta.data_ptr(), dpre.numel(), stream_ptr())
     Bm = xp[:, dt_rank:dt_rank + n].contiguous().reshape(B, L, n)
     Cm = xp[:, dt_rank + n:].contiguous().reshape(B, L, n)
-    A = -torch.exp(mx.A_log.detach())                     # parameter transform (models.py:94), like the weight re-layouts
+    A = -torch.exp(A_log.detach())                        # parameter transform (models.py:94), like the weight re-layouts
     delta3 = delta.reshape(B, L, di)
     y = selective_scan(xc, delta3, A, Bm, Cm, chunk_reset=None)
     if bidirectional:
@@ -290,8 +281,115 @@ def mamba_block_forward(x, blk, bidirectional=False):
     g = torch.empty_like(y)
     call("b2_mul_silu_f32", y.data_ptr(), xr.data_ptr() + di * 4, 2 * di, di, g.data_ptr(), B * L, cols, stream_ptr())
     out = xc_in.reshape(B * L, dm).clone()                # residual: out = y W^T + b + 1 * x
-    sgemm(g.reshape(B * L, cols), mx.out_proj.weight, trans_b=True, out=out, beta=1.0, bias=mx.out_proj.bias)
-    return out.reshape(B, L, dm)
+    sgemm(g.reshape(B * L, cols), out_w, trans_b=True, out=out, beta=1.0, bias=out_b)
+    return out.reshape(B, L, dm), (xc_in, xn, xr, xc, xp, dpre, delta3, Bm, Cm, A, y, g)
+
+
+class MambaBlockFn(torch.autograd.Function):
+    """The reference's Mamba `ResidualBlock` (medsos_lrcn/src/models.py:19-117) as one autograd node: forward chain of
+    `_mamba_fwd`, backward through b2_selective_scan_bwd (BPTT with recomputed states) and the b2_*_bwd element kernels;
+    all weight / input gradients of the projections on the fp32 SIMT GEMM."""
+
+    @staticmethod
+    def forward(ctx, x, norm_w, A_log, in_w, in_b, conv_w, conv_b, xproj_w, dt_w, dt_b, out_w, out_b, eps, bidirectional):
+        _chk(x)
+        out, saved = _mamba_fwd(x, norm_w, eps, A_log, in_w, in_b, conv_w, conv_b, xproj_w, dt_w, dt_b, out_w, out_b,
+                                bidirectional)
+        ctx.save_for_backward(norm_w, in_w, conv_w, conv_b if conv_b is not None else norm_w.new_empty(0), xproj_w, dt_w,
+                              out_w, *saved)
+        ctx.eps = eps
+        ctx.bidirectional = bidirectional
+        ctx.has = (in_b is not None, conv_b is not None, dt_b is not None, out_b is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (norm_w, in_w, conv_w, conv_b, xproj_w, dt_w, out_w, x, xn, xr, xc, xp, dpre, delta3, Bm, Cm, A, y, g) = \
+            ctx.saved_tensors
+        has_in_b, has_conv_b, has_dt_b, has_out_b = ctx.has
+        B, L, dm = x.shape
+        di, n = A.shape
+        dt_rank = dt_w.shape[1]
+        K = conv_w.shape[-1]
+        R = B * L
+        cols = y.shape[-1]
+        dev = x.device
+        st = stream_ptr()
+        do2 = dout.reshape(R, dm)
+        if not do2.is_contiguous():
+            do2 = do2.contiguous()
+        if do2.dtype != F32:
+            do2 = do2.float()
+        g2, y2 = g.reshape(R, cols), y.reshape(R, cols)
+        # out_proj
+        d_out_w = sgemm(do2, g2, trans_a=True)                                   # [dm, cols]
+        d_out_b = colsum(do2) if has_out_b else None
+        dg = sgemm(do2, out_w)                                                   # [R, cols]
+        # gate: g = y * silu(res)
+        dxr = torch.zeros((R, 2 * di), device=dev, dtype=F32)
+        dy = torch.empty((R, cols), device=dev, dtype=F32)
+        call("b2_mul_silu_bwd_f32", dg.data_ptr(), y2.data_ptr(), xr.data_ptr() + di * 4, 2 * di, di, dy.data_ptr(),
+             dxr.data_ptr() + di * 4, 2 * di, R, cols, st)
+        # scan(s)
+        ws = torch.empty(B * di * L * n, device=dev, dtype=F32)
+        dA_log = torch.zeros((di, n), device=dev, dtype=F32)
+        dBC = torch.zeros((2, B, L, n), device=dev, dtype=F32)
+        dxc = ddelta = None
+        for rev in range(2 if ctx.bidirectional else 1):
+            dyd = dy if cols == di else dy[:, rev * di:(rev + 1) * di].contiguous()
+            du = torch.empty((B, L, di), device=dev, dtype=F32)
+            dd = torch.empty((B, L, di), device=dev, dtype=F32)
+            call("b2_selective_scan_bwd", xc.data_ptr(), delta3.data_ptr(), A.data_ptr(), Bm.data_ptr(), Cm.data_ptr(),
+                 dyd.data_ptr(), ws.data_ptr(), du.data_ptr(), dd.data_ptr(), dA_log.data_ptr(), dBC[0].data_ptr(),
+                 dBC[1].data_ptr(), B, L, di, n, rev, st)
+            if rev == 0:
+                dxc, ddelta = du, dd
+            else:
+                dxc += du
+                ddelta += dd
+        # delta = softplus(dt_proj(xp[:, :dt_rank]))
+        ddpre = torch.empty((R, di), device=dev, dtype=F32)
+        call("b2_softplus_bwd_f32", ddelta.data_ptr(), dpre.data_ptr(), ddpre.data_ptr(), ddpre.numel(), st)
+        d_dt_w = sgemm(ddpre, xp[:, :dt_rank], trans_a=True)                     # [di, dt_rank]
+        d_dt_b = colsum(ddpre) if has_dt_b else None
+        dxp = torch.empty_like(xp)
+        sgemm(ddpre, dt_w, out=dxp[:, :dt_rank])
+        dxp[:, dt_rank:dt_rank + n].copy_(dBC[0].reshape(R, n))
+        dxp[:, dt_rank + n:].copy_(dBC[1].reshape(R, n))
+        # x_proj
+        d_xproj_w = sgemm(dxp, xc.reshape(R, di), trans_a=True)                  # [dt_rank + 2n, di]
+        sgemm(dxp, xproj_w, out=dxc.reshape(R, di), beta=1.0)
+        # causal depthwise conv + SiLU over xr[:, :di]
+        d_conv_w = torch.zeros((di, K), device=dev, dtype=F32)
+        d_conv_b = torch.zeros(di, device=dev, dtype=F32) if has_conv_b else None
+        call("b2_dwconv1d_silu_bwd_f32", dxc.data_ptr(), xr.data_ptr(), 2 * di, conv_w.data_ptr(),
+             conv_b.data_ptr() if has_conv_b else 0, dxr.data_ptr(), 2 * di, d_conv_w.data_ptr(), ptr(d_conv_b), B, L, di, K, st)
+        # in_proj
+        d_in_w = sgemm(dxr, xn.reshape(R, dm), trans_a=True)                     # [2 di, dm]
+        d_in_b = colsum(dxr) if has_in_b else None
+        dxn = sgemm(dxr, in_w)                                                   # [R, dm]
+        # RMSNorm, + the residual branch
+        dx = torch.empty((R, dm), device=dev, dtype=F32)
+        d_norm_w = torch.zeros(dm, device=dev, dtype=F32)
+        call("b2_rmsnorm_bwd_f32", dxn.data_ptr(), x.data_ptr(), norm_w.data_ptr(), dx.data_ptr(), d_norm_w.data_ptr(), R, dm,
+             float(ctx.eps), st)
+        dx += do2
+        return (dx.reshape(B, L, dm), d_norm_w, dA_log, d_in_w, d_in_b, d_conv_w.reshape(conv_w.shape), d_conv_b, d_xproj_w,
+                d_dt_w, d_dt_b, d_out_w, d_out_b, None, None)
+
+
+def mamba_block_forward(x, blk, bidirectional=False):
+    """The reference's Mamba `ResidualBlock` (medsos_lrcn/src/models.py:19-117: RMSNorm -> in_proj -> causal
+    depthwise conv + SiLU -> x_proj / dt_proj + softplus -> selective scan (forward [+ reversed]) -> * silu(res) ->
+    out_proj, + x) on the b2_* kernels.  `blk` is a parameter container with the reference's attribute names
+    (norm.weight, mixer.{A_log, in_proj, conv1d, x_proj, dt_proj, out_proj}).  Differentiable (MambaBlockFn)."""
+    _chk(x)
+    mx = blk.mixer
+    args = (blk.norm.weight, mx.A_log, mx.in_proj.weight, mx.in_proj.bias, mx.conv1d.weight, mx.conv1d.bias,
+            mx.x_proj.weight, mx.dt_proj.weight, mx.dt_proj.bias, mx.out_proj.weight, mx.out_proj.bias)
+    if torch.is_grad_enabled() and (x.requires_grad or any(a is not None and a.requires_grad for a in args)):
+        return MambaBlockFn.apply(x, *args, float(blk.norm.eps), bool(bidirectional))
+    return _mamba_fwd(x, args[0], float(blk.norm.eps), *args[1:], bidirectional)[0]
 
 
 # ----------------------------------------------------------------------------------------
