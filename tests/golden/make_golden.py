@@ -277,6 +277,51 @@ def gold_mamba():
         save(f"mamba_block_{tag}.npz", **arrs)
 
 
+def save_as(model, path, module_name, extra=()):
+    """torch.save(model) with the class pickled under the import path the reference's own scripts give it
+    (`models.LRCN` via main.py:6, `__main__.LRCN` for a script run directly)."""
+    import sys, types
+    classes = {type(model)} | set(extra)
+    fake = types.ModuleType(module_name)
+    prev_mod = sys.modules.get(module_name)
+    prev = {c: (c.__module__, c.__qualname__) for c in classes}
+    try:
+        for c in classes:
+            c.__module__, c.__qualname__ = module_name, c.__name__
+            setattr(fake, c.__name__, c)
+        if module_name == "__main__":
+            for c in classes:
+                setattr(prev_mod, c.__name__, c)
+        else:
+            sys.modules[module_name] = fake
+        torch.save(model, path)
+    finally:
+        for c, (m, q) in prev.items():
+            c.__module__, c.__qualname__ = m, q
+        if module_name != "__main__":
+            if prev_mod is None:
+                sys.modules.pop(module_name, None)
+            else:
+                sys.modules[module_name] = prev_mod
+
+
+def gold_ckpt():
+    # whole-module pickles as train_eval.py:53 / ucf50-lrcn.py:468 write them, tiny shapes (committed fixtures)
+    here = os.path.dirname(os.path.abspath(__file__))
+    torch.manual_seed(41)
+    m = refload.notebook_lrcn()(5, 4, 8, input_shape=(3, 16, 16)).eval()
+    x = torch.rand(2, 4, 3, 16, 16)
+    with torch.no_grad():
+        y = m(x)
+    save_as(m, os.path.join(here, "ckpt_smallcnn_lstm.pt"), "__main__")
+    torch.manual_seed(42)
+    m2 = refload.backup_lrcn2()(3, 4, 8, (3, 16, 16)).eval()
+    with torch.no_grad():
+        y2 = m2(x)
+    save_as(m2, os.path.join(here, "ckpt_smallcnn_gru.pt"), "__main__")
+    save("ckpt_io.npz", x=x.numpy(), y_lstm=y.numpy(), y_gru=y2.numpy())
+
+
 def gold_scan():
     torch.manual_seed(3)
     Bz, L, D, N = 2, 300, 12, 4
@@ -303,3 +348,4 @@ if __name__ == "__main__":
     gold_scan()
     gold_gru()
     gold_mamba()
+    gold_ckpt()

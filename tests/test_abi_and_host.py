@@ -158,3 +158,64 @@ def test_gradient_bucket_allreduce_world2_gloo(tmp_path):
                        capture_output=True, text=True, env=env, timeout=240)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert r.stdout.count("dp ok") == 2
+
+
+def _same_state(a, b):
+    assert set(a) == set(b), set(a) ^ set(b)
+    for k in a:
+        assert torch.equal(a[k].cpu(), b[k].cpu()), k
+
+
+def test_reference_whole_module_checkpoints_load_without_the_reference_source():
+    """train_eval.py:53 / ucf50-lrcn.py:468 `torch.save(model)` files (committed tiny fixtures made by the reference's
+    own classes, pickled as `__main__.LRCN` / `__main__.LRCN2`): plain torch.load cannot resolve the class here; the
+    shim rebuilds the equivalent module with identical weights and inferred hyper-parameters."""
+    import video_classif_b200 as vc
+    from video_classif_b200 import checkpoint as C
+    path = os.path.join(GOLDEN, "ckpt_smallcnn_lstm.pt")
+    with pytest.raises(Exception):
+        torch.load(path, weights_only=False)
+    raw = torch.load(path, pickle_module=C._pickle_module(), weights_only=False)
+    assert isinstance(raw, C.ReferencePlaceholder) and raw._ref_name == "LRCN"
+    m = vc.load_reference_checkpoint(path, precision="fp32")
+    assert type(m).__name__ == "SmallCNNLRCN" and not m.training
+    assert (m.sequence_length, m.hidden_size, m.num_classes, m.lstm.num_layers, m.dropout.p) == (4, 8, 5, 2, 0.5)
+    _same_state(m.state_dict(), raw.state_dict())
+    g = vc.load_reference_checkpoint(os.path.join(GOLDEN, "ckpt_smallcnn_gru.pt"), precision="fp32")
+    assert type(g).__name__ == "SmallCNNGRU" and isinstance(g.lstm, torch.nn.GRU) and g.lstm.bidirectional
+    assert g.fc.weight.shape == (3, 64) and g.dropout.p == 0.3
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="builds the reference's backbone classes on the fly")
+def test_reference_backbone_checkpoints_roundtrip(tmp_path):
+    """medsos `models.LRCN` (lstm and mamba variants), ucf50-lrcn `__main__.LRCN` and crime `LRCN` pickles written by the
+    reference classes -> load_reference_checkpoint: topology, hyper-parameters, requires_grad flags and every tensor."""
+    sys.path.insert(0, GOLDEN)
+    import make_golden as MG
+    from oracle import refload
+    import video_classif_b200 as vc
+    mod = refload.medsos_models(CONF_RNN_LAYER=2, CONF_CLASSIF_MODE="multiclass", CONF_DROPOUT=0.25)
+    for rnn_type, bidir in (("lstm", False), ("gru", True), ("mamba", True)):
+        torch.manual_seed(5)
+        ref = mod.LRCN(4, 6, 16, 8, cnn_backbone="resnet18", rnn_type=rnn_type, rnn_out="all", bidirectional=bidir)
+        p = str(tmp_path / f"medsos_{rnn_type}.pt")
+        MG.save_as(ref, p, "models", extra=(mod.ResidualBlock, mod.ParallelMamba, mod.RMSNorm))
+        m = vc.load_reference_checkpoint(p)
+        assert type(m).__name__ == "LRCN" and m.rnn_type == rnn_type and m.bidirectional == bidir and m.training
+        assert (m.sequence_length, m.hidden_size) == (6, 16)
+        _same_state(m.state_dict(), ref.state_dict())
+        assert {n for n, q in m.named_parameters() if q.requires_grad} == {n for n, q in ref.named_parameters() if q.requires_grad}
+    U, _ = refload.ucf50_lrcn(CONF_RNN_LAYER=2, CONF_CNN_BACKBONE="resnet18")
+    ref = U(5, 4, 12, 16, cnn_backbone="resnet18").eval()
+    p = str(tmp_path / "ucf50.pt")
+    MG.save_as(ref, p, "__main__")
+    m = vc.load_reference_checkpoint(p)
+    assert type(m).__name__ == "UCF50LRCN" and not m.training and m.rnn.num_layers == 2 and m.rnn.hidden_size == 12
+    _same_state(m.state_dict(), ref.state_dict())
+    Cr, _ = refload.crime_lrcn(CONF_RNN_LAYER=2, CONF_CNN_BACKBONE="resnet18")
+    ref = Cr(3, 4, 12, 16, cnn_backbone="resnet18")
+    p = str(tmp_path / "crime.pt")
+    MG.save_as(ref, p, "__main__")
+    m = vc.load_reference_checkpoint(p)
+    assert type(m).__name__ == "CrimeLRCN" and len(m.fc) == 3
+    _same_state(m.state_dict(), ref.state_dict())

@@ -9,7 +9,10 @@ def __getattr__(name):   # lazy: models/ops import torch + torchvision
     if name in ("SmallCNNLRCN", "SmallCNNGRU", "LRCN", "UCF50LRCN", "CrimeLRCN", "GraphedInference", "count_parameters"):
         from . import models
         return getattr(models, name)
-    if name in ("ops", "models", "ingest", "backbone", "dp", "scan"):
+    if name in ("load_reference_checkpoint", "convert_reference_module"):
+        from . import checkpoint
+        return getattr(checkpoint, name)
+    if name in ("ops", "models", "ingest", "backbone", "dp", "scan", "checkpoint"):
         import importlib
         return importlib.import_module("." + name, __name__)
     raise AttributeError(name)
