@@ -261,6 +261,23 @@ int b2_selective_scan_bwd(const float* u, const float* delta, const float* A, co
                           float* workspace, float* du, float* ddelta, float* dA_log, float* dB, float* dC, int batch, int L,
                           int D, int N, int reverse, void* stream);
 
+/* ---- trainable frame encoder: backward kernels (csrc/conv_bwd.cu; fine-tune paths rgb_lrcn.py:208-245, lrcn.py:246-283) ----
+ * b2_conv2d_wgrad_nhwc_bf16: dw[Cout,R,S,C] fp32 += sum_m dy[m,co] * x[pix(m)+(r,s),ci] (tcgen05, MN-major operands straight
+ *   from the NHWC tensors; ACCUMULATED: the caller zeroes dw).  R = S = 1, stride 1: C % 8 == 0; otherwise C % 64 == 0.
+ * b2_bn_bwd_nhwc_bf16: BatchNorm backward over [M,C] bf16: dzm = dz * [z > 0] when z != NULL (else dz is used); s1 (= dbeta), s2
+ *   (= dgamma) ACCUMULATED; dy = gamma*invstd*(dz - s1/count - xhat*s2/count) (train) or gamma*invstd*dz (eval).
+ * b2_dilate2_nhwc_bf16: zero-dilation of dy for the data gradient of stride-2 convs (z pre-zeroed).
+ * b2_avgpool_bwd_nhwc: dz[n,hw,c] = dfeat[n,c] / HW.   b2_maxpool_relu_bwd_nhwc: stem tail backward (dbn fp32 pre-zeroed). */
+int b2_conv2d_wgrad_nhwc_bf16(const void* x, int Nimg, int H, int W, int C, const void* dy, int Cout, int R, int S, int stride,
+                              int pad, float* dw, void* stream);
+int b2_bn_bwd_nhwc_bf16(const void* dz, void* dzm, const void* z, const void* y, void* dy, const float* gamma, const float* sum,
+                        const float* sumsq, const float* running_mean, const float* running_var, float* s1, float* s2, long M,
+                        int C, long count, float eps, int train, void* stream);
+int b2_dilate2_nhwc_bf16(const void* dy, void* z, int N, int P, int Q, int H, int W, int C, void* stream);
+int b2_avgpool_bwd_nhwc(const float* dfeat, void* dz, long N, int HW, int C, void* stream);
+int b2_maxpool_relu_bwd_nhwc(const void* raw, const float* scale, const float* shift, const void* dpool, float* dbn, int N,
+                             int H, int W, int P, int Q, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -136,17 +136,19 @@ class ResNetRunner:
         call("b2_avgpool_nhwc", y.data_ptr(), feat.data_ptr(), 0, Nn, Hh * Ww, C, stream_ptr())
         return feat
 
-    def __call__(self, x, training: bool, return_stages: bool = False):
+    def __call__(self, x, training: bool, return_stages: bool = False, stop_at=None):
         """x: [N,3,H,W] fp32 or bf16 (NCHW, the reference's frame tensor) -> [N, feat] fp32.
-        return_stages=True also returns the spatial means after the stem and each stage (tests)."""
+        return_stages=True also returns the spatial means after the stem and each stage (tests).
+        stop_at=(layer, block): return the NHWC bf16 activation entering that block (the frozen prefix of a partially
+        trainable encoder, backbone_train.py)."""
         _lib.require_device()
         net = self.net
         if self._frozen is None:
             self._frozen = list(net.parameters())
         if torch.is_grad_enabled() and any(p.requires_grad for p in self._frozen):
-            raise NotImplementedError(
-                "trainable CNN backbone (full fine-tune, rgb_lrcn.py:208-227) has no backward kernels yet; "
-                "freeze it (requires_grad=False) as medsos models.py:144-145 / ucf50-lrcn.py:271-272 do")
+            # (partially) trainable encoder: rgb_lrcn.py:208-245 / lrcn.py:246-283 -- autograd path with backward kernels
+            from .backbone_train import encode_trainable
+            return encode_trainable(self, x, training)
         x = x.contiguous()
         N, Cin, H, W = x.shape
         assert Cin == 3, "frame encoder expects RGB frames"
@@ -214,6 +216,12 @@ class ResNetRunner:
             layer = getattr(net, f"layer{li}")
             for bi, blk in enumerate(layer):
                 pfx = f"layer{li}.{bi}"
+                if stop_at == (li, bi):
+                    if train:
+                        done = [net.bn1] + [m for lj in range(1, 5) for bj, b in enumerate(getattr(net, f"layer{lj}"))
+                                            if (lj, bj) < stop_at for m in b.modules() if isinstance(m, torch.nn.BatchNorm2d)]
+                        torch._foreach_add_([b.num_batches_tracked for b in done if b.num_batches_tracked is not None], 1)
+                    return y
                 stride = blk.stride if isinstance(blk.stride, int) else blk.stride[0]
                 bottleneck = hasattr(blk, "conv3")
                 if fuse:

@@ -335,8 +335,8 @@ class UCF50LRCN(_BackboneLRCN):
 class CrimeLRCN(_BackboneLRCN):
     """lrcn/lrcn.py:181-305 (and rgb_lrcn.py:168-263 with classif_mode='multiclass'): backbone,
     one `adapt` Linear, N-layer biLSTM stored as `lstm`, `fc` or per-class heads.
-    freeze_until_layer / finetune follow freeze_cnn_layers (lrcn.py:246-283); a backbone left
-    trainable is rejected at forward time (no backbone backward kernels yet)."""
+    freeze_until_layer / finetune follow freeze_cnn_layers (lrcn.py:246-283); a (partially) trainable backbone
+    runs through the autograd nodes of backbone_train.py."""
 
     def __init__(self, num_classes, sequence_length, hidden_size, rnn_input_size, cnn_backbone="resnet50",
                  rnn_out="all", freeze_until_layer=None, rnn_layers=4, classif_mode="multiple_binary",
