@@ -23,13 +23,14 @@ def rnd(t):
 
 GEOMS = [(3, 10, 10, 64, 64, 3, 1, 1), (2, 9, 9, 128, 256, 1, 1, 0), (2, 14, 14, 256, 512, 3, 2, 1), (5, 7, 7, 512, 128, 1, 2, 0),
          (4, 28, 28, 64, 256, 1, 1, 0), (2, 8, 8, 2048, 512, 1, 1, 0), (2, 7, 7, 512, 512, 3, 1, 1), (1, 1, 777, 168, 64, 1, 1, 0),
-         (1, 5, 5, 64, 8, 3, 1, 1)]
+         (1, 5, 5, 64, 8, 3, 1, 1), (2, 9, 9, 128, 64, 3, 1, 1), (2, 12, 12, 64, 128, 3, 2, 1), (3, 6, 6, 128, 256, 3, 2, 1)]
 
 
 @pytest.mark.parametrize("N,H,W,C,Cout,R,s,p", GEOMS)
 def test_conv_wgrad_vs_torch(N, H, W, C, Cout, R, s, p):
     """b2_conv2d_wgrad_nhwc_bf16 (tcgen05, MN-major operands, im2col-TMA taps) vs F.conv2d's weight gradient on the same
-    bf16 inputs: fp32 accumulation on both sides -> 1e-5; covers 1x1 / 3x3, stride 1 / 2, Cout < 128 (zero-filled
+    bf16 inputs: fp32 accumulation on both sides -> 1e-5; covers 1x1 / 3x3, stride 1 / 2, narrow layers (C = 64 / 128:
+    4 / 2 filter taps side by side in one MMA), Cout < 128 (zero-filled
     panel), C not a multiple of 64 (the stem's patch matrix), pixel counts that are not multiples of the 64-row stage."""
     from video_classif_b200 import backbone_train as BT
     torch.manual_seed(N * 1000 + C)

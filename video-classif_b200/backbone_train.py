@@ -36,18 +36,20 @@ def _finalize(stat, C, bn, count, train, momentum=None):
          float(_momentum(bn) if momentum is None else momentum), int(train), base + 8 * C, base + 12 * C, C, stream_ptr())
 
 
-def _bn_backward(dz, z, y, bn, stat, count, train):
-    """-> (dy bf16, dz masked by z > 0 (or dz itself), dgamma, dbeta)."""
+def _bn_backward(dz, z, y, bn, stat, count, train, want_masked=False):
+    """-> (dy bf16, dz masked by z > 0 if want_masked (else None), dgamma, dbeta).  z = None: no ReLU behind the BN."""
     C = y.shape[-1]
     M = y.numel() // C
     dy = torch.empty_like(y)
-    dzm = torch.empty_like(y) if z is not None else None
+    dzm = torch.empty_like(y) if (want_masked and z is not None) else None
     s12 = torch.zeros(2 * C, device=y.device, dtype=F32)
     base = stat.data_ptr()
     call("b2_bn_bwd_nhwc_bf16", dz.data_ptr(), ptr(dzm), ptr(z), y.data_ptr(), dy.data_ptr(), bn.weight.data_ptr(),
          base if train else 0, base + 4 * C if train else 0, bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
          s12.data_ptr(), s12.data_ptr() + 4 * C, M, C, count, float(bn.eps), int(train), stream_ptr())
-    return dy, (dzm if z is not None else dz), s12[C:], s12[:C]
+    if want_masked and z is None:
+        dzm = dz
+    return dy, dzm, s12[C:], s12[:C]
 
 
 def conv_wgrad(x, dy, R, S, stride, pad):
@@ -104,14 +106,15 @@ class ConvBnFn(torch.autograd.Function):
         stride, pad = ctx.geom
         Cout, Cin, R, S = w.shape
         dz = dz.contiguous()
-        dy, dzm, dgamma, dbeta = _bn_backward(dz, z, y, ctx.bn, stat, ctx.count, ctx.train)
+        want_res = ctx.has_res and ctx.needs_input_grad[4]
+        dy, dzm, dgamma, dbeta = _bn_backward(dz, z, y, ctx.bn, stat, ctx.count, ctx.train, want_masked=want_res)
         dx = dw = None
         if ctx.needs_input_grad[1]:
             dw = conv_wgrad(x, dy, R, S, stride, pad).permute(0, 3, 1, 2)
         if ctx.needs_input_grad[0]:
             dx = conv_dgrad(dy, w, x.shape[1:3], stride, pad)
         return (dx, dw, dgamma if ctx.needs_input_grad[2] else None, dbeta if ctx.needs_input_grad[3] else None,
-                dzm if ctx.has_res and ctx.needs_input_grad[4] else None, None, None, None, None, None)
+                dzm if want_res else None, None, None, None, None, None)
 
 
 class StemFn(torch.autograd.Function):

@@ -43,6 +43,9 @@ struct WgGeom {
   int Mp;          // output pixels N * P * Q
   int Cout, C;
   int ci_blocks;
+  int tpg;         // filter taps per CTA: narrow layers (C <= 128) put 256 / C taps side by side in the N dimension of one
+  int ppt;         //   MMA (the dy tile is fetched once for all of them); ppt = 64-channel panels per tap
+  int tap_groups;
 };
 
 // MN-major SWIZZLE_128B descriptor (same encoding as the Gram kernel of gemm_tc.cu): 64 contiguous MN elements per
@@ -71,9 +74,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int tap = blockIdx.x % g.taps;
-  const int split = blockIdx.x / g.taps;
-  const int splits = gridDim.x / g.taps;
+  const int tap0 = (blockIdx.x % g.tap_groups) * g.tpg;
+  const int split = blockIdx.x / g.tap_groups;
+  const int splits = gridDim.x / g.tap_groups;
   const int ci_blk = blockIdx.y % g.ci_blocks;
   const int co_blk = blockIdx.y / g.ci_blocks;
   const int num_tiles = (g.Mp + kRows - 1) / kRows;
@@ -101,32 +104,40 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const int r = tap / g.S;
-      const int s = tap - r * g.S;
+      int valid = 0;                                   // panels that hold a real (tap, channel slab)
+      for (int pp = 0; pp < L::kBPanels; ++pp)
+        valid += (tap0 + pp / g.ppt < g.taps) && (ci_blk * BNC + (pp % g.ppt) * 64 < g.C);
+      const uint32_t stage_tx = (uint32_t)((2 + valid) * kPanel);
       for (int t = split; t < num_tiles; t += splits) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * L::kStageBytes;
         uint8_t* sb = sa + 2 * kPanel;
-        mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+        mbar_expect_tx(&full_bar[stage], stage_tx);
         const int m0 = t * kRows;
         tma_load_2d(sa, &tmap_dy, &full_bar[stage], co_blk * 128, m0);               // columns past Cout: zero fill
         tma_load_2d(sa + kPanel, &tmap_dy, &full_bar[stage], co_blk * 128 + 64, m0);
+        int cn = 0, cw = 0, ch = 0;
         if (g.is_im2col) {
           const int pq = g.P * g.Q;
-          const int cn = m0 / pq;
+          cn = m0 / pq;
           const int rem = m0 - cn * pq;
           const int p = rem / g.Q;
           const int q = rem - p * g.Q;
-          const int cw = g.lower_w + q * g.stride;
-          const int ch = g.lower_h + p * g.stride;
+          cw = g.lower_w + q * g.stride;
+          ch = g.lower_h + p * g.stride;
+        }
 #pragma unroll
-          for (int pp = 0; pp < L::kBPanels; ++pp)
-            tma_load_im2col_4d(sb + pp * kPanel, &tmap_x, &full_bar[stage], ci_blk * BNC + pp * 64, cw, ch, cn, (uint16_t)s,
-                               (uint16_t)r);
-        } else {
-#pragma unroll
-          for (int pp = 0; pp < L::kBPanels; ++pp)
-            tma_load_2d(sb + pp * kPanel, &tmap_x, &full_bar[stage], ci_blk * BNC + pp * 64, m0);
+        for (int pp = 0; pp < L::kBPanels; ++pp) {
+          const int tap = tap0 + pp / g.ppt;
+          const int c0 = ci_blk * BNC + (pp % g.ppt) * 64;
+          if (tap >= g.taps || c0 >= g.C) continue;          // the MMA reads stale shared memory there: never drained
+          if (g.is_im2col) {
+            const int r = tap / g.S;
+            const int s = tap - r * g.S;
+            tma_load_im2col_4d(sb + pp * kPanel, &tmap_x, &full_bar[stage], c0, cw, ch, cn, (uint16_t)s, (uint16_t)r);
+          } else {
+            tma_load_2d(sb + pp * kPanel, &tmap_x, &full_bar[stage], c0, m0);
+          }
         }
         if (++stage == kStages) {
           stage = 0;
@@ -171,11 +182,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
       tc_fence_after();
       const int quarter = warp & 3;
       const int co = co_blk * 128 + quarter * 32 + lane;
-      float* dst_row = dw + ((long)co * g.taps + tap) * g.C;
 #pragma unroll 1
       for (int ch = 0; ch < BNC / 32; ++ch) {
-        const int ci0 = ci_blk * BNC + ch * 32;
-        if (ci0 >= g.C) break;                       // warp-uniform
+        const int pp = ch >> 1;
+        const int tap = tap0 + pp / g.ppt;
+        const int ci0 = ci_blk * BNC + (pp % g.ppt) * 64 + (ch & 1) * 32;
+        if (tap >= g.taps || ci0 >= g.C) continue;     // warp-uniform
+        float* dst_row = dw + ((long)co * g.taps + tap) * g.C;
         uint32_t raw[32];
         tc_ld32(tmem_base + (uint32_t)(ch * 32) + ((uint32_t)(quarter * 32) << 16), raw);
         tc_wait_ld();
@@ -265,7 +278,7 @@ bn_bwd_reduce_kernel(const bf16* dz, bf16* dzm, const bf16* __restrict__ z, cons
 #pragma unroll
         for (int j = 0; j < 8; ++j) gf[j] = zf[j] > 0.f ? gf[j] : 0.f;
         g.x = pack2(gf[0], gf[1]); g.y = pack2(gf[2], gf[3]); g.z = pack2(gf[4], gf[5]); g.w = pack2(gf[6], gf[7]);
-        *reinterpret_cast<uint4*>(dzm + off) = g;
+        if (dzm != nullptr) *reinterpret_cast<uint4*>(dzm + off) = g;
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -295,32 +308,42 @@ bn_bwd_reduce_kernel(const bf16* dz, bf16* dzm, const bf16* __restrict__ z, cons
   }
 }
 
+// dy = A[c] * dz + B[c] * y + K[c]  with  A = gamma * invstd,  B = -A * invstd * s2 / count,  K = -A * s1 / count - B * mean
+// (train) or dy = A[c] * dz (eval).  A thread's 8 channels are the same for every row it visits (the grid stride is a
+// multiple of the channel-group count), so the coefficients are computed once.  z != NULL: dz is masked by (z > 0) here.
 __global__ void __launch_bounds__(256)
-bn_bwd_apply_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ y, bf16* __restrict__ dy,
-                    const float* __restrict__ gamma, const float* __restrict__ sum, const float* __restrict__ sumsq,
-                    const float* __restrict__ rmean, const float* __restrict__ rvar, const float* __restrict__ s1,
-                    const float* __restrict__ s2, long M, int C, float inv_count, float eps, int train) {
+bn_bwd_apply_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ z, const bf16* __restrict__ y,
+                    bf16* __restrict__ dy, const float* __restrict__ gamma, const float* __restrict__ sum,
+                    const float* __restrict__ sumsq, const float* __restrict__ rmean, const float* __restrict__ rvar,
+                    const float* __restrict__ s1, const float* __restrict__ s2, long M, int C, float inv_count, float eps,
+                    int train) {
   const int groups = C >> 3;
   const long total = M * groups;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int grp = (int)(i % groups);
+  const long i0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int grp = (int)(i0 % groups);
+  float ca[8], cb[8], ck[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = grp * 8 + j;
+    float mean, invstd;
+    bn_mean_invstd(sum, sumsq, rmean, rvar, c, inv_count, eps, train, mean, invstd);
+    ca[j] = gamma[c] * invstd;
+    cb[j] = train ? -ca[j] * invstd * s2[c] * inv_count : 0.f;
+    ck[j] = train ? -ca[j] * s1[c] * inv_count - cb[j] * mean : 0.f;
+  }
+  for (long i = i0; i < total; i += (long)gridDim.x * blockDim.x) {
     const long off = (i / groups) * C + grp * 8;
     float gf[8], yf[8], o[8];
     unpack8(*reinterpret_cast<const uint4*>(dz + off), gf);
     unpack8(*reinterpret_cast<const uint4*>(y + off), yf);
+    if (z != nullptr) {
+      float zf[8];
+      unpack8(*reinterpret_cast<const uint4*>(z + off), zf);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = grp * 8 + j;
-      float mean, invstd;
-      bn_mean_invstd(sum, sumsq, rmean, rvar, c, inv_count, eps, train, mean, invstd);
-      const float a = gamma[c] * invstd;
-      if (train) {
-        const float xh = (yf[j] - mean) * invstd;
-        o[j] = a * (gf[j] - s1[c] * inv_count - xh * s2[c] * inv_count);
-      } else {
-        o[j] = a * gf[j];
-      }
+      for (int j = 0; j < 8; ++j) gf[j] = zf[j] > 0.f ? gf[j] : 0.f;
     }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = fmaf(ca[j], gf[j], fmaf(cb[j], yf[j], ck[j]));
     uint4 r;
     r.x = pack2(o[0], o[1]); r.y = pack2(o[2], o[3]); r.z = pack2(o[4], o[5]); r.w = pack2(o[6], o[7]);
     *reinterpret_cast<uint4*>(dy + off) = r;
@@ -452,12 +475,12 @@ int launch_wgrad(const CUtensorMap& tdy, const CUtensorMap& tx, const WgGeom& g,
     attr_set = true;
   }
   const int co_blocks = b2_ceil_div(g.Cout, 128);
-  const int units = g.taps * co_blocks * g.ci_blocks;
+  const int units = g.tap_groups * co_blocks * g.ci_blocks;
   const int tiles = b2_ceil_div(g.Mp, kRows);
-  int splits = b2_ceil_div(b2_num_sms(), units);
+  int splits = b2_num_sms() / units;          // one CTA per SM and a single wave
   if (splits > tiles) splits = tiles;
   if (splits < 1) splits = 1;
-  dim3 grid((unsigned)(g.taps * splits), (unsigned)(co_blocks * g.ci_blocks));
+  dim3 grid((unsigned)(g.tap_groups * splits), (unsigned)(co_blocks * g.ci_blocks));
   conv_wgrad_kernel<BNC><<<grid, kWgThreads, L::kSmem, stream>>>(tdy, tx, g, dw);
   B2_LAUNCH_CHECK("conv_wgrad_kernel");
   return 0;
@@ -510,8 +533,12 @@ B2_API int b2_conv2d_wgrad_nhwc_bf16(const void* x, int Nimg, int H, int W, int 
     cudaDriverGetVersion(&drv);
     if (drv <= 13010 && (long)Nimg * H * W * C * 2 < 131072) reinterpret_cast<uint64_t*>(&tx)[1] &= ~(1ull << 21);
   }
-  const int bnc = C > 128 ? 256 : (C > 64 ? 128 : 64);
-  WgGeom g = {plain ? 0 : 1, P, Q, S, stride, -pad, -pad, R * S, (int)Ml, Cout, C, b2_ceil_div(C, bnc)};
+  const int taps = R * S;
+  const bool grouped = taps > 1 && C <= 128;         // C = 64: 4 taps per CTA, C = 128: 2 taps per CTA (N = 256)
+  const int bnc = grouped ? 256 : (C > 128 ? 256 : (C > 64 ? 128 : 64));
+  const int tpg = grouped ? 256 / C : 1;
+  WgGeom g = {plain ? 0 : 1, P, Q, S, stride, -pad, -pad, taps, (int)Ml, Cout, C, grouped ? 1 : b2_ceil_div(C, bnc),
+              tpg,  grouped ? C / 64 : bnc / 64, b2_ceil_div(taps, tpg)};
   cudaStream_t st = (cudaStream_t)stream;
   switch (bnc) {
     case 256: return launch_wgrad<256>(tdy, tx, g, dw, st);
@@ -521,16 +548,15 @@ B2_API int b2_conv2d_wgrad_nhwc_bf16(const void* x, int Nimg, int H, int W, int 
 }
 
 // Train-mode (train = 1: mean / invstd from sum, sumsq over `count` rows) or eval-mode (running statistics) BatchNorm
-// backward over [M, C] bf16.  When z is given (the ReLU behind the BatchNorm) dzm = dz * [z > 0] is written and used;
+// backward over [M, C] bf16.  When z is given (the ReLU behind the BatchNorm) dz is masked by (z > 0); the masked
+// gradient is also written to dzm when dzm != NULL (the shortcut branch's gradient);
 // s1 = sum(dz) = dbeta and s2 = sum(dz * xhat) = dgamma are ACCUMULATED (caller zeroes); dy may alias nothing.
 B2_API int b2_bn_bwd_nhwc_bf16(const void* dz, void* dzm, const void* z, const void* y, void* dy, const float* gamma, const float* sum,
                                const float* sumsq, const float* running_mean, const float* running_var, float* s1, float* s2,
                                long M, int C, long count, float eps, int train, void* stream) {
   const char* who = "b2_bn_bwd_nhwc_bf16";
   B2_ARG_CHECK(dz && y && dy && gamma && s1 && s2 && M > 0, "%s: null pointer or empty", who);
-  B2_ARG_CHECK((z == nullptr) == (dzm == nullptr), "%s: the ReLU mask z and the masked-gradient output dzm go together", who);
-  B2_ARG_CHECK(C % 8 == 0 && C >= 8 && C <= 2048, "%s: C must be a multiple of 8 in [8, 2048] (got %d)", who, C);
-  B2_ARG_CHECK(train ? (sum && sumsq && count > 0) : (running_mean && running_var), "%s: statistics missing", who);
+  B2_ARG_CHECK(dzm == nullptr || z != nullptr, "%s: the masked-gradient output dzm needs the ReLU mask z", who);
   cudaStream_t st = (cudaStream_t)stream;
   const float inv = train ? 1.f / (float)count : 0.f;
   const int groups = C / 8;
@@ -541,8 +567,11 @@ B2_API int b2_bn_bwd_nhwc_bf16(const void* dz, void* dzm, const void* z, const v
   bn_bwd_reduce_kernel<<<blocks, 256, 0, st>>>((const bf16*)dz, (bf16*)dzm, (const bf16*)z, (const bf16*)y, sum, sumsq, running_mean,
                                                running_var, s1, s2, M, C, (int)rpb, inv, eps, train);
   B2_LAUNCH_CHECK("bn_bwd_reduce_kernel");
-  bn_bwd_apply_kernel<<<ew_blocks(M * groups), 256, 0, st>>>((const bf16*)(z != nullptr ? dzm : dz), (const bf16*)y, (bf16*)dy, gamma, sum, sumsq,
-                                                             running_mean, running_var, s1, s2, M, C, inv, eps, train);
+  // the grid stride (blocks * 256 threads) must be a multiple of the channel-group count for the hoisted coefficients
+  unsigned ab = ew_blocks(M * groups);
+  if (256 % groups != 0) ab = ab / groups * groups > 0 ? ab / groups * groups : groups;
+  bn_bwd_apply_kernel<<<ab, 256, 0, st>>>((const bf16*)dz, (const bf16*)z, (const bf16*)y, (bf16*)dy, gamma, sum, sumsq,
+                                          running_mean, running_var, s1, s2, M, C, inv, eps, train);
   B2_LAUNCH_CHECK("bn_bwd_apply_kernel");
   return 0;
 }
