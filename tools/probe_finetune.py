@@ -21,8 +21,9 @@ runner = vc.backbone.ResNetRunner(net)
 x = torch.rand(frames, 3, 112, 112, device=dev)
 g = torch.randn(frames, feat, device=dev)
 n0 = vc._lib.launch_count()
-for it in range(steps + 2):
-    if it == 2:
+WARM = int(os.environ.get('WARM', '2'))
+for it in range(steps + WARM):
+    if it == WARM:
         torch.cuda.synchronize()
         t0 = time.time()
         n0 = vc._lib.launch_count()
