@@ -278,6 +278,15 @@ int b2_avgpool_bwd_nhwc(const float* dfeat, void* dz, long N, int HW, int C, voi
 int b2_maxpool_relu_bwd_nhwc(const void* raw, const float* scale, const float* shift, const void* dpool, float* dbn, int N,
                              int H, int W, int P, int Q, int C, void* stream);
 
+/* ---- DenseNet frame encoder element kernels (csrc/dense_ops.cu; densenet121 of lrcn/lrcn.py:196-209, rgb_lrcn.py:180-193) ----
+ * A dense block is ONE channel-concatenated NHWC buffer (row stride = final channel count); these kernels work on
+ * row-strided bf16 tensors.  b2_scale_shift_apply_ld_bf16: y[r,:C] = act(x[r,:C]*scale+shift) (scale = NULL: slice copy);
+ * b2_colstats_ld_bf16: per-channel sum / sumsq, ACCUMULATED; b2_avgpool2x2_nhwc_bf16: AvgPool2d(2,2) into a strided dst. */
+int b2_scale_shift_apply_ld_bf16(const void* x, long ldx, void* y, long ldy, long rows, int C, const float* scale,
+                                 const float* shift, int relu, void* stream);
+int b2_colstats_ld_bf16(const void* x, long ld, long rows, int C, float* sum, float* sumsq, void* stream);
+int b2_avgpool2x2_nhwc_bf16(const void* x, void* y, long ldy, int N, int H, int W, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -372,6 +372,50 @@ def resnet_features(sd: Dict[str, torch.Tensor], x: torch.Tensor, arch: str, tra
     return feat, ns
 
 
+_DENSENET_CFG = {"densenet121": (32, (6, 12, 24, 16), 64), "densenet169": (32, (6, 12, 32, 32), 64),
+                 "densenet201": (32, (6, 12, 48, 32), 64),
+                 "densenet_tiny": (32, (2, 2, 2, 2), 64)}     # test-only: every layer type, little depth
+
+
+def densenet_features(sd: Dict[str, torch.Tensor], x: torch.Tensor, arch: str, train: bool = True,
+                      prefix: str = "cnn_backbone.", emulate_bf16: bool = False, return_stages: bool = False):
+    """torchvision.models.densenet{121,169,201} with classifier=Identity (lrcn/lrcn.py:196-209): conv0 7x7/2, norm0,
+    relu, maxpool 3x3/2; dense blocks of layers [norm1, relu, conv1 1x1 -> 4*growth, norm2, relu, conv2 3x3 -> growth,
+    concatenated to the input]; transitions [norm, relu, conv 1x1 -> C/2, avgpool 2x2]; norm5, relu, global average pool.
+    Train-mode BN uses batch statistics.  emulate_bf16: bf16 storage at the points the B200 path rounds.
+    Returns (features, new running stats) [+ per-stage spatial means]."""
+    growth, blocks, c0 = _DENSENET_CFG[arch]
+    sdp = {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+    ns: Dict[str, torch.Tensor] = {}
+    rnd = _bf16 if emulate_bf16 else (lambda t: t)
+
+    def conv(inp, w, **kw):
+        return rnd(F.conv2d(rnd(inp), rnd(w), None, **kw))
+
+    y = conv(x, sdp["features.conv0.weight"], stride=2, padding=3)
+    y = rnd(F.max_pool2d(torch.relu(_bn(y, sdp, "features.norm0", train, ns)), 3, 2, 1))
+    stages = [y.mean(dim=(2, 3))]
+    for bi, depth in enumerate(blocks):
+        for li in range(depth):
+            p = f"features.denseblock{bi + 1}.denselayer{li + 1}"
+            o = rnd(torch.relu(_bn(y, sdp, p + ".norm1", train, ns)))
+            o = conv(o, sdp[p + ".conv1.weight"])
+            o = rnd(torch.relu(_bn(o, sdp, p + ".norm2", train, ns)))
+            o = conv(o, sdp[p + ".conv2.weight"], padding=1)
+            y = torch.cat([y, o], dim=1)
+        stages.append(y.mean(dim=(2, 3)))
+        if bi + 1 < len(blocks):
+            p = f"features.transition{bi + 1}"
+            o = rnd(torch.relu(_bn(y, sdp, p + ".norm", train, ns)))
+            y = rnd(F.avg_pool2d(conv(o, sdp[p + ".conv.weight"]), 2, 2))
+    y = rnd(torch.relu(_bn(y, sdp, "features.norm5", train, ns)))
+    feat = y.mean(dim=(2, 3))
+    ns = {prefix + k: v for k, v in ns.items()}
+    if return_stages:
+        return feat, ns, stages
+    return feat, ns
+
+
 def medsos_lrcn_forward(sd, x, arch, hidden, rnn_layers, bidirectional, rnn_out="all",
                         train=True, emulate_bf16_backbone=False):
     """medsos_lrcn/src/models.py:188-234 with rnn_type='lstm', multiclass head, dropout p=0."""
@@ -396,7 +440,8 @@ def simple_lrcn_forward(sd, x, arch, hidden, rnn_layers, adapt_names=("adapt1", 
     lrcn/lrcn.py:285-305 / rgb_lrcn.py:247-263 (one `adapt`, attribute `lstm`); always
     bidirectional.  num_heads!=None -> per-class binary heads fc.{i} concatenated (lrcn.py:303)."""
     B, T, C, H, W = x.shape
-    feat, ns = resnet_features(sd, x.reshape(B * T, C, H, W), arch, train, emulate_bf16=emulate_bf16_backbone)
+    backbone = densenet_features if arch.startswith("densenet") else resnet_features
+    feat, ns = backbone(sd, x.reshape(B * T, C, H, W), arch, train, emulate_bf16=emulate_bf16_backbone)
     y = feat.reshape(B, T, -1)
     for a in adapt_names:
         y = y @ sd[a + ".weight"].t() + sd[a + ".bias"]

@@ -204,6 +204,41 @@ def gold_simple():
     save("crime_lrcn_resnet18.npz", **arrs)
 
 
+def gold_crime_densenet():
+    # crime lrcn.py topology with ITS default backbone (CONF_CNN_BACKBONE = densenet121, lrcn.py:196-209), frozen
+    C, g0 = refload.crime_lrcn(CONF_CNN_BACKBONE="densenet121", CONF_RNN_LAYER=2, CONF_CLASSIF_MODE="multiple_binary",
+                               CONF_FINETUNE=False)
+    torch.manual_seed(17)
+    m = C(3, 3, 12, 16, cnn_backbone="densenet121")
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randint(0, 256, (2, 3, 3, 64, 64), generator=g).float() / 255.0
+    yb = torch.tensor([[1., 0., 0.], [0., 0., 1.]])
+    sd0, out, loss, grads, sd1 = run_step(m, x, yb, loss_kind="bce")
+    arrs = {"x": x.numpy(), "y": yb.numpy(), "logits": out.numpy(), "loss": loss.numpy(),
+            "backbone_checksum": np.array(checksum(sd0, "cnn_backbone.")),
+            "meta": np.array(json.dumps(dict(arch="densenet121", size=64, B=2, T=3, hidden=12, rnn_input=16,
+                                             rnn_layers=2, num_classes=3, seed=17,
+                                             source="lrcn/lrcn.py:181-305 multiple_binary; loss=mean BCEWithLogits")))}
+    for k, v in npd(sd0).items():
+        if not k.startswith("cnn_backbone."):
+            arrs["sd0/" + k] = v
+    for k, v in npd(grads).items():
+        arrs["grad/" + k] = v
+    for k in ("cnn_backbone.features.norm0.running_mean", "cnn_backbone.features.denseblock1.denselayer3.norm1.running_var",
+              "cnn_backbone.features.transition2.norm.running_mean", "cnn_backbone.features.denseblock4.denselayer16.norm2.running_var",
+              "cnn_backbone.features.norm5.running_var"):
+        arrs["sd1/" + k] = sd1[k].numpy()
+    with torch.no_grad():                       # pooled backbone features (train-mode BN) and eval-mode features
+        m2 = C(3, 3, 12, 16, cnn_backbone="densenet121")
+        m2.load_state_dict(sd0)
+        m2.train()
+        arrs["features"] = m2.cnn_backbone(x.view(6, 3, 64, 64)).numpy()
+        m2.load_state_dict(sd0)
+        m2.eval()
+        arrs["features_eval"] = m2.cnn_backbone(x.view(6, 3, 64, 64)).numpy()
+    save("crime_lrcn_densenet121.npz", **arrs)
+
+
 def gold_lstm():
     # nn.LSTM exactly as the reference configures it (lrcn.py:236: 4-layer biLSTM H=56 -> here 2x2, H=7)
     torch.manual_seed(5)
@@ -349,3 +384,4 @@ if __name__ == "__main__":
     gold_gru()
     gold_mamba()
     gold_ckpt()
+    gold_crime_densenet()

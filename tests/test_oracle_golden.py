@@ -120,6 +120,24 @@ def test_simple_and_crime_oracle_vs_golden():
     assert err(logits, torch.from_numpy(g["logits"])) < 1e-4
 
 
+def test_densenet_oracle_vs_golden():
+    """DenseNet-121 restated by the oracle vs the reference crime LRCN's own default backbone (lrcn.py:196-209): pooled
+    features in train- and eval-mode BN, running statistics after the step, logits through the crime tail."""
+    m, g, meta = build_backbone_model("crime_lrcn_densenet121.npz")
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    x = torch.from_numpy(g["x"])
+    frames = x.reshape(-1, *x.shape[2:])
+    feat, ns = O.densenet_features(sd, frames, "densenet121", train=True)
+    assert err(feat, torch.from_numpy(g["features"])) < 1e-4
+    for k, v in golden_tensors(g, "sd1/").items():
+        assert err(ns[k], v) < 1e-4, k
+    feat_e, _ = O.densenet_features(sd, frames, "densenet121", train=False)
+    assert err(feat_e, torch.from_numpy(g["features_eval"])) < 1e-4
+    logits, _ = O.simple_lrcn_forward(sd, x, "densenet121", meta["hidden"], meta["rnn_layers"], adapt_names=("adapt",),
+                                      rnn_prefix="lstm.", num_heads=meta["num_classes"])
+    assert err(logits, torch.from_numpy(g["logits"])) < 1e-4
+
+
 @pytest.mark.parametrize("tag", ["uni", "bi"])
 def test_gru_oracle_vs_golden(tag):
     """Manual GRU cell of the oracle vs torch.nn.GRU outputs and gradients recorded from the reference's engine."""

@@ -32,14 +32,28 @@ def make_backbone(name: str, pretrained: bool = False):
     """torchvision constructor + the reference's head surgery (fc/classifier -> Identity).
     Returns (module, feature_size)."""
     import torchvision.models as tvm
+    from .densenet import SUPPORTED as DENSE
+    if name in DENSE:
+        net = getattr(tvm, name)(weights="DEFAULT" if pretrained else None)
+        feat = net.classifier.in_features
+        net.classifier = torch.nn.Identity()
+        return net, feat
     if name not in SUPPORTED:
         raise NotImplementedError(
-            f"cnn_backbone={name!r}: only ResNet-class backbones {SUPPORTED} run on the B200 kernels in this "
-            "round (DenseNet/MobileNet are listed under 'next' in DESIGN.md)")
+            f"cnn_backbone={name!r}: the B200 kernels run the ResNet-class backbones {SUPPORTED} and {DENSE} "
+            "(MobileNet and the other torchvision families are listed under 'next' in DESIGN.md)")
     net = getattr(tvm, name)(weights="DEFAULT" if pretrained else None)
     feat = net.fc.in_features
     net.fc = torch.nn.Identity()
     return net, feat
+
+
+def make_runner(net):
+    """The kernel-side executor of a backbone module built by make_backbone()."""
+    if hasattr(net, "features"):
+        from .densenet import DenseNetRunner
+        return DenseNetRunner(net)
+    return ResNetRunner(net)
 
 
 class ResNetRunner:

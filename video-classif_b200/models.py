@@ -18,7 +18,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .backbone import ResNetRunner, make_backbone
+from .backbone import ResNetRunner, make_backbone, make_runner  # noqa: F401
 
 
 def _check_input(x, seq_len=None):
@@ -134,7 +134,7 @@ class _BackboneLRCN(nn.Module):
 
     def _make_backbone(self, name, pretrained):
         self.cnn_backbone, feat = make_backbone(name, pretrained)
-        object.__setattr__(self, "_runner", ResNetRunner(self.cnn_backbone))
+        object.__setattr__(self, "_runner", make_runner(self.cnn_backbone))
         return feat
 
     def _features(self, x):
@@ -203,7 +203,7 @@ class _BackboneLRCN(nn.Module):
 
     def __setstate__(self, state):
         self.__dict__.update(state)
-        object.__setattr__(self, "_runner", ResNetRunner(self.cnn_backbone))
+        object.__setattr__(self, "_runner", make_runner(self.cnn_backbone))
 
 
 class LRCN(_BackboneLRCN):
