@@ -286,6 +286,13 @@ int b2_scale_shift_apply_ld_bf16(const void* x, long ldx, void* y, long ldy, lon
                                  const float* shift, int relu, void* stream);
 int b2_colstats_ld_bf16(const void* x, long ld, long rows, int C, float* sum, float* sumsq, void* stream);
 int b2_avgpool2x2_nhwc_bf16(const void* x, void* y, long ldy, int N, int H, int W, int C, void* stream);
+/* backward twins: BatchNorm (+ReLU mask) backward between row-strided tensors, result written / ACCUMULATED into the
+ * block's gradient buffer; AvgPool2d(2,2) backward. */
+int b2_bn_bwd_ld_bf16(const void* dz, long lddz, const void* z, long ldz, const void* x, long ldx, void* dx, long lddx,
+                      int accumulate, const float* gamma, const float* sum, const float* sumsq, const float* running_mean,
+                      const float* running_var, float* s1, float* s2, long M, int C, long count, float eps, int train,
+                      void* stream);
+int b2_avgpool2x2_bwd_nhwc_bf16(const void* dy, long lddy, void* dx, int N, int H, int W, int C, void* stream);
 
 #ifdef __cplusplus
 }

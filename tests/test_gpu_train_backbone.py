@@ -229,3 +229,107 @@ def test_crime_lrcn_partial_freeze_trains():
     assert all(p.grad is not None for n, p in m.cnn_backbone.named_parameters() if n in trainable)
     assert all(p.grad is None for n, p in m.cnn_backbone.named_parameters() if n not in trainable)
     assert losses[-1] < losses[0], losses
+
+
+def _densenet_teacher_forced(net, y0, saved, G):
+    """torch autograd over torchvision DenseNet's trunk with every produced tensor's VALUE replaced by ours (block buffers,
+    bottleneck tensors) and the ReLU masks of the bottleneck taken from ours; see _teacher_forced_reference."""
+    def sub(v, ours_nhwc, relu=False):
+        ours = ours_nhwc.float().permute(0, 3, 1, 2)
+        assert ours.shape == v.shape, (ours.shape, v.shape)
+        if relu:
+            v = v * (ours > 0).float()
+        return ours.detach() + (v - v.detach())
+
+    def bn(t, m):
+        return F.batch_norm(t, None, None, m.weight, m.bias, True, 0.0, m.eps)
+
+    f = net.features
+    feats = y0
+    pos = [0]
+
+    def nxt_entry():
+        pos[0] += 1
+        return saved[pos[0] - 1]
+
+    for name, mod in f.named_children():
+        if name.startswith("denseblock"):
+            _, X, S, C0, growth, rec = nxt_entry()
+            N, H, W, Cfin = X.shape
+            for k, (lname, layer) in enumerate(mod.named_children()):
+                _, _, y1, a2, _ = rec[k]
+                Ct = C0 + k * growth
+                a1 = rnd(torch.relu(bn(feats, layer.norm1)))
+                y1_t = sub(rnd(F.conv2d(a1, rnd(layer.conv1.weight))), y1.view(N, H, W, -1))
+                a2_t = sub(bn(y1_t, layer.norm2), a2.view(N, H, W, -1), relu=True)
+                y2_t = sub(rnd(F.conv2d(a2_t, rnd(layer.conv2.weight), padding=1)), X[..., Ct:Ct + growth])
+                feats = torch.cat([feats, y2_t], dim=1)
+        elif name.startswith("transition"):
+            _, _, _, X, S, Hc, Wc, C, Cn = nxt_entry()
+            a = rnd(torch.relu(bn(feats, mod.norm)))
+            pooled = F.avg_pool2d(rnd(F.conv2d(a, rnd(mod.conv.weight))), 2, 2)
+            feats = sub(pooled, saved[pos[0]][1][..., :Cn])          # the next block's buffer starts with the pooled features
+        elif name == "norm5":
+            feats = torch.relu(bn(feats, mod))
+    feat = feats.mean(dim=(2, 3))
+    (feat * G).sum().backward()
+    return feat
+
+
+def test_densenet_finetune_gradients_teacher_forced():
+    """Trainable DenseNet (growth 32, blocks (2,2,2,2): every layer type): features and the gradient of EVERY parameter
+    behind the stem, plus the gradient handed to the stem, vs the teacher-forced torch reference."""
+    import torchvision
+    from video_classif_b200 import densenet_train as DT
+    from video_classif_b200.densenet import DenseNetRunner
+    torch.manual_seed(5)
+    net = torchvision.models.DenseNet(32, (2, 2, 2, 2), 64)
+    net.classifier = torch.nn.Identity()
+    net = net.to(DEV).train()
+    runner = DenseNetRunner(net)
+    x = torch.rand(8, 3, 64, 64, device=DEV)
+    G = torch.randn(8, net.features.norm5.num_features, device=DEV)
+    with torch.no_grad():
+        y0 = runner.stem(x, True)
+    y0 = y0.requires_grad_(True)
+    names, params = DT._trunk_params(net)
+    DT._record = rec = []
+    try:
+        feat = DT.DenseTrunkFn.apply(y0, runner, True, names, *params)
+    finally:
+        DT._record = None
+    (feat * G).sum().backward()
+    got = {n: p.grad.clone() for n, p in zip(names, params)}
+    dy0 = y0.grad.clone()
+    assert all(torch.isfinite(v).all() for v in got.values())
+    for p in params:
+        p.grad = None
+    y0r = y0.detach().float().permute(0, 3, 1, 2).requires_grad_(True)
+    ref_feat = _densenet_teacher_forced(net, y0r, rec[0], G)
+    assert rel(feat, ref_feat) < 1e-2
+    errs = sorted(((rel(got[n], p.grad, floor=1e-6), n) for n, p in zip(names, params)), reverse=True)
+    assert errs[0][0] < 5e-2, errs[:6]
+    assert errs[len(errs) // 2][0] < 2e-2, errs[len(errs) // 2]
+    assert rel(dy0.float().permute(0, 3, 1, 2), y0r.grad) < 3e-2
+
+
+def test_crime_lrcn_default_densenet121_finetune_trains():
+    """The reference's default crime configuration (densenet121, FINETUNE = True -> nothing frozen, lrcn.py:27,34,230):
+    whole-model training steps; every backbone parameter receives a finite gradient and the loss goes down."""
+    import video_classif_b200 as vc
+    torch.manual_seed(3)
+    m = vc.CrimeLRCN(3, 2, 8, 16, cnn_backbone="densenet121", finetune=True, rnn_layers=1).to(DEV).train()
+    assert all(p.requires_grad for p in m.cnn_backbone.parameters())
+    x = torch.rand(4, 2, 3, 64, 64, device=DEV)
+    y = torch.tensor([[1., 0., 0.], [0., 1., 0.], [0., 0., 1.], [1., 0., 0.]], device=DEV)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    losses = []
+    for _ in range(5):
+        opt.zero_grad()
+        loss = F.binary_cross_entropy_with_logits(m(x), y)
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.cnn_backbone.parameters())
+    assert int(m.cnn_backbone.features.denseblock2.denselayer5.norm2.num_batches_tracked) == 5
+    assert losses[-1] < losses[0], losses

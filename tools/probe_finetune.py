@@ -17,7 +17,7 @@ for n, p in net.named_parameters():
     on = on or n.startswith(first)
     p.requires_grad_(on)
 net = net.to(dev).train()
-runner = vc.backbone.ResNetRunner(net)
+runner = vc.backbone.make_runner(net)
 x = torch.rand(frames, 3, 112, 112, device=dev)
 g = torch.randn(frames, feat, device=dev)
 n0 = vc._lib.launch_count()

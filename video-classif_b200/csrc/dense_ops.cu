@@ -133,6 +133,144 @@ avgpool2x2_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, long ldy, in
   }
 }
 
+// ---- BatchNorm (+ReLU) backward between row-strided tensors, for the pre-activation BatchNorms of a dense block:
+// x = X[:, :C] of the concatenated buffer (stride ldx), dz / z contiguous-ish (their own strides), the result is written or
+// ACCUMULATED into the block's gradient buffer dX[:, :C] (stride lddx): every later layer adds its contribution there.
+__device__ __forceinline__ void mean_invstd(const float* sum, const float* sumsq, const float* rmean, const float* rvar, int c,
+                                            float inv_count, float eps, int train, float& mean, float& invstd) {
+  if (train) {
+    mean = sum[c] * inv_count;
+    const float var = fmaxf(sumsq[c] * inv_count - mean * mean, 0.f);
+    invstd = rsqrtf(var + eps);
+  } else {
+    mean = rmean[c];
+    invstd = rsqrtf(rvar[c] + eps);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_ld_kernel(const bf16* __restrict__ dz, long lddz, const bf16* __restrict__ z, long ldz,
+                        const bf16* __restrict__ x, long ldx, const float* __restrict__ sum, const float* __restrict__ sumsq,
+                        const float* __restrict__ rmean, const float* __restrict__ rvar, float* __restrict__ out_s1,
+                        float* __restrict__ out_s2, long M, int C, int rows_per_block, float inv_count, float eps, int train) {
+  __shared__ float red[2][256 * 8];
+  const int groups = C >> 3;
+  const int lanes = 256 / groups > 0 ? 256 / groups : 1;
+  const int grp = threadIdx.x % groups;
+  const int rl = threadIdx.x / groups;
+  const bool active = rl < lanes;
+  float mean[8], invstd[8], s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    s1[j] = s2[j] = 0.f;
+    mean[j] = invstd[j] = 0.f;
+    if (active) mean_invstd(sum, sumsq, rmean, rvar, grp * 8 + j, inv_count, eps, train, mean[j], invstd[j]);
+  }
+  const long r0 = (long)blockIdx.x * rows_per_block;
+  const long r1 = min(M, r0 + rows_per_block);
+  if (active) {
+    for (long r = r0 + rl; r < r1; r += lanes) {
+      float gf[8], xf[8];
+      unpack8(*reinterpret_cast<const uint4*>(dz + r * lddz + grp * 8), gf);
+      unpack8(*reinterpret_cast<const uint4*>(x + r * ldx + grp * 8), xf);
+      if (z != nullptr) {
+        float zf[8];
+        unpack8(*reinterpret_cast<const uint4*>(z + r * ldz + grp * 8), zf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gf[j] = zf[j] > 0.f ? gf[j] : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s1[j] += gf[j];
+        s2[j] = fmaf(gf[j], (xf[j] - mean[j]) * invstd[j], s2[j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red[0][threadIdx.x * 8 + j] = active ? s1[j] : 0.f;
+    red[1][threadIdx.x * 8 + j] = active ? s2[j] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += 256) {
+    const int gq = i >> 3, j = i & 7;
+    float a = 0.f, b = 0.f;
+    for (int l = 0; l < lanes; ++l) {
+      a += red[0][(l * groups + gq) * 8 + j];
+      b += red[1][(l * groups + gq) * 8 + j];
+    }
+    atomicAdd(out_s1 + i, a);
+    atomicAdd(out_s2 + i, b);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_ld_kernel(const bf16* __restrict__ dz, long lddz, const bf16* __restrict__ z, long ldz,
+                       const bf16* __restrict__ x, long ldx, bf16* __restrict__ dx, long lddx, int accumulate,
+                       const float* __restrict__ gamma, const float* __restrict__ sum, const float* __restrict__ sumsq,
+                       const float* __restrict__ rmean, const float* __restrict__ rvar, const float* __restrict__ s1,
+                       const float* __restrict__ s2, long M, int C, float inv_count, float eps, int train) {
+  const int groups = C >> 3;
+  const long total = M * groups;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int grp = (int)(i % groups);
+    const long r = i / groups;
+    float gf[8], xf[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(dz + r * lddz + grp * 8), gf);
+    unpack8(*reinterpret_cast<const uint4*>(x + r * ldx + grp * 8), xf);
+    if (z != nullptr) {
+      float zf[8];
+      unpack8(*reinterpret_cast<const uint4*>(z + r * ldz + grp * 8), zf);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gf[j] = zf[j] > 0.f ? gf[j] : 0.f;
+    }
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + grp * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + grp * 8 + 4));
+    const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = grp * 8 + j;
+      float mean, invstd;
+      mean_invstd(sum, sumsq, rmean, rvar, c, inv_count, eps, train, mean, invstd);
+      const float a = gm[j] * invstd;
+      o[j] = train ? a * (gf[j] - s1[c] * inv_count - (xf[j] - mean) * invstd * s2[c] * inv_count) : a * gf[j];
+    }
+    bf16* dst = dx + r * lddx + grp * 8;
+    if (accumulate) {
+      float prev[8];
+      unpack8(*reinterpret_cast<const uint4*>(dst), prev);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += prev[j];
+    }
+    *reinterpret_cast<uint4*>(dst) = pack8(o);
+  }
+}
+
+// backward of AvgPool2d(2, 2): dx[n, h, w, :] = 0.25 * dy[n, h/2, w/2, :] (rows / columns past 2P, 2Q get zero); dy row-strided
+__global__ void __launch_bounds__(256)
+avgpool2x2_bwd_kernel(const bf16* __restrict__ dy, long lddy, bf16* __restrict__ dx, int N, int H, int W, int C) {
+  const int groups = C >> 3;
+  const int P = H >> 1, Q = W >> 1;
+  const long total = (long)N * H * W * groups;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % groups) << 3;
+    long px = i / groups;
+    const long orow = px;
+    const int w = (int)(px % W);
+    px /= W;
+    const int h = (int)(px % H);
+    const long n = px / H;
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = 0.f;
+    if ((h >> 1) < P && (w >> 1) < Q) {
+      unpack8(*reinterpret_cast<const uint4*>(dy + ((n * P + (h >> 1)) * Q + (w >> 1)) * lddy + c0), o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] *= 0.25f;
+    }
+    *reinterpret_cast<uint4*>(dx + orow * C + c0) = pack8(o);
+  }
+}
+
 unsigned ew_blocks(long n) {
   long b = (n + 255) / 256;
   const long cap = (long)b2_num_sms() * 16;
@@ -175,5 +313,42 @@ B2_API int b2_avgpool2x2_nhwc_bf16(const void* x, void* y, long ldy, int N, int 
   avgpool2x2_kernel<<<ew_blocks((long)N * (H / 2) * (W / 2) * (C / 8)), 256, 0, (cudaStream_t)stream>>>(
       (const bf16*)x, (bf16*)y, ldy, N, H, W, C);
   B2_LAUNCH_CHECK("avgpool2x2_kernel");
+  return 0;
+}
+
+// BatchNorm (+ReLU mask z > 0 when z != NULL) backward between row-strided tensors; s1 (= dbeta), s2 (= dgamma) ACCUMULATED
+// (caller zeroes); dx[:, :C] is overwritten (accumulate = 0) or added to (accumulate = 1).
+B2_API int b2_bn_bwd_ld_bf16(const void* dz, long lddz, const void* z, long ldz, const void* x, long ldx, void* dx, long lddx,
+                             int accumulate, const float* gamma, const float* sum, const float* sumsq,
+                             const float* running_mean, const float* running_var, float* s1, float* s2, long M, int C,
+                             long count, float eps, int train, void* stream) {
+  const char* who = "b2_bn_bwd_ld_bf16";
+  B2_ARG_CHECK(dz && x && dx && gamma && s1 && s2 && M > 0, "%s: null pointer or empty", who);
+  B2_ARG_CHECK(C % 8 == 0 && C >= 8 && C <= 2048, "%s: C must be a multiple of 8 in [8, 2048] (got %d)", who, C);
+  B2_ARG_CHECK(lddz % 8 == 0 && ldx % 8 == 0 && lddx % 8 == 0 && (z == nullptr || ldz % 8 == 0), "%s: row strides must be multiples of 8", who);
+  B2_ARG_CHECK(train ? (sum && sumsq && count > 0) : (running_mean && running_var), "%s: statistics missing", who);
+  cudaStream_t st = (cudaStream_t)stream;
+  const float inv = train ? 1.f / (float)count : 0.f;
+  const int groups = C / 8;
+  const int lanes = 256 / groups > 0 ? 256 / groups : 1;
+  long rpb = (M + (long)b2_num_sms() * 8 - 1) / ((long)b2_num_sms() * 8);
+  rpb = (rpb + lanes - 1) / lanes * lanes;
+  bn_bwd_reduce_ld_kernel<<<(unsigned)((M + rpb - 1) / rpb), 256, 0, st>>>((const bf16*)dz, lddz, (const bf16*)z, ldz,
+                                                                          (const bf16*)x, ldx, sum, sumsq, running_mean,
+                                                                          running_var, s1, s2, M, C, (int)rpb, inv, eps, train);
+  B2_LAUNCH_CHECK("bn_bwd_reduce_ld_kernel");
+  bn_bwd_apply_ld_kernel<<<ew_blocks(M * groups), 256, 0, st>>>((const bf16*)dz, lddz, (const bf16*)z, ldz, (const bf16*)x,
+                                                               ldx, (bf16*)dx, lddx, accumulate, gamma, sum, sumsq,
+                                                               running_mean, running_var, s1, s2, M, C, inv, eps, train);
+  B2_LAUNCH_CHECK("bn_bwd_apply_ld_kernel");
+  return 0;
+}
+
+B2_API int b2_avgpool2x2_bwd_nhwc_bf16(const void* dy, long lddy, void* dx, int N, int H, int W, int C, void* stream) {
+  B2_ARG_CHECK(dy && dx && N > 0 && H >= 2 && W >= 2, "b2_avgpool2x2_bwd_nhwc_bf16: null pointer or empty");
+  B2_ARG_CHECK(C % 8 == 0 && lddy % 8 == 0 && lddy >= C, "b2_avgpool2x2_bwd_nhwc_bf16: C and lddy must be multiples of 8");
+  avgpool2x2_bwd_kernel<<<ew_blocks((long)N * H * W * (C / 8)), 256, 0, (cudaStream_t)stream>>>((const bf16*)dy, lddy,
+                                                                                               (bf16*)dx, N, H, W, C);
+  B2_LAUNCH_CHECK("avgpool2x2_bwd_kernel");
   return 0;
 }

@@ -72,33 +72,50 @@ class DenseNetRunner:
         if self._params is None:
             self._params = list(net.parameters())
         if torch.is_grad_enabled() and any(p.requires_grad for p in self._params):
-            raise NotImplementedError("trainable DenseNet backbone: only the ResNet encoders have backward kernels "
-                                      "(backbone_train.py); freeze it (freeze_cnn_layers(None), lrcn.py:272-274)")
+            # lrcn.py / rgb_lrcn.py default: FINETUNE = True leaves the whole densenet121 trainable
+            from .densenet_train import encode_trainable
+            return encode_trainable(self, x, training)
+        y = self.stem(x, bool(training))
+        stages = [y.float().mean(dim=(1, 2))] if return_stages else None
+        feat = self.trunk(y, bool(training), stages=stages)
+        if training:
+            bns = [m for m in net.modules() if isinstance(m, torch.nn.BatchNorm2d)]
+            torch._foreach_add_([b.num_batches_tracked for b in bns if b.num_batches_tracked is not None], 1)
+        if return_stages:
+            return feat, stages
+        return feat
+
+    def stem(self, x, train):
+        """conv0 7x7/2 -> norm0 -> relu -> maxpool 3x3/2 (the ResNet stem kernels) -> [N, H/4, W/4, 64] bf16."""
         x = x.contiguous()
         N, Cin, H, W = x.shape
         assert Cin == 3, "frame encoder expects RGB frames"
         dev = x.device
         w = self._weights()
-        train = bool(training)
-        f = net.features
         st = stream_ptr()
-        # ---- stem: conv0 7x7/2 -> norm0 -> relu -> maxpool 3x3/2 (same kernels as the ResNet stem) ----
         s0 = torch.zeros(2 * 64, device=dev, dtype=F32)
         raw = stem_conv(x, w["features.conv0"], stats=(s0[:64], s0[64:]) if train else None)
         P, Q = raw.shape[1], raw.shape[2]
         Hc, Wc = (P + 2 - 3) // 2 + 1, (Q + 2 - 3) // 2 + 1
         y = torch.empty((N, Hc, Wc, 64), device=dev, dtype=BF16)
-        bn0 = f.norm0
+        bn0 = self.net.features.norm0
         call("b2_bn_relu_maxpool_nhwc", raw.data_ptr(), y.data_ptr(), N, P, Q, 64, ptr(s0[:64] if train else None),
              ptr(s0[64:] if train else None), bn0.weight.data_ptr(), bn0.bias.data_ptr(), bn0.running_mean.data_ptr(),
              bn0.running_var.data_ptr(), float(bn0.eps), float(_mom(bn0)), int(train), st)
-        del raw
-        stages = [y.float().mean(dim=(1, 2))] if return_stages else None
-        C = 64
-        src, src_ld = y, 64                               # the tensor (and row stride) holding the block's input features
+        return y
+
+    def trunk(self, y, train, stages=None, saved=None):
+        """Dense blocks, transitions, norm5 + ReLU + global average pool on the stem output y [N,H,W,64] bf16.
+        saved: a list that receives what the backward needs (densenet_train.py); nothing is kept otherwise."""
+        dev = y.device
+        w = self._weights()
+        f = self.net.features
+        st = stream_ptr()
+        N, Hc, Wc, C = y.shape
+        src, src_ld = y, C                                # the tensor (and row stride) holding the block's input features
         mods = [(n, m) for n, m in f.named_children() if n.startswith(("denseblock", "transition", "norm5"))]
-        X = S = None
-        for name, mod in mods:
+        X = S = ss = None
+        for mi, (name, mod) in enumerate(mods):
             if name.startswith("denseblock"):
                 layers = list(mod.children())
                 growth = layers[0].conv2.out_channels
@@ -115,6 +132,7 @@ class DenseNetRunner:
                 smid = torch.zeros((len(layers), 2, mid), device=dev, dtype=F32)
                 ssmid = torch.empty((2, mid), device=dev, dtype=F32)
                 pfx = "features." + name + "."
+                rec = []
                 for k, (lname, layer) in enumerate(mod.named_children()):
                     Ct = C + k * growth
                     self._finalize(layer.norm1, S.data_ptr(), S.data_ptr() + 4 * Cfin, M, train, ss, Ct)
@@ -123,13 +141,18 @@ class DenseNetRunner:
                          ss.data_ptr() + ss.stride(0) * 4, 1, st)
                     y1 = gemm_tn(a1, w[pfx + lname + ".conv1"], out_dtype=BF16, stats=(smid[k, 0], smid[k, 1]) if train else None)
                     self._finalize(layer.norm2, smid[k, 0].data_ptr(), smid[k, 1].data_ptr(), M, train, ssmid, mid)
-                    scale_shift_apply(y1, ssmid[0], ssmid[1], relu=True)
-                    y2 = conv2d_nhwc(y1.view(N, Hc, Wc, mid), w[pfx + lname + ".conv2"], 1, 1,
+                    a2 = torch.empty_like(y1) if saved is not None else y1
+                    scale_shift_apply(y1, ssmid[0], ssmid[1], relu=True, out=a2)
+                    y2 = conv2d_nhwc(a2.view(N, Hc, Wc, mid), w[pfx + lname + ".conv2"], 1, 1,
                                      stats=(S.data_ptr() + 4 * Ct, S.data_ptr() + 4 * (Cfin + Ct)) if train else None)
                     call("b2_scale_shift_apply_ld_bf16", y2.data_ptr(), growth, X.data_ptr() + 2 * Ct, Cfin, M, growth, 0, 0, 0, st)
-                    del a1, y1, y2
+                    if saved is not None:
+                        rec.append((pfx + lname, layer, y1, a2, smid[k]))
+                    del a1, y1, y2, a2
+                if saved is not None:
+                    saved.append(("block", X, S, C, growth, rec))
                 C = Cfin
-                if return_stages:
+                if stages is not None:
                     stages.append(X.float().mean(dim=(1, 2)))
             elif name.startswith("transition"):
                 M = N * Hc * Wc
@@ -141,13 +164,14 @@ class DenseNetRunner:
                 Cn = yt.shape[1]
                 del a
                 # AvgPool2d(2, 2) straight into the next block's concatenated buffer
-                nxt = mods[[n for n, _ in mods].index(name) + 1][1]
-                nl = list(nxt.children())
+                nl = list(mods[mi + 1][1].children())
                 Cfin = Cn + len(nl) * nl[0].conv2.out_channels
                 Hn, Wn = Hc // 2, Wc // 2
                 Xn = torch.empty((N, Hn, Wn, Cfin), device=dev, dtype=BF16)
                 call("b2_avgpool2x2_nhwc_bf16", yt.data_ptr(), Xn.data_ptr(), Cfin, N, Hc, Wc, Cn, st)
                 del yt
+                if saved is not None:
+                    saved.append(("transition", "features." + name, mod, X, S, Hc, Wc, C, Cn))
                 X, Hc, Wc, C = Xn, Hn, Wn, Cn
                 src, src_ld = X, Cfin
             else:                                           # norm5 -> F.relu -> adaptive_avg_pool2d(1) -> flatten
@@ -158,9 +182,6 @@ class DenseNetRunner:
                      ss.data_ptr() + ss.stride(0) * 4, 1, st)
                 feat = torch.empty((N, C), device=dev, dtype=F32)
                 call("b2_avgpool_nhwc", a.data_ptr(), feat.data_ptr(), 0, N, Hc * Wc, C, st)
-        if train:
-            bns = [m for m in net.modules() if isinstance(m, torch.nn.BatchNorm2d)]
-            torch._foreach_add_([b.num_batches_tracked for b in bns if b.num_batches_tracked is not None], 1)
-        if return_stages:
-            return feat, stages
+                if saved is not None:
+                    saved.append(("norm5", mod, X, S, a, Hc, Wc, C))
         return feat

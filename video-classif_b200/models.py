@@ -364,7 +364,8 @@ class CrimeLRCN(_BackboneLRCN):
 
     def freeze_cnn_layers(self, freeze_until_layer=None, unfreeze_dense_layer=False):
         if unfreeze_dense_layer:
-            for p in self.cnn_backbone.fc.parameters():     # Identity: nothing to unfreeze (lrcn.py:250-253)
+            head = "classifier" if hasattr(self.cnn_backbone, "classifier") else "fc"      # lrcn.py:250-258
+            for p in getattr(self.cnn_backbone, head).parameters():     # Identity: nothing to unfreeze, nothing frozen
                 p.requires_grad = True
         elif freeze_until_layer is None:
             for p in self.cnn_backbone.parameters():
