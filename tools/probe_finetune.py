@@ -10,6 +10,8 @@ steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 arch = sys.argv[3] if len(sys.argv) > 3 else "resnet50"
 first = sys.argv[4] if len(sys.argv) > 4 else "conv1"
 dev = "cuda"
+if arch.startswith("densenet") and first == "conv1":
+    first = "features"
 torch.manual_seed(0)
 net, feat = vc.backbone.make_backbone(arch)
 on = False
@@ -33,6 +35,5 @@ for it in range(steps + WARM):
     (f * g).sum().backward()
 torch.cuda.synchronize()
 dt = (time.time() - t0) / steps
-flop = 2.152e9 * (3 if first == "conv1" else 1)
 print("%s trainable from %s, %d frames @112: fwd+bwd %.2f ms/step -> %.0f frames/s; %d b2 launches/step; mem %.1f GB" %
       (arch, first, frames, dt * 1e3, frames / dt, (vc._lib.launch_count() - n0) // steps, torch.cuda.max_memory_allocated() / 2**30))
