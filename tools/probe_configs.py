@@ -54,3 +54,33 @@ x = torch.rand(32, 16, 3, 224, 224, device=dev); y = torch.randint(0, 50, (32,),
 r, ms = rate(m, x, y, steps=6, graph=True)
 print(f"cfg3 ucf50 ResNet-50 @224 16 frames biLSTM H=56 x4 B=32 bf16: {r:9.0f} clips/s ({ms:.2f} ms/step, "
       f"{130.8 * 32 / ms / 1e0:.0f} GFLOP/ms encoder)")
+del m, x
+torch.cuda.empty_cache()
+# cfg 2, second topology: the crime / rgb scripts' default -- densenet121 fully trainable (FINETUNE = True), one adapt,
+# 4-layer biLSTM H = 56, 3 binary heads (sum of BCE-with-logits), 16 x 112x112, B = 64
+if "--finetune" in sys.argv or True:
+    for arch, B in (("densenet121", 64), ("resnet50", 64)):
+        m = vc.CrimeLRCN(3, 16, 56, 512, cnn_backbone=arch, finetune=True, rnn_layers=4, classif_mode="multiple_binary").to(dev).train()
+        x = torch.rand(B, 16, 3, 112, 112, device=dev)
+        yb = (torch.rand(B, 3, device=dev) > 0.5).float()
+        opt = torch.optim.Adam(m.parameters(), lr=1e-4, fused=True)
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            loss = torch.nn.functional.binary_cross_entropy_with_logits(m(x), yb)
+            loss.backward()
+            opt.step()
+        for _ in range(3):
+            step()
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(5):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        print(f"cfg2b crime LRCN {arch} FULL fine-tune 16x112x112 B={B} biLSTM H=56 x4, 3 binary heads: {B / ms * 1e3:9.0f} clips/s "
+              f"({ms:.2f} ms/step, {torch.cuda.max_memory_allocated() / 2**30:.1f} GB)")
+        del m, x, opt
+        torch.cuda.empty_cache()
