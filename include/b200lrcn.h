@@ -282,6 +282,11 @@ int b2_maxpool_relu_bwd_nhwc(const void* raw, const float* scale, const float* s
  * A dense block is ONE channel-concatenated NHWC buffer (row stride = final channel count); these kernels work on
  * row-strided bf16 tensors.  b2_scale_shift_apply_ld_bf16: y[r,:C] = act(x[r,:C]*scale+shift) (scale = NULL: slice copy);
  * b2_colstats_ld_bf16: per-channel sum / sumsq, ACCUMULATED; b2_avgpool2x2_nhwc_bf16: AvgPool2d(2,2) into a strided dst. */
+/* D[M,N] bf16 = relu?(A[M,K]*a_scale[k]+a_shift[k]) B[N,K]^T (+ column statistics): the pre-activation BatchNorm + ReLU of a
+ * dense layer / transition folded into the 1x1 conv's A-tile transform; A row-strided (lda); a_scale / a_shift readable up
+ * to the next multiple of 64 channels (zero padded); N % 32 == 0, N >= 64. */
+int b2_gemm_bn_bf16_tn(const void* A, long lda, const void* B, long ldb, void* D, long ldd, int M, int N, int K,
+                       const float* a_scale, const float* a_shift, int a_relu, float* col_sum, float* col_sumsq, void* stream);
 int b2_scale_shift_apply_ld_bf16(const void* x, long ldx, void* y, long ldy, long rows, int C, const float* scale,
                                  const float* shift, int relu, void* stream);
 int b2_colstats_ld_bf16(const void* x, long ld, long rows, int C, float* sum, float* sumsq, void* stream);

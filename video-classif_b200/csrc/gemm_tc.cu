@@ -1522,6 +1522,28 @@ B2_API int b2_gemm_bf16_tn(const void* A, long lda, const void* B, long ldb, voi
                   (cudaStream_t)stream);
 }
 
+// D[M,N] (bf16) = relu?(A[M,K] * a_scale[k] + a_shift[k]) B[N,K]^T with the pre-activation BatchNorm of a DenseNet layer
+// applied to the A tile in shared memory (A row-strided: a channel slice of a concatenated block buffer) ; see the header
+B2_API int b2_gemm_bn_bf16_tn(const void* A, long lda, const void* B, long ldb, void* D, long ldd, int M, int N, int K,
+                              const float* a_scale, const float* a_shift, int a_relu, float* col_sum, float* col_sumsq,
+                              void* stream) {
+  const char* who = "b2_gemm_bn_bf16_tn";
+  B2_ARG_CHECK(A && B && D && a_scale && a_shift && M > 0 && N > 0 && K > 0, "%s: null pointer or empty shape", who);
+  B2_ARG_CHECK((lda % 8) == 0 && (ldb % 8) == 0 && (ldd % 8) == 0, "%s: row strides must be multiples of 8 elements", who);
+  B2_ARG_CHECK(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)D & 15) == 0, "%s: 16 B alignment", who);
+  B2_ARG_CHECK(N % 32 == 0 && N >= 64, "%s: N must be a multiple of 32, at least 64 (got %d)", who, N);
+  B2_ARG_CHECK((col_sum == nullptr) == (col_sumsq == nullptr), "%s: col_sum and col_sumsq go together", who);
+  if (int r = load_driver_entry_points()) return r;
+  const int bn = pick_bn(N);
+  CUtensorMap ta, tb;
+  if (int r = make_tmap_2d(&ta, A, M, K, lda, BM)) return r;
+  if (int r = make_tmap_2d(&tb, B, N, K, ldb, bn)) return r;
+  ConvGeom g = {};
+  ATransform at = {a_scale, a_shift, a_relu};      // scale / shift must be readable up to the next multiple of 64 channels
+  return dispatch(bn, ta, tb, M, N, K, g, at, plain_epi(D, ldd, nullptr, nullptr, 1, 0, col_sum, col_sumsq),
+                  (cudaStream_t)stream);
+}
+
 // y[N,P,Q,Cout] = conv(x[N,H,W,C], w[Cout,R,S,C]) ; NHWC bf16, C % 64 == 0 ; see include/b200lrcn.h
 B2_API int b2_conv2d_nhwc_bf16(const void* x, int Nimg, int H, int W, int C, const void* w, int Cout, int R, int S,
                                int stride, int pad, void* y, const float* bias, int out_bf16, int relu,

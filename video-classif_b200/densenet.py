@@ -10,6 +10,8 @@ the statistics of its output in the epilogue -> BN2+ReLU in place -> 3x3 im2col-
 -> slice copy into the block buffer."""
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
@@ -32,6 +34,7 @@ class DenseNetRunner:
         self._params = None
         self._graphs = {}
         self.use_graph = False
+        self.fold_bn1 = os.environ.get("B2_DENSE_FOLD", "1") == "1"   # BN1+ReLU in the 1x1 GEMM's A transform (tests run both)
         self.fuse_bn = None          # (ResNet-only switches; part of the CUDA-graph cache key of the shared graphed())
         self.stem_impl = None
 
@@ -136,10 +139,20 @@ class DenseNetRunner:
                 for k, (lname, layer) in enumerate(mod.named_children()):
                     Ct = C + k * growth
                     self._finalize(layer.norm1, S.data_ptr(), S.data_ptr() + 4 * Cfin, M, train, ss, Ct)
-                    a1 = torch.empty((M, Ct), device=dev, dtype=BF16)
-                    call("b2_scale_shift_apply_ld_bf16", X.data_ptr(), Cfin, a1.data_ptr(), Ct, M, Ct, ss.data_ptr(),
-                         ss.data_ptr() + ss.stride(0) * 4, 1, st)
-                    y1 = gemm_tn(a1, w[pfx + lname + ".conv1"], out_dtype=BF16, stats=(smid[k, 0], smid[k, 1]) if train else None)
+                    w1 = w[pfx + lname + ".conv1"]
+                    if self.fold_bn1:
+                        # BN1 + ReLU of the concatenated input folded into the GEMM's A-tile transform: X is read once,
+                        # the normalised copy is never written
+                        y1 = torch.empty((M, mid), device=dev, dtype=BF16)
+                        call("b2_gemm_bn_bf16_tn", X.data_ptr(), Cfin, w1.data_ptr(), w1.stride(0), y1.data_ptr(), mid, M, mid, Ct,
+                             ss.data_ptr(), ss.data_ptr() + ss.stride(0) * 4, 1, smid[k, 0].data_ptr() if train else 0,
+                             smid[k, 1].data_ptr() if train else 0, st)
+                    else:
+                        a1 = torch.empty((M, Ct), device=dev, dtype=BF16)
+                        call("b2_scale_shift_apply_ld_bf16", X.data_ptr(), Cfin, a1.data_ptr(), Ct, M, Ct, ss.data_ptr(),
+                             ss.data_ptr() + ss.stride(0) * 4, 1, st)
+                        y1 = gemm_tn(a1, w1, out_dtype=BF16, stats=(smid[k, 0], smid[k, 1]) if train else None)
+                        del a1
                     self._finalize(layer.norm2, smid[k, 0].data_ptr(), smid[k, 1].data_ptr(), M, train, ssmid, mid)
                     a2 = torch.empty_like(y1) if saved is not None else y1
                     scale_shift_apply(y1, ssmid[0], ssmid[1], relu=True, out=a2)
@@ -148,7 +161,7 @@ class DenseNetRunner:
                     call("b2_scale_shift_apply_ld_bf16", y2.data_ptr(), growth, X.data_ptr() + 2 * Ct, Cfin, M, growth, 0, 0, 0, st)
                     if saved is not None:
                         rec.append((pfx + lname, layer, y1, a2, smid[k]))
-                    del a1, y1, y2, a2
+                    del y1, y2, a2
                 if saved is not None:
                     saved.append(("block", X, S, C, growth, rec))
                 C = Cfin
