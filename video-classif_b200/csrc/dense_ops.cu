@@ -204,6 +204,8 @@ bn_bwd_reduce_ld_kernel(const bf16* __restrict__ dz, long lddz, const bf16* __re
   }
 }
 
+// dx = A[c] dz + B[c] x + K[c] (train; see bn_bwd_apply_kernel in conv_bwd.cu) or A[c] dz (eval).  The launch makes the grid
+// stride a multiple of the channel-group count, so a thread's 8 channels -- and its three coefficient vectors -- are fixed.
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_ld_kernel(const bf16* __restrict__ dz, long lddz, const bf16* __restrict__ z, long ldz,
                        const bf16* __restrict__ x, long ldx, bf16* __restrict__ dx, long lddx, int accumulate,
@@ -212,8 +214,19 @@ bn_bwd_apply_ld_kernel(const bf16* __restrict__ dz, long lddz, const bf16* __res
                        const float* __restrict__ s2, long M, int C, float inv_count, float eps, int train) {
   const int groups = C >> 3;
   const long total = M * groups;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int grp = (int)(i % groups);
+  const long i0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int grp = (int)(i0 % groups);
+  float ca[8], cb[8], ck[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = grp * 8 + j;
+    float mean, invstd;
+    mean_invstd(sum, sumsq, rmean, rvar, c, inv_count, eps, train, mean, invstd);
+    ca[j] = gamma[c] * invstd;
+    cb[j] = train ? -ca[j] * invstd * s2[c] * inv_count : 0.f;
+    ck[j] = train ? -ca[j] * s1[c] * inv_count - cb[j] * mean : 0.f;
+  }
+  for (long i = i0; i < total; i += (long)gridDim.x * blockDim.x) {
     const long r = i / groups;
     float gf[8], xf[8], o[8];
     unpack8(*reinterpret_cast<const uint4*>(dz + r * lddz + grp * 8), gf);
@@ -224,16 +237,8 @@ bn_bwd_apply_ld_kernel(const bf16* __restrict__ dz, long lddz, const bf16* __res
 #pragma unroll
       for (int j = 0; j < 8; ++j) gf[j] = zf[j] > 0.f ? gf[j] : 0.f;
     }
-    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + grp * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + grp * 8 + 4));
-    const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = grp * 8 + j;
-      float mean, invstd;
-      mean_invstd(sum, sumsq, rmean, rvar, c, inv_count, eps, train, mean, invstd);
-      const float a = gm[j] * invstd;
-      o[j] = train ? a * (gf[j] - s1[c] * inv_count - (xf[j] - mean) * invstd * s2[c] * inv_count) : a * gf[j];
-    }
+    for (int j = 0; j < 8; ++j) o[j] = fmaf(ca[j], gf[j], fmaf(cb[j], xf[j], ck[j]));
     bf16* dst = dx + r * lddx + grp * 8;
     if (accumulate) {
       float prev[8];
@@ -337,7 +342,9 @@ B2_API int b2_bn_bwd_ld_bf16(const void* dz, long lddz, const void* z, long ldz,
                                                                           (const bf16*)x, ldx, sum, sumsq, running_mean,
                                                                           running_var, s1, s2, M, C, (int)rpb, inv, eps, train);
   B2_LAUNCH_CHECK("bn_bwd_reduce_ld_kernel");
-  bn_bwd_apply_ld_kernel<<<ew_blocks(M * groups), 256, 0, st>>>((const bf16*)dz, lddz, (const bf16*)z, ldz, (const bf16*)x,
+  unsigned ab = ew_blocks(M * groups);       // grid stride (ab * 256) must be a multiple of the channel-group count
+  if (256 % groups != 0) ab = ab / groups * groups > 0 ? ab / groups * groups : (unsigned)groups;
+  bn_bwd_apply_ld_kernel<<<ab, 256, 0, st>>>((const bf16*)dz, lddz, (const bf16*)z, ldz, (const bf16*)x,
                                                                ldx, (bf16*)dx, lddx, accumulate, gamma, sum, sumsq,
                                                                running_mean, running_var, s1, s2, M, C, inv, eps, train);
   B2_LAUNCH_CHECK("bn_bwd_apply_ld_kernel");
