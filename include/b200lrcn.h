@@ -299,6 +299,15 @@ int b2_bn_bwd_ld_bf16(const void* dz, long lddz, const void* z, long ldz, const 
                       void* stream);
 int b2_avgpool2x2_bwd_nhwc_bf16(const void* dy, long lddy, void* dx, int N, int H, int W, int C, void* stream);
 
+/* ---- MobileNetV2 frame encoder kernels (csrc/mobilenet_ops.cu; mobilenet_v2 under medsos models.py:133-143, in the search
+ * space of medsos_lrcn/src/automation.py:28).  b2_mbv2_stem_conv: Conv2d(3,32,3,s2,p1) NCHW frames -> NHWC bf16 (+ statistics);
+ * b2_dwconv3x3_bn_nhwc_bf16: depthwise 3x3 with the previous BatchNorm + activation (act 0 none / 1 ReLU / 2 ReLU6) applied on
+ * load, raw output + statistics.  (b2_scale_shift_apply_ld_bf16's `relu` argument takes the same 0 / 1 / 2.) */
+int b2_mbv2_stem_conv(const void* x, int in_bf16, const float* w, void* y, float* sum, float* sumsq, int N, int H, int W,
+                      void* stream);
+int b2_dwconv3x3_bn_nhwc_bf16(const void* x, const float* scale, const float* shift, int act, const float* w, void* y,
+                              float* sum, float* sumsq, int N, int H, int W, int C, int stride, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -416,11 +416,62 @@ def densenet_features(sd: Dict[str, torch.Tensor], x: torch.Tensor, arch: str, t
     return feat, ns
 
 
+_MBV2_CFG = [(1, 16, 1, 1), (6, 24, 2, 2), (6, 32, 3, 2), (6, 64, 4, 2), (6, 96, 3, 1), (6, 160, 3, 2), (6, 320, 1, 1)]
+
+
+def mobilenetv2_features(sd: Dict[str, torch.Tensor], x: torch.Tensor, arch: str = "mobilenet_v2", train: bool = True,
+                         prefix: str = "cnn_backbone.", emulate_bf16: bool = False, return_stages: bool = False):
+    """torchvision.models.mobilenet_v2 with classifier=Identity (medsos models.py:133-143): Conv 3x3/2 -> BN -> ReLU6; 17
+    inverted residual blocks [1x1 expand (t > 1) -> BN -> ReLU6 -> depthwise 3x3 (stride s) -> BN -> ReLU6 -> 1x1 project ->
+    BN (+ input when stride 1 and equal widths)]; Conv 1x1 -> 1280 -> BN -> ReLU6; global average pool."""
+    sdp = {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+    ns: Dict[str, torch.Tensor] = {}
+    rnd = _bf16 if emulate_bf16 else (lambda t: t)
+    relu6 = lambda t: torch.clamp(t, 0.0, 6.0)
+
+    def conv(inp, w, **kw):
+        return rnd(F.conv2d(rnd(inp), rnd(w), None, **kw))
+
+    y = conv(x, sdp["features.0.0.weight"], stride=2, padding=1)
+    y = rnd(relu6(_bn(y, sdp, "features.0.1", train, ns)))
+    stages = []
+    idx, cin = 1, 32
+    for t, c, n, s in _MBV2_CFG:
+        for i in range(n):
+            stride = s if i == 0 else 1
+            p = f"features.{idx}.conv"
+            o, j = y, 0
+            if t != 1:
+                o = conv(o, sdp[f"{p}.0.0.weight"])
+                o = rnd(relu6(_bn(o, sdp, f"{p}.0.1", train, ns)))
+                j = 1
+            wd = sdp[f"{p}.{j}.0.weight"]
+            o = conv(o, wd, stride=stride, padding=1, groups=wd.shape[0])
+            o = rnd(relu6(_bn(o, sdp, f"{p}.{j}.1", train, ns)))
+            o = conv(o, sdp[f"{p}.{j + 1}.weight"])
+            o = _bn(o, sdp, f"{p}.{j + 2}", train, ns)
+            if stride == 1 and cin == c:
+                o = o + y
+            y = rnd(o)
+            stages.append(y.mean(dim=(2, 3)))
+            cin = c
+            idx += 1
+    y = conv(y, sdp["features.18.0.weight"])
+    y = rnd(relu6(_bn(y, sdp, "features.18.1", train, ns)))
+    feat = y.mean(dim=(2, 3))
+    ns = {prefix + k: v for k, v in ns.items()}
+    if return_stages:
+        return feat, ns, stages
+    return feat, ns
+
+
 def medsos_lrcn_forward(sd, x, arch, hidden, rnn_layers, bidirectional, rnn_out="all",
                         train=True, emulate_bf16_backbone=False):
     """medsos_lrcn/src/models.py:188-234 with rnn_type='lstm', multiclass head, dropout p=0."""
     B, T, C, H, W = x.shape
-    feat, ns = resnet_features(sd, x.reshape(B * T, C, H, W), arch, train, emulate_bf16=emulate_bf16_backbone)
+    backbone = (mobilenetv2_features if arch.startswith("mobilenet") else
+                densenet_features if arch.startswith("densenet") else resnet_features)
+    feat, ns = backbone(sd, x.reshape(B * T, C, H, W), arch, train, emulate_bf16=emulate_bf16_backbone)
     y = feat.reshape(B, T, -1)
     for k in (1, 2, 3):
         y = y @ sd[f"adapt{k}.weight"].t() + sd[f"adapt{k}.bias"]

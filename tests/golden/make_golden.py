@@ -239,6 +239,42 @@ def gold_crime_densenet():
     save("crime_lrcn_densenet121.npz", **arrs)
 
 
+def gold_medsos_mobilenet():
+    # medsos models.py with mobilenet_v2 (the second backbone of its search space, automation.py:28), frozen, train-mode BN
+    mm = refload.medsos_models(CONF_RNN_LAYER=2, CONF_RNN_OUT="all", CONF_CLASSIF_MODE="multiclass", CONF_DROPOUT=0.0)
+    torch.manual_seed(19)
+    m = mm.LRCN(4, 3, 16, 8, cnn_backbone="mobilenet_v2", rnn_type="lstm", rnn_out="all", bidirectional=False)
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randint(0, 256, (2, 3, 3, 64, 64), generator=g).float() / 255.0
+    y = torch.randint(0, 4, (2,), generator=g)
+    sd0, out, loss, grads, sd1 = run_step(m, x, y)
+    arrs = {"x": x.numpy(), "y": y.numpy(), "logits": out.numpy(), "loss": loss.numpy(),
+            "backbone_checksum": np.array(checksum(sd0, "cnn_backbone.")),
+            "meta": np.array(json.dumps(dict(arch="mobilenet_v2", size=64, B=2, T=3, hidden=16, rnn_input=8, rnn_layers=2,
+                                             num_classes=4, seed=19, source="medsos_lrcn/src/models.py:121-234, dropout 0")))}
+    big = lambda v: v.size > 100000               # seed-reproducible (checksum above): keep the fixture small
+    for k, v in npd(sd0).items():
+        if not k.startswith("cnn_backbone.") and not big(v):
+            arrs["sd0/" + k] = v
+    for k, v in npd(grads).items():
+        if big(v):
+            arrs["gradsub16/" + k] = v[::16, ::16].copy()
+        else:
+            arrs["grad/" + k] = v
+    for k in ("cnn_backbone.features.0.1.running_mean", "cnn_backbone.features.3.conv.1.1.running_var",
+              "cnn_backbone.features.14.conv.3.running_mean", "cnn_backbone.features.18.1.running_var"):
+        arrs["sd1/" + k] = sd1[k].numpy()
+    with torch.no_grad():
+        m2 = mm.LRCN(4, 3, 16, 8, cnn_backbone="mobilenet_v2", rnn_type="lstm", rnn_out="all", bidirectional=False)
+        m2.load_state_dict(sd0)
+        m2.train()
+        arrs["features"] = m2.cnn_backbone(x.view(6, 3, 64, 64)).numpy()
+        m2.load_state_dict(sd0)
+        m2.eval()
+        arrs["features_eval"] = m2.cnn_backbone(x.view(6, 3, 64, 64)).numpy()
+    save("medsos_lrcn_mobilenet_v2.npz", **arrs)
+
+
 def gold_lstm():
     # nn.LSTM exactly as the reference configures it (lrcn.py:236: 4-layer biLSTM H=56 -> here 2x2, H=7)
     torch.manual_seed(5)
@@ -385,3 +421,4 @@ if __name__ == "__main__":
     gold_mamba()
     gold_ckpt()
     gold_crime_densenet()
+    gold_medsos_mobilenet()

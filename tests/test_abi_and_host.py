@@ -97,7 +97,7 @@ def test_state_dict_layout_matches_reference_checkpoints():
     assert ck["lstm.weight_ih_l0_reverse"].shape == (224, 512) and ck["lstm.weight_ih_l3"].shape == (224, 112)
     assert ck["fc.2.weight"].shape == (1, 2 * 56 * 4) and "adapt.weight" in ck
     with pytest.raises(NotImplementedError):
-        vc.LRCN(4, 3, 32, 8, cnn_backbone="mobilenet_v2")
+        vc.LRCN(4, 3, 32, 8, cnn_backbone="efficientnet_b1")
     mam = vc.LRCN(4, 3, 32, 8, cnn_backbone="resnet18", rnn_type="mamba", rnn_layers=2).state_dict()   # models.py:159-164
     assert mam["rnn.1.mixer.A_log"].shape == (16, 32) and mam["rnn.0.mixer.in_proj.weight"].shape == (32, 8)
     assert mam["rnn.0.mixer.conv1d.weight"].shape == (16, 1, 3) and mam["rnn.0.mixer.x_proj.weight"].shape == (96, 16)

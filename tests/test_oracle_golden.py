@@ -120,6 +120,23 @@ def test_simple_and_crime_oracle_vs_golden():
     assert err(logits, torch.from_numpy(g["logits"])) < 1e-4
 
 
+def test_mobilenet_oracle_vs_golden():
+    """MobileNetV2 restated by the oracle vs the reference medsos LRCN built on it (models.py:133-143): pooled features in
+    train- and eval-mode BN, running statistics, logits."""
+    m, g, meta = build_backbone_model("medsos_lrcn_mobilenet_v2.npz")
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    x = torch.from_numpy(g["x"])
+    frames = x.reshape(-1, *x.shape[2:])
+    feat, ns = O.mobilenetv2_features(sd, frames, train=True)
+    assert err(feat, torch.from_numpy(g["features"])) < 1e-4
+    for k, v in golden_tensors(g, "sd1/").items():
+        assert err(ns[k], v) < 1e-4, k
+    feat_e, _ = O.mobilenetv2_features(sd, frames, train=False)
+    assert err(feat_e, torch.from_numpy(g["features_eval"])) < 1e-4
+    logits, _ = O.medsos_lrcn_forward(sd, x, "mobilenet_v2", meta["hidden"], meta["rnn_layers"], False)
+    assert err(logits, torch.from_numpy(g["logits"])) < 1e-4
+
+
 def test_densenet_oracle_vs_golden():
     """DenseNet-121 restated by the oracle vs the reference crime LRCN's own default backbone (lrcn.py:196-209): pooled
     features in train- and eval-mode BN, running statistics after the step, logits through the crime tail."""

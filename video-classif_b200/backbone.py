@@ -33,6 +33,12 @@ def make_backbone(name: str, pretrained: bool = False):
     Returns (module, feature_size)."""
     import torchvision.models as tvm
     from .densenet import SUPPORTED as DENSE
+    from .mobilenet import SUPPORTED as MOBILE
+    if name in MOBILE:
+        net = getattr(tvm, name)(weights="DEFAULT" if pretrained else None)
+        feat = net.classifier[-1].in_features                  # models.py:138-140: Sequential classifier
+        net.classifier = torch.nn.Identity()
+        return net, feat
     if name in DENSE:
         net = getattr(tvm, name)(weights="DEFAULT" if pretrained else None)
         feat = net.classifier.in_features
@@ -40,8 +46,8 @@ def make_backbone(name: str, pretrained: bool = False):
         return net, feat
     if name not in SUPPORTED:
         raise NotImplementedError(
-            f"cnn_backbone={name!r}: the B200 kernels run the ResNet-class backbones {SUPPORTED} and {DENSE} "
-            "(MobileNet and the other torchvision families are listed under 'next' in DESIGN.md)")
+            f"cnn_backbone={name!r}: the B200 kernels run the torchvision backbones {SUPPORTED}, {DENSE} and {MOBILE} "
+            "(other torchvision families are listed under 'next' in DESIGN.md)")
     net = getattr(tvm, name)(weights="DEFAULT" if pretrained else None)
     feat = net.fc.in_features
     net.fc = torch.nn.Identity()
@@ -50,6 +56,9 @@ def make_backbone(name: str, pretrained: bool = False):
 
 def make_runner(net):
     """The kernel-side executor of a backbone module built by make_backbone()."""
+    if type(net).__name__ == "MobileNetV2":
+        from .mobilenet import MobileNetRunner
+        return MobileNetRunner(net)
     if hasattr(net, "features"):
         from .densenet import DenseNetRunner
         return DenseNetRunner(net)

@@ -48,8 +48,10 @@ scale_shift_apply_ld_kernel(const bf16* __restrict__ x, long ldx, bf16* __restri
       const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float o = fmaf(a[j], sc[j], sh[j]);
-        a[j] = relu ? fmaxf(o, 0.f) : o;
+        float o = fmaf(a[j], sc[j], sh[j]);
+        if (relu >= 1) o = fmaxf(o, 0.f);
+        if (relu == 2) o = fminf(o, 6.f);       // ReLU6 (MobileNetV2)
+        a[j] = o;
       }
       u = pack8(a);
     }

@@ -1,0 +1,224 @@
+// MobileNetV2 frame encoder kernels (torchvision mobilenet_v2 under medsos_lrcn/src/models.py:133-143; it is in the
+// reference's own backbone search space, medsos_lrcn/src/automation.py:28).  Every layer of this network is memory bound
+// (depthwise 3x3 convs and thin 1x1 convs), so the kernels minimise passes over the activations:
+//   * stem3x3s2_kernel   Conv2d(3, 32, 3, stride 2, pad 1) straight from the NCHW fp32 / bf16 frames to NHWC bf16, with
+//                        the per-channel batch statistics of its output
+//   * dwconv3x3_kernel   depthwise 3x3 (stride 1 / 2, pad 1) over NHWC bf16 with the PREVIOUS BatchNorm + ReLU6 applied to
+//                        the input on load (padding stays zero), raw bf16 output + its batch statistics
+// The 1x1 convs run on the tcgen05 GEMM (gemm_tc.cu) with the statistics in their epilogue.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xffff0000u);
+  f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xffff0000u);
+  f[4] = __uint_as_float(u.z << 16); f[5] = __uint_as_float(u.z & 0xffff0000u);
+  f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xffff0000u);
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ uint4 pack8(const float (&o)[8]) {
+  uint4 r;
+  r.x = pack2(o[0], o[1]); r.y = pack2(o[2], o[3]); r.z = pack2(o[4], o[5]); r.w = pack2(o[6], o[7]);
+  return r;
+}
+__device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16(v)); }
+
+// block-level combine of per-thread (8 channel) partial sums: threads with the same channel group are summed, then one
+// atomic per channel.  red: [2][256 * 8] floats of shared memory.
+__device__ __forceinline__ void flush_stats(float (&s1)[8], float (&s2)[8], int grp, int groups, bool active, float* red,
+                                            float* __restrict__ sum, float* __restrict__ sumsq) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red[threadIdx.x * 8 + j] = active ? s1[j] : 0.f;
+    red[256 * 8 + threadIdx.x * 8 + j] = active ? s2[j] : 0.f;
+  }
+  __syncthreads();
+  const int C = groups * 8;
+  const int base = (int)(((long)blockIdx.x * 256) % groups);       // thread t owns channel group (base + t) % groups
+  for (int i = threadIdx.x; i < C; i += 256) {
+    const int gq = i >> 3, j = i & 7;
+    float a = 0.f, b = 0.f;
+    for (int t = (gq - base + groups) % groups; t < 256; t += groups) {
+      a += red[t * 8 + j];
+      b += red[256 * 8 + t * 8 + j];
+    }
+    atomicAdd(sum + i, a);
+    atomicAdd(sumsq + i, b);
+  }
+}
+
+// thread = (output pixel, 8 of the 32 output channels); grid stride is a multiple of 4 so the channel group is fixed
+template <typename T>
+__global__ void __launch_bounds__(256)
+stem3x3s2_kernel(const T* __restrict__ x, const float* __restrict__ w, bf16* __restrict__ y, float* __restrict__ sum,
+                 float* __restrict__ sumsq, int N, int H, int W, int P, int Q) {
+  __shared__ float ws[27 * 32];          // [c*9 + r*3 + s][cout], bf16-rounded operands
+  __shared__ float red[2 * 256 * 8];
+  for (int i = threadIdx.x; i < 27 * 32; i += 256) {
+    const int k = i >> 5, co = i & 31;
+    ws[i] = bf16_round(w[co * 27 + k]);
+  }
+  __syncthreads();
+  const long total = (long)N * P * Q * 4;
+  const long i0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int grp = (int)(i0 & 3);
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+  for (long i = i0; i < total; i += (long)gridDim.x * blockDim.x) {
+    long px = i >> 2;
+    const int q = (int)(px % Q);
+    px /= Q;
+    const int p = (int)(px % P);
+    const long n = px / P;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int h = 2 * p - 1 + r;
+        if (h < 0 || h >= H) continue;
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          const int wq = 2 * q - 1 + s;
+          if (wq < 0 || wq >= W) continue;
+          const float v = bf16_round((float)x[((n * 3 + c) * H + h) * W + wq]);
+          const float* wk = ws + (c * 9 + r * 3 + s) * 32 + grp * 8;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wk[j], acc[j]);
+        }
+      }
+    const uint4 o = pack8(acc);
+    *reinterpret_cast<uint4*>(y + (i >> 2) * 32 + grp * 8) = o;
+    if (sum != nullptr) {
+      float r8[8];
+      unpack8(o, r8);                    // statistics of the value as stored
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s1[j] += r8[j];
+        s2[j] = fmaf(r8[j], r8[j], s2[j]);
+      }
+    }
+  }
+  if (sum != nullptr) flush_stats(s1, s2, grp, 4, true, red, sum, sumsq);
+}
+
+// thread = (output pixel, 8 channels), channel group fixed per thread (the launch makes the grid stride a multiple of the
+// group count); act: 0 none, 1 ReLU, 2 ReLU6 applied to x * scale + shift on load (scale = NULL: x is used as it is)
+__global__ void __launch_bounds__(256)
+dwconv3x3_kernel(const bf16* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift, int act,
+                 const float* __restrict__ w, bf16* __restrict__ y, float* __restrict__ sum, float* __restrict__ sumsq, int N,
+                 int H, int W, int C, int P, int Q, int stride) {
+  __shared__ float red[2 * 256 * 8];
+  const int groups = C >> 3;
+  const long total = (long)N * P * Q * groups;
+  const long i0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int grp = (int)(i0 % groups);
+  float wk[9][8], sc[8], sh[8], s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = grp * 8 + j;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wk[t][j] = bf16_round(w[c * 9 + t]);
+    sc[j] = scale != nullptr ? scale[c] : 1.f;
+    sh[j] = scale != nullptr ? shift[c] : 0.f;
+    s1[j] = s2[j] = 0.f;
+  }
+  for (long i = i0; i < total; i += (long)gridDim.x * blockDim.x) {
+    long px = i / groups;
+    const long orow = px;
+    const int q = (int)(px % Q);
+    px /= Q;
+    const int p = (int)(px % P);
+    const long n = px / P;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int h = p * stride - 1 + r;
+      if (h < 0 || h >= H) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int wq = q * stride - 1 + s;
+        if (wq < 0 || wq >= W) continue;
+        float a[8];
+        unpack8(*reinterpret_cast<const uint4*>(x + ((n * H + h) * W + wq) * C + grp * 8), a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float v = a[j];
+          if (scale != nullptr) {
+            v = fmaf(v, sc[j], sh[j]);
+            if (act >= 1) v = fmaxf(v, 0.f);
+            if (act == 2) v = fminf(v, 6.f);
+            v = bf16_round(v);           // the activation is a bf16 tensor in the unfused formulation
+          }
+          acc[j] = fmaf(v, wk[r * 3 + s][j], acc[j]);
+        }
+      }
+    }
+    const uint4 o = pack8(acc);
+    *reinterpret_cast<uint4*>(y + orow * C + grp * 8) = o;
+    if (sum != nullptr) {
+      float r8[8];
+      unpack8(o, r8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s1[j] += r8[j];
+        s2[j] = fmaf(r8[j], r8[j], s2[j]);
+      }
+    }
+  }
+  if (sum != nullptr) flush_stats(s1, s2, grp, groups, true, red, sum, sumsq);
+}
+
+unsigned blocks_for(long items, int groups) {
+  long b = (items + 255) / 256;
+  const long cap = (long)b2_num_sms() * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  if (256 % groups != 0) b = b / groups * groups > 0 ? b / groups * groups : groups;   // grid stride % groups == 0
+  return (unsigned)b;
+}
+
+}  // namespace
+
+// y [N,P,Q,32] bf16 = Conv2d(3, 32, 3, stride 2, pad 1)(x [N,3,H,W] fp32 or bf16); w [32,3,3,3] fp32 (torch layout);
+// sum / sumsq [32] ACCUMULATED when given
+B2_API int b2_mbv2_stem_conv(const void* x, int in_bf16, const float* w, void* y, float* sum, float* sumsq, int N, int H, int W,
+                             void* stream) {
+  B2_ARG_CHECK(x && w && y && N > 0 && H > 0 && W > 0, "b2_mbv2_stem_conv: null pointer or empty");
+  B2_ARG_CHECK((sum == nullptr) == (sumsq == nullptr), "b2_mbv2_stem_conv: sum and sumsq go together");
+  const int P = (H + 2 - 3) / 2 + 1, Q = (W + 2 - 3) / 2 + 1;
+  const unsigned blocks = blocks_for((long)N * P * Q * 4, 4);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (in_bf16)
+    stem3x3s2_kernel<bf16><<<blocks, 256, 0, st>>>((const bf16*)x, w, (bf16*)y, sum, sumsq, N, H, W, P, Q);
+  else
+    stem3x3s2_kernel<float><<<blocks, 256, 0, st>>>((const float*)x, w, (bf16*)y, sum, sumsq, N, H, W, P, Q);
+  B2_LAUNCH_CHECK("stem3x3s2_kernel");
+  return 0;
+}
+
+// y [N,P,Q,C] bf16 = depthwise 3x3 (stride 1 or 2, pad 1) of act(x * scale + shift); w [C,1,3,3] fp32; statistics ACCUMULATED
+B2_API int b2_dwconv3x3_bn_nhwc_bf16(const void* x, const float* scale, const float* shift, int act, const float* w, void* y,
+                                     float* sum, float* sumsq, int N, int H, int W, int C, int stride, void* stream) {
+  B2_ARG_CHECK(x && w && y && N > 0 && H > 0 && W > 0, "b2_dwconv3x3_bn_nhwc_bf16: null pointer or empty");
+  B2_ARG_CHECK(C % 8 == 0 && C >= 8 && C <= 2048, "b2_dwconv3x3_bn_nhwc_bf16: C must be a multiple of 8 in [8, 2048]");
+  B2_ARG_CHECK(stride == 1 || stride == 2, "b2_dwconv3x3_bn_nhwc_bf16: stride 1 or 2");
+  B2_ARG_CHECK((scale == nullptr) == (shift == nullptr) && (sum == nullptr) == (sumsq == nullptr),
+               "b2_dwconv3x3_bn_nhwc_bf16: scale/shift and sum/sumsq go in pairs");
+  const int P = (H + 2 - 3) / stride + 1, Q = (W + 2 - 3) / stride + 1;
+  const int groups = C / 8;
+  dwconv3x3_kernel<<<blocks_for((long)N * P * Q * groups, groups), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)x, scale, shift, act, w, (bf16*)y, sum, sumsq, N, H, W, C, P, Q, stride);
+  B2_LAUNCH_CHECK("dwconv3x3_kernel");
+  return 0;
+}
