@@ -110,15 +110,23 @@ stem3x3s2_kernel(const T* __restrict__ x, const float* __restrict__ w, bf16* __r
   if (sum != nullptr) flush_stats(s1, s2, grp, 4, true, red, sum, sumsq);
 }
 
-// thread = (output pixel, 8 channels), channel group fixed per thread (the launch makes the grid stride a multiple of the
-// group count); act: 0 none, 1 ReLU, 2 ReLU6 applied to x * scale + shift on load (scale = NULL: x is used as it is)
-__global__ void __launch_bounds__(256)
+// thread = (strip of TW consecutive output pixels of one row, 8 channels); the channel group is fixed per thread (the launch
+// makes the grid stride a multiple of the group count), so the 9 x 8 filter taps and the BatchNorm coefficients live in
+// registers.  A strip shares its input window: 3 rows x ((TW-1) * STRIDE + 3) pixels are loaded (all loads of a row issued
+// before any use), normalised + activated ONCE each and scattered into the <= 3 outputs they feed -- 4.5 (stride 1) / 7.5
+// (stride 2) loads and activations per output instead of 9.  act: 0 none, 1 ReLU, 2 ReLU6 on x * scale + shift (scale =
+// NULL: x as it is); padding contributes exact zeros.
+template <int STRIDE>
+__global__ void __launch_bounds__(256, 2)
 dwconv3x3_kernel(const bf16* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift, int act,
                  const float* __restrict__ w, bf16* __restrict__ y, float* __restrict__ sum, float* __restrict__ sumsq, int N,
-                 int H, int W, int C, int P, int Q, int stride) {
+                 int H, int W, int C, int P, int Q) {
+  constexpr int TW = STRIDE == 1 ? 4 : 2;
+  constexpr int NIN = (TW - 1) * STRIDE + 3;
   __shared__ float red[2 * 256 * 8];
   const int groups = C >> 3;
-  const long total = (long)N * P * Q * groups;
+  const int strips = (Q + TW - 1) / TW;
+  const long total = (long)N * P * strips * groups;
   const long i0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const int grp = (int)(i0 % groups);
   float wk[9][8], sc[8], sh[8], s1[8], s2[8];
@@ -131,48 +139,70 @@ dwconv3x3_kernel(const bf16* __restrict__ x, const float* __restrict__ scale, co
     sh[j] = scale != nullptr ? shift[c] : 0.f;
     s1[j] = s2[j] = 0.f;
   }
+  const bool tf = scale != nullptr;
   for (long i = i0; i < total; i += (long)gridDim.x * blockDim.x) {
     long px = i / groups;
-    const long orow = px;
-    const int q = (int)(px % Q);
-    px /= Q;
+    const int qs = (int)(px % strips);
+    px /= strips;
     const int p = (int)(px % P);
     const long n = px / P;
-    float acc[8];
+    const int q0 = qs * TW;
+    const int w0 = q0 * STRIDE - 1;
+    float acc[TW][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int t = 0; t < TW; ++t)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-      const int h = p * stride - 1 + r;
-      if (h < 0 || h >= H) continue;
+      const int h = p * STRIDE - 1 + r;
+      const bool row_ok = h >= 0 && h < H;
+      const bf16* xrow = x + ((n * H + (row_ok ? h : 0)) * W) * C + grp * 8;
+      uint4 u[NIN];
+      bool ok[NIN];
 #pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const int wq = q * stride - 1 + s;
-        if (wq < 0 || wq >= W) continue;
+      for (int c = 0; c < NIN; ++c) {
+        ok[c] = row_ok && (w0 + c) >= 0 && (w0 + c) < W;
+        u[c] = ok[c] ? *reinterpret_cast<const uint4*>(xrow + (long)(w0 + c) * C) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int c = 0; c < NIN; ++c) {
         float a[8];
-        unpack8(*reinterpret_cast<const uint4*>(x + ((n * H + h) * W + wq) * C + grp * 8), a);
+        unpack8(u[c], a);
+        if (tf) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float v = a[j];
-          if (scale != nullptr) {
-            v = fmaf(v, sc[j], sh[j]);
+          for (int j = 0; j < 8; ++j) {
+            float v = fmaf(a[j], sc[j], sh[j]);
             if (act >= 1) v = fmaxf(v, 0.f);
             if (act == 2) v = fminf(v, 6.f);
-            v = bf16_round(v);           // the activation is a bf16 tensor in the unfused formulation
+            a[j] = ok[c] ? bf16_round(v) : 0.f;     // the activation is a bf16 tensor in the unfused formulation
           }
-          acc[j] = fmaf(v, wk[r * 3 + s][j], acc[j]);
+        }
+#pragma unroll
+        for (int t = 0; t < TW; ++t) {
+          const int s = c - t * STRIDE;             // compile-time after unrolling
+          if (s >= 0 && s < 3) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(a[j], wk[r * 3 + s][j], acc[t][j]);
+          }
         }
       }
     }
-    const uint4 o = pack8(acc);
-    *reinterpret_cast<uint4*>(y + orow * C + grp * 8) = o;
-    if (sum != nullptr) {
-      float r8[8];
-      unpack8(o, r8);
+    bf16* yrow = y + (((n * P + p) * Q) + q0) * C + grp * 8;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        s1[j] += r8[j];
-        s2[j] = fmaf(r8[j], r8[j], s2[j]);
+    for (int t = 0; t < TW; ++t) {
+      if (q0 + t < Q) {
+        const uint4 o = pack8(acc[t]);
+        *reinterpret_cast<uint4*>(yrow + (long)t * C) = o;
+        if (sum != nullptr) {
+          float r8[8];
+          unpack8(o, r8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            s1[j] += r8[j];
+            s2[j] = fmaf(r8[j], r8[j], s2[j]);
+          }
+        }
       }
     }
   }
@@ -217,8 +247,13 @@ B2_API int b2_dwconv3x3_bn_nhwc_bf16(const void* x, const float* scale, const fl
                "b2_dwconv3x3_bn_nhwc_bf16: scale/shift and sum/sumsq go in pairs");
   const int P = (H + 2 - 3) / stride + 1, Q = (W + 2 - 3) / stride + 1;
   const int groups = C / 8;
-  dwconv3x3_kernel<<<blocks_for((long)N * P * Q * groups, groups), 256, 0, (cudaStream_t)stream>>>(
-      (const bf16*)x, scale, shift, act, w, (bf16*)y, sum, sumsq, N, H, W, C, P, Q, stride);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (stride == 1)
+    dwconv3x3_kernel<1><<<blocks_for((long)N * P * ((Q + 3) / 4) * groups, groups), 256, 0, st>>>(
+        (const bf16*)x, scale, shift, act, w, (bf16*)y, sum, sumsq, N, H, W, C, P, Q);
+  else
+    dwconv3x3_kernel<2><<<blocks_for((long)N * P * ((Q + 1) / 2) * groups, groups), 256, 0, st>>>(
+        (const bf16*)x, scale, shift, act, w, (bf16*)y, sum, sumsq, N, H, W, C, P, Q);
   B2_LAUNCH_CHECK("dwconv3x3_kernel");
   return 0;
 }
