@@ -70,7 +70,17 @@ def _count_layers(sd, prefix):
 
 
 def infer_backbone(sd, prefix="cnn_backbone."):
-    """torchvision ResNet name from the block structure of the state_dict keys."""
+    """torchvision backbone name (ResNet / DenseNet / MobileNetV2) from the block structure of the state_dict keys."""
+    if (prefix + "features.denseblock1.denselayer1.conv1.weight") in sd:
+        depth = [len({k.split(".")[len(prefix.split(".")) + 1] for k in sd if k.startswith(f"{prefix}features.denseblock{b}.")})
+                 for b in range(1, 5)]
+        growth = sd[prefix + "features.denseblock1.denselayer1.conv2.weight"].shape[0]
+        table = {(32, (6, 12, 24, 16)): "densenet121", (32, (6, 12, 32, 32)): "densenet169", (32, (6, 12, 48, 32)): "densenet201"}
+        if (growth, tuple(depth)) not in table:
+            raise NotImplementedError(f"unrecognised DenseNet layout growth={growth} blocks={depth}")
+        return table[(growth, tuple(depth))]
+    if (prefix + "features.18.0.weight") in sd and (prefix + "features.1.conv.0.0.weight") in sd:
+        return "mobilenet_v2"
     blocks = []
     for layer in range(1, 5):
         ids = {int(m.group(1)) for k in sd for m in [re.match(re.escape(prefix) + rf"layer{layer}\.(\d+)\.", k)] if m}
