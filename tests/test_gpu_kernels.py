@@ -430,3 +430,162 @@ def test_errors_are_loud(ops):
     with pytest.raises(vc.B200LrcnError):
         ops.conv2d_nhwc(torch.zeros(1, 4, 4, 48, device=DEV, dtype=torch.bfloat16),
                         torch.zeros(64, 3, 3, 48, device=DEV, dtype=torch.bfloat16), 1, 1)   # C % 64 != 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# DenseNet / MobileNetV2 element kernels and the strided BatchNorm backward, one by one against torch
+# ---------------------------------------------------------------------------------------------------------------
+def _rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("C,ld,act", [(96, 256, 1), (64, 64, 2), (200, 512, 0), (32, 40, -1)])
+def test_scale_shift_apply_ld(C, ld, act):
+    """Row-strided BN apply / slice copy (act -1: scale = NULL) between channel slices of concatenated buffers."""
+    from video_classif_b200._lib import call, stream_ptr
+    torch.manual_seed(C)
+    M = 777
+    X = torch.randn(M, ld, device=DEV).to(torch.bfloat16)
+    Y = torch.zeros(M, ld + 8, device=DEV, dtype=torch.bfloat16)
+    sc, sh = torch.randn(C, device=DEV), torch.randn(C, device=DEV)
+    call("b2_scale_shift_apply_ld_bf16", X.data_ptr(), ld, Y.data_ptr() + 16, ld + 8, M, C, sc.data_ptr() if act >= 0 else 0,
+         sh.data_ptr() if act >= 0 else 0, max(act, 0), stream_ptr())
+    ref = X[:, :C].float()
+    if act >= 0:
+        ref = ref * sc + sh
+        ref = ref.clamp(0, 6) if act == 2 else (ref.clamp_min(0) if act == 1 else ref)
+    if act < 0:
+        assert torch.equal(Y[:, 8:8 + C], X[:, :C])                              # slice copy: bit exact
+    else:
+        assert _rel(Y[:, 8:8 + C].float(), ref) < 8e-3                           # fused multiply-add, one bf16 rounding
+    assert Y[:, :8].abs().sum() == 0 and Y[:, 8 + C:].abs().sum() == 0          # nothing outside the slice is touched
+
+
+@pytest.mark.parametrize("C,ld", [(64, 256), (96, 96), (1024, 1024), (24, 32)])
+def test_colstats_ld(C, ld):
+    from video_classif_b200._lib import call, stream_ptr
+    torch.manual_seed(ld)
+    M = 5000
+    X = (torch.randn(M, ld, device=DEV) * 2 + 0.5).to(torch.bfloat16)
+    s = torch.zeros(2, C, device=DEV)
+    call("b2_colstats_ld_bf16", X.data_ptr(), ld, M, C, s[0].data_ptr(), s[1].data_ptr(), stream_ptr())
+    x = X[:, :C].double()
+    assert _rel(s[0], x.sum(0)) < 1e-5 and _rel(s[1], (x * x).sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize("H,W", [(8, 8), (7, 7), (14, 9)])
+def test_avgpool2x2_fwd_bwd(H, W):
+    """AvgPool2d(2, 2) into a row-strided destination and its backward (odd sizes: the last row / column is dropped)."""
+    from video_classif_b200._lib import call, stream_ptr
+    torch.manual_seed(H * W)
+    N, C, ldy = 3, 40, 72
+    x = torch.randn(N, H, W, C, device=DEV).to(torch.bfloat16)
+    P, Q = H // 2, W // 2
+    y = torch.zeros(N * P * Q, ldy, device=DEV, dtype=torch.bfloat16)
+    call("b2_avgpool2x2_nhwc_bf16", x.data_ptr(), y.data_ptr(), ldy, N, H, W, C, stream_ptr())
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    ref = torch.nn.functional.avg_pool2d(xr, 2, 2)
+    assert _rel(y[:, :C].float().view(N, P, Q, C).permute(0, 3, 1, 2), ref) < 1e-2
+    assert y[:, C:].abs().max() == 0
+    g = torch.randn(N * P * Q, ldy, device=DEV).to(torch.bfloat16)
+    dx = torch.empty(N, H, W, C, device=DEV, dtype=torch.bfloat16)
+    call("b2_avgpool2x2_bwd_nhwc_bf16", g.data_ptr(), ldy, dx.data_ptr(), N, H, W, C, stream_ptr())
+    ref.backward(g[:, :C].float().view(N, P, Q, C).permute(0, 3, 1, 2))
+    assert _rel(dx.float().permute(0, 3, 1, 2), xr.grad) < 1e-2
+
+
+@pytest.mark.parametrize("C,ldx,train,relu,acc", [(96, 256, 1, 1, 1), (64, 64, 1, 0, 0), (200, 512, 0, 1, 1), (1024, 1024, 1, 1, 0)])
+def test_bn_bwd_ld(C, ldx, train, relu, acc):
+    """Strided BatchNorm (+ReLU mask) backward, written or accumulated into a channel slice of a gradient buffer, vs torch
+    autograd of relu(batch_norm(x)) on the same values."""
+    from video_classif_b200._lib import call, stream_ptr
+    torch.manual_seed(C + acc)
+    M = 1500
+    X = (torch.randn(M, ldx, device=DEV) * 1.5 + 0.3).to(torch.bfloat16)
+    gamma, beta = torch.rand(C, device=DEV) + 0.5, torch.randn(C, device=DEV) * 0.2
+    rm, rv = torch.randn(C, device=DEV) * 0.1, torch.rand(C, device=DEV) + 0.5
+    xr = X[:, :C].float().requires_grad_(True)
+    out = torch.nn.functional.batch_norm(xr, None if train else rm, None if train else rv, gamma, beta, bool(train), 0.0, 1e-5)
+    z = (out.clamp_min(0) if relu else out)
+    dz = torch.randn(M, C, device=DEV).to(torch.bfloat16)
+    gr = gamma.clone().requires_grad_(True)
+    br = beta.clone().requires_grad_(True)
+    out2 = torch.nn.functional.batch_norm(xr, None if train else rm, None if train else rv, gr, br, bool(train), 0.0, 1e-5)
+    (out2.clamp_min(0) if relu else out2).backward(dz.float())
+    s = torch.stack([X[:, :C].float().sum(0), (X[:, :C].float() ** 2).sum(0)]).contiguous()
+    dX0 = torch.randn(M, ldx, device=DEV).to(torch.bfloat16)
+    dX = dX0.clone()
+    s12 = torch.zeros(2, C, device=DEV)
+    zb = z.detach().to(torch.bfloat16).contiguous()
+    call("b2_bn_bwd_ld_bf16", dz.data_ptr(), C, zb.data_ptr() if relu else 0, C, X.data_ptr(), ldx, dX.data_ptr(), ldx, acc,
+         gamma.data_ptr(), s[0].data_ptr(), s[1].data_ptr(), rm.data_ptr(), rv.data_ptr(), s12[0].data_ptr(), s12[1].data_ptr(),
+         M, C, M, 1e-5, train, stream_ptr())
+    want = xr.grad + (dX0[:, :C].float() if acc else 0)
+    assert _rel(dX[:, :C].float(), want) < 2e-2
+    assert torch.equal(dX[:, C:], dX0[:, C:])
+    assert _rel(s12[0], br.grad) < 1e-3 and _rel(s12[1], gr.grad) < 5e-3
+
+
+@pytest.mark.parametrize("C,H,W,stride,act", [(32, 9, 9, 1, 2), (96, 12, 10, 2, 2), (144, 7, 7, 1, 1), (960, 4, 4, 1, 2), (24, 5, 6, 2, 0)])
+def test_dwconv3x3_bn(C, H, W, stride, act):
+    """Depthwise 3x3 with the previous BatchNorm + ReLU / ReLU6 on load (padding stays zero), output statistics."""
+    from video_classif_b200._lib import call, stream_ptr
+    torch.manual_seed(C + H)
+    N = 3
+    x = torch.randn(N, H, W, C, device=DEV).to(torch.bfloat16)
+    sc, sh = torch.rand(C, device=DEV) + 0.5, torch.randn(C, device=DEV)
+    w = torch.randn(C, 1, 3, 3, device=DEV) * 0.3
+    P, Q = (H + 2 - 3) // stride + 1, (W + 2 - 3) // stride + 1
+    y = torch.empty(N, P, Q, C, device=DEV, dtype=torch.bfloat16)
+    s = torch.zeros(2, C, device=DEV)
+    call("b2_dwconv3x3_bn_nhwc_bf16", x.data_ptr(), sc.data_ptr() if act else 0, sh.data_ptr() if act else 0, act,
+         w.reshape(C, 9).contiguous().data_ptr(), y.data_ptr(), s[0].data_ptr(), s[1].data_ptr(), N, H, W, C, stride, stream_ptr())
+    a = x.float()
+    if act:
+        a = a * sc + sh
+        a = a.clamp(0, 6) if act == 2 else a.clamp_min(0)
+        a = a.to(torch.bfloat16).float()
+    ref = torch.nn.functional.conv2d(a.permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), stride=stride, padding=1, groups=C)
+    assert _rel(y.float().permute(0, 3, 1, 2), ref) < 1e-2
+    yf = y.float().reshape(-1, C)
+    assert _rel(s[0], yf.sum(0)) < 1e-4 and _rel(s[1], (yf * yf).sum(0)) < 1e-4
+
+
+def test_mbv2_stem_conv():
+    from video_classif_b200._lib import call, stream_ptr
+    torch.manual_seed(8)
+    x = torch.rand(5, 3, 31, 40, device=DEV)
+    w = torch.randn(32, 3, 3, 3, device=DEV) * 0.2
+    P, Q = 16, 20
+    y = torch.empty(5, P, Q, 32, device=DEV, dtype=torch.bfloat16)
+    s = torch.zeros(2, 32, device=DEV)
+    call("b2_mbv2_stem_conv", x.data_ptr(), 0, w.contiguous().data_ptr(), y.data_ptr(), s[0].data_ptr(), s[1].data_ptr(), 5, 31, 40,
+         stream_ptr())
+    ref = torch.nn.functional.conv2d(x.to(torch.bfloat16).float(), w.to(torch.bfloat16).float(), stride=2, padding=1)
+    assert _rel(y.float().permute(0, 3, 1, 2), ref) < 1e-2
+    yf = y.float().reshape(-1, 32)
+    assert _rel(s[0], yf.sum(0)) < 1e-4 and _rel(s[1], (yf * yf).sum(0)) < 1e-4
+
+
+@pytest.mark.parametrize("M,K,N,lda", [(1000, 96, 128, 256), (4096, 224, 128, 512), (300, 512, 256, 512)])
+def test_gemm_bn_fold(M, K, N, lda):
+    """1x1 conv with the pre-activation BatchNorm + ReLU folded into the A-tile transform over a row-strided operand (K not a
+    multiple of the 64-channel k-block: zero-padded coefficients) + output statistics."""
+    from video_classif_b200._lib import call, stream_ptr
+    torch.manual_seed(M)
+    X = torch.randn(M, lda, device=DEV).to(torch.bfloat16)
+    W = (torch.randn(N, K, device=DEV) * 0.1).to(torch.bfloat16)
+    Kp = (K + 63) // 64 * 64
+    ss = torch.zeros(2, Kp, device=DEV)
+    ss[0, :K] = torch.rand(K, device=DEV) + 0.5
+    ss[1, :K] = torch.randn(K, device=DEV) * 0.5
+    D = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    st = torch.zeros(2, N, device=DEV)
+    call("b2_gemm_bn_bf16_tn", X.data_ptr(), lda, W.data_ptr(), K, D.data_ptr(), N, M, N, K, ss[0].data_ptr(), ss[1].data_ptr(), 1,
+         st[0].data_ptr(), st[1].data_ptr(), stream_ptr())
+    a = (X[:, :K].float() * ss[0, :K] + ss[1, :K]).clamp_min(0).to(torch.bfloat16).float()
+    ref = a @ W.float().t()
+    assert _rel(D.float(), ref) < 1e-2
+    df = D.float()
+    assert _rel(st[0], df.sum(0)) < 1e-3 and _rel(st[1], (df * df).sum(0)) < 1e-3
