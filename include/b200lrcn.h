@@ -287,6 +287,11 @@ int b2_maxpool_relu_bwd_nhwc(const void* raw, const float* scale, const float* s
  * to the next multiple of 64 channels (zero padded); N % 32 == 0, N >= 64. */
 int b2_gemm_bn_bf16_tn(const void* A, long lda, const void* B, long ldb, void* D, long ldd, int M, int N, int K,
                        const float* a_scale, const float* a_shift, int a_relu, float* col_sum, float* col_sumsq, void* stream);
+/* Halo-tile 3x3 conv of a dense layer (128 -> 32 channels, stride 1, pad 1): the input halo is fetched once for all 9 taps,
+ * the 32 new channels are written straight into a channel slice of the block buffer (row stride ldy) + their statistics. */
+int b2_conv3x3_halo_dense_supported(int N, int H, int W, int C, int Cout);
+int b2_conv3x3_halo_dense_bf16(const void* x, int N, int H, int W, int C, const void* w, int Cout, void* y, long ldy,
+                               float* col_sum, float* col_sumsq, void* stream);
 int b2_scale_shift_apply_ld_bf16(const void* x, long ldx, void* y, long ldy, long rows, int C, const float* scale,
                                  const float* shift, int relu, void* stream);
 int b2_colstats_ld_bf16(const void* x, long ld, long rows, int C, float* sum, float* sumsq, void* stream);

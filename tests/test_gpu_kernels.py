@@ -589,3 +589,28 @@ def test_gemm_bn_fold(M, K, N, lda):
     assert _rel(D.float(), ref) < 1e-2
     df = D.float()
     assert _rel(st[0], df.sum(0)) < 1e-3 and _rel(st[1], (df * df).sum(0)) < 1e-3
+
+
+@pytest.mark.parametrize("N,H,W", [(3, 28, 28), (5, 14, 14), (4, 7, 7), (2, 3, 3), (2, 9, 20), (1024, 3, 3), (600, 2, 2)])
+def test_conv3x3_halo_dense(N, H, W):
+    """DenseNet dense-layer conv (128 -> 32, 3x3, pad 1) on the halo-tile kernel: output written into a channel slice of a
+    wider buffer (the rest of the buffer untouched), output statistics; vs F.conv2d on the same bf16 operands.  The many-tile
+    tiny-map cases exercise the shifted descriptors' reach past a small halo panel (shared-memory tail padding)."""
+    from video_classif_b200._lib import call, lib, stream_ptr
+    torch.manual_seed(H * W)
+    assert lib().b2_conv3x3_halo_dense_supported(N, H, W, 128, 32) == 1
+    x = torch.randn(N, H, W, 128, device=DEV).to(torch.bfloat16)
+    w = (torch.randn(32, 128, 3, 3, device=DEV) * 0.05)
+    wk = w.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+    ld = 256
+    X0 = torch.randn(N * H * W, ld, device=DEV).to(torch.bfloat16)
+    X = X0.clone()
+    s = torch.zeros(2, 32, device=DEV)
+    call("b2_conv3x3_halo_dense_bf16", x.data_ptr(), N, H, W, 128, wk.data_ptr(), 32, X.data_ptr() + 2 * 96, ld, s[0].data_ptr(),
+         s[1].data_ptr(), stream_ptr())
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), padding=1).permute(0, 2, 3, 1)
+    got = X[:, 96:128].float().view(N, H, W, 32)
+    assert _rel(got, ref) < 1e-2
+    assert torch.equal(X[:, :96], X0[:, :96]) and torch.equal(X[:, 128:], X0[:, 128:])
+    gf = X[:, 96:128].float()
+    assert _rel(s[0], gf.sum(0)) < 1e-3 and _rel(s[1], (gf * gf).sum(0)) < 1e-3

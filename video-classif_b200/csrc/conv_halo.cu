@@ -26,12 +26,9 @@ using namespace tc;
 
 constexpr int kEpiWarps = 8;
 constexpr int kTfWarps = 4;
-constexpr int kStages = 4;
 constexpr int kC = 64;                 // input channels (one 128-byte swizzle row per pixel)
 constexpr int kN = 64;                 // output channels
 constexpr int kTaps = 9;
-constexpr int kWTileBytes = kN * 128;  // one tap's [Cout x 64] weight tile
-constexpr int kWBytes = kTaps * kWTileBytes;
 constexpr int kStgBytes = 32 * 64;
 
 struct HaloGeom {
@@ -86,16 +83,25 @@ __device__ __forceinline__ uint32_t pack_relu(float lo, float hi) {
   return d;
 }
 
-template <bool TF>
+// CS = 64-channel slabs of the input (C = 64 CS), KN = output channels: <.., 1, 64> is the ResNet 64 -> 64 stage, <false, 2, 32>
+// the DenseNet dense-layer conv (128 -> growth 32) whose output goes straight into a channel slice of the block buffer (ldy).
+template <bool TF, int CS = 1, int KN = 64>
 __global__ void __launch_bounds__(64 + 32 * kEpiWarps + (TF ? 32 * kTfWarps : 0), 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                    bf16* __restrict__ y, HaloGeom g, InBn at, float* col_sum, float* col_sumsq, OutFin fin) {
+                    bf16* __restrict__ y, long ldy, HaloGeom g, InBn at, float* col_sum, float* col_sumsq, OutFin fin) {
+  static_assert(!TF || CS == 1, "the input transform is built for one channel slab");
   constexpr int kThreads = 64 + 32 * kEpiWarps + (TF ? 32 * kTfWarps : 0);
+  constexpr int kN = KN;
+  constexpr int kStages = CS == 1 ? 4 : 3;
+  constexpr int kWTileBytes = KN * 128;               // one (tap, slab) [KN x 64] weight tile
+  constexpr int kWBytes = kTaps * CS * kWTileBytes;
+  constexpr int kActEpi = KN / 32 * 4;                // epilogue warps that own a 32-column chunk
+  const int stage_stride = CS * g.stage_bytes;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* w_s = smem;                                        // 9 resident weight tiles
   uint8_t* stage_s = smem + kWBytes;                          // kStages halo tiles (+ 2 KB read slack after the last)
-  uint8_t* after = stage_s + kStages * g.stage_bytes + 2048;
+  uint8_t* after = stage_s + kStages * stage_stride + 2048;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(after);
   uint64_t* tf_bar = full_bar + kStages;
   uint64_t* empty_bar = tf_bar + kStages;
@@ -120,7 +126,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], kEpiWarps);
+      mbar_init(&tempty_bar[i], kActEpi);
     }
     mbar_init(w_bar, 1);
     fence_barrier_init();
@@ -138,15 +144,18 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     // =========================== TMA producer ===========================
     if (lane == 0) {
       mbar_expect_tx(w_bar, kWBytes);
-      for (int t = 0; t < kTaps; ++t) tma_load_2d(w_s + t * kWTileBytes, &tmap_w, w_bar, t * kC, 0);
+      for (int t = 0; t < kTaps; ++t)
+        for (int p = 0; p < CS; ++p)
+          tma_load_2d(w_s + (t * CS + p) * kWTileBytes, &tmap_w, w_bar, (t * CS + p) * 64, 0);
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
         const int n = g.tiles_per_img == 1 ? tile : (int)__umulhi((uint32_t)tile, g.magic_tpi);
         const int h0 = (tile - n * g.tiles_per_img) * g.TH;
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_expect_tx(&full_bar[stage], (uint32_t)(g.halo_px * 128));
-        tma_load_4d(stage_s + stage * g.stage_bytes, &tmap_x, &full_bar[stage], 0, -1, h0 - 1, n);
+        mbar_expect_tx(&full_bar[stage], (uint32_t)(CS * g.halo_px * 128));
+        for (int p = 0; p < CS; ++p)
+          tma_load_4d(stage_s + stage * stage_stride + p * g.stage_bytes, &tmap_x, &full_bar[stage], p * 64, -1, h0 - 1, n);
         if (++stage == kStages) {
           stage = 0;
           phase ^= 1;
@@ -174,13 +183,17 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       tc_fence_after();
       if (lane == 0) {
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kN);
-        const uint64_t da0 = make_sw128_desc_rows(smem_u32(stage_s + stage * g.stage_bytes), 0, 0);
+        const uint64_t da0 = make_sw128_desc_rows(smem_u32(stage_s + stage * stage_stride), 0, 0);
 #pragma unroll
         for (int t = 0; t < kTaps; ++t) {
 #pragma unroll
-          for (int k = 0; k < kC / 16; ++k) {
-            tc_mma_bf16(d_tmem, da0 + (uint64_t)(a_off[t] + k * 2), db0 + (uint64_t)(t * (kWTileBytes / 16) + k * 2), idesc,
-                        (t | k) != 0);
+          for (int p = 0; p < CS; ++p) {
+            const uint32_t pa = (uint32_t)(p * (g.stage_bytes / 16));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              tc_mma_bf16(d_tmem, da0 + (uint64_t)(pa + a_off[t] + k * 2),
+                          db0 + (uint64_t)((t * CS + p) * (kWTileBytes / 16) + k * 2), idesc, (t | p | k) != 0);
+            }
           }
         }
         tc_commit(&empty_bar[stage]);
@@ -200,6 +213,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     const int sw = (lane >> 1) & 3;
     const int sw_w = lane & 15, sw_hf = lane >> 4;
     int it = 0;
+    if (ch < KN / 32)           // (with 32 output channels only the first four epilogue warps have a chunk)
     for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
       const int n = g.tiles_per_img == 1 ? tile : (int)__umulhi((uint32_t)tile, g.magic_tpi);
       const int h0 = (tile - n * g.tiles_per_img) * g.TH;
@@ -220,7 +234,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
 #pragma unroll
       for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(raw[2 * j]), __uint_as_float(raw[2 * j + 1]));
       if (row_ok) {
-        bf16* dp = y + ((((long)n * g.H + h0 + pl) * g.W + q) * kN + ch * 32);
+        bf16* dp = y + ((((long)n * g.H + h0 + pl) * g.W + q) * ldy + ch * 32);
         asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dp), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
                      "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
                      : "memory");
@@ -270,7 +284,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       const int n = g.tiles_per_img == 1 ? tile : (int)__umulhi((uint32_t)tile, g.magic_tpi);
       const int h0 = (tile - n * g.tiles_per_img) * g.TH;
       mbar_wait(&full_bar[stage], phase);
-      uint8_t* sa = stage_s + stage * g.stage_bytes;
+      uint8_t* sa = stage_s + stage * stage_stride;
       for (int i0 = rb; i0 < g.halo_px; i0 += 16 * 4) {
         uint4 u[4];
         bool ok[4];
@@ -393,8 +407,15 @@ int make_geom(HaloGeom* g, int N, int H, int W) {
   return 0;
 }
 
-int halo_smem_bytes(const HaloGeom& g) {
-  return kWBytes + kStages * g.stage_bytes + 2048 + 256 + 16 * kN * 4 + kEpiWarps * kStgBytes + 1024;
+int halo_smem_bytes(const HaloGeom& g, int cs = 1, int kn = kN) {
+  const int stages = cs == 1 ? 4 : 3;
+  // the shifted A descriptors of the last taps read up to 128 + 2 Wp + 2 halo rows from a panel start: with small images
+  // (few halo rows per tile) that runs past the panel, the following stages and the tail regions -- harmless garbage (it only
+  // feeds discarded accumulator rows) but it must stay inside the CTA's allocation, so the tail is padded accordingly
+  const int reach = (128 + 2 * g.Wp + 3) * 128;
+  const int tail = 2048 + 256 + 16 * kn * 4 + (kn / 32 * 4) * kStgBytes + 1024;
+  const int pad = reach > g.stage_bytes + tail ? reach - g.stage_bytes - tail : 0;
+  return kTaps * cs * kn * 128 + stages * cs * g.stage_bytes + tail + pad;
 }
 
 }  // namespace
@@ -484,10 +505,74 @@ B2_API int b2_conv3x3_halo_bn_nhwc_bf16(const void* x, int N, int H, int W, int 
   const int grid = g.num_tiles < b2_num_sms() ? g.num_tiles : b2_num_sms();
   cudaStream_t st = (cudaStream_t)stream;
   if (tf)
-    conv3x3_halo_kernel<true><<<grid, 64 + 32 * kEpiWarps + 32 * kTfWarps, smem, st>>>(tx, tw, (bf16*)y, g, at, col_sum,
-                                                                                      col_sumsq, fin);
+    conv3x3_halo_kernel<true><<<grid, 64 + 32 * kEpiWarps + 32 * kTfWarps, smem, st>>>(tx, tw, (bf16*)y, (long)kN, g, at,
+                                                                                      col_sum, col_sumsq, fin);
   else
-    conv3x3_halo_kernel<false><<<grid, 64 + 32 * kEpiWarps, smem, st>>>(tx, tw, (bf16*)y, g, at, col_sum, col_sumsq, fin);
+    conv3x3_halo_kernel<false><<<grid, 64 + 32 * kEpiWarps, smem, st>>>(tx, tw, (bf16*)y, (long)kN, g, at, col_sum, col_sumsq,
+                                                                       fin);
   B2_LAUNCH_CHECK("conv3x3_halo_kernel");
+  return 0;
+}
+
+// ---- DenseNet dense-layer conv: y[:, :32] (row stride ldy: a channel slice of the block buffer) = conv3x3(x [N,H,W,128]),
+// stride 1, pad 1, + per-channel statistics of the output (csrc/dense_ops.cu explains the buffer layout)
+B2_API int b2_conv3x3_halo_dense_supported(int N, int H, int W, int C, int Cout) {
+  HaloGeom g;
+  if (C != 128 || Cout != 32 || N <= 0 || H <= 0 || W <= 0) return 0;
+  if (make_geom(&g, N, H, W) != 0) return 0;
+  return halo_smem_bytes(g, 2, 32) <= 227 * 1024 ? 1 : 0;
+}
+
+B2_API int b2_conv3x3_halo_dense_bf16(const void* x, int N, int H, int W, int C, const void* w, int Cout, void* y, long ldy,
+                                      float* col_sum, float* col_sumsq, void* stream) {
+  const char* who = "b2_conv3x3_halo_dense_bf16";
+  B2_ARG_CHECK(x && w && y, "%s: null pointer", who);
+  B2_ARG_CHECK(b2_conv3x3_halo_dense_supported(N, H, W, C, Cout), "%s: unsupported shape N=%d H=%d W=%d C=%d Cout=%d", who, N,
+               H, W, C, Cout);
+  B2_ARG_CHECK((col_sum == nullptr) == (col_sumsq == nullptr), "%s: col_sum and col_sumsq go together", who);
+  B2_ARG_CHECK(((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0 && ((uintptr_t)y & 31) == 0 && ldy % 16 == 0 && ldy >= Cout,
+               "%s: x / w 16 B aligned, y 32 B aligned with a row stride that keeps it so", who);
+  if (int r = load_encode()) return r;
+  HaloGeom g;
+  make_geom(&g, N, H, W);
+  CUtensorMap tx, tw;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {64u, (cuuint32_t)g.Wp, (cuuint32_t)(g.TH + 2), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult cr = g_encode(&tx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+      b2_set_error("%s: cuTensorMapEncodeTiled(x) failed (%d)", who, (int)cr);
+      return -3;
+    }
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)(kTaps * C), (cuuint64_t)Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)(kTaps * C) * 2};
+    cuuint32_t box[2] = {64u, (cuuint32_t)Cout};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult cr = g_encode(&tw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+      b2_set_error("%s: cuTensorMapEncodeTiled(w) failed (%d)", who, (int)cr);
+      return -3;
+    }
+  }
+  const int smem = halo_smem_bytes(g, 2, 32);
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    B2_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_halo_kernel<false, 2, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_smem = smem;
+  }
+  InBn at = {};
+  OutFin fin = {};
+  const int grid = g.num_tiles < b2_num_sms() ? g.num_tiles : b2_num_sms();
+  conv3x3_halo_kernel<false, 2, 32><<<grid, 64 + 32 * kEpiWarps, smem, (cudaStream_t)stream>>>(tx, tw, (bf16*)y, ldy, g, at,
+                                                                                              col_sum, col_sumsq, fin);
+  B2_LAUNCH_CHECK("conv3x3_halo_kernel<dense>");
   return 0;
 }

@@ -35,6 +35,7 @@ class DenseNetRunner:
         self._graphs = {}
         self.use_graph = False
         self.fold_bn1 = os.environ.get("B2_DENSE_FOLD", "1") == "1"   # BN1+ReLU in the 1x1 GEMM's A transform (tests run both)
+        self.halo_conv = os.environ.get("B2_DENSE_HALO", "1") == "1"  # halo-tile 3x3 conv (tests run both)
         self.fuse_bn = None          # (ResNet-only switches; part of the CUDA-graph cache key of the shared graphed())
         self.stem_impl = None
 
@@ -156,9 +157,18 @@ class DenseNetRunner:
                     self._finalize(layer.norm2, smid[k, 0].data_ptr(), smid[k, 1].data_ptr(), M, train, ssmid, mid)
                     a2 = torch.empty_like(y1) if saved is not None else y1
                     scale_shift_apply(y1, ssmid[0], ssmid[1], relu=True, out=a2)
-                    y2 = conv2d_nhwc(a2.view(N, Hc, Wc, mid), w[pfx + lname + ".conv2"], 1, 1,
-                                     stats=(S.data_ptr() + 4 * Ct, S.data_ptr() + 4 * (Cfin + Ct)) if train else None)
-                    call("b2_scale_shift_apply_ld_bf16", y2.data_ptr(), growth, X.data_ptr() + 2 * Ct, Cfin, M, growth, 0, 0, 0, st)
+                    w2 = w[pfx + lname + ".conv2"]
+                    if self.halo_conv and _lib.lib().b2_conv3x3_halo_dense_supported(N, Hc, Wc, mid, growth):
+                        # halo-tile conv: the input halo is fetched once for all 9 taps (the im2col path re-reads it 9
+                        # times and is L2 -> SM bound at 32 output channels); the 32 new channels go straight into X
+                        y2 = None
+                        call("b2_conv3x3_halo_dense_bf16", a2.data_ptr(), N, Hc, Wc, mid, w2.data_ptr(), growth,
+                             X.data_ptr() + 2 * Ct, Cfin, S.data_ptr() + 4 * Ct if train else 0,
+                             S.data_ptr() + 4 * (Cfin + Ct) if train else 0, st)
+                    else:
+                        y2 = conv2d_nhwc(a2.view(N, Hc, Wc, mid), w2, 1, 1,
+                                         stats=(S.data_ptr() + 4 * Ct, S.data_ptr() + 4 * (Cfin + Ct)) if train else None)
+                        call("b2_scale_shift_apply_ld_bf16", y2.data_ptr(), growth, X.data_ptr() + 2 * Ct, Cfin, M, growth, 0, 0, 0, st)
                     if saved is not None:
                         rec.append((pfx + lname, layer, y1, a2, smid[k]))
                     del y1, y2, a2
