@@ -333,3 +333,23 @@ def test_crime_lrcn_default_densenet121_finetune_trains():
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.cnn_backbone.parameters())
     assert int(m.cnn_backbone.features.denseblock2.denselayer5.norm2.num_batches_tracked) == 5
     assert losses[-1] < losses[0], losses
+
+
+def test_crime_lrcn_densenet_partial_freeze():
+    """`freeze_until_layer=k` on the DenseNet backbone (lrcn.py:275-283): gradients exactly on the parameters past the
+    boundary (the boundary may fall inside a dense layer), none before it; the frozen stem gets no gradient work."""
+    import video_classif_b200 as vc
+    torch.manual_seed(4)
+    m = vc.CrimeLRCN(3, 2, 8, 16, cnn_backbone="densenet121", freeze_until_layer=200, rnn_layers=1, classif_mode="multiclass",
+                     precision="fp32").to(DEV).train()
+    names = [n for n, _ in m.cnn_backbone.named_parameters()]
+    trainable = {n for n, p in m.cnn_backbone.named_parameters() if p.requires_grad}
+    assert trainable == set(names[201:]) and 0 < len(trainable) < len(names)
+    x = torch.rand(2, 2, 3, 64, 64, device=DEV)
+    loss = F.cross_entropy(m(x), torch.tensor([0, 2], device=DEV))
+    loss.backward()
+    for n, p in m.cnn_backbone.named_parameters():
+        if n in trainable:
+            assert p.grad is not None and torch.isfinite(p.grad).all(), n
+        else:
+            assert p.grad is None, n
