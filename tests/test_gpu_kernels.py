@@ -614,3 +614,19 @@ def test_conv3x3_halo_dense(N, H, W):
     assert torch.equal(X[:, :96], X0[:, :96]) and torch.equal(X[:, 128:], X0[:, 128:])
     gf = X[:, 96:128].float()
     assert _rel(s[0], gf.sum(0)) < 1e-3 and _rel(s[1], (gf * gf).sum(0)) < 1e-3
+
+
+@pytest.mark.parametrize("chunk,reverse", [(256, False), (None, False), (None, True), (64, False)])
+def test_selective_scan_backward_vs_oracle_autograd(ops, chunk, reverse):
+    """ops.selective_scan is differentiable: gradients w.r.t. u, delta, A, B, C vs torch autograd through the oracle's scan
+    (videomamba chunk-reset variant with its chunks in parallel, medsos forward / reversed variants) on the golden inputs."""
+    g = np.load(os.path.join(GOLDEN, "scan.npz"))
+    names = ("u", "delta", "A", "B", "C")
+    cpu = [torch.from_numpy(g[k]).clone().requires_grad_(True) for k in names]
+    gpu = [torch.from_numpy(g[k]).to(DEV).requires_grad_(True) for k in names]
+    w = torch.randn(cpu[0].shape, generator=torch.Generator().manual_seed(3))
+    (O.selective_scan(*cpu, chunk_reset=chunk, reverse=reverse) * w).sum().backward()
+    y = ops.selective_scan(*gpu, chunk_reset=chunk, reverse=reverse)
+    (y * w.to(DEV)).sum().backward()
+    for k, a, b in zip(names, gpu, cpu):
+        assert err(a.grad, b.grad) < 2e-3, k

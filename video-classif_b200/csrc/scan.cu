@@ -305,34 +305,39 @@ __global__ void __launch_bounds__(128)
 selective_scan_bwd_kernel(const float* __restrict__ u, const float* __restrict__ delta, const float* __restrict__ A,
                           const float* __restrict__ Bm, const float* __restrict__ Cm, const float* __restrict__ dy,
                           float* __restrict__ states, float* __restrict__ du, float* __restrict__ ddelta,
-                          float* __restrict__ dA_log, float* __restrict__ dB, float* __restrict__ dC, int batch, int L, int D,
-                          int reverse) {
+                          float* __restrict__ dA_out, float* __restrict__ dB, float* __restrict__ dC, int batch, int L, int D,
+                          int chunk, int reverse, int a_is_log) {
+  // one thread per (batch, chunk, channel): chunks are independent (the state is reset at their start), grid.y = chunks
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long)batch * D) return;
   const int d = (int)(idx % D);
   const long b = idx / D;
   const long row0 = b * L;
+  const int t_begin = blockIdx.y * chunk;
+  const int t_end = min(L, t_begin + chunk);
   float a[N], x[N];
 #pragma unroll
   for (int n = 0; n < N; ++n) {
     a[n] = A[(long)d * N + n];
     x[n] = 0.f;
   }
-  float* st = states + idx * (long)L * N;
-  for (int t = 0; t < L; ++t) {                      // forward recompute (same arithmetic as the forward kernel)
+  // states[b][t][d][n]: consecutive threads (channels) write consecutive N-float blocks
+  float* st = states + (row0 * D + d) * N;
+  const long t_stride = (long)D * N;
+  for (int t = t_begin; t < t_end; ++t) {            // forward recompute (same arithmetic as the forward kernel)
     const int ts = reverse ? L - 1 - t : t;
     const float dl = delta[(row0 + ts) * D + d];
     const float duv = dl * u[(row0 + ts) * D + d];
 #pragma unroll
     for (int n = 0; n < N; ++n) {
       x[n] = fmaf(ex2_approx(dl * a[n] * kLog2e), x[n], duv * Bm[(row0 + t) * N + n]);
-      st[(long)t * N + n] = x[n];
+      st[t * t_stride + n] = x[n];
     }
   }
   float g[N], dAacc[N];                               // g: gradient flowing into x_t from step t+1
 #pragma unroll
   for (int n = 0; n < N; ++n) g[n] = dAacc[n] = 0.f;
-  for (int t = L - 1; t >= 0; --t) {
+  for (int t = t_end - 1; t >= t_begin; --t) {
     const int ts = reverse ? L - 1 - t : t;
     const float dl = delta[(row0 + ts) * D + d];
     const float uv = u[(row0 + ts) * D + d];
@@ -340,8 +345,8 @@ selective_scan_bwd_kernel(const float* __restrict__ u, const float* __restrict__
     float ddl = 0.f, duv = 0.f;
 #pragma unroll
     for (int n = 0; n < N; ++n) {
-      const float xt = st[(long)t * N + n];
-      const float xp = t > 0 ? st[(long)(t - 1) * N + n] : 0.f;
+      const float xt = st[t * t_stride + n];
+      const float xp = t > t_begin ? st[(t - 1) * t_stride + n] : 0.f;
       const float bt = Bm[(row0 + t) * N + n];
       const float ct = Cm[(row0 + t) * N + n];
       const float at = ex2_approx(dl * a[n] * kLog2e);
@@ -359,7 +364,7 @@ selective_scan_bwd_kernel(const float* __restrict__ u, const float* __restrict__
     ddelta[(row0 + ts) * D + d] = ddl;
   }
 #pragma unroll
-  for (int n = 0; n < N; ++n) atomicAdd(dA_log + (long)d * N + n, dAacc[n] * a[n]);
+  for (int n = 0; n < N; ++n) atomicAdd(dA_out + (long)d * N + n, a_is_log ? dAacc[n] * a[n] : dAacc[n]);
 }
 
 }  // namespace
@@ -401,20 +406,26 @@ B2_API int b2_mul_silu_bwd_f32(const float* dy, const float* a, const float* res
   return 0;
 }
 
-// workspace: batch * D * L * N floats; du / ddelta overwritten; dA_log [D,N], dB / dC [batch,L,N] ACCUMULATED (caller zeroes)
+// workspace: batch * D * L * N floats; du / ddelta overwritten; dA [D,N], dB / dC [batch,L,N] ACCUMULATED (caller zeroes).
+// chunk_reset > 0: the state restarts from zero every chunk_reset steps (videomamba.py:242-284), chunks run in parallel;
+// a_is_log = 1: dA is the gradient of A_log where A = -exp(A_log) (medsos models.py:94), 0: the gradient of A itself
 B2_API int b2_selective_scan_bwd(const float* u, const float* delta, const float* A, const float* Bm, const float* Cm,
-                                 const float* dy, float* workspace, float* du, float* ddelta, float* dA_log, float* dB,
-                                 float* dC, int batch, int L, int D, int N, int reverse, void* stream) {
-  B2_ARG_CHECK(u && delta && A && Bm && Cm && dy && workspace && du && ddelta && dA_log && dB && dC,
+                                 const float* dy, float* workspace, float* du, float* ddelta, float* dA, float* dB, float* dC,
+                                 int batch, int L, int D, int N, int chunk_reset, int reverse, int a_is_log, void* stream) {
+  B2_ARG_CHECK(u && delta && A && Bm && Cm && dy && workspace && du && ddelta && dA && dB && dC,
                "b2_selective_scan_bwd: null pointer");
   B2_ARG_CHECK(batch > 0 && L > 0 && D > 0, "b2_selective_scan_bwd: empty shape");
   B2_ARG_CHECK(N == 4 || N == 8 || N == 16 || N == 32, "b2_selective_scan_bwd: n_state must be 4, 8, 16 or 32 (got %d)", N);
+  const int chunk = chunk_reset > 0 ? chunk_reset : L;
+  const int chunks = b2_ceil_div(L, chunk);
+  B2_ARG_CHECK(chunks <= 65535, "b2_selective_scan_bwd: too many chunks");
+  B2_ARG_CHECK(!(reverse && chunks > 1), "b2_selective_scan_bwd: the reference has no chunk-reset scan in the reverse direction");
   const long threads = (long)batch * D;
-  const unsigned grid = (unsigned)((threads + 127) / 128);
+  const dim3 grid((unsigned)((threads + 127) / 128), (unsigned)chunks);
   cudaStream_t st = (cudaStream_t)stream;
-#define B2_SCAN_BWD(NN)                                                                                              \
-  selective_scan_bwd_kernel<NN><<<grid, 128, 0, st>>>(u, delta, A, Bm, Cm, dy, workspace, du, ddelta, dA_log, dB, dC, \
-                                                      batch, L, D, reverse)
+#define B2_SCAN_BWD(NN)                                                                                          \
+  selective_scan_bwd_kernel<NN><<<grid, 128, 0, st>>>(u, delta, A, Bm, Cm, dy, workspace, du, ddelta, dA, dB, dC, \
+                                                      batch, L, D, chunk, reverse, a_is_log)
   switch (N) {
     case 4: B2_SCAN_BWD(4); break;
     case 8: B2_SCAN_BWD(8); break;

@@ -231,18 +231,53 @@ def ingest_u8(frames_u8, out_h, out_w, frame_index=None, out_dtype=F32, swap_rb=
     return out
 
 
+def _scan_fwd(u, delta, A, Bm, Cm, chunk_reset, reverse):
+    Bsz, L, D = u.shape
+    N = A.shape[1]
+    y = torch.empty_like(u)
+    call("b2_selective_scan_fwd", u.data_ptr(), delta.data_ptr(), A.data_ptr(), Bm.data_ptr(), Cm.data_ptr(), y.data_ptr(),
+         Bsz, L, D, N, int(chunk_reset or 0), int(reverse), stream_ptr())
+    return y
+
+
+class SelectiveScanFn(torch.autograd.Function):
+    """y = selective scan(u, delta, A, B, C): forward b2_selective_scan_fwd, backward b2_selective_scan_bwd (BPTT over the
+    recomputed states; chunks of the chunk-reset variant in parallel)."""
+
+    @staticmethod
+    def forward(ctx, u, delta, A, Bm, Cm, chunk_reset, reverse):
+        ctx.save_for_backward(u, delta, A, Bm, Cm)
+        ctx.cfg = (int(chunk_reset or 0), int(reverse))
+        return _scan_fwd(u, delta, A, Bm, Cm, chunk_reset, reverse)
+
+    @staticmethod
+    def backward(ctx, dy):
+        u, delta, A, Bm, Cm = ctx.saved_tensors
+        chunk, rev = ctx.cfg
+        Bsz, L, D = u.shape
+        N = A.shape[1]
+        dy = dy.contiguous().float()
+        ws = torch.empty(Bsz * D * L * N, device=u.device, dtype=F32)
+        du, dd = torch.empty_like(u), torch.empty_like(u)
+        dA = torch.zeros_like(A)
+        dB, dC = torch.zeros_like(Bm), torch.zeros_like(Cm)
+        call("b2_selective_scan_bwd", u.data_ptr(), delta.data_ptr(), A.data_ptr(), Bm.data_ptr(), Cm.data_ptr(), dy.data_ptr(),
+             ws.data_ptr(), du.data_ptr(), dd.data_ptr(), dA.data_ptr(), dB.data_ptr(), dC.data_ptr(), Bsz, L, D, N, chunk, rev, 0,
+             stream_ptr())
+        return du, dd, dA, dB, dC, None, None
+
+
 def selective_scan(u, delta, A, Bm, Cm, chunk_reset=256, reverse=False):
-    """b2_selective_scan_fwd: y[B,L,D] of the VideoMamba scan (videomamba.py:242-284; chunk_reset=None +
-    reverse for medsos models.py:47-71).  Forward only (BASELINE config 5)."""
+    """y[B,L,D] of the VideoMamba scan (videomamba.py:242-284: state reset every `chunk_reset` steps; chunk_reset=None +
+    reverse for medsos models.py:47-71).  Differentiable w.r.t. u, delta, A, B, C (BASELINE config 5)."""
     _chk(u, delta, A, Bm, Cm)
     u, delta, A, Bm, Cm = (t.contiguous().float() for t in (u, delta, A, Bm, Cm))
     Bsz, L, D = u.shape
     N = A.shape[1]
     assert delta.shape == u.shape and A.shape[0] == D and Bm.shape == (Bsz, L, N) and Cm.shape == (Bsz, L, N)
-    y = torch.empty_like(u)
-    call("b2_selective_scan_fwd", u.data_ptr(), delta.data_ptr(), A.data_ptr(), Bm.data_ptr(), Cm.data_ptr(), y.data_ptr(),
-         Bsz, L, D, N, int(chunk_reset or 0), int(reverse), stream_ptr())
-    return y
+    if torch.is_grad_enabled() and any(t.requires_grad for t in (u, delta, A, Bm, Cm)):
+        return SelectiveScanFn.apply(u, delta, A, Bm, Cm, chunk_reset, reverse)
+    return _scan_fwd(u, delta, A, Bm, Cm, chunk_reset, reverse)
 
 
 def rmsnorm(x, weight, eps=1e-5):
@@ -341,7 +376,7 @@ class MambaBlockFn(torch.autograd.Function):
             dd = torch.empty((B, L, di), device=dev, dtype=F32)
             call("b2_selective_scan_bwd", xc.data_ptr(), delta3.data_ptr(), A.data_ptr(), Bm.data_ptr(), Cm.data_ptr(),
                  dyd.data_ptr(), ws.data_ptr(), du.data_ptr(), dd.data_ptr(), dA_log.data_ptr(), dBC[0].data_ptr(),
-                 dBC[1].data_ptr(), B, L, di, n, rev, st)
+                 dBC[1].data_ptr(), B, L, di, n, 0, rev, 1, st)
             if rev == 0:
                 dxc, ddelta = du, dd
             else:
