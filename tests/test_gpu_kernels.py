@@ -630,3 +630,21 @@ def test_selective_scan_backward_vs_oracle_autograd(ops, chunk, reverse):
     (y * w.to(DEV)).sum().backward()
     for k, a, b in zip(names, gpu, cpu):
         assert err(a.grad, b.grad) < 2e-3, k
+
+
+@pytest.mark.parametrize("B,L,D,N,chunk,reverse", [(3, 40, 64, 16, 16, False), (2, 33, 96, 8, None, True), (2, 20, 160, 32, None, False)])
+def test_selective_scan_backward_wide(ops, B, L, D, N, chunk, reverse):
+    """D % 32 == 0: the dB / dC contributions of a warp's 32 channels are summed with shuffles (one atomic per warp)."""
+    g = torch.Generator().manual_seed(L + D)
+    u = torch.randn(B, L, D, generator=g)
+    delta = F.softplus(torch.randn(B, L, D, generator=g))
+    A = -torch.exp(torch.randn(D, N, generator=g) * 0.5)
+    Bm, Cm = torch.randn(B, L, N, generator=g), torch.randn(B, L, N, generator=g)
+    cpu = [t.clone().requires_grad_(True) for t in (u, delta, A, Bm, Cm)]
+    gpu = [t.to(DEV).requires_grad_(True) for t in (u, delta, A, Bm, Cm)]
+    w = torch.randn(B, L, D, generator=g)
+    (O.selective_scan(*cpu, chunk_reset=chunk, reverse=reverse) * w).sum().backward()
+    y = ops.selective_scan(*gpu, chunk_reset=chunk, reverse=reverse)
+    (y * w.to(DEV)).sum().backward()
+    for k, a, b in zip(("u", "delta", "A", "B", "C"), gpu, cpu):
+        assert err(a.grad, b.grad) < 2e-3, k

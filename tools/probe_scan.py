@@ -39,4 +39,19 @@ for (B, L, D, N, chunk) in [(8, 16, 2048, 16, None), (8, 3136, 2048, 16, 256), (
         err = (y[:, :Ls].cpu() - ref).abs().max().item() / ref.abs().max().item()
         line += f" | oracle port on {os.cpu_count()} host cores: {cpu_s * 1e6 / (B * Ls):8.1f} us/token vs GPU {us / (B * L):.4f} us/token, rel err {err:.1e}"
     print(line, flush=True)
+    # forward + backward (BPTT over recomputed states; chunks in parallel)
+    gargs = [t.clone().requires_grad_(True) for t in args]
+    w = torch.randn_like(args[0])
+    for _ in range(2):
+        for t in gargs:
+            t.grad = None
+        (ops.selective_scan(*gargs, chunk_reset=chunk) * w).sum().backward()
+    e0.record()
+    for _ in range(5):
+        for t in gargs:
+            t.grad = None
+        (ops.selective_scan(*gargs, chunk_reset=chunk) * w).sum().backward()
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"     forward + backward: {e0.elapsed_time(e1) / 5 * 1e3:9.1f} us ({torch.cuda.max_memory_allocated() / 2**30:.1f} GB peak)", flush=True)
 print("PROBE DONE")

@@ -309,10 +309,16 @@ selective_scan_bwd_kernel(const float* __restrict__ u, const float* __restrict__
                           int chunk, int reverse, int a_is_log) {
   // one thread per (batch, chunk, channel): chunks are independent (the state is reset at their start), grid.y = chunks
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long)batch * D) return;
-  const int d = (int)(idx % D);
-  const long b = idx / D;
+  // D % 32 == 0: a warp's 32 channels share (batch, t), so the dB / dC contributions are summed with shuffles and leave as
+  // ONE atomic per warp (per-thread atomics put D threads on each of the B*L*N addresses: 21 ms at B 8, L 3136, D 2048)
+  const bool warp_reduce = (D & 31) == 0;
+  if (!warp_reduce && idx >= (long)batch * D) return;
+  const bool live = idx < (long)batch * D;
+  const long idc = live ? idx : (long)batch * D - 1;     // idle lanes of the last warp shadow a valid thread, contribute 0
+  const int d = (int)(idc % D);
+  const long b = idc / D;
   const long row0 = b * L;
+  const int lane = threadIdx.x & 31;
   const int t_begin = blockIdx.y * chunk;
   const int t_end = min(L, t_begin + chunk);
   float a[N], x[N];
@@ -331,7 +337,7 @@ selective_scan_bwd_kernel(const float* __restrict__ u, const float* __restrict__
 #pragma unroll
     for (int n = 0; n < N; ++n) {
       x[n] = fmaf(ex2_approx(dl * a[n] * kLog2e), x[n], duv * Bm[(row0 + t) * N + n]);
-      st[t * t_stride + n] = x[n];
+      if (live) st[t * t_stride + n] = x[n];
     }
   }
   float g[N], dAacc[N];                               // g: gradient flowing into x_t from step t+1
@@ -350,21 +356,39 @@ selective_scan_bwd_kernel(const float* __restrict__ u, const float* __restrict__
       const float bt = Bm[(row0 + t) * N + n];
       const float ct = Cm[(row0 + t) * N + n];
       const float at = ex2_approx(dl * a[n] * kLog2e);
-      atomicAdd(dC + (row0 + t) * N + n, dyv * xt);
       const float dx = fmaf(dyv, ct, g[n]);
+      float vc = live ? dyv * xt : 0.f;
+      float vb = live ? dx * dl * uv : 0.f;
+      if (warp_reduce) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          vc += __shfl_xor_sync(0xffffffffu, vc, off);
+          vb += __shfl_xor_sync(0xffffffffu, vb, off);
+        }
+        if (lane == 0) {
+          atomicAdd(dC + (row0 + t) * N + n, vc);
+          atomicAdd(dB + (row0 + t) * N + n, vb);
+        }
+      } else {
+        atomicAdd(dC + (row0 + t) * N + n, vc);
+        atomicAdd(dB + (row0 + t) * N + n, vb);
+      }
       const float da = dx * xp;                       // gradient of a_t = exp(delta_t A)
       ddl = fmaf(da * at, a[n], ddl);
       ddl = fmaf(dx * bt, uv, ddl);
       dAacc[n] = fmaf(da * at, dl, dAacc[n]);
-      atomicAdd(dB + (row0 + t) * N + n, dx * dl * uv);
       duv = fmaf(dx * dl, bt, duv);
       g[n] = at * dx;
     }
-    du[(row0 + ts) * D + d] = duv;
-    ddelta[(row0 + ts) * D + d] = ddl;
+    if (live) {
+      du[(row0 + ts) * D + d] = duv;
+      ddelta[(row0 + ts) * D + d] = ddl;
+    }
   }
+  if (live) {
 #pragma unroll
-  for (int n = 0; n < N; ++n) atomicAdd(dA_out + (long)d * N + n, a_is_log ? dAacc[n] * a[n] : dAacc[n]);
+    for (int n = 0; n < N; ++n) atomicAdd(dA_out + (long)d * N + n, a_is_log ? dAacc[n] * a[n] : dAacc[n]);
+  }
 }
 
 }  // namespace
