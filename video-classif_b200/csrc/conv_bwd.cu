@@ -26,11 +26,14 @@ constexpr int kRows = 64;                   // pixels (reduction rows) per pipel
 constexpr int kPanel = kRows * 128;         // one [64 pixels x 64 channels] bf16 panel, SWIZZLE_128B: 8 KB
 constexpr int kWgThreads = 64 + 128;        // TMA warp, MMA warp, 4 drain warps
 
-template <int BNC>
+// MT = 128-row output-channel tiles per CTA: MT = 2 (two accumulators sharing the x panels, 512 TMEM columns) raises the
+// operand intensity 1.5x for the wide layers (the kernel is bound by L2 -> SM operand delivery)
+template <int BNC, int MT = 1>
 struct WgLayout {
   static constexpr int kBPanels = BNC / 64;
-  static constexpr int kStageBytes = (2 + kBPanels) * kPanel;          // 24 / 32 / 48 KB
-  static constexpr int kStages = BNC == 256 ? 4 : (BNC == 128 ? 6 : 8);
+  static constexpr int kAPanels = 2 * MT;
+  static constexpr int kStageBytes = (kAPanels + kBPanels) * kPanel;   // 24 / 32 / 48 KB (MT = 2: 64 KB)
+  static constexpr int kStages = MT == 2 ? 3 : (BNC == 256 ? 4 : (BNC == 128 ? 6 : 8));
   static constexpr int kBarOffset = kStages * kStageBytes;
   static constexpr int kSmem = kBarOffset + (2 * kStages + 1) * 8 + 16 + 1024;
   static_assert(kSmem <= 227 * 1024, "shared memory budget");
@@ -60,11 +63,12 @@ __device__ __forceinline__ uint64_t sw128_mn_desc(uint32_t smem_addr, uint32_t l
   return d;
 }
 
-template <int BNC>
+template <int BNC, int MT = 1>
 __global__ void __launch_bounds__(kWgThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x, WgGeom g,
                   float* __restrict__ dw) {
-  using L = WgLayout<BNC>;
+  using L = WgLayout<BNC, MT>;
+  static_assert(MT * BNC <= 512, "TMEM columns");
   constexpr int kStages = L::kStages;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -92,7 +96,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
     fence_barrier_init();
   }
   if (warp == 1) {
-    tc_alloc(tmem_slot, BNC);
+    tc_alloc(tmem_slot, MT * BNC);
     tc_relinquish();
   }
   tc_fence_before();
@@ -107,15 +111,16 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
       int valid = 0;                                   // panels that hold a real (tap, channel slab)
       for (int pp = 0; pp < L::kBPanels; ++pp)
         valid += (tap0 + pp / g.ppt < g.taps) && (ci_blk * BNC + (pp % g.ppt) * 64 < g.C);
-      const uint32_t stage_tx = (uint32_t)((2 + valid) * kPanel);
+      const uint32_t stage_tx = (uint32_t)((L::kAPanels + valid) * kPanel);
       for (int t = split; t < num_tiles; t += splits) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * L::kStageBytes;
-        uint8_t* sb = sa + 2 * kPanel;
+        uint8_t* sb = sa + L::kAPanels * kPanel;
         mbar_expect_tx(&full_bar[stage], stage_tx);
         const int m0 = t * kRows;
-        tma_load_2d(sa, &tmap_dy, &full_bar[stage], co_blk * 128, m0);               // columns past Cout: zero fill
-        tma_load_2d(sa + kPanel, &tmap_dy, &full_bar[stage], co_blk * 128 + 64, m0);
+#pragma unroll
+        for (int pa = 0; pa < L::kAPanels; ++pa)                                       // columns past Cout: zero fill
+          tma_load_2d(sa + pa * kPanel, &tmap_dy, &full_bar[stage], co_blk * (128 * MT) + pa * 64, m0);
         int cn = 0, cw = 0, ch = 0;
         if (g.is_im2col) {
           const int pq = g.P * g.Q;
@@ -156,12 +161,15 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
       tc_fence_after();
       if (lane == 0) {
         const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
-        const uint32_t sb = sa + 2 * kPanel;
+        const uint32_t sb = sa + L::kAPanels * kPanel;
 #pragma unroll
         for (int ks = 0; ks < kRows / 16; ++ks) {            // 16 pixel rows (two 8-row groups) per MMA
-          const uint64_t da = sw128_mn_desc(sa + ks * 2048, kPanel);
           const uint64_t db = sw128_mn_desc(sb + ks * 2048, kPanel);
-          tc_mma_bf16(tmem_base, da, db, idesc, !(first && ks == 0));
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint64_t da = sw128_mn_desc(sa + mt * 2 * kPanel + ks * 2048, kPanel);
+            tc_mma_bf16(tmem_base + (uint32_t)(mt * BNC), da, db, idesc, !(first && ks == 0));
+          }
         }
         tc_commit(&empty_bar[stage]);
       }
@@ -181,7 +189,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
       mbar_wait(done_bar, 0);
       tc_fence_after();
       const int quarter = warp & 3;
-      const int co = co_blk * 128 + quarter * 32 + lane;
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {
+      const int co = co_blk * (128 * MT) + mt * 128 + quarter * 32 + lane;
 #pragma unroll 1
       for (int ch = 0; ch < BNC / 32; ++ch) {
         const int pp = ch >> 1;
@@ -190,7 +200,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
         if (tap >= g.taps || ci0 >= g.C) continue;     // warp-uniform
         float* dst_row = dw + ((long)co * g.taps + tap) * g.C;
         uint32_t raw[32];
-        tc_ld32(tmem_base + (uint32_t)(ch * 32) + ((uint32_t)(quarter * 32) << 16), raw);
+        tc_ld32(tmem_base + (uint32_t)(mt * BNC + ch * 32) + ((uint32_t)(quarter * 32) << 16), raw);
         tc_wait_ld();
         if (co < g.Cout) {
           if (ci0 + 32 <= g.C) {
@@ -206,13 +216,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
           }
         }
       }
+      }
       tc_fence_before();
     }
   }
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tc_dealloc(tmem_base, BNC);
+    tc_dealloc(tmem_base, MT * BNC);
   }
 }
 
@@ -466,22 +477,22 @@ int tmap_rows64(CUtensorMap* map, const void* base, long rows, long cols, long l
   return 0;
 }
 
-template <int BNC>
+template <int BNC, int MT = 1>
 int launch_wgrad(const CUtensorMap& tdy, const CUtensorMap& tx, const WgGeom& g, float* dw, cudaStream_t stream) {
-  using L = WgLayout<BNC>;
+  using L = WgLayout<BNC, MT>;
   static bool attr_set = false;
   if (!attr_set) {
-    B2_CUDA_CHECK(cudaFuncSetAttribute(conv_wgrad_kernel<BNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kSmem));
+    B2_CUDA_CHECK(cudaFuncSetAttribute(conv_wgrad_kernel<BNC, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kSmem));
     attr_set = true;
   }
-  const int co_blocks = b2_ceil_div(g.Cout, 128);
+  const int co_blocks = b2_ceil_div(g.Cout, 128 * MT);
   const int units = g.tap_groups * co_blocks * g.ci_blocks;
   const int tiles = b2_ceil_div(g.Mp, kRows);
   int splits = b2_num_sms() / units;          // one CTA per SM and a single wave
   if (splits > tiles) splits = tiles;
   if (splits < 1) splits = 1;
   dim3 grid((unsigned)(g.tap_groups * splits), (unsigned)(co_blocks * g.ci_blocks));
-  conv_wgrad_kernel<BNC><<<grid, kWgThreads, L::kSmem, stream>>>(tdy, tx, g, dw);
+  conv_wgrad_kernel<BNC, MT><<<grid, kWgThreads, L::kSmem, stream>>>(tdy, tx, g, dw);
   B2_LAUNCH_CHECK("conv_wgrad_kernel");
   return 0;
 }
@@ -540,6 +551,10 @@ B2_API int b2_conv2d_wgrad_nhwc_bf16(const void* x, int Nimg, int H, int W, int 
   WgGeom g = {plain ? 0 : 1, P, Q, S, stride, -pad, -pad, taps, (int)Ml, Cout, C, grouped ? 1 : b2_ceil_div(C, bnc),
               tpg,  grouped ? C / 64 : bnc / 64, b2_ceil_div(taps, tpg)};
   cudaStream_t st = (cudaStream_t)stream;
+  // wide layers: 256 output channels per CTA (two accumulators share the x panels) while enough work units remain to
+  // fill the machine with pixel splits
+  static const bool no_mt2 = getenv("B2_WGRAD_NO_MT2") != nullptr;
+  if (bnc == 256 && Cout >= 256 && !no_mt2) return launch_wgrad<256, 2>(tdy, tx, g, dw, st);
   switch (bnc) {
     case 256: return launch_wgrad<256>(tdy, tx, g, dw, st);
     case 128: return launch_wgrad<128>(tdy, tx, g, dw, st);
