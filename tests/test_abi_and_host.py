@@ -98,6 +98,16 @@ def test_state_dict_layout_matches_reference_checkpoints():
     assert ck["fc.2.weight"].shape == (1, 2 * 56 * 4) and "adapt.weight" in ck
     with pytest.raises(NotImplementedError):
         vc.LRCN(4, 3, 32, 8, cnn_backbone="efficientnet_b1")
+    # the other torchvision families the reference configures: densenet121 (lrcn.py:27 default; classifier -> Identity) and
+    # mobilenet_v2 (automation.py:28; Sequential classifier, models.py:138-140)
+    dn = vc.CrimeLRCN(3, 2, 8, 16, cnn_backbone="densenet121", finetune=True, rnn_layers=1)
+    assert dn.adapt.in_features == 1024 and all(p.requires_grad for p in dn.cnn_backbone.parameters())   # FINETUNE: nothing frozen
+    assert "cnn_backbone.features.denseblock4.denselayer16.conv2.weight" in dn.state_dict()
+    assert type(dn._runner).__name__ == "DenseNetRunner"
+    mb = vc.LRCN(4, 3, 32, 8, cnn_backbone="mobilenet_v2")
+    assert mb.adapt1.in_features == 1280 and not any(p.requires_grad for p in mb.cnn_backbone.parameters())
+    assert type(mb._runner).__name__ == "MobileNetRunner" and "cnn_backbone.features.18.0.weight" in mb.state_dict()
+    assert vc.count_parameters(mb)[1] == sum(p.numel() for p in mb.cnn_backbone.parameters())
     mam = vc.LRCN(4, 3, 32, 8, cnn_backbone="resnet18", rnn_type="mamba", rnn_layers=2).state_dict()   # models.py:159-164
     assert mam["rnn.1.mixer.A_log"].shape == (16, 32) and mam["rnn.0.mixer.in_proj.weight"].shape == (32, 8)
     assert mam["rnn.0.mixer.conv1d.weight"].shape == (16, 1, 3) and mam["rnn.0.mixer.x_proj.weight"].shape == (96, 16)
