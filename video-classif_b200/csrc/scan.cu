@@ -300,6 +300,12 @@ mul_silu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ a, c
 // sequence are recomputed into a global workspace states[b, d, t, n] (L * N floats per thread), then the steps are
 // walked backwards.  du / ddelta [B, L, D] are written; dA_log [D, N] (through A = -exp(A_log): dA_log = dA * A),
 // dB / dC [B, L, N] are accumulated with atomics (caller zeroes them).
+// One thread per (batch, chunk, channel, group of 4 states): a channel's N states are spread over G = N / 4 adjacent lanes (more
+// threads in flight than one-thread-per-channel: the BPTT is a serial chain per thread and latency bound), a warp holds
+// 32 / G channels.  Per step the lanes of a channel combine their partial d(delta) / d(u) with shuffles; the dB / dC
+// contributions are summed over the warp's channels with shuffles when those channels share (batch, t) -- D % (32 / G) == 0 --
+// and leave as one atomic per warp and state (per-thread atomics put D threads on each of the B*L*N addresses).
+// Chunks are independent (the state is reset at their start): grid.y = chunks.  states[b][t][d][n] is the workspace.
 template <int N>
 __global__ void __launch_bounds__(128)
 selective_scan_bwd_kernel(const float* __restrict__ u, const float* __restrict__ delta, const float* __restrict__ A,
@@ -307,87 +313,105 @@ selective_scan_bwd_kernel(const float* __restrict__ u, const float* __restrict__
                           float* __restrict__ states, float* __restrict__ du, float* __restrict__ ddelta,
                           float* __restrict__ dA_out, float* __restrict__ dB, float* __restrict__ dC, int batch, int L, int D,
                           int chunk, int reverse, int a_is_log) {
-  // one thread per (batch, chunk, channel): chunks are independent (the state is reset at their start), grid.y = chunks
-  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  // D % 32 == 0: a warp's 32 channels share (batch, t), so the dB / dC contributions are summed with shuffles and leave as
-  // ONE atomic per warp (per-thread atomics put D threads on each of the B*L*N addresses: 21 ms at B 8, L 3136, D 2048)
-  const bool warp_reduce = (D & 31) == 0;
-  if (!warp_reduce && idx >= (long)batch * D) return;
-  const bool live = idx < (long)batch * D;
-  const long idc = live ? idx : (long)batch * D - 1;     // idle lanes of the last warp shadow a valid thread, contribute 0
-  const int d = (int)(idc % D);
-  const long b = idc / D;
+  constexpr int G = N / 4;                 // lanes per channel
+  constexpr int CW = 32 / G;               // channels per warp
+  const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long total = (long)batch * D * G;
+  const bool warp_reduce = (D % CW) == 0;  // the warp's channels share the batch index
+  const bool live = tid < total;
+  const long tc = live ? tid : total - 1;  // idle lanes of the last warp shadow a valid thread and contribute nothing
+  const int gq = (int)(tc % G);            // which 4 states
+  const long idx = tc / G;                 // (batch, channel)
+  const int d = (int)(idx % D);
+  const long b = idx / D;
   const long row0 = b * L;
-  const int lane = threadIdx.x & 31;
+  const int n0 = gq * 4;
   const int t_begin = blockIdx.y * chunk;
   const int t_end = min(L, t_begin + chunk);
-  float a[N], x[N];
+  float a[4], x[4];
 #pragma unroll
-  for (int n = 0; n < N; ++n) {
-    a[n] = A[(long)d * N + n];
+  for (int n = 0; n < 4; ++n) {
+    a[n] = A[(long)d * N + n0 + n];
     x[n] = 0.f;
   }
-  // states[b][t][d][n]: consecutive threads (channels) write consecutive N-float blocks
-  float* st = states + (row0 * D + d) * N;
+  float* st = states + (row0 * D + d) * N + n0;
   const long t_stride = (long)D * N;
   for (int t = t_begin; t < t_end; ++t) {            // forward recompute (same arithmetic as the forward kernel)
     const int ts = reverse ? L - 1 - t : t;
     const float dl = delta[(row0 + ts) * D + d];
     const float duv = dl * u[(row0 + ts) * D + d];
+    const float4 b4 = *reinterpret_cast<const float4*>(Bm + (row0 + t) * N + n0);
+    const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-    for (int n = 0; n < N; ++n) {
-      x[n] = fmaf(ex2_approx(dl * a[n] * kLog2e), x[n], duv * Bm[(row0 + t) * N + n]);
-      if (live) st[t * t_stride + n] = x[n];
-    }
+    for (int n = 0; n < 4; ++n) x[n] = fmaf(ex2_approx(dl * a[n] * kLog2e), x[n], duv * bb[n]);
+    if (live) *reinterpret_cast<float4*>(st + t * t_stride) = make_float4(x[0], x[1], x[2], x[3]);
   }
-  float g[N], dAacc[N];                               // g: gradient flowing into x_t from step t+1
+  float g[4], dAacc[4];                               // g: gradient flowing into x_t from step t+1
 #pragma unroll
-  for (int n = 0; n < N; ++n) g[n] = dAacc[n] = 0.f;
+  for (int n = 0; n < 4; ++n) g[n] = dAacc[n] = 0.f;
   for (int t = t_end - 1; t >= t_begin; --t) {
     const int ts = reverse ? L - 1 - t : t;
     const float dl = delta[(row0 + ts) * D + d];
     const float uv = u[(row0 + ts) * D + d];
     const float dyv = dy[(row0 + ts) * D + d];
-    float ddl = 0.f, duv = 0.f;
+    const float4 x4 = *reinterpret_cast<const float4*>(st + t * t_stride);
+    const float4 p4 = t > t_begin ? *reinterpret_cast<const float4*>(st + (t - 1) * t_stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 b4 = *reinterpret_cast<const float4*>(Bm + (row0 + t) * N + n0);
+    const float4 c4 = *reinterpret_cast<const float4*>(Cm + (row0 + t) * N + n0);
+    const float xt[4] = {x4.x, x4.y, x4.z, x4.w}, xp[4] = {p4.x, p4.y, p4.z, p4.w};
+    const float bt[4] = {b4.x, b4.y, b4.z, b4.w}, ct[4] = {c4.x, c4.y, c4.z, c4.w};
+    float ddl = 0.f, duv = 0.f, vc[4], vb[4];
 #pragma unroll
-    for (int n = 0; n < N; ++n) {
-      const float xt = st[t * t_stride + n];
-      const float xp = t > t_begin ? st[(t - 1) * t_stride + n] : 0.f;
-      const float bt = Bm[(row0 + t) * N + n];
-      const float ct = Cm[(row0 + t) * N + n];
+    for (int n = 0; n < 4; ++n) {
       const float at = ex2_approx(dl * a[n] * kLog2e);
-      const float dx = fmaf(dyv, ct, g[n]);
-      float vc = live ? dyv * xt : 0.f;
-      float vb = live ? dx * dl * uv : 0.f;
-      if (warp_reduce) {
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-          vc += __shfl_xor_sync(0xffffffffu, vc, off);
-          vb += __shfl_xor_sync(0xffffffffu, vb, off);
-        }
-        if (lane == 0) {
-          atomicAdd(dC + (row0 + t) * N + n, vc);
-          atomicAdd(dB + (row0 + t) * N + n, vb);
-        }
-      } else {
-        atomicAdd(dC + (row0 + t) * N + n, vc);
-        atomicAdd(dB + (row0 + t) * N + n, vb);
-      }
-      const float da = dx * xp;                       // gradient of a_t = exp(delta_t A)
+      const float dx = fmaf(dyv, ct[n], g[n]);
+      const float da = dx * xp[n];                    // gradient of a_t = exp(delta_t A)
       ddl = fmaf(da * at, a[n], ddl);
-      ddl = fmaf(dx * bt, uv, ddl);
+      ddl = fmaf(dx * bt[n], uv, ddl);
       dAacc[n] = fmaf(da * at, dl, dAacc[n]);
-      duv = fmaf(dx * dl, bt, duv);
+      duv = fmaf(dx * dl, bt[n], duv);
+      vc[n] = live ? dyv * xt[n] : 0.f;
+      vb[n] = live ? dx * dl * uv : 0.f;
       g[n] = at * dx;
     }
-    if (live) {
+    // d(delta), d(u): sum over the channel's G lanes
+#pragma unroll
+    for (int off = 1; off < G; off <<= 1) {
+      ddl += __shfl_xor_sync(0xffffffffu, ddl, off);
+      duv += __shfl_xor_sync(0xffffffffu, duv, off);
+    }
+    if (live && gq == 0) {
       du[(row0 + ts) * D + d] = duv;
       ddelta[(row0 + ts) * D + d] = ddl;
+    }
+    // dB, dC: sum over the warp's channels (lanes with the same state group), one atomic per warp and state
+    if (warp_reduce) {
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+#pragma unroll
+        for (int off = G; off < 32; off <<= 1) {
+          vc[n] += __shfl_xor_sync(0xffffffffu, vc[n], off);
+          vb[n] += __shfl_xor_sync(0xffffffffu, vb[n], off);
+        }
+      }
+      if ((threadIdx.x & 31) < G) {
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+          atomicAdd(dC + (row0 + t) * N + n0 + n, vc[n]);
+          atomicAdd(dB + (row0 + t) * N + n0 + n, vb[n]);
+        }
+      }
+    } else if (live) {
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        atomicAdd(dC + (row0 + t) * N + n0 + n, vc[n]);
+        atomicAdd(dB + (row0 + t) * N + n0 + n, vb[n]);
+      }
     }
   }
   if (live) {
 #pragma unroll
-    for (int n = 0; n < N; ++n) atomicAdd(dA_out + (long)d * N + n, a_is_log ? dAacc[n] * a[n] : dAacc[n]);
+    for (int n = 0; n < 4; ++n) atomicAdd(dA_out + (long)d * N + n0 + n, a_is_log ? dAacc[n] * a[n] : dAacc[n]);
   }
 }
 
@@ -444,7 +468,7 @@ B2_API int b2_selective_scan_bwd(const float* u, const float* delta, const float
   const int chunks = b2_ceil_div(L, chunk);
   B2_ARG_CHECK(chunks <= 65535, "b2_selective_scan_bwd: too many chunks");
   B2_ARG_CHECK(!(reverse && chunks > 1), "b2_selective_scan_bwd: the reference has no chunk-reset scan in the reverse direction");
-  const long threads = (long)batch * D;
+  const long threads = (long)batch * D * (N / 4);       // one lane per 4 states
   const dim3 grid((unsigned)((threads + 127) / 128), (unsigned)chunks);
   cudaStream_t st = (cudaStream_t)stream;
 #define B2_SCAN_BWD(NN)                                                                                          \
