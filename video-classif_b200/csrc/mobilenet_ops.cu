@@ -52,6 +52,28 @@ __device__ __forceinline__ void flush_stats(float (&s1)[8], float (&s2)[8], int 
   }
 }
 
+// same, for kernels whose thread t owns channel group t % groups
+__device__ __forceinline__ void flush_stats_local(float (&s1)[8], float (&s2)[8], int groups, bool active, float* red,
+                                                  float* __restrict__ sum, float* __restrict__ sumsq) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red[threadIdx.x * 8 + j] = active ? s1[j] : 0.f;
+    red[256 * 8 + threadIdx.x * 8 + j] = active ? s2[j] : 0.f;
+  }
+  __syncthreads();
+  const int C = groups * 8;
+  for (int i = threadIdx.x; i < C; i += 256) {
+    const int gq = i >> 3, j = i & 7;
+    float a = 0.f, b = 0.f;
+    for (int t = gq; t < 256; t += groups) {
+      a += red[t * 8 + j];
+      b += red[256 * 8 + t * 8 + j];
+    }
+    atomicAdd(sum + i, a);
+    atomicAdd(sumsq + i, b);
+  }
+}
+
 // thread = (output pixel, 8 of the 32 output channels); grid stride is a multiple of 4 so the channel group is fixed
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -123,29 +145,45 @@ dwconv3x3_kernel(const bf16* __restrict__ x, const float* __restrict__ scale, co
                  int H, int W, int C, int P, int Q) {
   constexpr int TW = STRIDE == 1 ? 4 : 2;
   constexpr int NIN = (TW - 1) * STRIDE + 3;
-  __shared__ float red[2 * 256 * 8];
-  const int groups = C >> 3;
-  const int strips = (Q + TW - 1) / TW;
-  const long total = (long)N * P * strips * groups;
-  const long i0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int grp = (int)(i0 % groups);
-  float wk[9][8], sc[8], sh[8], s1[8], s2[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = grp * 8 + j;
-#pragma unroll
-    for (int t = 0; t < 9; ++t) wk[t][j] = bf16_round(w[c * 9 + t]);
-    sc[j] = scale != nullptr ? scale[c] : 1.f;
-    sh[j] = scale != nullptr ? shift[c] : 0.f;
-    s1[j] = s2[j] = 0.f;
+  // filter taps [9][C] and BatchNorm coefficients [2][C] in shared memory (72 + 16 registers per thread otherwise: the kernel
+  // spilled at two blocks per SM); the same bytes are the statistics scratch after the main loop.  C <= 1024.
+  __shared__ __align__(16) float sm[11 * 1024];
+  float* wsm = sm;
+  float* ssm = sm + 9 * C;
+  for (int i = threadIdx.x; i < 9 * C; i += 256) {
+    const int t = i / C, c = i - t * C;
+    wsm[i] = bf16_round(w[c * 9 + t]);
   }
   const bool tf = scale != nullptr;
-  for (long i = i0; i < total; i += (long)gridDim.x * blockDim.x) {
-    long px = i / groups;
+  for (int i = threadIdx.x; i < C; i += 256) {
+    ssm[i] = tf ? scale[i] : 1.f;
+    ssm[C + i] = tf ? shift[i] : 0.f;
+  }
+  __syncthreads();
+  const unsigned groups = (unsigned)(C >> 3);
+  const unsigned strips = (unsigned)((Q + TW - 1) / TW);
+  const unsigned total = (unsigned)N * (unsigned)P * strips * groups;       // < 2^31 (checked by the launcher)
+  // Each block owns a CONTIGUOUS range of items (order: image, output row, strip, channel group) = a band of consecutive
+  // rows of one image, so the 3x vertical re-use of the input rows hits this SM's L1 instead of going to L2 (with a
+  // grid-stride order the kernel sat at the L2 -> SM limit: 4.5 loads per input pixel).  Threads step by S = the largest
+  // multiple of the group count <= 256, so a thread keeps its channel group (register-resident statistics).
+  const unsigned S = 256u / groups * groups;
+  unsigned chunk = (total + gridDim.x - 1) / gridDim.x;
+  chunk = (chunk + S - 1) / S * S;
+  const unsigned begin = blockIdx.x * chunk;
+  const unsigned end = min(total, begin + chunk);
+  const bool worker = threadIdx.x < S;
+  const int grp = (int)(threadIdx.x % groups);                              // begin is a multiple of S, S of groups
+  const float* wg = wsm + grp * 8;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+  for (unsigned i = begin + threadIdx.x; worker && i < end; i += S) {
+    unsigned px = i / groups;
     const int qs = (int)(px % strips);
     px /= strips;
-    const int p = (int)(px % P);
-    const long n = px / P;
+    const int p = (int)(px % (unsigned)P);
+    const long n = px / (unsigned)P;
     const int q0 = qs * TW;
     const int w0 = q0 * STRIDE - 1;
     float acc[TW][8];
@@ -153,7 +191,7 @@ dwconv3x3_kernel(const bf16* __restrict__ x, const float* __restrict__ scale, co
     for (int t = 0; t < TW; ++t)
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
-#pragma unroll
+#pragma unroll 1
     for (int r = 0; r < 3; ++r) {
       const int h = p * STRIDE - 1 + r;
       const bool row_ok = h >= 0 && h < H;
@@ -164,6 +202,21 @@ dwconv3x3_kernel(const bf16* __restrict__ x, const float* __restrict__ scale, co
       for (int c = 0; c < NIN; ++c) {
         ok[c] = row_ok && (w0 + c) >= 0 && (w0 + c) < W;
         u[c] = ok[c] ? *reinterpret_cast<const uint4*>(xrow + (long)(w0 + c) * C) : make_uint4(0u, 0u, 0u, 0u);
+      }
+      float wk[3][8];
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const float4 w0v = *reinterpret_cast<const float4*>(wg + (r * 3 + s) * C);
+        const float4 w1v = *reinterpret_cast<const float4*>(wg + (r * 3 + s) * C + 4);
+        wk[s][0] = w0v.x; wk[s][1] = w0v.y; wk[s][2] = w0v.z; wk[s][3] = w0v.w;
+        wk[s][4] = w1v.x; wk[s][5] = w1v.y; wk[s][6] = w1v.z; wk[s][7] = w1v.w;
+      }
+      float sc[8], sh[8];
+      if (tf) {
+        const float4 a0 = *reinterpret_cast<const float4*>(ssm + grp * 8), a1 = *reinterpret_cast<const float4*>(ssm + grp * 8 + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(ssm + C + grp * 8), b1 = *reinterpret_cast<const float4*>(ssm + C + grp * 8 + 4);
+        sc[0] = a0.x; sc[1] = a0.y; sc[2] = a0.z; sc[3] = a0.w; sc[4] = a1.x; sc[5] = a1.y; sc[6] = a1.z; sc[7] = a1.w;
+        sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
       }
 #pragma unroll
       for (int c = 0; c < NIN; ++c) {
@@ -183,7 +236,7 @@ dwconv3x3_kernel(const bf16* __restrict__ x, const float* __restrict__ scale, co
           const int s = c - t * STRIDE;             // compile-time after unrolling
           if (s >= 0 && s < 3) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(a[j], wk[r * 3 + s][j], acc[t][j]);
+            for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(a[j], wk[s][j], acc[t][j]);
           }
         }
       }
@@ -206,7 +259,10 @@ dwconv3x3_kernel(const bf16* __restrict__ x, const float* __restrict__ scale, co
       }
     }
   }
-  if (sum != nullptr) flush_stats(s1, s2, grp, groups, true, red, sum, sumsq);
+  if (sum != nullptr) {
+    __syncthreads();                                 // everyone is done with the filter taps: reuse the bytes
+    flush_stats_local(s1, s2, (int)groups, worker, sm, sum, sumsq);
+  }
 }
 
 unsigned blocks_for(long items, int groups) {
@@ -241,12 +297,13 @@ B2_API int b2_mbv2_stem_conv(const void* x, int in_bf16, const float* w, void* y
 B2_API int b2_dwconv3x3_bn_nhwc_bf16(const void* x, const float* scale, const float* shift, int act, const float* w, void* y,
                                      float* sum, float* sumsq, int N, int H, int W, int C, int stride, void* stream) {
   B2_ARG_CHECK(x && w && y && N > 0 && H > 0 && W > 0, "b2_dwconv3x3_bn_nhwc_bf16: null pointer or empty");
-  B2_ARG_CHECK(C % 8 == 0 && C >= 8 && C <= 2048, "b2_dwconv3x3_bn_nhwc_bf16: C must be a multiple of 8 in [8, 2048]");
+  B2_ARG_CHECK(C % 8 == 0 && C >= 8 && C <= 1024, "b2_dwconv3x3_bn_nhwc_bf16: C must be a multiple of 8 in [8, 1024]");
   B2_ARG_CHECK(stride == 1 || stride == 2, "b2_dwconv3x3_bn_nhwc_bf16: stride 1 or 2");
   B2_ARG_CHECK((scale == nullptr) == (shift == nullptr) && (sum == nullptr) == (sumsq == nullptr),
                "b2_dwconv3x3_bn_nhwc_bf16: scale/shift and sum/sumsq go in pairs");
   const int P = (H + 2 - 3) / stride + 1, Q = (W + 2 - 3) / stride + 1;
   const int groups = C / 8;
+  B2_ARG_CHECK((long)N * P * Q * groups < (1L << 31), "b2_dwconv3x3_bn_nhwc_bf16: too many work items");
   cudaStream_t st = (cudaStream_t)stream;
   if (stride == 1)
     dwconv3x3_kernel<1><<<blocks_for((long)N * P * ((Q + 3) / 4) * groups, groups), 256, 0, st>>>(
