@@ -229,3 +229,19 @@ def test_reference_backbone_checkpoints_roundtrip(tmp_path):
     m = vc.load_reference_checkpoint(p)
     assert type(m).__name__ == "CrimeLRCN" and len(m.fc) == 3
     _same_state(m.state_dict(), ref.state_dict())
+    # the crime script's own default: densenet121 with FINETUNE = True (nothing frozen) -- the trainable flags survive
+    Cd, _ = refload.crime_lrcn(CONF_RNN_LAYER=1, CONF_CNN_BACKBONE="densenet121", CONF_FINETUNE=True)
+    ref = Cd(3, 2, 8, 16, cnn_backbone="densenet121")
+    p = str(tmp_path / "crime_dn.pt")
+    MG.save_as(ref, p, "__main__")
+    m = vc.load_reference_checkpoint(p)
+    assert type(m).__name__ == "CrimeLRCN" and m.backbone == "densenet121" and type(m._runner).__name__ == "DenseNetRunner"
+    _same_state(m.state_dict(), ref.state_dict())
+    assert all(q.requires_grad for q in m.cnn_backbone.parameters()) == all(q.requires_grad for q in ref.cnn_backbone.parameters())
+    mm = refload.medsos_models(CONF_RNN_LAYER=2, CONF_CLASSIF_MODE="multiclass", CONF_DROPOUT=0.25)
+    ref = mm.LRCN(4, 3, 16, 8, cnn_backbone="mobilenet_v2", rnn_type="lstm", rnn_out="all", bidirectional=False)
+    p = str(tmp_path / "medsos_mb.pt")
+    MG.save_as(ref, p, "models", extra=(mm.ResidualBlock, mm.ParallelMamba, mm.RMSNorm))
+    m = vc.load_reference_checkpoint(p)
+    assert type(m).__name__ == "LRCN" and m.backbone == "mobilenet_v2" and type(m._runner).__name__ == "MobileNetRunner"
+    _same_state(m.state_dict(), ref.state_dict())
