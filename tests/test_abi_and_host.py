@@ -245,3 +245,26 @@ def test_reference_backbone_checkpoints_roundtrip(tmp_path):
     m = vc.load_reference_checkpoint(p)
     assert type(m).__name__ == "LRCN" and m.backbone == "mobilenet_v2" and type(m._runner).__name__ == "MobileNetRunner"
     _same_state(m.state_dict(), ref.state_dict())
+
+
+def test_trainable_prefix_boundaries_host_logic():
+    """freeze_until_layer semantics (lrcn.py:275-283: the first k+1 entries of named_parameters() frozen) -> which block the
+    autograd path starts at; the DenseNet trunk's parameter list excludes the stem (it has its own autograd node)."""
+    import video_classif_b200 as vc
+    from video_classif_b200 import backbone_train as BT, densenet_train as DT
+    m = vc.CrimeLRCN(3, 2, 8, 16, cnn_backbone="resnet18", freeze_until_layer=None, rnn_layers=1)
+    assert BT.first_trainable_block(m.cnn_backbone) is None                       # everything frozen
+    m = vc.CrimeLRCN(3, 2, 8, 16, cnn_backbone="resnet18", finetune=True, rnn_layers=1)
+    assert BT.first_trainable_block(m.cnn_backbone) == ("stem",)                  # FINETUNE: nothing frozen
+    names = [n for n, _ in m.cnn_backbone.named_parameters()]
+    k = names.index("layer3.0.conv1.weight")
+    m = vc.CrimeLRCN(3, 2, 8, 16, cnn_backbone="resnet18", freeze_until_layer=k - 1, rnn_layers=1)
+    assert BT.first_trainable_block(m.cnn_backbone) == (3, 0)
+    k = names.index("layer2.1.bn2.weight")                                        # boundary inside a block
+    m = vc.CrimeLRCN(3, 2, 8, 16, cnn_backbone="resnet18", freeze_until_layer=k - 1, rnn_layers=1)
+    assert BT.first_trainable_block(m.cnn_backbone) == (2, 1)
+    assert not m.cnn_backbone.layer2[1].conv2.weight.requires_grad and m.cnn_backbone.layer2[1].bn2.weight.requires_grad
+    dn = vc.CrimeLRCN(3, 2, 8, 16, cnn_backbone="densenet121", finetune=True, rnn_layers=1)
+    tn, tp = DT._trunk_params(dn.cnn_backbone)
+    assert len(tn) == len(tp) == len(list(dn.cnn_backbone.parameters())) - 3     # conv0.weight, norm0.{weight,bias}
+    assert tn[0] == "features.denseblock1.denselayer1.norm1.weight" and tn[-1] == "features.norm5.bias"
