@@ -13,7 +13,9 @@ topology and hyper-parameters are read back from the placeholder's attributes an
 video_classif_b200 module is constructed and the weights go in through `load_state_dict` (same keys, same shapes).
 `state_dict` checkpoints (lrcn/lrcn.py:347, rgb_lrcn.py:302) need none of this: `model.load_state_dict(torch.load(p))`.
 
-Host-side only; nothing here touches the GPU.
+Host-side only; nothing here touches the GPU.  Trust model: like the reference's own `torch.load(path)` this unpickles
+arbitrary Python objects (`weights_only=False`) -- load only checkpoints you wrote; classes outside torch / torchvision /
+numpy that cannot be imported are never executed, they become inert placeholders.
 """
 from __future__ import annotations
 
