@@ -56,6 +56,16 @@ def conv_wgrad(x, dy, R, S, stride, pad):
     """x [N,H,W,C] bf16, dy [N,P,Q,Cout] bf16 -> dW [Cout,R,S,C] fp32."""
     N, H, W, C = x.shape
     Cout = dy.shape[-1]
+    plain = R == 1 and S == 1 and stride == 1 and pad == 0
+    PQ = dy.shape[1] * dy.shape[2]
+    if not plain and (N * PQ) % 64 != 0:
+        # The kernel reduces over 64-pixel tiles.  In im2col mode the box of a partial last tile runs past the last image;
+        # its dy rows are zero (tiled-mode zero fill) but 0 x (whatever the x rows hold) must not meet a NaN bit pattern, so
+        # such (tiny-map) calls are padded with all-zero images until the pixel count is a whole number of tiles.
+        k = next(k for k in range(1, 65) if ((N + k) * PQ) % 64 == 0)
+        x = torch.cat([x, x.new_zeros((k, H, W, C))])
+        dy = torch.cat([dy, dy.new_zeros((k,) + tuple(dy.shape[1:]))])
+        N += k
     dw = torch.zeros((Cout, R, S, C), device=x.device, dtype=F32)
     call("b2_conv2d_wgrad_nhwc_bf16", x.data_ptr(), N, H, W, C, dy.data_ptr(), Cout, R, S, stride, pad, dw.data_ptr(),
          stream_ptr())
