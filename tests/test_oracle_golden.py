@@ -249,3 +249,25 @@ def test_oracle_backbone_configs_vs_torchvision(arch):
         # train mode: 12 samples per channel in the last stage of a 100-layer random-init network amplify fp32 summation-order
         # differences (3.8e-4 for resnet101); eval mode (fixed affine) pins the tables tightly
         assert err(got, want) < (2e-3 if train else 1e-4), (arch, train)
+
+
+@pytest.mark.skipif(not refload.available(), reason="/root/reference only exists in the authoring container")
+def test_oracle_and_module_surface_vs_live_rgb_lrcn():
+    """lrcn/rgb_lrcn.py:168-263 (the multiclass sibling of the crime model: one `adapt`, biLSTM stored as `lstm`, one `fc`): the
+    oracle's forward against the live reference class, and the replacement module's constructor / state_dict against it."""
+    import video_classif_b200 as vc
+    Rgb, g0 = refload.rgb_lrcn(CONF_CNN_BACKBONE="resnet18", CONF_RNN_LAYER=2, CONF_FINETUNE=False)
+    torch.manual_seed(29)
+    ref = Rgb(5, 3, 12, 16, cnn_backbone="resnet18").train()
+    x = torch.rand(2, 3, 3, 32, 32)
+    sd = {k: v.detach().clone() for k, v in ref.state_dict().items()}
+    want = ref(x)
+    got, _ = O.simple_lrcn_forward(sd, x, "resnet18", 12, 2, adapt_names=("adapt",), rnn_prefix="lstm.")
+    assert err(got, want) < 1e-4
+    torch.manual_seed(29)
+    mine = vc.CrimeLRCN(5, 3, 12, 16, cnn_backbone="resnet18", rnn_layers=2, classif_mode="multiclass")
+    mine_sd = mine.state_dict()
+    assert set(mine_sd) == set(sd)
+    for k, v in sd.items():
+        assert mine_sd[k].shape == v.shape and torch.equal(mine_sd[k], v), k        # same construction order -> same seeded init
+    assert [n for n, p in mine.named_parameters() if p.requires_grad] == [n for n, p in ref.named_parameters() if p.requires_grad]
