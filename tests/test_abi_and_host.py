@@ -268,3 +268,13 @@ def test_trainable_prefix_boundaries_host_logic():
     tn, tp = DT._trunk_params(dn.cnn_backbone)
     assert len(tn) == len(tp) == len(list(dn.cnn_backbone.parameters())) - 3     # conv0.weight, norm0.{weight,bias}
     assert tn[0] == "features.denseblock1.denselayer1.norm1.weight" and tn[-1] == "features.norm5.bias"
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/b200lrcn.h is the drop-in boundary: it must compile as C99 (extern "C" guards, no C++ types), so that any
+    language with a C FFI can bind it."""
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "b200lrcn.h"\nint main(void) { return b2_abi_version() == 0; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-Wno-comment", "-fsyntax-only", "-I",
+                        os.path.join(ROOT, "include"), str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
