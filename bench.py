@@ -36,7 +36,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-clips", type=int, default=8, help="clips per step of the CPU arms (bounded sample)")
+    ap.add_argument("--cpu-clips", type=int, default=0, help="clips per step of the CPU arms (0 = the workload's 64)")
+    ap.add_argument("--cpu-budget", type=float, default=280.0, help="wall-clock bound (s) of the --impl reference run")
+    ap.add_argument("--no-torch-baseline", action="store_true", help="skip the stock-PyTorch-on-this-GPU yardstick")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs only)")
@@ -52,6 +54,16 @@ def peaks():
         d = json.load(open(p))
         return d["bf16_tflops_sustained"], d["hbm_gbs"], "measured (MEASURED_PEAKS.json, sustained)"
     return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of the dominant kernels, from the committed ncu summary of this build
+    (profiles/ncu_traffic.json, written by tools/ncu_traffic.py from an ncu capture of `bench.py`); {} when absent."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
 
 
 class ClockSampler(threading.Thread):
@@ -103,65 +115,159 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arms: the oracle port of the reference train step on the host cores
+# reference arms: the reference's OWN LRCN class (medsos_lrcn/src/models.py:121-234, staged unmodified into
+# oracle/_ref by oracle/build_ref.py) driven by the inner body of its train loop (train_eval.py:20-43)
 # ------------------------------------------------------------------------------------------------
 
-def cpu_reference_step_rate(clips, steps, warmup):
-    """zero_grad -> forward -> CE -> backward -> Adam of the reference topology, fp32, torch CPU
-    kernels with every host thread (the reference's own execution engine), on `clips` clips/step."""
+def reference_model_and_kind():
+    """(model, kind): the reference class when its sources are reachable (kind "reference"), else None."""
     import torch
-    import video_classif_b200 as vc
-    from oracle import lrcn_oracle as O
+    from oracle import refload
+    W = WORKLOAD
+    if not refload.available():
+        return None, "port"
+    mm = refload.medsos_models(CONF_RNN_LAYER=W["rnn_layers"], CONF_RNN_OUT="all", CONF_CLASSIF_MODE="multiclass",
+                               CONF_DROPOUT=0.25, CONF_BIDIR=False, CONF_RNN_TYPE="lstm")
+    torch.manual_seed(0)
+    m = mm.LRCN(W["num_classes"], W["frames"], W["hidden"], W["rnn_input"], cnn_backbone="resnet50", rnn_type="lstm",
+                rnn_out="all", bidirectional=False)       # random init: no network for the ImageNet weights
+    return m, "reference"
+
+
+def reference_train_step(model, opt, x, y):
+    """train_eval.py:20-43 without the per-step `.item()` host syncs (they only feed the epoch print)."""
+    import torch
+    opt.zero_grad()
+    out = model(x)
+    loss = torch.nn.functional.cross_entropy(out, y)        # nn.CrossEntropyLoss(), main.py:147
+    _, pred = torch.max(out, 1)
+    loss.backward()
+    opt.step()
+    return loss, pred
+
+
+def cpu_reference_step_rate(clips, steps, warmup, budget_s=None):
+    """The reference train step on the host cores, fp32, every host thread, `clips` clips per step.
+    Returns (clips/s, median s/step, cores, kind, steps actually timed)."""
+    import torch
     W = WORKLOAD
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    torch.manual_seed(0)
-    shell = vc.LRCN(W["num_classes"], W["frames"], W["hidden"], W["rnn_input"], cnn_backbone="resnet50",
-                    rnn_layers=W["rnn_layers"], dropout=0.0)        # parameter container only (CPU)
-    sd = {k: v.detach().clone() for k, v in shell.state_dict().items()}
-    train_keys = [k for k, p in shell.named_parameters() if p.requires_grad]
-    for k in train_keys:
-        sd[k].requires_grad_(True)
-    opt = torch.optim.Adam([sd[k] for k in train_keys], lr=1e-4)
+    model, kind = reference_model_and_kind()
     g = torch.Generator().manual_seed(1234)
     x = torch.randint(0, 256, (clips, W["frames"], 3, W["size"], W["size"]), generator=g).float() / 255.0
     y = torch.randint(0, W["num_classes"], (clips,), generator=g)
+    if model is not None:
+        model.train()                                            # train_eval.py:12
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4)      # main.py:151
+        one = lambda: reference_train_step(model, opt, x, y)
+    else:                                                        # no staged reference: the oracle port
+        import video_classif_b200 as vc
+        from oracle import lrcn_oracle as O
+        torch.manual_seed(0)
+        shell = vc.LRCN(W["num_classes"], W["frames"], W["hidden"], W["rnn_input"], cnn_backbone="resnet50",
+                        rnn_layers=W["rnn_layers"], dropout=0.0)
+        sd = {k: v.detach().clone() for k, v in shell.state_dict().items()}
+        keys = [k for k, p in shell.named_parameters() if p.requires_grad]
+        for k in keys:
+            sd[k].requires_grad_(True)
+        opt = torch.optim.Adam([sd[k] for k in keys], lr=1e-4)
+
+        def one():
+            opt.zero_grad()
+            logits, ns = O.medsos_lrcn_forward(sd, x, "resnet50", W["hidden"], W["rnn_layers"], False)
+            O.cross_entropy_mean(logits, y).backward()
+            opt.step()
+            sd.update(ns)
     times = []
+    t_start = time.perf_counter()
+    done = 0
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        opt.zero_grad()
-        logits, ns = O.medsos_lrcn_forward(sd, x, "resnet50", W["hidden"], W["rnn_layers"], False)
-        loss = O.cross_entropy_mean(logits, y)
-        loss.backward()
-        opt.step()
-        for k, v in ns.items():
-            sd[k] = v
+        one()
+        dt = time.perf_counter() - t0
         if i >= warmup:
-            times.append(time.perf_counter() - t0)
+            times.append(dt)
+            done += 1
+        # bounded: never let the CPU arm run past its budget (the line reports the steps actually timed)
+        if budget_s is not None and done >= 1 and (time.perf_counter() - t_start) + dt > budget_s:
+            break
     times.sort()
     med = times[len(times) // 2]
-    return clips / med, med, cores
+    return clips / med, med, cores, kind, done
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 5))
-    warm = max(1, min(args.warmup, 2))
-    rate, sec, cores = cpu_reference_step_rate(args.cpu_clips, steps, warm)
     W = WORKLOAD
+    clips = args.cpu_clips or W["clips_per_gpu"]
+    rate, sec, cores, kind, done = cpu_reference_step_rate(clips, max(1, args.steps), max(0, args.warmup),
+                                                           budget_s=args.cpu_budget)
+    what = ("the reference's own LRCN class (medsos_lrcn/src/models.py:121-234, staged unmodified in oracle/_ref) + "
+            "train_eval.py:20-43 step" if kind == "reference" else "oracle port of the reference train step")
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "clips/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "steps": done, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{W['name']}: {W['frames']} frames x {W['size']}x{W['size']}, train step, "
-                               f"{args.cpu_clips} clips/step (bounded CPU sample of the 64-clip batch)"},
-        "cpu_baseline": {"value": rate, "unit": "clips/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.cpu_clips} clips/step x {steps} steps, oracle port (torch CPU fp32 kernels)"},
+        "config": {"workload": f"{W['name']}: {W['frames']} frames x {W['size']}x{W['size']}, {clips} clips/step, frozen "
+                               f"ResNet-50 (train-mode BN) + GELU/LN adapts + {W['rnn_layers']}-layer LSTM H={W['hidden']} + head, "
+                               "full train step (fwd, CE, bwd, Adam); BASELINE.json configs[1]",
+                   "global_batch": clips, "engine": "torch CPU fp32 kernels, all host threads"},
+        "cpu_baseline": {"value": rate, "unit": "clips/s", "cores": cores, "kind": kind,
+                         "sample": f"{clips} clips/step x {done} timed steps (median), {what}"},
         "e2e": {"value": rate, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def torch_gpu_baseline(dev, steps=8, warmup=3):
+    """Second yardstick (SURVEY.md:100): the reference's own LRCN class executed by STOCK PyTorch
+    (cuDNN / cuBLASLt) on the same B200, same shape, same train step, inputs resident in HBM -- fp32 as the reference
+    runs it, and bf16 autocast + channels_last as a tuned user would.  Returns a dict for the bench line."""
+    import torch
+    W = WORKLOAD
+    B, T, S = W["clips_per_gpu"], W["frames"], W["size"]
+    model, kind = reference_model_and_kind()
+    if model is None:
+        return {"unavailable": "reference sources not staged (oracle/_ref missing)"}
+    model = model.to(dev).train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    g = torch.Generator().manual_seed(1234)
+    xs = [(torch.randint(0, 256, (B, T, 3, S, S), generator=g).float() / 255.0).to(dev) for _ in range(2)]
+    ys = [torch.randint(0, W["num_classes"], (B,), generator=g).to(dev) for _ in range(2)]
+    out = {"what": "reference LRCN class (oracle/_ref) on stock PyTorch " + torch.__version__ + f", cuDNN {torch.backends.cudnn.version()}, "
+                   f"same GPU, {B} clips x {T} x {S}x{S}, train step, inputs resident", "unit": "clips/s"}
+
+    def timed(fn):
+        for i in range(warmup):
+            fn(i)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return B / (e0.elapsed_time(e1) / steps * 1e-3)
+
+    out["fp32"] = timed(lambda i: reference_train_step(model, opt, xs[i % 2], ys[i % 2]))
+    out["fp32_note"] = "torch defaults (cuDNN convs may use TF32, matmuls fp32)"
+    try:
+        model.cnn_backbone.to(memory_format=torch.channels_last)
+
+        def step_bf16(i):
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                # clips are [B,T,C,H,W]; the class folds them to frames itself, channels_last weights make cuDNN pick NHWC
+                return reference_train_step(model, opt, xs[i % 2], ys[i % 2])
+        out["bf16_autocast_channels_last"] = timed(step_bf16)
+    except Exception as e:      # the yardstick must never take the bench line down
+        out["bf16_autocast_channels_last"] = None
+        out["bf16_error"] = repr(e)[:200]
+    del model, opt, xs, ys
+    torch.cuda.empty_cache()
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -395,7 +501,9 @@ def run_ours(args):
         tot_fl = sum(f for _, _, f in events)
         achieved = tot_fl / (tot_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": achieved, "peak": tflops_peak, "unit": "TFLOP/s",
-                "frac": achieved / tflops_peak, "traffic": None, "kernel": "gemm_tc_kernel (tcgen05 GEMM + implicit-GEMM conv)",
+                "frac": achieved / tflops_peak, "traffic": (ncu_traffic().get("family") or {}).get("dram_bytes_per_launch"),
+                "traffic_note": (ncu_traffic().get("family") or {}).get("note"),
+                "kernel": "gemm_tc_kernel (tcgen05 GEMM + implicit-GEMM conv)",
                 "launches_per_step": len(events), "kernel_ms_per_step": tot_ms, "algorithmic_gflop_per_step": tot_fl / 1e9,
                 "share_of_step": tot_ms / ms_per_step, "peak_source": peak_src} if rank == 0 else None
         if roof is not None and post_events:
@@ -407,14 +515,23 @@ def run_ours(args):
                                   "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
                                   "launches_per_step": len(post_events), "kernel_ms_per_step": p_ms,
                                   "algorithmic_mb_per_step": p_b / 1e6,
-                                  "traffic": 885.3e6, "traffic_note": "dram read+write of the l1.conv3 launch (925 MB algorithmic), "
-                                  "ncu --set full, profiles/r01_ncu_full_v6.csv"}
+                                  "traffic": (ncu_traffic().get("hbm_member") or {}).get("dram_bytes_per_launch"),
+                                  "traffic_note": (ncu_traffic().get("hbm_member") or {}).get("note")}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, sec, cores = cpu_reference_step_rate(args.cpu_clips, 3, 1)
-        cpu = {"value": rate, "unit": "clips/s", "cores": cores, "kind": "port",
-               "sample": f"{args.cpu_clips} clips/step x 3 steps of the same train step, oracle port (torch CPU fp32 kernels)"}
+        clips = args.cpu_clips or B
+        rate, sec, cores, kind, done = cpu_reference_step_rate(clips, 2, 1, budget_s=60.0)
+        cpu = {"value": rate, "unit": "clips/s", "cores": cores, "kind": kind,
+               "sample": f"{clips} clips/step x {done} timed steps (median) of the same train step, "
+                         + ("the reference's own LRCN class (oracle/_ref) on torch CPU fp32 kernels" if kind == "reference"
+                            else "oracle port (torch CPU fp32 kernels)")}
+    torch_gpu = None
+    if rank == 0 and world == 1 and not args.no_torch_baseline:
+        try:
+            torch_gpu = torch_gpu_baseline(dev)
+        except Exception as e:
+            torch_gpu = {"unavailable": repr(e)[:200]}
 
     if rank == 0:
         line = {
@@ -440,6 +557,8 @@ def run_ours(args):
             line["roofline"] = roof
         if cpu:
             line["cpu_baseline"] = cpu
+        if torch_gpu:
+            line["torch_gpu_baseline"] = torch_gpu
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -18,11 +18,19 @@ import os
 import sys
 import types
 
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")   # oracle/build_ref.py (GPU box)
 REF_ROOT = os.environ.get("B200LRCN_REFERENCE", "/root/reference")
+if not os.path.isdir(os.path.join(REF_ROOT, "lrcn")) and os.path.isdir(os.path.join(_STAGED, "lrcn")):
+    REF_ROOT = _STAGED
 
 
 def available() -> bool:
     return os.path.isdir(os.path.join(REF_ROOT, "lrcn"))
+
+
+def is_staged_copy() -> bool:
+    """True when the classes come from oracle/_ref (the unmodified files staged by oracle/build_ref.py)."""
+    return os.path.abspath(REF_ROOT) == os.path.abspath(_STAGED)
 
 
 def _stub_modules():

@@ -18,7 +18,7 @@ sys.path.insert(0, ROOT)
 from oracle import refload  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
-torch.set_num_threads(4)
+torch.set_num_threads(8)
 
 
 def npd(d):
@@ -408,8 +408,186 @@ def gold_scan():
          y_videomamba=y_vm.numpy(), y_medsos_fwd=y_f.numpy(), y_medsos_bwd=y_b.numpy())
 
 
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json config shapes (round 2).  These fixtures hold SEEDS + OUTPUTS only: the weights are the reference
+# class's default init under torch.manual_seed(seed) (bit-identical to the drop-in module built under the same seed;
+# the tests check a checksum), the clips are torch.randint under Generator(1234).  Big gradient tensors are stored
+# as strided sub-samples.  "yard/*" entries are the error of the REFERENCE ITSELF under torch's CPU bf16 autocast
+# against its own fp32 run on the same inputs -- the bf16 yardstick the GPU tests print beside our error.
+# ------------------------------------------------------------------------------------------------
+
+def _sub(v, limit=70000):
+    """strided sub-sample spec (row step, col step) keeping a tensor under `limit` elements"""
+    if v.ndim < 2 or v.size <= limit:
+        return None
+    r = c = 1
+    rows, cols = v.shape[0], int(np.prod(v.shape[1:]))
+    while (rows // r) * (cols // c) > limit:
+        if cols // c >= rows // r:
+            c *= 2
+        else:
+            r *= 2
+    return r, c
+
+
+def _store_grads(arrs, grads, prefix="grad/"):
+    for k, v in npd(grads).items():
+        sp = _sub(v)
+        if sp is None:
+            arrs[prefix + k] = v
+        else:
+            r, c = sp
+            arrs[f"gradsub/{r}/{c}/" + k] = v.reshape(v.shape[0], -1)[::r, ::c].copy()
+        arrs["gradabs/" + k] = np.array(float(np.abs(v).max()))
+
+
+def _relerr(a, b):
+    den = float(b.abs().max())
+    return float((a - b).abs().max()) / (den if den > 0 else 1.0)
+
+
+def _autocast_yard(model, x, y, out32, grads32, loss_kind="ce"):
+    """errors of torch's own CPU bf16 autocast on the reference module vs its fp32 run (BN buffers restored after)"""
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    model.zero_grad()
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        out = model(x)
+        if loss_kind == "ce":
+            loss = torch.nn.functional.cross_entropy(out.float(), y)
+        else:
+            loss = torch.nn.functional.binary_cross_entropy_with_logits(out.float(), y, reduction="mean")
+    loss.backward()
+    yard = {"yard/logits": np.array(_relerr(out.float(), out32))}
+    for k, p in model.named_parameters():
+        if p.grad is not None and k in grads32:
+            yard["yard/grad/" + k] = np.array(_relerr(p.grad.float(), grads32[k]))
+    model.load_state_dict(sd)
+    model.zero_grad()
+    return yard
+
+
+def _clips(B, T, S, classes, seed=1234):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randint(0, 256, (B, T, 3, S, S), generator=g).float() / 255.0
+    y = torch.randint(0, classes, (B,), generator=g)
+    return x, y
+
+
+def gold_cfg1():
+    """BASELINE.json configs[0]: notebook small-CNN LRCN, 20 frames x 64x64, 50 classes, batch 8, hidden 32 (nb:148-193)."""
+    LRCN = refload.notebook_lrcn()
+    C, T, H, S, B, seed = 50, 20, 32, 64, 8, 201
+    torch.manual_seed(seed)
+    m = LRCN(C, T, H, (3, S, S))
+    m.dropout.p = 0.0
+    x, y = _clips(B, T, S, C)
+    sd0, out, loss, grads, sd1 = run_step(m, x, y)
+    arrs = {"logits": out.numpy(), "loss": loss.numpy(), "state_checksum": np.array(checksum(sd0, "")),
+            "meta": np.array(json.dumps(dict(num_classes=C, T=T, hidden=H, size=S, B=B, seed=seed, clip_seed=1234,
+                                             source="nb:148-193 LRCN, dropout p=0; BASELINE.json configs[0]")))}
+    _store_grads(arrs, grads)
+    for k, v in npd(sd1).items():
+        if "running" in k or "num_batches" in k:
+            arrs["sd1/" + k] = v
+    m.load_state_dict(sd0)
+    arrs.update(_autocast_yard(m, x, y, out, grads))
+    save("cfg1_smallcnn.npz", **arrs)
+
+
+def gold_cfg2():
+    """BASELINE.json configs[1]: medsos LRCN, frozen ResNet-50 (train-mode BN), 16 frames x 112x112; an 8-clip slice
+    (128 frames per BatchNorm batch) and the bench's exact 64-clip batch (medsos_lrcn/src/models.py:121-234)."""
+    for tag, B in (("b8", 8), ("b64", 64)):
+        mm = refload.medsos_models(CONF_RNN_LAYER=3, CONF_RNN_OUT="all", CONF_CLASSIF_MODE="multiclass", CONF_DROPOUT=0.0)
+        T, S, seed = 16, 112, 7
+        torch.manual_seed(seed)
+        m = mm.LRCN(4, T, 32, 8, cnn_backbone="resnet50", rnn_type="lstm", rnn_out="all", bidirectional=False)
+        x, y = _clips(B, T, S, 4)
+        sd0, out, loss, grads, sd1 = run_step(m, x, y)
+        arrs = {"logits": out.numpy(), "loss": loss.numpy(),
+                "backbone_checksum": np.array(checksum(sd0, "cnn_backbone.")),
+                "tail_checksum": np.array(checksum({k: v for k, v in sd0.items() if not k.startswith("cnn_backbone.")}, "")),
+                "meta": np.array(json.dumps(dict(arch="resnet50", size=S, B=B, T=T, hidden=32, rnn_input=8, rnn_layers=3,
+                                                 num_classes=4, seed=seed, clip_seed=1234,
+                                                 source="medsos_lrcn/src/models.py:121-234, dropout 0; BASELINE.json configs[1]")))}
+        _store_grads(arrs, grads)
+        for k in ("cnn_backbone.bn1.running_mean", "cnn_backbone.bn1.running_var", "cnn_backbone.layer1.0.bn3.running_var",
+                  "cnn_backbone.layer3.5.bn3.running_mean", "cnn_backbone.layer4.2.bn3.running_var",
+                  "cnn_backbone.layer2.0.downsample.1.running_mean"):
+            arrs["sd1/" + k] = sd1[k].numpy()
+        m.load_state_dict(sd0)
+        m.train()
+        with torch.no_grad():
+            feat = m.cnn_backbone(x.view(B * T, 3, S, S))
+        arrs["features_sub8"] = feat[:, ::8].numpy().copy()            # [B*T, 256] of the 2048 pooled features
+        arrs["features_absmax"] = np.array(float(feat.abs().max()))
+        if B == 8:
+            m.load_state_dict(sd0)
+            arrs.update(_autocast_yard(m, x, y, out, grads))
+        save(f"cfg2_medsos_{tag}.npz", **arrs)
+
+
+def gold_cfg3():
+    """BASELINE.json configs[2]: frozen ResNet-50 at 224x224 x 16 frames + 4-layer biLSTM H=56 (lrcn/ucf50-lrcn.py:252-336
+    topology: the frozen-encoder form of rgb_lrcn.py), batch 2."""
+    C, g0 = refload.ucf50_lrcn(CONF_CNN_BACKBONE="resnet50", CONF_RNN_LAYER=4)
+    T, S, B, seed = 16, 224, 2, 23
+    torch.manual_seed(seed)
+    m = C(5, T, 56, 64, cnn_backbone="resnet50")
+    x, y = _clips(B, T, S, 5)
+    sd0, out, loss, grads, sd1 = run_step(m, x, y)
+    arrs = {"logits": out.numpy(), "loss": loss.numpy(), "backbone_checksum": np.array(checksum(sd0, "cnn_backbone.")),
+            "tail_checksum": np.array(checksum({k: v for k, v in sd0.items() if not k.startswith("cnn_backbone.")}, "")),
+            "meta": np.array(json.dumps(dict(arch="resnet50", size=S, B=B, T=T, hidden=56, rnn_input=64, rnn_layers=4,
+                                             num_classes=5, seed=seed, clip_seed=1234,
+                                             source="lrcn/ucf50-lrcn.py:252-336; BASELINE.json configs[2]")))}
+    _store_grads(arrs, grads)
+    m.load_state_dict(sd0)
+    m.train()
+    with torch.no_grad():
+        feat = m.cnn_backbone(x.view(B * T, 3, S, S))
+    arrs["features_sub8"] = feat[:, ::8].numpy().copy()
+    arrs["features_absmax"] = np.array(float(feat.abs().max()))
+    save("cfg3_ucf50_224.npz", **arrs)
+
+
+def gold_crime_trainable():
+    """crime LRCN with the WHOLE backbone trainable (lrcn/lrcn.py:181-305 with CONF_FINETUNE=True: freeze_cnn_layers
+    un-freezes the Identity head and freezes nothing, lrcn.py:246-258), ResNet-18, 8 clips x 8 frames x 64x64:
+    reference gradients of backbone parameters + torch's own bf16-autocast error on each."""
+    C, g0 = refload.crime_lrcn(CONF_CNN_BACKBONE="resnet18", CONF_RNN_LAYER=2, CONF_CLASSIF_MODE="multiple_binary",
+                               CONF_FINETUNE=True)
+    T, S, B, seed = 8, 64, 8, 29
+    torch.manual_seed(seed)
+    m = C(3, T, 12, 16, cnn_backbone="resnet18")
+    assert all(p.requires_grad for p in m.cnn_backbone.parameters())
+    x, _ = _clips(B, T, S, 3)
+    gy = torch.Generator().manual_seed(99)
+    yb = (torch.rand(B, 3, generator=gy) > 0.5).float()
+    sd0, out, loss, grads, sd1 = run_step(m, x, yb, loss_kind="bce")
+    arrs = {"y": yb.numpy(), "logits": out.numpy(), "loss": loss.numpy(), "state_checksum": np.array(checksum(sd0, "")),
+            "meta": np.array(json.dumps(dict(arch="resnet18", size=S, B=B, T=T, hidden=12, rnn_input=16, rnn_layers=2,
+                                             num_classes=3, seed=seed, clip_seed=1234, finetune=True,
+                                             source="lrcn/lrcn.py:181-305 multiple_binary, CONF_FINETUNE=True; loss=mean BCEWithLogits")))}
+    _store_grads(arrs, grads)
+    m.load_state_dict(sd0)
+    arrs.update(_autocast_yard(m, x, yb, out, grads, loss_kind="bce"))
+    save("crime_trainable_resnet18.npz", **arrs)
+
+
+def gold_baseline_shapes():
+    gold_cfg1()
+    gold_cfg2()
+    gold_cfg3()
+    gold_crime_trainable()
+
+
 if __name__ == "__main__":
     assert refload.available(), "needs /root/reference"
+    if len(sys.argv) > 1:                      # python make_golden.py gold_cfg1 gold_cfg2 ...
+        for name in sys.argv[1:]:
+            globals()[name]()
+        sys.exit(0)
     gold_sampling()
     gold_resize()
     gold_smallcnn()
