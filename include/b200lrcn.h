@@ -230,12 +230,14 @@ int b2_lstm_stack_bwd(const float* dout, const float* x, int In0, const void* co
 /* ---- selective scan forward (VideoMamba temporal mixer; lrcn/videomamba.py:242-284 parallel_scan,
  * medsos_lrcn/src/models.py:47-71) -------------------------------------------------------------------
  * x_t = exp(delta_t A) x_{t-1} + delta_t B_t u_t ; y_t = <x_t, C_t>.  u, delta, y [batch, L, D] fp32;
- * A [D, N]; B, C [batch, L, N]; N in {4, 8, 16, 32}.
+ * A [D, N]; B, C [batch, L, N]; any N in 1..64 (the medsos search grid gives n_state = hidden in {12,...,64}: the kernels
+ * run on the next compiled width b2_scan_padded_states(N) in {4, 8, 16, 32, 64} with the padding states held at zero).
  * chunk_reset > 0: the state restarts from zero every chunk_reset steps (videomamba.py resets per 256-step
  * chunk); <= 0: one scan over L.  reverse = 1: u and delta are read time-reversed, B and C are not, y is written
  * time-reversed (the medsos "backward" direction). */
 int b2_selective_scan_fwd(const float* u, const float* delta, const float* A, const float* B, const float* C, float* y,
                           int batch, int L, int D, int N, int chunk_reset, int reverse, void* stream);
+int b2_scan_padded_states(int N);
 
 /* Elementwise pieces of the Mamba ResidualBlock around the scan (medsos_lrcn/src/models.py:9-117), forward only, fp32:
  * RMSNorm over the last dim; causal depthwise Conv1d over time (k taps, padding k-1, output trimmed to L) + SiLU on
@@ -248,7 +250,7 @@ int b2_softplus_f32(const float* x, float* y, long n, void* stream);
 int b2_mul_silu_f32(const float* a, const float* res, long res_ld, int res_cols, float* y, long rows, int cols, void* stream);
 
 /* Backward of the same pieces (training rnn_type="mamba": small L / D / N).  Buffers marked ACCUMULATED are added into
- * with atomics and must be zeroed by the caller.  b2_selective_scan_bwd: workspace = batch*D*L*N floats (recomputed forward
+ * with atomics and must be zeroed by the caller.  b2_selective_scan_bwd: workspace = batch*D*L*b2_scan_padded_states(N) floats (recomputed forward
  * states); chunk_reset > 0: state reset every chunk_reset steps (videomamba), chunks in parallel; a_is_log = 1: dA is the
  * gradient of A_log where A = -exp(A_log), 0: of A itself. */
 int b2_rmsnorm_bwd_f32(const float* dy, const float* x, const float* w, float* dx, float* dw, long rows, int D, float eps,

@@ -74,3 +74,17 @@ def build_backbone_model(fixture):
         if k.startswith("sd0/"):
             assert np.array_equal(g[k], sd[k[4:]].numpy()), k
     return m, g, meta
+
+
+def condition_backbone(net, gamma=0.25):
+    """Same 'trained-like' conditioning tests/golden/make_golden.py applied before generating the *_cond fixtures:
+    gamma = 0.25 on the last BatchNorm of every residual block (bn3 of a Bottleneck, bn2 of a BasicBlock)."""
+    import torch
+    mods = dict(net.named_modules())
+    with torch.no_grad():
+        for name, mod in mods.items():
+            if not isinstance(mod, torch.nn.BatchNorm2d) or "." not in name:
+                continue
+            parent = mods[name.rsplit(".", 1)[0]]
+            if name.endswith(".bn3") or (name.endswith(".bn2") and not hasattr(parent, "bn3")):
+                mod.weight.fill_(gamma)

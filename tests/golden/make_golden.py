@@ -473,6 +473,19 @@ def _clips(B, T, S, classes, seed=1234):
     return x, y
 
 
+def condition_backbone(net, gamma=0.25):
+    """'Trained-like' conditioning of a randomly initialised torchvision ResNet (the reference loads ImageNet weights,
+    which cannot be fetched here): the LAST BatchNorm of every residual block gets gamma = 0.25, so the residual
+    branches are perturbations of the shortcut path as in a trained network.  With the default gamma = 1 a 50-layer
+    batch-statistics ResNet amplifies ANY bf16 rounding (torch's own autocast included) to 0.4 of the feature range.
+    tests/conftest.py applies the same function to the drop-in module."""
+    with torch.no_grad():
+        for name, mod in net.named_modules():
+            if isinstance(mod, torch.nn.BatchNorm2d) and (name.endswith(".bn3") or (name.endswith(".bn2") and not hasattr(
+                    dict(net.named_modules())[name.rsplit(".", 1)[0]], "bn3"))):
+                mod.weight.fill_(gamma)
+
+
 def gold_cfg1():
     """BASELINE.json configs[0]: notebook small-CNN LRCN, 20 frames x 64x64, 50 classes, batch 8, hidden 32 (nb:148-193)."""
     LRCN = refload.notebook_lrcn()
@@ -491,24 +504,35 @@ def gold_cfg1():
             arrs["sd1/" + k] = v
     m.load_state_dict(sd0)
     arrs.update(_autocast_yard(m, x, y, out, grads))
+    # sensitivity yardstick: how far the REFERENCE'S OWN fp32 gradients move when the clips are perturbed by 1e-7
+    # (one fp32 ulp of a [0,1] pixel): ReLU / max-pool decisions that flip put a floor under any fp32 comparison
+    m.load_state_dict(sd0)
+    m.zero_grad()
+    torch.manual_seed(5)
+    _, out_p, _, grads_p, _ = run_step(m, x + 1e-7 * torch.randn_like(x), y)
+    arrs["sens/logits"] = np.array(_relerr(out_p, out))
+    for k in grads:
+        arrs["sens/grad/" + k] = np.array(_relerr(grads_p[k], grads[k]))
     save("cfg1_smallcnn.npz", **arrs)
 
 
 def gold_cfg2():
     """BASELINE.json configs[1]: medsos LRCN, frozen ResNet-50 (train-mode BN), 16 frames x 112x112; an 8-clip slice
     (128 frames per BatchNorm batch) and the bench's exact 64-clip batch (medsos_lrcn/src/models.py:121-234)."""
-    for tag, B in (("b8", 8), ("b64", 64)):
+    for tag, B, cond in (("b8", 8, False), ("b64", 64, False), ("b8_cond", 8, True)):
         mm = refload.medsos_models(CONF_RNN_LAYER=3, CONF_RNN_OUT="all", CONF_CLASSIF_MODE="multiclass", CONF_DROPOUT=0.0)
         T, S, seed = 16, 112, 7
         torch.manual_seed(seed)
         m = mm.LRCN(4, T, 32, 8, cnn_backbone="resnet50", rnn_type="lstm", rnn_out="all", bidirectional=False)
+        if cond:
+            condition_backbone(m.cnn_backbone)
         x, y = _clips(B, T, S, 4)
         sd0, out, loss, grads, sd1 = run_step(m, x, y)
         arrs = {"logits": out.numpy(), "loss": loss.numpy(),
                 "backbone_checksum": np.array(checksum(sd0, "cnn_backbone.")),
                 "tail_checksum": np.array(checksum({k: v for k, v in sd0.items() if not k.startswith("cnn_backbone.")}, "")),
                 "meta": np.array(json.dumps(dict(arch="resnet50", size=S, B=B, T=T, hidden=32, rnn_input=8, rnn_layers=3,
-                                                 num_classes=4, seed=seed, clip_seed=1234,
+                                                 num_classes=4, seed=seed, clip_seed=1234, conditioned=cond,
                                                  source="medsos_lrcn/src/models.py:121-234, dropout 0; BASELINE.json configs[1]")))}
         _store_grads(arrs, grads)
         for k in ("cnn_backbone.bn1.running_mean", "cnn_backbone.bn1.running_var", "cnn_backbone.layer1.0.bn3.running_var",
@@ -521,9 +545,11 @@ def gold_cfg2():
             feat = m.cnn_backbone(x.view(B * T, 3, S, S))
         arrs["features_sub8"] = feat[:, ::8].numpy().copy()            # [B*T, 256] of the 2048 pooled features
         arrs["features_absmax"] = np.array(float(feat.abs().max()))
-        if B == 8:
-            m.load_state_dict(sd0)
-            arrs.update(_autocast_yard(m, x, y, out, grads))
+        m.load_state_dict(sd0)
+        with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+            arrs["yard/features"] = np.array(_relerr(m.cnn_backbone(x.view(B * T, 3, S, S)).float(), feat))
+        m.load_state_dict(sd0)
+        arrs.update(_autocast_yard(m, x, y, out, grads))
         save(f"cfg2_medsos_{tag}.npz", **arrs)
 
 
@@ -548,6 +574,11 @@ def gold_cfg3():
         feat = m.cnn_backbone(x.view(B * T, 3, S, S))
     arrs["features_sub8"] = feat[:, ::8].numpy().copy()
     arrs["features_absmax"] = np.array(float(feat.abs().max()))
+    m.load_state_dict(sd0)
+    with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+        arrs["yard/features"] = np.array(_relerr(m.cnn_backbone(x.view(B * T, 3, S, S)).float(), feat))
+    m.load_state_dict(sd0)
+    arrs.update(_autocast_yard(m, x, y, out, grads))
     save("cfg3_ucf50_224.npz", **arrs)
 
 
@@ -555,11 +586,18 @@ def gold_crime_trainable():
     """crime LRCN with the WHOLE backbone trainable (lrcn/lrcn.py:181-305 with CONF_FINETUNE=True: freeze_cnn_layers
     un-freezes the Identity head and freezes nothing, lrcn.py:246-258), ResNet-18, 8 clips x 8 frames x 64x64:
     reference gradients of backbone parameters + torch's own bf16-autocast error on each."""
+    for cond in (False, True):
+        _gold_crime_trainable(cond)
+
+
+def _gold_crime_trainable(cond):
     C, g0 = refload.crime_lrcn(CONF_CNN_BACKBONE="resnet18", CONF_RNN_LAYER=2, CONF_CLASSIF_MODE="multiple_binary",
                                CONF_FINETUNE=True)
     T, S, B, seed = 8, 64, 8, 29
     torch.manual_seed(seed)
     m = C(3, T, 12, 16, cnn_backbone="resnet18")
+    if cond:
+        condition_backbone(m.cnn_backbone)
     assert all(p.requires_grad for p in m.cnn_backbone.parameters())
     x, _ = _clips(B, T, S, 3)
     gy = torch.Generator().manual_seed(99)
@@ -567,12 +605,12 @@ def gold_crime_trainable():
     sd0, out, loss, grads, sd1 = run_step(m, x, yb, loss_kind="bce")
     arrs = {"y": yb.numpy(), "logits": out.numpy(), "loss": loss.numpy(), "state_checksum": np.array(checksum(sd0, "")),
             "meta": np.array(json.dumps(dict(arch="resnet18", size=S, B=B, T=T, hidden=12, rnn_input=16, rnn_layers=2,
-                                             num_classes=3, seed=seed, clip_seed=1234, finetune=True,
+                                             num_classes=3, seed=seed, clip_seed=1234, finetune=True, conditioned=cond,
                                              source="lrcn/lrcn.py:181-305 multiple_binary, CONF_FINETUNE=True; loss=mean BCEWithLogits")))}
     _store_grads(arrs, grads)
     m.load_state_dict(sd0)
     arrs.update(_autocast_yard(m, x, yb, out, grads, loss_kind="bce"))
-    save("crime_trainable_resnet18.npz", **arrs)
+    save("crime_trainable_resnet18_cond.npz" if cond else "crime_trainable_resnet18.npz", **arrs)
 
 
 def gold_baseline_shapes():

@@ -35,12 +35,12 @@ def make_backbone(name: str, pretrained: bool = False):
     from .densenet import SUPPORTED as DENSE
     from .mobilenet import SUPPORTED as MOBILE
     if name in MOBILE:
-        net = getattr(tvm, name)(weights="DEFAULT" if pretrained else None)
+        net = getattr(tvm, name)(weights="IMAGENET1K_V1" if pretrained else None)
         feat = net.classifier[-1].in_features                  # models.py:138-140: Sequential classifier
         net.classifier = torch.nn.Identity()
         return net, feat
     if name in DENSE:
-        net = getattr(tvm, name)(weights="DEFAULT" if pretrained else None)
+        net = getattr(tvm, name)(weights="IMAGENET1K_V1" if pretrained else None)
         feat = net.classifier.in_features
         net.classifier = torch.nn.Identity()
         return net, feat
@@ -48,7 +48,7 @@ def make_backbone(name: str, pretrained: bool = False):
         raise NotImplementedError(
             f"cnn_backbone={name!r}: the B200 kernels run the torchvision backbones {SUPPORTED}, {DENSE} and {MOBILE} "
             "(other torchvision families are listed under 'next' in DESIGN.md)")
-    net = getattr(tvm, name)(weights="DEFAULT" if pretrained else None)
+    net = getattr(tvm, name)(weights="IMAGENET1K_V1" if pretrained else None)
     feat = net.fc.in_features
     net.fc = torch.nn.Identity()
     return net, feat

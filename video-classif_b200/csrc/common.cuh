@@ -6,6 +6,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #define B2_API extern "C" __attribute__((visibility("default")))
 
 // ---- status plumbing (include/b200lrcn.h: 0 ok, <0 argument error, >0 cudaError_t) ----
@@ -38,6 +40,25 @@ void b2_count_launch(int n = 1);
       return (int)e__;                                                           \
     }                                                                            \
   } while (0)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is PER DEVICE: a process that touches a second GPU must repeat it
+// there.  One flag word per call site, one bit (or one high-water mark) per device ordinal; safe from concurrent host threads.
+constexpr int kB2MaxDevices = 64;
+static inline int b2_current_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return d & (kB2MaxDevices - 1);
+}
+struct B2PerDeviceOnce {
+  std::atomic<unsigned long long> done{0};
+  bool needed() const { return !((done.load(std::memory_order_acquire) >> b2_current_device()) & 1ull); }
+  void mark() { done.fetch_or(1ull << b2_current_device(), std::memory_order_release); }
+};
+struct B2PerDeviceMax {      // largest dynamic shared-memory size the attribute was raised to, per device
+  std::atomic<int> v[kB2MaxDevices] = {};
+  bool below(int need) const { return v[b2_current_device()].load(std::memory_order_acquire) < need; }
+  void set(int need) { v[b2_current_device()].store(need, std::memory_order_release); }
+};
 
 static inline int b2_ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 int b2_num_sms();

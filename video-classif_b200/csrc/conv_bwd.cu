@@ -480,10 +480,10 @@ int tmap_rows64(CUtensorMap* map, const void* base, long rows, long cols, long l
 template <int BNC, int MT = 1>
 int launch_wgrad(const CUtensorMap& tdy, const CUtensorMap& tx, const WgGeom& g, float* dw, cudaStream_t stream) {
   using L = WgLayout<BNC, MT>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static B2PerDeviceOnce attr_set;
+  if (attr_set.needed()) {
     B2_CUDA_CHECK(cudaFuncSetAttribute(conv_wgrad_kernel<BNC, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kSmem));
-    attr_set = true;
+    attr_set.mark();
   }
   const int co_blocks = b2_ceil_div(g.Cout, 128 * MT);
   const int units = g.tap_groups * co_blocks * g.ci_blocks;

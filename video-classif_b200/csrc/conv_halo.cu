@@ -493,14 +493,14 @@ B2_API int b2_conv3x3_halo_bn_nhwc_bf16(const void* x, int N, int H, int W, int 
     fin.momentum = momentum;
   }
   const int smem = halo_smem_bytes(g);
-  static int attr_smem[2] = {0, 0};
+  static B2PerDeviceMax attr_smem[2];
   const int tf = a_scale != nullptr;
-  if (smem > attr_smem[tf]) {
+  if (attr_smem[tf].below(smem)) {
     if (tf)
       B2_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     else
       B2_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_smem[tf] = smem;
+    attr_smem[tf].set(smem);
   }
   const int grid = g.num_tiles < b2_num_sms() ? g.num_tiles : b2_num_sms();
   cudaStream_t st = (cudaStream_t)stream;
@@ -563,10 +563,10 @@ B2_API int b2_conv3x3_halo_dense_bf16(const void* x, int N, int H, int W, int C,
     }
   }
   const int smem = halo_smem_bytes(g, 2, 32);
-  static int attr_smem = 0;
-  if (smem > attr_smem) {
+  static B2PerDeviceMax attr_smem;
+  if (attr_smem.below(smem)) {
     B2_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_halo_kernel<false, 2, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_smem = smem;
+    attr_smem.set(smem);
   }
   InBn at = {};
   OutFin fin = {};

@@ -882,11 +882,11 @@ template <int BN, int MODE, bool TF, bool CL = false, bool DEEP = false>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tr, int M, int N,
                 int K, const ConvGeom& g, const ATransform& at, const EpiParams& ep, cudaStream_t stream) {
   using L = SmemLayout<BN, MODE, DEEP>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static B2PerDeviceOnce attr_set;
+  if (attr_set.needed()) {
     B2_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, MODE, TF, CL, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        L::kTotal));
-    attr_set = true;
+    attr_set.mark();
   }
   const int m_blocks = CL ? ((b2_ceil_div(M, BM) + 1) & ~1) : b2_ceil_div(M, BM);
   const int tiles = m_blocks * b2_ceil_div(N, BN);
@@ -1629,10 +1629,10 @@ B2_API long b2_gram_workspace_floats(int C) { return (long)(kGramCopies + 1) * (
 template <int KC>
 int launch_gram(const CUtensorMap& ta, long M, const ATransform& at, float* workspace, cudaStream_t st) {
   using G = GramLayout<KC>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static B2PerDeviceOnce attr_set;
+  if (attr_set.needed()) {
     B2_CUDA_CHECK(cudaFuncSetAttribute(gram_stats_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::kSmem));
-    attr_set = true;
+    attr_set.mark();
   }
   const int rows_per_super = KC == 64 ? 2 * BM : BM;
   const int num_super = b2_ceil_div(M, rows_per_super);
@@ -1679,11 +1679,11 @@ B2_API int b2_conv1x1_gram_bnstats_bf16(const void* x, long M, int C, const void
   float* cov = fin_acc + kGramMaxCout + 256;                           // centred covariance + mean vector
   gram_reduce_kernel<<<b2_ceil_div(C * C / 4, 256), 256, 0, st>>>(workspace, cov, C, f.inv_count);
   B2_LAUNCH_CHECK("gram_reduce_kernel");
-  static bool fin_attr = false;
+  static B2PerDeviceOnce fin_attr;
   const size_t fin_smem = (size_t)(kGramFinRows * 256 + 256 + kGramFinWarps * kGramFinPerWarp * 256) * sizeof(float);
-  if (!fin_attr) {
+  if (fin_attr.needed()) {
     B2_CUDA_CHECK(cudaFuncSetAttribute(gram_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
-    fin_attr = true;
+    fin_attr.mark();
   }
   dim3 fgrid(b2_ceil_div(Cout, kGramFinWarps * kGramFinPerWarp), b2_ceil_div(C, kGramFinRows));
   gram_finalize_kernel<<<fgrid, 32 * kGramFinWarps, (size_t)(kGramFinRows * C + C + kGramFinWarps * kGramFinPerWarp * C) * sizeof(float), st>>>(

@@ -236,10 +236,10 @@ B2_API int b2_gru_seq_bwd(const float* dout, long dout_ld, const float* out, lon
     gru_bwd_kernel<32><<<grid, 128, smem, st>>>(dout, dout_ld, out, out_ld, saved, Whh, dG, dG_ld, dWhh,
                                                                      dbhh, B, T, H, reverse);
   } else {
-    static bool attr = false;
-    if (!attr) {
+    static B2PerDeviceOnce attr;
+    if (attr.needed()) {
       B2_CUDA_CHECK(cudaFuncSetAttribute(gru_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-      attr = true;
+      attr.mark();
     }
     const size_t smem = (size_t)(3 * 64 * 64 + NB * 3 * 64 + NB * 64) * sizeof(float);
     gru_bwd_kernel<64><<<grid, 256, smem, st>>>(dout, dout_ld, out, out_ld, saved, Whh, dG, dG_ld,

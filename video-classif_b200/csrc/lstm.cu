@@ -231,10 +231,10 @@ B2_API int b2_lstm_seq_bwd(const float* dout, long dout_ld, const float* out, lo
     lstm_bwd_kernel<32><<<grid, 128, smem, st>>>(dout, dout_ld, out, out_ld, gates, cstate, Whh, dG, dG_ld, dWhh, B, T, H,
                                                  reverse);
   } else {
-    static bool attr = false;
-    if (!attr) {
+    static B2PerDeviceOnce attr;
+    if (attr.needed()) {
       B2_CUDA_CHECK(cudaFuncSetAttribute(lstm_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-      attr = true;
+      attr.mark();
     }
     lstm_bwd_kernel<64><<<grid, 256, smem, st>>>(dout, dout_ld, out, out_ld, gates, cstate, Whh, dG, dG_ld, dWhh, B, T, H,
                                                  reverse);

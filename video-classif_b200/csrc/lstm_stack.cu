@@ -388,11 +388,11 @@ B2_API int b2_lstm_stack_bwd(const float* dout, const float* x, int In0, const v
     g.db[l] = (float*)db[l];
   }
   cudaStream_t st = (cudaStream_t)stream;
-  static bool attr = false;
-  if (!attr) {
+  static B2PerDeviceOnce attr;
+  if (attr.needed()) {
     B2_CUDA_CHECK(cudaFuncSetAttribute(lstm_stack_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     B2_CUDA_CHECK(cudaFuncSetAttribute(lstm_stack_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    attr = true;
+    attr.mark();
   }
   if (H <= 32) {
     const size_t smem = (size_t)(4 * T * kMaxIn + 4 * 32 * kMaxIn + 4 * 32 * 32 + 4 * 32 + 4 * 2 * kMaxIn) * sizeof(float);

@@ -27,31 +27,33 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-template <int N>
+// NP = n_state rounded up to a compiled width; states n >= N are padding: a = B = C = 0 keeps them at zero
+template <int NP>
 __global__ void __launch_bounds__(kScanThreads)
 selective_scan_fwd_kernel(const float* __restrict__ u, const float* __restrict__ delta, const float* __restrict__ A,
                           const float* __restrict__ Bm, const float* __restrict__ Cm, float* __restrict__ y, int L, int D,
-                          int chunk, int reverse) {
-  __shared__ float bc_s[kScanTile][2 * N];      // [t][B_t | C_t]
+                          int N, int chunk, int reverse) {
+  __shared__ float bc_s[kScanTile][2 * NP];     // [t][B_t | C_t]
   const int b = blockIdx.z;
   const int d = blockIdx.x * kScanThreads + threadIdx.x;
   const int t_begin = blockIdx.y * chunk;
   const int t_end = min(L, t_begin + chunk);
   const bool active = d < D;
-  float a2[N], x[N];
+  float a2[NP], x[NP];
 #pragma unroll
-  for (int n = 0; n < N; ++n) {
-    a2[n] = active ? A[(long)d * N + n] * kLog2e : 0.f;     // exp(delta a) = 2^(delta a log2 e)
+  for (int n = 0; n < NP; ++n) {
+    a2[n] = (active && n < N) ? A[(long)d * N + n] * kLog2e : 0.f;     // exp(delta a) = 2^(delta a log2 e)
     x[n] = 0.f;
   }
   const long row0 = (long)b * L;
   for (int t0 = t_begin; t0 < t_end; t0 += kScanTile) {
     const int nt = min(kScanTile, t_end - t0);
     __syncthreads();
-    for (int i = threadIdx.x; i < nt * 2 * N; i += kScanThreads) {
-      const int tt = i / (2 * N), j = i - tt * 2 * N;
+    for (int i = threadIdx.x; i < nt * 2 * NP; i += kScanThreads) {
+      const int tt = i / (2 * NP), j = i - tt * 2 * NP;
       const long r = (row0 + t0 + tt) * N;
-      bc_s[tt][j] = j < N ? Bm[r + j] : Cm[r + j - N];
+      const int n = j < NP ? j : j - NP;
+      bc_s[tt][j] = n < N ? (j < NP ? Bm[r + n] : Cm[r + n]) : 0.f;
     }
     __syncthreads();
     if (!active) continue;
@@ -73,9 +75,9 @@ selective_scan_fwd_kernel(const float* __restrict__ u, const float* __restrict__
           const float* bc = bc_s[tq + k];
           float acc = 0.f;
 #pragma unroll
-          for (int n = 0; n < N; ++n) {
+          for (int n = 0; n < NP; ++n) {
             x[n] = fmaf(ex2_approx(dd[k] * a2[n]), x[n], du * bc[n]);
-            acc = fmaf(x[n], bc[N + n], acc);
+            acc = fmaf(x[n], bc[NP + n], acc);
           }
           const int ts = reverse ? L - 1 - t : t;
           y[(row0 + ts) * D + d] = acc;
@@ -88,11 +90,18 @@ selective_scan_fwd_kernel(const float* __restrict__ u, const float* __restrict__
 }  // namespace
 
 // y [B,L,D] = selective scan ; chunk_reset <= 0: no state reset ; see include/b200lrcn.h
+// compiled state widths: 4, 8, 16, 32, 64; the backward workspace is sized with this padded count
+B2_API int b2_scan_padded_states(int N) {
+  int np = 4;
+  while (np < N) np <<= 1;
+  return np;
+}
+
 B2_API int b2_selective_scan_fwd(const float* u, const float* delta, const float* A, const float* Bm, const float* Cm,
                                  float* y, int batch, int L, int D, int N, int chunk_reset, int reverse, void* stream) {
   B2_ARG_CHECK(u && delta && A && Bm && Cm && y, "b2_selective_scan_fwd: null pointer");
   B2_ARG_CHECK(batch > 0 && L > 0 && D > 0, "b2_selective_scan_fwd: empty shape");
-  B2_ARG_CHECK(N == 4 || N == 8 || N == 16 || N == 32, "b2_selective_scan_fwd: n_state must be 4, 8, 16 or 32 (got %d)", N);
+  B2_ARG_CHECK(N >= 1 && N <= 64, "b2_selective_scan_fwd: n_state must be in 1..64 (got %d)", N);
   B2_ARG_CHECK(batch <= 65535, "b2_selective_scan_fwd: batch too large");
   const int chunk = chunk_reset > 0 ? chunk_reset : L;
   const int chunks = b2_ceil_div(L, chunk);
@@ -101,12 +110,15 @@ B2_API int b2_selective_scan_fwd(const float* u, const float* delta, const float
                "b2_selective_scan_fwd: the reference has no chunk-reset scan in the reverse direction");
   dim3 grid(b2_ceil_div(D, kScanThreads), chunks, batch);
   cudaStream_t st = (cudaStream_t)stream;
-  switch (N) {
-    case 4: selective_scan_fwd_kernel<4><<<grid, kScanThreads, 0, st>>>(u, delta, A, Bm, Cm, y, L, D, chunk, reverse); break;
-    case 8: selective_scan_fwd_kernel<8><<<grid, kScanThreads, 0, st>>>(u, delta, A, Bm, Cm, y, L, D, chunk, reverse); break;
-    case 16: selective_scan_fwd_kernel<16><<<grid, kScanThreads, 0, st>>>(u, delta, A, Bm, Cm, y, L, D, chunk, reverse); break;
-    default: selective_scan_fwd_kernel<32><<<grid, kScanThreads, 0, st>>>(u, delta, A, Bm, Cm, y, L, D, chunk, reverse); break;
+#define B2_SCAN_FWD(NP) selective_scan_fwd_kernel<NP><<<grid, kScanThreads, 0, st>>>(u, delta, A, Bm, Cm, y, L, D, N, chunk, reverse)
+  switch (b2_scan_padded_states(N)) {      // any n_state 1..64 runs on the next compiled width
+    case 4: B2_SCAN_FWD(4); break;
+    case 8: B2_SCAN_FWD(8); break;
+    case 16: B2_SCAN_FWD(16); break;
+    case 32: B2_SCAN_FWD(32); break;
+    default: B2_SCAN_FWD(64); break;
   }
+#undef B2_SCAN_FWD
   B2_LAUNCH_CHECK("selective_scan_fwd_kernel");
   return 0;
 }
@@ -306,14 +318,15 @@ mul_silu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ a, c
 // contributions are summed over the warp's channels with shuffles when those channels share (batch, t) -- D % (32 / G) == 0 --
 // and leave as one atomic per warp and state (per-thread atomics put D threads on each of the B*L*N addresses).
 // Chunks are independent (the state is reset at their start): grid.y = chunks.  states[b][t][d][n] is the workspace.
-template <int N>
+// NP = n_state rounded up to a compiled width (states n >= N are padding and contribute nothing); workspace stride NP
+template <int NP>
 __global__ void __launch_bounds__(128)
 selective_scan_bwd_kernel(const float* __restrict__ u, const float* __restrict__ delta, const float* __restrict__ A,
                           const float* __restrict__ Bm, const float* __restrict__ Cm, const float* __restrict__ dy,
                           float* __restrict__ states, float* __restrict__ du, float* __restrict__ ddelta,
                           float* __restrict__ dA_out, float* __restrict__ dB, float* __restrict__ dC, int batch, int L, int D,
-                          int chunk, int reverse, int a_is_log) {
-  constexpr int G = N / 4;                 // lanes per channel
+                          int N, int chunk, int reverse, int a_is_log) {
+  constexpr int G = NP / 4;                // lanes per channel
   constexpr int CW = 32 / G;               // channels per warp
   const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long total = (long)batch * D * G;
@@ -329,19 +342,25 @@ selective_scan_bwd_kernel(const float* __restrict__ u, const float* __restrict__
   const int t_begin = blockIdx.y * chunk;
   const int t_end = min(L, t_begin + chunk);
   float a[4], x[4];
+  bool okn[4];
 #pragma unroll
   for (int n = 0; n < 4; ++n) {
-    a[n] = A[(long)d * N + n0 + n];
+    okn[n] = n0 + n < N;
+    a[n] = okn[n] ? A[(long)d * N + n0 + n] : 0.f;
     x[n] = 0.f;
   }
-  float* st = states + (row0 * D + d) * N + n0;
-  const long t_stride = (long)D * N;
+  float* st = states + (row0 * D + d) * NP + n0;
+  const long t_stride = (long)D * NP;
+  auto ld4 = [&](const float* p, float (&o)[4]) {      // 4 states of a [.., N] row; N need not be a multiple of 4
+#pragma unroll
+    for (int n = 0; n < 4; ++n) o[n] = okn[n] ? __ldg(p + n) : 0.f;
+  };
   for (int t = t_begin; t < t_end; ++t) {            // forward recompute (same arithmetic as the forward kernel)
     const int ts = reverse ? L - 1 - t : t;
     const float dl = delta[(row0 + ts) * D + d];
     const float duv = dl * u[(row0 + ts) * D + d];
-    const float4 b4 = *reinterpret_cast<const float4*>(Bm + (row0 + t) * N + n0);
-    const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+    float bb[4];
+    ld4(Bm + (row0 + t) * N + n0, bb);
 #pragma unroll
     for (int n = 0; n < 4; ++n) x[n] = fmaf(ex2_approx(dl * a[n] * kLog2e), x[n], duv * bb[n]);
     if (live) *reinterpret_cast<float4*>(st + t * t_stride) = make_float4(x[0], x[1], x[2], x[3]);
@@ -356,10 +375,10 @@ selective_scan_bwd_kernel(const float* __restrict__ u, const float* __restrict__
     const float dyv = dy[(row0 + ts) * D + d];
     const float4 x4 = *reinterpret_cast<const float4*>(st + t * t_stride);
     const float4 p4 = t > t_begin ? *reinterpret_cast<const float4*>(st + (t - 1) * t_stride) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 b4 = *reinterpret_cast<const float4*>(Bm + (row0 + t) * N + n0);
-    const float4 c4 = *reinterpret_cast<const float4*>(Cm + (row0 + t) * N + n0);
     const float xt[4] = {x4.x, x4.y, x4.z, x4.w}, xp[4] = {p4.x, p4.y, p4.z, p4.w};
-    const float bt[4] = {b4.x, b4.y, b4.z, b4.w}, ct[4] = {c4.x, c4.y, c4.z, c4.w};
+    float bt[4], ct[4];
+    ld4(Bm + (row0 + t) * N + n0, bt);
+    ld4(Cm + (row0 + t) * N + n0, ct);
     float ddl = 0.f, duv = 0.f, vc[4], vb[4];
 #pragma unroll
     for (int n = 0; n < 4; ++n) {
@@ -397,21 +416,26 @@ selective_scan_bwd_kernel(const float* __restrict__ u, const float* __restrict__
       if ((threadIdx.x & 31) < G) {
 #pragma unroll
         for (int n = 0; n < 4; ++n) {
-          atomicAdd(dC + (row0 + t) * N + n0 + n, vc[n]);
-          atomicAdd(dB + (row0 + t) * N + n0 + n, vb[n]);
+          if (okn[n]) {
+            atomicAdd(dC + (row0 + t) * N + n0 + n, vc[n]);
+            atomicAdd(dB + (row0 + t) * N + n0 + n, vb[n]);
+          }
         }
       }
     } else if (live) {
 #pragma unroll
       for (int n = 0; n < 4; ++n) {
-        atomicAdd(dC + (row0 + t) * N + n0 + n, vc[n]);
-        atomicAdd(dB + (row0 + t) * N + n0 + n, vb[n]);
+        if (okn[n]) {
+          atomicAdd(dC + (row0 + t) * N + n0 + n, vc[n]);
+          atomicAdd(dB + (row0 + t) * N + n0 + n, vb[n]);
+        }
       }
     }
   }
   if (live) {
 #pragma unroll
-    for (int n = 0; n < 4; ++n) atomicAdd(dA_out + (long)d * N + n0 + n, a_is_log ? dAacc[n] * a[n] : dAacc[n]);
+    for (int n = 0; n < 4; ++n)
+      if (okn[n]) atomicAdd(dA_out + (long)d * N + n0 + n, a_is_log ? dAacc[n] * a[n] : dAacc[n]);
   }
 }
 
@@ -454,7 +478,7 @@ B2_API int b2_mul_silu_bwd_f32(const float* dy, const float* a, const float* res
   return 0;
 }
 
-// workspace: batch * D * L * N floats; du / ddelta overwritten; dA [D,N], dB / dC [batch,L,N] ACCUMULATED (caller zeroes).
+// workspace: batch * D * L * b2_scan_padded_states(N) floats; du / ddelta overwritten; dA [D,N], dB / dC [batch,L,N] ACCUMULATED (caller zeroes).
 // chunk_reset > 0: the state restarts from zero every chunk_reset steps (videomamba.py:242-284), chunks run in parallel;
 // a_is_log = 1: dA is the gradient of A_log where A = -exp(A_log) (medsos models.py:94), 0: the gradient of A itself
 B2_API int b2_selective_scan_bwd(const float* u, const float* delta, const float* A, const float* Bm, const float* Cm,
@@ -463,22 +487,24 @@ B2_API int b2_selective_scan_bwd(const float* u, const float* delta, const float
   B2_ARG_CHECK(u && delta && A && Bm && Cm && dy && workspace && du && ddelta && dA && dB && dC,
                "b2_selective_scan_bwd: null pointer");
   B2_ARG_CHECK(batch > 0 && L > 0 && D > 0, "b2_selective_scan_bwd: empty shape");
-  B2_ARG_CHECK(N == 4 || N == 8 || N == 16 || N == 32, "b2_selective_scan_bwd: n_state must be 4, 8, 16 or 32 (got %d)", N);
+  B2_ARG_CHECK(N >= 1 && N <= 64, "b2_selective_scan_bwd: n_state must be in 1..64 (got %d)", N);
+  const int NP = b2_scan_padded_states(N);
   const int chunk = chunk_reset > 0 ? chunk_reset : L;
   const int chunks = b2_ceil_div(L, chunk);
   B2_ARG_CHECK(chunks <= 65535, "b2_selective_scan_bwd: too many chunks");
   B2_ARG_CHECK(!(reverse && chunks > 1), "b2_selective_scan_bwd: the reference has no chunk-reset scan in the reverse direction");
-  const long threads = (long)batch * D * (N / 4);       // one lane per 4 states
+  const long threads = (long)batch * D * (NP / 4);      // one lane per 4 states
   const dim3 grid((unsigned)((threads + 127) / 128), (unsigned)chunks);
   cudaStream_t st = (cudaStream_t)stream;
 #define B2_SCAN_BWD(NN)                                                                                          \
   selective_scan_bwd_kernel<NN><<<grid, 128, 0, st>>>(u, delta, A, Bm, Cm, dy, workspace, du, ddelta, dA, dB, dC, \
-                                                      batch, L, D, chunk, reverse, a_is_log)
-  switch (N) {
+                                                      batch, L, D, N, chunk, reverse, a_is_log)
+  switch (NP) {
     case 4: B2_SCAN_BWD(4); break;
     case 8: B2_SCAN_BWD(8); break;
     case 16: B2_SCAN_BWD(16); break;
-    default: B2_SCAN_BWD(32); break;
+    case 32: B2_SCAN_BWD(32); break;
+    default: B2_SCAN_BWD(64); break;
   }
 #undef B2_SCAN_BWD
   B2_LAUNCH_CHECK("selective_scan_bwd_kernel");

@@ -394,12 +394,12 @@ B2_API int b2_conv3x3_wgrad_f32(const float* x, const float* dy, float* dw, int 
   if (ci_per == 1) {
     conv3x3_wgrad_kernel<1><<<grid, 256, smem, st>>>(x, dy, dw, N, Cin, Cout, H, W);
   } else if (ci_per == 2) {
-    static bool a2 = false;
-    if (!a2) { B2_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); a2 = true; }
+    static B2PerDeviceOnce a2;
+    if (a2.needed()) { B2_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); a2.mark(); }
     conv3x3_wgrad_kernel<2><<<grid, 256, smem, st>>>(x, dy, dw, N, Cin, Cout, H, W);
   } else {
-    static bool a4 = false;
-    if (!a4) { B2_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_wgrad_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); a4 = true; }
+    static B2PerDeviceOnce a4;
+    if (a4.needed()) { B2_CUDA_CHECK(cudaFuncSetAttribute(conv3x3_wgrad_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); a4.mark(); }
     conv3x3_wgrad_kernel<4><<<grid, 256, smem, st>>>(x, dy, dw, N, Cin, Cout, H, W);
   }
   B2_LAUNCH_CHECK("conv3x3_wgrad_kernel");

@@ -334,10 +334,10 @@ B2_API int b2_stem_conv_bf16(const void* xp, const void* wk, void* y, int N, int
   B2_ARG_CHECK((unsigned long)g.N * g.tiles_per_img * g.tiles_per_img < (1ul << 32) &&
                    (unsigned long)(g.tiles_per_img * 128 + 128) * g.Wq < (1ul << 32),
                "b2_stem_conv_bf16: shape outside the multiply-high division range");
-  static int attr_smem = 0;
-  if (smem > attr_smem) {
+  static B2PerDeviceMax attr_smem;
+  if (attr_smem.below((int)smem)) {
     B2_CUDA_CHECK(cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_smem = smem;
+    attr_smem.set((int)smem);
   }
   const int tiles = g.N * g.tiles_per_img;
   const int grid = tiles < b2_num_sms() ? tiles : b2_num_sms();

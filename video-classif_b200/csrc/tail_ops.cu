@@ -118,6 +118,41 @@ act_ln_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ pre,
   }
 }
 
+// Wide rows (N > 256*kMaxCols, e.g. bn0 = LayerNorm(T * dirs * H) with rnn_out='all': 60 x 2 x 64 = 7680 columns): the
+// same row algebra with a column loop; dgamma / dbeta leave as one atomic per (row, column) -- rows = clips, a few hundred
+__global__ void __launch_bounds__(256)
+act_ln_bwd_wide_kernel(const float* __restrict__ dout, const float* __restrict__ pre, const float* __restrict__ gamma,
+                       const float* __restrict__ mean_in, const float* __restrict__ rstd_in, float* __restrict__ dpre,
+                       float* __restrict__ dgamma, float* __restrict__ dbeta, long M, int N, int apply_gelu) {
+  __shared__ float red[32];
+  for (long row = blockIdx.x; row < M; row += gridDim.x) {
+    const float* p = pre + row * N;
+    const float* d = dout + row * N;
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = threadIdx.x; c < N; c += 256) {
+      const float g = apply_gelu ? gelu_f(p[c]) : p[c];
+      const float xh = (g - mean) * rstd;
+      const float dxh = d[c] * gamma[c];
+      s1 += dxh;
+      s2 += dxh * xh;
+      atomicAdd(dgamma + c, d[c] * xh);
+      atomicAdd(dbeta + c, d[c]);
+    }
+    const float m1 = block_sum(s1, red) / (float)N;
+    const float m2 = block_sum(s2, red) / (float)N;
+    for (int c = threadIdx.x; c < N; c += 256) {
+      const float x = p[c];
+      const float g = apply_gelu ? gelu_f(x) : x;
+      const float xh = (g - mean) * rstd;
+      const float dxh = d[c] * gamma[c];
+      float dgv = rstd * (dxh - m1 - xh * m2);
+      if (apply_gelu) dgv *= gelu_grad_f(x);
+      dpre[row * N + c] = dgv;
+    }
+  }
+}
+
 // ---- fp32 SIMT GEMM: C[M,N] = alpha * op(A)[M,K] op(B)[K,N] + beta * C, row-major ----
 constexpr int TS = 64, TK = 32;
 template <bool TA, bool TB>
@@ -287,11 +322,14 @@ B2_API int b2_act_ln_bwd(const float* dout, const float* pre, const float* gamma
                          void* stream) {
   B2_ARG_CHECK(dout && pre && gamma && mean && rstd && dpre && dgamma && dbeta && M > 0 && N > 0,
                "b2_act_ln_bwd: null pointer or empty");
-  B2_ARG_CHECK(N <= 256 * kMaxCols, "b2_act_ln_bwd: N=%d exceeds %d", N, 256 * kMaxCols);
   const long cap = (long)b2_num_sms() * 2;
-  act_ln_bwd_kernel<<<(unsigned)(M < cap ? M : cap), 256, 0, (cudaStream_t)stream>>>(dout, pre, gamma, mean, rstd,
-                                                                                    dpre, dgamma, dbeta, M, N,
-                                                                                    apply_gelu);
+  if (N <= 256 * kMaxCols)
+    act_ln_bwd_kernel<<<(unsigned)(M < cap ? M : cap), 256, 0, (cudaStream_t)stream>>>(dout, pre, gamma, mean, rstd,
+                                                                                      dpre, dgamma, dbeta, M, N,
+                                                                                      apply_gelu);
+  else      // no column limit (the forward kernel has none either)
+    act_ln_bwd_wide_kernel<<<(unsigned)(M < cap * 4 ? M : cap * 4), 256, 0, (cudaStream_t)stream>>>(
+        dout, pre, gamma, mean, rstd, dpre, dgamma, dbeta, M, N, apply_gelu);
   B2_LAUNCH_CHECK("act_ln_bwd_kernel");
   return 0;
 }

@@ -257,7 +257,7 @@ class SelectiveScanFn(torch.autograd.Function):
         Bsz, L, D = u.shape
         N = A.shape[1]
         dy = dy.contiguous().float()
-        ws = torch.empty(Bsz * D * L * N, device=u.device, dtype=F32)
+        ws = torch.empty(Bsz * D * L * _lib.lib().b2_scan_padded_states(N), device=u.device, dtype=F32)
         du, dd = torch.empty_like(u), torch.empty_like(u)
         dA = torch.zeros_like(A)
         dB, dC = torch.zeros_like(Bm), torch.zeros_like(Cm)
@@ -366,7 +366,7 @@ class MambaBlockFn(torch.autograd.Function):
         call("b2_mul_silu_bwd_f32", dg.data_ptr(), y2.data_ptr(), xr.data_ptr() + di * 4, 2 * di, di, dy.data_ptr(),
              dxr.data_ptr() + di * 4, 2 * di, R, cols, st)
         # scan(s)
-        ws = torch.empty(B * di * L * n, device=dev, dtype=F32)
+        ws = torch.empty(B * di * L * _lib.lib().b2_scan_padded_states(n), device=dev, dtype=F32)
         dA_log = torch.zeros((di, n), device=dev, dtype=F32)
         dBC = torch.zeros((2, B, L, n), device=dev, dtype=F32)
         dxc = ddelta = None
