@@ -278,3 +278,31 @@ def test_header_is_plain_c(tmp_path):
     r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-Wno-comment", "-fsyntax-only", "-I",
                         os.path.join(ROOT, "include"), str(src)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_checkpoint_unpickler_never_resolves_foreign_globals(tmp_path):
+    """`os.system`, `builtins.eval` ... must not be importable through load_reference_checkpoint: they become
+    inert placeholders (REDUCE only constructs an empty nn.Module), nothing is executed."""
+    import pickle
+
+    import video_classif_b200.checkpoint as ck
+
+    class Evil:
+        def __reduce__(self):
+            import os
+            return (os.system, ("echo pwned > %s" % (tmp_path / "pwned"),))
+
+    for name, obj in (("evil.pkl", Evil()),):
+        p = tmp_path / name
+        with open(p, "wb") as f:
+            pickle.dump(obj, f)
+        with open(p, "rb") as f:
+            try:
+                out = ck._Unpickler(f).load()
+            except Exception:
+                out = None
+        assert not (tmp_path / "pwned").exists()
+        assert out is None or isinstance(out, ck.ReferencePlaceholder)
+    assert not ck._allowed_global("builtins", "eval") and not ck._allowed_global("builtins", "getattr")
+    assert not ck._allowed_global("os", "system") and not ck._allowed_global("subprocess", "Popen")
+    assert ck._allowed_global("collections", "OrderedDict") and ck._allowed_global("torch._utils", "_rebuild_tensor_v2")

@@ -13,9 +13,12 @@ topology and hyper-parameters are read back from the placeholder's attributes an
 video_classif_b200 module is constructed and the weights go in through `load_state_dict` (same keys, same shapes).
 `state_dict` checkpoints (lrcn/lrcn.py:347, rgb_lrcn.py:302) need none of this: `model.load_state_dict(torch.load(p))`.
 
-Host-side only; nothing here touches the GPU.  Trust model: like the reference's own `torch.load(path)` this unpickles
-arbitrary Python objects (`weights_only=False`) -- load only checkpoints you wrote; classes outside torch / torchvision /
-numpy that cannot be imported are never executed, they become inert placeholders.
+Host-side only; nothing here touches the GPU.  Trust model: the unpickler resolves ONLY an allowlist of globals --
+torch tensor / storage rebuild helpers, classes under torch.nn / torchvision.models (module objects), OrderedDict, numpy
+array reconstruction and a handful of inert builtins (set, frozenset, slice, range, complex, int, float, bool, ...).
+Every other global (`os.system`, `builtins.eval`, `subprocess.Popen`, the reference's own classes, ...) is NEVER imported
+or called: it becomes an inert `ReferencePlaceholder` class, so a REDUCE on it only constructs an empty nn.Module.
+That is stricter than the reference's own `torch.load(path)`; it is still a pickle -- load checkpoints you trust.
 """
 from __future__ import annotations
 
@@ -28,7 +31,30 @@ import torch
 import torch.nn as nn
 
 REFERENCE_CLASS_NAMES = ("LRCN", "LRCN2", "ResidualBlock", "ParallelMamba", "RMSNorm")
-_TRUSTED_ROOTS = ("torch", "torchvision", "collections", "numpy", "builtins", "_codecs", "copyreg")
+# globals a torch module pickle legitimately needs (checked by (module, name); prefixes end with a dot)
+_ALLOWED_EXACT = {
+    ("collections", "OrderedDict"), ("collections", "defaultdict"), ("_codecs", "encode"), ("copyreg", "_reconstructor"),
+    ("builtins", "set"), ("builtins", "frozenset"), ("builtins", "slice"), ("builtins", "range"), ("builtins", "complex"),
+    ("builtins", "int"), ("builtins", "float"), ("builtins", "bool"), ("builtins", "str"), ("builtins", "bytes"),
+    ("builtins", "bytearray"), ("builtins", "list"), ("builtins", "tuple"), ("builtins", "dict"), ("builtins", "object"),
+    ("torch", "Size"), ("torch", "device"), ("torch", "dtype"), ("torch", "Tensor"), ("torch", "layout"),
+    ("torch", "memory_format"), ("torch.serialization", "_get_layout"), ("torch._tensor", "_rebuild_from_type_v2"),
+    ("numpy", "ndarray"), ("numpy", "dtype"), ("numpy.core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "_reconstruct"),
+    ("numpy.core.multiarray", "scalar"), ("numpy._core.multiarray", "scalar"),
+}
+_ALLOWED_PREFIX = ("torch._utils._rebuild_", "torch.nn.", "torch.storage.", "torchvision.models.", "torchvision.ops.")
+_ALLOWED_TORCH_ATTRS = re.compile(r"^(Float|Double|Half|BFloat16|Long|Int|Short|Char|Byte|Bool)Storage$")
+
+
+def _allowed_global(mod_name, name):
+    if mod_name == "__builtin__":          # protocol-2 spelling of `builtins` (pickle's fix_imports maps it on lookup)
+        mod_name = "builtins"
+    if (mod_name, name) in _ALLOWED_EXACT:
+        return True
+    if mod_name == "torch" and _ALLOWED_TORCH_ATTRS.match(name):
+        return True
+    full = mod_name + "." + name
+    return any(full.startswith(p) for p in _ALLOWED_PREFIX)
 
 
 class ReferencePlaceholder(nn.Module):
@@ -44,14 +70,13 @@ class _Unpickler(pickle.Unpickler):
     _made: dict = {}
 
     def find_class(self, mod_name, name):
-        root = mod_name.split(".")[0]
-        if root in _TRUSTED_ROOTS:
-            return super().find_class(mod_name, name)
-        if name not in REFERENCE_CLASS_NAMES:
-            try:
-                return super().find_class(mod_name, name)
-            except (ImportError, AttributeError):
-                pass
+        if _allowed_global(mod_name, name):
+            obj = super().find_class(mod_name, name)
+            # torch.nn.* / torchvision.* entries must be classes (module types, parameter containers), never functions
+            if mod_name.startswith(("torch.nn", "torchvision")) and not isinstance(obj, type) \
+                    and not name.startswith("_rebuild_"):
+                raise pickle.UnpicklingError(f"refusing non-class global {mod_name}.{name}")
+            return obj
         key = (mod_name, name)
         if key not in _Unpickler._made:
             _Unpickler._made[key] = type(name, (ReferencePlaceholder,), {"_ref_module": mod_name, "_ref_name": name})
