@@ -78,6 +78,14 @@ class ResNetRunner:
         self.use_graph = False        # models route through graphed() when set (enable_encoder_graph())
         self.stem_impl = "direct"     # "im2col": patch matrix + plain GEMM (A/B parity tests)
         self.fuse_bn = ResNetRunner.FUSE_BN   # BatchNorms folded into the conv kernels vs stand-alone bn_apply passes
+        self.gram_wide = os.environ.get("B2_GRAM_WIDE", "1") == "1"   # Gram-form BN3 statistics for 256-channel conv3 inputs too
+        self._ident = None
+
+    def _identity(self, dev):
+        """(scale, shift) = (1, 0) over 256 channels: the Gram statistics kernel always applies its A transform."""
+        if self._ident is None or self._ident[0].device != dev:
+            self._ident = (torch.ones(256, device=dev, dtype=F32), torch.zeros(256, device=dev, dtype=F32))
+        return self._ident
 
     # ---- weights in kernel layout: [Cout, R, S, C] bf16 (K-major), stem [64, STEM_KP] ----
     def _weights(self):
@@ -279,10 +287,12 @@ class ResNetRunner:
                         if r2.shape[-1] >= 256:
                             scale_shift_apply(r2, a2[0], a2[1], relu=True)
                             a2 = None
-                        if train and a2 is not None and r2.shape[-1] in GRAM_CHANNELS:
+                        if train and r2.shape[-1] in GRAM_CHANNELS and (a2 is not None or self.gram_wide):
                             # BN3 statistics from the Gram matrix of conv3's (transformed) input: one HBM-bound
                             # pass over the small tensor instead of a full conv3 whose output is thrown away
-                            conv1x1_gram_bnstats(r2, w[pfx + ".conv3"], a2, fin_of(blk.bn3))
+                            # (256 channels: the input is already normalised in place -> identity transform)
+                            conv1x1_gram_bnstats(r2, w[pfx + ".conv3"], a2 if a2 is not None else self._identity(dev),
+                                                 fin_of(blk.bn3), a_relu=a2 is not None)
                         elif train:            # statistics-only pass of conv3
                             conv2d_bn_nhwc(r2, w[pfx + ".conv3"], 1, 0, a=a2, stats=stats_of(blk.bn3),
                                            fin=fin_of(blk.bn3), store=False)
