@@ -9,8 +9,8 @@ mean of per-shard gradients.
 
 Gradients are tiny (0.75-35 MB) -> the all-reduce is latency bound, so what matters is WHEN each
 collective starts, not its size:
-  * parameters are packed into flat buckets of at most `bucket_bytes` (default 1 MB; a larger
-    parameter gets a bucket of its own) in reverse registration order = the order backward
+  * parameters are packed into flat buckets of at most `bucket_bytes` (default: 1/8 of the payload,
+    clamped to 1..8 MB; a larger parameter gets a bucket of its own) in reverse registration order = the order backward
     produces them, so the head / LSTM / adapt3 / adapt2 gradients are on the wire while the
     weight-gradient GEMM of the first trainable layer is still running;
   * a bucket's all-reduce (NCCL `AVG`: no separate scaling pass) is launched from the autograd hook
@@ -42,7 +42,7 @@ class _Bucket:
 class GradBucketAllReduce:
     """Usage (per step):  loss.backward(); dp.finish(); optimizer.step()"""
 
-    def __init__(self, module: torch.nn.Module, bucket_bytes: int = 1 << 20, process_group=None, record_timeline: bool = False):
+    def __init__(self, module: torch.nn.Module, bucket_bytes: int = None, process_group=None, record_timeline: bool = False):
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed must be initialised (one process per GPU, NCCL backend)")
         self.group = process_group
@@ -50,6 +50,12 @@ class GradBucketAllReduce:
         self.record_timeline = record_timeline
         self._avg = dist.get_backend(process_group) == "nccl"          # gloo has no AVG: SUM + one scaling pass
         params = [p for p in module.parameters() if p.requires_grad]
+        if bucket_bytes is None:
+            # ~8 collectives per step: each bucket costs one staging launch + one NCCL launch on the host thread, and the
+            # trainable-backbone steps are launch bound (DenseNet-121 fine-tune, 364 parameters: 34 buckets of 1 MB cost
+            # 5 ms of a 27 ms step at N = 2, profiles/r02_probe_dp_n2.log); never below 1 MB, never above 8 MB
+            total = sum(p.numel() * p.element_size() for p in params)
+            bucket_bytes = min(max(total // 8, 1 << 20), 8 << 20)
         self.buckets: List[_Bucket] = []
         cur, cur_bytes = [], 0
         for p in reversed(params):
