@@ -163,6 +163,7 @@ int b2_transpose_cast_f32_bf16(const float* src, long ld_src, void* dst, long ld
 /* nn.Dropout(p) in train mode (nb:163, models.py:153,182): y = x*keep/(1-p) with a counter-hash
  * mask; calling it again with the same seed on dy replays the mask for the backward pass. */
 int b2_dropout_f32(const float* x, float* y, long n, float p, unsigned long long seed, void* stream);
+int b2_transpose_bf16(const void* src, long ld_src, void* dst, long ld_dst, long R, long C, void* stream);   /* dst[c][r] = src[r][c], bf16 */
 
 /* ---- K3/K4 persistent LSTM --------------------------------------------------------------
  * torch.nn.LSTM(batch_first=True) semantics (nb:169, models.py:156-158, lrcn.py:236): gate order
@@ -201,6 +202,41 @@ int b2_bn2d_act_pool_bwd_apply_f32(const float* x, const float* dy, const float*
                                    const double* s2, long count, int train, float* dx, int N, int C, int H,
                                    int W, int pool, void* stream);
 int b2_f64_to_f32(const double* src, float* dst, int n, int accumulate, void* stream);
+
+/* ---- small-CNN tensor-core path (csrc/smallcnn_tc.cu): the notebook CNN (nb:156-163,181-183; backup_ucf50.py:113-115,138-140)
+ * in bf16 NHWC on tcgen05.  One pixel = one swizzle row of 2*C bytes (C = 16 / 32 / 64 -> SWIZZLE_32B / 64B / 128B); a tile is
+ * TH whole output rows, its halo comes in by one TMA and every filter tap reads it through a shifted descriptor.
+ * b2_sc_conv3x3_bf16: y [N,H,W,Cout] = conv3x3(x [N,H,W,Cin], w [Cout][3][3][Cin]) (+ bias), stride 1, pad 1, + optional
+ *   per-channel sum / sum of squares of the stored values (ACCUMULATED).  (Cin, Cout) in {(16,32), (32,64)} (forward) and
+ *   {(64,32), (32,16)} (their data gradients: w = the flipped, transposed filter).
+ * b2_sc_conv3x3_wgrad_bf16: dw [Cout][3][3][Cin] fp32 (ACCUMULATED) = sum over pixels of dz [N,H,W,Cout] x shifted x [N,H,W,Cin].
+ * b2_sc_conv1_fwd / _wgrad: the 3-channel first layer on CUDA cores (x fp32 NCHW [N,3,H,W], w / dw fp32 [16][3][3][3] in torch
+ *   layout, y / dz bf16 NHWC [N,H,W,16]); dw ACCUMULATED.
+ * b2_sc_bn_finalize: (sum, sumsq, count) -> scale, shift, mean, rstd (+ running statistics, momentum; train = 0: from them).
+ * b2_sc_act_pool_fwd: y = maxpool_pool(relu(raw * scale + shift)), pool in {1, 2}; _bwd_reduce: s1 = sum dpre (= dbeta),
+ *   s2 = sum dpre * xhat (= dgamma), ACCUMULATED, dpre = dy routed to the first maximum of its window where positive;
+ *   _bwd_apply: dz [N,H,W,C] = scale * (dpre - s1/M - xhat s2/M) (train) or scale * dpre (eval).
+ * b2_sc_nhwc_to_chw: feat [N][C*HW] bf16 (the channel-major flatten of nb:186) = dropout_p(act [N][HW][C]); b2_sc_chw_to_nhwc:
+ *   the inverse on the fp32 / bf16 gradient with the same mask (same seed). */
+int b2_sc_conv3x3_bf16(const void* x, int N, int H, int W, int Cin, const void* w, int Cout, void* y, const float* bias,
+                       float* col_sum, float* col_sumsq, void* stream);
+int b2_sc_conv3x3_wgrad_bf16(const void* x, const void* dz, int N, int H, int W, int Cin, int Cout, float* dw, void* stream);
+int b2_sc_conv1_fwd(const float* x, const float* w, const float* bias, void* y, int N, int H, int W, float* col_sum,
+                    float* col_sumsq, void* stream);
+int b2_sc_conv1_wgrad(const float* x, const void* dz, float* dw, int N, int H, int W, void* stream);
+int b2_sc_bn_finalize(const float* sum, const float* sumsq, const float* gamma, const float* beta, float* running_mean,
+                      float* running_var, long count, float eps, float momentum, int train, float* scale, float* shift,
+                      float* mean, float* rstd, int C, void* stream);
+int b2_sc_act_pool_fwd(const void* raw, const float* scale, const float* shift, void* y, int N, int H, int W, int C, int pool,
+                       void* stream);
+int b2_sc_act_pool_bwd_reduce(const void* raw, const void* dy, const float* scale, const float* shift, const float* mean,
+                              const float* rstd, float* s1, float* s2, int N, int H, int W, int C, int pool, void* stream);
+int b2_sc_act_pool_bwd_apply(const void* raw, const void* dy, const float* scale, const float* shift, const float* mean,
+                             const float* rstd, const float* s1, const float* s2, int train, void* dz, int N, int H, int W,
+                             int C, int pool, void* stream);
+int b2_sc_nhwc_to_chw(const void* act, void* feat, int N, int HW, int C, float p_drop, unsigned long long seed, void* stream);
+int b2_sc_chw_to_nhwc(const void* dfeat, int in_bf16, void* dact, int N, int HW, int C, float p_drop, unsigned long long seed,
+                      void* stream);
 
 /* ---- persistent GRU layer (torch.nn.GRU semantics, gate order r,z,n; lrcn/backup_ucf50.py:126, medsos models.py:160-170)
  * G [B,T,3H] = x W_ih^T + b_ih (hoisted gate GEMM); Whh [3H,H]; bhh [3H] (b_hn stays inside the r product);

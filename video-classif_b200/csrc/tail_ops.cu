@@ -276,6 +276,23 @@ transpose_cast_kernel(const float* __restrict__ src, long ld_src, bf16* __restri
   }
 }
 
+// dst[c, r] (bf16, ld_dst) = src[r, c] (bf16, ld_src) ; 32x32 smem tile transpose (no fp32 round trip of a bf16 operand)
+__global__ void __launch_bounds__(256)
+transpose_bf16_kernel(const bf16* __restrict__ src, long ld_src, bf16* __restrict__ dst, long ld_dst, long R, long Ccols) {
+  __shared__ bf16 tile[32][34];
+  const long r0 = (long)blockIdx.y * 32, c0 = (long)blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const long r = r0 + i, c = c0 + tx;
+    tile[i][tx] = (r < R && c < Ccols) ? src[r * ld_src + c] : __float2bfloat16_rn(0.f);
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const long c = c0 + i, r = r0 + tx;
+    if (c < Ccols && r < R) dst[c * ld_dst + r] = tile[tx][i];
+  }
+}
+
 // y = x * keep(i) / (1-p), keep(i) = [hash(seed, i) >= p] -- the same call with the same seed
 // replays the mask for the backward pass (dx = dy * keep / (1-p)).
 __device__ __forceinline__ uint32_t mix32(uint64_t z) {
@@ -295,6 +312,15 @@ dropout_kernel(const float* __restrict__ x, float* __restrict__ y, long n, float
 }
 
 }  // namespace
+
+B2_API int b2_transpose_bf16(const void* src, long ld_src, void* dst, long ld_dst, long R, long C, void* stream) {
+  B2_ARG_CHECK(src && dst && R > 0 && C > 0 && ld_src >= C && ld_dst >= R, "b2_transpose_bf16: bad arguments");
+  dim3 grid((unsigned)((C + 31) / 32), (unsigned)((R + 31) / 32));
+  B2_ARG_CHECK(grid.y <= 65535, "b2_transpose_bf16: too many rows");
+  transpose_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)src, ld_src, (bf16*)dst, ld_dst, R, C);
+  B2_LAUNCH_CHECK("transpose_bf16_kernel");
+  return 0;
+}
 
 B2_API int b2_dropout_f32(const float* x, float* y, long n, float p, unsigned long long seed, void* stream) {
   B2_ARG_CHECK(x && y && n > 0, "b2_dropout_f32: null pointer or empty");

@@ -31,8 +31,10 @@ def _check_input(x, seq_len=None):
 class SmallCNNLRCN(nn.Module):
     """Notebook `LRCN(num_classes, sequence_length, hidden_size, input_shape=(3,64,64))`.
 
-    precision="fp32": every layer in fp32 (parity 1e-4).  precision="bf16": the layer-0 gate GEMM
-    [B*T,16384]x[16384,4H] and the classifier run on the tcgen05 GEMM (bf16 operands, fp32 accumulate)."""
+    precision="fp32": every layer in fp32 (parity 1e-4).  precision="bf16": the frame CNN runs NHWC bf16 on the
+    tcgen05 kernels of csrc/smallcnn_tc.cu (conv2 / conv3 forward, data and weight gradients on the tensor core, BN
+    statistics in the conv epilogues, pooled feature written channel-major as the gate GEMM's A operand), the layer-0
+    gate GEMM [B*T,16384]x[16384,4H] and the classifier on the tcgen05 GEMM (bf16 operands, fp32 accumulate)."""
 
     def __init__(self, num_classes, sequence_length, hidden_size, input_shape=(3, 64, 64), dropout=0.5,
                  lstm_layers=2, precision="fp32"):
@@ -58,6 +60,11 @@ class SmallCNNLRCN(nn.Module):
         B, T, C, H, W = x.shape
         bf16 = self.precision == "bf16"
         y = x.reshape(B * T, C, H, W)
+        if bf16 and ops.smallcnn_trunk_supported(y):
+            # tensor-core path: NHWC bf16 tcgen05 convs, feature written straight in the gate GEMM's layout
+            feat = ops.smallcnn_trunk(y, self, self.training).reshape(B, T, -1)
+            out = ops.rnn_forward(feat, self.lstm, bf16=True)
+            return ops.linear(out.reshape(B, -1), self.fc.weight, self.fc.bias, bf16=True)
         if y.dtype != torch.float32:
             y = y.float()
         y = ops.conv_bn_relu_pool(y, self.conv1, self.bn1, False, self.training)

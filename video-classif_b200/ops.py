@@ -216,6 +216,21 @@ def transpose_cast_bf16(x):
     return buf[:, :R]
 
 
+def transpose_bf16(x):
+    """bf16 [R,C] (any row stride) -> bf16 [C, pad8(R)] view [:, :R]: the K-major form of a bf16 operand for a weight-gradient GEMM."""
+    _chk(x)
+    assert x.dtype == BF16 and x.stride(1) == 1
+    R, C = x.shape
+    buf = torch.empty((C, _pad8(R)), device=x.device, dtype=BF16)
+    call("b2_transpose_bf16", x.data_ptr(), x.stride(0), buf.data_ptr(), buf.stride(0), R, C, stream_ptr())
+    return buf[:, :R]
+
+
+def _kmajor_bf16(x):
+    """[R,C] fp32 or bf16 -> bf16 [C,R] (transposed copy) for gemm_tn."""
+    return transpose_bf16(x) if x.dtype == BF16 else transpose_cast_bf16(x)
+
+
 def ingest_u8(frames_u8, out_h, out_w, frame_index=None, out_dtype=F32, swap_rb=True, divisor=255.0):
     """uint8 [F,H0,W0,3] device frames -> [n_out,3,out_h,out_w]; see b2_ingest_u8."""
     _chk(frames_u8)
@@ -608,7 +623,8 @@ class LSTMLayerFn(torch.autograd.Function):
         big = ctx.bf16 and B * T * 4 * H * In >= TC_MIN_MACS and H % 2 == 0
         H4 = 4 * H
         dG_all = torch.empty((B * T, dirs * H4), device=dout.device, dtype=F32)   # [dG_fwd | dG_bwd]
-        xf = x2 if x2.dtype == F32 else x2.float()
+        xf = x2 if (x2.dtype == F32 or big) else x2.float()     # big: the tcgen05 GEMM takes the bf16 operand as is
+        xt = _kmajor_bf16(xf) if big else None                  # one transposed copy of x for all directions
         for d in range(dirs):
             w_ih, w_hh, b_ih, b_hh = params[4 * d:4 * d + 4]
             gates, cst = saved[2 * d:2 * d + 2]
@@ -619,7 +635,7 @@ class LSTMLayerFn(torch.autograd.Function):
             call("b2_lstm_seq_bwd", do.data_ptr(), dirs * H, oo.data_ptr(), dirs * H, gates.data_ptr(), cst.data_ptr(),
                  w_hh.data_ptr(), dG.data_ptr(), dirs * H4, dWhh.data_ptr(), B, T, H, int(d == 1), stream_ptr())
             if big:
-                dWih = gemm_tn(transpose_cast_bf16(dG), transpose_cast_bf16(xf), out_dtype=F32)
+                dWih = gemm_tn(transpose_cast_bf16(dG), xt, out_dtype=F32)
             else:
                 dWih = sgemm(dG, xf, trans_a=True)
             db = colsum(dG)
@@ -628,8 +644,8 @@ class LSTMLayerFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             # dx = [dG_fwd | dG_bwd] @ [W_ih ; W_ih_reverse]  -- one GEMM over K = dirs*4H
             w_cat = params[0] if dirs == 1 else torch.cat([params[0], params[4]], dim=0)
-            if big:
-                dx = gemm_tn(cast_bf16(dG_all), transpose_cast_bf16(w_cat), out_dtype=F32)
+            if big:      # a bf16 input (the tensor-core CNN's feature) takes its gradient in bf16: half the bytes of the widest tensor
+                dx = gemm_tn(cast_bf16(dG_all), transpose_cast_bf16(w_cat), out_dtype=BF16 if x2.dtype == BF16 else F32)
             else:
                 dx = sgemm(dG_all, w_cat)
             dx = dx.reshape(B, T, In)
@@ -675,7 +691,8 @@ class GRULayerFn(torch.autograd.Function):
         H3 = 3 * H
         big = ctx.bf16 and B * T * H3 * In >= TC_MIN_MACS and H % 8 == 0
         dG_all = torch.empty((B * T, dirs * H3), device=dout.device, dtype=F32)
-        xf = x2 if x2.dtype == F32 else x2.float()
+        xf = x2 if (x2.dtype == F32 or big) else x2.float()
+        xt = _kmajor_bf16(xf) if big else None
         grads = []
         for d in range(dirs):
             w_ih, w_hh, b_ih, b_hh = params[4 * d:4 * d + 4]
@@ -686,7 +703,7 @@ class GRULayerFn(torch.autograd.Function):
                  saved[d].data_ptr(), w_hh.data_ptr(), dG.data_ptr(), dirs * H3, dWhh.data_ptr(), dbhh.data_ptr(), B, T, H,
                  int(d == 1), stream_ptr())
             if big:
-                dWih = gemm_tn(transpose_cast_bf16(dG), transpose_cast_bf16(xf), out_dtype=F32)
+                dWih = gemm_tn(transpose_cast_bf16(dG), xt, out_dtype=F32)
             else:
                 dWih = sgemm(dG, xf, trans_a=True)
             grads += [dWih, dWhh, colsum(dG), dbhh]
@@ -900,3 +917,156 @@ def conv_bn_relu_pool(x, conv, bn, pool, training):
     if training and bn.track_running_stats:
         bn.num_batches_tracked += 1
     return y
+
+
+# ----------------------------------------------------------------------------------------
+# autograd: the whole small-CNN trunk on the bf16 tensor-core path (csrc/smallcnn_tc.cu)
+# ----------------------------------------------------------------------------------------
+
+def _sc_conv(x, w_k, cout, bias=None, stats=None):
+    """b2_sc_conv3x3_bf16: x [N,H,W,Cin] bf16, w_k [Cout,3,3,Cin] bf16 -> raw [N,H,W,Cout] bf16 (+ bias, + statistics)."""
+    N, H, W, Cin = x.shape
+    y = torch.empty((N, H, W, cout), device=x.device, dtype=BF16)
+    s1, s2 = stats if stats is not None else (None, None)
+    call("b2_sc_conv3x3_bf16", x.data_ptr(), N, H, W, Cin, w_k.data_ptr(), cout, y.data_ptr(), ptr(bias), ptr(s1), ptr(s2),
+         stream_ptr())
+    return y
+
+
+def _sc_kernel_weight(w):
+    """torch [Cout,Cin,3,3] fp32 -> [Cout,3,3,Cin] bf16 (forward B operand)."""
+    return w.detach().permute(0, 2, 3, 1).contiguous().to(BF16)
+
+
+def _sc_kernel_weight_dgrad(w):
+    """data-gradient filter: Wd[ci][r][s][co] = w[co][ci][2-r][2-s] as [Cin,3,3,Cout] bf16."""
+    return w.detach().flip(2, 3).permute(1, 2, 3, 0).contiguous().to(BF16)
+
+
+class SmallCNNTrunkFn(torch.autograd.Function):
+    """conv1 -> BN -> ReLU -> conv2 -> BN -> ReLU -> pool -> conv3 -> BN -> ReLU -> pool -> dropout -> channel-major
+    flatten (nb:178-186) as ONE autograd node on the bf16 NHWC tensor-core kernels: raw conv outputs + their batch
+    statistics come from the conv epilogues, BN + ReLU (+ pool) is one element pass per layer, the backward walks
+    BN backward (two passes) -> weight gradient (tcgen05, both operands MN-major) -> data gradient (the forward conv
+    kernel on the flipped filter).  Returns the feature [N, 64 * H/4 * W/4] bf16 = the gate GEMM's A operand."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, g1, be1, w2, b2, g2, be2, w3, b3, g3, be3, running, train, momentum, eps, p_drop, seed):
+        _chk(x, w1, w2, w3)
+        x = x.contiguous()
+        if x.dtype != F32:
+            x = x.float()
+        N, _, H, W = x.shape
+        dev = x.device
+        st = stream_ptr()
+        stats = torch.zeros((3, 2, 64), device=dev, dtype=F32)
+        coef = torch.empty((3, 4, 64), device=dev, dtype=F32)          # scale, shift, mean, rstd per layer
+
+        def finalize(k, gamma, beta, count, C):
+            rm, rv = running[2 * k], running[2 * k + 1]
+            call("b2_sc_bn_finalize", stats[k, 0].data_ptr(), stats[k, 1].data_ptr(), gamma.data_ptr(), beta.data_ptr(), ptr(rm),
+                 ptr(rv), count, float(eps), float(momentum[k]), int(train), coef[k, 0].data_ptr(), coef[k, 1].data_ptr(),
+                 coef[k, 2].data_ptr(), coef[k, 3].data_ptr(), C, st)
+
+        def act(raw, k, pool):
+            n, h, w, c = raw.shape
+            y = torch.empty((n, h // pool, w // pool, c), device=dev, dtype=BF16)
+            call("b2_sc_act_pool_fwd", raw.data_ptr(), coef[k, 0].data_ptr(), coef[k, 1].data_ptr(), y.data_ptr(), n, h, w, c,
+                 pool, st)
+            return y
+
+        raw1 = torch.empty((N, H, W, 16), device=dev, dtype=BF16)
+        call("b2_sc_conv1_fwd", x.data_ptr(), w1.data_ptr(), ptr(b1), raw1.data_ptr(), N, H, W,
+             stats[0, 0].data_ptr() if train else 0, stats[0, 1].data_ptr() if train else 0, st)
+        finalize(0, g1, be1, N * H * W, 16)
+        a1 = act(raw1, 0, 1)
+        raw2 = _sc_conv(a1, _sc_kernel_weight(w2), 32, b2, (stats[1, 0], stats[1, 1]) if train else None)
+        finalize(1, g2, be2, N * H * W, 32)
+        a2 = act(raw2, 1, 2)
+        raw3 = _sc_conv(a2, _sc_kernel_weight(w3), 64, b3, (stats[2, 0], stats[2, 1]) if train else None)
+        finalize(2, g3, be3, N * (H // 2) * (W // 2), 64)
+        a3 = act(raw3, 2, 2)
+        HW = (H // 4) * (W // 4)
+        feat = torch.empty((N, 64 * HW), device=dev, dtype=BF16)
+        call("b2_sc_nhwc_to_chw", a3.data_ptr(), feat.data_ptr(), N, HW, 64, float(p_drop), int(seed), st)
+        ctx.save_for_backward(x, raw1, a1, raw2, a2, raw3, coef, w2, w3)
+        ctx.cfg = (bool(train), float(p_drop), int(seed), b1 is not None, b2 is not None, b3 is not None)
+        return feat
+
+    @staticmethod
+    def backward(ctx, dfeat):
+        x, raw1, a1, raw2, a2, raw3, coef, w2, w3 = ctx.saved_tensors
+        train, p_drop, seed, hb1, hb2, hb3 = ctx.cfg
+        N, _, H, W = x.shape
+        dev = x.device
+        st = stream_ptr()
+        dfeat = dfeat.contiguous()
+        if dfeat.dtype not in (F32, BF16):
+            dfeat = dfeat.float()
+        HW = (H // 4) * (W // 4)
+        s = torch.zeros((3, 2, 64), device=dev, dtype=F32)               # [layer][dbeta | dgamma][channel]
+
+        def bn_bwd(raw, dy, k, pool):
+            n, h, w, c = raw.shape
+            args = (raw.data_ptr(), dy.data_ptr(), coef[k, 0].data_ptr(), coef[k, 1].data_ptr(), coef[k, 2].data_ptr(),
+                    coef[k, 3].data_ptr(), s[k, 0].data_ptr(), s[k, 1].data_ptr())
+            call("b2_sc_act_pool_bwd_reduce", *args, n, h, w, c, pool, st)
+            dz = torch.empty_like(raw)
+            call("b2_sc_act_pool_bwd_apply", *args, int(train), dz.data_ptr(), n, h, w, c, pool, st)
+            return dz
+
+        def wgrad(xa, dz, cin, cout):
+            n, h, w, _ = xa.shape
+            dw = torch.zeros((cout, 3, 3, cin), device=dev, dtype=F32)
+            call("b2_sc_conv3x3_wgrad_bf16", xa.data_ptr(), dz.data_ptr(), n, h, w, cin, cout, dw.data_ptr(), st)
+            return dw.permute(0, 3, 1, 2)                                # torch layout [Cout,Cin,3,3] (a view)
+
+        d3 = torch.empty((N, H // 4, W // 4, 64), device=dev, dtype=BF16)
+        call("b2_sc_chw_to_nhwc", dfeat.data_ptr(), int(dfeat.dtype == BF16), d3.data_ptr(), N, HW, 64, p_drop, seed, st)
+        dz3 = bn_bwd(raw3, d3, 2, 2)
+        dw3 = wgrad(a2, dz3, 32, 64)
+        da2 = _sc_conv(dz3, _sc_kernel_weight_dgrad(w3), 32)
+        dz2 = bn_bwd(raw2, da2, 1, 2)
+        dw2 = wgrad(a1, dz2, 16, 32)
+        da1 = _sc_conv(dz2, _sc_kernel_weight_dgrad(w2), 16)
+        dz1 = bn_bwd(raw1, da1, 0, 1)
+        dw1 = torch.zeros((16, 3, 3, 3), device=dev, dtype=F32)
+        call("b2_sc_conv1_wgrad", x.data_ptr(), dz1.data_ptr(), dw1.data_ptr(), N, H, W, st)
+
+        def dbias(k, C, has):
+            # a bias ahead of train-mode BatchNorm has a zero gradient; eval mode: sum dz = scale * sum dpre
+            if not has:
+                return None
+            return torch.zeros(C, device=dev, dtype=F32) if train else (coef[k, 0, :C] * s[k, 0, :C])
+        return (None, dw1, dbias(0, 16, hb1), s[0, 1, :16], s[0, 0, :16], dw2, dbias(1, 32, hb2), s[1, 1, :32], s[1, 0, :32],
+                dw3, dbias(2, 64, hb3), s[2, 1, :64], s[2, 0, :64], None, None, None, None, None, None)
+
+
+def smallcnn_trunk_supported(x):
+    """The tensor-core trunk needs two exact 2x2 pools and a padded row that fits one TMA box."""
+    return x.dim() == 4 and x.shape[1] == 3 and x.shape[2] % 4 == 0 and x.shape[3] % 4 == 0 and x.shape[3] <= 254
+
+
+def smallcnn_trunk(x, m, training):
+    """x [N,3,H,W] -> feature [N, 64*H/4*W/4] bf16 through SmallCNNTrunkFn; `m` carries conv1-3 / bn1-3 / dropout containers."""
+    bns = (m.bn1, m.bn2, m.bn3)
+    train = training or not all(b.track_running_stats for b in bns)
+    running = [t for b in bns for t in (b.running_mean, b.running_var)]
+    if training:
+        running_arg = running
+    else:
+        running_arg = running           # eval: read only
+    mom = [b.momentum if b.momentum is not None else 0.1 for b in bns]
+    p = m.dropout.p if training else 0.0
+    seed = 0
+    if p > 0.0:
+        _dropout_counter[0] += 1
+        seed = (torch.initial_seed() * 1000003 + _dropout_counter[0]) & 0x7FFFFFFFFFFFFFFF
+    feat = SmallCNNTrunkFn.apply(x, m.conv1.weight, m.conv1.bias, m.bn1.weight, m.bn1.bias, m.conv2.weight, m.conv2.bias,
+                                 m.bn2.weight, m.bn2.bias, m.conv3.weight, m.conv3.bias, m.bn3.weight, m.bn3.bias, running_arg,
+                                 train, mom, m.bn1.eps, p, seed)
+    if training:
+        for b in bns:
+            if b.track_running_stats:
+                b.num_batches_tracked += 1
+    return feat
