@@ -28,6 +28,18 @@ def rate(step, B, steps=20):
 
 print(torch.cuda.get_device_name(0))
 torch.manual_seed(0)
+if "--profile" in sys.argv:           # 4 steps of the B = 64 bf16 path only (for an ncu launch list)
+    B = 64
+    x = torch.rand(B, 20, 3, 64, 64, device=dev) * 255
+    y = torch.randint(0, 50, (B,), device=dev)
+    m = vc.SmallCNNLRCN(50, 20, 32, (3, 64, 64), dropout=0.5, precision="bf16").to(dev).train()
+    opt = torch.optim.Adam(m.parameters(), lr=1e-4, fused=True)
+    for _ in range(4):
+        opt.zero_grad(set_to_none=True)
+        torch.nn.functional.cross_entropy(m(x), y).backward()
+        opt.step()
+    torch.cuda.synchronize()
+    sys.exit(0)
 for B in (8, 64):
     x = torch.rand(B, 20, 3, 64, 64, device=dev) * 255
     y = torch.randint(0, 50, (B,), device=dev)
