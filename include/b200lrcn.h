@@ -207,12 +207,15 @@ int b2_f64_to_f32(const double* src, float* dst, int n, int accumulate, void* st
  * in bf16 NHWC on tcgen05.  One pixel = one swizzle row of 2*C bytes (C = 16 / 32 / 64 -> SWIZZLE_32B / 64B / 128B); a tile is
  * TH whole output rows, its halo comes in by one TMA and every filter tap reads it through a shifted descriptor.
  * b2_sc_conv3x3_bf16: y [N,H,W,Cout] = conv3x3(x [N,H,W,Cin], w [Cout][3][3][Cin]) (+ bias), stride 1, pad 1, + optional
- *   per-channel sum / sum of squares of the stored values (ACCUMULATED).  (Cin, Cout) in {(16,32), (32,64)} (forward) and
+ *   per-channel sum / sum of squares of the stored values (ACCUMULATED).  (Cin, Cout) in {(16,16), (16,32), (32,64)} (forward) and
  *   {(64,32), (32,16)} (their data gradients: w = the flipped, transposed filter).
  * b2_sc_conv3x3_wgrad_bf16: dw [Cout][3][3][Cin] fp32 (ACCUMULATED) = sum over pixels of dz [N,H,W,Cout] x shifted x [N,H,W,Cin].
  * b2_sc_conv1_fwd / _wgrad: the 3-channel first layer on CUDA cores (x fp32 NCHW [N,3,H,W], w / dw fp32 [16][3][3][3] in torch
  *   layout, y / dz bf16 NHWC [N,H,W,16]); dw ACCUMULATED.
- * b2_sc_bn_finalize: (sum, sumsq, count) -> scale, shift, mean, rstd (+ running statistics, momentum; train = 0: from them).
+ * b2_sc_pack_input: x fp32 NCHW [N,3,H,W] -> bf16 NHWC [N,H,W,16] (channels 3..15 zero) so that the first layer runs on the same
+ *   tensor-core kernels ((Cin, Cout) = (16,16), filter zero-padded to 16 input channels).
+ * b2_sc_bn_finalize: (sum, sumsq, count) of the BIAS-FREE raw conv output + the conv bias -> scale, shift, mean, rstd for that
+ *   tensor (+ running statistics of raw + bias, momentum; train = 0: from the running statistics).
  * b2_sc_act_pool_fwd: y = maxpool_pool(relu(raw * scale + shift)), pool in {1, 2}; _bwd_reduce: s1 = sum dpre (= dbeta),
  *   s2 = sum dpre * xhat (= dgamma), ACCUMULATED, dpre = dy routed to the first maximum of its window where positive;
  *   _bwd_apply: dz [N,H,W,C] = scale * (dpre - s1/M - xhat s2/M) (train) or scale * dpre (eval).
@@ -224,16 +227,17 @@ int b2_sc_conv3x3_wgrad_bf16(const void* x, const void* dz, int N, int H, int W,
 int b2_sc_conv1_fwd(const float* x, const float* w, const float* bias, void* y, int N, int H, int W, float* col_sum,
                     float* col_sumsq, void* stream);
 int b2_sc_conv1_wgrad(const float* x, const void* dz, float* dw, int N, int H, int W, void* stream);
-int b2_sc_bn_finalize(const float* sum, const float* sumsq, const float* gamma, const float* beta, float* running_mean,
-                      float* running_var, long count, float eps, float momentum, int train, float* scale, float* shift,
-                      float* mean, float* rstd, int C, void* stream);
+int b2_sc_pack_input(const float* x, void* y, int N, int H, int W, void* stream);
+int b2_sc_bn_finalize(const float* sum, const float* sumsq, const float* conv_bias, const float* gamma, const float* beta,
+                      float* running_mean, float* running_var, long count, float eps, float momentum, int train, float* scale,
+                      float* shift, float* mean, float* rstd, int C, void* stream);
 int b2_sc_act_pool_fwd(const void* raw, const float* scale, const float* shift, void* y, int N, int H, int W, int C, int pool,
                        void* stream);
 int b2_sc_act_pool_bwd_reduce(const void* raw, const void* dy, const float* scale, const float* shift, const float* mean,
                               const float* rstd, float* s1, float* s2, int N, int H, int W, int C, int pool, void* stream);
 int b2_sc_act_pool_bwd_apply(const void* raw, const void* dy, const float* scale, const float* shift, const float* mean,
-                             const float* rstd, const float* s1, const float* s2, int train, void* dz, int N, int H, int W,
-                             int C, int pool, void* stream);
+                             const float* rstd, float* s1, float* s2, int train, void* dz, int N, int H, int W, int C, int pool,
+                             void* stream);
 int b2_sc_nhwc_to_chw(const void* act, void* feat, int N, int HW, int C, float p_drop, unsigned long long seed, void* stream);
 int b2_sc_chw_to_nhwc(const void* dfeat, int in_bf16, void* dact, int N, int HW, int C, float p_drop, unsigned long long seed,
                       void* stream);

@@ -19,7 +19,7 @@ def _bf(t):
     return t.to(torch.bfloat16).float()
 
 
-@pytest.mark.parametrize("cin,cout", [(16, 32), (32, 64), (64, 32), (32, 16)])
+@pytest.mark.parametrize("cin,cout", [(16, 16), (16, 32), (32, 64), (64, 32), (32, 16)])
 @pytest.mark.parametrize("shape", [(3, 64, 64), (5, 32, 32), (2, 16, 16), (2, 20, 12), (1, 8, 124)])
 def test_sc_conv3x3_vs_torch(cin, cout, shape):
     """b2_sc_conv3x3_bf16 (halo tile, one pixel per swizzle row, shifted tap descriptors): output within bf16 rounding
@@ -46,7 +46,7 @@ def test_sc_conv3x3_vs_torch(cin, cout, shape):
         assert err(yd.float().permute(0, 3, 1, 2).cpu(), refd) < 6e-3
 
 
-@pytest.mark.parametrize("cin,cout", [(16, 32), (32, 64)])
+@pytest.mark.parametrize("cin,cout", [(16, 16), (16, 32), (32, 64)])
 @pytest.mark.parametrize("shape", [(3, 64, 64), (7, 32, 32), (2, 16, 16), (2, 20, 12)])
 def test_sc_wgrad_vs_torch(cin, cout, shape):
     """b2_sc_conv3x3_wgrad_bf16 (both operands MN-major, pixel-shifted copies of the x tile fill M): fp32 accumulation of
@@ -114,7 +114,7 @@ def test_sc_bn_act_pool_fwd_bwd_vs_torch_autograd(C, pool, train):
     sums = torch.stack([rawd.float().sum((0, 1, 2)), (rawd.float() ** 2).sum((0, 1, 2))])
     coef = torch.empty(4, C, device=DEV)
     g_d, b_d, rm_d, rv_d = gamma.to(DEV), beta.to(DEV), rm.to(DEV), rv.to(DEV)
-    call("b2_sc_bn_finalize", sums[0].data_ptr(), sums[1].data_ptr(), g_d.data_ptr(), b_d.data_ptr(), rm_d.data_ptr(),
+    call("b2_sc_bn_finalize", sums[0].data_ptr(), sums[1].data_ptr(), 0, g_d.data_ptr(), b_d.data_ptr(), rm_d.data_ptr(),
          rv_d.data_ptr(), N * H * W, 1e-5, 0.1, int(train), coef[0].data_ptr(), coef[1].data_ptr(), coef[2].data_ptr(),
          coef[3].data_ptr(), C, st)
     if train:
@@ -194,3 +194,38 @@ def test_smallcnn_lrcn_bf16_tensor_core_path_vs_reference_golden(tag):
     with torch.no_grad():
         out_e = m(x)
     assert err(out_e, torch.from_numpy(g["logits_eval_after"])) < 3e-2
+
+
+def test_sc_bias_folded_into_bn_finalize_and_input_pack():
+    """The raw conv outputs are stored bias-free; b2_sc_bn_finalize folds the conv bias into the running mean (train) and
+    into the effective mean (eval): BN(conv(x) + b) == scale * conv(x) + shift in both modes.  b2_sc_pack_input: NCHW fp32
+    frames -> NHWC bf16 with 13 zero channels."""
+    from video_classif_b200._lib import call, stream_ptr
+    torch.manual_seed(4)
+    C, M = 32, 4096
+    z = torch.randn(M, C) * 2 + 0.5                       # bias-free conv output, rows = pixels
+    b, gamma, beta = torch.randn(C), torch.rand(C) + 0.5, torch.randn(C)
+    for train in (True, False):
+        rm, rv = torch.randn(C) * 0.3, torch.rand(C) + 0.5
+        bn = torch.nn.BatchNorm1d(C)
+        with torch.no_grad():
+            bn.weight.copy_(gamma); bn.bias.copy_(beta); bn.running_mean.copy_(rm); bn.running_var.copy_(rv)
+        bn.train(train)
+        ref = bn(z + b)
+        zd = z.to(DEV)
+        sums = torch.stack([zd.sum(0), (zd * zd).sum(0)])
+        coef = torch.empty(4, C, device=DEV)
+        d = [t.to(DEV) for t in (b, gamma, beta, rm, rv)]
+        call("b2_sc_bn_finalize", sums[0].data_ptr(), sums[1].data_ptr(), d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(),
+             d[3].data_ptr(), d[4].data_ptr(), M, 1e-5, 0.1, int(train), coef[0].data_ptr(), coef[1].data_ptr(), coef[2].data_ptr(),
+             coef[3].data_ptr(), C, stream_ptr())
+        got = zd * coef[0] + coef[1]
+        assert err(got, ref) < 1e-5
+        if train:
+            assert err(d[3].cpu(), bn.running_mean) < 1e-5 and err(d[4].cpu(), bn.running_var) < 1e-5
+    x = torch.rand(3, 3, 20, 12) * 255
+    y = torch.empty(3, 20, 12, 16, device=DEV, dtype=torch.bfloat16)
+    xd = x.to(DEV)
+    call("b2_sc_pack_input", xd.data_ptr(), y.data_ptr(), 3, 20, 12, stream_ptr())
+    assert torch.equal(y[..., :3].float().cpu(), x.permute(0, 2, 3, 1).to(torch.bfloat16).float())
+    assert (y[..., 3:] == 0).all()

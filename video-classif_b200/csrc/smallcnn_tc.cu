@@ -103,8 +103,8 @@ sc_conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                bf16* __restrict__ y, ScGeom g, const float* __restrict__ bias, float* col_sum, float* col_sumsq) {
   constexpr int RB = CIN * 2;                          // bytes per pixel row
   constexpr int KS = CIN / 16;                         // K = 16 steps per tap
-  constexpr int kWTile = COUT * RB;                    // one tap's [COUT x CIN] weight tile (a multiple of 1024)
-  static_assert(kWTile % 1024 == 0, "weight tiles keep the 1024-byte stage alignment");
+  constexpr int kWBytes = COUT * RB;                   // one tap's [COUT x CIN] weight tile ...
+  constexpr int kWTile = (kWBytes + 1023) / 1024 * 1024;   // ... in a slot that keeps the 1024-byte stage alignment
   constexpr int CW = COUT < 32 ? COUT : 32;            // columns per TMEM load
   constexpr int kChunks = COUT / CW;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -119,6 +119,7 @@ sc_conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   uint64_t* w_bar = tempty_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
   float* stat_s = reinterpret_cast<float*>(after + 128);          // [8 warps][2][COUT]
+  uint32_t* xpose_s = reinterpret_cast<uint32_t*>(after + 128 + 8 * 2 * COUT * 4);   // [8 warps][16][33] words
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const bool want_stats = col_sum != nullptr;
@@ -150,7 +151,7 @@ sc_conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(w_bar, kTaps * kWTile);
+      mbar_expect_tx(w_bar, kTaps * kWBytes);
       for (int t = 0; t < kTaps; ++t) tma_load_2d(w_s + t * kWTile, &tmap_w, w_bar, t * CIN, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -204,9 +205,9 @@ sc_conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     // =========================== epilogue (warps 2..9) ===========================
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;          // the two warps of a lane quarter take alternate accumulator blocks
-    float acc1[kChunks], acc2[kChunks];        // lane l: running sum / sum of squares of channel chunk*32 + l
+    float2 acc1[kChunks], acc2[kChunks];       // lane (w, grp): running sum / sum of squares of channels chunk*CW + 2w, 2w+1
 #pragma unroll
-    for (int c = 0; c < kChunks; ++c) acc1[c] = acc2[c] = 0.f;
+    for (int c = 0; c < kChunks; ++c) acc1[c] = acc2[c] = make_float2(0.f, 0.f);
     int it = 0;
     for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
       const int n = g.tiles_per_img == 1 ? tile : (int)__umulhi((uint32_t)tile, g.magic_tpi);
@@ -245,21 +246,29 @@ sc_conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
                            "r"(pk[8 * s8 + 5]), "r"(pk[8 * s8 + 6]), "r"(pk[8 * s8 + 7])
                            : "memory");
           }
-          if (want_stats) {        // statistics of the values as stored (bf16-rounded)
-            float s2[32];
+          if (want_stats) {
+            // statistics of the values as stored (bf16-rounded): the warp's 32 x CW tile goes through shared memory
+            // column-pair-major (word j of row `lane` at [j][lane], pitch 33 words: conflict-free both ways); lane
+            // (w, grp) then sums column pair w over its CW/2-th share of the rows -- no shuffles (a butterfly
+            // reduce-scatter made the epilogue the bottleneck: 62 SHFL per chunk against one SHFL / clk / SM)
+            constexpr int kWords = CW / 2;                 // packed column pairs per row
+            constexpr int kRowsPer = kWords;               // 32 lanes = kWords column pairs x (32 / kWords) row groups
+            uint32_t* xp = xpose_s + (warp - 2) * (16 * 33);
+            __syncwarp();
 #pragma unroll
-            for (int j = 0; j < CW / 2; ++j) {
-              const float lo = __uint_as_float(pk[j] << 16), hi = __uint_as_float(pk[j] & 0xffff0000u);
-              v[2 * j] = row_ok ? lo : 0.f;
-              v[2 * j + 1] = row_ok ? hi : 0.f;
-            }
+            for (int j = 0; j < kWords; ++j) xp[j * 33 + lane] = row_ok ? pk[j] : 0u;
+            __syncwarp();
+            const int w2 = lane % kWords, grp = lane / kWords;
+            float2 s1 = make_float2(0.f, 0.f), s2 = s1;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (j >= CW) v[j] = 0.f;
-              s2[j] = v[j] * v[j];
+            for (int i = 0; i < kRowsPer; ++i) {
+              const uint32_t u = xp[w2 * 33 + grp * kRowsPer + i];
+              const float2 xv = make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+              s1 = __fadd2_rn(s1, xv);
+              s2 = __ffma2_rn(xv, xv, s2);
             }
-            acc1[c] += colsum32(v, lane);
-            acc2[c] += colsum32(s2, lane);
+            acc1[c] = __fadd2_rn(acc1[c], s1);
+            acc2[c] = __fadd2_rn(acc2[c], s2);
           }
         }
       }
@@ -268,11 +277,22 @@ sc_conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
     if (want_stats) {
+      constexpr int kWords = CW / 2;
 #pragma unroll
-      for (int c = 0; c < kChunks; ++c) {
-        if (lane < CW) {
-          stat_s[((warp - 2) * 2 + 0) * COUT + c * CW + lane] = acc1[c];
-          stat_s[((warp - 2) * 2 + 1) * COUT + c * CW + lane] = acc2[c];
+      for (int c = 0; c < kChunks; ++c) {        // combine the row groups of a column pair, then one writer per slot
+        float2 a = acc1[c], b = acc2[c];
+#pragma unroll
+        for (int off = kWords; off < 32; off <<= 1) {
+          a.x += __shfl_xor_sync(0xffffffffu, a.x, off);
+          a.y += __shfl_xor_sync(0xffffffffu, a.y, off);
+          b.x += __shfl_xor_sync(0xffffffffu, b.x, off);
+          b.y += __shfl_xor_sync(0xffffffffu, b.y, off);
+        }
+        if (lane < kWords) {
+          float* d1 = stat_s + ((warp - 2) * 2 + 0) * COUT + c * CW + 2 * lane;
+          float* d2 = stat_s + ((warp - 2) * 2 + 1) * COUT + c * CW + 2 * lane;
+          d1[0] = a.x; d1[1] = a.y;
+          d2[0] = b.x; d2[1] = b.y;
         }
       }
     }
@@ -610,22 +630,26 @@ sc_conv1_wgrad_kernel(const float* __restrict__ x, const bf16* __restrict__ dz, 
 // ------------------------------------------------------------------------------------------------------------------
 // BatchNorm finalisation, BN + ReLU (+ pool) forward / backward, layout changes
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void sc_bn_finalize_kernel(const float* sum, const float* sumsq, const float* gamma, const float* beta,
-                                      float* running_mean, float* running_var, float inv_count, float unbias, float eps,
-                                      float momentum, int train, float* scale, float* shift, float* mean_out, float* rstd_out,
-                                      int C) {
+// The raw conv outputs are stored WITHOUT the conv bias (train-mode BatchNorm subtracts it again; adding it in the conv epilogue
+// costs 32 loads per TMEM chunk): the bias only shifts the mean, so it is folded in here -- running_mean tracks mean(raw) + bias,
+// and with running statistics (eval) the effective mean of the bias-free tensor is running_mean - bias.
+__global__ void sc_bn_finalize_kernel(const float* sum, const float* sumsq, const float* conv_bias, const float* gamma,
+                                      const float* beta, float* running_mean, float* running_var, float inv_count, float unbias,
+                                      float eps, float momentum, int train, float* scale, float* shift, float* mean_out,
+                                      float* rstd_out, int C) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
+  const float b = conv_bias != nullptr ? conv_bias[c] : 0.f;
   float mean, var;
   if (train) {
     mean = sum[c] * inv_count;
     var = fmaxf(sumsq[c] * inv_count - mean * mean, 0.f);
     if (running_mean != nullptr) {
-      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (mean + b);
       running_var[c] = (1.f - momentum) * running_var[c] + momentum * var * unbias;
     }
   } else {
-    mean = running_mean[c];
+    mean = running_mean[c] - b;
     var = running_var[c];
   }
   const float rstd = rsqrtf(var + eps);
@@ -689,128 +713,144 @@ sc_act_pool_fwd_kernel(const bf16* __restrict__ raw, const float* __restrict__ s
 }
 
 // The gradient arriving at relu(bn(raw)) after un-pooling: window position k gets dy when it is the FIRST maximum of the
-// window (torch's max_pool2d backward) and its activation is positive, else 0.
-template <int POOL>
-__device__ __forceinline__ void route(const bf16* __restrict__ raw, long n, int yo, int xo, int H, int W, int C, int cg,
-                                      const float (&sc)[8], const float (&sh)[8], const float (&dy)[8],
-                                      float (&rawv)[POOL * POOL][8], float (&dpre)[POOL * POOL][8]) {
-  float best[8];
-  int arg[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    best[j] = -1.f;
-    arg[j] = 0;
-  }
-#pragma unroll
-  for (int k = 0; k < POOL * POOL; ++k) {
-    const int dyy = k / POOL, dxx = k % POOL;
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(raw + ((n * H + yo * POOL + dyy) * W + xo * POOL + dxx) * C + cg * 8));
-    unpack8(u, rawv[k]);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float a = fmaxf(fmaf(rawv[k][j], sc[j], sh[j]), 0.f);
-      if (a > best[j]) {
-        best[j] = a;
-        arg[j] = k;
-      }
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < POOL * POOL; ++k)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) dpre[k][j] = (arg[j] == k && best[j] > 0.f) ? dy[j] : 0.f;
-}
-
-// s1[c] += sum dpre ; s2[c] += sum dpre * xhat  (dgamma = s2, dbeta = s1)
-template <int POOL>
-__global__ void __launch_bounds__(256)
-sc_act_pool_bwd_reduce_kernel(const bf16* __restrict__ raw, const bf16* __restrict__ dyp, const float* __restrict__ scale,
-                              const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ rstd,
-                              float* s1, float* s2, int N, int H, int W, int C) {
+// window (torch's max_pool2d backward) and its activation is positive, else 0.  One kernel body serves both passes of the
+// train-mode BatchNorm backward:
+//   APPLY = false   s1[c] += sum dpre ; s2[c] += sum dpre * xhat            (dbeta, dgamma; ACCUMULATED)
+//   APPLY = true    dz = scale * (dpre - s1/M - xhat * s2/M) (train) | scale * dpre (eval), full resolution, every position
+// A thread owns 8 channels; all 128-bit loads of its pixel(s) (POOL = 1: two pixels, 4 loads; POOL = 2: one pooled pixel,
+// 5 loads) are issued before any math (the first version, one pixel in flight at 100+ registers, ran at a third of the copy bandwidth: latency bound); the
+// window stays packed in registers and is unpacked once to find the arg-max and once to emit.
+template <int POOL, bool APPLY>
+__global__ void __launch_bounds__(256, 2)
+sc_act_pool_bwd_kernel(const bf16* __restrict__ raw, const bf16* __restrict__ dyp, const float* __restrict__ scale,
+                       const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ rstd,
+                       float* __restrict__ s1, float* __restrict__ s2, float inv_count, int train, bf16* __restrict__ dz, int N,
+                       int H, int W, int C) {
+  constexpr int KW = POOL * POOL;
   __shared__ float red[2][64];
   const int cgs = C >> 3;
   const int Ho = H / POOL, Wo = W / POOL;
   const long total = (long)N * Ho * Wo * cgs;
-  const long stride = (long)gridDim.x * blockDim.x;
+  const long stride = (long)gridDim.x * blockDim.x;        // a multiple of 8 -> a thread's channel group is fixed
   long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const int cg = (int)(idx % cgs);
-  float sc[8], sh[8], mu[8], rs[8], a1[8], a2[8];
+  float sc[8], sh[8], x1[8], x0[8], m1[8], m2[8];           // xhat = raw * x1 + x0
   load8f(scale + cg * 8, sc);
   load8f(shift + cg * 8, sh);
-  load8f(mean + cg * 8, mu);
-  load8f(rstd + cg * 8, rs);
+  load8f(rstd + cg * 8, x1);
+  load8f(mean + cg * 8, x0);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) a1[j] = a2[j] = 0.f;
-  if (threadIdx.x < 128) red[threadIdx.x >> 6][threadIdx.x & 63] = 0.f;
-  __syncthreads();
-  for (; idx < total; idx += stride) {
-    const long pix = idx / cgs;
+  for (int j = 0; j < 8; ++j) x0[j] = -x0[j] * x1[j];
+  if (APPLY) {
+    load8f(s1 + cg * 8, m1);
+    load8f(s2 + cg * 8, m2);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      m1[j] = train ? m1[j] * inv_count : 0.f;
+      m2[j] = train ? m2[j] * inv_count : 0.f;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m1[j] = m2[j] = 0.f;       // accumulators
+    if (threadIdx.x < 128) red[threadIdx.x >> 6][threadIdx.x & 63] = 0.f;
+    __syncthreads();
+  }
+  auto win_ptr = [&](long pix, int k) {
     const int xo = (int)(pix % Wo);
     const int yo = (int)((pix / Wo) % Ho);
     const long n = pix / ((long)Wo * Ho);
-    float dy[8], rawv[POOL * POOL][8], dpre[POOL * POOL][8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(dyp + pix * C + cg * 8)), dy);
-    route<POOL>(raw, n, yo, xo, H, W, C, cg, sc, sh, dy, rawv, dpre);
+    return ((n * H + yo * POOL + k / POOL) * W + xo * POOL + k % POOL) * C + cg * 8;
+  };
+  auto process = [&](long pix, const uint4 (&rw)[KW], const uint4& dyu) {
+    float dy[8], best[8];
+    int arg[8];
+    unpack8(dyu, dy);
 #pragma unroll
-    for (int k = 0; k < POOL * POOL; ++k)
+    for (int j = 0; j < 8; ++j) {
+      best[j] = -1.f;
+      arg[j] = 0;
+    }
+#pragma unroll
+    for (int k = 0; k < KW; ++k) {
+      float f[8];
+      unpack8(rw[k], f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        a1[j] += dpre[k][j];
-        a2[j] = fmaf(dpre[k][j], (rawv[k][j] - mu[j]) * rs[j], a2[j]);
+        const float a = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
+        if (a > best[j]) {
+          best[j] = a;
+          arg[j] = k;
+        }
       }
-  }
+    }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    atomicAdd(&red[0][cg * 8 + j], a1[j]);
-    atomicAdd(&red[1][cg * 8 + j], a2[j]);
+    for (int k = 0; k < KW; ++k) {
+      float f[8], o[8];
+      unpack8(rw[k], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float dpre = (arg[j] == k && best[j] > 0.f) ? dy[j] : 0.f;
+        const float xh = fmaf(f[j], x1[j], x0[j]);
+        if (APPLY) {
+          o[j] = sc[j] * (dpre - m1[j] - xh * m2[j]);
+        } else {
+          m1[j] += dpre;
+          m2[j] = fmaf(dpre, xh, m2[j]);
+        }
+      }
+      if (APPLY) *reinterpret_cast<uint4*>(dz + win_ptr(pix, k)) = pack8(o);
+    }
+  };
+  if constexpr (POOL == 1) {           // two pixels in flight (4 loads)
+    for (; idx < total; idx += 2 * stride) {
+      const long pa = idx / cgs;
+      const long ib = idx + stride;
+      const bool has_b = ib < total;
+      const long pb = has_b ? ib / cgs : pa;
+      uint4 ra[KW], rb[KW];
+      ra[0] = __ldg(reinterpret_cast<const uint4*>(raw + win_ptr(pa, 0)));
+      const uint4 da = __ldg(reinterpret_cast<const uint4*>(dyp + pa * C + cg * 8));
+      rb[0] = __ldg(reinterpret_cast<const uint4*>(raw + win_ptr(pb, 0)));
+      const uint4 db = __ldg(reinterpret_cast<const uint4*>(dyp + pb * C + cg * 8));
+      process(pa, ra, da);
+      if (has_b) process(pb, rb, db);
+    }
+  } else {                             // one pooled pixel = 5 loads in flight
+    for (; idx < total; idx += stride) {
+      const long pa = idx / cgs;
+      uint4 ra[KW];
+#pragma unroll
+      for (int k = 0; k < KW; ++k) ra[k] = __ldg(reinterpret_cast<const uint4*>(raw + win_ptr(pa, k)));
+      const uint4 da = __ldg(reinterpret_cast<const uint4*>(dyp + pa * C + cg * 8));
+      process(pa, ra, da);
+    }
   }
-  __syncthreads();
-  if (threadIdx.x < C) {
-    atomicAdd(s1 + threadIdx.x, red[0][threadIdx.x]);
-    atomicAdd(s2 + threadIdx.x, red[1][threadIdx.x]);
+  if (!APPLY) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&red[0][cg * 8 + j], m1[j]);
+      atomicAdd(&red[1][cg * 8 + j], m2[j]);
+    }
+    __syncthreads();
+    if (threadIdx.x < C) {
+      atomicAdd(s1 + threadIdx.x, red[0][threadIdx.x]);
+      atomicAdd(s2 + threadIdx.x, red[1][threadIdx.x]);
+    }
   }
 }
 
-// dz = scale * (dpre - s1/M - xhat * s2/M)  (train)  |  scale * dpre  (eval) ; full resolution, every position written
-template <int POOL>
+// x fp32 NCHW [N,3,H,W] -> bf16 NHWC [N,H,W,16] with channels 3..15 zero: the first layer then runs on the same tensor-core
+// kernels as the others (the 0..255 / 0..1 pixel values lose nothing that the bf16 conv input of autocast would keep)
 __global__ void __launch_bounds__(256)
-sc_act_pool_bwd_apply_kernel(const bf16* __restrict__ raw, const bf16* __restrict__ dyp, const float* __restrict__ scale,
-                             const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ rstd,
-                             const float* __restrict__ s1, const float* __restrict__ s2, float inv_count, int train,
-                             bf16* __restrict__ dz, int N, int H, int W, int C) {
-  const int cgs = C >> 3;
-  const int Ho = H / POOL, Wo = W / POOL;
-  const long total = (long)N * Ho * Wo * cgs;
-  const long stride = (long)gridDim.x * blockDim.x;
-  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int cg = (int)(idx % cgs);
-  float sc[8], sh[8], mu[8], rs[8], m1[8], m2[8];
-  load8f(scale + cg * 8, sc);
-  load8f(shift + cg * 8, sh);
-  load8f(mean + cg * 8, mu);
-  load8f(rstd + cg * 8, rs);
-  load8f(s1 + cg * 8, m1);
-  load8f(s2 + cg * 8, m2);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    m1[j] = train ? m1[j] * inv_count : 0.f;
-    m2[j] = train ? m2[j] * inv_count : 0.f;
-  }
-  for (; idx < total; idx += stride) {
-    const long pix = idx / cgs;
-    const int xo = (int)(pix % Wo);
-    const int yo = (int)((pix / Wo) % Ho);
-    const long n = pix / ((long)Wo * Ho);
-    float dy[8], rawv[POOL * POOL][8], dpre[POOL * POOL][8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(dyp + pix * C + cg * 8)), dy);
-    route<POOL>(raw, n, yo, xo, H, W, C, cg, sc, sh, dy, rawv, dpre);
-#pragma unroll
-    for (int k = 0; k < POOL * POOL; ++k) {
-      float o[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = sc[j] * (dpre[k][j] - m1[j] - (rawv[k][j] - mu[j]) * rs[j] * m2[j]);
-      *reinterpret_cast<uint4*>(dz + ((n * H + yo * POOL + k / POOL) * W + xo * POOL + k % POOL) * C + cg * 8) = pack8(o);
-    }
+sc_pack_input_kernel(const float* __restrict__ x, bf16* __restrict__ y, long pixels_per_img, long total) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long n = i / pixels_per_img, p = i - n * pixels_per_img;
+    const float* src = x + n * 3 * pixels_per_img + p;
+    const uint32_t w0 = pack_bf16x2(src[0], src[pixels_per_img]);
+    const uint32_t w1 = pack_bf16x2(src[2 * pixels_per_img], 0.f);
+    uint4* dst = reinterpret_cast<uint4*>(y + i * 16);
+    dst[0] = make_uint4(w0, w1, 0u, 0u);
+    dst[1] = make_uint4(0u, 0u, 0u, 0u);
   }
 }
 
@@ -934,7 +974,7 @@ int make_sc_geom(ScGeom* g, int N, int H, int W, int Cin, int Cout) {
   if (g->Wp > 256) return -1;
   const int rb = Cin * 2;
   const int nb_max = 256 / Cout < 16 ? 256 / Cout : 16;          // two accumulator sets of NB x Cout columns in 512
-  const int w_bytes = kTaps * Cout * rb;
+  const int w_bytes = kTaps * ((Cout * rb + 1023) / 1024 * 1024) + 8 * 16 * 33 * 4;
   double best = -1.0;
   int best_th = 0;
   for (int th = 1; th <= H && th + 2 <= 256; ++th) {
@@ -989,7 +1029,8 @@ int launch_sc_conv(const void* x, int N, int H, int W, const void* w, void* y, c
       return -3;
     }
   }
-  const int smem = kTaps * COUT * CIN * 2 + g.stages * g.stage_bytes + 128 + 8 * 2 * COUT * 4 + 1024;
+  const int w_slot = (COUT * CIN * 2 + 1023) / 1024 * 1024;
+  const int smem = kTaps * w_slot + g.stages * g.stage_bytes + 128 + 8 * 2 * COUT * 4 + 8 * 16 * 33 * 4 + 1024;
   static B2PerDeviceMax attr;
   if (attr.below(smem)) {
     B2_CUDA_CHECK(cudaFuncSetAttribute(sc_conv_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -1061,6 +1102,7 @@ B2_API int b2_sc_conv3x3_bf16(const void* x, int N, int H, int W, int Cin, const
   B2_ARG_CHECK(((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0 && ((uintptr_t)y & 31) == 0, "%s: alignment", who);
   if (int r = load_encode()) return r;
   cudaStream_t st = (cudaStream_t)stream;
+  if (Cin == 16 && Cout == 16) return launch_sc_conv<16, 16>(x, N, H, W, w, y, bias, col_sum, col_sumsq, st, who);
   if (Cin == 16 && Cout == 32) return launch_sc_conv<16, 32>(x, N, H, W, w, y, bias, col_sum, col_sumsq, st, who);
   if (Cin == 32 && Cout == 64) return launch_sc_conv<32, 64>(x, N, H, W, w, y, bias, col_sum, col_sumsq, st, who);
   if (Cin == 64 && Cout == 32) return launch_sc_conv<64, 32>(x, N, H, W, w, y, bias, col_sum, col_sumsq, st, who);
@@ -1077,6 +1119,7 @@ B2_API int b2_sc_conv3x3_wgrad_bf16(const void* x, const void* dz, int N, int H,
   B2_ARG_CHECK(((uintptr_t)x & 15) == 0 && ((uintptr_t)dz & 15) == 0, "%s: alignment", who);
   if (int r = load_encode()) return r;
   cudaStream_t st = (cudaStream_t)stream;
+  if (Cin == 16 && Cout == 16) return launch_sc_wgrad<16, 16>(x, dz, N, H, W, dw, st, who);
   if (Cin == 16 && Cout == 32) return launch_sc_wgrad<16, 32>(x, dz, N, H, W, dw, st, who);
   if (Cin == 32 && Cout == 64) return launch_sc_wgrad<32, 64>(x, dz, N, H, W, dw, st, who);
   b2_set_error("%s: unsupported channel pair (%d -> %d)", who, Cin, Cout);
@@ -1106,15 +1149,25 @@ B2_API int b2_sc_conv1_wgrad(const float* x, const void* dz, float* dw, int N, i
   return 0;
 }
 
-B2_API int b2_sc_bn_finalize(const float* sum, const float* sumsq, const float* gamma, const float* beta, float* running_mean,
-                             float* running_var, long count, float eps, float momentum, int train, float* scale, float* shift,
-                             float* mean, float* rstd, int C, void* stream) {
+// x fp32 NCHW [N,3,H,W] -> bf16 NHWC [N,H,W,16] (channels 3..15 zero)
+B2_API int b2_sc_pack_input(const float* x, void* y, int N, int H, int W, void* stream) {
+  B2_ARG_CHECK(x && y && N > 0 && H > 0 && W > 0 && ((uintptr_t)y & 15) == 0, "b2_sc_pack_input: null pointer, empty shape or alignment");
+  const long total = (long)N * H * W;
+  sc_pack_input_kernel<<<ew_grid_sc(total), 256, 0, (cudaStream_t)stream>>>(x, (bf16*)y, (long)H * W, total);
+  B2_LAUNCH_CHECK("sc_pack_input_kernel");
+  return 0;
+}
+
+B2_API int b2_sc_bn_finalize(const float* sum, const float* sumsq, const float* conv_bias, const float* gamma, const float* beta,
+                             float* running_mean, float* running_var, long count, float eps, float momentum, int train,
+                             float* scale, float* shift, float* mean, float* rstd, int C, void* stream) {
   B2_ARG_CHECK(gamma && beta && scale && shift && mean && rstd && C > 0 && count > 0, "b2_sc_bn_finalize: null pointer or empty");
   B2_ARG_CHECK(train ? (sum && sumsq) : (running_mean && running_var), "b2_sc_bn_finalize: missing statistics");
   const float inv = (float)(1.0 / (double)count);
   const float unbias = count > 1 ? (float)((double)count / (double)(count - 1)) : 1.f;
-  sc_bn_finalize_kernel<<<(C + 63) / 64, 64, 0, (cudaStream_t)stream>>>(sum, sumsq, gamma, beta, running_mean, running_var, inv,
-                                                                        unbias, eps, momentum, train, scale, shift, mean, rstd, C);
+  sc_bn_finalize_kernel<<<(C + 63) / 64, 64, 0, (cudaStream_t)stream>>>(sum, sumsq, conv_bias, gamma, beta, running_mean, running_var,
+                                                                        inv, unbias, eps, momentum, train, scale, shift, mean, rstd,
+                                                                        C);
   B2_LAUNCH_CHECK("sc_bn_finalize_kernel");
   return 0;
 }
@@ -1142,17 +1195,17 @@ B2_API int b2_sc_act_pool_bwd_reduce(const void* raw, const void* dy, const floa
   const long items = (long)N * (H / pool) * (W / pool) * (C / 8);
   cudaStream_t st = (cudaStream_t)stream;
   if (pool == 2)
-    sc_act_pool_bwd_reduce_kernel<2><<<ew_grid_sc(items), 256, 0, st>>>((const bf16*)raw, (const bf16*)dy, scale, shift, mean, rstd,
-                                                                       s1, s2, N, H, W, C);
+    sc_act_pool_bwd_kernel<2, false><<<ew_grid_sc(items), 256, 0, st>>>((const bf16*)raw, (const bf16*)dy, scale, shift, mean, rstd,
+                                                                           s1, s2, 0.f, 1, nullptr, N, H, W, C);
   else
-    sc_act_pool_bwd_reduce_kernel<1><<<ew_grid_sc(items), 256, 0, st>>>((const bf16*)raw, (const bf16*)dy, scale, shift, mean, rstd,
-                                                                       s1, s2, N, H, W, C);
-  B2_LAUNCH_CHECK("sc_act_pool_bwd_reduce_kernel");
+    sc_act_pool_bwd_kernel<1, false><<<ew_grid_sc(items / 2), 256, 0, st>>>((const bf16*)raw, (const bf16*)dy, scale, shift, mean, rstd,
+                                                                           s1, s2, 0.f, 1, nullptr, N, H, W, C);
+  B2_LAUNCH_CHECK("sc_act_pool_bwd_kernel<reduce>");
   return 0;
 }
 
 B2_API int b2_sc_act_pool_bwd_apply(const void* raw, const void* dy, const float* scale, const float* shift, const float* mean,
-                                    const float* rstd, const float* s1, const float* s2, int train, void* dz, int N, int H, int W,
+                                    const float* rstd, float* s1, float* s2, int train, void* dz, int N, int H, int W,
                                     int C, int pool, void* stream) {
   B2_ARG_CHECK(raw && dy && scale && shift && mean && rstd && s1 && s2 && dz, "b2_sc_act_pool_bwd_apply: null pointer");
   B2_ARG_CHECK((C == 16 || C == 32 || C == 64) && (pool == 1 || (pool == 2 && H % 2 == 0 && W % 2 == 0)),
@@ -1161,12 +1214,12 @@ B2_API int b2_sc_act_pool_bwd_apply(const void* raw, const void* dy, const float
   const float inv = (float)(1.0 / ((double)N * H * W));
   cudaStream_t st = (cudaStream_t)stream;
   if (pool == 2)
-    sc_act_pool_bwd_apply_kernel<2><<<ew_grid_sc(items), 256, 0, st>>>((const bf16*)raw, (const bf16*)dy, scale, shift, mean, rstd, s1,
-                                                                      s2, inv, train, (bf16*)dz, N, H, W, C);
+    sc_act_pool_bwd_kernel<2, true><<<ew_grid_sc(items), 256, 0, st>>>((const bf16*)raw, (const bf16*)dy, scale, shift, mean, rstd, s1,
+                                                                          s2, inv, train, (bf16*)dz, N, H, W, C);
   else
-    sc_act_pool_bwd_apply_kernel<1><<<ew_grid_sc(items), 256, 0, st>>>((const bf16*)raw, (const bf16*)dy, scale, shift, mean, rstd, s1,
-                                                                      s2, inv, train, (bf16*)dz, N, H, W, C);
-  B2_LAUNCH_CHECK("sc_act_pool_bwd_apply_kernel");
+    sc_act_pool_bwd_kernel<1, true><<<ew_grid_sc(items / 2), 256, 0, st>>>((const bf16*)raw, (const bf16*)dy, scale, shift, mean, rstd, s1,
+                                                                          s2, inv, train, (bf16*)dz, N, H, W, C);
+  B2_LAUNCH_CHECK("sc_act_pool_bwd_kernel<apply>");
   return 0;
 }
 

@@ -962,10 +962,10 @@ class SmallCNNTrunkFn(torch.autograd.Function):
         stats = torch.zeros((3, 2, 64), device=dev, dtype=F32)
         coef = torch.empty((3, 4, 64), device=dev, dtype=F32)          # scale, shift, mean, rstd per layer
 
-        def finalize(k, gamma, beta, count, C):
+        def finalize(k, bias, gamma, beta, count, C):
             rm, rv = running[2 * k], running[2 * k + 1]
-            call("b2_sc_bn_finalize", stats[k, 0].data_ptr(), stats[k, 1].data_ptr(), gamma.data_ptr(), beta.data_ptr(), ptr(rm),
-                 ptr(rv), count, float(eps), float(momentum[k]), int(train), coef[k, 0].data_ptr(), coef[k, 1].data_ptr(),
+            call("b2_sc_bn_finalize", stats[k, 0].data_ptr(), stats[k, 1].data_ptr(), ptr(bias), gamma.data_ptr(), beta.data_ptr(),
+                 ptr(rm), ptr(rv), count, float(eps), float(momentum[k]), int(train), coef[k, 0].data_ptr(), coef[k, 1].data_ptr(),
                  coef[k, 2].data_ptr(), coef[k, 3].data_ptr(), C, st)
 
         def act(raw, k, pool):
@@ -975,29 +975,36 @@ class SmallCNNTrunkFn(torch.autograd.Function):
                  pool, st)
             return y
 
-        raw1 = torch.empty((N, H, W, 16), device=dev, dtype=BF16)
-        call("b2_sc_conv1_fwd", x.data_ptr(), w1.data_ptr(), ptr(b1), raw1.data_ptr(), N, H, W,
-             stats[0, 0].data_ptr() if train else 0, stats[0, 1].data_ptr() if train else 0, st)
-        finalize(0, g1, be1, N * H * W, 16)
+        def layer_stats(k):
+            return (stats[k, 0], stats[k, 1]) if train else None
+
+        # the conv bias is folded into the BatchNorm finalisation (raw tensors are stored bias-free)
+        x16 = torch.empty((N, H, W, 16), device=dev, dtype=BF16)        # frames as NHWC bf16, channels 3..15 zero
+        call("b2_sc_pack_input", x.data_ptr(), x16.data_ptr(), N, H, W, st)
+        w1k = torch.zeros((16, 3, 3, 16), device=dev, dtype=BF16)
+        w1k[..., :3] = w1.detach().permute(0, 2, 3, 1)
+        raw1 = _sc_conv(x16, w1k, 16, None, layer_stats(0))
+        finalize(0, b1, g1, be1, N * H * W, 16)
         a1 = act(raw1, 0, 1)
-        raw2 = _sc_conv(a1, _sc_kernel_weight(w2), 32, b2, (stats[1, 0], stats[1, 1]) if train else None)
-        finalize(1, g2, be2, N * H * W, 32)
+        raw2 = _sc_conv(a1, _sc_kernel_weight(w2), 32, None, layer_stats(1))
+        finalize(1, b2, g2, be2, N * H * W, 32)
         a2 = act(raw2, 1, 2)
-        raw3 = _sc_conv(a2, _sc_kernel_weight(w3), 64, b3, (stats[2, 0], stats[2, 1]) if train else None)
-        finalize(2, g3, be3, N * (H // 2) * (W // 2), 64)
+        raw3 = _sc_conv(a2, _sc_kernel_weight(w3), 64, None, layer_stats(2))
+        finalize(2, b3, g3, be3, N * (H // 2) * (W // 2), 64)
         a3 = act(raw3, 2, 2)
         HW = (H // 4) * (W // 4)
         feat = torch.empty((N, 64 * HW), device=dev, dtype=BF16)
         call("b2_sc_nhwc_to_chw", a3.data_ptr(), feat.data_ptr(), N, HW, 64, float(p_drop), int(seed), st)
-        ctx.save_for_backward(x, raw1, a1, raw2, a2, raw3, coef, w2, w3)
+        ctx.save_for_backward(x16, raw1, a1, raw2, a2, raw3, coef, w2, w3)
         ctx.cfg = (bool(train), float(p_drop), int(seed), b1 is not None, b2 is not None, b3 is not None)
         return feat
 
     @staticmethod
     def backward(ctx, dfeat):
-        x, raw1, a1, raw2, a2, raw3, coef, w2, w3 = ctx.saved_tensors
+        x16, raw1, a1, raw2, a2, raw3, coef, w2, w3 = ctx.saved_tensors
         train, p_drop, seed, hb1, hb2, hb3 = ctx.cfg
-        N, _, H, W = x.shape
+        N, H, W, _ = x16.shape
+        x = x16
         dev = x.device
         st = stream_ptr()
         dfeat = dfeat.contiguous()
@@ -1030,8 +1037,7 @@ class SmallCNNTrunkFn(torch.autograd.Function):
         dw2 = wgrad(a1, dz2, 16, 32)
         da1 = _sc_conv(dz2, _sc_kernel_weight_dgrad(w2), 16)
         dz1 = bn_bwd(raw1, da1, 0, 1)
-        dw1 = torch.zeros((16, 3, 3, 3), device=dev, dtype=F32)
-        call("b2_sc_conv1_wgrad", x.data_ptr(), dz1.data_ptr(), dw1.data_ptr(), N, H, W, st)
+        dw1 = wgrad(x16, dz1, 16, 16)[:, :3]                              # the zero-padded input channels carry no gradient
 
         def dbias(k, C, has):
             # a bias ahead of train-mode BatchNorm has a zero gradient; eval mode: sum dz = scale * sum dpre
