@@ -690,11 +690,14 @@ sc_act_pool_fwd_kernel(const bf16* __restrict__ raw, const float* __restrict__ s
   float sc[8], sh[8];
   load8f(scale + cg * 8, sc);
   load8f(shift + cg * 8, sh);
+  const int sh_cg = cgs == 8 ? 3 : (cgs == 4 ? 2 : 1);     // 32-bit index math: 64-bit divisions made these passes ALU bound
   for (; idx < total; idx += stride) {
-    const long pix = idx / cgs;
-    const int xo = (int)(pix % Wo);
-    const int yo = (int)((pix / Wo) % Ho);
-    const long n = pix / ((long)Wo * Ho);
+    const uint32_t pix = (uint32_t)(idx >> sh_cg);
+    const uint32_t t = pix / (uint32_t)Wo;
+    const uint32_t xo = pix - t * (uint32_t)Wo;
+    const uint32_t n = t / (uint32_t)Ho;
+    const uint32_t yo = t - n * (uint32_t)Ho;
+    const bf16* win = raw + (((long)n * H + yo * POOL) * W + xo * POOL) * C + cg * 8;
     float best[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) best[j] = 0.f;                // relu floor
@@ -702,13 +705,13 @@ sc_act_pool_fwd_kernel(const bf16* __restrict__ raw, const float* __restrict__ s
     for (int dy = 0; dy < POOL; ++dy)
 #pragma unroll
       for (int dx = 0; dx < POOL; ++dx) {
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(raw + ((n * H + yo * POOL + dy) * W + xo * POOL + dx) * C + cg * 8));
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(win + ((long)dy * W + dx) * C));
         float f[8];
         unpack8(u, f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) best[j] = fmaxf(best[j], fmaf(f[j], sc[j], sh[j]));
       }
-    *reinterpret_cast<uint4*>(y + pix * C + cg * 8) = pack8(best);
+    *reinterpret_cast<uint4*>(y + (long)pix * C + cg * 8) = pack8(best);
   }
 }
 
@@ -755,13 +758,17 @@ sc_act_pool_bwd_kernel(const bf16* __restrict__ raw, const bf16* __restrict__ dy
     if (threadIdx.x < 128) red[threadIdx.x >> 6][threadIdx.x & 63] = 0.f;
     __syncthreads();
   }
-  auto win_ptr = [&](long pix, int k) {
-    const int xo = (int)(pix % Wo);
-    const int yo = (int)((pix / Wo) % Ho);
-    const long n = pix / ((long)Wo * Ho);
-    return ((n * H + yo * POOL + k / POOL) * W + xo * POOL + k % POOL) * C + cg * 8;
+  const int sh_cg = cgs == 8 ? 3 : (cgs == 4 ? 2 : 1);
+  auto win_base = [&](uint32_t pix) {        // element offset of window position 0 (32-bit index math, one division pair per pixel)
+    if (POOL == 1) return (long)pix * C + cg * 8;
+    const uint32_t t = pix / (uint32_t)Wo;
+    const uint32_t xo = pix - t * (uint32_t)Wo;
+    const uint32_t n = t / (uint32_t)Ho;
+    const uint32_t yo = t - n * (uint32_t)Ho;
+    return (((long)n * H + yo * POOL) * W + xo * POOL) * C + cg * 8;
   };
-  auto process = [&](long pix, const uint4 (&rw)[KW], const uint4& dyu) {
+  auto win_off = [&](int k) { return ((long)(k / POOL) * W + (k % POOL)) * C; };
+  auto process = [&](long base, const uint4 (&rw)[KW], const uint4& dyu) {
     float dy[8], best[8];
     int arg[8];
     unpack8(dyu, dy);
@@ -798,31 +805,32 @@ sc_act_pool_bwd_kernel(const bf16* __restrict__ raw, const bf16* __restrict__ dy
           m2[j] = fmaf(dpre, xh, m2[j]);
         }
       }
-      if (APPLY) *reinterpret_cast<uint4*>(dz + win_ptr(pix, k)) = pack8(o);
+      if (APPLY) *reinterpret_cast<uint4*>(dz + base + win_off(k)) = pack8(o);
     }
   };
   if constexpr (POOL == 1) {           // two pixels in flight (4 loads)
     for (; idx < total; idx += 2 * stride) {
-      const long pa = idx / cgs;
       const long ib = idx + stride;
       const bool has_b = ib < total;
-      const long pb = has_b ? ib / cgs : pa;
+      const uint32_t pa = (uint32_t)(idx >> sh_cg), pb = has_b ? (uint32_t)(ib >> sh_cg) : pa;
+      const long ba = win_base(pa), bb = win_base(pb);
       uint4 ra[KW], rb[KW];
-      ra[0] = __ldg(reinterpret_cast<const uint4*>(raw + win_ptr(pa, 0)));
-      const uint4 da = __ldg(reinterpret_cast<const uint4*>(dyp + pa * C + cg * 8));
-      rb[0] = __ldg(reinterpret_cast<const uint4*>(raw + win_ptr(pb, 0)));
-      const uint4 db = __ldg(reinterpret_cast<const uint4*>(dyp + pb * C + cg * 8));
-      process(pa, ra, da);
-      if (has_b) process(pb, rb, db);
+      ra[0] = __ldg(reinterpret_cast<const uint4*>(raw + ba));
+      const uint4 da = __ldg(reinterpret_cast<const uint4*>(dyp + ba));
+      rb[0] = __ldg(reinterpret_cast<const uint4*>(raw + bb));
+      const uint4 db = __ldg(reinterpret_cast<const uint4*>(dyp + bb));
+      process(ba, ra, da);
+      if (has_b) process(bb, rb, db);
     }
   } else {                             // one pooled pixel = 5 loads in flight
     for (; idx < total; idx += stride) {
-      const long pa = idx / cgs;
+      const uint32_t pa = (uint32_t)(idx >> sh_cg);
+      const long ba = win_base(pa);
       uint4 ra[KW];
 #pragma unroll
-      for (int k = 0; k < KW; ++k) ra[k] = __ldg(reinterpret_cast<const uint4*>(raw + win_ptr(pa, k)));
-      const uint4 da = __ldg(reinterpret_cast<const uint4*>(dyp + pa * C + cg * 8));
-      process(pa, ra, da);
+      for (int k = 0; k < KW; ++k) ra[k] = __ldg(reinterpret_cast<const uint4*>(raw + ba + win_off(k)));
+      const uint4 da = __ldg(reinterpret_cast<const uint4*>(dyp + (long)pa * C + cg * 8));
+      process(ba, ra, da);
     }
   }
   if (!APPLY) {
@@ -1179,6 +1187,7 @@ B2_API int b2_sc_act_pool_fwd(const void* raw, const float* scale, const float* 
   B2_ARG_CHECK((C == 16 || C == 32 || C == 64) && (pool == 1 || (pool == 2 && H % 2 == 0 && W % 2 == 0)),
                "b2_sc_act_pool_fwd: C in {16,32,64}, pool 1 or 2 (even H, W)");
   const long items = (long)N * (H / pool) * (W / pool) * (C / 8);
+  B2_ARG_CHECK((long)N * H * W < (1L << 31), "b2_sc_act_pool_fwd: too many pixels for 32-bit index math");
   cudaStream_t st = (cudaStream_t)stream;
   if (pool == 2) sc_act_pool_fwd_kernel<2><<<ew_grid_sc(items), 256, 0, st>>>((const bf16*)raw, scale, shift, (bf16*)y, N, H, W, C);
   else sc_act_pool_fwd_kernel<1><<<ew_grid_sc(items), 256, 0, st>>>((const bf16*)raw, scale, shift, (bf16*)y, N, H, W, C);
@@ -1192,6 +1201,7 @@ B2_API int b2_sc_act_pool_bwd_reduce(const void* raw, const void* dy, const floa
   B2_ARG_CHECK(raw && dy && scale && shift && mean && rstd && s1 && s2, "b2_sc_act_pool_bwd_reduce: null pointer");
   B2_ARG_CHECK((C == 16 || C == 32 || C == 64) && (pool == 1 || (pool == 2 && H % 2 == 0 && W % 2 == 0)),
                "b2_sc_act_pool_bwd_reduce: C in {16,32,64}, pool 1 or 2 (even H, W)");
+  B2_ARG_CHECK((long)N * H * W < (1L << 31), "b2_sc_act_pool_bwd_reduce: too many pixels for 32-bit index math");
   const long items = (long)N * (H / pool) * (W / pool) * (C / 8);
   cudaStream_t st = (cudaStream_t)stream;
   if (pool == 2)
@@ -1210,6 +1220,7 @@ B2_API int b2_sc_act_pool_bwd_apply(const void* raw, const void* dy, const float
   B2_ARG_CHECK(raw && dy && scale && shift && mean && rstd && s1 && s2 && dz, "b2_sc_act_pool_bwd_apply: null pointer");
   B2_ARG_CHECK((C == 16 || C == 32 || C == 64) && (pool == 1 || (pool == 2 && H % 2 == 0 && W % 2 == 0)),
                "b2_sc_act_pool_bwd_apply: C in {16,32,64}, pool 1 or 2 (even H, W)");
+  B2_ARG_CHECK((long)N * H * W < (1L << 31), "b2_sc_act_pool_bwd_apply: too many pixels for 32-bit index math");
   const long items = (long)N * (H / pool) * (W / pool) * (C / 8);
   const float inv = (float)(1.0 / ((double)N * H * W));
   cudaStream_t st = (cudaStream_t)stream;
