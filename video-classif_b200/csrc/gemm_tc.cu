@@ -96,6 +96,7 @@ struct EpiParams {
   int relu;
   int tma_store;     // bf16 output leaves through smem staging + TMA bulk stores (tmap_d valid)
   int store;         // 0: statistics-only pass, D is never written
+  int k_splits;      // > 1 (plain GEMM, fp32 output, EPI_GENERIC): gridDim.y CTAs share a tile's K range and ADD into a zeroed D
   const float* o_scale;   // [N] or null: BatchNorm of the output applied in the epilogue
   const float* o_shift;
   const bf16* res;        // [M][ldres] or null: shortcut added before the ReLU
@@ -181,7 +182,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int m_blocks = CL ? (((M + BM - 1) / BM + 1) & ~1) : (M + BM - 1) / BM;
   const int n_blocks = (N + BN - 1) / BN;
   const int num_tiles = m_blocks * n_blocks;
-  const int k_blocks = (K + BK - 1) / BK;
+  // split-K (skinny products such as the LSTM gate GEMM [B*T,16384] x [16384,4H]: 20 output tiles would leave 128 SMs idle
+  // on a 47 MB operand stream): blockIdx.y owns k-blocks [kb0, kb0 + k_blocks) and its epilogue adds into D
+  const int k_blocks_all = (K + BK - 1) / BK;
+  const int kb_per = MODE == EPI_GENERIC && gridDim.y > 1 ? (k_blocks_all + (int)gridDim.y - 1) / (int)gridDim.y : k_blocks_all;
+  const int kb0 = MODE == EPI_GENERIC ? (int)blockIdx.y * kb_per : 0;
+  const int k_blocks = k_blocks_all - kb0 < kb_per ? k_blocks_all - kb0 : kb_per;     // >= 1 (the host sizes gridDim.y)
+  const bool split_k = MODE == EPI_GENERIC && gridDim.y > 1;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
@@ -244,14 +251,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               ++tap;
             }
           } else {
-            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], (kb0 + kb) * BK, m_blk * BM);
           }
           if (CL) {
             const int rank = (int)cluster_ctarank();
-            tma_load_2d_multicast(sb + rank * (BN / 2) * BK * 2, &tmap_b, &full_bar[stage], kb * BK,
+            tma_load_2d_multicast(sb + rank * (BN / 2) * BK * 2, &tmap_b, &full_bar[stage], (kb0 + kb) * BK,
                                   n_blk * BN + rank * (BN / 2), (uint16_t)3);
           } else {
-            tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
+            tma_load_2d(sb, &tmap_b, &full_bar[stage], (kb0 + kb) * BK, n_blk * BN);
           }
           if (++stage == kStages) {
             stage = 0;
@@ -513,7 +520,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
           for (int jj = 0; jj < 32; ++jj) v[jj] = __uint_as_float(raw[jj]);
           // every option below is a WARP-UNIFORM branch around its own loop
-          if (kGeneric && ep.bias != nullptr) {
+          if (kGeneric && ep.bias != nullptr && kb0 == 0) {
             if (full_chunk) {
 #pragma unroll
               for (int jj = 0; jj < 32; jj += 4) {
@@ -525,7 +532,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 if (col0 + jj < N) v[jj] += __ldg(ep.bias + col0 + jj);
             }
           }
-          if (kGeneric && ep.bias2 != nullptr) {
+          if (kGeneric && ep.bias2 != nullptr && kb0 == 0) {
             for (int jj = 0; jj < 32; ++jj)
               if (col0 + jj < N) v[jj] += __ldg(ep.bias2 + col0 + jj);
           }
@@ -612,7 +619,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 for (int jj = 0; jj < 32; ++jj) v[jj] = fmaxf(v[jj], 0.0f);
               }
               float* dp = reinterpret_cast<float*>(ep.D) + (long)row * ep.ldd + col0;
-              if (full_chunk && ((reinterpret_cast<uintptr_t>(dp) & 31) == 0)) {
+              if (split_k) {                    // partial sum of this K range: vector reductions into the zeroed output
+                if (full_chunk && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0)) {
+#pragma unroll
+                  for (int jj = 0; jj < 32; jj += 4)
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dp + jj), "f"(v[jj]), "f"(v[jj + 1]),
+                                 "f"(v[jj + 2]), "f"(v[jj + 3])
+                                 : "memory");
+                } else {
+                  for (int jj = 0; jj < 32; ++jj)
+                    if (col0 + jj < N) atomicAdd(dp + jj, v[jj]);
+                }
+              } else if (full_chunk && ((reinterpret_cast<uintptr_t>(dp) & 31) == 0)) {
 #pragma unroll
                 for (int jj = 0; jj < 32; jj += 8)
                   asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dp + jj), "f"(v[jj]), "f"(v[jj + 1]),
@@ -738,7 +756,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int r = 0, s = 0, slab = 0;
       const unsigned uH = g.is_conv ? (unsigned)g.H : 0x7fffffffu, uW = g.is_conv ? (unsigned)g.W : 0x7fffffffu;
       for (int kb = 0; kb < k_blocks; ++kb) {
-        const int c0 = (g.is_conv ? slab : kb) * BK + c * 8;
+        const int c0 = (g.is_conv ? slab : kb0 + kb) * BK + c * 8;
         const float4 sc0 = __ldg(reinterpret_cast<const float4*>(at.scale + c0));
         const float4 sc1 = __ldg(reinterpret_cast<const float4*>(at.scale + c0 + 4));
         const float4 sh0 = __ldg(reinterpret_cast<const float4*>(at.shift + c0));
@@ -893,7 +911,8 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
   int grid = tiles < b2_num_sms() ? tiles : b2_num_sms();
   if (CL) grid &= ~1;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid);
+  const int splits = (MODE == EPI_GENERIC && ep.k_splits > 1) ? ep.k_splits : 1;
+  cfg.gridDim = dim3(grid, splits);
   cfg.blockDim = dim3(TF ? kThreadsTf : kThreadsNoTf);
   cfg.dynamicSmemBytes = L::kTotal;
   cfg.stream = stream;
@@ -1518,8 +1537,21 @@ B2_API int b2_gemm_bf16_tn(const void* A, long lda, const void* B, long ldb, voi
   if (int r = make_tmap_2d(&tb, B, N, K, ldb, bn)) return r;
   ConvGeom g = {};
   ATransform at = {};
-  return dispatch(bn, ta, tb, M, N, K, g, at, plain_epi(D, ldd, bias, bias2, out_bf16, relu, col_sum, col_sumsq),
-                  (cudaStream_t)stream);
+  EpiParams ep = plain_epi(D, ldd, bias, bias2, out_bf16, relu, col_sum, col_sumsq);
+  // skinny output, long reduction (the hoisted LSTM gate GEMM X[B*T,16384] W_ih^T[16384,4H]): split K over the idle SMs
+  const int tiles = b2_ceil_div(M, BM) * b2_ceil_div(N, bn);
+  const int k_blocks = b2_ceil_div(K, BK);
+  if (!out_bf16 && !relu && col_sum == nullptr && tiles * 2 <= b2_num_sms() && k_blocks >= 32 && getenv("B2_NO_SPLITK") == nullptr) {
+    int splits = b2_num_sms() / tiles;
+    if (splits > k_blocks / 8) splits = k_blocks / 8;
+    const int per = b2_ceil_div(k_blocks, splits);
+    splits = b2_ceil_div(k_blocks, per);                 // every split owns at least one k-block
+    if (splits > 1) {
+      ep.k_splits = splits;
+      B2_CUDA_CHECK(cudaMemset2DAsync(D, (size_t)ldd * 4, 0, (size_t)N * 4, (size_t)M, (cudaStream_t)stream));
+    }
+  }
+  return dispatch(bn, ta, tb, M, N, K, g, at, ep, (cudaStream_t)stream);
 }
 
 // D[M,N] (bf16) = relu?(A[M,K] * a_scale[k] + a_shift[k]) B[N,K]^T with the pre-activation BatchNorm of a DenseNet layer

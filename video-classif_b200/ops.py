@@ -6,6 +6,8 @@ every arithmetic step of the forward and backward pass is a b2_* kernel.  No CPU
 entry points raise B200LrcnError when the tensors are not on an sm_100 device."""
 from __future__ import annotations
 
+import weakref
+
 import torch
 
 from . import _lib
@@ -204,6 +206,25 @@ def cast_bf16(x):
     y = torch.empty(x.shape, device=x.device, dtype=BF16)
     call("b2_cast_f32_bf16", x.data_ptr(), y.data_ptr(), x.numel(), stream_ptr())
     return y
+
+
+_weight_cache = weakref.WeakKeyDictionary()      # parameter -> {kind: (data_ptr, _version, bf16 copy)}
+
+
+def _cached_weight(w, kind):
+    """bf16 ("cast") or transposed bf16 ("tcast") copy of a weight, reused while the parameter is unchanged (same storage,
+    same version counter): eval / serving and frozen layers pay the conversion once, a training step once per optimizer
+    update instead of once per use (forward + backward)."""
+    if not isinstance(w, torch.nn.Parameter) and w.requires_grad:
+        return cast_bf16(w) if kind == "cast" else transpose_cast_bf16(w)      # a differentiable view (stacked heads): no cache
+    slot = _weight_cache.get(w)
+    if slot is None:
+        slot = _weight_cache[w] = {}
+    ent = slot.get(kind)
+    if ent is None or ent[0] != w.data_ptr() or ent[1] != w._version:
+        copy = cast_bf16(w.detach()) if kind == "cast" else transpose_cast_bf16(w.detach())
+        ent = slot[kind] = (w.data_ptr(), w._version, copy)
+    return ent[2]
 
 
 def transpose_cast_bf16(x):
@@ -451,7 +472,7 @@ def _linear_fwd(x2, weight, bias, bf16, bias2=None):
     N = weight.shape[0]
     if bf16 and M * N * K >= TC_MIN_MACS and K % 8 == 0:
         xa = x2 if x2.dtype == BF16 else cast_bf16(x2)
-        return gemm_tn(xa, cast_bf16(weight), bias=bias, bias2=bias2, out_dtype=F32)
+        return gemm_tn(xa, _cached_weight(weight, "cast"), bias=bias, bias2=bias2, out_dtype=F32)
     xf = x2 if x2.dtype == F32 else x2.float()
     return sgemm(xf, weight, trans_b=True, bias=bias, bias2=bias2)
 
@@ -484,7 +505,7 @@ class LinearFn(torch.autograd.Function):
         big = ctx.bf16 and M * N * K >= TC_MIN_MACS
         if ctx.needs_input_grad[0]:
             if big and N % 8 == 0:
-                dx = gemm_tn(cast_bf16(dy2), transpose_cast_bf16(weight), out_dtype=F32)   # [M,N]x[K,N]^T
+                dx = gemm_tn(cast_bf16(dy2), _cached_weight(weight, "tcast"), out_dtype=F32)   # [M,N]x[K,N]^T
             else:
                 dx = sgemm(dy2, weight)
             dx = dx.reshape(ctx.x_shape)
@@ -645,7 +666,8 @@ class LSTMLayerFn(torch.autograd.Function):
             # dx = [dG_fwd | dG_bwd] @ [W_ih ; W_ih_reverse]  -- one GEMM over K = dirs*4H
             w_cat = params[0] if dirs == 1 else torch.cat([params[0], params[4]], dim=0)
             if big:      # a bf16 input (the tensor-core CNN's feature) takes its gradient in bf16: half the bytes of the widest tensor
-                dx = gemm_tn(cast_bf16(dG_all), transpose_cast_bf16(w_cat), out_dtype=BF16 if x2.dtype == BF16 else F32)
+                w_t = _cached_weight(w_cat, "tcast") if dirs == 1 else transpose_cast_bf16(w_cat)
+                dx = gemm_tn(cast_bf16(dG_all), w_t, out_dtype=BF16 if x2.dtype == BF16 else F32)
             else:
                 dx = sgemm(dG_all, w_cat)
             dx = dx.reshape(B, T, In)
