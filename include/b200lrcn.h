@@ -163,6 +163,9 @@ int b2_transpose_cast_f32_bf16(const float* src, long ld_src, void* dst, long ld
 /* nn.Dropout(p) in train mode (nb:163, models.py:153,182): y = x*keep/(1-p) with a counter-hash
  * mask; calling it again with the same seed on dy replays the mask for the backward pass. */
 int b2_dropout_f32(const float* x, float* y, long n, float p, unsigned long long seed, void* stream);
+/* stand-alone activations (models_bidir.py:119-155 Adapt 's'/'g'/'r', F.silu head): kind 0 relu, 1 gelu (erf), 2 silu; x = the pre-activation */
+int b2_act_fwd_f32(const float* x, float* y, long n, int kind, void* stream);
+int b2_act_bwd_f32(const float* dy, const float* x, float* dx, long n, int kind, void* stream);
 int b2_transpose_bf16(const void* src, long ld_src, void* dst, long ld_dst, long R, long C, void* stream);   /* dst[c][r] = src[r][c], bf16 */
 
 /* ---- K3/K4 persistent LSTM --------------------------------------------------------------

@@ -129,6 +129,44 @@ def ucf50_lrcn(**conf):
     return g["LRCN"], g
 
 
+def ucf50_lrcn_full(**conf):
+    """class LRCN of lrcn/ucf50-lrcn.py:252-336 together with that file's own RMSNorm / ParallelMamba / ResidualBlock
+    (:123-250), so that rnn_type='mamba' constructs."""
+    base = dict(CONF_CNN_BACKBONE="resnet50", CONF_RNN_TYPE="lstm", CONF_RNN_OUT="all",
+                CONF_RNN_LAYER=4, CONF_CLASSIF_MODE="multiclass")
+    base.update(conf)
+    g = _base_globals(**base)
+    _exec_lines(os.path.join(REF_ROOT, "lrcn/ucf50-lrcn.py"), 123, 336, g)
+    return g["LRCN"], g
+
+
+def dump_lrcn(**conf):
+    """class LRCN of lrcn/dump_lrcn.py:278-339 (one adapt, temporal layer stored as `rnn`, lstm / gru switch)."""
+    base = dict(CONF_CNN_BACKBONE="resnet50", CONF_RNN_TYPE="lstm", CONF_RNN_OUT="all", CONF_RNN_LAYER=4,
+                CONF_CLASSIF_MODE="multiple_binary", CONF_FINETUNE=False)
+    base.update(conf)
+    g = _base_globals(**base)
+    _exec_lines(os.path.join(REF_ROOT, "lrcn/dump_lrcn.py"), 278, 339, g)
+    return g["LRCN"], g
+
+
+def medsos_models_bidir(**conf):
+    """module medsos_lrcn/src/models_bidir.py (string-programmed Adapt :119-155, LRCN :158-248) with all_config patched."""
+    _stub_modules()
+    src_dir = os.path.join(REF_ROOT, "medsos_lrcn/src")
+    if src_dir not in sys.path:
+        sys.path.insert(0, src_dir)
+    import all_config
+    for k, v in conf.items():
+        setattr(all_config, k, v)
+    spec = importlib.util.spec_from_file_location("ref_medsos_models_bidir", os.path.join(src_dir, "models_bidir.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.models = _NoDownloadModels()
+    mod.all_config = all_config
+    return mod
+
+
 def crime_lrcn(**conf):
     """class LRCN of lrcn/lrcn.py:181-305 (trainable/frozen backbone, one adapt, biLSTM)."""
     base = dict(CONF_CNN_BACKBONE="densenet121", CONF_RNN_OUT="all", CONF_RNN_LAYER=4,

@@ -613,6 +613,58 @@ def _gold_crime_trainable(cond):
     save("crime_trainable_resnet18_cond.npz" if cond else "crime_trainable_resnet18.npz", **arrs)
 
 
+def gold_variants():
+    """Temporal-layer / adapt-stack variants of the backbone LRCNs (VERDICT r01 missing #4, #5): one train step of each
+    reference class on a frozen ResNet-18, 2 clips x 4 frames x 32x32.  The fixture keeps the reference's pooled backbone
+    features so the GPU test can check the TRAINABLE TAIL in fp32 (1e-4 / 2e-3) independent of the bf16 encoder."""
+    B, T, S = 2, 4, 32
+    cases = []
+    C, _ = refload.ucf50_lrcn_full(CONF_CNN_BACKBONE="resnet18", CONF_RNN_LAYER=2)
+    cases.append(("ucf50_gru", lambda: C(5, T, 8, 16, cnn_backbone="resnet18", rnn_type="gru"), "ce", 5,
+                  dict(cls="UCF50LRCN", kw=dict(num_classes=5, sequence_length=T, hidden_size=8, rnn_input_size=16, cnn_backbone="resnet18",
+                                                rnn_type="gru", rnn_layers=2)), "lrcn/ucf50-lrcn.py:252-336 rnn_type=gru"))
+    cases.append(("ucf50_mamba", lambda: C(5, T, 8, 16, cnn_backbone="resnet18", rnn_type="mamba"), "ce", 5,
+                  dict(cls="UCF50LRCN", kw=dict(num_classes=5, sequence_length=T, hidden_size=8, rnn_input_size=16, cnn_backbone="resnet18",
+                                                rnn_type="mamba", rnn_layers=2)), "lrcn/ucf50-lrcn.py:123-336 rnn_type=mamba"))
+    for rt in ("gru", "lstm"):
+        D, _ = refload.dump_lrcn(CONF_CNN_BACKBONE="resnet18", CONF_RNN_LAYER=2, CONF_CLASSIF_MODE="multiple_binary", CONF_RNN_TYPE=rt)
+        cases.append((f"dump_{rt}", (lambda D=D, rt=rt: D(3, T, 8, 16, cnn_backbone="resnet18", rnn_type=rt)), "bce", 3,
+                      dict(cls="CrimeLRCN", kw=dict(num_classes=3, sequence_length=T, hidden_size=8, rnn_input_size=16, cnn_backbone="resnet18",
+                                                    rnn_layers=2, classif_mode="multiple_binary", rnn_type=rt, rnn_attr="rnn",
+                                                    finetune=True)), f"lrcn/dump_lrcn.py:278-339 rnn_type={rt}"))
+    for tag, mode, rt, bidir in (("adapt_lstm", "lnslnslnsd", "lstm", False), ("adapt_gru_bi", "lgnlrnlsd", "gru", True),
+                                 ("adapt_mamba", "lsnlsnlsn", "mamba", False)):
+        mb = refload.medsos_models_bidir(CONF_ADAPT=mode, CONF_RNN_LAYER=2, CONF_DROPOUT=0.0, CONF_CLASSIF_MODE="multiclass",
+                                         CONF_RNN_OUT="all")
+        cases.append((tag, (lambda mb=mb, rt=rt, bidir=bidir: mb.LRCN(4, T, 16, 8, cnn_backbone="resnet18", rnn_type=rt, rnn_out="all",
+                                                                      bidirectional=bidir)), "ce", 4,
+                      dict(cls="AdaptLRCN", kw=dict(num_classes=4, sequence_length=T, hidden_size=16, rnn_input_size=8, cnn_backbone="resnet18",
+                                                    rnn_type=rt, bidirectional=bidir, rnn_layers=2, dropout=0.0, adapt_mode=mode)),
+                      f"medsos_lrcn/src/models_bidir.py:119-248 CONF_ADAPT={mode} rnn_type={rt}"))
+    for i, (tag, make, loss_kind, ncls, build, source) in enumerate(cases):
+        torch.manual_seed(300 + i)
+        m = make()
+        for p in m.cnn_backbone.parameters():      # dump_lrcn.py never freezes: the tail test does not need backbone gradients
+            p.requires_grad = False
+        x, y = _clips(B, T, S, ncls, seed=77 + i)
+        if loss_kind == "bce":
+            y = (torch.rand(B, ncls, generator=torch.Generator().manual_seed(5 + i)) > 0.5).float()
+        sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+        m.train()
+        with torch.no_grad():
+            feat = m.cnn_backbone(x.view(B * T, 3, S, S))
+        m.load_state_dict(sd0)
+        _, out, loss, grads, _ = run_step(m, x, y, loss_kind=loss_kind)
+        arrs = {"x": x.numpy(), "y": y.numpy(), "features": feat.numpy(), "logits": out.numpy(), "loss": loss.numpy(),
+                "meta": np.array(json.dumps(dict(build=build, loss=loss_kind, source=source)))}
+        for k, v in npd(sd0).items():
+            if not k.startswith("cnn_backbone."):
+                arrs["sd0/" + k] = v
+        for k, v in npd(grads).items():
+            arrs["grad/" + k] = v
+        save(f"variant_{tag}.npz", **arrs)
+
+
 def gold_baseline_shapes():
     gold_cfg1()
     gold_cfg2()

@@ -306,3 +306,21 @@ def test_checkpoint_unpickler_never_resolves_foreign_globals(tmp_path):
     assert not ck._allowed_global("builtins", "eval") and not ck._allowed_global("builtins", "getattr")
     assert not ck._allowed_global("os", "system") and not ck._allowed_global("subprocess", "Popen")
     assert ck._allowed_global("collections", "OrderedDict") and ck._allowed_global("torch._utils", "_rebuild_tensor_v2")
+
+
+def test_variant_modules_convert_from_reference_layout():
+    """convert_reference_module() recognises the new layouts from their state_dict keys / module types (CPU side)."""
+    import video_classif_b200 as vc
+    for tag in ("ucf50_mamba", "dump_gru", "adapt_gru_bi"):
+        from conftest import load_golden
+        g, meta = load_golden(f"variant_{tag}.npz")
+        build = meta["build"]
+        m = getattr(vc, build["cls"])(**build["kw"])
+        m2 = vc.convert_reference_module(m)
+        assert type(m2) is type(m)
+        assert set(m2.state_dict()) == set(m.state_dict())
+        for attr in ("rnn_type", "rnn_attr"):
+            if hasattr(m, attr):
+                assert getattr(m2, attr) == getattr(m, attr)
+        if hasattr(m, "adapt") and hasattr(m.adapt, "mode"):
+            assert m2.adapt.mode == m.adapt.mode

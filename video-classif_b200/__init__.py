@@ -6,7 +6,8 @@ from ._lib import B200LrcnError  # noqa: F401
 
 
 def __getattr__(name):   # lazy: models/ops import torch + torchvision
-    if name in ("SmallCNNLRCN", "SmallCNNGRU", "LRCN", "UCF50LRCN", "CrimeLRCN", "GraphedInference", "count_parameters"):
+    if name in ("SmallCNNLRCN", "SmallCNNGRU", "LRCN", "UCF50LRCN", "CrimeLRCN", "AdaptLRCN", "Adapt", "GraphedInference",
+                "count_parameters"):
         from . import models
         return getattr(models, name)
     if name in ("load_reference_checkpoint", "convert_reference_module"):

@@ -178,26 +178,64 @@ def convert_reference_module(ref, precision="bf16", **overrides):
         kw.update(overrides)
         model = M.LRCN(**kw)
     elif "adapt1.weight" in sd:                                                            # lrcn/ucf50-lrcn.py:252-336
-        H = sd["rnn.weight_hh_l0"].shape[1]
         ncls, mode, fc_in = _heads(sd)
+        if "rnn.0.mixer.A_log" in sd:                                                      # Mamba blocks (:285-289)
+            rnn_type, H = "mamba", sd["rnn.0.mixer.A_log"].shape[1]
+            layers = len({k.split(".")[1] for k in sd if k.startswith("rnn.")})
+        else:
+            H = sd["rnn.weight_hh_l0"].shape[1]
+            rnn_type = "gru" if sd["rnn.weight_ih_l0"].shape[0] == 3 * H else "lstm"
+            layers = _count_layers(sd, "rnn.")
         T = attr("sequence_length") or fc_in // (2 * H)
         kw = dict(num_classes=ncls, sequence_length=T, hidden_size=H, rnn_input_size=sd["adapt3.weight"].shape[0],
-                  cnn_backbone=infer_backbone(sd), rnn_type=attr("rnn_type", "lstm"),
-                  rnn_out="all" if fc_in == 2 * H * T and T > 1 else "last", rnn_layers=_count_layers(sd, "rnn."),
+                  cnn_backbone=infer_backbone(sd), rnn_type=rnn_type,
+                  rnn_out="all" if fc_in == 2 * H * T and T > 1 else "last", rnn_layers=layers,
                   classif_mode=mode, precision=precision)
         kw.update(overrides)
         model = M.UCF50LRCN(**kw)
-    elif "adapt.weight" in sd and "lstm.weight_ih_l0" in sd:                               # lrcn/lrcn.py:181-305, rgb_lrcn.py
-        H = sd["lstm.weight_hh_l0"].shape[1]
+    elif "adapt.weight" in sd and ("lstm.weight_ih_l0" in sd or "rnn.weight_ih_l0" in sd):
+        # lrcn/lrcn.py:181-305, rgb_lrcn.py (`lstm`); lrcn/dump_lrcn.py:278-339 (`rnn`, lstm / gru switch)
+        rnn_attr = "lstm" if "lstm.weight_ih_l0" in sd else "rnn"
+        H = sd[rnn_attr + ".weight_hh_l0"].shape[1]
         ncls, mode, fc_in = _heads(sd)
         T = attr("sequence_length") or fc_in // (2 * H)
         kw = dict(num_classes=ncls, sequence_length=T, hidden_size=H, rnn_input_size=sd["adapt.weight"].shape[0],
                   cnn_backbone=infer_backbone(sd), rnn_out="all" if fc_in == 2 * H * T and T > 1 else "last",
-                  rnn_layers=_count_layers(sd, "lstm."), classif_mode=mode,
+                  rnn_layers=_count_layers(sd, rnn_attr + "."), classif_mode=mode,
                   finetune=any(p.requires_grad for n, p in ref.named_parameters() if n.startswith("cnn_backbone.")),
+                  rnn_type="gru" if sd[rnn_attr + ".weight_ih_l0"].shape[0] == 3 * H else "lstm", rnn_attr=rnn_attr,
                   precision=precision)
         kw.update(overrides)
         model = M.CrimeLRCN(**kw)
+    elif any(k.startswith("adapt.adapt.") for k in sd):                                    # models_bidir.py:158-248
+        seq = getattr(getattr(ref, "adapt", None), "adapt", None)
+        if seq is None and "adapt_mode" not in overrides:
+            raise NotImplementedError("a models_bidir state_dict does not record its activation layers: pass adapt_mode=")
+        mode_str = overrides.pop("adapt_mode", None) or "".join(
+            {"Linear": "l", "LayerNorm": "n", "SiLU": "s", "GELU": "g", "ReLU": "r", "Dropout": "d"}[type(m).__name__] for m in seq)
+        lin = sorted((int(k.split(".")[2]), v) for k, v in sd.items() if k.startswith("adapt.adapt.") and k.endswith(".weight")
+                     and v.dim() == 2)
+        rnn_in = lin[-1][1].shape[0]
+        ncls, mode, fc_in = _heads(sd)
+        if "rnn.0.mixer.A_log" in sd:
+            rnn_type, H = "mamba", sd["rnn.0.mixer.A_log"].shape[1]
+            layers = len({k.split(".")[1] for k in sd if k.startswith("rnn.")})
+            bidir = sd["rnn.0.mixer.out_proj.weight"].shape[1] == 2 * sd["rnn.0.mixer.A_log"].shape[0]
+            out_w = rnn_in
+        else:
+            H = sd["rnn.weight_hh_l0"].shape[1]
+            rnn_type = "gru" if sd["rnn.weight_ih_l0"].shape[0] == 3 * H else "lstm"
+            layers = _count_layers(sd, "rnn.")
+            bidir = "rnn.weight_ih_l0_reverse" in sd
+            out_w = H * (2 if bidir else 1)
+        T = attr("sequence_length") or fc_in // out_w
+        drops = [m.p for m in (seq or []) if type(m).__name__ == "Dropout"]
+        kw = dict(num_classes=ncls, sequence_length=T, hidden_size=H, rnn_input_size=rnn_in, cnn_backbone=infer_backbone(sd),
+                  rnn_type=rnn_type, rnn_out="all" if fc_in == out_w * T and T > 1 else "last", bidirectional=bidir,
+                  rnn_layers=layers, dropout=float(drops[0]) if drops else 0.25, classif_mode=mode, adapt_mode=mode_str,
+                  adapt_depth=len(lin), precision=precision)
+        kw.update(overrides)
+        model = M.AdaptLRCN(**kw)
     else:
         raise NotImplementedError("unrecognised reference checkpoint layout: " + ", ".join(sorted(sd)[:8]) + " ...")
 

@@ -276,6 +276,29 @@ transpose_cast_kernel(const float* __restrict__ src, long ld_src, bf16* __restri
   }
 }
 
+// stand-alone activations of the string-programmed Adapt stacks (medsos_lrcn/src/models_bidir.py:119-155: 's' nn.SiLU,
+// 'g' nn.GELU (erf form), 'r' nn.ReLU) and of that file's head (F.silu after the LayerNorm): kind 0 relu, 1 gelu, 2 silu
+__device__ __forceinline__ float act_f(float x, int kind) {
+  if (kind == 0) return fmaxf(x, 0.f);
+  if (kind == 1) return gelu_f(x);
+  return x / (1.f + __expf(-x));
+}
+__device__ __forceinline__ float act_grad_f(float x, int kind) {
+  if (kind == 0) return x > 0.f ? 1.f : 0.f;
+  if (kind == 1) return gelu_grad_f(x);
+  const float sg = 1.f / (1.f + __expf(-x));
+  return sg * (1.f + x * (1.f - sg));
+}
+__global__ void __launch_bounds__(256)
+act_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long n, int kind) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) y[i] = act_f(x[i], kind);
+}
+__global__ void __launch_bounds__(256)
+act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dx, long n, int kind) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    dx[i] = dy[i] * act_grad_f(x[i], kind);
+}
+
 // dst[c, r] (bf16, ld_dst) = src[r, c] (bf16, ld_src) ; 32x32 smem tile transpose (no fp32 round trip of a bf16 operand)
 __global__ void __launch_bounds__(256)
 transpose_bf16_kernel(const bf16* __restrict__ src, long ld_src, bf16* __restrict__ dst, long ld_dst, long R, long Ccols) {
@@ -312,6 +335,24 @@ dropout_kernel(const float* __restrict__ x, float* __restrict__ y, long n, float
 }
 
 }  // namespace
+
+B2_API int b2_act_fwd_f32(const float* x, float* y, long n, int kind, void* stream) {
+  B2_ARG_CHECK(x && y && n > 0 && kind >= 0 && kind <= 2, "b2_act_fwd_f32: null pointer, empty, or kind not in {0 relu, 1 gelu, 2 silu}");
+  long blocks = (n + 255) / 256;
+  const long cap = (long)b2_num_sms() * 8;
+  act_fwd_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(x, y, n, kind);
+  B2_LAUNCH_CHECK("act_fwd_kernel");
+  return 0;
+}
+
+B2_API int b2_act_bwd_f32(const float* dy, const float* x, float* dx, long n, int kind, void* stream) {
+  B2_ARG_CHECK(dy && x && dx && n > 0 && kind >= 0 && kind <= 2, "b2_act_bwd_f32: null pointer, empty, or bad kind");
+  long blocks = (n + 255) / 256;
+  const long cap = (long)b2_num_sms() * 8;
+  act_bwd_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(dy, x, dx, n, kind);
+  B2_LAUNCH_CHECK("act_bwd_kernel");
+  return 0;
+}
 
 B2_API int b2_transpose_bf16(const void* src, long ld_src, void* dst, long ld_dst, long R, long C, void* stream) {
   B2_ARG_CHECK(src && dst && R > 0 && C > 0 && ld_src >= C && ld_dst >= R, "b2_transpose_bf16: bad arguments");

@@ -4,7 +4,8 @@ reference classes, executed on the sm_100a kernels.
     SmallCNNLRCN  <- notebook `LRCN` (lrcn/.ipynb_checkpoints/LRCN-ucf50-checkpoint.ipynb nb:148-193)
     LRCN          <- medsos_lrcn/src/models.py:121-234  (frozen backbone, GELU/LN adapts, LN head)
     UCF50LRCN     <- lrcn/ucf50-lrcn.py:252-336         (frozen backbone, 3 plain adapts, biLSTM)
-    CrimeLRCN     <- lrcn/lrcn.py:181-305 / lrcn/rgb_lrcn.py:168-263 (one adapt, attribute `lstm`)
+    CrimeLRCN     <- lrcn/lrcn.py:181-305 / lrcn/rgb_lrcn.py:168-263 / lrcn/dump_lrcn.py:278-339 (one adapt, `lstm` / `rnn`)
+    AdaptLRCN     <- medsos_lrcn/src/models_bidir.py:158-248 (string-programmed Adapt stack, LN -> SiLU head)
 
 `forward(x: float32[B,T,C,H,W]) -> logits[B,num_classes]`.  The torch.nn sub-modules (Conv2d,
 BatchNorm2d, Linear, LayerNorm, LSTM, torchvision ResNet) are PARAMETER CONTAINERS only: they give
@@ -296,15 +297,16 @@ def _binary_heads(r, heads, bf16):
 
 
 class UCF50LRCN(_BackboneLRCN):
-    """lrcn/ucf50-lrcn.py:252-336: frozen backbone, adapt1..3 plain Linear, N-layer biLSTM (attribute
-    `rnn`), `fc` Linear or per-class binary heads."""
+    """lrcn/ucf50-lrcn.py:252-336: frozen backbone, adapt1..3 plain Linear, temporal layer under the attribute `rnn`
+    (N-layer bidirectional nn.LSTM / nn.GRU, or a ModuleList of unidirectional Mamba ResidualBlocks, :280-292), `fc` Linear
+    or per-class binary heads (sized for 2*hidden*T inputs in every case, as in the reference)."""
 
     def __init__(self, num_classes, sequence_length, hidden_size, rnn_input_size, cnn_backbone="resnet50",
                  rnn_type="lstm", rnn_out="all", rnn_layers=4, classif_mode="multiclass", pretrained=False,
                  precision="bf16"):
         super().__init__()
-        if rnn_type != "lstm":
-            raise NotImplementedError(f"rnn_type={rnn_type!r}: only the LSTM temporal layer is built")
+        if rnn_type not in ("lstm", "gru", "mamba"):
+            raise ValueError(f"rnn_type={rnn_type!r}: expected 'lstm', 'gru' or 'mamba' (ucf50-lrcn.py:280-292)")
         self.sequence_length = sequence_length
         self.hidden_size = hidden_size
         self.backbone = cnn_backbone
@@ -318,8 +320,13 @@ class UCF50LRCN(_BackboneLRCN):
         self.adapt1 = nn.Linear(f, f // 2)
         self.adapt2 = nn.Linear(f // 2, f // 4)
         self.adapt3 = nn.Linear(f // 4, rnn_input_size)
-        self.rnn = nn.LSTM(input_size=rnn_input_size, hidden_size=hidden_size, num_layers=rnn_layers,
-                           bidirectional=True, batch_first=True)
+        if rnn_type == "mamba":       # ucf50-lrcn.py:285-289: unidirectional blocks (the class of ucf50-lrcn.py:123-250)
+            self.rnn = nn.ModuleList([ResidualBlock(rnn_input_size, rnn_input_size * 2, hidden_size, hidden_size, bias=True,
+                                                    conv_bias=True, kernel_size=3) for _ in range(rnn_layers)])
+        else:
+            rnn_cls = nn.LSTM if rnn_type == "lstm" else nn.GRU
+            self.rnn = rnn_cls(input_size=rnn_input_size, hidden_size=hidden_size, num_layers=rnn_layers,
+                               bidirectional=True, batch_first=True)
         fc_in = hidden_size * 2 * (sequence_length if rnn_out == "all" else 1)
         if classif_mode == "multiclass":
             self.fc = nn.Linear(fc_in, num_classes)
@@ -332,7 +339,12 @@ class UCF50LRCN(_BackboneLRCN):
         y = self._features_or_handle(x, features)
         for a in (self.adapt1, self.adapt2, self.adapt3):
             y = ops.linear(y, a.weight, a.bias, bf16)
-        r = ops.lstm_forward(y, self.rnn, bf16=bf16)
+        if self.rnn_type == "mamba":
+            r = y
+            for blk in self.rnn:
+                r = blk(r)
+        else:
+            r = ops.rnn_forward(y, self.rnn, bf16=bf16)
         r = r.reshape(B, -1) if self.rnn_out == "all" else r[:, -1, :]
         if self.classif_mode == "multiclass":
             return ops.linear(r, self.fc.weight, self.fc.bias, bf16)
@@ -341,14 +353,21 @@ class UCF50LRCN(_BackboneLRCN):
 
 class CrimeLRCN(_BackboneLRCN):
     """lrcn/lrcn.py:181-305 (and rgb_lrcn.py:168-263 with classif_mode='multiclass'): backbone,
-    one `adapt` Linear, N-layer biLSTM stored as `lstm`, `fc` or per-class heads.
+    one `adapt` Linear, N-layer biLSTM stored as `lstm`, `fc` or per-class heads; lrcn/dump_lrcn.py:278-339 is the same
+    topology with the temporal layer stored as `rnn` and an lstm / gru switch (rnn_type=, rnn_attr='rnn').
     freeze_until_layer / finetune follow freeze_cnn_layers (lrcn.py:246-283); a (partially) trainable backbone
     runs through the autograd nodes of backbone_train.py."""
 
     def __init__(self, num_classes, sequence_length, hidden_size, rnn_input_size, cnn_backbone="resnet50",
                  rnn_out="all", freeze_until_layer=None, rnn_layers=4, classif_mode="multiple_binary",
-                 finetune=False, pretrained=False, precision="bf16"):
+                 finetune=False, pretrained=False, precision="bf16", rnn_type="lstm", rnn_attr="lstm"):
         super().__init__()
+        if rnn_type not in ("lstm", "gru"):
+            raise ValueError(f"rnn_type={rnn_type!r}: expected 'lstm' or 'gru' (dump_lrcn.py:306-310)")
+        if rnn_attr not in ("lstm", "rnn"):
+            raise ValueError("rnn_attr: 'lstm' (lrcn.py:236, rgb_lrcn.py checkpoints) or 'rnn' (dump_lrcn.py:307-310)")
+        self.rnn_type = rnn_type
+        self.rnn_attr = rnn_attr
         self.sequence_length = sequence_length
         self.num_classes = num_classes
         self.hidden_size = hidden_size
@@ -359,8 +378,9 @@ class CrimeLRCN(_BackboneLRCN):
         f = self._make_backbone(cnn_backbone, pretrained)
         self.freeze_cnn_layers(freeze_until_layer, unfreeze_dense_layer=finetune)
         self.adapt = nn.Linear(f, rnn_input_size)
-        self.lstm = nn.LSTM(input_size=rnn_input_size, hidden_size=hidden_size, num_layers=rnn_layers,
-                            bidirectional=True, batch_first=True)
+        rnn_cls = nn.LSTM if rnn_type == "lstm" else nn.GRU          # dump_lrcn.py:306-310 (`rnn`); lrcn.py:236 (`lstm`)
+        setattr(self, rnn_attr, rnn_cls(input_size=rnn_input_size, hidden_size=hidden_size, num_layers=rnn_layers,
+                                        bidirectional=True, batch_first=True))
         fc_in = hidden_size * 2 * (sequence_length if rnn_out == "all" else 1)
         if classif_mode == "multiclass":
             self.fc = nn.Linear(fc_in, num_classes)
@@ -386,10 +406,126 @@ class CrimeLRCN(_BackboneLRCN):
         B = x.shape[0]
         y = self._features_or_handle(x, features)
         y = ops.linear(y, self.adapt.weight, self.adapt.bias, bf16)
-        r = ops.lstm_forward(y, self.lstm, bf16=bf16)
+        r = ops.rnn_forward(y, getattr(self, self.rnn_attr), bf16=bf16)
         r = r.reshape(B, -1) if self.rnn_out == "all" else r[:, -1, :]
         if self.classif_mode == "multiclass":
             return ops.linear(r, self.fc.weight, self.fc.bias, bf16)
+        return _binary_heads(r, self.fc, bf16)
+
+
+class Adapt(nn.Module):
+    """medsos_lrcn/src/models_bidir.py:119-155: the string-programmed adapt stack.  `mode` is read character by character --
+    'l' Linear(size[i] -> size[i+1]) with size = [in, in/2, ..., in/2^(depth-1), out]; 'n' LayerNorm(size[i]); 's' SiLU;
+    'g' GELU; 'r' ReLU; 'd' Dropout (accepted only after the last Linear) -- into `self.adapt = nn.Sequential(...)`, so the
+    checkpoint keys are `adapt.adapt.{position}.weight|bias`.  The Sequential holds parameter containers; forward() walks
+    it on the b2_* kernels (GELU directly followed by LayerNorm takes the fused GELU+LN kernel)."""
+
+    def __init__(self, in_size, out_size, mode, drop=0.25, depth=3, precision="bf16"):
+        super().__init__()
+        self.input_size, self.output_size, self.depth, self.mode, self.precision = in_size, out_size, depth, mode, precision
+        sizes = [in_size]
+        for _ in range(1, depth):
+            sizes.append(sizes[-1] // 2)
+        sizes.append(out_size)
+        layers, i = [], 0
+        for ch in mode:
+            if ch == "l":
+                if i >= depth:
+                    raise ValueError(f"mode {mode!r} has more than depth={depth} 'l' layers")
+                layers.append(nn.Linear(sizes[i], sizes[i + 1]))
+                i += 1
+            elif ch == "n":
+                layers.append(nn.LayerNorm(sizes[i]))
+            elif ch == "s":
+                layers.append(nn.SiLU())
+            elif ch == "g":
+                layers.append(nn.GELU())
+            elif ch == "r":
+                layers.append(nn.ReLU())
+            elif ch == "d" and i == depth:
+                layers.append(nn.Dropout(drop))
+            else:
+                raise ValueError(f"Undefined layer type: {ch}")          # models_bidir.py:149-150
+        self.adapt = nn.Sequential(*layers)
+
+    def forward(self, x):
+        bf16 = self.precision == "bf16"
+        mods = list(self.adapt)
+        k = 0
+        while k < len(mods):
+            m = mods[k]
+            if isinstance(m, nn.Linear):
+                x = ops.linear(x, m.weight, m.bias, bf16)
+            elif isinstance(m, nn.GELU) and k + 1 < len(mods) and isinstance(mods[k + 1], nn.LayerNorm):
+                ln = mods[k + 1]
+                x = ops.act_layernorm(x, ln.weight, ln.bias, True, ln.eps)
+                k += 1
+            elif isinstance(m, nn.LayerNorm):
+                x = ops.act_layernorm(x, m.weight, m.bias, False, m.eps)
+            elif isinstance(m, nn.Dropout):
+                x = ops.dropout(x, m.p, self.training)
+            else:
+                x = ops.act(x, {nn.SiLU: "silu", nn.GELU: "gelu", nn.ReLU: "relu"}[type(m)])
+            k += 1
+        return x
+
+
+class AdaptLRCN(_BackboneLRCN):
+    """medsos_lrcn/src/models_bidir.py:158-248: frozen backbone -> `Adapt(cnn_out, rnn_input, mode=CONF_ADAPT)` -> LSTM / GRU /
+    Mamba blocks -> bn0 -> silu(bna(fc)) -> silu(bnb(fca)) -> fcb (LayerNorm BEFORE the SiLU here, and no drop2 in the
+    forward, :236-240), or per-class binary heads.  adapt_mode is the reference's CONF_ADAPT string."""
+
+    def __init__(self, num_classes, sequence_length, hidden_size, rnn_input_size, cnn_backbone="resnet50", rnn_type="lstm",
+                 rnn_out="all", bidirectional=False, rnn_layers=3, dropout=0.25, classif_mode="multiclass",
+                 adapt_mode="lnslnslnsd", adapt_depth=3, pretrained=False, precision="bf16"):
+        super().__init__()
+        if rnn_type not in ("lstm", "gru", "mamba"):
+            raise ValueError(f"rnn_type={rnn_type!r}: expected 'lstm', 'gru' or 'mamba'")
+        self.sequence_length, self.hidden_size, self.backbone = sequence_length, hidden_size, cnn_backbone
+        self.rnn_type, self.rnn_out, self.bidirectional = rnn_type, rnn_out, bidirectional
+        self.classif_mode, self.precision = classif_mode, precision
+        f = self._make_backbone(cnn_backbone, pretrained)
+        for p in self.cnn_backbone.parameters():
+            p.requires_grad = False
+        self.adapt = Adapt(f, rnn_input_size, adapt_mode, drop=dropout, depth=adapt_depth, precision=precision)
+        if rnn_type == "mamba":
+            self.rnn = nn.ModuleList([ResidualBlock(rnn_input_size, rnn_input_size * 2, hidden_size, hidden_size,
+                                                    bidirectional=bidirectional) for _ in range(rnn_layers)])
+            self.rnn_output_size = rnn_input_size
+        else:
+            rnn_cls = nn.LSTM if rnn_type == "lstm" else nn.GRU
+            self.rnn = rnn_cls(input_size=rnn_input_size, hidden_size=hidden_size, num_layers=rnn_layers,
+                               bidirectional=bidirectional, batch_first=True)
+            self.rnn_output_size = hidden_size * (2 if bidirectional else 1)
+        fc_in = self.rnn_output_size * (sequence_length if rnn_out == "all" else 1)
+        if classif_mode == "multiclass":
+            self.fc = nn.Linear(fc_in, fc_in // 2)
+            self.fca = nn.Linear(fc_in // 2, fc_in // 4)
+            self.fcb = nn.Linear(fc_in // 4, num_classes)
+            self.bn0 = nn.LayerNorm(fc_in)
+            self.bna = nn.LayerNorm(fc_in // 2)
+            self.bnb = nn.LayerNorm(fc_in // 4)
+            self.drop2 = nn.Dropout(dropout)
+        else:
+            self.fc = nn.ModuleList([nn.Linear(fc_in, 1) for _ in range(num_classes)])
+
+    def forward(self, x, features=None):
+        bf16 = self.precision == "bf16"
+        B = x.shape[0]
+        y = self.adapt(self._features_or_handle(x, features))
+        if self.rnn_type == "mamba":
+            r = y
+            for blk in self.rnn:
+                r = blk(r)
+        else:
+            r = ops.rnn_forward(y, self.rnn, bf16=bf16)
+        r = r.reshape(B, -1) if self.rnn_out == "all" else r[:, -1, :]
+        if self.classif_mode == "multiclass":
+            lin, aln = ops.linear, ops.act_layernorm
+            o = aln(r, self.bn0.weight, self.bn0.bias, False, self.bn0.eps)
+            o = ops.act(aln(lin(o, self.fc.weight, self.fc.bias, bf16), self.bna.weight, self.bna.bias, False, self.bna.eps), "silu")
+            o = ops.act(aln(lin(o, self.fca.weight, self.fca.bias, bf16), self.bnb.weight, self.bnb.bias, False, self.bnb.eps), "silu")
+            return lin(o, self.fcb.weight, self.fcb.bias, bf16)
         return _binary_heads(r, self.fc, bf16)
 
 

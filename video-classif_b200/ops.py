@@ -208,23 +208,25 @@ def cast_bf16(x):
     return y
 
 
-_weight_cache = weakref.WeakKeyDictionary()      # parameter -> {kind: (data_ptr, _version, bf16 copy)}
+_weight_cache = {}      # id(parameter) -> (weakref, {kind: (data_ptr, _version, bf16 copy)}); entries die with their parameter
 
 
 def _cached_weight(w, kind):
     """bf16 ("cast") or transposed bf16 ("tcast") copy of a weight, reused while the parameter is unchanged (same storage,
     same version counter): eval / serving and frozen layers pay the conversion once, a training step once per optimizer
     update instead of once per use (forward + backward)."""
-    if not isinstance(w, torch.nn.Parameter) and w.requires_grad:
-        return cast_bf16(w) if kind == "cast" else transpose_cast_bf16(w)      # a differentiable view (stacked heads): no cache
-    slot = _weight_cache.get(w)
-    if slot is None:
-        slot = _weight_cache[w] = {}
-    ent = slot.get(kind)
-    if ent is None or ent[0] != w.data_ptr() or ent[1] != w._version:
+    if not isinstance(w, torch.nn.Parameter):
+        return cast_bf16(w) if kind == "cast" else transpose_cast_bf16(w)      # a view / stacked heads: no cache
+    key = id(w)
+    ent = _weight_cache.get(key)
+    if ent is None or ent[0]() is not w:
+        ent = _weight_cache[key] = (weakref.ref(w, lambda _r, k=key: _weight_cache.pop(k, None)), {})
+    slot = ent[1]
+    hit = slot.get(kind)
+    if hit is None or hit[0] != w.data_ptr() or hit[1] != w._version:
         copy = cast_bf16(w.detach()) if kind == "cast" else transpose_cast_bf16(w.detach())
-        ent = slot[kind] = (w.data_ptr(), w._version, copy)
-    return ent[2]
+        hit = slot[kind] = (w.data_ptr(), w._version, copy)
+    return hit[2]
 
 
 def transpose_cast_bf16(x):
@@ -561,6 +563,40 @@ class ActLayerNormFn(torch.autograd.Function):
 
 def act_layernorm(pre, gamma, beta, apply_gelu=True, eps=1e-5):
     return ActLayerNormFn.apply(pre, gamma, beta, apply_gelu, eps)
+
+
+# ----------------------------------------------------------------------------------------
+# autograd: stand-alone activation (string-programmed Adapt stacks, SiLU head of models_bidir.py)
+# ----------------------------------------------------------------------------------------
+
+ACT_KINDS = {"relu": 0, "gelu": 1, "silu": 2}
+
+
+class ActFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, kind):
+        _chk(x)
+        xc = x.contiguous()
+        if xc.dtype != F32:
+            xc = xc.float()
+        y = torch.empty_like(xc)
+        call("b2_act_fwd_f32", xc.data_ptr(), y.data_ptr(), xc.numel(), kind, stream_ptr())
+        ctx.save_for_backward(xc)
+        ctx.kind = kind
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (xc,) = ctx.saved_tensors
+        dc = dy.contiguous()
+        dx = torch.empty_like(xc)
+        call("b2_act_bwd_f32", dc.data_ptr(), xc.data_ptr(), dx.data_ptr(), xc.numel(), ctx.kind, stream_ptr())
+        return dx, None
+
+
+def act(x, kind):
+    """relu / gelu (erf form) / silu as one kernel each way."""
+    return ActFn.apply(x, ACT_KINDS[kind])
 
 
 # ----------------------------------------------------------------------------------------
