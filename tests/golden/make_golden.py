@@ -636,8 +636,10 @@ def gold_variants():
                                  ("adapt_mamba", "lsnlsnlsn", "mamba", False)):
         mb = refload.medsos_models_bidir(CONF_ADAPT=mode, CONF_RNN_LAYER=2, CONF_DROPOUT=0.0, CONF_CLASSIF_MODE="multiclass",
                                          CONF_RNN_OUT="all")
-        cases.append((tag, (lambda mb=mb, rt=rt, bidir=bidir: mb.LRCN(4, T, 16, 8, cnn_backbone="resnet18", rnn_type=rt, rnn_out="all",
-                                                                      bidirectional=bidir)), "ce", 4,
+        # (all_config is one shared module: CONF_ADAPT is read when the model is CONSTRUCTED, so pin it again right there)
+        cases.append((tag, (lambda mb=mb, rt=rt, bidir=bidir, mode=mode: (setattr(mb.all_config, "CONF_ADAPT", mode),
+                                                                          mb.LRCN(4, T, 16, 8, cnn_backbone="resnet18", rnn_type=rt,
+                                                                                  rnn_out="all", bidirectional=bidir))[1]), "ce", 4,
                       dict(cls="AdaptLRCN", kw=dict(num_classes=4, sequence_length=T, hidden_size=16, rnn_input_size=8, cnn_backbone="resnet18",
                                                     rnn_type=rt, bidirectional=bidir, rnn_layers=2, dropout=0.0, adapt_mode=mode)),
                       f"medsos_lrcn/src/models_bidir.py:119-248 CONF_ADAPT={mode} rnn_type={rt}"))
