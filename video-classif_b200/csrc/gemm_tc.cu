@@ -110,15 +110,17 @@ constexpr int kStgBytes = 32 * 64;  // epilogue staging tile: 32 rows x 32 bf16 
 
 constexpr int kResSlots = 4;         // EPI_POST: per-warp ring of shortcut / output tiles (power of two)
 
-template <int BN, int MODE, bool DEEP = false>
+template <int BN, int MODE, bool DEEP = false, bool PAIR = false>
 struct SmemLayout {
   static constexpr bool kPost = MODE == EPI_POST;
-  static constexpr int kStageBytes = (BM * BK + BN * BK) * 2;
+  // PAIR (cta_group::2): each CTA of the pair stages its own 128 rows of A and HALF of the B tile
+  static constexpr int kStageBytes = (BM * BK + (PAIR ? BN / 2 : BN) * BK) * 2;
   // EPI_POST trades operand stages for the 64 KB shortcut ring (its GEMMs are short-K and memory bound).
   // DEEP (BN = 256, long K, tensor bound): a 4th operand stage paid for with the second staging tile -- three
   // 48 KB stages cover ~0.8 us of TMA latency, less than the latency of an L2 hit under load
-  static constexpr int kStages = kPost ? (BN >= 256 ? 3 : (BN >= 128 ? 4 : 5))
-                                       : (BN >= 256 ? (DEEP ? 4 : 3) : (BN >= 128 ? 5 : (BN >= 64 ? 7 : 8)));
+  static constexpr int kStages = PAIR ? (kPost ? 4 : 5)
+                                 : kPost ? (BN >= 256 ? 3 : (BN >= 128 ? 4 : 5))
+                                         : (BN >= 256 ? (DEEP ? 4 : 3) : (BN >= 128 ? 5 : (BN >= 64 ? 7 : 8)));
   static constexpr int kStgBufs = DEEP ? 1 : 2;          // output staging tiles per epilogue warp (not EPI_POST)
   static constexpr int kTileBytes = kStageBytes * kStages;
   static constexpr int kBarOffset = kTileBytes;
@@ -140,12 +142,13 @@ __device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
   return d;
 }
 
-template <int BN, int MODE, bool TF, bool CL = false, bool DEEP = false>
+template <int BN, int MODE, bool TF, bool CL = false, bool DEEP = false, bool PAIR = false>
 __global__ void __launch_bounds__(TF ? kThreadsTf : kThreadsNoTf, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_r, int M, int N,
                int K, ConvGeom g, ATransform at, EpiParams ep) {
-  using L = SmemLayout<BN, MODE, DEEP>;
+  static_assert(!PAIR || (!TF && !CL && BN == 256 && MODE != EPI_GENERIC), "CTA pairs: 256-column conv epilogues without the A transform");
+  using L = SmemLayout<BN, MODE, DEEP, PAIR>;
   constexpr int kStages = L::kStages;
   constexpr uint32_t kTmemCols = 2 * BN;  // two accumulators (32 <= cols <= 512, power of two)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -179,9 +182,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   // of the weight tile and TMA-multicasts it into both CTAs' stages: the L2 -> SM traffic of the B operand, the
   // larger one at BN = 256, halves.  A slot is refilled only after BOTH CTAs' MMAs released it (empty count 2).
   // The row-block count is padded to even; an all-out-of-range tile loads zeros and stores nothing.
-  const int m_blocks = CL ? (((M + BM - 1) / BM + 1) & ~1) : (M + BM - 1) / BM;
+  // PAIR: a pair of CTAs (cluster ranks 0 / 1) owns the 256-row tile {2 mt, 2 mt + 1} x one n-block; the tile index space
+  // is (row pairs x n-blocks) walked by pair id.  An odd row-block count leaves an all-out-of-range block (zeros in, nothing out)
+  const int pair_rank = PAIR ? (int)cluster_ctarank() : 0;
+  const int m_blocks = CL ? (((M + BM - 1) / BM + 1) & ~1) : (PAIR ? ((M + BM - 1) / BM + 1) / 2 : (M + BM - 1) / BM);
   const int n_blocks = (N + BN - 1) / BN;
   const int num_tiles = m_blocks * n_blocks;
+  const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  auto row_block = [&](int mt) { return PAIR ? 2 * mt + pair_rank : mt; };    // tile-space row index -> 128-row block
   // split-K (skinny products such as the LSTM gate GEMM [B*T,16384] x [16384,4H]: 20 output tiles would leave 128 SMs idle
   // on a 47 MB operand stream): blockIdx.y owns k-blocks [kb0, kb0 + k_blocks) and its epilogue adds into D
   const int k_blocks_all = (K + BK - 1) / BK;
@@ -195,23 +204,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     prefetch_tmap(&tmap_b);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], CL ? 2 : 1);
+      mbar_init(&empty_bar[i], CL ? 2 : 1);     // (PAIR: one multicast commit by the leader frees the slot in both CTAs)
       mbar_init(&tf_bar[i], 32 * kTfWarps);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], kEpiWarps);
+      mbar_init(&tempty_bar[i], PAIR ? 2 * kEpiWarps : kEpiWarps);     // PAIR: the epilogue warps of BOTH CTAs release it
     }
     for (int i = 0; i < kEpiWarps * kResSlots; ++i) mbar_init(&res_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
-    tc_alloc(tmem_slot, kTmemCols);
-    tc_relinquish();
+    if (PAIR) {
+      tc_alloc_pair(tmem_slot, kTmemCols);
+      tc_relinquish_pair();
+    } else {
+      tc_alloc(tmem_slot, kTmemCols);
+      tc_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (CL) cluster_sync();          // the peer's barriers exist before any multicast can reach them
+  if (CL || PAIR) cluster_sync();  // the peer's barriers exist before any multicast / remote arrive can reach them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   grid_dependency_wait();          // PDL: the set-up above overlapped the previous kernel's tail; its results are visible now
@@ -222,9 +236,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         const int n_blk = tile / m_blocks;           // m-fastest: concurrent CTAs share one weight tile
-        const int m_blk = tile - n_blk * m_blocks;
+        const int m_blk = row_block(tile - n_blk * m_blocks);
         int cn = 0, cw = 0, ch = 0;
         if (g.is_conv) {
           const int m0 = m_blk * BM;
@@ -241,6 +255,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::kStageBytes;
           uint8_t* sb = sa + BM * BK * 2;
+          if (PAIR) {
+            // the LEADER's barrier collects the bytes of both CTAs (each: its A rows + its half of B)
+            if (pair_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
+            if (g.is_conv) {
+              const int r = tap / g.S;
+              const int s = tap - r * g.S;
+              tma_load_im2col_4d_pair(sa, &tmap_a, &full_bar[stage], slab * BK, cw, ch, cn, (uint16_t)s, (uint16_t)r);
+              if (++slab == g.c_slabs) {
+                slab = 0;
+                ++tap;
+              }
+            } else {
+              tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], (kb0 + kb) * BK, m_blk * BM);
+            }
+            tma_load_2d_pair(sb, &tmap_b, &full_bar[stage], (kb0 + kb) * BK, n_blk * BN + pair_rank * (BN / 2));
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
           mbar_expect_tx(&full_bar[stage], L::kStageBytes);
           if (g.is_conv) {
             const int r = tap / g.S;
@@ -269,12 +304,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    constexpr uint32_t idesc = make_idesc(BM, BN);
+    constexpr uint32_t idesc = make_idesc(PAIR ? 2 * BM : BM, BN);
     uint64_t* ready_bar = TF ? tf_bar : full_bar;   // with a transform the MMA waits for the rewritten tile
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    if (!PAIR || pair_rank == 0)                    // PAIR: only the leader issues (its peer's warp 1 owns the TMEM allocation)
+    for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -291,11 +327,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // +32 B per K=16 step inside the 128 B swizzle row (encoded >>4 -> +2)
-            tc_mma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            if (PAIR) tc_mma_bf16_pair(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            else tc_mma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
           }
+          if (PAIR) {
+            tc_commit_pair(&empty_bar[stage], (uint16_t)3);                          // frees the slot in BOTH CTAs
+            if (kb == k_blocks - 1) tc_commit_pair(&tfull_bar[acc], (uint16_t)3);    // both epilogues: accumulator complete
+          } else {
           if (CL) tc_commit_multicast(&empty_bar[stage], (uint16_t)3);   // frees the slot in BOTH CTAs
           else tc_commit(&empty_bar[stage]);                  // frees the smem slot when the MMAs retire
           if (kb == k_blocks - 1) tc_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+          }
         }
         __syncwarp();
         if (++stage == kStages) {
@@ -328,13 +370,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const bool has_rbn = ep.r_scale != nullptr;
       const bool relu = ep.relu != 0;
       float* ss_s = stat_s;                // [4][BN]: o_scale, o_shift, r_scale, r_shift of the current n-block
-      const int my_tiles = ((int)blockIdx.x < num_tiles) ? (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+      const int my_tiles = (tile0 < num_tiles) ? (num_tiles - tile0 + tile_step - 1) / tile_step : 0;
       const int total_iters = my_tiles * kMyChunks;
       auto issue_res = [&](int i) {        // chunk-iteration i -> (tile, chunk) -> slot i % R
-        const int tile = blockIdx.x + (i / kMyChunks) * gridDim.x;
+        const int tile = tile0 + (i / kMyChunks) * tile_step;
         const int j = i - (i / kMyChunks) * kMyChunks;
         const int n_blk = tile / m_blocks;
-        const int m_blk = tile - n_blk * m_blocks;
+        const int m_blk = row_block(tile - n_blk * m_blocks);
         uint64_t* bar = &rbar[i & (R - 1)];
         mbar_expect_tx(bar, kStgBytes);
         tma_load_2d(ring + (i & (R - 1)) * kStgBytes, &tmap_r, bar, n_blk * BN + (half + 2 * j) * 32,
@@ -342,9 +384,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       };
       if (has_res && lane == 0)
         for (int i = 0; i < R - 1 && i < total_iters; ++i) issue_res(i);
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
         const int n_blk = tile / m_blocks;
-        const int m_blk = tile - n_blk * m_blocks;
+        const int m_blk = row_block(tile - n_blk * m_blocks);
         if (n_blk != cur_nblk) {
           // ---- per-column BatchNorm coefficients of the new n-block -> shared memory
           asm volatile("bar.sync 1, 256;" ::: "memory");       // everyone is done with the previous block's values
@@ -444,7 +486,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_leader(&tempty_bar[acc]);
+          else mbar_arrive(&tempty_bar[acc]);
+        }
       }
       if (lane == 0) bulk_wait_all();
     } else {
@@ -468,9 +513,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       rd_off[1][k] = col - (uint32_t)(sw_hf * 64);    // odd i:  row i - hf
     }
 
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
       const int n_blk = tile / m_blocks;
-      const int m_blk = tile - n_blk * m_blocks;
+      const int m_blk = row_block(tile - n_blk * m_blocks);
       if (n_blk != cur_nblk) {
         if (want_stats && cur_nblk >= 0) {
           // ---- flush the finished n-block: stat_s (4 quarter copies) -> global atomics, then clear
@@ -509,7 +554,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       auto release_acc = [&]() {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_leader(&tempty_bar[acc]);
+          else mbar_arrive(&tempty_bar[acc]);
+        }
       };
       auto process = [&](int j, const uint32_t (&raw)[32]) {
         const int ch = half + 2 * j;
@@ -732,9 +780,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int row = rb + 16 * i;
       row_off[i] = (uint32_t)(row * 128 + ((c ^ (row & 7)) << 4));
     }
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       const int n_blk = tile / m_blocks;
-      const int m_blk = tile - n_blk * m_blocks;
+      const int m_blk = row_block(tile - n_blk * m_blocks);
       int iy0[8], ix0[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -840,9 +888,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
   }
+  if (PAIR) cluster_sync();        // both CTAs are done with the pair's tensor memory and barriers
   if (warp == 1) {
     tc_fence_after();
-    tc_dealloc(tmem_base, kTmemCols);
+    if (PAIR) tc_dealloc_pair(tmem_base, kTmemCols);
+    else tc_dealloc(tmem_base, kTmemCols);
   }
   if (CL) cluster_sync();          // no CTA leaves while its peer can still multicast into it / arrive on its barriers
 }
@@ -896,20 +946,20 @@ int make_tmap_2d(CUtensorMap* map, const void* base, long rows, long cols, long 
   return 0;
 }
 
-template <int BN, int MODE, bool TF, bool CL = false, bool DEEP = false>
+template <int BN, int MODE, bool TF, bool CL = false, bool DEEP = false, bool PAIR = false>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tr, int M, int N,
                 int K, const ConvGeom& g, const ATransform& at, const EpiParams& ep, cudaStream_t stream) {
-  using L = SmemLayout<BN, MODE, DEEP>;
+  using L = SmemLayout<BN, MODE, DEEP, PAIR>;
   static B2PerDeviceOnce attr_set;
   if (attr_set.needed()) {
-    B2_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, MODE, TF, CL, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B2_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, MODE, TF, CL, DEEP, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        L::kTotal));
     attr_set.mark();
   }
   const int m_blocks = CL ? ((b2_ceil_div(M, BM) + 1) & ~1) : b2_ceil_div(M, BM);
-  const int tiles = m_blocks * b2_ceil_div(N, BN);
+  const int tiles = PAIR ? 2 * ((m_blocks + 1) / 2) * b2_ceil_div(N, BN) : m_blocks * b2_ceil_div(N, BN);   // in CTAs
   int grid = tiles < b2_num_sms() ? tiles : b2_num_sms();
-  if (CL) grid &= ~1;
+  if (CL || PAIR) grid &= ~1;
   cudaLaunchConfig_t cfg = {};
   const int splits = (MODE == EPI_GENERIC && ep.k_splits > 1) ? ep.k_splits : 1;
   cfg.gridDim = dim3(grid, splits);
@@ -924,7 +974,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
     attr[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;
   }
-  if (CL) {
+  if (CL || PAIR) {
     attr[na].id = cudaLaunchAttributeClusterDimension;
     attr[na].val.clusterDim.x = 2;
     attr[na].val.clusterDim.y = 1;
@@ -933,7 +983,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  B2_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, MODE, TF, CL, DEEP>, ta, tb, td, tr, M, N, K, g, at, ep));
+  B2_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, MODE, TF, CL, DEEP, PAIR>, ta, tb, td, tr, M, N, K, g, at, ep));
   B2_LAUNCH_CHECK("gemm_tc_kernel");
   return 0;
 }
@@ -957,10 +1007,16 @@ int pick_bn_gemm(int M, int N) {
 template <int MODE, bool TF>
 int dispatch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tr,
                 int M, int N, int K, const ConvGeom& g, const ATransform& at, const EpiParams& ep, cudaStream_t stream,
-                const CUtensorMap* tb_half = nullptr) {
+                const CUtensorMap* tb_half = nullptr, const CUtensorMap* tb_pair = nullptr) {
   if constexpr (MODE != EPI_GENERIC) {
     if (bn == 256 && tb_half != nullptr)      // two-CTA clusters with the weight tile multicast (see the kernel)
       return launch_gemm<256, MODE, TF, true>(ta, *tb_half, td, tr, M, N, K, g, at, ep, stream);
+  }
+  if constexpr (MODE != EPI_GENERIC && !TF) {
+    // CTA pairs (tcgen05.mma.cta_group::2, M = 256): the wide layers (256+ output channels, K >= 256) -- each CTA stages
+    // half of the weight tile, so the shared-memory read and L2 -> SM traffic of the B operand halve
+    if (bn == 256 && K >= 256 && tb_pair != nullptr)
+      return launch_gemm<256, MODE, TF, false, false, true>(ta, *tb_pair, td, tr, M, N, K, g, at, ep, stream);
   }
   if constexpr ((MODE == EPI_BF16 || MODE == EPI_STATS) && !TF) {
     if (bn == 256 && K >= 512 && getenv("B2_NO_DEEP") == nullptr)   // long K: four operand stages
@@ -979,7 +1035,8 @@ int dispatch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const CUte
 }
 
 int dispatch(int bn, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const ConvGeom& g,
-             const ATransform& at, EpiParams ep, cudaStream_t stream, const CUtensorMap* tb_half = nullptr) {
+             const ATransform& at, EpiParams ep, cudaStream_t stream, const CUtensorMap* tb_half = nullptr,
+             const CUtensorMap* tb_pair = nullptr) {
   // bf16 outputs whose rows are 16-byte multiples leave through TMA bulk stores
   CUtensorMap td = ta, tr = ta;
   ep.tma_store = 0;
@@ -1006,13 +1063,13 @@ int dispatch(int bn, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N,
   switch (mode) {
     case EPI_STATS:
       return tf ? dispatch_bn<EPI_STATS, true>(bn, ta, tb, td, tr, M, N, K, g, at, ep, stream, tb_half)
-                : dispatch_bn<EPI_STATS, false>(bn, ta, tb, td, tr, M, N, K, g, at, ep, stream, tb_half);
+                : dispatch_bn<EPI_STATS, false>(bn, ta, tb, td, tr, M, N, K, g, at, ep, stream, tb_half, tb_pair);
     case EPI_POST:
       return tf ? dispatch_bn<EPI_POST, true>(bn, ta, tb, td, tr, M, N, K, g, at, ep, stream, tb_half)
-                : dispatch_bn<EPI_POST, false>(bn, ta, tb, td, tr, M, N, K, g, at, ep, stream, tb_half);
+                : dispatch_bn<EPI_POST, false>(bn, ta, tb, td, tr, M, N, K, g, at, ep, stream, tb_half, tb_pair);
     case EPI_BF16:
       return tf ? dispatch_bn<EPI_BF16, true>(bn, ta, tb, td, tr, M, N, K, g, at, ep, stream, tb_half)
-                : dispatch_bn<EPI_BF16, false>(bn, ta, tb, td, tr, M, N, K, g, at, ep, stream, tb_half);
+                : dispatch_bn<EPI_BF16, false>(bn, ta, tb, td, tr, M, N, K, g, at, ep, stream, tb_half, tb_pair);
     default:
       return dispatch_bn<EPI_GENERIC, false>(bn, ta, tb, td, tr, M, N, K, g, at, ep, stream);
   }
@@ -1060,10 +1117,18 @@ int conv_common(const void* x, int Nimg, int H, int W, int C, const void* w, int
     if (int r = make_tmap_2d(&tbh, w, Cout, K, K, bn / 2)) return r;
     tb_half = &tbh;
   }
+  // CTA pairs (cta_group::2): every wide conv without an A transform; B2_PAIR=0 falls back to one CTA per tile (A/B runs)
+  static const bool pair_on = getenv("B2_PAIR") == nullptr || getenv("B2_PAIR")[0] != '0';
+  CUtensorMap tbp;
+  const CUtensorMap* tb_pair = nullptr;
+  if (pair_on && tb_half == nullptr && bn == 256 && K >= 256 && Cout % 256 == 0 && at.scale == nullptr) {
+    if (int r = make_tmap_2d(&tbp, w, Cout, K, K, bn / 2)) return r;
+    tb_pair = &tbp;
+  }
   if (R == 1 && S == 1 && stride == 1 && pad == 0) {
     if (int r = make_tmap_2d(&ta, x, M, C, C, BM)) return r;
     ConvGeom g = {};
-    return dispatch(bn, ta, tb, M, Cout, K, g, at, ep, stream, tb_half);
+    return dispatch(bn, ta, tb, M, Cout, K, g, at, ep, stream, tb_half, tb_pair);
   }
   // IM2COL-mode map over the NHWC activation: dims {C, W, H, N}; the bounding box of filter-window
   // base positions is [-pad, dim-1 + (pad - (R-1))] and is walked with the convolution stride.
@@ -1089,7 +1154,7 @@ int conv_common(const void* x, int Nimg, int H, int W, int C, const void* w, int
     if (drv <= 13010 && (long)Nimg * H * W * C * 2 < 131072) reinterpret_cast<uint64_t*>(&ta)[1] &= ~(1ull << 21);
   }
   ConvGeom g = {1, P, Q, S, C / 64, stride, -pad, -pad, H, W};
-  return dispatch(bn, ta, tb, M, Cout, K, g, at, ep, stream, tb_half);
+  return dispatch(bn, ta, tb, M, Cout, K, g, at, ep, stream, tb_half, tb_pair);
 }
 
 // ------------------------------------------------------------------ Gram-matrix BatchNorm statistics
