@@ -358,6 +358,15 @@ int b2_mbv2_stem_conv(const void* x, int in_bf16, const float* w, void* y, float
                       void* stream);
 int b2_dwconv3x3_bn_nhwc_bf16(const void* x, const float* scale, const float* shift, int act, const float* w, void* y,
                               float* sum, float* sumsq, int N, int H, int W, int C, int stride, void* stream);
+/* backward of the trainable MobileNetV2 (lrcn/lrcn.py:196-230,246-283, rgb_lrcn.py:208-227 with CNN_BACKBONE = "mobilenet_v2"):
+ * depthwise data / weight gradients (dw fp32 [C,1,3,3] ACCUMULATED), the stem's weight gradient (dw fp32 [32,3,3,3] ACCUMULATED),
+ * and BatchNorm backward with the ReLU6 mask 0 < z < 6 (same contract as b2_bn_bwd_nhwc_bf16). */
+int b2_dwconv3x3_dgrad_nhwc_bf16(const void* dy, const float* w, void* dx, int N, int H, int W, int C, int stride, void* stream);
+int b2_dwconv3x3_wgrad_nhwc_bf16(const void* x, const void* dy, float* dw, int N, int H, int W, int C, int stride, void* stream);
+int b2_mbv2_stem_wgrad(const void* x, int in_bf16, const void* dy, float* dw, int N, int H, int W, void* stream);
+int b2_bn_bwd_relu6_nhwc_bf16(const void* dz, void* dzm, const void* z, const void* y, void* dy, const float* gamma,
+                              const float* sum, const float* sumsq, const float* running_mean, const float* running_var,
+                              float* s1, float* s2, long M, int C, long count, float eps, int train, void* stream);
 
 #ifdef __cplusplus
 }

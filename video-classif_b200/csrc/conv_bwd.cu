@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const bf16* dz, bf16* dzm, const bf16* __restrict__ z, const bf16* __restrict__ y,
                      const float* __restrict__ sum, const float* __restrict__ sumsq, const float* __restrict__ rmean,
                      const float* __restrict__ rvar, float* __restrict__ out_s1, float* __restrict__ out_s2, long M, int C,
-                     int rows_per_block, float inv_count, float eps, int train) {
+                     int rows_per_block, float inv_count, float eps, int train, float hi) {
   __shared__ float red[2][256 * 8];                 // [s1 | s2][thread][8 channels]: 16 KB
   const int groups = C >> 3;                         // channel groups per row
   const int lanes = 256 / groups > 0 ? 256 / groups : 1;   // rows handled concurrently by the block
@@ -287,7 +287,7 @@ bn_bwd_reduce_kernel(const bf16* dz, bf16* dzm, const bf16* __restrict__ z, cons
         float zf[8];
         unpack8(zv, zf);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) gf[j] = zf[j] > 0.f ? gf[j] : 0.f;
+        for (int j = 0; j < 8; ++j) gf[j] = (zf[j] > 0.f && zf[j] < hi) ? gf[j] : 0.f;     // ReLU (hi = inf) / ReLU6 (hi = 6)
         g.x = pack2(gf[0], gf[1]); g.y = pack2(gf[2], gf[3]); g.z = pack2(gf[4], gf[5]); g.w = pack2(gf[6], gf[7]);
         if (dzm != nullptr) *reinterpret_cast<uint4*>(dzm + off) = g;
       }
@@ -327,7 +327,7 @@ bn_bwd_apply_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ z, con
                     bf16* __restrict__ dy, const float* __restrict__ gamma, const float* __restrict__ sum,
                     const float* __restrict__ sumsq, const float* __restrict__ rmean, const float* __restrict__ rvar,
                     const float* __restrict__ s1, const float* __restrict__ s2, long M, int C, float inv_count, float eps,
-                    int train) {
+                    int train, float hi) {
   const int groups = C >> 3;
   const long total = M * groups;
   const long i0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -351,7 +351,7 @@ bn_bwd_apply_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ z, con
       float zf[8];
       unpack8(*reinterpret_cast<const uint4*>(z + off), zf);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) gf[j] = zf[j] > 0.f ? gf[j] : 0.f;
+      for (int j = 0; j < 8; ++j) gf[j] = (zf[j] > 0.f && zf[j] < hi) ? gf[j] : 0.f;
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = fmaf(ca[j], gf[j], fmaf(cb[j], yf[j], ck[j]));
@@ -566,10 +566,9 @@ B2_API int b2_conv2d_wgrad_nhwc_bf16(const void* x, int Nimg, int H, int W, int 
 // backward over [M, C] bf16.  When z is given (the ReLU behind the BatchNorm) dz is masked by (z > 0); the masked
 // gradient is also written to dzm when dzm != NULL (the shortcut branch's gradient);
 // s1 = sum(dz) = dbeta and s2 = sum(dz * xhat) = dgamma are ACCUMULATED (caller zeroes); dy may alias nothing.
-B2_API int b2_bn_bwd_nhwc_bf16(const void* dz, void* dzm, const void* z, const void* y, void* dy, const float* gamma, const float* sum,
-                               const float* sumsq, const float* running_mean, const float* running_var, float* s1, float* s2,
-                               long M, int C, long count, float eps, int train, void* stream) {
-  const char* who = "b2_bn_bwd_nhwc_bf16";
+static int bn_bwd_impl(const void* dz, void* dzm, const void* z, const void* y, void* dy, const float* gamma, const float* sum,
+                       const float* sumsq, const float* running_mean, const float* running_var, float* s1, float* s2, long M,
+                       int C, long count, float eps, int train, float hi, void* stream, const char* who) {
   B2_ARG_CHECK(dz && y && dy && gamma && s1 && s2 && M > 0, "%s: null pointer or empty", who);
   B2_ARG_CHECK(dzm == nullptr || z != nullptr, "%s: the masked-gradient output dzm needs the ReLU mask z", who);
   cudaStream_t st = (cudaStream_t)stream;
@@ -580,15 +579,30 @@ B2_API int b2_bn_bwd_nhwc_bf16(const void* dz, void* dzm, const void* z, const v
   rpb = (rpb + lanes - 1) / lanes * lanes;
   const unsigned blocks = (unsigned)((M + rpb - 1) / rpb);
   bn_bwd_reduce_kernel<<<blocks, 256, 0, st>>>((const bf16*)dz, (bf16*)dzm, (const bf16*)z, (const bf16*)y, sum, sumsq, running_mean,
-                                               running_var, s1, s2, M, C, (int)rpb, inv, eps, train);
+                                               running_var, s1, s2, M, C, (int)rpb, inv, eps, train, hi);
   B2_LAUNCH_CHECK("bn_bwd_reduce_kernel");
   // the grid stride (blocks * 256 threads) must be a multiple of the channel-group count for the hoisted coefficients
   unsigned ab = ew_blocks(M * groups);
   if (256 % groups != 0) ab = ab / groups * groups > 0 ? ab / groups * groups : groups;
   bn_bwd_apply_kernel<<<ab, 256, 0, st>>>((const bf16*)dz, (const bf16*)z, (const bf16*)y, (bf16*)dy, gamma, sum, sumsq,
-                                          running_mean, running_var, s1, s2, M, C, inv, eps, train);
+                                          running_mean, running_var, s1, s2, M, C, inv, eps, train, hi);
   B2_LAUNCH_CHECK("bn_bwd_apply_kernel");
   return 0;
+}
+
+B2_API int b2_bn_bwd_nhwc_bf16(const void* dz, void* dzm, const void* z, const void* y, void* dy, const float* gamma, const float* sum,
+                               const float* sumsq, const float* running_mean, const float* running_var, float* s1, float* s2,
+                               long M, int C, long count, float eps, int train, void* stream) {
+  return bn_bwd_impl(dz, dzm, z, y, dy, gamma, sum, sumsq, running_mean, running_var, s1, s2, M, C, count, eps, train, INFINITY,
+                     stream, "b2_bn_bwd_nhwc_bf16");
+}
+
+// the same with the ReLU6 mask 0 < z < 6 (MobileNetV2: nn.ReLU6 behind every BatchNorm but the linear bottleneck's)
+B2_API int b2_bn_bwd_relu6_nhwc_bf16(const void* dz, void* dzm, const void* z, const void* y, void* dy, const float* gamma,
+                                     const float* sum, const float* sumsq, const float* running_mean, const float* running_var,
+                                     float* s1, float* s2, long M, int C, long count, float eps, int train, void* stream) {
+  return bn_bwd_impl(dz, dzm, z, y, dy, gamma, sum, sumsq, running_mean, running_var, s1, s2, M, C, count, eps, train, 6.0f, stream,
+                     "b2_bn_bwd_relu6_nhwc_bf16");
 }
 
 // z [N,H,W,C] (caller zeroes) <- dy [N,P,Q,C] at the even positions: the stride-2 data gradient runs a stride-1 conv over z

@@ -7,7 +7,8 @@ Every layer is memory bound, so the plan is about passes over the activations, p
   BN2 + ReLU6  one in-place element pass
   project 1x1  tcgen05 GEMM + statistics
   BN3 (+ x)    one element pass (linear bottleneck: no activation; the shortcut is added here)
-The frozen encoder replays from a CUDA graph like the other backbones."""
+The frozen encoder replays from a CUDA graph like the other backbones; a (partially) trainable one runs through the autograd
+node of mobilenet_train.py (saved activations + backward kernels)."""
 from __future__ import annotations
 
 import os
@@ -68,8 +69,9 @@ class MobileNetRunner:
         if self._params is None:
             self._params = list(net.parameters())
         if torch.is_grad_enabled() and any(p.requires_grad for p in self._params):
-            raise NotImplementedError("trainable MobileNetV2 backbone: no backward kernels (the reference keeps it frozen, "
-                                      "medsos models.py:144-145); ResNet and DenseNet encoders are trainable")
+            # (partially) trainable encoder: lrcn.py:246-283 / rgb_lrcn.py:208-227 with CNN_BACKBONE = "mobilenet_v2"
+            from .mobilenet_train import encode_trainable
+            return encode_trainable(self, x, training)
         x = x.contiguous()
         N, Cin, H, W = x.shape
         assert Cin == 3, "frame encoder expects RGB frames"
