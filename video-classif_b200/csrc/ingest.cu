@@ -123,10 +123,14 @@ template <typename OutT>
 __global__ void __launch_bounds__(256)
 ingest_identity_vec_kernel(const uint8_t* __restrict__ src, long src_frame_stride, int h, int w,
                            const int* __restrict__ frame_index, int n_out, OutT* __restrict__ dst, int swap_rb, float divisor) {
+  // byte -> float through a 256-entry table: the correctly rounded fp32 division (bit-exact with numpy's /255.0 cast to
+  // float32) costs ~10 instructions per value, and the first vectorised version was issue bound, not HBM bound
+  __shared__ float lut[256];
+  for (int v = threadIdx.x; v < 256; v += blockDim.x) lut[v] = divisor != 1.0f ? __fdiv_rn((float)v, divisor) : (float)v;
+  __syncthreads();
   const int chunks = w >> 4;                                   // 16-pixel chunks per row
   const long total = (long)n_out * h * chunks;
   const long plane = (long)h * w;
-  const bool scale = divisor != 1.0f;
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
     const int cx = (int)(idx % chunks);
     const long row = idx / chunks;
@@ -149,10 +153,7 @@ ingest_identity_vec_kernel(const uint8_t* __restrict__ src, long src_frame_strid
       for (int g = 0; g < 4; ++g) {
         float v[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float u = (float)b[(g * 4 + k) * 3 + sc];
-          v[k] = scale ? __fdiv_rn(u, divisor) : u;
-        }
+        for (int k = 0; k < 4; ++k) v[k] = lut[b[(g * 4 + k) * 3 + sc]];
         store4<OutT>(o + c * plane + g * 4, v[0], v[1], v[2], v[3]);
       }
     }
@@ -174,6 +175,10 @@ ingest_bilinear_rows_kernel(const uint8_t* __restrict__ src, long src_frame_stri
   const int row_bytes = src_w * 3;                             // multiple of 16 (host guarantees src_w % 16 == 0)
   uint8_t* rows_s = ism;                                       // [rows_per_cta][2][row_bytes]
   TapX* tx_s = reinterpret_cast<TapX*>(ism + (size_t)rows_per_cta * 2 * row_bytes);
+  __shared__ float lut[256];
+  __shared__ int rowidx_s[16];                                 // source row of staged row rr = 2 r + {0, 1}
+  __shared__ short rowwt_s[16];                                // vertical coefficients w0, w1 of output row r at [2 r], [2 r + 1]
+  for (int v = threadIdx.x; v < 256; v += blockDim.x) lut[v] = divisor != 1.0f ? __fdiv_rn((float)v, divisor) : (float)v;
   const int f = blockIdx.x / strips;
   const int y0 = (blockIdx.x - f * strips) * rows_per_cta;
   const int nrows = min(rows_per_cta, dst_h - y0);
@@ -196,20 +201,25 @@ ingest_bilinear_rows_kernel(const uint8_t* __restrict__ src, long src_frame_stri
     const Tap t = make_tap(x, src_w, scale_x, false);
     tx_s[x] = {t.i0 * 3, t.i1 * 3, (short)t.w0, (short)t.w1};
   }
+  if (threadIdx.x < nrows) {
+    const Tap ty = make_tap(y0 + threadIdx.x, src_h, scale_y, true);
+    rowidx_s[2 * threadIdx.x] = ty.i0;
+    rowidx_s[2 * threadIdx.x + 1] = ty.i1;
+    rowwt_s[2 * threadIdx.x] = (short)ty.w0;
+    rowwt_s[2 * threadIdx.x + 1] = (short)ty.w1;
+  }
+  __syncthreads();
   const int vec_per_row = row_bytes >> 4;
   for (int i = threadIdx.x; i < nrows * 2 * vec_per_row; i += blockDim.x) {
     const int rr = i / vec_per_row, v = i - rr * vec_per_row;
-    const Tap ty = make_tap(y0 + (rr >> 1), src_h, scale_y, true);
-    const int sy = (rr & 1) ? ty.i1 : ty.i0;
     reinterpret_cast<uint4*>(rows_s + (size_t)rr * row_bytes)[v] =
-        __ldg(reinterpret_cast<const uint4*>(fr + (long)sy * row_bytes) + v);
+        __ldg(reinterpret_cast<const uint4*>(fr + (long)rowidx_s[rr] * row_bytes) + v);
   }
   __syncthreads();
-  const bool scale = divisor != 1.0f;
   const bool vec_ok = (dst_w & 3) == 0;
   for (int i = threadIdx.x; i < nrows * quads; i += blockDim.x) {
     const int r = i / quads, x0 = (i - r * quads) * 4;
-    const Tap ty = make_tap(y0 + r, src_h, scale_y, true);
+    const int tyw0 = rowwt_s[2 * r], tyw1 = rowwt_s[2 * r + 1];
     const uint8_t* r0 = rows_s + (size_t)(2 * r) * row_bytes;
     const uint8_t* r1 = r0 + row_bytes;
     float v[3][4];
@@ -220,9 +230,8 @@ ingest_bilinear_rows_kernel(const uint8_t* __restrict__ src, long src_frame_stri
       for (int c = 0; c < 3; ++c) {
         const int h0 = r0[t.i0 + c] * t.w0 + r0[t.i1 + c] * t.w1;
         const int h1 = r1[t.i0 + c] * t.w0 + r1[t.i1 + c] * t.w1;
-        int px = (((ty.w0 * (h0 >> 4)) >> 16) + ((ty.w1 * (h1 >> 4)) >> 16) + 2) >> 2;
-        px = min(max(px, 0), 255);
-        v[c][k] = scale ? __fdiv_rn((float)px, divisor) : (float)px;
+        int px = (((tyw0 * (h0 >> 4)) >> 16) + ((tyw1 * (h1 >> 4)) >> 16) + 2) >> 2;
+        v[c][k] = lut[min(max(px, 0), 255)];
       }
     }
 #pragma unroll
