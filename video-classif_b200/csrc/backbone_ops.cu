@@ -259,49 +259,45 @@ bn_relu_maxpool_reg_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int
     sc[j] = s.x;
     sh[j] = s.y;
   }
-  const long npix = (long)N * P * Q;
-  for (long pix = (long)blockIdx.x * pix_per_block + threadIdx.x / vec; pix < npix; pix += (long)gridDim.x * pix_per_block) {
-    const int q = (int)(pix % Q);
-    const long t = pix / Q;
-    const int p = (int)(t % P);
-    const long n = t / P;
-    const bf16* base = x + (n * H * W) * C + cg * 8;
+  // sign trick: max_t relu(x_t sc + sh) = relu(|sc| max_t(sign(sc) x_t) + sh), and flipping a bf16 sign is one XOR on the packed
+  // pair -> ONE packed max per word and tap (the min / max pair + selects of the previous version made the kernel ALU bound at
+  // 0.48 of the copy bandwidth).  Padding taps are replaced by the clamped (always in-window) pixel: a duplicate never changes a max.
+  uint32_t flip[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    flip[k] = (sc[2 * k] < 0.f ? 0x00008000u : 0u) | (sc[2 * k + 1] < 0.f ? 0x80000000u : 0u);
+    sc[2 * k] = fabsf(sc[2 * k]);
+    sc[2 * k + 1] = fabsf(sc[2 * k + 1]);
+  }
+  const unsigned npix = (unsigned)((long)N * P * Q);          // host checks < 2^31
+  for (unsigned pix = blockIdx.x * pix_per_block + threadIdx.x / vec; pix < npix; pix += gridDim.x * pix_per_block) {
+    const unsigned t = pix / (unsigned)Q;
+    const int q = (int)(pix - t * (unsigned)Q);
+    const unsigned n = t / (unsigned)P;
+    const int p = (int)(t - n * (unsigned)P);
+    const bf16* base = x + ((long)n * H * W) * C + cg * 8;
     uint4 win[9];
-    bool ok[9];
 #pragma unroll
     for (int t9 = 0; t9 < 9; ++t9) {           // all 9 window loads in flight before any use
-      const int iy = 2 * p - 1 + t9 / 3, ix = 2 * q - 1 + t9 % 3;
-      ok[t9] = iy >= 0 && iy < H && ix >= 0 && ix < W;
-      win[t9] = ok[t9] ? __ldg(reinterpret_cast<const uint4*>(base + ((long)iy * W + ix) * C)) : make_uint4(0u, 0u, 0u, 0u);
+      const int iy = min(max(2 * p - 1 + t9 / 3, 0), H - 1), ix = min(max(2 * q - 1 + t9 % 3, 0), W - 1);
+      win[t9] = __ldg(reinterpret_cast<const uint4*>(base + ((long)iy * W + ix) * C));
     }
-    uint32_t mx[4], mn[4];
+    uint32_t mx[4] = {win[0].x ^ flip[0], win[0].y ^ flip[1], win[0].z ^ flip[2], win[0].w ^ flip[3]};
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      mx[k] = 0xFF80FF80u;                     // -inf pairs
-      mn[k] = 0x7F807F80u;                     // +inf pairs
-    }
+    for (int t9 = 1; t9 < 9; ++t9) {
+      const uint32_t w4[4] = {win[t9].x ^ flip[0], win[t9].y ^ flip[1], win[t9].z ^ flip[2], win[t9].w ^ flip[3]};
 #pragma unroll
-    for (int t9 = 0; t9 < 9; ++t9) {
-      const uint32_t w4[4] = {win[t9].x, win[t9].y, win[t9].z, win[t9].w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        uint32_t a, b2;
-        asm("max.bf16x2 %0, %1, %2;" : "=r"(a) : "r"(mx[k]), "r"(w4[k]));
-        asm("min.bf16x2 %0, %1, %2;" : "=r"(b2) : "r"(mn[k]), "r"(w4[k]));
-        mx[k] = ok[t9] ? a : mx[k];
-        mn[k] = ok[t9] ? b2 : mn[k];
-      }
+      for (int k = 0; k < 4; ++k) asm("max.bf16x2 %0, %1, %2;" : "=r"(mx[k]) : "r"(mx[k]), "r"(w4[k]));
     }
     float m[8];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      float hi0, hi1, lo0, lo1;
-      unpack_bf16x2(mx[k], hi0, hi1);
-      unpack_bf16x2(mn[k], lo0, lo1);
-      m[2 * k] = fmaxf(fmaf(sc[2 * k] >= 0.f ? hi0 : lo0, sc[2 * k], sh[2 * k]), 0.f);
-      m[2 * k + 1] = fmaxf(fmaf(sc[2 * k + 1] >= 0.f ? hi1 : lo1, sc[2 * k + 1], sh[2 * k + 1]), 0.f);
+      float v0, v1;
+      unpack_bf16x2(mx[k], v0, v1);
+      m[2 * k] = fmaxf(fmaf(v0, sc[2 * k], sh[2 * k]), 0.f);
+      m[2 * k + 1] = fmaxf(fmaf(v1, sc[2 * k + 1], sh[2 * k + 1]), 0.f);
     }
-    store8(y + pix * C + cg * 8, m);
+    store8(y + (long)pix * C + cg * 8, m);
   }
 }
 
@@ -451,7 +447,7 @@ B2_API int b2_bn_relu_maxpool_nhwc(const void* x, void* y, int N, int H, int W, 
   const long count = (long)N * H * W;
   const float inv = 1.f / (float)count;
   const float unbias = count > 1 ? (float)((double)count / (double)(count - 1)) : 1.f;
-  if (256 % (C / 8) == 0) {
+  if (256 % (C / 8) == 0 && (long)N * P * Q < (1L << 31)) {
     bn_relu_maxpool_reg_kernel<<<grid_for((long)N * P * Q * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>(
         (const bf16*)x, (bf16*)y, N, H, W, C, P, Q, bn, inv, unbias, eps, momentum, train);
   } else {

@@ -5,16 +5,18 @@
 // (reference: medsos_lrcn/src/loader_data.py:162-163,182,201,112; crime path lrcn/lrcn.py:136-142).
 // The resize is OpenCV's INTER_LINEAR 8-bit algorithm restated in integer arithmetic (11-bit
 // coefficients, two-pass rounding) so the uint8 result is bit-identical to cv2; the exact 2x2
-// decimation case is OpenCV's INTER_AREA shortcut.  HBM-bound.  Two vectorised kernels carry the common shapes:
-//   * ingest_identity_vec_kernel  (no resize, W % 16 == 0): a thread converts 16 pixels -- three 128-bit loads of the
-//     interleaved bytes, per channel plane four 128-bit (fp32) or two 128-bit (bf16) stores;
-//   * ingest_bilinear_rows_kernel (general resize, W0 % 16 == 0): a CTA owns a strip of output rows of one frame, copies
-//     the two source rows each of them taps into shared memory with 128-bit loads (every touched 32-byte sector is
-//     fetched once: at the usual down-scales the horizontal taps hit every sector of those rows anyway), the horizontal
-//     coefficients are computed once per CTA, a thread produces 4 neighbouring pixels and stores them as one vector
-//     per channel plane.
-// ingest_kernel (one pixel per thread, byte gathers) remains for the 2x2 shortcut and unaligned widths.
+// decimation case is OpenCV's INTER_AREA shortcut.
+//   * ingest_identity_vec_kernel  (no resize, W % 16 == 0: the bench's 112x112 clips, cfg 1's 64x64): a thread converts 16 pixels --
+//     three 128-bit loads of the interleaved bytes, per channel plane four 128-bit (fp32) or two 128-bit (bf16) stores; byte ->
+//     float through a 256-entry table of correctly rounded quotients (the division was the issue-slot hog): 0.30 -> 0.56 of copy peak
+//   * ingest_kernel               general resize: one output pixel per thread gathering its 2 x 2 taps through L1 (neighbouring
+//     threads share the 32-byte sectors).  It moves (source rows touched + output) at 4.4 TB/s = 0.67 of the copy peak; a
+//     row-strip variant that staged the two source rows of every output row in shared memory with 128-bit loads was measured
+//     SLOWER (171 vs 135 us at 1024 x 360x640 -> 112x112): the 11-bit fixed-point arithmetic (~150 instructions per pixel)
+//     bounds the kernel, not the loads (ncu: 61 % issue-slot utilisation, DRAM 440 MB read in both forms).
 #include "common.cuh"
+
+#include <stdlib.h>
 
 namespace {
 
@@ -62,6 +64,9 @@ __global__ void __launch_bounds__(256)
 ingest_kernel(const uint8_t* __restrict__ src, long src_frame_stride, int src_h, int src_w,
               const int* __restrict__ frame_index, int n_out, OutT* __restrict__ dst, int dst_h, int dst_w,
               int swap_rb, float divisor, int mode, double scale_x, double scale_y) {
+  __shared__ float lut[256];                     // byte -> float: correctly rounded v / divisor, computed once per CTA
+  for (int v = threadIdx.x; v < 256; v += blockDim.x) lut[v] = divisor != 1.0f ? __fdiv_rn((float)v, divisor) : (float)v;
+  __syncthreads();
   const long total = (long)n_out * dst_h * dst_w;
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
     const int x = (int)(idx % dst_w);
@@ -100,8 +105,7 @@ ingest_kernel(const uint8_t* __restrict__ src, long src_frame_stride, int src_h,
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const int sc = swap_rb ? 2 - c : c;
-      const float v = (divisor == 1.0f) ? (float)px[sc] : __fdiv_rn((float)px[sc], divisor);
-      o[c * plane] = to_out<OutT>(v);
+      o[c * plane] = to_out<OutT>(lut[px[sc]]);
     }
   }
 }
@@ -160,90 +164,6 @@ ingest_identity_vec_kernel(const uint8_t* __restrict__ src, long src_frame_strid
   }
 }
 
-struct TapX {
-  int i0, i1;
-  short w0, w1;
-};
-
-// general bilinear: CTA = (frame, strip of `rows_per_cta` output rows); source rows staged in shared memory
-template <typename OutT>
-__global__ void __launch_bounds__(256)
-ingest_bilinear_rows_kernel(const uint8_t* __restrict__ src, long src_frame_stride, int src_h, int src_w,
-                            const int* __restrict__ frame_index, OutT* __restrict__ dst, int dst_h, int dst_w, int swap_rb,
-                            float divisor, double scale_x, double scale_y, int rows_per_cta, int strips) {
-  extern __shared__ __align__(16) uint8_t ism[];
-  const int row_bytes = src_w * 3;                             // multiple of 16 (host guarantees src_w % 16 == 0)
-  uint8_t* rows_s = ism;                                       // [rows_per_cta][2][row_bytes]
-  TapX* tx_s = reinterpret_cast<TapX*>(ism + (size_t)rows_per_cta * 2 * row_bytes);
-  __shared__ float lut[256];
-  __shared__ int rowidx_s[16];                                 // source row of staged row rr = 2 r + {0, 1}
-  __shared__ short rowwt_s[16];                                // vertical coefficients w0, w1 of output row r at [2 r], [2 r + 1]
-  for (int v = threadIdx.x; v < 256; v += blockDim.x) lut[v] = divisor != 1.0f ? __fdiv_rn((float)v, divisor) : (float)v;
-  const int f = blockIdx.x / strips;
-  const int y0 = (blockIdx.x - f * strips) * rows_per_cta;
-  const int nrows = min(rows_per_cta, dst_h - y0);
-  const int sf = frame_index ? frame_index[f] : f;
-  const long plane = (long)dst_h * dst_w;
-  OutT* out_f = dst + (long)f * 3 * plane;
-  const int quads = (dst_w + 3) >> 2;
-  if (sf < 0) {                                                // zero frame (crime sampler padding)
-    for (int i = threadIdx.x; i < nrows * quads * 3; i += blockDim.x) {
-      const int c = i / (nrows * quads), rem = i - c * nrows * quads;
-      const int r = rem / quads, x = (rem - r * quads) * 4;
-      OutT* o = out_f + c * plane + (long)(y0 + r) * dst_w + x;
-      if (x + 4 <= dst_w && (dst_w & 3) == 0) store4<OutT>(o, 0.f, 0.f, 0.f, 0.f);
-      else for (int k = 0; k < 4 && x + k < dst_w; ++k) o[k] = to_out<OutT>(0.f);
-    }
-    return;
-  }
-  const uint8_t* fr = src + (long)sf * src_frame_stride;
-  for (int x = threadIdx.x; x < dst_w; x += blockDim.x) {
-    const Tap t = make_tap(x, src_w, scale_x, false);
-    tx_s[x] = {t.i0 * 3, t.i1 * 3, (short)t.w0, (short)t.w1};
-  }
-  if (threadIdx.x < nrows) {
-    const Tap ty = make_tap(y0 + threadIdx.x, src_h, scale_y, true);
-    rowidx_s[2 * threadIdx.x] = ty.i0;
-    rowidx_s[2 * threadIdx.x + 1] = ty.i1;
-    rowwt_s[2 * threadIdx.x] = (short)ty.w0;
-    rowwt_s[2 * threadIdx.x + 1] = (short)ty.w1;
-  }
-  __syncthreads();
-  const int vec_per_row = row_bytes >> 4;
-  for (int i = threadIdx.x; i < nrows * 2 * vec_per_row; i += blockDim.x) {
-    const int rr = i / vec_per_row, v = i - rr * vec_per_row;
-    reinterpret_cast<uint4*>(rows_s + (size_t)rr * row_bytes)[v] =
-        __ldg(reinterpret_cast<const uint4*>(fr + (long)rowidx_s[rr] * row_bytes) + v);
-  }
-  __syncthreads();
-  const bool vec_ok = (dst_w & 3) == 0;
-  for (int i = threadIdx.x; i < nrows * quads; i += blockDim.x) {
-    const int r = i / quads, x0 = (i - r * quads) * 4;
-    const int tyw0 = rowwt_s[2 * r], tyw1 = rowwt_s[2 * r + 1];
-    const uint8_t* r0 = rows_s + (size_t)(2 * r) * row_bytes;
-    const uint8_t* r1 = r0 + row_bytes;
-    float v[3][4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const TapX t = tx_s[min(x0 + k, dst_w - 1)];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const int h0 = r0[t.i0 + c] * t.w0 + r0[t.i1 + c] * t.w1;
-        const int h1 = r1[t.i0 + c] * t.w0 + r1[t.i1 + c] * t.w1;
-        int px = (((tyw0 * (h0 >> 4)) >> 16) + ((tyw1 * (h1 >> 4)) >> 16) + 2) >> 2;
-        v[c][k] = lut[min(max(px, 0), 255)];
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const int sc = swap_rb ? 2 - c : c;
-      OutT* o = out_f + c * plane + (long)(y0 + r) * dst_w + x0;
-      if (vec_ok) store4<OutT>(o, v[sc][0], v[sc][1], v[sc][2], v[sc][3]);
-      else for (int k = 0; k < 4 && x0 + k < dst_w; ++k) o[k] = to_out<OutT>(v[sc][k]);
-    }
-  }
-}
-
 }  // namespace
 
 B2_API int b2_ingest_u8(const void* src, int n_src_frames, int src_h, int src_w, long src_frame_stride,
@@ -276,29 +196,6 @@ B2_API int b2_ingest_u8(const void* src, int n_src_frames, int src_h, int src_w,
                                                           n_out, (float*)dst, swap_rb, divisor);
     B2_LAUNCH_CHECK("ingest_identity_vec_kernel");
     return 0;
-  }
-  if (mode == 2 && (src_w & 15) == 0 && src16 && dst16 && ((long)dst_h * dst_w * (out_bf16 ? 2 : 4)) % 16 == 0 &&
-      (dst_w % 4 != 0 || (dst_w * (out_bf16 ? 2 : 4)) % (out_bf16 ? 8 : 16) == 0)) {
-    const int row_bytes = src_w * 3;
-    int rows = (40 * 1024) / (2 * row_bytes);                  // source rows of a strip must fit 40 KB of shared memory
-    if (rows > 8) rows = 8;
-    if (rows >= 1 && (long)n_out * b2_ceil_div(dst_h, rows) < (1L << 31)) {
-      const int strips = b2_ceil_div(dst_h, rows);
-      const size_t smem = (size_t)rows * 2 * row_bytes + (size_t)dst_w * sizeof(TapX);
-      if (smem <= 48 * 1024) {
-        const unsigned g = (unsigned)((long)n_out * strips);
-        if (out_bf16)
-          ingest_bilinear_rows_kernel<bf16><<<g, 256, smem, st>>>((const uint8_t*)src, src_frame_stride, src_h, src_w,
-                                                                  frame_index, (bf16*)dst, dst_h, dst_w, swap_rb, divisor, sx,
-                                                                  sy, rows, strips);
-        else
-          ingest_bilinear_rows_kernel<float><<<g, 256, smem, st>>>((const uint8_t*)src, src_frame_stride, src_h, src_w,
-                                                                   frame_index, (float*)dst, dst_h, dst_w, swap_rb, divisor, sx,
-                                                                   sy, rows, strips);
-        B2_LAUNCH_CHECK("ingest_bilinear_rows_kernel");
-        return 0;
-      }
-    }
   }
   if (out_bf16)
     ingest_kernel<bf16><<<grid, 256, 0, st>>>((const uint8_t*)src, src_frame_stride, src_h, src_w, frame_index, n_out,
