@@ -293,8 +293,9 @@ int b2_softplus_f32(const float* x, float* y, long n, void* stream);
 int b2_mul_silu_f32(const float* a, const float* res, long res_ld, int res_cols, float* y, long rows, int cols, void* stream);
 
 /* Backward of the same pieces (training rnn_type="mamba": small L / D / N).  Buffers marked ACCUMULATED are added into
- * with atomics and must be zeroed by the caller.  b2_selective_scan_bwd: workspace = batch*D*L*b2_scan_padded_states(N) floats (recomputed forward
- * states); chunk_reset > 0: state reset every chunk_reset steps (videomamba), chunks in parallel; a_is_log = 1: dA is the
+ * with atomics and must be zeroed by the caller.  b2_selective_scan_bwd: scans / chunks of up to 512 steps keep the recomputed forward
+ * states on chip (checkpoints in shared memory, segments in registers) and take workspace = NULL; longer ones need
+ * workspace[b2_scan_bwd_workspace_floats(...)] (= batch*D*L*b2_scan_padded_states(N), 0 when none is needed); chunk_reset > 0: state reset every chunk_reset steps (videomamba), chunks in parallel; a_is_log = 1: dA is the
  * gradient of A_log where A = -exp(A_log), 0: of A itself. */
 int b2_rmsnorm_bwd_f32(const float* dy, const float* x, const float* w, float* dx, float* dw, long rows, int D, float eps,
                        void* stream);
@@ -303,6 +304,7 @@ int b2_dwconv1d_silu_bwd_f32(const float* dy, const float* x, long x_ld, const f
 int b2_softplus_bwd_f32(const float* dy, const float* x, float* dx, long n, void* stream);
 int b2_mul_silu_bwd_f32(const float* dy, const float* a, const float* res, long res_ld, int res_cols, float* da, float* dres,
                         long dres_ld, long rows, int cols, void* stream);
+long b2_scan_bwd_workspace_floats(int batch, int L, int D, int N, int chunk_reset);
 int b2_selective_scan_bwd(const float* u, const float* delta, const float* A, const float* B, const float* C, const float* dy,
                           float* workspace, float* du, float* ddelta, float* dA, float* dB, float* dC, int batch, int L,
                           int D, int N, int chunk_reset, int reverse, int a_is_log, void* stream);

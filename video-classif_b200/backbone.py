@@ -129,7 +129,10 @@ class ResNetRunner:
             torch.cuda.synchronize(x.device)
             graph = torch.cuda.CUDAGraph()
             n0 = _lib.launch_count()
-            with torch.cuda.graph(graph):
+            # kernel nodes inherit the capture stream's priority: B2_ENC_PRIORITY=-1 lets the encoder's CTAs go first and
+            # the small tail kernels of the previous batch fill the gaps of its partial waves
+            prio = int(os.environ.get("B2_ENC_PRIORITY", "0"))
+            with torch.cuda.graph(graph, stream=torch.cuda.Stream(device=x.device, priority=prio)):
                 static_feat = self(static_x, training)
             # results rotate through a small ring of persistent buffers: no per-call allocation (a tensor handed from
             # the encoder's stream to the consumer's stream every step made the caching allocator hold blocks back)

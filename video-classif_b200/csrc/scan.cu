@@ -27,63 +27,131 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-// NP = n_state rounded up to a compiled width; states n >= N are padding: a = B = C = 0 keeps them at zero
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// NP = n_state rounded up to a compiled width; states n >= N are padding: a = B = C = 0 keeps them at zero.
+// The kernel is bound by the exponentials (16 MUFU.EX2 per channel and step against 4 lanes per clock and SM partition:
+// ~128 clocks per warp and step, 2.6x the HBM time of its traffic), so everything else is kept off the critical path:
+// the B_t / C_t tiles arrive through a double-buffered cp.async ring one tile ahead, and the u / delta values of the next
+// four steps are loaded into registers while the current four are computed.
 template <int NP>
 __global__ void __launch_bounds__(kScanThreads)
 selective_scan_fwd_kernel(const float* __restrict__ u, const float* __restrict__ delta, const float* __restrict__ A,
                           const float* __restrict__ Bm, const float* __restrict__ Cm, float* __restrict__ y, int L, int D,
                           int N, int chunk, int reverse) {
-  __shared__ float bc_s[kScanTile][2 * NP];     // [t][B_t | C_t]
+  __shared__ __align__(16) float bc_s[2][kScanTile][2 * NP];     // [buffer][t][B_t | C_t]
   const int b = blockIdx.z;
   const int d = blockIdx.x * kScanThreads + threadIdx.x;
   const int t_begin = blockIdx.y * chunk;
   const int t_end = min(L, t_begin + chunk);
   const bool active = d < D;
-  float a2[NP], x[NP];
+  // 16-byte copies need whole float4 groups per row and aligned rows
+  const bool fast = N == NP && (((uintptr_t)Bm | (uintptr_t)Cm) & 15) == 0;
+  // packed fp32 pairs (FMUL2 / FFMA2): half the issue slots of the scalar form, the MUFU stays the bound
+  float2 a2[NP / 2], x[NP / 2];
 #pragma unroll
-  for (int n = 0; n < NP; ++n) {
-    a2[n] = (active && n < N) ? A[(long)d * N + n] * kLog2e : 0.f;     // exp(delta a) = 2^(delta a log2 e)
-    x[n] = 0.f;
+  for (int n = 0; n < NP / 2; ++n) {
+    a2[n].x = (active && 2 * n < N) ? A[(long)d * N + 2 * n] * kLog2e : 0.f;     // exp(delta a) = 2^(delta a log2 e)
+    a2[n].y = (active && 2 * n + 1 < N) ? A[(long)d * N + 2 * n + 1] * kLog2e : 0.f;
+    x[n] = make_float2(0.f, 0.f);
   }
   const long row0 = (long)b * L;
-  for (int t0 = t_begin; t0 < t_end; t0 += kScanTile) {
+  auto load_tile = [&](int buf, int t0) {
     const int nt = min(kScanTile, t_end - t0);
-    __syncthreads();
-    for (int i = threadIdx.x; i < nt * 2 * NP; i += kScanThreads) {
-      const int tt = i / (2 * NP), j = i - tt * 2 * NP;
-      const long r = (row0 + t0 + tt) * N;
-      const int n = j < NP ? j : j - NP;
-      bc_s[tt][j] = n < N ? (j < NP ? Bm[r + n] : Cm[r + n]) : 0.f;
+    if (fast) {
+      constexpr int kQ = NP / 4;                 // float4 groups per B (or C) row
+      for (int i = threadIdx.x; i < nt * 2 * kQ; i += kScanThreads) {
+        const int tt = i / (2 * kQ), j = i - tt * 2 * kQ;
+        const long r = (row0 + t0 + tt) * N;
+        cp_async16(&bc_s[buf][tt][4 * j], j < kQ ? Bm + r + 4 * j : Cm + r + 4 * (j - kQ));
+      }
+    } else {
+      for (int i = threadIdx.x; i < nt * 2 * NP; i += kScanThreads) {
+        const int tt = i / (2 * NP), j = i - tt * 2 * NP;
+        const long r = (row0 + t0 + tt) * N;
+        const int n = j < NP ? j : j - NP;
+        bc_s[buf][tt][j] = n < N ? (j < NP ? Bm[r + n] : Cm[r + n]) : 0.f;
+      }
+    }
+    cp_async_commit();
+  };
+  // u / delta / y are walked with one pointer each: element (t, d) of this clip, `step` floats to the next time step
+  const long step = reverse ? -(long)D : (long)D;
+  const long e0 = (row0 + (reverse ? L - 1 - t_begin : t_begin)) * D + (active ? d : 0);
+  const float* pu = u + e0;
+  const float* pd = delta + e0;
+  float* py = y + e0;
+  auto load_ud = [&](int t, const float* qu, const float* qd, float (&uu)[4], float (&dd)[4]) {
+    if (t + 4 <= t_end) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        uu[k] = __ldg(qu + k * step);
+        dd[k] = __ldg(qd + k * step);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const bool ok = t + k < t_end;
+        uu[k] = ok ? __ldg(qu + k * step) : 0.f;
+        dd[k] = ok ? __ldg(qd + k * step) : 0.f;
+      }
+    }
+  };
+  float un[4], dn[4];
+  load_tile(0, t_begin);
+  load_ud(t_begin, pu, pd, un, dn);
+  int buf = 0;
+  for (int t0 = t_begin; t0 < t_end; t0 += kScanTile, buf ^= 1) {
+    const int nt = min(kScanTile, t_end - t0);
+    if (t0 + kScanTile < t_end) {
+      load_tile(buf ^ 1, t0 + kScanTile);        // its previous readers passed the barrier that closed the last iteration
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
     __syncthreads();
-    if (!active) continue;
     for (int tq = 0; tq < nt; tq += 4) {
       float uu[4], dd[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {             // four steps of u / delta in flight
-        const int t = t0 + tq + k;
-        const int ts = reverse ? L - 1 - t : t;
-        const bool ok = tq + k < nt;
-        uu[k] = ok ? u[(row0 + ts) * D + d] : 0.f;
-        dd[k] = ok ? delta[(row0 + ts) * D + d] : 0.f;
+      for (int k = 0; k < 4; ++k) {
+        uu[k] = un[k];
+        dd[k] = dn[k];
       }
+      pu += 4 * step;
+      pd += 4 * step;
+      load_ud(t0 + tq + 4, pu, pd, un, dn);      // the next four steps (possibly of the next tile) are in flight
+      const int kn = min(4, nt - tq);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        if (tq + k < nt) {
-          const int t = t0 + tq + k;
-          const float du = dd[k] * uu[k];
-          const float* bc = bc_s[tq + k];
-          float acc = 0.f;
+        if (k < kn) {
+          const float2 du2 = make_float2(dd[k] * uu[k], dd[k] * uu[k]);
+          const float2 dd2 = make_float2(dd[k], dd[k]);
+          const float4* bc = reinterpret_cast<const float4*>(bc_s[buf][tq + k]);
+          float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
-          for (int n = 0; n < NP; ++n) {
-            x[n] = fmaf(ex2_approx(dd[k] * a2[n]), x[n], du * bc[n]);
-            acc = fmaf(x[n], bc[NP + n], acc);
+          for (int q = 0; q < NP / 4; ++q) {
+            const float4 b4 = bc[q], c4 = bc[NP / 4 + q];
+            float2 e0v = __fmul2_rn(dd2, a2[2 * q]), e1v = __fmul2_rn(dd2, a2[2 * q + 1]);
+            e0v.x = ex2_approx(e0v.x);
+            e0v.y = ex2_approx(e0v.y);
+            e1v.x = ex2_approx(e1v.x);
+            e1v.y = ex2_approx(e1v.y);
+            x[2 * q] = __ffma2_rn(e0v, x[2 * q], __fmul2_rn(du2, make_float2(b4.x, b4.y)));
+            x[2 * q + 1] = __ffma2_rn(e1v, x[2 * q + 1], __fmul2_rn(du2, make_float2(b4.z, b4.w)));
+            acc = __ffma2_rn(x[2 * q], make_float2(c4.x, c4.y), acc);
+            acc = __ffma2_rn(x[2 * q + 1], make_float2(c4.z, c4.w), acc);
           }
-          const int ts = reverse ? L - 1 - t : t;
-          y[(row0 + ts) * D + d] = acc;
+          if (active) py[k * step] = acc.x + acc.y;
         }
       }
+      py += 4 * step;
     }
+    __syncthreads();
   }
 }
 
@@ -321,7 +389,7 @@ mul_silu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ a, c
 // NP = n_state rounded up to a compiled width (states n >= N are padding and contribute nothing); workspace stride NP
 template <int NP>
 __global__ void __launch_bounds__(128)
-selective_scan_bwd_kernel(const float* __restrict__ u, const float* __restrict__ delta, const float* __restrict__ A,
+selective_scan_bwd_ws_kernel(const float* __restrict__ u, const float* __restrict__ delta, const float* __restrict__ A,
                           const float* __restrict__ Bm, const float* __restrict__ Cm, const float* __restrict__ dy,
                           float* __restrict__ states, float* __restrict__ du, float* __restrict__ ddelta,
                           float* __restrict__ dA_out, float* __restrict__ dB, float* __restrict__ dC, int batch, int L, int D,
@@ -439,6 +507,206 @@ selective_scan_bwd_kernel(const float* __restrict__ u, const float* __restrict__
   }
 }
 
+
+// ---- BPTT with the states kept on chip -------------------------------------------------------------------------------
+// Same thread mapping as the workspace kernel (a channel's states spread over G = NP / 4 lanes, grid.y = chunks), but the
+// forward states never leave the SM.  Pass 1 walks the chunk forwards and keeps only the state ENTERING every kSeg-th step
+// in shared memory (16 B per lane and segment: 32 KB per block at 256-step chunks).  Pass 2 takes the segments last to
+// first: the segment's kSeg states are recomputed from its checkpoint into REGISTERS, then its steps are walked backwards.
+// HBM traffic is the algorithmic u / delta / dy / du / ddelta (+ the B, C rows); the 3.3 GB state workspace of the other
+// kernel (B 8, L 3136, D 2048, N 16: one write + two reads) is gone, at the price of a second evaluation of the forward.
+// Cross-lane sums use exchange-and-halve steps (each lane keeps half of the values and sends the other half): the eight
+// dB / dC partials of a step are summed over the warp's 8 channels with 4 + 2 + 1 shuffles and leave as ONE atomic per
+// lane; d(delta) / d(u) over the channel's lanes take one shuffle per level.
+constexpr int kSeg = 16;
+constexpr int kBwdMaxChunk = 512;          // 64 KB of checkpoints per block
+
+template <int NP>
+__global__ void __launch_bounds__(128, 4)
+selective_scan_bwd_kernel(const float* __restrict__ u, const float* __restrict__ delta, const float* __restrict__ A,
+                          const float* __restrict__ Bm, const float* __restrict__ Cm, const float* __restrict__ dy,
+                          float* __restrict__ du, float* __restrict__ ddelta, float* __restrict__ dA_out,
+                          float* __restrict__ dB, float* __restrict__ dC, int batch, int L, int D, int N, int chunk, int reverse,
+                          int a_is_log) {
+  constexpr int G = NP / 4;                // lanes per channel
+  constexpr int CW = 32 / G;               // channels per warp
+  constexpr int kLv = CW == 32 ? 5 : CW == 16 ? 4 : CW == 8 ? 3 : CW == 4 ? 2 : 1;
+  constexpr int kT = kLv < 3 ? kLv : 3;    // exchange-and-halve levels of the 8-value dB / dC reduction
+  extern __shared__ float4 ck_s[];         // [segment][thread]: state entering the segment
+  const int lane = threadIdx.x & 31;
+  const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long total = (long)batch * D * G;
+  const bool warp_reduce = (D % CW) == 0;  // the warp's channels share the batch index
+  const bool live = tid < total;
+  const long tc = live ? tid : total - 1;  // idle lanes of the last warp shadow a valid thread and contribute nothing
+  const int gq = (int)(tc % G);            // which 4 states
+  const long idx = tc / G;                 // (batch, channel)
+  const int d = (int)(idx % D);
+  const long b = idx / D;
+  const long row0 = b * L;
+  const int n0 = gq * 4;
+  const int t_begin = blockIdx.y * chunk;
+  const int t_end = min(L, t_begin + chunk);
+  const bool vec4 = (N & 3) == 0 && (((uintptr_t)Bm | (uintptr_t)Cm) & 15) == 0;
+  float a2[4];
+  bool okn[4];
+#pragma unroll
+  for (int n = 0; n < 4; ++n) {
+    okn[n] = n0 + n < N;
+    a2[n] = okn[n] ? A[(long)d * N + n0 + n] * kLog2e : 0.f;
+  }
+  auto ld4 = [&](const float* p, float (&o)[4]) {      // 4 states of a [.., N] row
+    if (vec4) {
+      const float4 v = okn[0] ? __ldg(reinterpret_cast<const float4*>(p)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+    } else {
+#pragma unroll
+      for (int n = 0; n < 4; ++n) o[n] = okn[n] ? __ldg(p + n) : 0.f;
+    }
+  };
+  auto step_fwd = [&](int t, float (&x)[4]) {          // x_t from x_{t-1} (same arithmetic as the forward kernel)
+    const int ts = reverse ? L - 1 - t : t;
+    const float dl = __ldg(delta + (row0 + ts) * D + d);
+    const float duv = dl * __ldg(u + (row0 + ts) * D + d);
+    float bb[4];
+    ld4(Bm + (row0 + t) * N + n0, bb);
+#pragma unroll
+    for (int n = 0; n < 4; ++n) x[n] = fmaf(ex2_approx(dl * a2[n]), x[n], duv * bb[n]);
+  };
+  // ---- pass 1: checkpoints
+  {
+    float x[4] = {0.f, 0.f, 0.f, 0.f};
+    int seg = 0;
+    for (int t0 = t_begin; t0 < t_end; t0 += kSeg, ++seg) {
+      ck_s[seg * 128 + threadIdx.x] = make_float4(x[0], x[1], x[2], x[3]);
+      if (t0 + kSeg < t_end) {                          // the last segment's end state is never needed
+#pragma unroll 4
+        for (int k = 0; k < kSeg; ++k) step_fwd(t0 + k, x);
+      }
+    }
+  }
+  // ---- pass 2: segments last to first
+  float g[4], dAacc[4];                                 // g: gradient flowing into x_t from step t+1
+#pragma unroll
+  for (int n = 0; n < 4; ++n) g[n] = dAacc[n] = 0.f;
+  const int nseg = (t_end - t_begin + kSeg - 1) / kSeg;
+  for (int seg = nseg - 1; seg >= 0; --seg) {
+    const int ts0 = t_begin + seg * kSeg;
+    const float4 c4 = ck_s[seg * 128 + threadIdx.x];
+    float xs[kSeg][4];
+    {
+      float x[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+      for (int k = 0; k < kSeg; ++k) {
+        if (ts0 + k < t_end) step_fwd(ts0 + k, x);
+#pragma unroll
+        for (int n = 0; n < 4; ++n) xs[k][n] = x[n];
+      }
+    }
+#pragma unroll
+    for (int k = kSeg - 1; k >= 0; --k) {
+      const int t = ts0 + k;
+      if (t < t_end) {
+        const int ts = reverse ? L - 1 - t : t;
+        const float dl = __ldg(delta + (row0 + ts) * D + d);
+        const float uv = __ldg(u + (row0 + ts) * D + d);
+        const float dyv = __ldg(dy + (row0 + ts) * D + d);
+        float bt[4], ct[4];
+        ld4(Bm + (row0 + t) * N + n0, bt);
+        ld4(Cm + (row0 + t) * N + n0, ct);
+        const float dlu = dl * uv;
+        float s1 = 0.f, s2 = 0.f, v[8];
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+          const float xp = k > 0 ? xs[k > 0 ? k - 1 : 0][n] : (n == 0 ? c4.x : n == 1 ? c4.y : n == 2 ? c4.z : c4.w);
+          const float at = ex2_approx(dl * a2[n]);
+          const float dx = fmaf(dyv, ct[n], g[n]);
+          const float e = dx * xp * at;                 // d a_t / d(delta A) folded in: a_t = exp(delta A)
+          s1 = fmaf(e, a2[n], s1);                      // d(delta) = ln2 * s1 + u * s2
+          s2 = fmaf(dx, bt[n], s2);                     // d(u)     = delta * s2
+          dAacc[n] = fmaf(e, dl, dAacc[n]);
+          v[n] = live ? dx * dlu : 0.f;                 // dB
+          v[4 + n] = live ? dyv * xs[k][n] : 0.f;       // dC
+          g[n] = at * dx;
+        }
+        float ddl = fmaf(s1, 0.6931471805599453f, uv * s2);
+        float duv = dl * s2;
+        // d(delta), d(u): sum over the channel's G lanes; afterwards lanes with (gq & G/2) == 0 hold d(delta), the others d(u)
+        if (G > 1) {
+          const bool up = (gq & (G / 2)) != 0;
+          const float send = up ? ddl : duv;
+          float keep = up ? duv : ddl;
+          keep += __shfl_xor_sync(0xffffffffu, send, G / 2);
+#pragma unroll
+          for (int off = G / 4; off >= 1; off >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, off);
+          if (live && (gq & (G / 2 - 1)) == 0) {
+            if (up) du[(row0 + ts) * D + d] = keep;
+            else ddelta[(row0 + ts) * D + d] = keep;
+          }
+        } else if (live) {
+          du[(row0 + ts) * D + d] = duv;
+          ddelta[(row0 + ts) * D + d] = ddl;
+        }
+        // dB, dC: sum over the warp's channels
+        if (warp_reduce) {
+          if (kT >= 1) {
+            const bool up = (lane & 16) != 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float send = up ? v[i] : v[i + 4];
+              const float keep = up ? v[i + 4] : v[i];
+              v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+          }
+          if (kT >= 2) {
+            const bool up = (lane & 8) != 0;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const float send = up ? v[i] : v[i + 2];
+              const float keep = up ? v[i + 2] : v[i];
+              v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+          }
+          if (kT >= 3) {
+            const bool up = (lane & 4) != 0;
+            const float send = up ? v[0] : v[1];
+            const float keep = up ? v[1] : v[0];
+            v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+#pragma unroll
+            for (int off = 2; off >= G; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+          }
+          // this lane now holds 8 >> kT complete sums: original value indices base .. base + (8 >> kT) - 1
+          constexpr int kKeep = 8 >> kT;
+          const int base = (kT >= 1 ? ((lane >> 4) & 1) * 4 : 0) + (kT >= 2 ? ((lane >> 3) & 1) * 2 : 0) + (kT >= 3 ? ((lane >> 2) & 1) : 0);
+          const bool writer = kT < 3 || (lane & 3 & ~(G - 1)) == 0;    // after the plain levels every lane of the group holds the sum
+#pragma unroll
+          for (int i = 0; i < kKeep; ++i) {
+            const int vi = base + i;                   // 0..3: dB state vi, 4..7: dC state vi - 4
+            const int n = vi & 3;
+            if (writer && n0 + n < N) atomicAdd((vi < 4 ? dB : dC) + (row0 + t) * N + n0 + n, v[i]);
+          }
+        } else if (live) {
+#pragma unroll
+          for (int n = 0; n < 4; ++n) {
+            if (okn[n]) {
+              atomicAdd(dB + (row0 + t) * N + n0 + n, v[n]);
+              atomicAdd(dC + (row0 + t) * N + n0 + n, v[4 + n]);
+            }
+          }
+        }
+      }
+    }
+  }
+  if (live) {
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+      if (okn[n]) {
+        const float a = a2[n] * 0.6931471805599453f;
+        atomicAdd(dA_out + (long)d * N + n0 + n, a_is_log ? dAacc[n] * a : dAacc[n]);
+      }
+  }
+}
+
 }  // namespace
 
 // dw is ACCUMULATED into (caller zeroes)
@@ -478,13 +746,21 @@ B2_API int b2_mul_silu_bwd_f32(const float* dy, const float* a, const float* res
   return 0;
 }
 
-// workspace: batch * D * L * b2_scan_padded_states(N) floats; du / ddelta overwritten; dA [D,N], dB / dC [batch,L,N] ACCUMULATED (caller zeroes).
+// du / ddelta overwritten; dA [D,N], dB / dC [batch,L,N] ACCUMULATED (caller zeroes).
 // chunk_reset > 0: the state restarts from zero every chunk_reset steps (videomamba.py:242-284), chunks run in parallel;
-// a_is_log = 1: dA is the gradient of A_log where A = -exp(A_log) (medsos models.py:94), 0: the gradient of A itself
+// a_is_log = 1: dA is the gradient of A_log where A = -exp(A_log) (medsos models.py:94), 0: the gradient of A itself.
+// Scans (or chunks) of up to 512 steps keep their states on chip and need no workspace (b2_scan_bwd_workspace_floats = 0,
+// `workspace` may be NULL); longer ones recompute them into workspace[batch * D * L * b2_scan_padded_states(N)].
+B2_API long b2_scan_bwd_workspace_floats(int batch, int L, int D, int N, int chunk_reset) {
+  const int chunk = chunk_reset > 0 && chunk_reset < L ? chunk_reset : L;
+  if (chunk <= kBwdMaxChunk) return 0;
+  return (long)batch * D * L * b2_scan_padded_states(N);
+}
+
 B2_API int b2_selective_scan_bwd(const float* u, const float* delta, const float* A, const float* Bm, const float* Cm,
                                  const float* dy, float* workspace, float* du, float* ddelta, float* dA, float* dB, float* dC,
                                  int batch, int L, int D, int N, int chunk_reset, int reverse, int a_is_log, void* stream) {
-  B2_ARG_CHECK(u && delta && A && Bm && Cm && dy && workspace && du && ddelta && dA && dB && dC,
+  B2_ARG_CHECK(u && delta && A && Bm && Cm && dy && du && ddelta && dA && dB && dC,
                "b2_selective_scan_bwd: null pointer");
   B2_ARG_CHECK(batch > 0 && L > 0 && D > 0, "b2_selective_scan_bwd: empty shape");
   B2_ARG_CHECK(N >= 1 && N <= 64, "b2_selective_scan_bwd: n_state must be in 1..64 (got %d)", N);
@@ -493,12 +769,41 @@ B2_API int b2_selective_scan_bwd(const float* u, const float* delta, const float
   const int chunks = b2_ceil_div(L, chunk);
   B2_ARG_CHECK(chunks <= 65535, "b2_selective_scan_bwd: too many chunks");
   B2_ARG_CHECK(!(reverse && chunks > 1), "b2_selective_scan_bwd: the reference has no chunk-reset scan in the reverse direction");
+  const bool on_chip = b2_scan_bwd_workspace_floats(batch, L, D, N, chunk_reset) == 0;
+  B2_ARG_CHECK(on_chip || workspace, "b2_selective_scan_bwd: a %d-step scan needs the state workspace", chunk < L ? chunk : L);
   const long threads = (long)batch * D * (NP / 4);      // one lane per 4 states
   const dim3 grid((unsigned)((threads + 127) / 128), (unsigned)chunks);
   cudaStream_t st = (cudaStream_t)stream;
-#define B2_SCAN_BWD(NN)                                                                                          \
-  selective_scan_bwd_kernel<NN><<<grid, 128, 0, st>>>(u, delta, A, Bm, Cm, dy, workspace, du, ddelta, dA, dB, dC, \
-                                                      batch, L, D, N, chunk, reverse, a_is_log)
+  if (on_chip) {
+    const int steps = chunk < L ? chunk : L;
+    const int smem = b2_ceil_div(steps, kSeg) * 128 * (int)sizeof(float4);
+    static B2PerDeviceOnce attr;
+    if (attr.needed()) {
+      const int max_smem = kBwdMaxChunk / kSeg * 128 * (int)sizeof(float4);
+      B2_CUDA_CHECK(cudaFuncSetAttribute(selective_scan_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+      B2_CUDA_CHECK(cudaFuncSetAttribute(selective_scan_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+      B2_CUDA_CHECK(cudaFuncSetAttribute(selective_scan_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+      B2_CUDA_CHECK(cudaFuncSetAttribute(selective_scan_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+      B2_CUDA_CHECK(cudaFuncSetAttribute(selective_scan_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+      attr.mark();
+    }
+#define B2_SCAN_BWD(NN)                                                                                       \
+  selective_scan_bwd_kernel<NN><<<grid, 128, smem, st>>>(u, delta, A, Bm, Cm, dy, du, ddelta, dA, dB, dC, batch, L, D, N, \
+                                                         chunk, reverse, a_is_log)
+    switch (NP) {
+      case 4: B2_SCAN_BWD(4); break;
+      case 8: B2_SCAN_BWD(8); break;
+      case 16: B2_SCAN_BWD(16); break;
+      case 32: B2_SCAN_BWD(32); break;
+      default: B2_SCAN_BWD(64); break;
+    }
+#undef B2_SCAN_BWD
+    B2_LAUNCH_CHECK("selective_scan_bwd_kernel");
+    return 0;
+  }
+#define B2_SCAN_BWD(NN)                                                                                             \
+  selective_scan_bwd_ws_kernel<NN><<<grid, 128, 0, st>>>(u, delta, A, Bm, Cm, dy, workspace, du, ddelta, dA, dB, dC, \
+                                                         batch, L, D, N, chunk, reverse, a_is_log)
   switch (NP) {
     case 4: B2_SCAN_BWD(4); break;
     case 8: B2_SCAN_BWD(8); break;

@@ -15,6 +15,8 @@ hyper-parameters from module globals (CONF_RNN_LAYER, CONF_RNN_OUT, CONF_CLASSIF
 CONF_DROPOUT); here they are explicit keyword arguments with the reference's defaults."""
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -173,7 +175,7 @@ class _BackboneLRCN(nn.Module):
         ingest kernel) keeps their storage in that stream's allocator pool: no cross-stream hand-over per batch."""
         side = self.__dict__.get("_side_stream")
         if side is None or side.device != torch.device(device):
-            side = torch.cuda.Stream(device=device)
+            side = torch.cuda.Stream(device=device, priority=int(os.environ.get("B2_ENC_PRIORITY", "0")))
             object.__setattr__(self, "_side_stream", side)
         return side
 

@@ -278,6 +278,12 @@ def _scan_fwd(u, delta, A, Bm, Cm, chunk_reset, reverse):
     return y
 
 
+def _scan_workspace(batch, L, D, N, chunk, device):
+    """State workspace of b2_selective_scan_bwd: None when the chunk's states stay on chip (<= 512 steps)."""
+    n = int(_lib.lib().b2_scan_bwd_workspace_floats(batch, L, D, N, int(chunk or 0)))
+    return torch.empty(n, device=device, dtype=F32) if n else None
+
+
 class SelectiveScanFn(torch.autograd.Function):
     """y = selective scan(u, delta, A, B, C): forward b2_selective_scan_fwd, backward b2_selective_scan_bwd (BPTT over the
     recomputed states; chunks of the chunk-reset variant in parallel)."""
@@ -295,12 +301,12 @@ class SelectiveScanFn(torch.autograd.Function):
         Bsz, L, D = u.shape
         N = A.shape[1]
         dy = dy.contiguous().float()
-        ws = torch.empty(Bsz * D * L * _lib.lib().b2_scan_padded_states(N), device=u.device, dtype=F32)
+        ws = _scan_workspace(Bsz, L, D, N, chunk, u.device)
         du, dd = torch.empty_like(u), torch.empty_like(u)
         dA = torch.zeros_like(A)
         dB, dC = torch.zeros_like(Bm), torch.zeros_like(Cm)
         call("b2_selective_scan_bwd", u.data_ptr(), delta.data_ptr(), A.data_ptr(), Bm.data_ptr(), Cm.data_ptr(), dy.data_ptr(),
-             ws.data_ptr(), du.data_ptr(), dd.data_ptr(), dA.data_ptr(), dB.data_ptr(), dC.data_ptr(), Bsz, L, D, N, chunk, rev, 0,
+             ptr(ws), du.data_ptr(), dd.data_ptr(), dA.data_ptr(), dB.data_ptr(), dC.data_ptr(), Bsz, L, D, N, chunk, rev, 0,
              stream_ptr())
         return du, dd, dA, dB, dC, None, None
 
@@ -404,7 +410,7 @@ class MambaBlockFn(torch.autograd.Function):
         call("b2_mul_silu_bwd_f32", dg.data_ptr(), y2.data_ptr(), xr.data_ptr() + di * 4, 2 * di, di, dy.data_ptr(),
              dxr.data_ptr() + di * 4, 2 * di, R, cols, st)
         # scan(s)
-        ws = torch.empty(B * di * L * _lib.lib().b2_scan_padded_states(n), device=dev, dtype=F32)
+        ws = _scan_workspace(B, L, di, n, 0, dev)
         dA_log = torch.zeros((di, n), device=dev, dtype=F32)
         dBC = torch.zeros((2, B, L, n), device=dev, dtype=F32)
         dxc = ddelta = None
@@ -413,7 +419,7 @@ class MambaBlockFn(torch.autograd.Function):
             du = torch.empty((B, L, di), device=dev, dtype=F32)
             dd = torch.empty((B, L, di), device=dev, dtype=F32)
             call("b2_selective_scan_bwd", xc.data_ptr(), delta3.data_ptr(), A.data_ptr(), Bm.data_ptr(), Cm.data_ptr(),
-                 dyd.data_ptr(), ws.data_ptr(), du.data_ptr(), dd.data_ptr(), dA_log.data_ptr(), dBC[0].data_ptr(),
+                 dyd.data_ptr(), ptr(ws), du.data_ptr(), dd.data_ptr(), dA_log.data_ptr(), dBC[0].data_ptr(),
                  dBC[1].data_ptr(), B, L, di, n, 0, rev, 1, st)
             if rev == 0:
                 dxc, ddelta = du, dd
