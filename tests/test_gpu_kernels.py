@@ -632,9 +632,13 @@ def test_selective_scan_backward_vs_oracle_autograd(ops, chunk, reverse):
         assert err(a.grad, b.grad) < 2e-3, k
 
 
-@pytest.mark.parametrize("B,L,D,N,chunk,reverse", [(3, 40, 64, 16, 16, False), (2, 33, 96, 8, None, True), (2, 20, 160, 32, None, False)])
+@pytest.mark.parametrize("B,L,D,N,chunk,reverse", [(3, 40, 64, 16, 16, False), (2, 33, 96, 8, None, True), (2, 20, 160, 32, None, False),
+                                                   (2, 37, 128, 4, None, False), (2, 70, 128, 8, 32, False), (1, 25, 16, 64, None, True),
+                                                   (2, 19, 64, 12, None, False), (1, 530, 64, 16, None, False), (2, 300, 64, 16, 256, False)])
 def test_selective_scan_backward_wide(ops, B, L, D, N, chunk, reverse):
-    """D % 32 == 0: the dB / dC contributions of a warp's 32 channels are summed with shuffles (one atomic per warp)."""
+    """Both backward kernels at every compiled state width: the on-chip one (N in {4, 8, 16, 32, 64}, D a multiple of 512 / N
+    channels, chunks of up to 512 steps, ragged last segment / last chunk) and the workspace one (padded N = 12, D = 96 with
+    N = 8, a 530-step scan without reset)."""
     g = torch.Generator().manual_seed(L + D)
     u = torch.randn(B, L, D, generator=g)
     delta = F.softplus(torch.randn(B, L, D, generator=g))

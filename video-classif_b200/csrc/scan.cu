@@ -509,111 +509,148 @@ selective_scan_bwd_ws_kernel(const float* __restrict__ u, const float* __restric
 
 
 // ---- BPTT with the states kept on chip -------------------------------------------------------------------------------
-// Same thread mapping as the workspace kernel (a channel's states spread over G = NP / 4 lanes, grid.y = chunks), but the
-// forward states never leave the SM.  Pass 1 walks the chunk forwards and keeps only the state ENTERING every kSeg-th step
-// in shared memory (16 B per lane and segment: 32 KB per block at 256-step chunks).  Pass 2 takes the segments last to
-// first: the segment's kSeg states are recomputed from its checkpoint into REGISTERS, then its steps are walked backwards.
+// Same lane mapping as the workspace kernel (a channel's states spread over G = NP / 4 lanes; a block = 128 / G channels of
+// one clip and one chunk), but the forward states never leave the SM and nothing inside the time loops touches global memory:
+//   * pass 1 walks the chunk forwards and keeps the state ENTERING every kSeg-th step in shared memory (16 B per lane and
+//     segment: 32 KB per block at 256-step chunks);
+//   * pass 2 takes the segments last to first: the segment's kSeg states are recomputed from its checkpoint into REGISTERS,
+//     then its steps are walked backwards;
+//   * the u / delta / dy / B / C rows of a segment arrive through a double-buffered cp.async ring one segment ahead (the
+//     time loops read shared memory only: four warps per scheduler cannot hide global latency on a serial chain);
+//   * d(u) / d(delta) leave as whole 128-byte rows once per segment; the dB / dC partials are summed over the warp's
+//     channels with exchange-and-halve shuffles (4 + 2 + 1 instead of 8 x 3), over the block's warps in shared memory, and
+//     leave as one vector reduction per 4 states and segment row.
 // HBM traffic is the algorithmic u / delta / dy / du / ddelta (+ the B, C rows); the 3.3 GB state workspace of the other
 // kernel (B 8, L 3136, D 2048, N 16: one write + two reads) is gone, at the price of a second evaluation of the forward.
-// Cross-lane sums use exchange-and-halve steps (each lane keeps half of the values and sends the other half): the eight
-// dB / dC partials of a step are summed over the warp's 8 channels with 4 + 2 + 1 shuffles and leave as ONE atomic per
-// lane; d(delta) / d(u) over the channel's lanes take one shuffle per level.
+// Needs N == NP (a compiled width), D % (128 / G) == 0, 16-byte aligned tensors; chunks of up to kBwdMaxChunk steps.
 constexpr int kSeg = 16;
 constexpr int kBwdMaxChunk = 512;          // 64 KB of checkpoints per block
+
+template <int NP>
+struct BwdSmem {
+  static constexpr int G = NP / 4;
+  static constexpr int CPB = 128 / G;                      // channels per block
+  static constexpr int kUd = 2 * 3 * kSeg * CPB;           // floats: [buffer][u | delta | dy][step][channel]
+  static constexpr int kBc = 2 * kSeg * 2 * NP;            // [buffer][step][B | C]
+  static constexpr int kOut = 2 * kSeg * CPB;              // [du | ddelta][step][channel]
+  static constexpr int kDbc = kSeg * 2 * NP;               // [step][dB | dC]
+  static constexpr int kFixedFloats = kUd + kBc + kOut + kDbc;
+  static int bytes(int steps) { return kFixedFloats * 4 + b2_ceil_div(steps, kSeg) * 128 * 16; }
+};
+
+__device__ __forceinline__ void red_add_v4(float* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 
 template <int NP>
 __global__ void __launch_bounds__(128, 4)
 selective_scan_bwd_kernel(const float* __restrict__ u, const float* __restrict__ delta, const float* __restrict__ A,
                           const float* __restrict__ Bm, const float* __restrict__ Cm, const float* __restrict__ dy,
                           float* __restrict__ du, float* __restrict__ ddelta, float* __restrict__ dA_out,
-                          float* __restrict__ dB, float* __restrict__ dC, int batch, int L, int D, int N, int chunk, int reverse,
-                          int a_is_log) {
-  constexpr int G = NP / 4;                // lanes per channel
+                          float* __restrict__ dB, float* __restrict__ dC, int L, int D, int chunk, int reverse, int a_is_log) {
+  using S = BwdSmem<NP>;
+  constexpr int G = S::G, CPB = S::CPB, N = NP;
   constexpr int CW = 32 / G;               // channels per warp
   constexpr int kLv = CW == 32 ? 5 : CW == 16 ? 4 : CW == 8 ? 3 : CW == 4 ? 2 : 1;
   constexpr int kT = kLv < 3 ? kLv : 3;    // exchange-and-halve levels of the 8-value dB / dC reduction
-  extern __shared__ float4 ck_s[];         // [segment][thread]: state entering the segment
+  extern __shared__ __align__(16) float smem_f[];
+  float* ud_s = smem_f;                    // [2][3][kSeg][CPB]
+  float* bc_s = ud_s + S::kUd;             // [2][kSeg][2 NP]
+  float* out_s = bc_s + S::kBc;            // [2][kSeg][CPB]
+  float* dbc_s = out_s + S::kOut;          // [kSeg][2 NP]
+  float4* ck_s = reinterpret_cast<float4*>(dbc_s + S::kDbc);   // [segment][thread]
   const int lane = threadIdx.x & 31;
-  const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long total = (long)batch * D * G;
-  const bool warp_reduce = (D % CW) == 0;  // the warp's channels share the batch index
-  const bool live = tid < total;
-  const long tc = live ? tid : total - 1;  // idle lanes of the last warp shadow a valid thread and contribute nothing
-  const int gq = (int)(tc % G);            // which 4 states
-  const long idx = tc / G;                 // (batch, channel)
-  const int d = (int)(idx % D);
-  const long b = idx / D;
-  const long row0 = b * L;
+  const int c = threadIdx.x / G;           // channel within the block
+  const int gq = threadIdx.x % G;          // which 4 states
   const int n0 = gq * 4;
+  const int d0 = blockIdx.x * CPB;
+  const long row0 = (long)blockIdx.z * L;
   const int t_begin = blockIdx.y * chunk;
   const int t_end = min(L, t_begin + chunk);
-  const bool vec4 = (N & 3) == 0 && (((uintptr_t)Bm | (uintptr_t)Cm) & 15) == 0;
+  const int nseg = (t_end - t_begin + kSeg - 1) / kSeg;
   float a2[4];
-  bool okn[4];
-#pragma unroll
-  for (int n = 0; n < 4; ++n) {
-    okn[n] = n0 + n < N;
-    a2[n] = okn[n] ? A[(long)d * N + n0 + n] * kLog2e : 0.f;
+  {
+    const float4 av = __ldg(reinterpret_cast<const float4*>(A + (long)(d0 + c) * N + n0));
+    a2[0] = av.x * kLog2e; a2[1] = av.y * kLog2e; a2[2] = av.z * kLog2e; a2[3] = av.w * kLog2e;
   }
-  auto ld4 = [&](const float* p, float (&o)[4]) {      // 4 states of a [.., N] row
-    if (vec4) {
-      const float4 v = okn[0] ? __ldg(reinterpret_cast<const float4*>(p)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
-    } else {
-#pragma unroll
-      for (int n = 0; n < 4; ++n) o[n] = okn[n] ? __ldg(p + n) : 0.f;
+  // one segment's rows -> buffer `buf` (cp.async, one commit group)
+  auto load_seg = [&](int buf, int seg, bool with_dy) {
+    const int ts0 = t_begin + seg * kSeg;
+    const int rows = min(kSeg, t_end - ts0);
+    constexpr int kPer = CPB / 4;                                 // 16-byte pieces per row
+    const int nt = with_dy ? 3 : 2;
+    for (int i = threadIdx.x; i < nt * rows * kPer; i += 128) {
+      const int which = i / (rows * kPer), r = i - which * rows * kPer;
+      const int k = r / kPer, j = r - k * kPer;
+      const int t = ts0 + k, ts = reverse ? L - 1 - t : t;
+      const float* src = (which == 0 ? u : which == 1 ? delta : dy) + (row0 + ts) * D + d0 + 4 * j;
+      cp_async16(ud_s + ((buf * 3 + which) * kSeg + k) * CPB + 4 * j, src);
     }
+    constexpr int kQ = NP / 4;
+    for (int i = threadIdx.x; i < rows * 2 * kQ; i += 128) {
+      const int k = i / (2 * kQ), j = i - k * 2 * kQ;
+      const long r = (row0 + ts0 + k) * N;
+      cp_async16(bc_s + (buf * kSeg + k) * 2 * NP + 4 * j, j < kQ ? Bm + r + 4 * j : Cm + r + 4 * (j - kQ));
+    }
+    cp_async_commit();
   };
-  auto step_fwd = [&](int t, float (&x)[4]) {          // x_t from x_{t-1} (same arithmetic as the forward kernel)
-    const int ts = reverse ? L - 1 - t : t;
-    const float dl = __ldg(delta + (row0 + ts) * D + d);
-    const float duv = dl * __ldg(u + (row0 + ts) * D + d);
-    float bb[4];
-    ld4(Bm + (row0 + t) * N + n0, bb);
-#pragma unroll
-    for (int n = 0; n < 4; ++n) x[n] = fmaf(ex2_approx(dl * a2[n]), x[n], duv * bb[n]);
+  auto step_fwd = [&](int buf, int k, float (&x)[4]) {          // x_t from x_{t-1} (same arithmetic as the forward kernel)
+    const float dl = ud_s[((buf * 3 + 1) * kSeg + k) * CPB + c];
+    const float duv = dl * ud_s[((buf * 3 + 0) * kSeg + k) * CPB + c];
+    const float4 b4 = *reinterpret_cast<const float4*>(bc_s + (buf * kSeg + k) * 2 * NP + n0);
+    x[0] = fmaf(ex2_approx(dl * a2[0]), x[0], duv * b4.x);
+    x[1] = fmaf(ex2_approx(dl * a2[1]), x[1], duv * b4.y);
+    x[2] = fmaf(ex2_approx(dl * a2[2]), x[2], duv * b4.z);
+    x[3] = fmaf(ex2_approx(dl * a2[3]), x[3], duv * b4.w);
   };
-  // ---- pass 1: checkpoints
+  for (int i = threadIdx.x; i < S::kDbc; i += 128) dbc_s[i] = 0.f;
+  // ---- pass 1: checkpoints (the state entering segment s); the last segment's end state is never needed
   {
     float x[4] = {0.f, 0.f, 0.f, 0.f};
-    int seg = 0;
-    for (int t0 = t_begin; t0 < t_end; t0 += kSeg, ++seg) {
-      ck_s[seg * 128 + threadIdx.x] = make_float4(x[0], x[1], x[2], x[3]);
-      if (t0 + kSeg < t_end) {                          // the last segment's end state is never needed
-#pragma unroll 4
-        for (int k = 0; k < kSeg; ++k) step_fwd(t0 + k, x);
-      }
+    ck_s[threadIdx.x] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (nseg > 1) load_seg(0, 0, false);
+    for (int seg = 0; seg + 1 < nseg; ++seg) {
+      const int buf = seg & 1;
+      cp_async_wait<0>();
+      __syncthreads();                                            // rows of `seg` visible; readers of the other buffer are done
+      if (seg + 2 < nseg) load_seg(buf ^ 1, seg + 1, false);
+#pragma unroll
+      for (int k = 0; k < kSeg; ++k) step_fwd(buf, k, x);         // a segment that is followed by another one is complete
+      ck_s[(seg + 1) * 128 + threadIdx.x] = make_float4(x[0], x[1], x[2], x[3]);
     }
   }
+  __syncthreads();
   // ---- pass 2: segments last to first
-  float g[4], dAacc[4];                                 // g: gradient flowing into x_t from step t+1
+  float g[4], dAacc[4];                                           // g: gradient flowing into x_t from step t+1
 #pragma unroll
   for (int n = 0; n < 4; ++n) g[n] = dAacc[n] = 0.f;
-  const int nseg = (t_end - t_begin + kSeg - 1) / kSeg;
+  load_seg((nseg - 1) & 1, nseg - 1, true);
   for (int seg = nseg - 1; seg >= 0; --seg) {
+    const int buf = seg & 1;
     const int ts0 = t_begin + seg * kSeg;
+    cp_async_wait<0>();
+    __syncthreads();                                              // rows visible; the previous segment's flush is complete
+    if (seg > 0) load_seg(buf ^ 1, seg - 1, true);
     const float4 c4 = ck_s[seg * 128 + threadIdx.x];
     float xs[kSeg][4];
     {
       float x[4] = {c4.x, c4.y, c4.z, c4.w};
 #pragma unroll
       for (int k = 0; k < kSeg; ++k) {
-        if (ts0 + k < t_end) step_fwd(ts0 + k, x);
+        if (ts0 + k < t_end) step_fwd(buf, k, x);
 #pragma unroll
         for (int n = 0; n < 4; ++n) xs[k][n] = x[n];
       }
     }
 #pragma unroll
     for (int k = kSeg - 1; k >= 0; --k) {
-      const int t = ts0 + k;
-      if (t < t_end) {
-        const int ts = reverse ? L - 1 - t : t;
-        const float dl = __ldg(delta + (row0 + ts) * D + d);
-        const float uv = __ldg(u + (row0 + ts) * D + d);
-        const float dyv = __ldg(dy + (row0 + ts) * D + d);
-        float bt[4], ct[4];
-        ld4(Bm + (row0 + t) * N + n0, bt);
-        ld4(Cm + (row0 + t) * N + n0, ct);
+      if (ts0 + k < t_end) {
+        const float uv = ud_s[((buf * 3 + 0) * kSeg + k) * CPB + c];
+        const float dl = ud_s[((buf * 3 + 1) * kSeg + k) * CPB + c];
+        const float dyv = ud_s[((buf * 3 + 2) * kSeg + k) * CPB + c];
+        const float4 b4 = *reinterpret_cast<const float4*>(bc_s + (buf * kSeg + k) * 2 * NP + n0);
+        const float4 cc4 = *reinterpret_cast<const float4*>(bc_s + (buf * kSeg + k) * 2 * NP + NP + n0);
+        const float bt[4] = {b4.x, b4.y, b4.z, b4.w}, ct[4] = {cc4.x, cc4.y, cc4.z, cc4.w};
         const float dlu = dl * uv;
         float s1 = 0.f, s2 = 0.f, v[8];
 #pragma unroll
@@ -625,85 +662,89 @@ selective_scan_bwd_kernel(const float* __restrict__ u, const float* __restrict__
           s1 = fmaf(e, a2[n], s1);                      // d(delta) = ln2 * s1 + u * s2
           s2 = fmaf(dx, bt[n], s2);                     // d(u)     = delta * s2
           dAacc[n] = fmaf(e, dl, dAacc[n]);
-          v[n] = live ? dx * dlu : 0.f;                 // dB
-          v[4 + n] = live ? dyv * xs[k][n] : 0.f;       // dC
+          v[n] = dx * dlu;                              // dB
+          v[4 + n] = dyv * xs[k][n];                    // dC
           g[n] = at * dx;
         }
-        float ddl = fmaf(s1, 0.6931471805599453f, uv * s2);
-        float duv = dl * s2;
+        const float ddl = fmaf(s1, 0.6931471805599453f, uv * s2);
+        const float duv = dl * s2;
         // d(delta), d(u): sum over the channel's G lanes; afterwards lanes with (gq & G/2) == 0 hold d(delta), the others d(u)
         if (G > 1) {
           const bool up = (gq & (G / 2)) != 0;
-          const float send = up ? ddl : duv;
           float keep = up ? duv : ddl;
-          keep += __shfl_xor_sync(0xffffffffu, send, G / 2);
+          keep += __shfl_xor_sync(0xffffffffu, up ? ddl : duv, G / 2);
 #pragma unroll
           for (int off = G / 4; off >= 1; off >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, off);
-          if (live && (gq & (G / 2 - 1)) == 0) {
-            if (up) du[(row0 + ts) * D + d] = keep;
-            else ddelta[(row0 + ts) * D + d] = keep;
-          }
-        } else if (live) {
-          du[(row0 + ts) * D + d] = duv;
-          ddelta[(row0 + ts) * D + d] = ddl;
+          if ((gq & (G / 2 - 1)) == 0) out_s[((up ? 0 : 1) * kSeg + k) * CPB + c] = keep;
+        } else {
+          out_s[k * CPB + c] = duv;
+          out_s[(kSeg + k) * CPB + c] = ddl;
         }
-        // dB, dC: sum over the warp's channels
-        if (warp_reduce) {
-          if (kT >= 1) {
-            const bool up = (lane & 16) != 0;
+        // dB, dC: sum over the warp's channels, then over the block's warps in shared memory
+        if (kT >= 1) {
+          const bool up = (lane & 16) != 0;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float send = up ? v[i] : v[i + 4];
-              const float keep = up ? v[i + 4] : v[i];
-              v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-            }
+          for (int i = 0; i < 4; ++i) {
+            const float send = up ? v[i] : v[i + 4];
+            const float keep = up ? v[i + 4] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
           }
-          if (kT >= 2) {
-            const bool up = (lane & 8) != 0;
+        }
+        if (kT >= 2) {
+          const bool up = (lane & 8) != 0;
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const float send = up ? v[i] : v[i + 2];
-              const float keep = up ? v[i + 2] : v[i];
-              v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-            }
+          for (int i = 0; i < 2; ++i) {
+            const float send = up ? v[i] : v[i + 2];
+            const float keep = up ? v[i + 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
           }
-          if (kT >= 3) {
-            const bool up = (lane & 4) != 0;
-            const float send = up ? v[0] : v[1];
-            const float keep = up ? v[1] : v[0];
-            v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+        if (kT >= 3) {
+          const bool up = (lane & 4) != 0;
+          const float send = up ? v[0] : v[1];
+          const float keep = up ? v[1] : v[0];
+          v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
 #pragma unroll
-            for (int off = 2; off >= G; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
-          }
-          // this lane now holds 8 >> kT complete sums: original value indices base .. base + (8 >> kT) - 1
-          constexpr int kKeep = 8 >> kT;
-          const int base = (kT >= 1 ? ((lane >> 4) & 1) * 4 : 0) + (kT >= 2 ? ((lane >> 3) & 1) * 2 : 0) + (kT >= 3 ? ((lane >> 2) & 1) : 0);
-          const bool writer = kT < 3 || (lane & 3 & ~(G - 1)) == 0;    // after the plain levels every lane of the group holds the sum
+          for (int off = 2; off >= G; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+        }
+        // this lane now holds 8 >> kT complete warp sums: original value indices base .. base + (8 >> kT) - 1
+        constexpr int kKeep = 8 >> kT;
+        const int base = (kT >= 1 ? ((lane >> 4) & 1) * 4 : 0) + (kT >= 2 ? ((lane >> 3) & 1) * 2 : 0) + (kT >= 3 ? ((lane >> 2) & 1) : 0);
+        const bool writer = kT < 3 || (lane & 3 & ~(G - 1)) == 0;    // after the plain levels every lane of the group holds the sum
+        if (writer) {
 #pragma unroll
           for (int i = 0; i < kKeep; ++i) {
             const int vi = base + i;                   // 0..3: dB state vi, 4..7: dC state vi - 4
-            const int n = vi & 3;
-            if (writer && n0 + n < N) atomicAdd((vi < 4 ? dB : dC) + (row0 + t) * N + n0 + n, v[i]);
-          }
-        } else if (live) {
-#pragma unroll
-          for (int n = 0; n < 4; ++n) {
-            if (okn[n]) {
-              atomicAdd(dB + (row0 + t) * N + n0 + n, v[n]);
-              atomicAdd(dC + (row0 + t) * N + n0 + n, v[4 + n]);
-            }
+            atomicAdd(dbc_s + k * 2 * NP + (vi < 4 ? 0 : NP) + n0 + (vi & 3), v[i]);
           }
         }
       }
     }
-  }
-  if (live) {
-#pragma unroll
-    for (int n = 0; n < 4; ++n)
-      if (okn[n]) {
-        const float a = a2[n] * 0.6931471805599453f;
-        atomicAdd(dA_out + (long)d * N + n0 + n, a_is_log ? dAacc[n] * a : dAacc[n]);
+    __syncthreads();                                              // the segment's outputs are complete in shared memory
+    {
+      const int rows = min(kSeg, t_end - ts0);
+      constexpr int kPer = CPB / 4;
+      for (int i = threadIdx.x; i < 2 * rows * kPer; i += 128) {
+        const int which = i / (rows * kPer), r = i - which * rows * kPer;
+        const int k = r / kPer, j = r - k * kPer;
+        const int t = ts0 + k, ts = reverse ? L - 1 - t : t;
+        const float4 val = *reinterpret_cast<const float4*>(out_s + (which * kSeg + k) * CPB + 4 * j);
+        *reinterpret_cast<float4*>((which == 0 ? du : ddelta) + (row0 + ts) * D + d0 + 4 * j) = val;
       }
+      constexpr int kQ = NP / 4;
+      for (int i = threadIdx.x; i < rows * 2 * kQ; i += 128) {
+        const int k = i / (2 * kQ), j = i - k * 2 * kQ;
+        float4* sp = reinterpret_cast<float4*>(dbc_s + k * 2 * NP + 4 * j);
+        const float4 val = *sp;
+        *sp = make_float4(0.f, 0.f, 0.f, 0.f);
+        red_add_v4((j < kQ ? dB + (row0 + ts0 + k) * N + 4 * j : dC + (row0 + ts0 + k) * N + 4 * (j - kQ)), val);
+      }
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < 4; ++n) {
+    const float a = a2[n] * 0.6931471805599453f;
+    atomicAdd(dA_out + (long)(d0 + c) * N + n0 + n, a_is_log ? dAacc[n] * a : dAacc[n]);
   }
 }
 
@@ -749,11 +790,19 @@ B2_API int b2_mul_silu_bwd_f32(const float* dy, const float* a, const float* res
 // du / ddelta overwritten; dA [D,N], dB / dC [batch,L,N] ACCUMULATED (caller zeroes).
 // chunk_reset > 0: the state restarts from zero every chunk_reset steps (videomamba.py:242-284), chunks run in parallel;
 // a_is_log = 1: dA is the gradient of A_log where A = -exp(A_log) (medsos models.py:94), 0: the gradient of A itself.
-// Scans (or chunks) of up to 512 steps keep their states on chip and need no workspace (b2_scan_bwd_workspace_floats = 0,
-// `workspace` may be NULL); longer ones recompute them into workspace[batch * D * L * b2_scan_padded_states(N)].
-B2_API long b2_scan_bwd_workspace_floats(int batch, int L, int D, int N, int chunk_reset) {
+// Scans (or chunks) of up to 512 steps with N a compiled width (4, 8, 16, 32, 64) and D a multiple of 512 / N channels keep
+// their states on chip and need no workspace (b2_scan_bwd_workspace_floats = 0, `workspace` may be NULL); every other shape
+// recomputes them into workspace[batch * D * L * b2_scan_padded_states(N)].
+namespace {
+bool scan_bwd_on_chip_shape(int batch, int L, int D, int N, int chunk_reset) {
   const int chunk = chunk_reset > 0 && chunk_reset < L ? chunk_reset : L;
-  if (chunk <= kBwdMaxChunk) return 0;
+  const int NP = b2_scan_padded_states(N);
+  return chunk <= kBwdMaxChunk && N == NP && D % (512 / NP) == 0 && batch <= 65535;
+}
+}  // namespace
+
+B2_API long b2_scan_bwd_workspace_floats(int batch, int L, int D, int N, int chunk_reset) {
+  if (scan_bwd_on_chip_shape(batch, L, D, N, chunk_reset)) return 0;
   return (long)batch * D * L * b2_scan_padded_states(N);
 }
 
@@ -769,27 +818,25 @@ B2_API int b2_selective_scan_bwd(const float* u, const float* delta, const float
   const int chunks = b2_ceil_div(L, chunk);
   B2_ARG_CHECK(chunks <= 65535, "b2_selective_scan_bwd: too many chunks");
   B2_ARG_CHECK(!(reverse && chunks > 1), "b2_selective_scan_bwd: the reference has no chunk-reset scan in the reverse direction");
-  const bool on_chip = b2_scan_bwd_workspace_floats(batch, L, D, N, chunk_reset) == 0;
-  B2_ARG_CHECK(on_chip || workspace, "b2_selective_scan_bwd: a %d-step scan needs the state workspace", chunk < L ? chunk : L);
-  const long threads = (long)batch * D * (NP / 4);      // one lane per 4 states
-  const dim3 grid((unsigned)((threads + 127) / 128), (unsigned)chunks);
+  const uintptr_t align = (uintptr_t)u | (uintptr_t)delta | (uintptr_t)A | (uintptr_t)Bm | (uintptr_t)Cm | (uintptr_t)dy |
+                          (uintptr_t)du | (uintptr_t)ddelta | (uintptr_t)dB | (uintptr_t)dC;
+  const bool on_chip = scan_bwd_on_chip_shape(batch, L, D, N, chunk_reset) && (align & 15) == 0;
+  B2_ARG_CHECK(on_chip || workspace, "b2_selective_scan_bwd: this shape / alignment needs the state workspace");
   cudaStream_t st = (cudaStream_t)stream;
   if (on_chip) {
     const int steps = chunk < L ? chunk : L;
-    const int smem = b2_ceil_div(steps, kSeg) * 128 * (int)sizeof(float4);
-    static B2PerDeviceOnce attr;
-    if (attr.needed()) {
-      const int max_smem = kBwdMaxChunk / kSeg * 128 * (int)sizeof(float4);
-      B2_CUDA_CHECK(cudaFuncSetAttribute(selective_scan_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-      B2_CUDA_CHECK(cudaFuncSetAttribute(selective_scan_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-      B2_CUDA_CHECK(cudaFuncSetAttribute(selective_scan_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-      B2_CUDA_CHECK(cudaFuncSetAttribute(selective_scan_bwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-      B2_CUDA_CHECK(cudaFuncSetAttribute(selective_scan_bwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-      attr.mark();
-    }
-#define B2_SCAN_BWD(NN)                                                                                       \
-  selective_scan_bwd_kernel<NN><<<grid, 128, smem, st>>>(u, delta, A, Bm, Cm, dy, du, ddelta, dA, dB, dC, batch, L, D, N, \
-                                                         chunk, reverse, a_is_log)
+    const dim3 cgrid((unsigned)(D / (512 / NP)), (unsigned)chunks, (unsigned)batch);
+#define B2_SCAN_BWD(NN)                                                                                                   \
+  {                                                                                                                       \
+    static B2PerDeviceOnce attr;                                                                                          \
+    if (attr.needed()) {                                                                                                  \
+      B2_CUDA_CHECK(cudaFuncSetAttribute(selective_scan_bwd_kernel<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                         BwdSmem<NN>::bytes(kBwdMaxChunk)));                                              \
+      attr.mark();                                                                                                        \
+    }                                                                                                                     \
+    selective_scan_bwd_kernel<NN><<<cgrid, 128, BwdSmem<NN>::bytes(steps), st>>>(u, delta, A, Bm, Cm, dy, du, ddelta, dA, \
+                                                                                 dB, dC, L, D, chunk, reverse, a_is_log); \
+  }
     switch (NP) {
       case 4: B2_SCAN_BWD(4); break;
       case 8: B2_SCAN_BWD(8); break;
@@ -801,6 +848,8 @@ B2_API int b2_selective_scan_bwd(const float* u, const float* delta, const float
     B2_LAUNCH_CHECK("selective_scan_bwd_kernel");
     return 0;
   }
+  const long threads = (long)batch * D * (NP / 4);      // one lane per 4 states
+  const dim3 grid((unsigned)((threads + 127) / 128), (unsigned)chunks);
 #define B2_SCAN_BWD(NN)                                                                                             \
   selective_scan_bwd_ws_kernel<NN><<<grid, 128, 0, st>>>(u, delta, A, Bm, Cm, dy, workspace, du, ddelta, dA, dB, dC, \
                                                          batch, L, D, N, chunk, reverse, a_is_log)
