@@ -533,12 +533,16 @@ def test_bn_bwd_ld(C, ldx, train, relu, acc):
     assert _rel(s12[0], br.grad) < 1e-3 and _rel(s12[1], gr.grad) < 5e-3
 
 
-@pytest.mark.parametrize("C,H,W,stride,act", [(32, 9, 9, 1, 2), (96, 12, 10, 2, 2), (144, 7, 7, 1, 1), (960, 4, 4, 1, 2), (24, 5, 6, 2, 0)])
-def test_dwconv3x3_bn(C, H, W, stride, act):
-    """Depthwise 3x3 with the previous BatchNorm + ReLU / ReLU6 on load (padding stays zero), output statistics."""
+@pytest.mark.parametrize("C,H,W,stride,act,N", [(32, 9, 9, 1, 2, 3), (96, 12, 10, 2, 2, 3), (144, 7, 7, 1, 1, 3), (960, 4, 4, 1, 2, 3),
+                                                 (24, 5, 6, 2, 0, 3), (96, 56, 56, 2, 2, 3), (144, 28, 28, 1, 2, 2), (32, 56, 56, 1, 0, 2),
+                                                 (192, 14, 14, 1, 2, 5), (384, 7, 7, 1, 2, 37), (576, 7, 7, 2, 1, 37), (960, 4, 4, 1, 2, 70),
+                                                 (96, 13, 11, 2, 1, 4), (48, 30, 17, 1, 0, 3), (144, 28, 28, 2, 2, 3), (32, 112, 112, 1, 2, 1)])
+def test_dwconv3x3_bn(C, H, W, stride, act, N):
+    """Depthwise 3x3 with the previous BatchNorm + ReLU / ReLU6 on load (padding stays zero), output statistics, at the
+    MobileNetV2 layer shapes of a 112x112 frame (32 @56, 96 @56 s2, 144 @28 s1 / s2, 192 @14, 384 / 576 @7, 960 @4), odd
+    sizes, a channel count that is not a multiple of 16 (24) and batch sizes that leave ragged block ranges."""
     from video_classif_b200._lib import call, stream_ptr
     torch.manual_seed(C + H)
-    N = 3
     x = torch.randn(N, H, W, C, device=DEV).to(torch.bfloat16)
     sc, sh = torch.rand(C, device=DEV) + 0.5, torch.randn(C, device=DEV)
     w = torch.randn(C, 1, 3, 3, device=DEV) * 0.3
