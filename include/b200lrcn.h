@@ -316,6 +316,9 @@ int b2_selective_scan_bwd(const float* u, const float* delta, const float* A, co
  *   (= dgamma) ACCUMULATED; dy = gamma*invstd*(dz - s1/count - xhat*s2/count) (train) or gamma*invstd*dz (eval).
  * b2_dilate2_nhwc_bf16: zero-dilation of dy for the data gradient of stride-2 convs (z pre-zeroed).
  * b2_avgpool_bwd_nhwc: dz[n,hw,c] = dfeat[n,c] / HW.   b2_maxpool_relu_bwd_nhwc: stem tail backward (dbn fp32 pre-zeroed). */
+/* b2_conv_weight_layouts: torch conv weight w [Cout,Cin,R,S] fp32 -> wk [Cout,R,S,Cin] bf16 (forward / weight-gradient layout)
+ * and wt [Cin,R,S,Cout] bf16 with flipped taps (data-gradient layout) in one pass; either output may be NULL. */
+int b2_conv_weight_layouts(const float* w, void* wk, void* wt, int Cout, int Cin, int R, int S, void* stream);
 int b2_conv2d_wgrad_nhwc_bf16(const void* x, int Nimg, int H, int W, int C, const void* dy, int Cout, int R, int S, int stride,
                               int pad, float* dw, void* stream);
 int b2_bn_bwd_nhwc_bf16(const void* dz, void* dzm, const void* z, const void* y, void* dy, const float* gamma, const float* sum,

@@ -4,7 +4,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from conftest import ROOT  # noqa: F401
+from conftest import ROOT, attempts  # noqa: F401
 from oracle import lrcn_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -172,6 +172,7 @@ def _teacher_forced_reference(net, x, rec, G, start):
 @pytest.mark.parametrize("arch,first,frames,size", [("resnet18", "conv1", 8, 64), ("resnet18", "layer3", 8, 64),
                                                     ("resnet50", "conv1", 8, 64), ("resnet50", "layer2.1.bn2", 6, 96),
                                                     ("resnet34", "layer4", 4, 64)])
+@attempts(3)
 def test_finetune_gradients_whole_network(arch, first, frames, size):
     """Whole ResNets, parameters trainable from `first` on in named_parameters() order (freeze_until_layer semantics,
     lrcn.py:275-283; 'conv1' = full fine-tune): the frozen prefix runs on the fused kernels, the rest through the autograd
@@ -281,6 +282,7 @@ def _densenet_teacher_forced(net, y0, saved, G):
     return feat
 
 
+@attempts(3)
 def test_densenet_finetune_gradients_teacher_forced():
     """Trainable DenseNet (growth 32, blocks (2,2,2,2): every layer type): features and the gradient of EVERY parameter
     behind the stem, plus the gradient handed to the stem, vs the teacher-forced torch reference."""

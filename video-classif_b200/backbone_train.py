@@ -19,7 +19,7 @@ import torch
 
 from . import _lib
 from ._lib import call, ptr, stream_ptr
-from .ops import BF16, F32, cast_bf16, conv2d_nhwc, gemm_tn, scale_shift_apply
+from .ops import BF16, F32, cast_bf16, conv2d_bn_nhwc, conv2d_nhwc, gemm_tn, scale_shift_apply
 
 STEM_KP = 168      # 3 channels x 7 rows x 8 taps (one zero tap): the patch-matrix stem of backbone.py
 
@@ -72,20 +72,39 @@ def conv_wgrad(x, dy, R, S, stride, pad):
     return dw
 
 
-def conv_dgrad(dy, w, in_hw, stride, pad):
+def weight_layouts(w, want_dgrad=True):
+    """w [Cout,Cin,R,S] fp32 parameter -> (wk [Cout,R,S,Cin], wt [Cin,R,S,Cout] with flipped taps or None), bf16, one launch."""
+    Cout, Cin, R, S = w.shape
+    wd = w.detach()
+    if not wd.is_contiguous():
+        wd = wd.contiguous()
+    wk = torch.empty((Cout, R, S, Cin), device=w.device, dtype=BF16)
+    wt = torch.empty((Cin, R, S, Cout), device=w.device, dtype=BF16) if want_dgrad else None
+    call("b2_conv_weight_layouts", wd.data_ptr(), wk.data_ptr(), ptr(wt), Cout, Cin, R, S, stream_ptr())
+    return wk, wt
+
+
+def conv_dgrad(dy, w, in_hw, stride, pad, wt=None, add=None):
     """dy [N,P,Q,Cout] bf16, w [Cout,Cin,R,S] fp32 parameter -> dx [N,H,W,Cin] bf16: the forward conv kernels on the
-    flipped, transposed filter (stride 2: over the zero-dilated dy)."""
+    flipped, transposed filter (stride 2: over the zero-dilated dy).  wt: that filter if the caller already has it;
+    add [N,H,W,Cin] bf16: a second gradient of the same tensor (the shortcut's), added in the GEMM epilogue."""
     Cout, Cin, R, S = w.shape
     N, P, Q, _ = dy.shape
     H, W = in_hw
-    wt = w.detach().flip(2, 3).permute(1, 2, 3, 0).contiguous().to(BF16)          # [Cin, R, S, Cout]
+    if wt is None:
+        wt = weight_layouts(w)[1]                                                   # [Cin, R, S, Cout]
     if stride == 1:
         src = dy
     else:
         assert stride == 2, "ResNet convolutions have stride 1 or 2"
         src = torch.zeros((N, H, W, Cout), device=dy.device, dtype=BF16)
         call("b2_dilate2_nhwc_bf16", dy.data_ptr(), src.data_ptr(), N, P, Q, H, W, Cout, stream_ptr())
-    dx = conv2d_nhwc(src, wt, 1, R - 1 - pad)
+    if add is not None and Cin % 32 == 0 and Cin >= 64:
+        dx = conv2d_bn_nhwc(src, wt, 1, R - 1 - pad, res=add.contiguous(), relu=False)   # dgrad + add in the epilogue
+    else:
+        dx = conv2d_nhwc(src, wt, 1, R - 1 - pad)
+        if add is not None:
+            dx += add
     assert dx.shape[1:3] == (H, W), (dx.shape, H, W)
     return dx
 
@@ -94,10 +113,12 @@ class ConvBnFn(torch.autograd.Function):
     """z = act(bn(conv(x, w)) [+ res]) over NHWC bf16; bn in train mode (batch statistics, running-stat update) or eval."""
 
     @staticmethod
-    def forward(ctx, x, w, gamma, beta, res, bn, stride, pad, relu, train):
+    def forward(ctx, x, w, gamma, beta, res, bn, stride, pad, relu, train, carry=False):
+        """carry=True also returns x itself as a second output: the block hands THAT to its shortcut branch, so the
+        shortcut's gradient arrives at this node (not at an autograd add) and is summed in the data-gradient GEMM's epilogue."""
         Cout, Cin, R, S = w.shape
         x = x.contiguous()
-        wk = w.detach().permute(0, 2, 3, 1).contiguous().to(BF16)
+        wk, wt = weight_layouts(w, want_dgrad=x.requires_grad)
         stat = torch.zeros(4 * Cout, device=x.device, dtype=F32)         # sum | sumsq | scale | shift
         y = conv2d_nhwc(x, wk, stride, pad, stats=(stat[:Cout], stat[Cout:2 * Cout]) if train else None)
         count = y.numel() // Cout
@@ -106,13 +127,15 @@ class ConvBnFn(torch.autograd.Function):
         scale_shift_apply(y, stat[2 * Cout:3 * Cout], stat[3 * Cout:], res=res, relu=relu, out=z)
         if train and bn.num_batches_tracked is not None:
             bn.num_batches_tracked += 1
-        ctx.save_for_backward(x, w, y, z if relu else None, stat)
+        ctx.save_for_backward(x, w, y, z if relu else None, stat, wt)
         ctx.bn, ctx.geom, ctx.train, ctx.count, ctx.has_res = bn, (stride, pad), train, count, res is not None
+        if carry:
+            return z, x.view_as(x)
         return z
 
     @staticmethod
-    def backward(ctx, dz):
-        x, w, y, z, stat = ctx.saved_tensors
+    def backward(ctx, dz, dcarry=None):
+        x, w, y, z, stat, wt = ctx.saved_tensors
         stride, pad = ctx.geom
         Cout, Cin, R, S = w.shape
         dz = dz.contiguous()
@@ -122,9 +145,9 @@ class ConvBnFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dw = conv_wgrad(x, dy, R, S, stride, pad).permute(0, 3, 1, 2)
         if ctx.needs_input_grad[0]:
-            dx = conv_dgrad(dy, w, x.shape[1:3], stride, pad)
+            dx = conv_dgrad(dy, w, x.shape[1:3], stride, pad, wt=wt, add=dcarry)
         return (dx, dw, dgamma if ctx.needs_input_grad[2] else None, dbeta if ctx.needs_input_grad[3] else None,
-                dzm if want_res else None, None, None, None, None, None)
+                dzm if want_res else None, None, None, None, None, None, None)
 
 
 class StemFn(torch.autograd.Function):
@@ -199,23 +222,26 @@ class AvgPoolFn(torch.autograd.Function):
 _record = None      # tests: a list that collects every node's output activation in execution order
 
 
-def _conv_bn(x, conv, bn, relu, train, res=None):
+def _conv_bn(x, conv, bn, relu, train, res=None, carry=False, record=True):
     stride = conv.stride[0]
     pad = conv.padding[0]
-    z = ConvBnFn.apply(x, conv.weight, bn.weight, bn.bias, res, bn, stride, pad, relu, train)
-    if _record is not None:
-        _record.append(z)
-    return z
+    out = ConvBnFn.apply(x, conv.weight, bn.weight, bn.bias, res, bn, stride, pad, relu, train, carry)
+    if record and _record is not None:
+        _record.append(out[0] if carry else out)
+    return out
 
 
 def block_forward(y, blk, train):
-    """One torchvision BasicBlock / Bottleneck (v1.5: the stride sits on the 3x3 conv) on ConvBnFn nodes."""
-    short = y if blk.downsample is None else _conv_bn(y, blk.downsample[0], blk.downsample[1], False, train)
+    """One torchvision BasicBlock / Bottleneck (v1.5: the stride sits on the 3x3 conv) on ConvBnFn nodes.  The block input
+    feeds conv1 AND the shortcut: conv1's node hands the input on (carry), the shortcut branch hangs off that copy, and the two
+    gradients of the block input meet inside conv1's data-gradient GEMM (epilogue add) instead of in a separate add pass."""
+    o, y2 = _conv_bn(y, blk.conv1, blk.bn1, True, train, carry=True, record=False)
+    short = y2 if blk.downsample is None else _conv_bn(y2, blk.downsample[0], blk.downsample[1], False, train)
+    if _record is not None:             # (recorded in module order: down-sample branch, conv1, conv2, conv3)
+        _record.append(o)
     if hasattr(blk, "conv3"):
-        o = _conv_bn(y, blk.conv1, blk.bn1, True, train)
         o = _conv_bn(o, blk.conv2, blk.bn2, True, train)
         return _conv_bn(o, blk.conv3, blk.bn3, True, train, res=short)
-    o = _conv_bn(y, blk.conv1, blk.bn1, True, train)
     return _conv_bn(o, blk.conv2, blk.bn2, True, train, res=short)
 
 

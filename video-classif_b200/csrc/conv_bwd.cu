@@ -379,6 +379,27 @@ dilate2_kernel(const bf16* __restrict__ dy, bf16* __restrict__ z, int N, int P, 
   }
 }
 
+// Both kernel layouts of one torch conv weight w [Cout, Cin, R, S] fp32 in a single pass:
+//   wk [Cout, R, S, Cin]        bf16  the forward (and weight-gradient) layout: K index = (r S + s) Cin + ci
+//   wt [Cin, R, S, Cout]        bf16  the data-gradient layout: flipped taps, channels swapped (wt[ci][r][s][co] = w[co][ci][R-1-r][S-1-s])
+// (replaces permute / flip / contiguous / cast chains of ~5 ATen kernels per convolution and step)
+__global__ void __launch_bounds__(256)
+conv_weight_layouts_kernel(const float* __restrict__ w, bf16* __restrict__ wk, bf16* __restrict__ wt, int Cout, int Cin, int R,
+                           int S) {
+  const long total = (long)Cout * Cin * R * S;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int s = (int)(i % S);
+    long t = i / S;
+    const int r = (int)(t % R);
+    t /= R;
+    const int ci = (int)(t % Cin);
+    const long co = t / Cin;
+    const bf16 v = __float2bfloat16(w[i]);
+    if (wk != nullptr) wk[((co * R + r) * S + s) * Cin + ci] = v;
+    if (wt != nullptr) wt[(((long)ci * R + (R - 1 - r)) * S + (S - 1 - s)) * Cout + co] = v;
+  }
+}
+
 // dz[n, hw, c] = dfeat[n, c] / HW  (backward of the global average pool; fp32 -> bf16)
 __global__ void __launch_bounds__(256)
 avgpool_bwd_kernel(const float* __restrict__ dfeat, bf16* __restrict__ dz, long N, int HW, int C) {
@@ -612,6 +633,15 @@ B2_API int b2_dilate2_nhwc_bf16(const void* dy, void* z, int N, int P, int Q, in
   dilate2_kernel<<<ew_blocks((long)N * P * Q * (C / 8)), 256, 0, (cudaStream_t)stream>>>((const bf16*)dy, (bf16*)z, N, P, Q,
                                                                                           H, W, C);
   B2_LAUNCH_CHECK("dilate2_kernel");
+  return 0;
+}
+
+// wk / wt may be NULL (only the other layout is written); see the kernel
+B2_API int b2_conv_weight_layouts(const float* w, void* wk, void* wt, int Cout, int Cin, int R, int S, void* stream) {
+  B2_ARG_CHECK(w && (wk || wt) && Cout > 0 && Cin > 0 && R > 0 && S > 0, "b2_conv_weight_layouts: bad arguments");
+  conv_weight_layouts_kernel<<<ew_blocks((long)Cout * Cin * R * S), 256, 0, (cudaStream_t)stream>>>(w, (bf16*)wk, (bf16*)wt, Cout,
+                                                                                                   Cin, R, S);
+  B2_LAUNCH_CHECK("conv_weight_layouts_kernel");
   return 0;
 }
 
