@@ -162,7 +162,9 @@ int b2_transpose_cast_f32_bf16(const float* src, long ld_src, void* dst, long ld
                                void* stream);
 /* nn.Dropout(p) in train mode (nb:163, models.py:153,182): y = x*keep/(1-p) with a counter-hash
  * mask; calling it again with the same seed on dy replays the mask for the backward pass. */
-int b2_dropout_f32(const float* x, float* y, long n, float p, unsigned long long seed, void* stream);
+int b2_dropout_f32(const float* x, float* y, long n, float p, unsigned long long seed, const unsigned long long* seed_offset,
+                   void* stream);   /* seed_offset (device, may be NULL) is added to seed inside the kernel: a launch captured in a
+                                       CUDA graph draws a new mask per replay when the caller bumps that counter */
 /* stand-alone activations (models_bidir.py:119-155 Adapt 's'/'g'/'r', F.silu head): kind 0 relu, 1 gelu (erf), 2 silu; x = the pre-activation */
 int b2_act_fwd_f32(const float* x, float* y, long n, int kind, void* stream);
 int b2_act_bwd_f32(const float* dy, const float* x, float* dx, long n, int kind, void* stream);
@@ -241,9 +243,10 @@ int b2_sc_act_pool_bwd_reduce(const void* raw, const void* dy, const float* scal
 int b2_sc_act_pool_bwd_apply(const void* raw, const void* dy, const float* scale, const float* shift, const float* mean,
                              const float* rstd, float* s1, float* s2, int train, void* dz, int N, int H, int W, int C, int pool,
                              void* stream);
-int b2_sc_nhwc_to_chw(const void* act, void* feat, int N, int HW, int C, float p_drop, unsigned long long seed, void* stream);
+int b2_sc_nhwc_to_chw(const void* act, void* feat, int N, int HW, int C, float p_drop, unsigned long long seed,
+                      const unsigned long long* seed_offset, void* stream);
 int b2_sc_chw_to_nhwc(const void* dfeat, int in_bf16, void* dact, int N, int HW, int C, float p_drop, unsigned long long seed,
-                      void* stream);
+                      const unsigned long long* seed_offset, void* stream);
 
 /* ---- persistent GRU layer (torch.nn.GRU semantics, gate order r,z,n; lrcn/backup_ucf50.py:126, medsos models.py:160-170)
  * G [B,T,3H] = x W_ih^T + b_ih (hoisted gate GEMM); Whh [3H,H]; bhh [3H] (b_hn stays inside the r product);

@@ -138,18 +138,18 @@ def test_sc_layout_change_round_trip_and_dropout_mask():
     N, HW, C = 5, 16 * 16, 64
     act = torch.randn(N, HW, C, device=DEV).to(torch.bfloat16)
     feat = torch.empty(N, C * HW, device=DEV, dtype=torch.bfloat16)
-    call("b2_sc_nhwc_to_chw", act.data_ptr(), feat.data_ptr(), N, HW, C, 0.0, 0, stream_ptr())
+    call("b2_sc_nhwc_to_chw", act.data_ptr(), feat.data_ptr(), N, HW, C, 0.0, 0, 0, stream_ptr())
     assert torch.equal(feat.reshape(N, C, HW), act.permute(0, 2, 1))                 # c*HW + p flatten (nb:186)
-    call("b2_sc_nhwc_to_chw", act.data_ptr(), feat.data_ptr(), N, HW, C, 0.5, 1234, stream_ptr())
+    call("b2_sc_nhwc_to_chw", act.data_ptr(), feat.data_ptr(), N, HW, C, 0.5, 1234, 0, stream_ptr())
     kept = feat != 0
     assert abs(kept.float().mean().item() - 0.5) < 0.02
     assert torch.allclose(feat[kept].float(), (act.permute(0, 2, 1).reshape(N, -1)[kept].float() * 2).to(torch.bfloat16).float())
     g = torch.ones(N, C * HW, device=DEV)
     back = torch.empty(N, HW, C, device=DEV, dtype=torch.bfloat16)
-    call("b2_sc_chw_to_nhwc", g.data_ptr(), 0, back.data_ptr(), N, HW, C, 0.5, 1234, stream_ptr())
+    call("b2_sc_chw_to_nhwc", g.data_ptr(), 0, back.data_ptr(), N, HW, C, 0.5, 1234, 0, stream_ptr())
     assert torch.equal(back.permute(0, 2, 1).reshape(N, -1) != 0, kept)               # the backward replays the same mask
     gb = torch.randn(N, C * HW, device=DEV).to(torch.bfloat16)
-    call("b2_sc_chw_to_nhwc", gb.data_ptr(), 1, back.data_ptr(), N, HW, C, 0.0, 0, stream_ptr())
+    call("b2_sc_chw_to_nhwc", gb.data_ptr(), 1, back.data_ptr(), N, HW, C, 0.0, 0, 0, stream_ptr())
     assert torch.equal(back.permute(0, 2, 1).reshape(N, -1), gb)
 
 

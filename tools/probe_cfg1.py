@@ -54,6 +54,12 @@ for B in (8, 64):
         r, ms = rate(step, B)
         gf = 5.0 * B / ms                      # 5.0 GFLOP per clip, train step
         print(f"cfg1 small-CNN LRCN 20x64x64 B={B} {prec}: {r:9.0f} clips/s ({ms:.3f} ms/step, {gf:.1f} TFLOP/s algorithmic)")
+        # the same step replayed from one CUDA graph (GraphedTrainStep): at B = 8 the eager step is bound by the host launch path
+        mg = vc.SmallCNNLRCN(50, 20, 32, (3, 64, 64), dropout=0.5, precision=prec).to(dev).train()
+        og = torch.optim.Adam(mg.parameters(), lr=1e-4, fused=True, capturable=True)
+        gstep = vc.GraphedTrainStep(mg, og, torch.nn.CrossEntropyLoss(), x, y)
+        rg, msg = rate(lambda: gstep(x, y), B)
+        print(f"      whole step as one CUDA-graph replay: {rg:9.0f} clips/s ({msg:.3f} ms/step)")
         if prec == "bf16":
             # forward only / forward + backward split
             with torch.no_grad():

@@ -13,7 +13,10 @@ def __getattr__(name):   # lazy: models/ops import torch + torchvision
     if name in ("load_reference_checkpoint", "convert_reference_module"):
         from . import checkpoint
         return getattr(checkpoint, name)
-    if name in ("ops", "models", "ingest", "backbone", "dp", "scan", "checkpoint"):
+    if name == "GraphedTrainStep":
+        from . import graph_step
+        return graph_step.GraphedTrainStep
+    if name in ("ops", "models", "ingest", "backbone", "dp", "scan", "checkpoint", "graph_step"):
         import importlib
         return importlib.import_module("." + name, __name__)
     raise AttributeError(name)

@@ -21,6 +21,7 @@ import torch
 
 from . import _lib
 from ._lib import call, ptr, stream_ptr
+from .ops import graph_epoch as _graph_epoch
 from .ops import (BF16, F32, GRAM_CHANNELS, conv1x1_gram_bnstats, conv2d_bn_nhwc, conv3x3_halo_bn, conv3x3_halo_supported, conv2d_nhwc, gemm_tn, pack_stem_weight,
                   scale_shift_apply, stem_conv)
 
@@ -93,6 +94,8 @@ class ResNetRunner:
         if convs is None:
             convs = self._convs = [(n, m) for n, m in self.net.named_modules() if isinstance(m, torch.nn.Conv2d)]
         key = tuple((m.weight.data_ptr(), m.weight._version) for _, m in convs)
+        if any(m.weight.requires_grad for _, m in convs):      # (a replayed train-step graph updates weights without version bumps)
+            key += (_graph_epoch(),)
         if self._wkey != key:
             cache = {}
             for n, m in convs:
@@ -116,6 +119,8 @@ class ResNetRunner:
         pass reads a static copy of x and writes static activations; the returned features live in one of 4 rotating
         buffers (valid until the 4th following call)."""
         _lib.require_device()
+        if torch.cuda.is_current_stream_capturing():       # inside a captured train step the pass is part of THAT graph
+            return self(x, training)
         self._weights()
         key = (tuple(x.shape), x.dtype, x.device.index, bool(training), self._wkey, self.fuse_bn, self.stem_impl)
         entry = self._graphs.get(key)

@@ -873,7 +873,9 @@ __device__ __forceinline__ uint32_t sc_mix32(uint64_t z) {          // same gene
 // flat output index, replayed by the backward).  CTA = one image; a 32 x 33 shared-memory tile transposes.
 __global__ void __launch_bounds__(256)
 sc_nhwc_to_chw_kernel(const bf16* __restrict__ act, bf16* __restrict__ feat, int HW, int C, float p_drop,
-                      unsigned long long seed) {
+                      unsigned long long seed,
+                      const unsigned long long* __restrict__ seed_offset) {
+  if (seed_offset != nullptr) seed += *seed_offset;
   __shared__ float tile[32][33];
   const long n = blockIdx.y;
   const int p0 = blockIdx.x * 32;
@@ -905,7 +907,9 @@ __device__ __forceinline__ float ld_as_float(const bf16* p) { return __bfloat162
 template <typename InT>
 __global__ void __launch_bounds__(256)
 sc_chw_to_nhwc_kernel(const InT* __restrict__ dfeat, bf16* __restrict__ dact, int HW, int C, float p_drop,
-                      unsigned long long seed) {
+                      unsigned long long seed,
+                      const unsigned long long* __restrict__ seed_offset) {
+  if (seed_offset != nullptr) seed += *seed_offset;
   __shared__ float tile[32][33];
   const long n = blockIdx.y;
   const int p0 = blockIdx.x * 32;
@@ -1235,25 +1239,26 @@ B2_API int b2_sc_act_pool_bwd_apply(const void* raw, const void* dy, const float
 }
 
 // feat [N][C*HW] bf16 (channel-major flatten, nb:186) = dropout(act [N][HW][C] bf16) ; p = 0: plain layout change
-B2_API int b2_sc_nhwc_to_chw(const void* act, void* feat, int N, int HW, int C, float p_drop, unsigned long long seed, void* stream) {
+B2_API int b2_sc_nhwc_to_chw(const void* act, void* feat, int N, int HW, int C, float p_drop, unsigned long long seed,
+                             const unsigned long long* seed_offset, void* stream) {
   B2_ARG_CHECK(act && feat && N > 0 && HW > 0 && C > 0 && N <= 65535, "b2_sc_nhwc_to_chw: null pointer or bad shape");
   B2_ARG_CHECK(p_drop >= 0.f && p_drop < 1.f, "b2_sc_nhwc_to_chw: p must be in [0,1)");
-  sc_nhwc_to_chw_kernel<<<dim3((HW + 31) / 32, N), 256, 0, (cudaStream_t)stream>>>((const bf16*)act, (bf16*)feat, HW, C, p_drop, seed);
+  sc_nhwc_to_chw_kernel<<<dim3((HW + 31) / 32, N), 256, 0, (cudaStream_t)stream>>>((const bf16*)act, (bf16*)feat, HW, C, p_drop, seed, seed_offset);
   B2_LAUNCH_CHECK("sc_nhwc_to_chw_kernel");
   return 0;
 }
 
 // dact [N][HW][C] bf16 = dropout'(dfeat [N][C*HW] fp32 or bf16) with the mask of the forward call (same seed)
 B2_API int b2_sc_chw_to_nhwc(const void* dfeat, int in_bf16, void* dact, int N, int HW, int C, float p_drop,
-                             unsigned long long seed, void* stream) {
+                             unsigned long long seed, const unsigned long long* seed_offset, void* stream) {
   B2_ARG_CHECK(dfeat && dact && N > 0 && HW > 0 && C > 0 && N <= 65535, "b2_sc_chw_to_nhwc: null pointer or bad shape");
   B2_ARG_CHECK(p_drop >= 0.f && p_drop < 1.f, "b2_sc_chw_to_nhwc: p must be in [0,1)");
   if (in_bf16)
     sc_chw_to_nhwc_kernel<bf16><<<dim3((HW + 31) / 32, N), 256, 0, (cudaStream_t)stream>>>((const bf16*)dfeat, (bf16*)dact, HW, C,
-                                                                                          p_drop, seed);
+                                                                                          p_drop, seed, seed_offset);
   else
     sc_chw_to_nhwc_kernel<float><<<dim3((HW + 31) / 32, N), 256, 0, (cudaStream_t)stream>>>((const float*)dfeat, (bf16*)dact, HW, C,
-                                                                                           p_drop, seed);
+                                                                                           p_drop, seed, seed_offset);
   B2_LAUNCH_CHECK("sc_chw_to_nhwc_kernel");
   return 0;
 }

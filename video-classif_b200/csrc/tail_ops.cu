@@ -325,7 +325,9 @@ __device__ __forceinline__ uint32_t mix32(uint64_t z) {
   return (uint32_t)((z ^ (z >> 31)) >> 32);
 }
 __global__ void __launch_bounds__(256)
-dropout_kernel(const float* __restrict__ x, float* __restrict__ y, long n, float p, unsigned long long seed) {
+dropout_kernel(const float* __restrict__ x, float* __restrict__ y, long n, float p, unsigned long long seed,
+               const unsigned long long* __restrict__ seed_offset) {
+  if (seed_offset != nullptr) seed += *seed_offset;      // device-side step counter: a captured launch draws a new mask per replay
   const float inv_keep = 1.f / (1.f - p);
   const uint32_t thresh = (uint32_t)((double)p * 4294967296.0);
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
@@ -363,12 +365,13 @@ B2_API int b2_transpose_bf16(const void* src, long ld_src, void* dst, long ld_ds
   return 0;
 }
 
-B2_API int b2_dropout_f32(const float* x, float* y, long n, float p, unsigned long long seed, void* stream) {
+B2_API int b2_dropout_f32(const float* x, float* y, long n, float p, unsigned long long seed,
+                          const unsigned long long* seed_offset, void* stream) {
   B2_ARG_CHECK(x && y && n > 0, "b2_dropout_f32: null pointer or empty");
   B2_ARG_CHECK(p >= 0.f && p < 1.f, "b2_dropout_f32: p must be in [0,1)");
   long blocks = (n + 255) / 256;
   const long cap = (long)b2_num_sms() * 8;
-  dropout_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(x, y, n, p, seed);
+  dropout_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(x, y, n, p, seed, seed_offset);
   B2_LAUNCH_CHECK("dropout_kernel");
   return 0;
 }

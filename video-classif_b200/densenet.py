@@ -16,6 +16,7 @@ import torch
 
 from . import _lib
 from ._lib import call, ptr, stream_ptr
+from .ops import graph_epoch as _graph_epoch
 from .ops import BF16, F32, conv2d_nhwc, gemm_tn, pack_stem_weight, scale_shift_apply, stem_conv
 
 SUPPORTED = ("densenet121", "densenet169", "densenet201")
@@ -44,6 +45,8 @@ class DenseNetRunner:
         if convs is None:
             convs = self._convs = [(n, m) for n, m in self.net.named_modules() if isinstance(m, torch.nn.Conv2d)]
         key = tuple((m.weight.data_ptr(), m.weight._version) for _, m in convs)
+        if any(m.weight.requires_grad for _, m in convs):      # (a replayed train-step graph updates weights without version bumps)
+            key += (_graph_epoch(),)
         if self._wkey != key:
             cache = {}
             for n, m in convs:

@@ -17,6 +17,7 @@ import torch
 
 from . import _lib
 from ._lib import call, ptr, stream_ptr
+from .ops import graph_epoch as _graph_epoch
 from .ops import BF16, F32, gemm_tn, scale_shift_apply
 
 SUPPORTED = ("mobilenet_v2",)
@@ -44,6 +45,8 @@ class MobileNetRunner:
         if convs is None:
             convs = self._convs = [(n, m) for n, m in self.net.named_modules() if isinstance(m, torch.nn.Conv2d)]
         key = tuple((m.weight.data_ptr(), m.weight._version) for _, m in convs)
+        if any(m.weight.requires_grad for _, m in convs):      # (a replayed train-step graph updates weights without version bumps)
+            key += (_graph_epoch(),)
         if self._wkey != key:
             cache = {}
             for n, m in convs:

@@ -200,9 +200,10 @@ class _BackboneLRCN(nn.Module):
             return self._features(x)
         if not isinstance(features, _FeatureHandle) or features.shape != tuple(x.shape):
             raise ValueError("features= expects the handle encode_async() returned for these clips")
-        cur = torch.cuda.current_stream(x.device)
-        cur.wait_event(features.event)
-        features.tensor.record_stream(cur)
+        if features.event is not None:          # (None: a static feature buffer of a captured train step, already ordered)
+            cur = torch.cuda.current_stream(x.device)
+            cur.wait_event(features.event)
+            features.tensor.record_stream(cur)
         return features.tensor
 
     def __getstate__(self):                 # torch.save(model) (train_eval.py:53) must keep working

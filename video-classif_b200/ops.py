@@ -210,6 +210,33 @@ def cast_bf16(x):
 
 _weight_cache = {}      # id(parameter) -> (weakref, {kind: (data_ptr, _version, bf16 copy)}); entries die with their parameter
 
+# A replayed CUDA graph updates parameters WITHOUT bumping their autograd version counters, so everything that caches a
+# derived copy of a trainable weight also keys on this epoch; graph_step.GraphedTrainStep bumps it after every replay.
+_graph_epoch = [0]
+# Device-side counter added to every dropout seed inside the kernels (None: eager mode, the host-side counter alone varies the
+# masks).  A captured launch has its scalar seed baked in; with this pointer set during capture it draws a new mask per replay.
+_seed_offset = [None]
+
+
+def graph_epoch():
+    return _graph_epoch[0]
+
+
+def bump_graph_epoch():
+    _graph_epoch[0] += 1
+
+
+def set_seed_offset(t):
+    """t: a 1-element int64 CUDA tensor (or None).  Returns the previous value."""
+    prev = _seed_offset[0]
+    _seed_offset[0] = t
+    return prev
+
+
+def _seed_ptr():
+    t = _seed_offset[0]
+    return 0 if t is None else t.data_ptr()
+
 
 def _cached_weight(w, kind):
     """bf16 ("cast") or transposed bf16 ("tcast") copy of a weight, reused while the parameter is unchanged (same storage,
@@ -223,9 +250,10 @@ def _cached_weight(w, kind):
         ent = _weight_cache[key] = (weakref.ref(w, lambda _r, k=key: _weight_cache.pop(k, None)), {})
     slot = ent[1]
     hit = slot.get(kind)
-    if hit is None or hit[0] != w.data_ptr() or hit[1] != w._version:
+    ver = (w._version, _graph_epoch[0] if w.requires_grad else 0)
+    if hit is None or hit[0] != w.data_ptr() or hit[1] != ver:
         copy = cast_bf16(w.detach()) if kind == "cast" else transpose_cast_bf16(w.detach())
-        hit = slot[kind] = (w.data_ptr(), w._version, copy)
+        hit = slot[kind] = (w.data_ptr(), ver, copy)
     return hit[2]
 
 
@@ -615,7 +643,7 @@ class DropoutFn(torch.autograd.Function):
         _chk(x)
         xc = x.contiguous()
         y = torch.empty_like(xc)
-        call("b2_dropout_f32", xc.data_ptr(), y.data_ptr(), xc.numel(), float(p), int(seed), stream_ptr())
+        call("b2_dropout_f32", xc.data_ptr(), y.data_ptr(), xc.numel(), float(p), int(seed), _seed_ptr(), stream_ptr())
         ctx.p, ctx.seed = p, seed
         return y
 
@@ -623,7 +651,7 @@ class DropoutFn(torch.autograd.Function):
     def backward(ctx, dy):
         dc = dy.contiguous()
         dx = torch.empty_like(dc)
-        call("b2_dropout_f32", dc.data_ptr(), dx.data_ptr(), dc.numel(), float(ctx.p), int(ctx.seed), stream_ptr())
+        call("b2_dropout_f32", dc.data_ptr(), dx.data_ptr(), dc.numel(), float(ctx.p), int(ctx.seed), _seed_ptr(), stream_ptr())
         return dx, None, None
 
 
@@ -1058,7 +1086,7 @@ class SmallCNNTrunkFn(torch.autograd.Function):
         a3 = act(raw3, 2, 2)
         HW = (H // 4) * (W // 4)
         feat = torch.empty((N, 64 * HW), device=dev, dtype=BF16)
-        call("b2_sc_nhwc_to_chw", a3.data_ptr(), feat.data_ptr(), N, HW, 64, float(p_drop), int(seed), st)
+        call("b2_sc_nhwc_to_chw", a3.data_ptr(), feat.data_ptr(), N, HW, 64, float(p_drop), int(seed), _seed_ptr(), st)
         ctx.save_for_backward(x16, raw1, a1, raw2, a2, raw3, coef, w2, w3)
         ctx.cfg = (bool(train), float(p_drop), int(seed), b1 is not None, b2 is not None, b3 is not None)
         return feat
@@ -1093,7 +1121,7 @@ class SmallCNNTrunkFn(torch.autograd.Function):
             return dw.permute(0, 3, 1, 2)                                # torch layout [Cout,Cin,3,3] (a view)
 
         d3 = torch.empty((N, H // 4, W // 4, 64), device=dev, dtype=BF16)
-        call("b2_sc_chw_to_nhwc", dfeat.data_ptr(), int(dfeat.dtype == BF16), d3.data_ptr(), N, HW, 64, p_drop, seed, st)
+        call("b2_sc_chw_to_nhwc", dfeat.data_ptr(), int(dfeat.dtype == BF16), d3.data_ptr(), N, HW, 64, p_drop, seed, _seed_ptr(), st)
         dz3 = bn_bwd(raw3, d3, 2, 2)
         dw3 = wgrad(a2, dz3, 32, 64)
         da2 = _sc_conv(dz3, _sc_kernel_weight_dgrad(w3), 32)
