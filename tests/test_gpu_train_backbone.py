@@ -125,6 +125,30 @@ def test_stem_node_vs_torch():
     assert rel(bn.weight.grad, bn_ref.weight.grad) < 1e-2 and rel(bn.bias.grad, bn_ref.bias.grad) < 1e-2
 
 
+@pytest.mark.parametrize("N,H,W", [(3, 20, 16), (2, 7, 9), (1, 56, 56), (2, 5, 4)])
+def test_maxpool_relu_backward_vs_torch_with_ties(N, H, W):
+    """Backward of the stem tail (b2_maxpool_relu_bwd_nhwc) vs torch autograd through max_pool2d(relu(raw * scale + shift), 3, 2, 1).
+    The raw values take few distinct levels so that every window has TIES (first-maximal-element rule), half of the scales are
+    negative (argmax of the raw values flips to argmin), odd sizes leave ragged windows."""
+    from video_classif_b200._lib import call, stream_ptr
+    C = 64
+    g = torch.Generator().manual_seed(N * H + W)
+    raw = (torch.randint(-3, 4, (N, H, W, C), generator=g).float() * 0.5).to(BF16).to(DEV)
+    scale = (torch.rand(C, generator=g) + 0.5) * torch.where(torch.rand(C, generator=g) > 0.5, 1.0, -1.0)
+    shift = torch.randn(C, generator=g) * 0.3
+    P, Q = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+    dpool = torch.randn(N, P, Q, C, generator=g).to(BF16).to(DEV)
+    scale, shift = scale.to(DEV), shift.to(DEV)
+    dbn = torch.zeros((N, H, W, C), device=DEV, dtype=torch.float32)
+    call("b2_maxpool_relu_bwd_nhwc", raw.data_ptr(), scale.data_ptr(), shift.data_ptr(), dpool.data_ptr(), dbn.data_ptr(),
+         N, H, W, P, Q, C, stream_ptr())
+    a = (raw.float() * scale + shift).permute(0, 3, 1, 2).detach().requires_grad_(True)
+    F.max_pool2d(torch.relu(a), 3, 2, 1).backward(dpool.float().permute(0, 3, 1, 2))
+    # torch routes ties among equal ACTIVATIONS; ours among equal raw values: identical whenever scale != 0 (monotone map),
+    # except inside the ReLU's flat region, where the gradient is masked to zero by both
+    assert rel(dbn.permute(0, 3, 1, 2), a.grad) < 1e-5
+
+
 def _teacher_forced_reference(net, x, rec, G, start):
     """torch autograd over torchvision's graph where every node's VALUE is replaced by the activation the B200 path
     produced (rec, execution order) while its local Jacobian stays torch's: parameter gradients then differ from ours by
