@@ -6,6 +6,7 @@ every arithmetic step of the forward and backward pass is a b2_* kernel.  No CPU
 entry points raise B200LrcnError when the tensors are not on an sm_100 device."""
 from __future__ import annotations
 
+import os
 import weakref
 
 import torch
@@ -277,6 +278,26 @@ def transpose_bf16(x):
     return buf[:, :R]
 
 
+_WGRAD_LINEAR = os.environ.get("B2_LINEAR_WGRAD", "1") == "1"
+
+
+def linear_wgrad_tc(x2, dy2):
+    """dW [N, K] fp32 = dy2^T @ x2 for x2 [M, K], dy2 [M, N] (nn.Linear / the hoisted RNN gate GEMM) on the tcgen05
+    weight-gradient kernel: both operands are read MN-major straight from their row-major tensors (pixels = rows of the
+    batch are the reduction), so neither transposed copy of the old gemm_tn form is materialised.  Needs K % 8 == N % 8 == 0."""
+    M, K = x2.shape
+    N = dy2.shape[1]
+    xa = x2 if x2.dtype == BF16 else cast_bf16(x2)
+    da = dy2 if dy2.dtype == BF16 else cast_bf16(dy2)
+    dw = torch.zeros((N, K), device=x2.device, dtype=F32)
+    call("b2_conv2d_wgrad_nhwc_bf16", xa.data_ptr(), M, 1, 1, K, da.data_ptr(), N, 1, 1, 1, 0, dw.data_ptr(), stream_ptr())
+    return dw
+
+
+def _wgrad_ok(x2, dy2):
+    return (_WGRAD_LINEAR and x2.shape[1] % 8 == 0 and dy2.shape[1] % 8 == 0 and x2.is_contiguous() and dy2.is_contiguous())
+
+
 def _kmajor_bf16(x):
     """[R,C] fp32 or bf16 -> bf16 [C,R] (transposed copy) for gemm_tn."""
     return transpose_bf16(x) if x.dtype == BF16 else transpose_cast_bf16(x)
@@ -546,10 +567,13 @@ class LinearFn(torch.autograd.Function):
                 dx = sgemm(dy2, weight)
             dx = dx.reshape(ctx.x_shape)
         if ctx.needs_input_grad[1]:
-            xf = x2 if x2.dtype == F32 else x2.float()
-            if big:
+            if big and _wgrad_ok(x2, dy2):
+                dw = linear_wgrad_tc(x2, dy2)
+            elif big:
+                xf = x2 if x2.dtype == F32 else x2.float()
                 dw = gemm_tn(transpose_cast_bf16(dy2), transpose_cast_bf16(xf), out_dtype=F32)  # [N,M]x[K,M]^T
             else:
+                xf = x2 if x2.dtype == F32 else x2.float()
                 dw = sgemm(dy2, xf, trans_a=True)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = colsum(dy2)
@@ -715,7 +739,9 @@ class LSTMLayerFn(torch.autograd.Function):
         H4 = 4 * H
         dG_all = torch.empty((B * T, dirs * H4), device=dout.device, dtype=F32)   # [dG_fwd | dG_bwd]
         xf = x2 if (x2.dtype == F32 or big) else x2.float()     # big: the tcgen05 GEMM takes the bf16 operand as is
-        xt = _kmajor_bf16(xf) if big else None                  # one transposed copy of x for all directions
+        use_wg = big and _WGRAD_LINEAR and In % 8 == 0 and xf.is_contiguous()   # MN-major weight-gradient kernel: no transposes
+        xt = _kmajor_bf16(xf) if (big and not use_wg) else None  # (old form) one transposed copy of x for all directions
+        xa = (xf if xf.dtype == BF16 else cast_bf16(xf)) if use_wg else None
         for d in range(dirs):
             w_ih, w_hh, b_ih, b_hh = params[4 * d:4 * d + 4]
             gates, cst = saved[2 * d:2 * d + 2]
@@ -725,7 +751,9 @@ class LSTMLayerFn(torch.autograd.Function):
             oo = out[:, :, d * H:]
             call("b2_lstm_seq_bwd", do.data_ptr(), dirs * H, oo.data_ptr(), dirs * H, gates.data_ptr(), cst.data_ptr(),
                  w_hh.data_ptr(), dG.data_ptr(), dirs * H4, dWhh.data_ptr(), B, T, H, int(d == 1), stream_ptr())
-            if big:
+            if use_wg:
+                dWih = linear_wgrad_tc(xa, dG if dG.is_contiguous() else dG.contiguous())
+            elif big:
                 dWih = gemm_tn(transpose_cast_bf16(dG), xt, out_dtype=F32)
             else:
                 dWih = sgemm(dG, xf, trans_a=True)
@@ -784,7 +812,9 @@ class GRULayerFn(torch.autograd.Function):
         big = ctx.bf16 and B * T * H3 * In >= TC_MIN_MACS and H % 8 == 0
         dG_all = torch.empty((B * T, dirs * H3), device=dout.device, dtype=F32)
         xf = x2 if (x2.dtype == F32 or big) else x2.float()
-        xt = _kmajor_bf16(xf) if big else None
+        use_wg = big and _WGRAD_LINEAR and In % 8 == 0 and xf.is_contiguous()
+        xt = _kmajor_bf16(xf) if (big and not use_wg) else None
+        xa = (xf if xf.dtype == BF16 else cast_bf16(xf)) if use_wg else None
         grads = []
         for d in range(dirs):
             w_ih, w_hh, b_ih, b_hh = params[4 * d:4 * d + 4]
@@ -794,7 +824,9 @@ class GRULayerFn(torch.autograd.Function):
             call("b2_gru_seq_bwd", dout[:, :, d * H:].data_ptr(), dirs * H, out[:, :, d * H:].data_ptr(), dirs * H,
                  saved[d].data_ptr(), w_hh.data_ptr(), dG.data_ptr(), dirs * H3, dWhh.data_ptr(), dbhh.data_ptr(), B, T, H,
                  int(d == 1), stream_ptr())
-            if big:
+            if use_wg:
+                dWih = linear_wgrad_tc(xa, dG if dG.is_contiguous() else dG.contiguous())
+            elif big:
                 dWih = gemm_tn(transpose_cast_bf16(dG), xt, out_dtype=F32)
             else:
                 dWih = sgemm(dG, xf, trans_a=True)
