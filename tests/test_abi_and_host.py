@@ -36,6 +36,9 @@ def test_no_gpu_means_loud_failure_not_fallback():
     m = vc.SmallCNNLRCN(5, 2, 4, (3, 8, 8))
     with pytest.raises(vc.B200LrcnError):
         m(torch.rand(1, 2, 3, 8, 8))
+    with pytest.raises(vc.B200LrcnError):         # the captured train step has no CPU form either
+        vc.GraphedTrainStep(m, torch.optim.SGD(m.parameters(), lr=0.1), torch.nn.CrossEntropyLoss(),
+                            torch.rand(1, 2, 3, 8, 8), torch.zeros(1, dtype=torch.long))
 
 
 def test_product_never_imports_the_oracle():

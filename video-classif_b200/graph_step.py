@@ -19,7 +19,9 @@ What makes a replay equal to an eager step:
     call that follows (model.eval()(x), a checkpoint conversion) re-derives what it needs.
 The warm-up steps that PyTorch's capture recipe needs run on the example batch and are UNDONE before the capture: parameters,
 buffers and optimizer state are restored in place, so constructing the object does not train the model.
-Shapes are fixed at construction; a batch of another shape needs its own GraphedTrainStep (or the eager path)."""
+Shapes are fixed at construction; a batch of another shape needs its own GraphedTrainStep (or the eager path).
+Single process: the data-parallel gradient buckets (dp.GradBucketAllReduce) launch their collectives from autograd hooks on a
+side stream and are not captured -- use the eager step under DP."""
 from __future__ import annotations
 
 import copy
