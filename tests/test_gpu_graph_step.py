@@ -113,3 +113,32 @@ def test_graphed_step_frozen_backbone_lrcn_and_optimizer_check():
     for a, b in zip(got, ref):
         assert abs(a - b) < 2e-2 * max(1.0, abs(b)), (got, ref)
     assert torch.equal(m1.cnn_backbone.bn1.num_batches_tracked, m2.cnn_backbone.bn1.num_batches_tracked)
+
+
+def test_ingest_straight_into_the_encoder_graph_input():
+    """model.encoder_input_buffer(): the static input of the encoder's CUDA graph; ingest_batch(..., out=buf) followed by
+    encode_async(buf) must give the features of the ordinary path (separate ingest result copied into the graph)."""
+    import video_classif_b200 as vc
+    from video_classif_b200.ingest import ingest_batch
+    torch.manual_seed(4)
+    m = vc.LRCN(4, 3, 16, 8, cnn_backbone="resnet18", rnn_layers=1, dropout=0.0).to(DEV).eval()
+    m.enable_encoder_graph()
+    g = torch.Generator().manual_seed(9)
+    u8 = [torch.randint(0, 256, (2, 3, 64, 64, 3), generator=g, dtype=torch.uint8).to(DEV) for _ in range(3)]
+    shape = (2, 3, 3, 64, 64)
+    assert m.encoder_input_buffer(shape) is None                       # nothing captured yet
+    with torch.no_grad():
+        ref = [m(ingest_batch(u, 64, 64)).clone() for u in u8]         # ordinary path (captures the graph on first use)
+        buf = m.encoder_input_buffer(shape)
+        assert buf is not None and tuple(buf.shape) == shape
+        for u, r in zip(u8, ref):
+            side = m.side_stream(DEV)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                x = ingest_batch(u, 64, 64, out=buf)
+            assert x.data_ptr() == buf.data_ptr()
+            h = m.encode_async(x)
+            out = m(x, features=h)
+            assert torch.allclose(out, r, atol=1e-4, rtol=1e-4)
+    with pytest.raises(ValueError):
+        ingest_batch(u8[0], 64, 64, out=torch.empty(5, device=DEV))

@@ -154,6 +154,15 @@ class ResNetRunner:
         out.copy_(static_feat)
         return out
 
+    def static_input(self, shape, dtype, device, training: bool):
+        """The static input tensor of the graph captured for this frame-batch shape / mode (None before its first replay):
+        a producer that writes its frames THERE (ingest_batch(..., out=...)) saves the per-step copy into the graph."""
+        for key, entry in self._graphs.items():
+            if key[0] == tuple(shape) and key[1] == dtype and key[2] == torch.device(device).index and key[3] == bool(training) \
+                    and key[4] == self._wkey:
+                return entry[1]
+        return None
+
     def _bn(self, x, bn, stats, count, train, relu=True, res_mode=0, res=None, rbn=None, rstats=None):
         rows = x.numel() // x.shape[-1]
         C = x.shape[-1]

@@ -29,9 +29,10 @@ def ingest_clip(frames_u8: torch.Tensor, sequence_length: int, height: int, widt
 
 
 def ingest_batch(clips_u8: torch.Tensor, height: int, width: int, out_dtype=torch.float32, swap_rb: bool = True,
-                 divisor: float = 255.0) -> torch.Tensor:
-    """Already-sampled uint8 clips [B,T,H0,W0,3] -> [B,T,3,height,width] in one launch."""
+                 divisor: float = 255.0, out=None) -> torch.Tensor:
+    """Already-sampled uint8 clips [B,T,H0,W0,3] -> [B,T,3,height,width] in one launch.  out: write into this tensor (e.g.
+    model.encoder_input_buffer(...): the encoder graph's static input, no copy between ingest and the encoder pass)."""
     B, T = clips_u8.shape[:2]
     out = ops.ingest_u8(clips_u8.reshape(B * T, *clips_u8.shape[2:]), height, width, out_dtype=out_dtype,
-                        swap_rb=swap_rb, divisor=divisor)
+                        swap_rb=swap_rb, divisor=divisor, out=out)
     return out.reshape(B, T, 3, height, width)

@@ -164,6 +164,17 @@ class _BackboneLRCN(nn.Module):
         self._runner.use_graph = bool(enabled)
         return self
 
+    def encoder_input_buffer(self, clip_shape, dtype=torch.float32, device=None):
+        """[B,T,3,H,W] view of the static input of the encoder's CUDA graph for clips of this shape in the current
+        train / eval mode, or None (graph replay not enabled / not captured yet / trainable encoder).  Writing the clips
+        there -- ingest_batch(u8, H, W, out=buf) on the stream the encoder runs on -- removes the copy into the graph."""
+        if not (self._runner.use_graph and self._frozen_encoder()):
+            return None
+        B, T, C, H, W = clip_shape
+        dev = device if device is not None else next(self.parameters()).device
+        buf = self._runner.static_input((B * T, C, H, W), dtype, dev, self.training)
+        return None if buf is None else buf.view(B, T, C, H, W)
+
     # ---- optional encoder prefetch (frozen backbone only) ------------------------------------------------
     # The frozen frame encoder does not depend on the optimizer update, so the encoder pass of batch i+1 can run
     # on a second stream while the (latency-bound, low-occupancy) trainable tail of batch i runs its forward,

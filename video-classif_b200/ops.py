@@ -303,8 +303,9 @@ def _kmajor_bf16(x):
     return transpose_bf16(x) if x.dtype == BF16 else transpose_cast_bf16(x)
 
 
-def ingest_u8(frames_u8, out_h, out_w, frame_index=None, out_dtype=F32, swap_rb=True, divisor=255.0):
-    """uint8 [F,H0,W0,3] device frames -> [n_out,3,out_h,out_w]; see b2_ingest_u8."""
+def ingest_u8(frames_u8, out_h, out_w, frame_index=None, out_dtype=F32, swap_rb=True, divisor=255.0, out=None):
+    """uint8 [F,H0,W0,3] device frames -> [n_out,3,out_h,out_w]; see b2_ingest_u8.  out: a preallocated contiguous result
+    (e.g. the static input buffer of the encoder's CUDA graph, so that no copy sits between ingest and the encoder pass)."""
     _chk(frames_u8)
     assert frames_u8.dtype == torch.uint8 and frames_u8.dim() == 4 and frames_u8.shape[-1] == 3
     frames_u8 = frames_u8.contiguous()
@@ -312,7 +313,14 @@ def ingest_u8(frames_u8, out_h, out_w, frame_index=None, out_dtype=F32, swap_rb=
     n_out = Fr if frame_index is None else frame_index.numel()
     if frame_index is not None:
         assert frame_index.dtype == torch.int32 and frame_index.is_cuda
-    out = torch.empty((n_out, 3, out_h, out_w), device=frames_u8.device, dtype=out_dtype)
+    if out is None:
+        out = torch.empty((n_out, 3, out_h, out_w), device=frames_u8.device, dtype=out_dtype)
+    else:
+        if (out.numel() != n_out * 3 * out_h * out_w or not out.is_contiguous() or out.device != frames_u8.device
+                or out.dtype not in (F32, BF16)):
+            raise ValueError("ingest_u8: out must be a contiguous fp32 / bf16 tensor of n_out * 3 * out_h * out_w elements on the frames' device")
+        out_dtype = out.dtype
+        out = out.view(n_out, 3, out_h, out_w)
     call("b2_ingest_u8", frames_u8.data_ptr(), Fr, H0, W0, H0 * W0 * 3, ptr(frame_index), n_out, out.data_ptr(), out_h,
          out_w, int(out_dtype == BF16), int(swap_rb), float(divisor), stream_ptr())
     return out
