@@ -142,3 +142,28 @@ def test_ingest_straight_into_the_encoder_graph_input():
             assert torch.allclose(out, r, atol=1e-4, rtol=1e-4)
     with pytest.raises(ValueError):
         ingest_batch(u8[0], 64, 64, out=torch.empty(5, device=DEV))
+
+
+def test_graphed_step_trainable_backbone_crime_lrcn():
+    """crime LRCN with the WHOLE ResNet-18 trainable (lrcn.py:181-305, CONF_FINETUNE = True): forward, the backbone's backward
+    kernels (weight / data gradients, BatchNorm backward, the stem) and the optimizer step replayed from one graph vs the eager
+    loop, three steps with SGD (update proportional to the gradient); BatchNorm running statistics advance identically."""
+    import video_classif_b200 as vc
+    torch.manual_seed(6)
+    m1 = vc.CrimeLRCN(3, 2, 8, 16, cnn_backbone="resnet18", finetune=True, rnn_layers=1, classif_mode="multiple_binary").to(DEV).train()
+    m2 = copy.deepcopy(m1)
+    crit = torch.nn.BCEWithLogitsLoss()
+    g = torch.Generator().manual_seed(11)
+    batches = [(torch.rand(4, 2, 3, 64, 64, generator=g).to(DEV), (torch.rand(4, 3, generator=g) > 0.5).float().to(DEV)) for _ in range(3)]
+    o1 = torch.optim.SGD(m1.parameters(), lr=1e-3, momentum=0.9)
+    o2 = torch.optim.SGD(m2.parameters(), lr=1e-3, momentum=0.9)
+    step = vc.GraphedTrainStep(m2, o2, crit, *batches[0])
+    ref = _eager(m1, o1, crit, batches)
+    got = [step(x, y).item() for x, y in batches]
+    for a, b in zip(got, ref):
+        assert abs(a - b) < 2e-2 * max(1.0, abs(b)), (got, ref)
+    sd1, sd2 = m1.state_dict(), m2.state_dict()
+    assert torch.equal(sd1["cnn_backbone.bn1.num_batches_tracked"], sd2["cnn_backbone.bn1.num_batches_tracked"])
+    for k in ("cnn_backbone.bn1.running_mean", "cnn_backbone.layer4.1.bn2.running_var", "cnn_backbone.conv1.weight", "fc.0.weight"):
+        d = (sd1[k] - sd2[k]).abs().max().item() / max(sd1[k].abs().max().item(), 1e-3)
+        assert d < 5e-2, (k, d)
