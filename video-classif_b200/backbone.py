@@ -22,7 +22,7 @@ import torch
 from . import _lib
 from ._lib import call, ptr, stream_ptr
 from .ops import graph_epoch as _graph_epoch
-from .ops import (BF16, F32, GRAM_CHANNELS, conv1x1_gram_bnstats, conv2d_bn_nhwc, conv3x3_halo_bn, conv3x3_halo_supported, conv2d_nhwc, gemm_tn, pack_stem_weight,
+from .ops import (BF16, F32, GRAM_CHANNELS, conv1x1_gram_bnstats, conv2d_bn_nhwc, conv3x3_halo_bn, conv3x3_halo_supported, conv2d_nhwc, gemm_tn, pack_stem_weight, stem_pack,
                   scale_shift_apply, stem_conv)
 
 SUPPORTED = ("resnet18", "resnet34", "resnet50", "resnet101", "resnet152")
@@ -128,7 +128,13 @@ class ResNetRunner:
             bufs = [b for b in self.net.buffers()]
             saved = [b.detach().clone() for b in bufs]          # the warm-up pass must not advance the running stats
             static_x = x.detach().clone()
-            self(static_x, training)                             # warm-up: function attributes, allocator pools
+            # ResNet direct stem: its operand packing (a pure re-layout of the frames) stays outside the graph and reads the
+            # caller's tensor directly, so no copy of the frames into a static buffer is needed per call
+            packs = (bool(getattr(self, "PACKED_STEM", False)) and self.stem_impl == "direct"
+                     and os.environ.get("B2_NO_PACKED_STEM") is None)
+            static_xp = stem_pack(static_x) if packs else None
+            kw = {"packed": static_xp} if packs else {}
+            self(static_x, training, **kw)                       # warm-up: function attributes, allocator pools
             for b, sv in zip(bufs, saved):
                 b.copy_(sv)
             torch.cuda.synchronize(x.device)
@@ -138,14 +144,16 @@ class ResNetRunner:
             # the small tail kernels of the previous batch fill the gaps of its partial waves
             prio = int(os.environ.get("B2_ENC_PRIORITY", "0"))
             with torch.cuda.graph(graph, stream=torch.cuda.Stream(device=x.device, priority=prio)):
-                static_feat = self(static_x, training)
+                static_feat = self(static_x, training, **kw)
             # results rotate through a small ring of persistent buffers: no per-call allocation (a tensor handed from
             # the encoder's stream to the consumer's stream every step made the caching allocator hold blocks back)
             ring = [torch.empty_like(static_feat) for _ in range(4)]
-            entry = [graph, static_x, static_feat, _lib.launch_count() - n0, ring, 0]
+            entry = [graph, static_x, static_feat, _lib.launch_count() - n0, ring, 0, static_xp]
             self._graphs[key] = entry
-        graph, static_x, static_feat, n_launch, ring, idx = entry
-        if x.data_ptr() != static_x.data_ptr():
+        graph, static_x, static_feat, n_launch, ring, idx, static_xp = entry
+        if static_xp is not None:
+            stem_pack(x, out=static_xp)                          # one kernel: caller's frames -> the graph's packed stem operand
+        elif x.data_ptr() != static_x.data_ptr():
             static_x.copy_(x)
         graph.replay()
         call("b2_add_launch_count", n_launch)
@@ -184,8 +192,11 @@ class ResNetRunner:
         call("b2_avgpool_nhwc", y.data_ptr(), feat.data_ptr(), 0, Nn, Hh * Ww, C, stream_ptr())
         return feat
 
-    def __call__(self, x, training: bool, return_stages: bool = False, stop_at=None):
+    PACKED_STEM = True      # graphed(): the stem's operand packing runs OUTSIDE the graph, straight from the caller's frames
+
+    def __call__(self, x, training: bool, return_stages: bool = False, stop_at=None, packed=None):
         """x: [N,3,H,W] fp32 or bf16 (NCHW, the reference's frame tensor) -> [N, feat] fp32.
+        packed: the frames already in the direct stem's packed layout (ops.stem_pack; x then only gives the shape).
         return_stages=True also returns the spatial means after the stem and each stage (tests).
         stop_at=(layer, block): return the NHWC bf16 activation entering that block (the frozen prefix of a partially
         trainable encoder, backbone_train.py)."""
@@ -243,7 +254,7 @@ class ResNetRunner:
         P, Q = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
         s_stem = stats_of(net.bn1)
         if self.stem_impl == "direct":
-            raw = stem_conv(x, w["conv1"], stats=s_stem)
+            raw = stem_conv(x, w["conv1"], stats=s_stem, xp=packed)
         else:                                   # patch-matrix path (kept for A/B parity tests)
             A = torch.empty((N * P * Q, STEM_KP), device=dev, dtype=BF16)
             call("b2_stem_im2col", x.data_ptr(), int(x.dtype == BF16), A.data_ptr(), N, H, W, STEM_KP, st)

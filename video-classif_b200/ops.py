@@ -155,17 +155,30 @@ def pack_stem_weight(w):
     return w4.reshape(64, 28, 8).permute(1, 0, 2).contiguous()
 
 
-def stem_conv(x, wk, stats=None):
-    """x [N,3,H,W] fp32/bf16 NCHW, wk = pack_stem_weight(conv1.weight) -> raw conv output [N,P,Q,64] bf16
-    (Conv2d 7x7 stride 2 pad 3) + optional per-channel sum / sum-of-squares."""
-    _chk(x, wk)
+def stem_pack(x, out=None):
+    """x [N,3,H,W] fp32/bf16 NCHW -> the packed bf16 operand of the direct stem conv (uint8 tensor of b2_stem_packed_bytes)."""
+    _chk(x)
     x = x.contiguous()
     N, C, H, W = x.shape
     assert C == 3 and x.dtype in (F32, BF16)
+    nbytes = _lib.lib().b2_stem_packed_bytes(N, H, W)
+    xp = out if out is not None else torch.empty(nbytes, device=x.device, dtype=torch.uint8)
+    assert xp.numel() == nbytes and xp.dtype == torch.uint8 and xp.is_contiguous()
+    call("b2_stem_pack", x.data_ptr(), int(x.dtype == BF16), xp.data_ptr(), N, H, W, stream_ptr())
+    return xp
+
+
+def stem_conv(x, wk, stats=None, xp=None):
+    """x [N,3,H,W] fp32/bf16 NCHW, wk = pack_stem_weight(conv1.weight) -> raw conv output [N,P,Q,64] bf16
+    (Conv2d 7x7 stride 2 pad 3) + optional per-channel sum / sum-of-squares.  xp: the frames already packed by stem_pack
+    (x is then read for its shape only)."""
+    _chk(wk)
+    N, C, H, W = x.shape
+    assert C == 3 and x.dtype in (F32, BF16)
     P, Q = (H - 1) // 2 + 1, (W - 1) // 2 + 1
-    xp = torch.empty(_lib.lib().b2_stem_packed_bytes(N, H, W), device=x.device, dtype=torch.uint8)
+    if xp is None:
+        xp = stem_pack(x)
     st = stream_ptr()
-    call("b2_stem_pack", x.data_ptr(), int(x.dtype == BF16), xp.data_ptr(), N, H, W, st)
     y = torch.empty((N, P, Q, 64), device=x.device, dtype=BF16)
     s1, s2 = stats if stats is not None else (None, None)
     call("b2_stem_conv_bf16", xp.data_ptr(), wk.data_ptr(), y.data_ptr(), N, H, W, ptr(s1), ptr(s2), st)
