@@ -74,8 +74,6 @@ def test_graphed_step_dropout_masks_change_and_eval_sees_current_weights():
     step = vc.GraphedTrainStep(m, opt, crit, x, y)
     l = [step(x, y).item() for _ in range(4)]
     assert len({round(v, 6) for v in l}) > 1, l
-    for g in opt.param_groups:
-        g["lr"] = torch.tensor(5e-2, device=DEV) if torch.is_tensor(g["lr"]) else 5e-2
     opt2 = torch.optim.Adam(m.parameters(), lr=5e-2, capturable=True)
     step2 = vc.GraphedTrainStep(m, opt2, crit, x, y)
     m.eval()
