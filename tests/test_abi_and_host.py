@@ -327,3 +327,21 @@ def test_variant_modules_convert_from_reference_layout():
                 assert getattr(m2, attr) == getattr(m, attr)
         if hasattr(m, "adapt") and hasattr(m.adapt, "mode"):
             assert m2.adapt.mode == m.adapt.mode
+
+
+def test_host_side_shape_contracts_need_no_gpu():
+    """Pure host functions of the C ABI that the Python layer uses to pick a kernel: which 3x3 shapes the halo-tile convs cover
+    (64 channels: resident weights, padded width <= 64; 128 channels: streamed weights, the halo stages must fit shared memory)
+    and when the selective-scan backward keeps its states on chip (no workspace)."""
+    import video_classif_b200 as vc
+    lib = vc._lib.lib()
+    sup = lib.b2_conv3x3_halo_supported
+    assert sup(1024, 14, 14, 128, 128) == 1 and sup(32, 28, 28, 128, 128) == 1 and sup(2, 4, 4, 128, 128) == 1
+    assert sup(8, 56, 56, 128, 128) == 0 and sup(2, 5, 60, 128, 128) == 0          # halo stages larger than shared memory
+    assert sup(1024, 28, 28, 64, 64) == 1 and sup(4, 62, 62, 64, 64) == 1 and sup(4, 63, 63, 64, 64) == 0
+    assert sup(4, 14, 14, 256, 256) == 0 and sup(4, 14, 14, 128, 64) == 0 and sup(0, 14, 14, 64, 64) == 0
+    ws = lib.b2_scan_bwd_workspace_floats
+    assert ws(8, 3136, 2048, 16, 256) == 0                                           # config 5: 256-step chunks stay on chip
+    assert ws(8, 3136, 2048, 16, 0) == 8 * 2048 * 3136 * 16                          # one 3136-step scan: workspace kernel
+    assert ws(2, 19, 64, 12, 0) == 2 * 64 * 19 * 16 and lib.b2_scan_padded_states(12) == 16   # padded state width
+    assert ws(2, 19, 96, 8, 0) == 2 * 96 * 19 * 8                                    # 96 channels are not a multiple of 512 / 8
